@@ -1,0 +1,675 @@
+// C-ABI entry points (include/mchrg_b200.h) and the device orchestration of
+// mchrg_model_type%solve (model/type.F90:151-292), get_charges (charge.f90:37-77) and the CLI
+// sequence (app/main.f90:114-118).
+//
+// How solve() is restated for the GPU (EEQ2019):
+//   reference (type.F90)                         here
+//   -------------------------------------------  ------------------------------------------------
+//   amat (N+1)^2 incl. constraint border         only the SPD Coulomb block J (padded to 128)
+//   sytrf: Bunch-Kaufman LDL^T of bordered amat   blocked Cholesky J = L L^T (DMMA trailing updates)
+//   sytrs / sytri+symv                            y = J^-1 x, z = J^-1 1, lambda = (1^T y - Q)/(1^T z),
+//                                                 q = y - lambda z   (Schur complement of the border)
+//   symv(0.5 J q - x), energy += q * (...)        (J q) re-evaluated from the pair formula (no J copy)
+//   dadr, dxdr (3 N (N+1) each), gemv x4          gradient = q * atrace - sum_k thalf_k q_k dcndr(:,:,k)
+//   dqdr = -(dadr - dxdr) * ainv(:, :N)  (gemm)   B = dadr - dxdr built once, X = B L^-T L^-1 (two
+//                                                 recursive right-side TRSMs), dqdr = -X + (B z) z^T / s
+#include <cmath>
+
+#include "dense.cuh"
+#include "eeq.cuh"
+#include "lattice.hpp"
+#include "param_tables.inc"
+
+using namespace mchrg;
+
+namespace mchrg {
+
+// ---------------------------------------------------------------------------------------------
+// small kernels of the solve tail
+// ---------------------------------------------------------------------------------------------
+
+// R(:,0) = x (zero padded), R(:,1) = 1 for atoms, 0 for padding
+__global__ void rhs_init_kernel(int nat, int64_t npad, const double* __restrict__ xvec, double* __restrict__ R) {
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= npad) return;
+   R[i] = (i < nat) ? xvec[i] : 0.0;
+   R[i + npad] = (i < nat) ? 1.0 : 0.0;
+}
+
+// Schur complement of the total-charge constraint: one CTA.
+// scal[0] = s = 1^T z, scal[1] = lambda; vrhs[0..nat-1] = q, vrhs[nat] = lambda
+__global__ void __launch_bounds__(1024) schur_charges_kernel(int nat, int64_t npad, const double* __restrict__ R,
+                                                             double charge, double* __restrict__ vrhs,
+                                                             double* __restrict__ qvec, double* __restrict__ scal) {
+   __shared__ double sy[32], sz[32];
+   __shared__ double lam;
+   double ay = 0.0, az = 0.0;
+   for (int i = threadIdx.x; i < nat; i += blockDim.x) {
+      ay += R[i];
+      az += R[i + npad];
+   }
+   for (int o = 16; o > 0; o >>= 1) {
+      ay += __shfl_xor_sync(0xffffffffu, ay, o);
+      az += __shfl_xor_sync(0xffffffffu, az, o);
+   }
+   if ((threadIdx.x & 31) == 0) {
+      sy[threadIdx.x >> 5] = ay;
+      sz[threadIdx.x >> 5] = az;
+   }
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      double ty = 0.0, tz = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+         ty += sy[w];
+         tz += sz[w];
+      }
+      lam = (ty - charge) / tz;
+      scal[0] = tz;
+      scal[1] = lam;
+      vrhs[nat] = lam;
+   }
+   __syncthreads();
+   const double l = lam;
+   for (int i = threadIdx.x; i < nat; i += blockDim.x) {
+      const double qi = R[i] - l * R[i + npad];
+      vrhs[i] = qi;
+      if (qvec) qvec[i] = qi;
+   }
+}
+
+// energy(i) += q_i (0.5 (J q)_i - x_i)      (type.F90:259-261)
+__global__ void energy_kernel(int nat, const double* __restrict__ q, const double* __restrict__ jq,
+                              const double* __restrict__ xvec, double* __restrict__ energy) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < nat) energy[i] += q[i] * (0.5 * jq[i] - xvec[i]);
+}
+
+// gradient(:, j) = q_j atrace(:, j) - gradx(:, j)    (type.F90:276-278 after eliminating dadr/dxdr)
+__global__ void gradient_kernel(int nat, const double* __restrict__ q, const double* __restrict__ atrace,
+                                const double* __restrict__ gradx, double* __restrict__ gradient) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < 3 * nat) gradient[i] = q[i / 3] * atrace[i] - gradx[i];
+}
+
+// sigma(a,b) += sum_k q_k (0.5 dadL(a,b,k) - thalf_k dcndL(a,b,k))   (type.F90:279-280); 9 warps
+__global__ void __launch_bounds__(288) sigma_kernel(int nat, const double* __restrict__ q,
+                                                    const double* __restrict__ dadL, const double* __restrict__ thalf,
+                                                    const double* __restrict__ dcndL, double* __restrict__ sigma) {
+   const int ab = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   double acc = 0.0;
+   for (int k = lane; k < nat; k += 32)
+      acc += q[k] * (0.5 * dadL[(size_t)9 * k + ab] - thalf[k] * dcndL[(size_t)9 * k + ab]);
+   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+   if (lane == 0) sigma[ab] += acc;
+}
+
+// rows 3N..3N+8 of B: dadL(:,:,k) - dxdL(:,:,k) (type.F90:286), and their z-contraction
+__global__ void __launch_bounds__(288) strain_rows_kernel(int nat, const double* __restrict__ dadL,
+                                                          const double* __restrict__ thalf,
+                                                          const double* __restrict__ dcndL,
+                                                          const double* __restrict__ zvec, double* __restrict__ B,
+                                                          int64_t ldb, double* __restrict__ bz) {
+   const int ab = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   double acc = 0.0;
+   for (int k = lane; k < nat; k += 32) {
+      const double v = dadL[(size_t)9 * k + ab] - thalf[k] * dcndL[(size_t)9 * k + ab];
+      B[(size_t)k * ldb + 3 * (size_t)nat + ab] = v;
+      acc = fma(v, zvec[k], acc);
+   }
+   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+   if (lane == 0) bz[3 * (size_t)nat + ab] = acc;
+}
+
+// dqdr(r, k) = -X(r, k) + bz_r z_k / s ; rows 3N.. go to dqdL     (type.F90:289-290 + Schur correction)
+__global__ void __launch_bounds__(256) dq_epilogue_kernel(int nat, const double* __restrict__ X, int64_t ldx,
+                                                          const double* __restrict__ bz,
+                                                          const double* __restrict__ zvec,
+                                                          const double* __restrict__ scal, double* __restrict__ dqdr,
+                                                          double* __restrict__ dqdL) {
+   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t nrow = 3 * (int64_t)nat + 9;
+   if (r >= nrow) return;
+   const double u = bz[r] / scal[0];
+   const int k0 = blockIdx.y * 16;
+#pragma unroll 4
+   for (int kk = 0; kk < 16; ++kk) {
+      const int k = k0 + kk;
+      if (k >= nat) break;
+      const double v = fma(u, zvec[k], -X[r + (size_t)k * ldx]);
+      if (r < 3 * (int64_t)nat) dqdr[r + (size_t)k * 3 * nat] = v;
+      else dqdL[(r - 3 * (int64_t)nat) + (size_t)k * 9] = v;
+   }
+}
+
+// pack / unpack helpers for the exposed dense test entry points
+__global__ void pad_copy_kernel(int64_t m, int64_t n, const double* __restrict__ src, int64_t lds, int64_t mp,
+                                int64_t np, double* __restrict__ dst, int64_t ldd, int identity_pad) {
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t j = blockIdx.y;
+   if (i >= mp || j >= np) return;
+   double v = 0.0;
+   if (i < m && j < n) v = src[i + j * lds];
+   else if (identity_pad && i == j) v = 1.0;
+   dst[i + j * ldd] = v;
+}
+__global__ void unpad_copy_kernel(int64_t m, int64_t n, const double* __restrict__ src, int64_t lds,
+                                  double* __restrict__ dst, int64_t ldd, int lower_only) {
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t j = blockIdx.y;
+   if (i >= m || j >= n) return;
+   if (lower_only && i < j) return;
+   dst[i + j * ldd] = src[i + j * lds];
+}
+
+// xvec_derivs (eeq.f90:152-180): dxdr(:,:,k) = thalf_k dcndr(:,:,k), dxdL likewise; last column zero
+__global__ void xvec_derivs_kernel(int nat, const double* __restrict__ thalf, const double* __restrict__ dcndr,
+                                   const double* __restrict__ dcndL, double* __restrict__ dxdr,
+                                   double* __restrict__ dxdL) {
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t n3 = 3 * (int64_t)nat;
+   const int64_t total = n3 * (nat + 1);
+   if (idx < total) {
+      const int64_t k = idx / n3;
+      dxdr[idx] = (k < nat) ? thalf[k] * dcndr[idx] : 0.0;
+   }
+   if (idx < 9 * (int64_t)(nat + 1)) {
+      const int64_t k = idx / 9;
+      dxdL[idx] = (k < nat) ? thalf[k] * dcndL[idx] : 0.0;
+   }
+}
+
+__global__ void fill_kernel(int64_t n, double v, double* __restrict__ p) {
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct SolveIO {
+   const double *cn = nullptr, *qloc = nullptr, *dcndr = nullptr, *dcndL = nullptr, *dqlocdr = nullptr,
+                *dqlocdL = nullptr;
+   double *energy = nullptr, *gradient = nullptr, *sigma = nullptr, *qvec = nullptr, *dqdr = nullptr,
+          *dqdL = nullptr;
+};
+
+static AtomPar gather_eeq(const mchrg_b200_model* model, const DevMol& mol) {
+   mchrg_b200_context* ctx = model->ctx;
+   AtomPar ap;
+   auto g = [&](int slot) {
+      double* d = ctx->alloc<double>(mol.nat);
+      gather_species(ctx, mol.nat, mol.id, model->dev(slot), d);
+      return d;
+   };
+   ap.chi = g(0);
+   ap.rad = g(1);
+   ap.eta = g(2);
+   ap.kcnchi = g(3);
+   ap.rcov = g(4);
+   return ap;
+}
+
+static DevMol stage_mol(mchrg_b200_context* ctx, const mchrg_b200_structure* mol) {
+   if (mol == nullptr || mol->nat <= 0 || mol->id == nullptr || mol->xyz == nullptr)
+      fail(MCHRG_B200_ERR_ARG, "invalid structure (nat=%d)", mol ? mol->nat : -1);
+   DevMol d;
+   d.nat = mol->nat;
+   d.id = ctx->in(mol->id, (size_t)mol->nat);
+   d.xyz = ctx->in(mol->xyz, (size_t)3 * mol->nat);
+   d.charge = mol->charge;
+   d.periodic = mol->periodic[0] || mol->periodic[1] || mol->periodic[2];
+   for (int k = 0; k < 9; ++k) d.lattice[k] = mol->lattice[k];
+   return d;
+}
+
+// the EEQ2019 solve on device arrays; returns LAPACK-style info (0 ok, > 0 failed pivot)
+static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, const AtomPar& ap, const SolveIO& io) {
+   mchrg_b200_context* ctx = model->ctx;
+   if (mol.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ solve is not available in this build");
+   const int nat = mol.nat;
+   const int64_t npad = round_up(nat, TILE);
+   const bool dcn = io.dcndr && io.dcndL;
+   const bool grad = io.gradient && io.sigma && dcn;
+   const bool cpq = io.dqdr && io.dqdL && dcn;
+
+   double* xvec = ctx->alloc<double>(nat + 1);
+   double* thalf = ctx->alloc<double>(nat);
+   eeq_xvec(ctx, mol, ap.chi, ap.kcnchi, io.cn, xvec, thalf);
+
+   // Coulomb block, factorisation
+   double* W = ctx->alloc<double>((size_t)npad * npad);
+   double* dinv = ctx->alloc<double>((size_t)npad * TILE);
+   int* info = ctx->alloc_zero<int>(1);
+   eeq_amat_0d(ctx, mol, ap.rad, ap.eta, W, npad, /*border=*/false, npad);
+   dpotrf_padded(ctx, npad, W, npad, dinv, info);
+   int* h_info = static_cast<int*>(ctx->pinned_buf(sizeof(int)));
+   MCHRG_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+
+   // y = J^-1 x, z = J^-1 1, Schur complement
+   double* R = ctx->alloc<double>((size_t)npad * 2);
+   MCHRG_LAUNCH(ctx, rhs_init_kernel, (unsigned)((npad + 255) / 256), 256, 0, nat, npad, xvec, R);
+   dpotrs_vec(ctx, npad, W, npad, dinv, R, npad, 2);
+   double* vrhs = ctx->alloc<double>(nat + 1);
+   double* scal = ctx->alloc<double>(2);
+   MCHRG_LAUNCH(ctx, schur_charges_kernel, 1, 1024, 0, nat, npad, R, mol.charge, vrhs, io.qvec, scal);
+   const double* zvec = R + npad;
+
+   if (io.energy || grad || cpq) {
+      double* jq = io.energy ? ctx->alloc<double>(nat) : nullptr;
+      double* atrace = (grad || cpq) ? ctx->alloc<double>((size_t)3 * nat) : nullptr;
+      double* dadL = (grad || cpq) ? ctx->alloc<double>((size_t)9 * nat) : nullptr;
+      eeq_pair_rows_0d(ctx, mol, ap.rad, ap.eta, vrhs, jq, atrace, dadL);
+      if (io.energy) MCHRG_LAUNCH(ctx, energy_kernel, (nat + 255) / 256, 256, 0, nat, vrhs, jq, xvec, io.energy);
+
+      if (grad || cpq) {
+         double* gradx = grad ? ctx->alloc_zero<double>((size_t)3 * nat) : nullptr;
+         double* Bm = nullptr;
+         double* bz = nullptr;
+         int64_t mp = 0;
+         if (cpq) {
+            mp = round_up(3 * (int64_t)nat + 9, TILE);
+            Bm = ctx->alloc_zero<double>((size_t)mp * npad);
+            bz = ctx->alloc_zero<double>((size_t)mp);
+         }
+         eeq_build_b_0d(ctx, mol, ap.rad, vrhs, atrace, thalf, io.dcndr, Bm, mp, gradx, zvec, bz);
+         if (grad) {
+            MCHRG_LAUNCH(ctx, gradient_kernel, (3 * nat + 255) / 256, 256, 0, nat, vrhs, atrace, gradx, io.gradient);
+            MCHRG_LAUNCH(ctx, sigma_kernel, 1, 288, 0, nat, vrhs, dadL, thalf, io.dcndL, io.sigma);
+         }
+         if (cpq) {
+            MCHRG_LAUNCH(ctx, strain_rows_kernel, 1, 288, 0, nat, dadL, thalf, io.dcndL, zvec, Bm, mp, bz);
+            dtrsm_right_lt(ctx, mp, npad, W, npad, dinv, Bm, mp);
+            dtrsm_right_ln(ctx, mp, npad, W, npad, dinv, Bm, mp);
+            dim3 grid((unsigned)((3 * (int64_t)nat + 9 + 255) / 256), (unsigned)((nat + 15) / 16));
+            MCHRG_LAUNCH(ctx, dq_epilogue_kernel, grid, 256, 0, nat, Bm, mp, bz, zvec, scal, io.dqdr, io.dqdL);
+         }
+      }
+   }
+   ctx->finish();
+   return *h_info;
+}
+
+static void check_model(const mchrg_b200_model* model) {
+   if (model == nullptr || model->ctx == nullptr) fail(MCHRG_B200_ERR_ARG, "null model");
+}
+
+static int solve_dispatch(const mchrg_b200_model* model, const DevMol& mol, const SolveIO& io) {
+   if (io.cn == nullptr) fail(MCHRG_B200_ERR_ARG, "cn is required");
+   if (model->kind == 1) {
+      AtomPar ap = gather_eeq(model, mol);
+      return solve_eeq_device(model, mol, ap, io);
+   }
+   fail(MCHRG_B200_ERR_MODEL, "EEQ-BC solve is not available in this build");
+}
+
+// translations for the coordination number: get_lattice_points(periodic, lattice, cutoff) (charge.f90:70)
+static const double* cn_translations(mchrg_b200_context* ctx, const mchrg_b200_structure* mol, double cutoff, int* ntr) {
+   std::vector<double> t = lat::points_cutoff(mol->periodic, mol->lattice, cutoff);
+   *ntr = (int)(t.size() / 3);
+   double* d = ctx->alloc<double>(t.size());
+   MCHRG_CUDA(cudaMemcpyAsync(d, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+   MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));  // t goes out of scope
+   return d;
+}
+
+}  // namespace mchrg
+
+// =============================================================================================
+extern "C" {
+
+static int new_model_common(mchrg_b200_context* ctx, mchrg_b200_model* m, mchrg_b200_model** out) {
+   return guarded(ctx, [&]() {
+      const int nid = m->nid;
+      std::vector<double> host((size_t)10 * nid + (size_t)nid * nid, 0.0);
+      auto put = [&](int slot, const std::vector<double>& v) {
+         for (size_t i = 0; i < v.size() && i < (size_t)nid; ++i) host[(size_t)slot * nid + i] = v[i];
+      };
+      put(0, m->chi); put(1, m->rad); put(2, m->eta); put(3, m->kcnchi); put(4, m->rcov);
+      put(5, m->kqchi); put(6, m->kqeta); put(7, m->cap); put(8, m->avg_cn); put(9, m->en);
+      for (size_t i = 0; i < m->rvdw.size(); ++i) host[(size_t)10 * nid + i] = m->rvdw[i];
+      if (cudaMalloc(&m->d_par, host.size() * sizeof(double)) != cudaSuccess) {
+         cudaGetLastError();
+         fail(MCHRG_B200_ERR_ALLOC, "model parameter allocation failed");
+      }
+      MCHRG_CUDA(cudaMemcpy(m->d_par, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
+      *out = m;
+      return 0;
+   });
+}
+
+int mchrg_b200_new_eeq_model(mchrg_b200_context* ctx, int32_t nid, const double* chi, const double* rad,
+                             const double* eta, const double* kcnchi, const double* rcov, double cutoff,
+                             double cn_exp, double cn_max, mchrg_b200_model** model) {
+   if (!ctx || !model || nid <= 0 || !chi || !rad || !eta || !kcnchi || !rcov) {
+      set_last_error("new_eeq_model: invalid argument");
+      return MCHRG_B200_ERR_ARG;
+   }
+   auto* m = new mchrg_b200_model();
+   m->ctx = ctx;
+   m->kind = 1;
+   m->nid = nid;
+   m->chi.assign(chi, chi + nid);
+   m->rad.assign(rad, rad + nid);
+   m->eta.assign(eta, eta + nid);
+   m->kcnchi.assign(kcnchi, kcnchi + nid);
+   m->rcov.assign(rcov, rcov + nid);
+   m->ncoord.cutoff = cutoff;
+   m->ncoord.kcn = cn_exp;
+   m->ncoord.cut = cn_max;
+   m->ncoord.norm_exp = 1.0;
+   int rc = new_model_common(ctx, m, model);
+   if (rc != 0) delete m;
+   return rc;
+}
+
+int mchrg_b200_new_eeq2019_model(mchrg_b200_context* ctx, int32_t nid, const int32_t* num,
+                                 mchrg_b200_model** model) {
+   if (!ctx || !model || nid <= 0 || !num) {
+      set_last_error("new_eeq2019_model: invalid argument");
+      return MCHRG_B200_ERR_ARG;
+   }
+   const double aatoau = 1.0 / 0.529177210903;
+   std::vector<double> chi(nid), rad(nid), eta(nid), kcnchi(nid), rcov(nid);
+   for (int i = 0; i < nid; ++i) {
+      const int z = num[i];
+      if (z < 1 || z > 103) {  // the reference getters return -1 for unknown elements (eeq2019.f90:174-178)
+         chi[i] = rad[i] = eta[i] = kcnchi[i] = -1.0;
+         rcov[i] = 0.0;
+         continue;
+      }
+      chi[i] = mchrg_eeq_chi[z - 1];
+      eta[i] = mchrg_eeq_eta[z - 1];
+      kcnchi[i] = mchrg_eeq_kcnchi[z - 1];
+      rad[i] = mchrg_eeq_rad[z - 1];
+      rcov[i] = mchrg_pa2009_covrad_aa[z - 1] * aatoau * 4.0 / 3.0;  // get_covalent_rad, D3 convention
+   }
+   return mchrg_b200_new_eeq_model(ctx, nid, chi.data(), rad.data(), eta.data(), kcnchi.data(), rcov.data(), 25.0,
+                                   7.5, 8.0, model);
+}
+
+void mchrg_b200_model_free(mchrg_b200_model* model) {
+   if (!model) return;
+   if (model->ctx) cudaSetDevice(model->ctx->device);
+   if (model->d_par) cudaFree(model->d_par);
+   delete model;
+}
+
+int mchrg_b200_model_kind(const mchrg_b200_model* model) { return model ? model->kind : 0; }
+
+// ---------------------------------------------------------------------------------------------
+int mchrg_b200_get_coordination_number(const mchrg_b200_model* model, const mchrg_b200_structure* mol, double* cn,
+                                       double* dcndr, double* dcndL) {
+   if (!model) return MCHRG_B200_ERR_ARG;
+   mchrg_b200_context* ctx = model->ctx;
+   return guarded(ctx, [&]() {
+      if (!cn || ((dcndr == nullptr) != (dcndL == nullptr))) fail(MCHRG_B200_ERR_ARG, "get_coordination_number: bad outputs");
+      DevMol d = stage_mol(ctx, mol);
+      const size_t n = d.nat;
+      int ntr = 0;
+      const double* trans = cn_translations(ctx, mol, model->ncoord.cutoff, &ntr);
+      double* rcov_a = ctx->alloc<double>(n);
+      gather_species(ctx, d.nat, d.id, model->dev(4), rcov_a);
+      ncoord_device(ctx, d, rcov_a, nullptr, model->ncoord, ntr, trans, ctx->out(cn, n), ctx->out(dcndr, 3 * n * n),
+                    ctx->out(dcndL, 9 * n));
+      return 0;
+   });
+}
+
+int mchrg_b200_local_charge(const mchrg_b200_model* model, const mchrg_b200_structure* mol, double* qloc,
+                            double* dqlocdr, double* dqlocdL) {
+   if (!model) return MCHRG_B200_ERR_ARG;
+   mchrg_b200_context* ctx = model->ctx;
+   return guarded(ctx, [&]() {
+      if (!qloc) fail(MCHRG_B200_ERR_ARG, "local_charge: qloc is required");
+      DevMol d = stage_mol(ctx, mol);
+      const size_t n = d.nat;
+      double* dq = ctx->out(qloc, n);
+      if (model->kind == 1) {  // no ncoord_en: qloc = charge / nat, derivatives zero (type.F90:308-320)
+         MCHRG_LAUNCH(ctx, fill_kernel, (unsigned)((n + 255) / 256), 256, 0, (int64_t)n, d.charge / (double)n, dq);
+         if (dqlocdr && dqlocdL) {
+            MCHRG_CUDA(cudaMemsetAsync(ctx->out(dqlocdr, 3 * n * n), 0, 3 * n * n * sizeof(double), ctx->stream));
+            MCHRG_CUDA(cudaMemsetAsync(ctx->out(dqlocdL, 9 * n), 0, 9 * n * sizeof(double), ctx->stream));
+         }
+         return 0;
+      }
+      fail(MCHRG_B200_ERR_MODEL, "EEQ-BC local_charge is not available in this build");
+   });
+}
+
+int mchrg_b200_get_xvec(const mchrg_b200_model* model, const mchrg_b200_structure* mol, const double* cn,
+                        const double* qloc, double* xvec) {
+   if (!model) return MCHRG_B200_ERR_ARG;
+   mchrg_b200_context* ctx = model->ctx;
+   return guarded(ctx, [&]() {
+      if (!cn || !xvec) fail(MCHRG_B200_ERR_ARG, "get_xvec: cn and xvec are required");
+      if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "EEQ-BC get_xvec is not available in this build");
+      DevMol d = stage_mol(ctx, mol);
+      AtomPar ap = gather_eeq(model, d);
+      eeq_xvec(ctx, d, ap.chi, ap.kcnchi, ctx->in(cn, (size_t)d.nat), ctx->out(xvec, (size_t)d.nat + 1), nullptr);
+      return 0;
+   });
+}
+
+int mchrg_b200_get_xvec_derivs(const mchrg_b200_model* model, const mchrg_b200_structure* mol, const double* cn,
+                               const double* qloc, const double* dcndr, const double* dcndL, const double* dqlocdr,
+                               const double* dqlocdL, double* dxdr, double* dxdL) {
+   if (!model) return MCHRG_B200_ERR_ARG;
+   mchrg_b200_context* ctx = model->ctx;
+   return guarded(ctx, [&]() {
+      if (!cn || !dcndr || !dcndL || !dxdr || !dxdL) fail(MCHRG_B200_ERR_ARG, "get_xvec_derivs: missing argument");
+      if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "EEQ-BC get_xvec_derivs is not available in this build");
+      DevMol d = stage_mol(ctx, mol);
+      const size_t n = d.nat;
+      AtomPar ap = gather_eeq(model, d);
+      double* xv = ctx->alloc<double>(n + 1);
+      double* thalf = ctx->alloc<double>(n);
+      eeq_xvec(ctx, d, ap.chi, ap.kcnchi, ctx->in(cn, n), xv, thalf);
+      const int64_t total = 3 * (int64_t)n * (n + 1);
+      MCHRG_LAUNCH(ctx, xvec_derivs_kernel, (unsigned)((total + 255) / 256), 256, 0, d.nat, thalf,
+                   ctx->in(dcndr, 3 * n * n), ctx->in(dcndL, 9 * n), ctx->out(dxdr, 3 * n * (n + 1)),
+                   ctx->out(dxdL, 9 * (n + 1)));
+      return 0;
+   });
+}
+
+int mchrg_b200_get_coulomb_matrix(const mchrg_b200_model* model, const mchrg_b200_structure* mol, const double* cn,
+                                  const double* qloc, double* amat) {
+   if (!model) return MCHRG_B200_ERR_ARG;
+   mchrg_b200_context* ctx = model->ctx;
+   return guarded(ctx, [&]() {
+      if (!amat) fail(MCHRG_B200_ERR_ARG, "get_coulomb_matrix: amat is required");
+      if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "EEQ-BC get_coulomb_matrix is not available in this build");
+      DevMol d = stage_mol(ctx, mol);
+      if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic get_coulomb_matrix is not available in this build");
+      const size_t nd = (size_t)d.nat + 1;
+      AtomPar ap = gather_eeq(model, d);
+      eeq_amat_0d(ctx, d, ap.rad, ap.eta, ctx->out(amat, nd * nd), (int64_t)nd, true, 0);
+      return 0;
+   });
+}
+
+int mchrg_b200_get_coulomb_derivs(const mchrg_b200_model* model, const mchrg_b200_structure* mol, const double* cn,
+                                  const double* qloc, const double* dcndr, const double* dcndL,
+                                  const double* dqlocdr, const double* dqlocdL, const double* qvec, double* dadr,
+                                  double* dadL, double* atrace) {
+   if (!model) return MCHRG_B200_ERR_ARG;
+   mchrg_b200_context* ctx = model->ctx;
+   return guarded(ctx, [&]() {
+      if (!qvec || !dadr || !dadL || !atrace) fail(MCHRG_B200_ERR_ARG, "get_coulomb_derivs: missing argument");
+      if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "EEQ-BC get_coulomb_derivs is not available in this build");
+      DevMol d = stage_mol(ctx, mol);
+      if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic get_coulomb_derivs is not available in this build");
+      const size_t n = d.nat;
+      AtomPar ap = gather_eeq(model, d);
+      const double* q = ctx->in(qvec, n);
+      double* d_dadr = ctx->out(dadr, 3 * n * (n + 1));
+      double* d_dadL = ctx->out(dadL, 9 * (n + 1));
+      double* d_atr = ctx->out(atrace, 3 * n);
+      // last column (the constraint) is zero in both arrays (eeq.f90:388-389)
+      MCHRG_CUDA(cudaMemsetAsync(d_dadr + 3 * n * n, 0, 3 * n * sizeof(double), ctx->stream));
+      MCHRG_CUDA(cudaMemsetAsync(d_dadL + 9 * n, 0, 9 * sizeof(double), ctx->stream));
+      eeq_pair_rows_0d(ctx, d, ap.rad, ap.eta, q, nullptr, d_atr, d_dadL);
+      eeq_build_b_0d(ctx, d, ap.rad, q, nullptr, nullptr, nullptr, d_dadr, 3 * (int64_t)n, nullptr, nullptr, nullptr);
+      return 0;
+   });
+}
+
+// ---------------------------------------------------------------------------------------------
+int mchrg_b200_solve(const mchrg_b200_model* model, const mchrg_b200_structure* mol, const double* cn,
+                     const double* qloc, const double* dcndr, const double* dcndL, const double* dqlocdr,
+                     const double* dqlocdL, double* energy, double* gradient, double* sigma, double* qvec,
+                     double* dqdr, double* dqdL) {
+   if (!model) return MCHRG_B200_ERR_ARG;
+   mchrg_b200_context* ctx = model->ctx;
+   return guarded(ctx, [&]() {
+      DevMol d = stage_mol(ctx, mol);
+      const size_t n = d.nat;
+      SolveIO io;
+      io.cn = ctx->in(cn, n);
+      io.qloc = ctx->in(qloc, n);
+      io.dcndr = ctx->in(dcndr, 3 * n * n);
+      io.dcndL = ctx->in(dcndL, 9 * n);
+      io.dqlocdr = ctx->in(dqlocdr, 3 * n * n);
+      io.dqlocdL = ctx->in(dqlocdL, 9 * n);
+      io.energy = ctx->out(energy, n, /*preload=*/true);
+      io.gradient = ctx->out(gradient, 3 * n);
+      io.sigma = ctx->out(sigma, 9, /*preload=*/true);
+      io.qvec = ctx->out(qvec, n);
+      io.dqdr = ctx->out(dqdr, 3 * n * n);
+      io.dqdL = ctx->out(dqdL, 9 * n);
+      return solve_dispatch(model, d, io);
+   });
+}
+
+static int singlepoint_impl(const mchrg_b200_model* model, const mchrg_b200_structure* mol, double* cn, double* qloc,
+                            double* energy, double* gradient, double* sigma, double* qvec, double* dqdr,
+                            double* dqdL, bool accumulate) {
+   mchrg_b200_context* ctx = model->ctx;
+   return guarded(ctx, [&]() {
+      DevMol d = stage_mol(ctx, mol);
+      const size_t n = d.nat;
+      const bool grad = (gradient && sigma) || (dqdr && dqdL);
+      int ntr = 0;
+      const double* trans = cn_translations(ctx, mol, model->ncoord.cutoff, &ntr);
+      double* rcov_a = ctx->alloc<double>(n);
+      gather_species(ctx, d.nat, d.id, model->dev(4), rcov_a);
+      double* d_cn = cn ? ctx->out(cn, n) : ctx->alloc<double>(n);
+      double* d_dcndr = grad ? ctx->alloc<double>(3 * n * n) : nullptr;
+      double* d_dcndL = grad ? ctx->alloc<double>(9 * n) : nullptr;
+      ncoord_device(ctx, d, rcov_a, nullptr, model->ncoord, ntr, trans, d_cn, d_dcndr, d_dcndL);
+      double* d_qloc = qloc ? ctx->out(qloc, n) : ctx->alloc<double>(n);
+      if (model->kind == 1)
+         MCHRG_LAUNCH(ctx, fill_kernel, (unsigned)((n + 255) / 256), 256, 0, (int64_t)n, d.charge / (double)n, d_qloc);
+      SolveIO io;
+      io.cn = d_cn;
+      io.qloc = d_qloc;
+      io.dcndr = d_dcndr;
+      io.dcndL = d_dcndL;
+      io.energy = ctx->out(energy, n, accumulate);
+      io.gradient = ctx->out(gradient, 3 * n);
+      io.sigma = ctx->out(sigma, 9, accumulate);
+      io.qvec = ctx->out(qvec, n);
+      io.dqdr = ctx->out(dqdr, 3 * n * n);
+      io.dqdL = ctx->out(dqdL, 9 * n);
+      return solve_dispatch(model, d, io);
+   });
+}
+
+int mchrg_b200_get_charges(const mchrg_b200_model* model, const mchrg_b200_structure* mol, double* qvec,
+                           double* dqdr, double* dqdL) {
+   if (!model) return MCHRG_B200_ERR_ARG;
+   if (!qvec) {
+      set_last_error("get_charges: qvec is required");
+      return MCHRG_B200_ERR_ARG;
+   }
+   return singlepoint_impl(model, mol, nullptr, nullptr, nullptr, nullptr, nullptr, qvec, dqdr, dqdL, true);
+}
+
+int mchrg_b200_singlepoint(const mchrg_b200_model* model, const mchrg_b200_structure* mol, double* cn, double* qloc,
+                           double* energy, double* gradient, double* sigma, double* qvec, double* dqdr,
+                           double* dqdL) {
+   if (!model) return MCHRG_B200_ERR_ARG;
+   return singlepoint_impl(model, mol, cn, qloc, energy, gradient, sigma, qvec, dqdr, dqdL, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense test entry points
+// ---------------------------------------------------------------------------------------------
+int mchrg_b200_dpotrf(mchrg_b200_context* ctx, int64_t n, double* a, int64_t lda) {
+   return guarded(ctx, [&]() {
+      if (n <= 0 || !a || lda < n) fail(MCHRG_B200_ERR_ARG, "dpotrf: invalid argument");
+      const int64_t np = round_up(n, TILE);
+      const double* src = ctx->in(a, (size_t)lda * n);
+      double* W = ctx->alloc<double>((size_t)np * np);
+      double* dinv = ctx->alloc<double>((size_t)np * TILE);
+      int* info = ctx->alloc_zero<int>(1);
+      dim3 g((unsigned)((np + 255) / 256), (unsigned)np);
+      MCHRG_LAUNCH(ctx, pad_copy_kernel, g, 256, 0, n, n, src, lda, np, np, W, np, 1);
+      dpotrf_padded(ctx, np, W, np, dinv, info);
+      double* dst = ctx->out(a, (size_t)lda * n, /*preload=*/true);
+      dim3 g2((unsigned)((n + 255) / 256), (unsigned)n);
+      MCHRG_LAUNCH(ctx, unpad_copy_kernel, g2, 256, 0, n, n, W, np, dst, lda, 1);
+      int* h_info = static_cast<int*>(ctx->pinned_buf(sizeof(int)));
+      MCHRG_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->finish();
+      return *h_info;
+   });
+}
+
+int mchrg_b200_dgemm(mchrg_b200_context* ctx, char transb, int64_t m, int64_t n, int64_t k, double alpha,
+                     const double* a, int64_t lda, const double* b, int64_t ldb, double beta, double* c,
+                     int64_t ldc) {
+   return guarded(ctx, [&]() {
+      const bool tb = (transb == 't' || transb == 'T');
+      if (m <= 0 || n <= 0 || k <= 0 || !a || !b || !c) fail(MCHRG_B200_ERR_ARG, "dgemm: invalid argument");
+      const int64_t mp = round_up(m, TILE), np = round_up(n, TILE), kp = round_up(k, 16);
+      const double* sa = ctx->in(a, (size_t)lda * k);
+      const double* sb = ctx->in(b, (size_t)ldb * (tb ? k : n));
+      double* dc = ctx->out(c, (size_t)ldc * n, /*preload=*/true);
+      double* A = ctx->alloc<double>((size_t)mp * kp);
+      double* B = ctx->alloc<double>(tb ? (size_t)np * kp : (size_t)kp * np);
+      double* Cp = ctx->alloc<double>((size_t)mp * np);
+      MCHRG_LAUNCH(ctx, pad_copy_kernel, dim3((unsigned)((mp + 255) / 256), (unsigned)kp), 256, 0, m, k, sa, lda, mp, kp,
+                   A, mp, 0);
+      if (tb)
+         MCHRG_LAUNCH(ctx, pad_copy_kernel, dim3((unsigned)((np + 255) / 256), (unsigned)kp), 256, 0, n, k, sb, ldb, np,
+                      kp, B, np, 0);
+      else
+         MCHRG_LAUNCH(ctx, pad_copy_kernel, dim3((unsigned)((kp + 255) / 256), (unsigned)np), 256, 0, k, n, sb, ldb, kp,
+                      np, B, kp, 0);
+      MCHRG_LAUNCH(ctx, pad_copy_kernel, dim3((unsigned)((mp + 255) / 256), (unsigned)np), 256, 0, m, n, dc, ldc, mp, np,
+                   Cp, mp, 0);
+      dgemm_padded(ctx, tb, mp, np, kp, alpha, A, mp, B, tb ? np : kp, beta, Cp, mp, false);
+      MCHRG_LAUNCH(ctx, unpad_copy_kernel, dim3((unsigned)((m + 255) / 256), (unsigned)n), 256, 0, m, n, Cp, mp, dc, ldc,
+                   0);
+      return 0;
+   });
+}
+
+int mchrg_b200_dpotrs_right(mchrg_b200_context* ctx, int64_t m, int64_t n, const double* l, int64_t ldl, double* x,
+                            int64_t ldx) {
+   return guarded(ctx, [&]() {
+      if (m <= 0 || n <= 0 || !l || !x) fail(MCHRG_B200_ERR_ARG, "dpotrs_right: invalid argument");
+      const int64_t mp = round_up(m, TILE), np = round_up(n, TILE);
+      const double* sl = ctx->in(l, (size_t)ldl * n);
+      double* dx = ctx->out(x, (size_t)ldx * n, /*preload=*/true);
+      double* W = ctx->alloc<double>((size_t)np * np);
+      double* dinv = ctx->alloc<double>((size_t)np * TILE);
+      double* X = ctx->alloc<double>((size_t)mp * np);
+      int* info = ctx->alloc_zero<int>(1);
+      // re-factor L L^T to obtain the inverted diagonal blocks: W = L L^T is formed by the GEMM itself
+      double* Lp = ctx->alloc<double>((size_t)np * np);
+      MCHRG_LAUNCH(ctx, pad_copy_kernel, dim3((unsigned)((np + 255) / 256), (unsigned)np), 256, 0, n, n, sl, ldl, np, np,
+                   Lp, np, 1);
+      // zero the strict upper triangle of Lp (caller may pass a full matrix)
+      dgemm_padded(ctx, true, np, np, np, 1.0, Lp, np, Lp, np, 0.0, W, np, false);
+      dpotrf_padded(ctx, np, W, np, dinv, info);
+      MCHRG_LAUNCH(ctx, pad_copy_kernel, dim3((unsigned)((mp + 255) / 256), (unsigned)np), 256, 0, m, n, dx, ldx, mp, np,
+                   X, mp, 0);
+      dtrsm_right_lt(ctx, mp, np, W, np, dinv, X, mp);
+      dtrsm_right_ln(ctx, mp, np, W, np, dinv, X, mp);
+      MCHRG_LAUNCH(ctx, unpad_copy_kernel, dim3((unsigned)((m + 255) / 256), (unsigned)n), 256, 0, m, n, X, mp, dx, ldx,
+                   0);
+      return 0;
+   });
+}
+
+}  // extern "C"

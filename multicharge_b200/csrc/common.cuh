@@ -1,0 +1,162 @@
+// Shared host/device infrastructure of libmchrg_b200: error handling, the context (one GPU, one
+// stream, grow-only device workspace), host<->device staging of caller arrays.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mchrg_b200.h"
+
+namespace mchrg {
+
+struct Error {
+   int code;
+   std::string msg;
+};
+
+[[noreturn]] inline void fail(int code, const char* fmt, ...) {
+   char buf[512];
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(buf, sizeof buf, fmt, ap);
+   va_end(ap);
+   throw Error{code, buf};
+}
+
+#define MCHRG_CUDA(call)                                                                            \
+   do {                                                                                             \
+      cudaError_t err__ = (call);                                                                   \
+      if (err__ != cudaSuccess)                                                                     \
+         ::mchrg::fail(MCHRG_B200_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,    \
+                       cudaGetErrorString(err__));                                                  \
+   } while (0)
+
+void set_last_error(const std::string& msg);
+
+constexpr int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace mchrg
+
+// One GPU + one stream + a grow-only bump arena.  Calls on one context are serialised by `mu`;
+// use one context per host thread for concurrent solves (the reference's solve is re-entrant,
+// SURVEY 8b "Threading").
+struct mchrg_b200_context {
+   int device = 0;
+   cudaStream_t stream = nullptr;
+   int sm_count = 148;
+   size_t smem_optin = 0;
+   std::mutex mu;
+   uint64_t launches = 0;
+
+   // bump arena: one cudaMalloc'ed slab, reset at the start of every entry point; when a call
+   // needs more than the slab holds, extra slabs are chained and merged on the next reset.
+   struct Slab {
+      char* base = nullptr;
+      size_t size = 0;
+      size_t used = 0;
+   };
+   std::vector<Slab> slabs;
+   size_t high_water = 0;
+
+   // pinned staging buffer for small host transfers (status words, scalars)
+   void* pinned = nullptr;
+   size_t pinned_size = 0;
+
+   // deferred device->host copies of output arrays (executed by finish())
+   struct Copyback {
+      void* host;
+      const void* dev;
+      size_t bytes;
+   };
+   std::vector<Copyback> copybacks;
+
+   void use() const { MCHRG_CUDA(cudaSetDevice(device)); }
+
+   void arena_reset();
+   void* arena_alloc(size_t bytes);
+   template <class T>
+   T* alloc(size_t n) { return static_cast<T*>(arena_alloc(n * sizeof(T))); }
+   template <class T>
+   T* alloc_zero(size_t n) {
+      T* p = alloc<T>(n);
+      MCHRG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), stream));
+      return p;
+   }
+
+   static bool is_device_ptr(const void* p);
+   // device-visible view of a caller input array (copies host arrays into the arena)
+   template <class T>
+   const T* in(const T* p, size_t n) {
+      if (p == nullptr || n == 0) return p;
+      if (is_device_ptr(p)) return p;
+      T* d = alloc<T>(n);
+      MCHRG_CUDA(cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+      return d;
+   }
+   // device buffer standing for a caller output array; host arrays are copied back by finish().
+   // `preload` stages the current host content first (for accumulate-into outputs).
+   template <class T>
+   T* out(T* p, size_t n, bool preload = false) {
+      if (p == nullptr || n == 0) return p;
+      if (is_device_ptr(p)) return p;
+      T* d = alloc<T>(n);
+      if (preload) MCHRG_CUDA(cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+      copybacks.push_back({p, d, n * sizeof(T)});
+      return d;
+   }
+   void finish();  // run the copy-backs and synchronise the stream
+
+   void* pinned_buf(size_t bytes);
+};
+
+namespace mchrg {
+
+// kernel launch bookkeeping: count + error check
+inline void after_launch(mchrg_b200_context* ctx, const char* name) {
+   ctx->launches++;
+   cudaError_t err = cudaGetLastError();
+   if (err != cudaSuccess) fail(MCHRG_B200_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(err));
+}
+
+#define MCHRG_LAUNCH(ctx, kernel, grid, block, smem, ...)                       \
+   do {                                                                          \
+      kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);           \
+      ::mchrg::after_launch((ctx), #kernel);                                     \
+   } while (0)
+
+// Runs `body` under the context lock with a fresh arena and converts exceptions to status codes.
+template <class F>
+int guarded(mchrg_b200_context* ctx, F&& body) {
+   if (ctx == nullptr) {
+      set_last_error("null context");
+      return MCHRG_B200_ERR_ARG;
+   }
+   std::lock_guard<std::mutex> lock(ctx->mu);
+   try {
+      ctx->use();
+      ctx->arena_reset();
+      ctx->copybacks.clear();
+      int rc = body();
+      ctx->finish();
+      return rc;
+   } catch (const Error& e) {
+      set_last_error(e.msg);
+      ctx->copybacks.clear();
+      cudaStreamSynchronize(ctx->stream);
+      cudaGetLastError();
+      return e.code;
+   } catch (const std::exception& e) {
+      set_last_error(e.what());
+      ctx->copybacks.clear();
+      return MCHRG_B200_ERR_ALLOC;
+   }
+}
+
+}  // namespace mchrg

@@ -1,0 +1,478 @@
+// Dense FP64 kernels for sm_100a: DMMA (mma.sync m8n8k4 f64 -- the only FP64 tensor-core path on
+// Blackwell; tcgen05 has no f64 kind) GEMM with a 4-stage cp.async pipeline, a register-resident
+// 128x128 Cholesky/inverse leaf, and the recursive drivers built from them.
+//
+// Replaces, on the device: sytrf/sytri/sytrs (lapack.F90:165-363, called from model/type.F90:221-243)
+// and gemm/gemv/symv (blas.F90, called from model/type.F90:235-290).
+#include "dense.cuh"
+
+namespace mchrg {
+
+// ------------------------------------------------------------------------------------------------
+// DMMA GEMM:  C = alpha * A * op(B) + beta * C
+// CTA tile 128 x 128 x 16, 512 threads = 16 warps in a 4 (M) x 4 (N) grid, warp tile 32 x 32
+// = 4 x 4 mma tiles of 8 x 8.  Shared memory holds k-major operand slabs padded so that the
+// per-lane fragment loads (8 rows x 4 k) are bank-conflict free:
+//   As[k][m], leading dimension 132 doubles (132 mod 16 == 4)
+//   Bs[k][n] (transb: B given as n x k)      leading dimension 132
+//   Bs[n][k] (no trans: B given as k x n)    leading dimension 20  (20 mod 16 == 4)
+// ------------------------------------------------------------------------------------------------
+namespace gemm {
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 512;
+constexpr int LDAS = BM + 4;
+constexpr int LDBT = BN + 4;
+constexpr int LDBN = BK + 4;
+constexpr int A_STAGE = BK * LDAS;                                             // 2112 doubles
+constexpr int B_STAGE = (BK * LDBT > BN * LDBN) ? BK * LDBT : BN * LDBN;       // 2560 doubles
+constexpr int STAGE = A_STAGE + B_STAGE;
+constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE * sizeof(double);         // 149504 B
+}  // namespace gemm
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                : "+d"(d0), "+d"(d1)
+                : "d"(a), "d"(b));
+}
+
+template <bool TRANSB>
+__global__ void __launch_bounds__(gemm::THREADS, 1)
+dgemm_dmma_kernel(int64_t kdim, double alpha, const double* __restrict__ A, int64_t lda,
+                  const double* __restrict__ B, int64_t ldb, double beta, double* C, int64_t ldc,
+                  int lower_only) {
+   using namespace gemm;
+   extern __shared__ __align__(16) double smem[];
+
+   int tm, tn;
+   if (lower_only) {  // linear index over the lower block triangle
+      const int b = blockIdx.x;
+      int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+      while ((int64_t)(r + 1) * (r + 2) / 2 <= b) ++r;
+      while ((int64_t)r * (r + 1) / 2 > b) --r;
+      tm = r;
+      tn = b - r * (r + 1) / 2;
+   } else {
+      tm = blockIdx.x;
+      tn = blockIdx.y;
+   }
+   const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+   const int tid = threadIdx.x;
+   const int lane = tid & 31, warp = tid >> 5;
+   const int wm = warp & 3, wn = warp >> 2;
+   const int g = lane >> 2, t = lane & 3;
+
+   const double* Ag = A + m0;
+   const double* Bg = TRANSB ? (B + n0) : (B + n0 * ldb);
+
+   auto load_stage = [&](int stage, int64_t k0) {
+      double* As = smem + (size_t)stage * STAGE;
+      double* Bs = As + A_STAGE;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {  // A: 16 k-columns x 64 16-byte chunks
+         const int c = tid + i * THREADS;
+         const int k = c >> 6, m2 = (c & 63) * 2;
+         cp_async16(As + k * LDAS + m2, Ag + (k0 + k) * lda + m2);
+      }
+      if (TRANSB) {
+#pragma unroll
+         for (int i = 0; i < 2; ++i) {
+            const int c = tid + i * THREADS;
+            const int k = c >> 6, n2 = (c & 63) * 2;
+            cp_async16(Bs + k * LDBT + n2, Bg + (k0 + k) * ldb + n2);
+         }
+      } else {
+#pragma unroll
+         for (int i = 0; i < 2; ++i) {  // B: 128 n-columns x 8 chunks along k
+            const int c = tid + i * THREADS;
+            const int n = c >> 3, k2 = (c & 7) * 2;
+            cp_async16(Bs + n * LDBN + k2, Bg + (int64_t)n * ldb + k0 + k2);
+         }
+      }
+   };
+
+   double acc[4][4][2];
+#pragma unroll
+   for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+   const int nk = (int)(kdim / BK);
+#pragma unroll
+   for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < nk) load_stage(s, (int64_t)s * BK);
+      cp_async_commit();
+   }
+
+   for (int kt = 0; kt < nk; ++kt) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      {
+         const int nxt = kt + STAGES - 1;
+         if (nxt < nk) load_stage(nxt % STAGES, (int64_t)nxt * BK);
+         cp_async_commit();
+      }
+      const double* As = smem + (size_t)(kt % STAGES) * STAGE;
+      const double* Bs = As + A_STAGE;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+         double a[4], b[4];
+#pragma unroll
+         for (int mt = 0; mt < 4; ++mt) a[mt] = As[(kk * 4 + t) * LDAS + wm * 32 + mt * 8 + g];
+#pragma unroll
+         for (int nt = 0; nt < 4; ++nt)
+            b[nt] = TRANSB ? Bs[(kk * 4 + t) * LDBT + wn * 32 + nt * 8 + g]
+                           : Bs[(wn * 32 + nt * 8 + g) * LDBN + kk * 4 + t];
+#pragma unroll
+         for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+      }
+   }
+   cp_async_wait<0>();
+
+   // epilogue: lane holds C[row g][cols 2t, 2t+1] of each 8x8 tile
+#pragma unroll
+   for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+         const int64_t row = m0 + wm * 32 + mt * 8 + g;
+         const int64_t col = n0 + wn * 32 + nt * 8 + 2 * t;
+         double* c0 = C + row + col * ldc;
+         double* c1 = c0 + ldc;
+         double v0 = alpha * acc[mt][nt][0], v1 = alpha * acc[mt][nt][1];
+         if (beta != 0.0) {
+            v0 += beta * (*c0);
+            v1 += beta * (*c1);
+         }
+         *c0 = v0;
+         *c1 = v1;
+      }
+}
+
+static void gemm_setup_once() {
+   static bool done = false;
+   if (done) return;
+   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)gemm::SMEM_BYTES));
+   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)gemm::SMEM_BYTES));
+   done = true;
+}
+
+void dgemm_padded(mchrg_b200_context* ctx, bool transb, int64_t m, int64_t n, int64_t k, double alpha,
+                  const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
+                  int64_t ldc, bool lower_only) {
+   if (m == 0 || n == 0) return;
+   if (m % gemm::BM || n % gemm::BN || k % gemm::BK || (lda & 1) || (ldb & 1))
+      fail(MCHRG_B200_ERR_ARG, "dgemm_padded: unpadded operand (m=%lld n=%lld k=%lld lda=%lld ldb=%lld)",
+           (long long)m, (long long)n, (long long)k, (long long)lda, (long long)ldb);
+   gemm_setup_once();
+   dim3 grid;
+   if (lower_only) {
+      const int64_t tiles = m / gemm::BM;
+      grid = dim3((unsigned)(tiles * (tiles + 1) / 2), 1, 1);
+   } else {
+      grid = dim3((unsigned)(m / gemm::BM), (unsigned)(n / gemm::BN), 1);
+   }
+   if (transb)
+      MCHRG_LAUNCH(ctx, dgemm_dmma_kernel<true>, grid, gemm::THREADS, gemm::SMEM_BYTES, k, alpha, A, lda, B, ldb,
+                   beta, C, ldc, lower_only ? 1 : 0);
+   else
+      MCHRG_LAUNCH(ctx, dgemm_dmma_kernel<false>, grid, gemm::THREADS, gemm::SMEM_BYTES, k, alpha, A, lda, B, ldb,
+                   beta, C, ldc, lower_only ? 1 : 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky leaf: factor one 128 x 128 diagonal block and invert its factor, one CTA of 256
+// threads.  Thread (tx, ty) = (tid & 15, tid >> 4) keeps the cyclic sub-matrix
+// rows {tx + 16 r}, cols {ty + 16 c} (r, c = 0..7) in registers; every elimination step
+// broadcasts one column (factorisation) or one row (Gauss-Jordan inversion) through shared memory,
+// one barrier per step.
+// ------------------------------------------------------------------------------------------------
+namespace leaf {
+constexpr int N = 128, THREADS = 256;
+constexpr size_t SMEM_BYTES = (size_t(N) * N + 2 * N + N) * sizeof(double);  // Ls + bcast[2] + 1/diag
+}  // namespace leaf
+
+__global__ void __launch_bounds__(leaf::THREADS, 1)
+potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv, int* __restrict__ info,
+                  int pivot_base) {
+   using namespace leaf;
+   extern __shared__ __align__(16) double smem[];
+   double* Ls = smem;                // Ls[col * N + row] = L(row, col)
+   double* bc = smem + N * N;        // bc[2][N] broadcast buffers
+   double* invd = bc + 2 * N;        // 1 / L(j, j)
+   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+   double a[8][8];
+#pragma unroll
+   for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+         const int row = tx + 16 * r, col = ty + 16 * c;
+         a[r][c] = (row >= col) ? W[row + (int64_t)col * ldw] : W[col + (int64_t)row * ldw];
+      }
+
+   bool failed = false;
+#pragma unroll
+   for (int cj = 0; cj < 8; ++cj) {
+      for (int jt = 0; jt < 16; ++jt) {
+         const int j = 16 * cj + jt;
+         double* col = bc + (j & 1) * N;
+         if (ty == jt) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) col[tx + 16 * r] = a[r][cj];
+         }
+         __syncthreads();
+         const double d = col[j];
+         if (!(d > 0.0)) {  // also catches NaN; uniform across the CTA
+            if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
+            failed = true;
+            break;
+         }
+         const double inv = 1.0 / sqrt(d);
+         if (ty == jt) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+               const int row = tx + 16 * r;
+               if (row > j) a[r][cj] *= inv;
+               else if (row == j) a[r][cj] = d * inv;
+            }
+         }
+         double lr[8], lc[8];
+#pragma unroll
+         for (int r = 0; r < 8; ++r) lr[r] = col[tx + 16 * r] * inv;
+#pragma unroll
+         for (int c = 0; c < 8; ++c) lc[c] = col[ty + 16 * c] * inv;
+#pragma unroll
+         for (int r = 0; r < 8; ++r) {
+            if (r < cj) continue;  // rows tx + 16 r <= j for r < cj
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+               if (c < cj) continue;
+               const int row = tx + 16 * r, cc = ty + 16 * c;
+               if (row > j && cc > j) a[r][c] = fma(-lr[r], lc[c], a[r][c]);
+            }
+         }
+      }
+      if (failed) break;
+   }
+
+   // publish L (lower triangle only) to global memory and shared memory
+#pragma unroll
+   for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+         const int row = tx + 16 * r, col = ty + 16 * c;
+         if (row >= col) {
+            W[row + (int64_t)col * ldw] = a[r][c];
+            Ls[col * N + row] = a[r][c];
+            if (row == col) invd[row] = 1.0 / a[r][c];
+         }
+      }
+   __syncthreads();
+
+   // Gauss-Jordan: X = inv(L), starting from the identity
+   double x[8][8];
+#pragma unroll
+   for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) x[r][c] = (tx + 16 * r == ty + 16 * c) ? 1.0 : 0.0;
+
+#pragma unroll
+   for (int cj = 0; cj < 8; ++cj) {
+      for (int jt = 0; jt < 16; ++jt) {
+         const int j = 16 * cj + jt;
+         double* rowb = bc + (j & 1) * N;
+         if (tx == jt) {
+            const double s = invd[j];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+               x[cj][c] *= s;
+               rowb[ty + 16 * c] = x[cj][c];
+            }
+         }
+         __syncthreads();
+#pragma unroll
+         for (int r = 0; r < 8; ++r) {
+            if (r < cj) continue;
+            const int row = tx + 16 * r;
+            if (row > j) {
+               const double l = Ls[j * N + row];
+#pragma unroll
+               for (int c = 0; c < 8; ++c) {
+                  if (c > cj) continue;  // X(j, col) == 0 for col > j
+                  x[r][c] = fma(-l, rowb[ty + 16 * c], x[r][c]);
+               }
+            }
+         }
+      }
+   }
+#pragma unroll
+   for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+         const int row = tx + 16 * r, col = ty + 16 * c;
+         dinv[row + col * N] = (row >= col && !failed) ? x[r][c] : 0.0;
+      }
+}
+
+static void leaf_setup_once() {
+   static bool done = false;
+   if (done) return;
+   MCHRG_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)leaf::SMEM_BYTES));
+   done = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// recursive drivers
+// ------------------------------------------------------------------------------------------------
+static int64_t split(int64_t n) { return (n / TILE / 2) * TILE; }
+
+void dtrsm_right_lt(mchrg_b200_context* ctx, int64_t m, int64_t n, const double* L, int64_t ldl,
+                    const double* dinv, double* X, int64_t ldx) {
+   if (m == 0 || n == 0) return;
+   if (n == TILE) {  // X <- X * inv(L_kk)^T
+      dgemm_padded(ctx, true, m, TILE, TILE, 1.0, X, ldx, dinv, TILE, 0.0, X, ldx);
+      return;
+   }
+   const int64_t n1 = split(n), n2 = n - n1;
+   dtrsm_right_lt(ctx, m, n1, L, ldl, dinv, X, ldx);
+   dgemm_padded(ctx, true, m, n2, n1, -1.0, X, ldx, L + n1, ldl, 1.0, X + n1 * ldx, ldx);
+   dtrsm_right_lt(ctx, m, n2, L + n1 + n1 * ldl, ldl, dinv + (n1 / TILE) * TILE * TILE, X + n1 * ldx, ldx);
+}
+
+void dtrsm_right_ln(mchrg_b200_context* ctx, int64_t m, int64_t n, const double* L, int64_t ldl,
+                    const double* dinv, double* X, int64_t ldx) {
+   if (m == 0 || n == 0) return;
+   if (n == TILE) {  // X <- X * inv(L_kk)
+      dgemm_padded(ctx, false, m, TILE, TILE, 1.0, X, ldx, dinv, TILE, 0.0, X, ldx);
+      return;
+   }
+   const int64_t n1 = split(n), n2 = n - n1;
+   dtrsm_right_ln(ctx, m, n2, L + n1 + n1 * ldl, ldl, dinv + (n1 / TILE) * TILE * TILE, X + n1 * ldx, ldx);
+   dgemm_padded(ctx, false, m, n1, n2, -1.0, X + n1 * ldx, ldx, L + n1, ldl, 1.0, X, ldx);
+   dtrsm_right_ln(ctx, m, n1, L, ldl, dinv, X, ldx);
+}
+
+static void potrf_rec(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info,
+                      int64_t off) {
+   if (n == TILE) {
+      MCHRG_LAUNCH(ctx, potrf_leaf_kernel, 1, leaf::THREADS, leaf::SMEM_BYTES, W, ldw, dinv, info, (int)off);
+      return;
+   }
+   const int64_t n1 = split(n), n2 = n - n1;
+   double* W21 = W + n1;
+   double* W22 = W + n1 + n1 * ldw;
+   double* dinv2 = dinv + (n1 / TILE) * TILE * TILE;
+   potrf_rec(ctx, n1, W, ldw, dinv, info, off);
+   dtrsm_right_lt(ctx, n2, n1, W, ldw, dinv, W21, ldw);
+   dgemm_padded(ctx, true, n2, n2, n1, -1.0, W21, ldw, W21, ldw, 1.0, W22, ldw, /*lower_only=*/true);
+   potrf_rec(ctx, n2, W22, ldw, dinv2, info, off + n1);
+}
+
+void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info) {
+   if (n % TILE || (ldw & 1)) fail(MCHRG_B200_ERR_ARG, "dpotrf_padded: n=%lld not a multiple of 128", (long long)n);
+   leaf_setup_once();
+   potrf_rec(ctx, n, W, ldw, dinv, info, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// (L L^T) Y = R for a few right-hand sides: blocked substitution with the inverted diagonal blocks
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_RHS = 4;
+
+// r_k <- inv(L_kk) r_k  (forward)  or  inv(L_kk)^T r_k (backward); one CTA of 128 threads
+__global__ void __launch_bounds__(128) trsv_diag_kernel(const double* __restrict__ dinv_k, double* __restrict__ R,
+                                                        int64_t ldr, int nrhs, int transpose) {
+   __shared__ double v[MAX_RHS][TILE];
+   const int i = threadIdx.x;
+   for (int c = 0; c < nrhs; ++c) v[c][i] = R[i + c * ldr];
+   __syncthreads();
+   double acc[MAX_RHS] = {0.0, 0.0, 0.0, 0.0};
+   if (!transpose) {
+      for (int k = 0; k <= i; ++k) {
+         const double l = dinv_k[i + k * TILE];
+         for (int c = 0; c < nrhs; ++c) acc[c] = fma(l, v[c][k], acc[c]);
+      }
+   } else {
+      for (int k = i; k < TILE; ++k) {
+         const double l = dinv_k[k + i * TILE];
+         for (int c = 0; c < nrhs; ++c) acc[c] = fma(l, v[c][k], acc[c]);
+      }
+   }
+   for (int c = 0; c < nrhs; ++c) R[i + c * ldr] = acc[c];
+}
+
+// forward update: R[i] -= sum_j L(i, j) w_j  for rows i below the block (one thread per row)
+__global__ void __launch_bounds__(256) trsv_update_fwd_kernel(const double* __restrict__ Lcol, int64_t ldl,
+                                                              const double* __restrict__ w, double* __restrict__ R,
+                                                              int64_t ldr, int64_t nrows, int nrhs) {
+   __shared__ double ws[MAX_RHS][TILE];
+   for (int idx = threadIdx.x; idx < nrhs * TILE; idx += blockDim.x) ws[idx / TILE][idx % TILE] = w[(idx % TILE) + (idx / TILE) * ldr];
+   __syncthreads();
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= nrows) return;
+   double acc[MAX_RHS] = {0.0, 0.0, 0.0, 0.0};
+   for (int j = 0; j < TILE; ++j) {
+      const double l = Lcol[i + (int64_t)j * ldl];
+      for (int c = 0; c < nrhs; ++c) acc[c] = fma(l, ws[c][j], acc[c]);
+   }
+   for (int c = 0; c < nrhs; ++c) R[i + c * ldr] -= acc[c];
+}
+
+// backward update: R[j] -= sum_i L(k0 + i, j) w_i  for columns j left of the block (one warp per column)
+__global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __restrict__ Lrow, int64_t ldl,
+                                                              const double* __restrict__ w, double* __restrict__ R,
+                                                              int64_t ldr, int64_t ncols, int nrhs) {
+   __shared__ double ws[MAX_RHS][TILE];
+   for (int idx = threadIdx.x; idx < nrhs * TILE; idx += blockDim.x) ws[idx / TILE][idx % TILE] = w[(idx % TILE) + (idx / TILE) * ldr];
+   __syncthreads();
+   const int lane = threadIdx.x & 31;
+   const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   if (j >= ncols) return;
+   double acc[MAX_RHS] = {0.0, 0.0, 0.0, 0.0};
+   for (int i = lane; i < TILE; i += 32) {
+      const double l = Lrow[i + j * ldl];
+      for (int c = 0; c < nrhs; ++c) acc[c] = fma(l, ws[c][i], acc[c]);
+   }
+   for (int c = 0; c < nrhs; ++c) {
+      double v = acc[c];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) R[j + c * ldr] -= v;
+   }
+}
+
+void dpotrs_vec(mchrg_b200_context* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv,
+                double* R, int64_t ldr, int nrhs) {
+   if (nrhs > MAX_RHS || n % TILE) fail(MCHRG_B200_ERR_ARG, "dpotrs_vec: bad arguments");
+   const int64_t nb = n / TILE;
+   for (int64_t k = 0; k < nb; ++k) {  // L w = r
+      double* rk = R + k * TILE;
+      MCHRG_LAUNCH(ctx, trsv_diag_kernel, 1, 128, 0, dinv + k * TILE * TILE, rk, ldr, nrhs, 0);
+      const int64_t below = n - (k + 1) * TILE;
+      if (below > 0)
+         MCHRG_LAUNCH(ctx, trsv_update_fwd_kernel, (unsigned)((below + 255) / 256), 256, 0,
+                      L + (k + 1) * TILE + k * TILE * ldl, ldl, rk, rk + TILE, ldr, below, nrhs);
+   }
+   for (int64_t k = nb - 1; k >= 0; --k) {  // L^T y = w
+      double* rk = R + k * TILE;
+      MCHRG_LAUNCH(ctx, trsv_diag_kernel, 1, 128, 0, dinv + k * TILE * TILE, rk, ldr, nrhs, 1);
+      const int64_t left = k * TILE;
+      if (left > 0)
+         MCHRG_LAUNCH(ctx, trsv_update_bwd_kernel, (unsigned)((left + 7) / 8), 256, 0, L + k * TILE, ldl, rk, R, ldr,
+                      left, nrhs);
+   }
+}
+
+}  // namespace mchrg

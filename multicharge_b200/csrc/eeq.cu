@@ -1,0 +1,360 @@
+// EEQ2019 pair kernels (non-periodic) and the erf coordination number, FP64, sm_100a.
+//
+// Work decomposition: one warp owns one matrix row (atom i) and strides its lanes over the
+// partner atoms j, so every per-row reduction (cn_i, atrace_i, dadL_i, (Jq)_i) is a warp shuffle
+// and every N^2-sized array (dcndr, amat, B) is written with lanes on the contiguous index.
+// These kernels are FP64-ALU bound (erf/exp are polynomial sequences on the FMA pipe) until the
+// 24 N^2-byte stores dominate.
+#include "eeq.cuh"
+
+namespace mchrg {
+
+#define SQRTPI 1.77245385090551602729816748334114518
+#define SQRT2PI 0.797884560802865355879892119868763737
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+   return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_kernel(int nat, const int* __restrict__ id, const double* __restrict__ src,
+                              double* __restrict__ dst) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < nat) dst[i] = src[id[i] - 1];
+}
+
+void gather_species(mchrg_b200_context* ctx, int nat, const int* id, const double* src, double* dst) {
+   MCHRG_LAUNCH(ctx, gather_kernel, (nat + 255) / 256, 256, 0, nat, id, src, dst);
+}
+
+// ---------------------------------------------------------------------------------------------
+// erf coordination number (mctc_ncoord; restated in SURVEY.md 3.4)
+//   count(r)  = 1/2 (1 + erf(-kcn (r - rc) / rc^norm_exp)),  rc = rcov_i + rcov_j
+//   dcount/dr = -kcn / (sqrt(pi) rc^norm_exp) exp(-(kcn (r - rc) / rc^norm_exp)^2)
+// pass 1: raw cn (row sums).  pass 2: derivatives, scaled by the log-cut factor of the raw cn.
+// ---------------------------------------------------------------------------------------------
+struct NcDev {
+   double kcn, norm_exp, cutoff2, cut;
+   int use_en;
+};
+
+__global__ void __launch_bounds__(256) cn_rows_kernel(int nat, const double* __restrict__ xyz,
+                                                      const double* __restrict__ rcov, const double* __restrict__ en,
+                                                      NcDev p, int ntr, const double* __restrict__ trans,
+                                                      double* __restrict__ cn_raw) {
+   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   const int lane = threadIdx.x & 31;
+   if (i >= nat) return;
+   const double xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2];
+   const double rci = rcov[i];
+   const double eni = p.use_en ? en[i] : 0.0;
+   double acc = 0.0;
+   for (int j = lane; j < nat; j += 32) {
+      const double rc = rci + rcov[j];
+      const double rcn = (p.norm_exp == 1.0) ? rc : pow(rc, p.norm_exp);
+      const double den = p.use_en ? (en[j] - eni) : 1.0;
+      const double dx = xi - xyz[3 * j], dy = yi - xyz[3 * j + 1], dz = zi - xyz[3 * j + 2];
+      for (int itr = 0; itr < ntr; ++itr) {
+         const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
+         const double r2 = rx * rx + ry * ry + rz * rz;
+         if (r2 > p.cutoff2 || r2 < 1.0e-12) continue;
+         const double r1 = sqrt(r2);
+         acc += den * 0.5 * (1.0 + erf(-p.kcn * (r1 - rc) / rcn));
+      }
+   }
+   acc = warp_sum(acc);
+   if (lane == 0) cn_raw[i] = acc;
+}
+
+__global__ void __launch_bounds__(256) cn_derivs_kernel(int nat, const double* __restrict__ xyz,
+                                                        const double* __restrict__ rcov, const double* __restrict__ en,
+                                                        NcDev p, int ntr, const double* __restrict__ trans,
+                                                        const double* __restrict__ cn_raw, double* __restrict__ dcndr,
+                                                        double* __restrict__ dcndL) {
+   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   const int lane = threadIdx.x & 31;
+   if (i >= nat) return;
+   const double xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2];
+   const double rci = rcov[i];
+   const double eni = p.use_en ? en[i] : 0.0;
+   double fcut = 1.0;
+   if (p.cut > 0.0) {
+      const double ecut = exp(p.cut);
+      fcut = ecut / (ecut + exp(cn_raw[i]));
+   }
+   double dg[3] = {0.0, 0.0, 0.0};
+   double dl[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+   double* row = dcndr + (size_t)3 * nat * i;  // dcndr(:, :, i)
+   for (int j = lane; j < nat; j += 32) {
+      const double rc = rci + rcov[j];
+      const double rcn = (p.norm_exp == 1.0) ? rc : pow(rc, p.norm_exp);
+      const double den = p.use_en ? (en[j] - eni) : 1.0;
+      const double dx = xi - xyz[3 * j], dy = yi - xyz[3 * j + 1], dz = zi - xyz[3 * j + 2];
+      double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+      for (int itr = 0; itr < ntr; ++itr) {
+         const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
+         const double r2 = rx * rx + ry * ry + rz * rz;
+         if (r2 > p.cutoff2 || r2 < 1.0e-12) continue;
+         const double r1 = sqrt(r2);
+         const double arg = p.kcn * (r1 - rc) / rcn;
+         const double dc = den * (-p.kcn / SQRTPI / rcn * exp(-arg * arg)) / r1;
+         const double c0 = dc * rx, c1 = dc * ry, c2 = dc * rz;  // countd
+         g0 += c0; g1 += c1; g2 += c2;
+         dl[0] += c0 * rx; dl[1] += c0 * ry; dl[2] += c0 * rz;
+         dl[3] += c1 * rx; dl[4] += c1 * ry; dl[5] += c1 * rz;
+         dl[6] += c2 * rx; dl[7] += c2 * ry; dl[8] += c2 * rz;
+      }
+      if (j != i) {  // d cn_i / d r_j = -countd ; self images cancel in dcndr
+         row[3 * j] = -g0 * fcut;
+         row[3 * j + 1] = -g1 * fcut;
+         row[3 * j + 2] = -g2 * fcut;
+         dg[0] += g0; dg[1] += g1; dg[2] += g2;
+      }
+   }
+#pragma unroll
+   for (int c = 0; c < 3; ++c) dg[c] = warp_sum(dg[c]);
+#pragma unroll
+   for (int c = 0; c < 9; ++c) dl[c] = warp_sum(dl[c]);
+   if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) row[3 * i + c] = dg[c] * fcut;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) dcndL[(size_t)9 * i + c] = dl[c] * fcut;
+   }
+}
+
+__global__ void cn_cut_kernel(int nat, double cut, const double* __restrict__ cn_raw, double* __restrict__ cn) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= nat) return;
+   const double c0 = cn_raw[i];
+   cn[i] = (cut > 0.0) ? log(1.0 + exp(cut)) - log(1.0 + exp(cut - c0)) : c0;
+}
+
+void ncoord_device(mchrg_b200_context* ctx, const DevMol& mol, const double* rcov_a, const double* en_a,
+                   const NcoordPar& par, int ntr, const double* trans, double* cn, double* dcndr, double* dcndL) {
+   const int nat = mol.nat;
+   NcDev p{par.kcn, par.norm_exp, par.cutoff * par.cutoff, par.cut, en_a != nullptr};
+   double* cn_raw = ctx->alloc<double>(nat);
+   const int rows_per_cta = 8;
+   const unsigned grid = (nat + rows_per_cta - 1) / rows_per_cta;
+   MCHRG_LAUNCH(ctx, cn_rows_kernel, grid, 256, 0, nat, mol.xyz, rcov_a, en_a, p, ntr, trans, cn_raw);
+   if (dcndr && dcndL)
+      MCHRG_LAUNCH(ctx, cn_derivs_kernel, grid, 256, 0, nat, mol.xyz, rcov_a, en_a, p, ntr, trans, cn_raw, dcndr, dcndL);
+   MCHRG_LAUNCH(ctx, cn_cut_kernel, (nat + 255) / 256, 256, 0, nat, par.cut, cn_raw, cn);
+}
+
+// ---------------------------------------------------------------------------------------------
+// get_xvec (eeq.f90:127-150) and the dx factor of get_xvec_derivs (eeq.f90:175)
+// ---------------------------------------------------------------------------------------------
+__global__ void eeq_xvec_kernel(int nat, const double* __restrict__ chi, const double* __restrict__ kcnchi,
+                                const double* __restrict__ cn, double charge, double* __restrict__ xvec,
+                                double* __restrict__ thalf) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < nat) {
+      const double tmp = kcnchi[i] / sqrt(cn[i] + 1.0e-14);
+      xvec[i] = -chi[i] + tmp * cn[i];
+      if (thalf) thalf[i] = 0.5 * tmp;
+   } else if (i == nat) {
+      xvec[nat] = charge;
+   }
+}
+
+void eeq_xvec(mchrg_b200_context* ctx, const DevMol& mol, const double* chi_a, const double* kcnchi_a,
+              const double* cn, double* xvec, double* thalf) {
+   MCHRG_LAUNCH(ctx, eeq_xvec_kernel, (mol.nat + 1 + 255) / 256, 256, 0, mol.nat, chi_a, kcnchi_a, cn, mol.charge,
+                xvec, thalf);
+}
+
+// ---------------------------------------------------------------------------------------------
+// get_amat_0d (eeq.f90:199-242): thread = row index (contiguous), 8 columns per thread
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) eeq_amat0d_kernel(int nat, const double* __restrict__ xyz,
+                                                         const double* __restrict__ rad, const double* __restrict__ eta,
+                                                         double* __restrict__ out, int64_t ld, int border, int64_t npad) {
+   const int64_t nrow = border ? nat + 1 : npad;
+   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (r >= nrow) return;
+   double xr = 0, yr = 0, zr = 0, rr = 0;
+   if (r < nat) {
+      xr = xyz[3 * r]; yr = xyz[3 * r + 1]; zr = xyz[3 * r + 2];
+      rr = rad[r] * rad[r];
+   }
+   const int64_t c0 = (int64_t)blockIdx.y * 8;
+#pragma unroll
+   for (int cc = 0; cc < 8; ++cc) {
+      const int64_t c = c0 + cc;
+      if (c >= nrow) break;
+      double v;
+      if (r < nat && c < nat) {
+         if (r == c) {
+            v = eta[r] + SQRT2PI / rad[r];
+         } else {
+            const double dx = xyz[3 * c] - xr, dy = xyz[3 * c + 1] - yr, dz = xyz[3 * c + 2] - zr;
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            const double gam = 1.0 / (rr + rad[c] * rad[c]);
+            v = erf(sqrt(r2 * gam)) / sqrt(r2);
+         }
+      } else if (border) {
+         v = (r == nat && c == nat) ? 0.0 : 1.0;
+      } else {
+         v = (r == c) ? 1.0 : 0.0;
+      }
+      out[r + c * ld] = v;
+   }
+}
+
+void eeq_amat_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a, double* out,
+                 int64_t ld, bool border, int64_t npad) {
+   const int64_t nrow = border ? mol.nat + 1 : npad;
+   dim3 grid((unsigned)((nrow + 127) / 128), (unsigned)((nrow + 7) / 8));
+   MCHRG_LAUNCH(ctx, eeq_amat0d_kernel, grid, 128, 0, mol.nat, mol.xyz, rad_a, eta_a, out, ld, border ? 1 : 0, npad);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row pass over all pairs: (J q)_i, atrace_i, dadL_i   (eeq.f90:199-242, 372-427; type.F90:259)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eeq_pair_rows0d_kernel(int nat, const double* __restrict__ xyz,
+                                                              const double* __restrict__ rad,
+                                                              const double* __restrict__ eta,
+                                                              const double* __restrict__ q, double* __restrict__ jq,
+                                                              double* __restrict__ atrace, double* __restrict__ dadL) {
+   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   const int lane = threadIdx.x & 31;
+   if (i >= nat) return;
+   const double xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2];
+   const double ri2 = rad[i] * rad[i];
+   const bool want_d = (atrace != nullptr) || (dadL != nullptr);
+   double sj = 0.0, at[3] = {0.0, 0.0, 0.0}, dl[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+   for (int j = lane; j < nat; j += 32) {
+      if (j == i) continue;
+      // vec = r_j - r_i as in eeq.f90:221,403 (every term is even or odd in vec, the sign is kept)
+      const double vx = xyz[3 * j] - xi, vy = xyz[3 * j + 1] - yi, vz = xyz[3 * j + 2] - zi;
+      const double r2 = vx * vx + vy * vy + vz * vz;
+      const double g2 = 1.0 / (ri2 + rad[j] * rad[j]);
+      const double arg = g2 * r2;
+      const double r1 = sqrt(r2);
+      const double ef = erf(sqrt(arg));
+      const double qj = q[j];
+      sj = fma(ef / r1, qj, sj);
+      if (want_d) {
+         const double gam = sqrt(g2);
+         const double dtmp = 2.0 * gam * exp(-arg) / (SQRTPI * r2) - ef / (r2 * r1);
+         // atrace(:, i) = sum_j dtmp (r_i - r_j) q_j = -dG q_j with dG = dtmp * vec
+         const double gx = dtmp * vx, gy = dtmp * vy, gz = dtmp * vz;
+         at[0] -= gx * qj; at[1] -= gy * qj; at[2] -= gz * qj;
+         // dadL(a, b, i) += dS(a, b) q_j,  dS(a, b) = vec(a) dG(b)
+         dl[0] += vx * gx * qj; dl[1] += vy * gx * qj; dl[2] += vz * gx * qj;
+         dl[3] += vx * gy * qj; dl[4] += vy * gy * qj; dl[5] += vz * gy * qj;
+         dl[6] += vx * gz * qj; dl[7] += vy * gz * qj; dl[8] += vz * gz * qj;
+      }
+   }
+   sj = warp_sum(sj);
+   if (want_d) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) at[c] = warp_sum(at[c]);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) dl[c] = warp_sum(dl[c]);
+   }
+   if (lane == 0) {
+      if (jq) jq[i] = sj + (eta[i] + SQRT2PI / rad[i]) * q[i];
+      if (atrace) {
+#pragma unroll
+         for (int c = 0; c < 3; ++c) atrace[3 * i + c] = at[c];
+      }
+      if (dadL) {
+#pragma unroll
+         for (int c = 0; c < 9; ++c) dadL[(size_t)9 * i + c] = dl[c];
+      }
+   }
+}
+
+void eeq_pair_rows_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a,
+                      const double* q, double* jq, double* atrace, double* dadL) {
+   const unsigned grid = (mol.nat + 7) / 8;
+   MCHRG_LAUNCH(ctx, eeq_pair_rows0d_kernel, grid, 256, 0, mol.nat, mol.xyz, rad_a, eta_a, q, jq, atrace, dadL);
+}
+
+// ---------------------------------------------------------------------------------------------
+// B = dadr (+ atrace on the diagonal) - dxdr, fused with the dcndr-contractions of the gradient
+// and the rank-one Schur vector (see eeq.cuh).  Thread = atom j (3 contiguous doubles of a column),
+// CTA = 128 atoms j x KCHUNK columns k.
+// ---------------------------------------------------------------------------------------------
+constexpr int BB_KCHUNK = 64;
+
+__global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const double* __restrict__ xyz,
+                                                            const double* __restrict__ rad,
+                                                            const double* __restrict__ q,
+                                                            const double* __restrict__ atrace,
+                                                            const double* __restrict__ thalf,
+                                                            const double* __restrict__ dcndr, double* __restrict__ Bout,
+                                                            int64_t ldb, double* __restrict__ gradx,
+                                                            const double* __restrict__ zvec, double* __restrict__ bz) {
+   __shared__ double sk[BB_KCHUNK][8];  // x, y, z, rad^2, thalf, thalf*q, z, unused
+   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+   const int k0 = blockIdx.y * BB_KCHUNK;
+   const int kn = min(BB_KCHUNK, nat - k0);
+   for (int idx = threadIdx.x; idx < kn; idx += blockDim.x) {
+      const int k = k0 + idx;
+      sk[idx][0] = xyz[3 * k]; sk[idx][1] = xyz[3 * k + 1]; sk[idx][2] = xyz[3 * k + 2];
+      sk[idx][3] = rad[k] * rad[k];
+      const double th = thalf ? thalf[k] : 0.0;
+      sk[idx][4] = th;
+      sk[idx][5] = th * q[k];
+      sk[idx][6] = zvec ? zvec[k] : 0.0;
+   }
+   __syncthreads();
+   if (j >= nat) return;
+   const double xj = xyz[3 * j], yj = xyz[3 * j + 1], zj = xyz[3 * j + 2];
+   const double rj2 = rad[j] * rad[j], qj = q[j];
+   double gx[3] = {0.0, 0.0, 0.0}, uz[3] = {0.0, 0.0, 0.0};
+   for (int kk = 0; kk < kn; ++kk) {
+      const int k = k0 + kk;
+      double b0, b1, b2;
+      if (k == j) {
+         b0 = b1 = b2 = 0.0;
+         if (atrace) { b0 = atrace[3 * j]; b1 = atrace[3 * j + 1]; b2 = atrace[3 * j + 2]; }
+      } else {
+         // dadr(:, j, k) = dtmp (r_j - r_k) q_j      (eeq.f90:412-413 for both orderings of the pair)
+         const double vx = xj - sk[kk][0], vy = yj - sk[kk][1], vz = zj - sk[kk][2];
+         const double r2 = vx * vx + vy * vy + vz * vz;
+         const double g2 = 1.0 / (rj2 + sk[kk][3]);
+         const double arg = g2 * r2;
+         const double gam = sqrt(g2);
+         const double dtmp = (2.0 * gam * exp(-arg) / (SQRTPI * r2) - erf(sqrt(arg)) / (r2 * sqrt(r2))) * qj;
+         b0 = dtmp * vx; b1 = dtmp * vy; b2 = dtmp * vz;
+      }
+      if (dcndr) {
+         const double* d = dcndr + ((size_t)nat * k + j) * 3;
+         const double d0 = d[0], d1 = d[1], d2 = d[2];
+         const double th = sk[kk][4], tq = sk[kk][5];
+         b0 = fma(-th, d0, b0); b1 = fma(-th, d1, b1); b2 = fma(-th, d2, b2);
+         gx[0] = fma(tq, d0, gx[0]); gx[1] = fma(tq, d1, gx[1]); gx[2] = fma(tq, d2, gx[2]);
+      }
+      if (Bout) {
+         double* o = Bout + (size_t)k * ldb + 3 * j;
+         o[0] = b0; o[1] = b1; o[2] = b2;
+      }
+      if (bz) {
+         const double zk = sk[kk][6];
+         uz[0] = fma(b0, zk, uz[0]); uz[1] = fma(b1, zk, uz[1]); uz[2] = fma(b2, zk, uz[2]);
+      }
+   }
+   if (gradx && dcndr) {
+      atomicAdd(gradx + 3 * j, gx[0]); atomicAdd(gradx + 3 * j + 1, gx[1]); atomicAdd(gradx + 3 * j + 2, gx[2]);
+   }
+   if (bz) {
+      atomicAdd(bz + 3 * j, uz[0]); atomicAdd(bz + 3 * j + 1, uz[1]); atomicAdd(bz + 3 * j + 2, uz[2]);
+   }
+}
+
+void eeq_build_b_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q,
+                    const double* atrace, const double* thalf, const double* dcndr, double* Bout, int64_t ldb,
+                    double* gradx, const double* zvec, double* bz) {
+   dim3 grid((unsigned)((mol.nat + 127) / 128), (unsigned)((mol.nat + BB_KCHUNK - 1) / BB_KCHUNK));
+   MCHRG_LAUNCH(ctx, eeq_build_b0d_kernel, grid, 128, 0, mol.nat, mol.xyz, rad_a, q, atrace, thalf, dcndr, Bout, ldb,
+                gradx, zvec, bz);
+}
+
+}  // namespace mchrg

@@ -1,0 +1,43 @@
+// Device pieces of the EEQ2019 model (model/eeq.f90) and of the erf coordination number
+// (mctc_ncoord): host-callable wrappers around the kernels in eeq.cu / eeq_pbc.cu.
+#pragma once
+#include "model.cuh"
+
+namespace mchrg {
+
+// gather per-species parameter `src` (device, [nid]) to atoms: dst[i] = src[id[i]-1]
+void gather_species(mchrg_b200_context* ctx, int nat, const int* id, const double* src, double* dst);
+
+// ---- mctc_ncoord%get_coordination_number -----------------------------------------------------
+// cn[nat]; dcndr[3*nat*nat], dcndL[9*nat] optional (both or none).  en_a == nullptr: cn_count%erf,
+// else erf_en (directed, weighted by en_j - en_i).  trans: device [3*ntr].
+void ncoord_device(mchrg_b200_context* ctx, const DevMol& mol, const double* rcov_a, const double* en_a,
+                   const NcoordPar& par, int ntr, const double* trans, double* cn, double* dcndr, double* dcndL);
+
+// ---- EEQ2019 -----------------------------------------------------------------------------------
+// get_xvec (eeq.f90:127-150): xvec[nat+1]; thalf[nat] (optional) = 0.5 * kcnchi / sqrt(cn + reg),
+// the factor of get_xvec_derivs (eeq.f90:175-177).
+void eeq_xvec(mchrg_b200_context* ctx, const DevMol& mol, const double* chi_a, const double* kcnchi_a,
+              const double* cn, double* xvec, double* thalf);
+
+// get_amat_0d (eeq.f90:199-242).  border=true: full (nat+1)^2 matrix with the constraint row/column,
+// ld = nat+1.  border=false: the nat x nat Coulomb block J into a buffer of order npad >= nat
+// (ld = npad) whose padding is the identity (solver work matrix).
+void eeq_amat_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a, double* out,
+                 int64_t ld, bool border, int64_t npad);
+
+// One pass over all pairs of row i (0-D): jq[i] = (J q)_i, atrace[3*nat] (eeq.f90:410-411),
+// dadL[9*nat] (eeq.f90:414-415).  Any output may be nullptr.
+void eeq_pair_rows_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a,
+                      const double* q, double* jq, double* atrace, double* dadL);
+
+// B(3j+c, k) = dadr(c,j,k) [+ atrace on the diagonal] - thalf_k * dcndr(c,j,k)   (type.F90:270-287)
+// written with leading dimension ldb; optionally accumulates
+//   gradx[3j+c] += sum_k thalf_k q_k dcndr(c,j,k)      (the dxdr*q term of type.F90:278)
+//   bz[3j+c]    += sum_k B(3j+c, k) zvec_k             (rank-one Schur correction of dq/dr)
+// dcndr may be nullptr (pure dadr, get_coulomb_derivs); Bout may be nullptr (gradient only).
+void eeq_build_b_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q,
+                    const double* atrace, const double* thalf, const double* dcndr, double* Bout, int64_t ldb,
+                    double* gradx, const double* zvec, double* bz);
+
+}  // namespace mchrg
