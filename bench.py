@@ -1,0 +1,385 @@
+#!/usr/bin/env python3
+"""Benchmark of the EEQ charge hot path (BASELINE.json metric) -- see DESIGN.md "Measurement".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload batch|cluster]
+
+Workload (N=1 and every N): BASELINE.json configs[1] -- EEQ2019 single points (charges + energy +
+gradient) for a batch of 100 000 synthetic 30-200-atom molecules per GPU; a "step" is one pass of the
+hot path over that batch.  Molecules are independent, so ranks get disjoint batches and there is no
+data-path collective ("scaling": "weak").
+
+  value   whole-job molecules/s with the batch already resident in HBM (CUDA events on the library's
+          stream, max over ranks)
+  e2e     the same through the public C-ABI call with pinned HOST buffers: H2D of the inputs and D2H of
+          charges/energies/gradients/status inside the timed region
+  roofline  the fused one-CTA-per-molecule kernel against the FP64 peak (cuBLAS DGEMM 8192^3 measured
+          live here, because MEASURED_PEAKS.json has no FP64 entry)
+  cpu_baseline  the CPU oracle (port of the reference's OpenMP+LAPACK path; the Fortran reference
+          cannot be built in this image) on a bounded sample of the same batch, all host cores
+  extra   the single-system numbers of the metric string: N = 16384 cluster, q+E+gradient time and the
+          FP64 fraction reached by the factorisation (configs[2])
+
+`--impl reference` times the CPU oracle alone (bounded sample per step) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+METRIC = "EEQ2019 q+E+gradient single points, batched molecules/s"
+UNIT = "molecules/s"
+NMOL = 100_000
+NMIN, NMAX = 30, 200
+SEED = 20250102
+CPU_SAMPLE = 20_000  # molecules in the bounded CPU sample (~10-30 s on the box's cores)
+
+# algorithmic FP64 work per molecule of n atoms (DESIGN.md "Algorithmic work"):
+#   Cholesky n^3/3 + two triangular solves with 2 right-hand sides 4 n^2 + C_PAIR per unique pair
+#   (3 erf + 2 exp at 40 / 25 flop each + 60 flop of arithmetic)
+C_PAIR = 3 * 40 + 2 * 25 + 60
+
+
+def algorithmic_flops(sizes):
+    n = sizes.astype(np.float64)
+    return float((n ** 3 / 3.0 + 4.0 * n ** 2 + C_PAIR * n * (n - 1) / 2.0).sum())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(ngpu):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29531")
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x, world, device):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def measure_fp64_peak(torch, dev):
+    """cuBLAS DGEMM 8192^3, best of 5 (the FP64 roofline denominator; not in MEASURED_PEAKS.json)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty(n, n, dtype=torch.float64, device=dev)
+    best = 1e30
+    for it in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / best / 1e12
+
+
+def cpu_reference_rate(nsample, seed, threads=None):
+    """CPU oracle on a bounded sample of the bench batch: molecules/s, threads, seconds."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    from synth import batch
+    offsets, num, xyz, charge = batch(nsample, seed, NMIN, NMAX)
+    orc.eeq2019_singlepoint_batch(offsets[:9], num[:offsets[8]], xyz[:offsets[8]], charge[:8], threads=threads)  # warm
+    t0 = time.perf_counter()
+    out = orc.eeq2019_singlepoint_batch(offsets, num, xyz, charge, threads=threads)
+    dt = time.perf_counter() - t0
+    assert int((out["status"] != 0).sum()) == 0
+    return nsample / dt, out["threads"], dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nsample = max(1000, CPU_SAMPLE // 4)
+    rates, thr = [], None
+    for it in range(args.warmup + args.steps):
+        rate, thr, _ = cpu_reference_rate(nsample, SEED + 1000 + it)
+        if it >= args.warmup:
+            rates.append(rate)
+    value = float(np.mean(rates))
+    sample = f"{nsample} molecules of the bench distribution (U{{{NMIN}..{NMAX}}} atoms) per step"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * nsample / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: batch of synthetic 30-200-atom molecules, EEQ2019 q+E+gradient",
+                       "sample_per_step": nsample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cluster_extra(torch, mc, ctx, ext, dev, fp64_peak):
+    """configs[2] numbers quoted by the metric string: N = 16384 cluster."""
+    from synth import cluster
+    nat = int(os.environ.get("MCHRG_BENCH_NAT", "16384"))
+    num, xyz = cluster(nat, SEED + 3)
+    mol = mc.Structure(num, xyz, 0.0)
+    model = mc.new_eeq2019_model(mol, ctx)
+    txyz = torch.tensor(mol.xyz, device=dev)
+    tid = torch.tensor(mol.id, device=dev)
+    res = {}
+
+    def run(want):
+        return model.singlepoint(mol, want=want, xyz=txyz, id=tid)
+
+    for tag, want in (("q_e_grad", ("qvec", "energy", "gradient")),):
+        run(want)
+        best = 1e30
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            run(want)
+            e1.record(ext)
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        res[tag + "_seconds"] = best
+    # factorisation alone: blocked Cholesky of a dense SPD matrix of the same order (device resident)
+    m = torch.randn(nat, nat, dtype=torch.float64, device=dev)
+    s = m @ m.T + nat * torch.eye(nat, dtype=torch.float64, device=dev)
+    del m
+    w = s.clone()
+    best = 1e30
+    for it in range(3):
+        w.copy_(s)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        ctx.dpotrf(w)
+        e1.record(ext)
+        torch.cuda.synchronize()
+        if it >= 1:
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+    res["nat"] = nat
+    res["cholesky_seconds_incl_pad_copies"] = best
+    res["cholesky_tflops"] = nat ** 3 / 3.0 / best / 1e12
+    res["cholesky_frac_of_measured_fp64_peak"] = res["cholesky_tflops"] / fp64_peak
+    del s, w
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args):
+    import torch
+    import multicharge_b200 as mc
+    from synth import batch
+
+    rank, world, local = dist_setup(args.gpus)
+    if world != args.gpus:
+        if rank == 0:
+            print(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = mc.Context(local)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    model = mc.new_eeq2019_batch_model(ctx)
+
+    nmol = args.nmol
+    offsets, num, xyz, charge = batch(nmol, SEED + 17 * rank, NMIN, NMAX)
+    sizes = np.diff(offsets)
+    ntot = int(offsets[-1])
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    d_in = (torch.tensor(offsets, device=dev), torch.tensor(num, device=dev), torch.tensor(xyz, device=dev),
+            torch.tensor(charge, device=dev))
+    d_out = dict(qvec=torch.empty(ntot, dtype=torch.float64, device=dev), energy=torch.empty(ntot, dtype=torch.float64, device=dev),
+                 gradient=torch.empty(ntot, 3, dtype=torch.float64, device=dev), status=torch.empty(nmol, dtype=torch.int32, device=dev))
+
+    def step_dev():
+        mc.singlepoint_batch(model, *d_in, out=d_out)
+
+    for _ in range(args.warmup):
+        step_dev()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier(world)
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_beg.record(ext)
+    for k in range(args.steps):
+        evs[k][0].record(ext)
+        step_dev()
+        evs[k][1].record(ext)
+    e_end.record(ext)
+    torch.cuda.synchronize()
+    barrier(world)
+    launches = ctx.launch_count - l0
+    total_s = e_beg.elapsed_time(e_end) * 1e-3
+    total_s = max_over_ranks(total_s, world, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_s = float(np.mean([a.elapsed_time(b) for a, b in evs])) * 1e-3  # all launches of the fused kernel in a step
+    nfail = int((d_out["status"] != 0).sum().item())
+
+    # ---- end-to-end arm: pinned host buffers through the public call -----------------------------
+    h_in = [torch.from_numpy(a).pin_memory() for a in (offsets, num, xyz, charge)]
+    h_out = dict(qvec=torch.empty(ntot, dtype=torch.float64).pin_memory(), energy=torch.empty(ntot, dtype=torch.float64).pin_memory(),
+                 gradient=torch.empty(ntot, 3, dtype=torch.float64).pin_memory(), status=torch.empty(nmol, dtype=torch.int32).pin_memory())
+    n_in = [t.numpy() for t in h_in]
+    n_out = {k: v.numpy() for k, v in h_out.items()}
+    h2d = int(sum(a.nbytes for a in n_in))
+    d2h = int(sum(a.nbytes for a in n_out.values()))
+
+    def step_e2e():
+        mc.singlepoint_batch(model, *n_in, out=n_out)
+
+    for _ in range(max(1, args.warmup - 1)):
+        step_e2e()
+    torch.cuda.synchronize()
+    barrier(world)
+    e_steps = max(2, min(args.steps, 5))
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record(ext)
+    for _ in range(e_steps):
+        step_e2e()
+    b1.record(ext)
+    torch.cuda.synchronize()
+    barrier(world)
+    e2e_s = max_over_ranks(b0.elapsed_time(b1) * 1e-3, world, dev)
+    # parity spot check of what the timed calls produced (device arm vs host arm, same inputs)
+    same = bool(np.array_equal(n_out["qvec"], d_out["qvec"].cpu().numpy()))
+
+    if rank != 0:
+        return 0
+
+    fp64_peak = measure_fp64_peak(torch, dev)
+    flops = algorithmic_flops(sizes)
+    achieved = flops / kernel_s / 1e12
+    cpu_rate, cpu_thr, cpu_dt = cpu_reference_rate(args.cpu_sample, SEED + 999)
+    extra = None
+    if args.gpus == 1 and not args.no_extra:
+        try:
+            extra = cluster_extra(torch, mc, ctx, ext, dev, fp64_peak)
+        except Exception as exc:  # keep the headline line even if the large case fails
+            extra = {"error": str(exc)}
+
+    line = {
+        "metric": METRIC, "value": world * nmol * args.steps / total_s, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 100k synthetic 30-200-atom molecules per GPU, EEQ2019 q+E+gradient",
+                   "molecules_per_gpu": nmol, "atoms_per_gpu": ntot, "seed": SEED,
+                   "l2": f"inputs+outputs {(h2d + d2h) / 1e6:.0f} MB per step exceed the 126 MB L2 (no flush needed)",
+                   "parallelism": f"independent molecules, {world} rank(s), no collective"},
+        "e2e": {"value": world * nmol * e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e_steps, "host_equals_device_result": same},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "eeq_batch_kernel (all size classes of one step)",
+                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                     "traffic": None,
+                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                     "algorithmic_flops_per_launch_set": flops, "seconds_per_launch_set": kernel_s},
+        "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cpu_thr, "kind": "port",
+                         "sample": f"{args.cpu_sample} molecules of the same distribution in {cpu_dt:.1f} s"},
+        "failed_molecules": nfail,
+    }
+    if extra is not None:
+        line["extra"] = extra
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nmol", type=int, default=NMOL)
+    ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

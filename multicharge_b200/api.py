@@ -295,3 +295,37 @@ def get_charges(model, mol, grad=False):
 def get_eeq_charges(mol, grad=False, ctx=None):
     """get_eeq_charges (charge.f90:81-104)."""
     return get_charges(new_eeq2019_model(mol, ctx), mol, grad)
+
+
+def new_eeq2019_batch_model(ctx=None):
+    """EEQ2019 model over all elements (species index == atomic number, Z = 1..103), as the batch
+    entry point requires."""
+    ctx = ctx or default_context()
+    h = C.c_void_p()
+    num = np.arange(1, 104, dtype=np.int32)
+    check(_lib.load().mchrg_b200_new_eeq2019_model(ctx._h, 103, _ptr(num), C.byref(h)))
+    return MchrgModel(h, ctx, 1)
+
+
+def singlepoint_batch(model, offsets, num, xyz, charge, gradient=True, out=None):
+    """CN -> solve(energy, gradient, qvec) for a batch of independent non-periodic molecules
+    (one get_charges / CLI single point per molecule, app/main.f90:114-118).
+
+    offsets[nmol+1] int64, num[ntot] int32 atomic numbers, xyz[ntot,3], charge[nmol]; arrays may be
+    numpy (host) or torch CUDA tensors (device).  Returns dict(qvec, energy, gradient, status);
+    pass `out` (same keys) to reuse buffers / keep results on the device.
+    """
+    nmol = int(offsets.shape[0]) - 1
+    host = isinstance(xyz, np.ndarray)
+    if out is None:
+        if not host:
+            raise ValueError("device inputs need caller-provided `out` tensors")
+        ntot = int(offsets[-1])
+        out = SolveResult(qvec=np.empty(ntot), energy=np.empty(ntot),
+                          gradient=np.empty((ntot, 3)) if gradient else None,
+                          status=np.empty(nmol, dtype=np.int32))
+    rc = _lib.load().mchrg_b200_singlepoint_batch(
+        model._h, nmol, _ptr(offsets), _ptr(num), _ptr(xyz), _ptr(charge), _ptr(out["qvec"]), _ptr(out["energy"]),
+        _ptr(out.get("gradient")), _ptr(out["status"]))
+    check(rc)
+    return out

@@ -1,10 +1,470 @@
-// Batched independent molecules (BASELINE.json configs[0..1]) -- placeholder until the fused
-// one-CTA-per-molecule kernel lands.
-#include "common.cuh"
+// Batches of independent non-periodic molecules (BASELINE.json configs[0..1]): ONE CTA PER MOLECULE,
+// the whole EEQ2019 single point (coordination number -> Coulomb block -> Cholesky + Schur
+// complement -> energy / gradient) inside one launch with the matrix resident in shared memory.
+//
+//   shared memory: packed lower triangle of J (row-major, order padded to a multiple of 16),
+//                  a 16 x (NP+4) k-major panel buffer, the 16x16 diagonal block, 13 per-atom vectors
+//   factorisation: right-looking blocked Cholesky, block 16: diagonal block in one warp (register
+//                  rows + shuffles), panel rows one thread each, trailing update on FP64 tensor
+//                  cores (mma.sync m8n8k4 DMMA, 16x16 tiles per warp, operands from the panel buffer)
+//   reference path replaced: app/main.f90:114-118 / charge.f90:37-77 per molecule, i.e.
+//                  mctc_ncoord (erf CN, log-cut), eeq.f90 get_xvec / get_amat_0d / get_damat_0d,
+//                  type.F90 solve (sytrf/sytrs -> Cholesky + Schur), energy and gradient.
+// Molecules are grouped by padded order NP (one launch per class) so shared memory, and with it the
+// number of resident CTAs per SM, matches the molecule size.
+#include <algorithm>
+#include <vector>
+
+#include "model.cuh"
+
+namespace mchrg {
+namespace batch {
+
+#define SQRTPI 1.77245385090551602729816748334114518
+#define SQRT2PI 0.797884560802865355879892119868763737
+
+constexpr int KB = 16;        // Cholesky block
+constexpr int NP_MAX = 208;   // largest padded order that fits in 227 KB of shared memory
+constexpr int NVEC = 13;
+
+struct Args {
+   const int64_t* offsets;
+   const int32_t* num;
+   const double* xyz;
+   const double* charge;
+   double* qvec;
+   double* energy;
+   double* gradient;
+   int32_t* status;
+   const int32_t* perm;  // molecule ids of this class
+   const double* par;    // model parameters [slot * nid + (Z-1)]
+   int nid;
+   double kcn, cutoff2, cut;
+   int np;               // padded order of the class (multiple of 16)
+};
+
+__host__ __device__ inline size_t smem_doubles(int np) {
+   return (size_t)np * (np + 1) / 2 + (size_t)KB * (np + 4) + KB * (KB + 1) + KB + (size_t)NVEC * np + 8;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+   return v;
+}
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                : "+d"(d0), "+d"(d1)
+                : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
+
+template <int NT>
+__global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
+   extern __shared__ __align__(16) double sm[];
+   const int np = p.np;
+   const int ldp = np + 4;
+   double* A = sm;                           // packed lower, row-major: A[tri(i) + j], j <= i
+   double* P = A + (size_t)np * (np + 1) / 2;  // panel, k-major: P[c * ldp + i]
+   double* Ld = P + (size_t)KB * ldp;        // diagonal block Ld[r * 17 + c]
+   double* rdiag = Ld + KB * (KB + 1);       // 1 / L(k0 + c, k0 + c)
+   double* vec = rdiag + KB;
+   double* X = vec;            double* Y = X + np;        double* Z = Y + np;
+   double* rad2 = Z + np;      double* dself = rad2 + np; double* rcov = dself + np;
+   double* fcut = rcov + np;   double* xv = fcut + np;    double* th = xv + np;
+   double* b0 = th + np;       double* b1 = b0 + np;      double* qv = b1 + np;
+   double* wf = qv + np;       // thalf * q * fcut
+   double* scal = wf + np;     // [0] lambda, [1] s
+   __shared__ int sfail;
+
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   constexpr int NW = NT / 32;
+   const int mol = p.perm[blockIdx.x];
+   const int64_t off = p.offsets[mol];
+   const int n = (int)(p.offsets[mol + 1] - off);
+   const double charge = p.charge[mol];
+
+   // ---- load atoms and per-element parameters (chi, rad, eta, kcnchi, rcov = slots 0..4) ----
+   if (tid == 0) sfail = 0;
+   for (int i = tid; i < np; i += NT) {
+      if (i < n) {
+         const int z = p.num[off + i] - 1;
+         X[i] = p.xyz[3 * (off + i)];
+         Y[i] = p.xyz[3 * (off + i) + 1];
+         Z[i] = p.xyz[3 * (off + i) + 2];
+         const double rad = p.par[1 * p.nid + z];
+         rad2[i] = rad * rad;
+         dself[i] = p.par[2 * p.nid + z] + SQRT2PI / rad;  // eta + sqrt(2/pi)/rad  (eeq.f90:228)
+         rcov[i] = p.par[4 * p.nid + z];
+         xv[i] = p.par[0 * p.nid + z];   // chi, turned into xvec below
+         th[i] = p.par[3 * p.nid + z];   // kcnchi, turned into thalf below
+      } else {
+         X[i] = Y[i] = Z[i] = 0.0;
+         rad2[i] = 1.0; dself[i] = 1.0; rcov[i] = 0.0; xv[i] = 0.0; th[i] = 0.0;
+      }
+   }
+   __syncthreads();
+
+   // ---- erf coordination number with log-cut (mctc_ncoord), xvec (eeq.f90:127-150) ----
+   const double ecut = exp(p.cut);
+   for (int i = warp; i < n; i += NW) {
+      const double xi = X[i], yi = Y[i], zi = Z[i], rci = rcov[i];
+      double acc = 0.0;
+      for (int j = lane; j < n; j += 32) {
+         const double dx = xi - X[j], dy = yi - Y[j], dz = zi - Z[j];
+         const double r2 = dx * dx + dy * dy + dz * dz;
+         if (r2 > p.cutoff2 || r2 < 1.0e-12) continue;
+         const double rc = rci + rcov[j];
+         acc += 0.5 * (1.0 + erf(-p.kcn * (sqrt(r2) - rc) / rc));
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+         double cn = acc, f = 1.0;
+         if (p.cut > 0.0) {
+            f = ecut / (ecut + exp(acc));
+            cn = log(1.0 + ecut) - log(1.0 + exp(p.cut - acc));
+         }
+         const double tmp = th[i] / sqrt(cn + 1.0e-14);
+         xv[i] = -xv[i] + tmp * cn;
+         th[i] = 0.5 * tmp;
+         fcut[i] = f;
+      }
+   }
+
+   // ---- Coulomb block J, packed lower (eeq.f90:199-242); padding = identity ----
+   const int ntri = np * (np + 1) / 2;
+   for (int e = tid; e < ntri; e += NT) {
+      int i = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+      while (tri(i + 1) <= e) ++i;
+      while (tri(i) > e) --i;
+      const int j = e - tri(i);
+      double v;
+      if (i == j) {
+         v = dself[i];
+      } else if (i < n) {
+         const double dx = X[j] - X[i], dy = Y[j] - Y[i], dz = Z[j] - Z[i];
+         const double r2 = dx * dx + dy * dy + dz * dz;
+         v = erf(sqrt(r2 / (rad2[i] + rad2[j]))) / sqrt(r2);
+      } else {
+         v = 0.0;
+      }
+      A[e] = v;
+   }
+   __syncthreads();
+
+   // ---- blocked Cholesky ----
+   for (int k0 = 0; k0 < np; k0 += KB) {
+      if (warp == 0) {  // diagonal block: lane r < 16 owns row k0 + r in registers
+         const int r = lane & 15;
+         double d[KB];
+#pragma unroll
+         for (int c = 0; c < KB; ++c) d[c] = (c <= r) ? A[tri(k0 + r) + k0 + c] : 0.0;
+         int bad = 0;
+#pragma unroll
+         for (int c = 0; c < KB; ++c) {
+            const double piv = __shfl_sync(0xffffffffu, d[c], c);
+            if (!(piv > 0.0) && bad == 0) bad = k0 + c + 1;
+            const double rinv = 1.0 / sqrt(piv);
+            if (r == c) {
+               d[c] = piv * rinv;
+               if (lane < KB) rdiag[c] = rinv;
+            } else if (r > c) {
+               d[c] *= rinv;
+            }
+#pragma unroll
+            for (int c2 = c + 1; c2 < KB; ++c2) {
+               const double l = __shfl_sync(0xffffffffu, d[c], c2);
+               if (r >= c2) d[c2] = fma(-d[c], l, d[c2]);
+            }
+         }
+         if (lane < KB) {
+#pragma unroll
+            for (int c = 0; c < KB; ++c) {
+               if (c <= r) A[tri(k0 + r) + k0 + c] = d[c];
+               Ld[r * (KB + 1) + c] = (c <= r) ? d[c] : 0.0;
+            }
+         }
+         if (bad && lane == 0) sfail = bad;
+      }
+      __syncthreads();
+      if (sfail) break;
+      const int t0 = k0 + KB;
+      if (t0 >= np) break;
+      // panel rows: one thread per row, a <- a * inv(Ld)^T
+      for (int i = t0 + tid; i < np; i += NT) {
+         double a[KB];
+         double* row = A + tri(i) + k0;
+#pragma unroll
+         for (int c = 0; c < KB; ++c) a[c] = row[c];
+#pragma unroll
+         for (int c = 0; c < KB; ++c) {
+            double s = a[c];
+#pragma unroll
+            for (int k = 0; k < c; ++k) s = fma(-a[k], Ld[c * (KB + 1) + k], s);
+            a[c] = s * rdiag[c];
+         }
+#pragma unroll
+         for (int c = 0; c < KB; ++c) {
+            row[c] = a[c];
+            P[c * ldp + i] = a[c];
+         }
+      }
+      __syncthreads();
+      // trailing update on DMMA: 16x16 tiles of the lower block triangle, one per warp iteration
+      const int nt = (np - t0) / KB;
+      const int ntile = nt * (nt + 1) / 2;
+      const int g = lane >> 2, t = lane & 3;
+      for (int tile = warp; tile < ntile; tile += NW) {
+         int ti = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+         while (tri(ti + 1) <= tile) ++ti;
+         while (tri(ti) > tile) --ti;
+         const int tj = tile - tri(ti);
+         const int i0 = t0 + KB * ti, j0 = t0 + KB * tj;
+         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+         for (int kk = 0; kk < KB / 4; ++kk) {
+            const double* pk = P + (4 * kk + t) * ldp;
+            const double a0 = pk[i0 + g], a1 = pk[i0 + 8 + g];
+            const double c0 = pk[j0 + g], c1 = pk[j0 + 8 + g];
+            dmma884(acc[0][0][0], acc[0][0][1], a0, c0);
+            dmma884(acc[0][1][0], acc[0][1][1], a0, c1);
+            dmma884(acc[1][0][0], acc[1][0][1], a1, c0);
+            dmma884(acc[1][1][0], acc[1][1][1], a1, c1);
+         }
+#pragma unroll
+         for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ntl = 0; ntl < 2; ++ntl) {
+               const int row = i0 + 8 * mt + g;
+               const int col = j0 + 8 * ntl + 2 * t;
+               double* dst = A + tri(row) + col;
+               if (col <= row) dst[0] -= acc[mt][ntl][0];
+               if (col + 1 <= row) dst[1] -= acc[mt][ntl][1];
+            }
+      }
+      __syncthreads();
+   }
+   if (sfail) {  // not positive definite: report the pivot, poison the outputs
+      const double nan = __longlong_as_double(0x7ff8000000000000LL);
+      for (int i = tid; i < n; i += NT) {
+         p.qvec[off + i] = nan;
+         if (p.energy) p.energy[off + i] = nan;
+         if (p.gradient) p.gradient[3 * (off + i)] = p.gradient[3 * (off + i) + 1] = p.gradient[3 * (off + i) + 2] = nan;
+      }
+      if (tid == 0) p.status[mol] = sfail;
+      return;
+   }
+
+   // ---- (L L^T) [y z] = [x 1] ----
+   for (int i = tid; i < np; i += NT) {
+      b0[i] = (i < n) ? xv[i] : 0.0;
+      b1[i] = (i < n) ? 1.0 : 0.0;
+   }
+   __syncthreads();
+   for (int k0 = 0; k0 < np; k0 += KB) {  // forward
+      if (warp == 0) {
+         const int r = lane & 15;
+         double v0 = b0[k0 + r], v1 = b1[k0 + r];
+#pragma unroll
+         for (int c = 0; c < KB; ++c) {
+            const double dinv = 1.0 / A[tri(k0 + c) + k0 + c];
+            const double w0 = __shfl_sync(0xffffffffu, v0, c) * dinv;
+            const double w1 = __shfl_sync(0xffffffffu, v1, c) * dinv;
+            if (r == c) { v0 = w0; v1 = w1; }
+            else if (r > c) {
+               const double l = A[tri(k0 + r) + k0 + c];
+               v0 = fma(-l, w0, v0);
+               v1 = fma(-l, w1, v1);
+            }
+         }
+         if (lane < KB) { b0[k0 + r] = v0; b1[k0 + r] = v1; }
+      }
+      __syncthreads();
+      for (int i = k0 + KB + tid; i < np; i += NT) {
+         const double* row = A + tri(i) + k0;
+         double s0 = b0[i], s1 = b1[i];
+#pragma unroll
+         for (int c = 0; c < KB; ++c) {
+            s0 = fma(-row[c], b0[k0 + c], s0);
+            s1 = fma(-row[c], b1[k0 + c], s1);
+         }
+         b0[i] = s0; b1[i] = s1;
+      }
+      __syncthreads();
+   }
+   for (int k0 = np - KB; k0 >= 0; k0 -= KB) {  // backward
+      if (warp == 0) {
+         const int r = lane & 15;
+         double v0 = b0[k0 + r], v1 = b1[k0 + r];
+#pragma unroll
+         for (int c = KB - 1; c >= 0; --c) {
+            const double dinv = 1.0 / A[tri(k0 + c) + k0 + c];
+            const double w0 = __shfl_sync(0xffffffffu, v0, c) * dinv;
+            const double w1 = __shfl_sync(0xffffffffu, v1, c) * dinv;
+            if (r == c) { v0 = w0; v1 = w1; }
+            else if (r < c) {
+               const double l = A[tri(k0 + c) + k0 + r];
+               v0 = fma(-l, w0, v0);
+               v1 = fma(-l, w1, v1);
+            }
+         }
+         if (lane < KB) { b0[k0 + r] = v0; b1[k0 + r] = v1; }
+      }
+      __syncthreads();
+      for (int j = tid; j < k0; j += NT) {
+         double s0 = b0[j], s1 = b1[j];
+#pragma unroll
+         for (int c = 0; c < KB; ++c) {
+            const double l = A[tri(k0 + c) + j];
+            s0 = fma(-l, b0[k0 + c], s0);
+            s1 = fma(-l, b1[k0 + c], s1);
+         }
+         b0[j] = s0; b1[j] = s1;
+      }
+      __syncthreads();
+   }
+   // Schur complement of the charge constraint: lambda = (1^T y - Q) / (1^T z), q = y - lambda z
+   if (warp == 0) {
+      double sy = 0.0, sz = 0.0;
+      for (int i = lane; i < n; i += 32) { sy += b0[i]; sz += b1[i]; }
+      sy = warp_sum(sy);
+      sz = warp_sum(sz);
+      if (lane == 0) { scal[0] = (sy - charge) / sz; scal[1] = sz; }
+   }
+   __syncthreads();
+   const double lam = scal[0];
+   for (int i = tid; i < n; i += NT) {
+      const double q = b0[i] - lam * b1[i];
+      qv[i] = q;
+      wf[i] = th[i] * q * fcut[i];
+      p.qvec[off + i] = q;
+   }
+   if (tid == 0) p.status[mol] = 0;
+   if (!p.energy && !p.gradient) return;
+   __syncthreads();
+
+   // ---- energy (type.F90:255-262) and gradient (type.F90:275-278) from one pair pass per row ----
+   for (int i = warp; i < n; i += NW) {
+      const double xi = X[i], yi = Y[i], zi = Z[i], ri2 = rad2[i], rci = rcov[i], qi = qv[i], wi = wf[i];
+      double jq = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+      for (int j = lane; j < n; j += 32) {
+         if (j == i) continue;
+         const double vx = xi - X[j], vy = yi - Y[j], vz = zi - Z[j];
+         const double r2 = vx * vx + vy * vy + vz * vz;
+         const double g2 = 1.0 / (ri2 + rad2[j]);
+         const double arg = g2 * r2, r1 = sqrt(r2);
+         const double ef = erf(sqrt(arg));
+         const double qj = qv[j];
+         jq = fma(ef / r1, qj, jq);
+         if (p.gradient) {
+            // q_i * atrace_i : dtmp (r_i - r_j) q_i q_j   (eeq.f90:403-411)
+            double f = (2.0 * sqrt(g2) * exp(-arg) / (SQRTPI * r2) - ef / (r2 * r1)) * qi * qj;
+            // - sum_k thalf_k q_k dcndr(:, i, k)  =  - sum_j dcount_ij (r_i - r_j)/r (w_i + w_j)
+            if (r2 <= p.cutoff2 && r2 >= 1.0e-12) {
+               const double rc = rci + rcov[j];
+               const double a = p.kcn * (r1 - rc) / rc;
+               const double dc = -p.kcn / SQRTPI / rc * exp(-a * a);
+               f -= dc / r1 * (wi + wf[j]);
+            }
+            gx = fma(f, vx, gx); gy = fma(f, vy, gy); gz = fma(f, vz, gz);
+         }
+      }
+      jq = warp_sum(jq);
+      if (p.gradient) { gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz); }
+      if (lane == 0) {
+         if (p.energy) p.energy[off + i] = qi * (0.5 * (jq + dself[i] * qi) - xv[i]);
+         if (p.gradient) {
+            p.gradient[3 * (off + i)] = gx;
+            p.gradient[3 * (off + i) + 1] = gy;
+            p.gradient[3 * (off + i) + 2] = gz;
+         }
+      }
+   }
+}
+
+template <int NT>
+static void launch_class(mchrg_b200_context* ctx, const Args& a, int count) {
+   const size_t smem = smem_doubles(a.np) * sizeof(double);
+   static size_t configured = 0;
+   if (smem > configured) {
+      MCHRG_CUDA(cudaFuncSetAttribute(eeq_batch_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(smem_doubles(NP_MAX) * sizeof(double))));
+      configured = smem_doubles(NP_MAX) * sizeof(double);
+   }
+   MCHRG_LAUNCH(ctx, eeq_batch_kernel<NT>, (unsigned)count, NT, smem, a);
+}
+
+}  // namespace batch
+}  // namespace mchrg
+
+using namespace mchrg;
 
 extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32_t nmol, const int64_t* offsets,
                                             const int32_t* num, const double* xyz, const double* charge, double* qvec,
                                             double* energy, double* gradient, int32_t* status) {
-   mchrg::set_last_error("singlepoint_batch is not available in this build");
-   return MCHRG_B200_ERR_MODEL;
+   if (!model) return MCHRG_B200_ERR_ARG;
+   mchrg_b200_context* ctx = model->ctx;
+   return guarded(ctx, [&]() {
+      if (nmol <= 0 || !offsets || !num || !xyz || !charge || !qvec || !status)
+         fail(MCHRG_B200_ERR_ARG, "singlepoint_batch: missing argument");
+      if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "singlepoint_batch serves EEQ2019-type models only");
+      // molecule sizes are needed on the host to form the size classes
+      std::vector<int64_t> hoff((size_t)nmol + 1);
+      if (mchrg_b200_context::is_device_ptr(offsets))
+         MCHRG_CUDA(cudaMemcpy(hoff.data(), offsets, hoff.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+      else
+         std::copy(offsets, offsets + nmol + 1, hoff.begin());
+      const size_t ntot = (size_t)hoff[nmol];
+      constexpr int NCLASS = batch::NP_MAX / batch::KB;
+      std::vector<std::vector<int32_t>> cls(NCLASS + 1);
+      for (int32_t m = 0; m < nmol; ++m) {
+         const int64_t n = hoff[m + 1] - hoff[m];
+         if (n <= 0) fail(MCHRG_B200_ERR_ARG, "singlepoint_batch: molecule %d is empty", m);
+         if (n > batch::NP_MAX)
+            fail(MCHRG_B200_ERR_ARG, "singlepoint_batch: molecule %d has %lld atoms (> %d); use mchrg_b200_singlepoint", m,
+                 (long long)n, batch::NP_MAX);
+         cls[(n + batch::KB - 1) / batch::KB].push_back(m);
+      }
+      std::vector<int32_t> perm;
+      perm.reserve(nmol);
+      for (auto& c : cls) perm.insert(perm.end(), c.begin(), c.end());
+      int32_t* dperm = ctx->alloc<int32_t>(nmol);
+      MCHRG_CUDA(cudaMemcpyAsync(dperm, perm.data(), perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+
+      batch::Args a;
+      a.offsets = ctx->in(offsets, (size_t)nmol + 1);
+      a.num = ctx->in(num, ntot);
+      a.xyz = ctx->in(xyz, 3 * ntot);
+      a.charge = ctx->in(charge, (size_t)nmol);
+      a.qvec = ctx->out(qvec, ntot);
+      a.energy = ctx->out(energy, ntot);
+      a.gradient = ctx->out(gradient, 3 * ntot);
+      a.status = ctx->out(status, (size_t)nmol);
+      a.par = model->d_par;
+      a.nid = model->nid;
+      a.kcn = model->ncoord.kcn;
+      a.cutoff2 = model->ncoord.cutoff * model->ncoord.cutoff;
+      a.cut = model->ncoord.cut;
+      size_t start = 0;
+      // largest classes first: their CTAs run longest, the small ones fill the tail
+      std::vector<std::pair<int, size_t>> order;
+      for (int c = 1; c <= NCLASS; ++c) {
+         order.push_back({c, start});
+         start += cls[c].size();
+      }
+      for (auto it = order.rbegin(); it != order.rend(); ++it) {
+         const int c = it->first;
+         const int count = (int)cls[c].size();
+         if (count == 0) continue;
+         a.np = c * batch::KB;
+         a.perm = dperm + it->second;
+         if (a.np <= 64) batch::launch_class<128>(ctx, a, count);
+         else if (a.np <= 128) batch::launch_class<256>(ctx, a, count);
+         else batch::launch_class<512>(ctx, a, count);
+      }
+      MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));  // perm (host vector) must outlive the async copy
+      return 0;
+   });
 }

@@ -875,3 +875,41 @@ int orc_param_eeqbc2025(int z, double* out) {
    out[8] = mchrg_eeqbc_avg_cn[z - 1];
    return 0;
 }
+
+/* ================= batch driver for the timed CPU baseline =================
+ * One reference single point (app/main.f90:114-118: CN -> solve with energy/gradient) per molecule,
+ * molecules distributed over the host threads (the inner OpenMP regions then run serially). */
+#include <stdint.h>
+int orc_eeq2019_singlepoint_batch(int nmol, const int64_t* offsets, const int* num, const double* xyz,
+                                  const double* charge, double* qvec, double* energy, double* gradient,
+                                  int* status, int want_gradient) {
+   static double chi[103], eta[103], kcnchi[103], rad[103], rcov[103];
+   for (int z = 1; z <= 103; ++z) {
+      double p[5];
+      orc_param_eeq2019(z, p);
+      chi[z - 1] = p[0]; eta[z - 1] = p[1]; kcnchi[z - 1] = p[2]; rad[z - 1] = p[3]; rcov[z - 1] = p[4];
+   }
+   orc_eeq_model model;
+   model.nid = 103;
+   model.chi = chi; model.rad = rad; model.eta = eta; model.kcnchi = kcnchi;
+   model.ncoord.rcov = rcov; model.ncoord.en = NULL; model.ncoord.kcn = 7.5; model.ncoord.norm_exp = 1.0;
+   model.ncoord.cutoff = 25.0; model.ncoord.cut = 8.0;
+   int nfail = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : nfail)
+   for (int m = 0; m < nmol; ++m) {
+      const int64_t off = offsets[m];
+      orc_mol mol;
+      memset(&mol, 0, sizeof mol);
+      mol.nat = (int)(offsets[m + 1] - off);
+      mol.nid = 103;
+      mol.id = num + off; /* species index == atomic number */
+      mol.xyz = xyz + 3 * off;
+      mol.charge = charge[m];
+      double sigma[9] = {0};
+      for (int i = 0; i < mol.nat; ++i) energy[off + i] = 0.0;
+      status[m] = orc_eeq_singlepoint(&model, &mol, NULL, qvec + off, energy + off,
+                                      want_gradient ? gradient + 3 * off : NULL, want_gradient ? sigma : NULL, NULL, NULL);
+      if (status[m]) ++nfail;
+   }
+   return nfail;
+}

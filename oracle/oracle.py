@@ -272,3 +272,24 @@ def eeq_singlepoint(model, mol, want=("qvec", "energy", "gradient")):
     out["stat"] = lib().orc_eeq_singlepoint(model.cref(), mol.cref(), _dp(out.cn), _dp(out.qvec), _dp(out.energy),
                                             _dp(out.gradient), _dp(out.sigma), _dp(out.dqdr), _dp(out.dqdL))
     return out
+
+
+def eeq2019_singlepoint_batch(offsets, num, xyz, charge, gradient=True, threads=None):
+    """CPU baseline for the batch workload: one reference single point per molecule, molecules spread
+    over `threads` host threads (default: all)."""
+    L = lib()
+    nthr = int(threads or os.cpu_count())
+    L.orc_set_num_threads(nthr)
+    L.scipy_openblas_set_num_threads(1)  # molecule-level parallelism; tiny LAPACK calls stay serial
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    num = np.ascontiguousarray(num, dtype=np.int32)
+    xyz = _f64(xyz)
+    charge = _f64(charge)
+    ntot, nmol = int(offsets[-1]), len(charge)
+    out = SolveResult(qvec=np.zeros(ntot), energy=np.zeros(ntot), gradient=np.zeros((ntot, 3)),
+                      status=np.zeros(nmol, dtype=np.int32))
+    L.orc_eeq2019_singlepoint_batch(C.c_int(nmol), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    num.ctypes.data_as(c_ip), _dp(xyz), _dp(charge), _dp(out.qvec), _dp(out.energy),
+                                    _dp(out.gradient), out.status.ctypes.data_as(c_ip), C.c_int(1 if gradient else 0))
+    out["threads"] = nthr
+    return out

@@ -1,0 +1,110 @@
+"""Parity of the one-CTA-per-molecule batch kernel against the CPU oracle (per molecule) and the
+reference's golden vectors.  Tolerance 1e-10 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def oracle_batch(oracle, offsets, num, xyz, charge):
+    q, e, g = np.zeros(len(num)), np.zeros(len(num)), np.zeros((len(num), 3))
+    for m in range(len(charge)):
+        s = slice(offsets[m], offsets[m + 1])
+        mol = oracle.Mol(num[s], xyz[s], charge[m])
+        r = oracle.eeq_singlepoint(oracle.new_eeq2019_model(mol), mol)
+        assert r.stat == 0
+        q[s], e[s], g[s] = r.qvec, r.energy, r.gradient
+    return q, e, g
+
+
+def test_batch_matches_oracle_all_size_classes(mc, oracle):
+    from synth import cluster
+    sizes = [1, 2, 3, 15, 16, 17, 31, 32, 33, 47, 64, 65, 80, 96, 100, 112, 127, 128, 129, 144, 160, 161, 176, 192, 200, 207, 208]
+    nums, xyzs = [], []
+    for k, n in enumerate(sizes):
+        num, xyz = cluster(n, 100 + k)
+        nums.append(num)
+        xyzs.append(xyz)
+    offsets = np.zeros(len(sizes) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    num, xyz = np.concatenate(nums), np.concatenate(xyzs)
+    charge = np.array([(k % 3) - 1.0 for k in range(len(sizes))])
+    model = mc.new_eeq2019_batch_model()
+    out = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    assert np.all(out["status"] == 0)
+    q, e, g = oracle_batch(oracle, offsets, num, xyz, charge)
+    assert np.abs(out["qvec"] - q).max() < TOL * max(1.0, np.abs(q).max())
+    assert np.abs(out["energy"] - e).max() < TOL * max(1.0, np.abs(e).max())
+    assert np.abs(out["gradient"] - g).max() < TOL * max(1.0, np.abs(g).max())
+    for m in range(len(sizes)):
+        assert abs(out["qvec"][offsets[m]:offsets[m + 1]].sum() - charge[m]) < 1e-10
+    # charges + energy only
+    out2 = mc.singlepoint_batch(model, offsets, num, xyz, charge, gradient=False)
+    assert np.abs(out2["qvec"] - q).max() < TOL and np.abs(out2["energy"] - e).max() < TOL
+
+
+def test_batch_golden_vectors(mc):
+    gs = [load_golden(n) for n in GOLDEN_CASES]
+    sizes = [len(g["num"]) for g in gs]
+    offsets = np.zeros(len(gs) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    num = np.concatenate([np.array(g["num"], dtype=np.int32) for g in gs])
+    xyz = np.concatenate([np.array(g["xyz"]) for g in gs])
+    charge = np.array([g["charge"] for g in gs])
+    out = mc.singlepoint_batch(mc.new_eeq2019_batch_model(), offsets, num, xyz, charge)
+    for m, g in enumerate(gs):
+        s = slice(offsets[m], offsets[m + 1])
+        assert np.abs(out["qvec"][s] - np.array(g["charges"])).max() < 5e-11
+        if "energy" in g:
+            assert abs(out["energy"][s].sum() - g["energy"]) < 5e-11
+            assert np.abs(out["gradient"][s].ravel() - np.array(g["gradient"])).max() < 5e-11
+
+
+def test_batch_random_1000_and_bad_molecule(mc, oracle):
+    from synth import batch
+    offsets, num, xyz, charge = batch(300, 77, nmin=30, nmax=200)
+    # molecule 5: two hydrogens on top of each other's charge cloud -> not positive definite
+    s = offsets[5]
+    num[s] = num[s + 1] = 1
+    xyz[s + 1] = xyz[s] + np.array([0.4, 0.0, 0.0])
+    out = mc.singlepoint_batch(mc.new_eeq2019_batch_model(), offsets, num, xyz, charge)
+    assert out["status"][5] > 0 and np.isnan(out["qvec"][offsets[5]])
+    ok = np.ones(len(charge), dtype=bool)
+    ok[5] = False
+    assert np.all(out["status"][ok] == 0)
+    pick = [0, 1, 2, 50, 123, 299]
+    for m in pick:
+        sl = slice(offsets[m], offsets[m + 1])
+        mol = oracle.Mol(num[sl], xyz[sl], charge[m])
+        r = oracle.eeq_singlepoint(oracle.new_eeq2019_model(mol), mol)
+        assert np.abs(out["qvec"][sl] - r.qvec).max() < TOL
+        assert np.abs(out["energy"][sl] - r.energy).max() < TOL
+        assert np.abs(out["gradient"][sl] - r.gradient).max() < TOL
+
+
+def test_batch_device_resident(mc, oracle):
+    import torch
+    from synth import batch
+    offsets, num, xyz, charge = batch(64, 5, nmin=10, nmax=120)
+    model = mc.new_eeq2019_batch_model()
+    ref = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    dev = torch.device("cuda:0")
+    ntot = int(offsets[-1])
+    out = dict(qvec=torch.empty(ntot, dtype=torch.float64, device=dev), energy=torch.empty(ntot, dtype=torch.float64, device=dev),
+               gradient=torch.empty(ntot, 3, dtype=torch.float64, device=dev), status=torch.empty(64, dtype=torch.int32, device=dev))
+    mc.singlepoint_batch(model, torch.tensor(offsets, device=dev), torch.tensor(num, device=dev), torch.tensor(xyz, device=dev),
+                         torch.tensor(charge, device=dev), out=out)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["qvec"].cpu().numpy(), ref["qvec"])
+    assert np.array_equal(out["gradient"].cpu().numpy(), ref["gradient"])
+
+
+def test_batch_rejects_oversized_molecule(mc):
+    from synth import cluster
+    num, xyz = cluster(209, 1)
+    offsets = np.array([0, 209], dtype=np.int64)
+    with pytest.raises(mc.MchrgError):
+        mc.singlepoint_batch(mc.new_eeq2019_batch_model(), offsets, num, xyz, np.zeros(1))
