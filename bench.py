@@ -76,7 +76,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, lo=0, hi=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -86,7 +89,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        for row in self.rows[lo:hi]:
             f = [x.strip() for x in row.split(",")]
             if len(f) < 7:
                 continue
@@ -270,14 +273,15 @@ def run_ours(args):
     def step_dev():
         mc.singlepoint_batch(model, *d_in, out=d_out)
 
-    for _ in range(args.warmup):
-        step_dev()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_dev()
+    torch.cuda.synchronize()
     barrier(world)
     torch.cuda.synchronize()
+    mark0 = sampler.mark()
     l0 = ctx.launch_count
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -292,7 +296,7 @@ def run_ours(args):
     launches = ctx.launch_count - l0
     total_s = e_beg.elapsed_time(e_end) * 1e-3
     total_s = max_over_ranks(total_s, world, dev)
-    clocks = sampler.stop() if rank == 0 else None
+    mark1 = sampler.mark()
     kernel_s = float(np.mean([a.elapsed_time(b) for a, b in evs])) * 1e-3  # all launches of the fused kernel in a step
     nfail = int((d_out["status"] != 0).sum().item())
 
@@ -323,6 +327,12 @@ def run_ours(args):
     e2e_s = max_over_ranks(b0.elapsed_time(b1) * 1e-3, world, dev)
     # parity spot check of what the timed calls produced (device arm vs host arm, same inputs)
     same = bool(np.array_equal(n_out["qvec"], d_out["qvec"].cpu().numpy()))
+    # clocks seen while the device-resident timed region ran (fall back to the whole run if it was too short
+    # for a sample)
+    clocks = None
+    if rank == 0:
+        time.sleep(0.3)
+        clocks = sampler.stop(mark0, max(mark1, mark0 + 1))
 
     if rank != 0:
         return 0
@@ -368,7 +378,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nmol", type=int, default=NMOL)

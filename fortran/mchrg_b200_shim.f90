@@ -1,0 +1,344 @@
+! iso_c_binding shim: multicharge's model API on top of libmchrg_b200.so (include/mchrg_b200.h).
+!
+! SOURCE ONLY -- this image has no Fortran compiler and mctc-lib v0.5.2 is not vendored, so this
+! file is neither compiled nor tested here (see INTEGRATION.md).  It is the binding a maintainer
+! adds to the reference tree: `b200_model_type` extends `mchrg_model_type`, overrides `solve`
+! (src/multicharge/model/type.F90:151-292) and implements the deferred procedures
+! (type.F90:78-125) by forwarding the caller's arrays -- unchanged, column-major -- to the C ABI.
+module mchrg_b200_shim
+   use, intrinsic :: iso_c_binding
+   use mctc_env, only : wp, error_type, fatal_error
+   use mctc_io, only : structure_type
+   use multicharge_model_type, only : mchrg_model_type
+   use multicharge_model_cache, only : cache_container
+   implicit none
+   private
+
+   public :: b200_model_type, new_b200_eeq2019_model, b200_get_charges
+
+   type, bind(C) :: c_structure
+      integer(c_int32_t) :: nat
+      integer(c_int32_t) :: nid
+      type(c_ptr) :: id
+      type(c_ptr) :: xyz
+      real(c_double) :: charge
+      integer(c_int32_t) :: periodic(3)
+      real(c_double) :: lattice(9)
+   end type c_structure
+
+   !> multicharge model whose hot path runs on a B200 (drop-in for eeq_model / eeqbc_model)
+   type, extends(mchrg_model_type) :: b200_model_type
+      type(c_ptr) :: ctx = c_null_ptr
+      type(c_ptr) :: handle = c_null_ptr
+   contains
+      procedure :: solve => b200_solve
+      procedure :: update => b200_update
+      procedure :: get_xvec => b200_get_xvec
+      procedure :: get_xvec_derivs => b200_get_xvec_derivs
+      procedure :: get_coulomb_matrix => b200_get_coulomb_matrix
+      procedure :: get_coulomb_derivs => b200_get_coulomb_derivs
+      final :: b200_free
+   end type b200_model_type
+
+   interface
+      function c_context_create(device, ctx) result(stat) bind(C, name="mchrg_b200_context_create")
+         import :: c_int, c_ptr
+         integer(c_int), value :: device
+         type(c_ptr), intent(out) :: ctx
+         integer(c_int) :: stat
+      end function
+      function c_new_eeq2019_model(ctx, nid, num, model) result(stat) bind(C, name="mchrg_b200_new_eeq2019_model")
+         import :: c_int, c_int32_t, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int32_t), value :: nid
+         integer(c_int32_t), intent(in) :: num(*)
+         type(c_ptr), intent(out) :: model
+         integer(c_int) :: stat
+      end function
+      subroutine c_model_free(model) bind(C, name="mchrg_b200_model_free")
+         import :: c_ptr
+         type(c_ptr), value :: model
+      end subroutine
+      function c_last_error() result(msg) bind(C, name="mchrg_b200_last_error")
+         import :: c_ptr
+         type(c_ptr) :: msg
+      end function
+      function c_solve(model, mol, cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL, energy, gradient, sigma, &
+            & qvec, dqdr, dqdL) result(stat) bind(C, name="mchrg_b200_solve")
+         import :: c_int, c_ptr, c_structure
+         type(c_ptr), value :: model
+         type(c_structure), intent(in) :: mol
+         type(c_ptr), value :: cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL
+         type(c_ptr), value :: energy, gradient, sigma, qvec, dqdr, dqdL
+         integer(c_int) :: stat
+      end function
+      function c_get_charges(model, mol, qvec, dqdr, dqdL) result(stat) bind(C, name="mchrg_b200_get_charges")
+         import :: c_int, c_ptr, c_structure
+         type(c_ptr), value :: model
+         type(c_structure), intent(in) :: mol
+         type(c_ptr), value :: qvec, dqdr, dqdL
+         integer(c_int) :: stat
+      end function
+      function c_get_xvec(model, mol, cn, qloc, xvec) result(stat) bind(C, name="mchrg_b200_get_xvec")
+         import :: c_int, c_ptr, c_structure
+         type(c_ptr), value :: model
+         type(c_structure), intent(in) :: mol
+         type(c_ptr), value :: cn, qloc, xvec
+         integer(c_int) :: stat
+      end function
+      function c_get_xvec_derivs(model, mol, cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL, dxdr, dxdL) &
+            & result(stat) bind(C, name="mchrg_b200_get_xvec_derivs")
+         import :: c_int, c_ptr, c_structure
+         type(c_ptr), value :: model
+         type(c_structure), intent(in) :: mol
+         type(c_ptr), value :: cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL, dxdr, dxdL
+         integer(c_int) :: stat
+      end function
+      function c_get_coulomb_matrix(model, mol, cn, qloc, amat) result(stat) &
+            & bind(C, name="mchrg_b200_get_coulomb_matrix")
+         import :: c_int, c_ptr, c_structure
+         type(c_ptr), value :: model
+         type(c_structure), intent(in) :: mol
+         type(c_ptr), value :: cn, qloc, amat
+         integer(c_int) :: stat
+      end function
+      function c_get_coulomb_derivs(model, mol, cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL, qvec, dadr, dadL, &
+            & atrace) result(stat) bind(C, name="mchrg_b200_get_coulomb_derivs")
+         import :: c_int, c_ptr, c_structure
+         type(c_ptr), value :: model
+         type(c_structure), intent(in) :: mol
+         type(c_ptr), value :: cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL, qvec, dadr, dadL, atrace
+         integer(c_int) :: stat
+      end function
+   end interface
+
+   !> per-solve cache payload: the B200 path rebuilds its device workspace per call, so the cache only
+   !> remembers the caller's arrays for the piecewise procedures (eeq.f90:97-125)
+   type :: b200_cache
+      real(wp), pointer :: cn(:) => null(), qloc(:) => null()
+      real(wp), pointer :: dcndr(:, :, :) => null(), dcndL(:, :, :) => null()
+      real(wp), pointer :: dqlocdr(:, :, :) => null(), dqlocdL(:, :, :) => null()
+   end type b200_cache
+
+contains
+
+!> new_eeq2019_model (src/multicharge/param.f90:46-73) on device `device`
+subroutine new_b200_eeq2019_model(mol, model, error, device)
+   type(structure_type), intent(in) :: mol
+   class(mchrg_model_type), allocatable, intent(out) :: model
+   type(error_type), allocatable, intent(out) :: error
+   integer, intent(in), optional :: device
+   type(b200_model_type), allocatable :: self
+   integer(c_int) :: stat, dev
+
+   dev = 0
+   if (present(device)) dev = device
+   allocate(self)
+   stat = c_context_create(dev, self%ctx)
+   if (stat == 0) stat = c_new_eeq2019_model(self%ctx, int(mol%nid, c_int32_t), int(mol%num, c_int32_t), self%handle)
+   if (stat /= 0) then
+      call fatal_error(error, "mchrg_b200: "//c_message())
+      return
+   end if
+   call move_alloc(self, model)
+end subroutine new_b200_eeq2019_model
+
+subroutine b200_free(self)
+   type(b200_model_type), intent(inout) :: self
+   if (c_associated(self%handle)) call c_model_free(self%handle)
+   self%handle = c_null_ptr
+end subroutine b200_free
+
+function c_message() result(msg)
+   character(len=:), allocatable :: msg
+   character(kind=c_char), pointer :: chars(:)
+   type(c_ptr) :: ptr
+   integer :: i
+   ptr = c_last_error()
+   msg = ""
+   if (.not. c_associated(ptr)) return
+   call c_f_pointer(ptr, chars, [512])
+   do i = 1, 512
+      if (chars(i) == c_null_char) exit
+      msg = msg//chars(i)
+   end do
+end function c_message
+
+function to_c(mol) result(cmol)
+   type(structure_type), intent(in), target :: mol
+   type(c_structure) :: cmol
+   cmol%nat = int(mol%nat, c_int32_t)
+   cmol%nid = int(mol%nid, c_int32_t)
+   cmol%id = c_loc(mol%id)
+   cmol%xyz = c_loc(mol%xyz)
+   cmol%charge = mol%charge
+   cmol%periodic = merge(1_c_int32_t, 0_c_int32_t, spread(any(mol%periodic), 1, 3) .and. mol%periodic)
+   cmol%lattice = 0.0_wp
+   if (any(mol%periodic)) cmol%lattice = reshape(mol%lattice, [9])
+end function to_c
+
+!> c_loc of an optional contiguous array, c_null_ptr when absent
+function opt3(a) result(p)
+   real(wp), intent(in), contiguous, optional, target :: a(:, :, :)
+   type(c_ptr) :: p
+   p = c_null_ptr
+   if (present(a)) p = c_loc(a)
+end function opt3
+function opt2(a) result(p)
+   real(wp), intent(in), contiguous, optional, target :: a(:, :)
+   type(c_ptr) :: p
+   p = c_null_ptr
+   if (present(a)) p = c_loc(a)
+end function opt2
+function opt1(a) result(p)
+   real(wp), intent(in), contiguous, optional, target :: a(:)
+   type(c_ptr) :: p
+   p = c_null_ptr
+   if (present(a)) p = c_loc(a)
+end function opt1
+
+!> mchrg_model_type%solve (model/type.F90:151-292): same dummy arguments, same optional protocol
+subroutine b200_solve(self, mol, error, cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL, &
+   & energy, gradient, sigma, qvec, dqdr, dqdL)
+   class(b200_model_type), intent(in) :: self
+   type(structure_type), intent(in) :: mol
+   type(error_type), allocatable, intent(out) :: error
+   real(wp), intent(in), contiguous, target :: cn(:)
+   real(wp), intent(in), contiguous, target :: qloc(:)
+   real(wp), intent(in), contiguous, optional :: dcndr(:, :, :)
+   real(wp), intent(in), contiguous, optional :: dcndL(:, :, :)
+   real(wp), intent(in), contiguous, optional :: dqlocdr(:, :, :)
+   real(wp), intent(in), contiguous, optional :: dqlocdL(:, :, :)
+   real(wp), intent(inout), contiguous, optional :: energy(:)
+   real(wp), intent(inout), contiguous, optional :: gradient(:, :)
+   real(wp), intent(inout), contiguous, optional :: sigma(:, :)
+   real(wp), intent(out), contiguous, optional :: qvec(:)
+   real(wp), intent(out), contiguous, optional :: dqdr(:, :, :)
+   real(wp), intent(out), contiguous, optional :: dqdL(:, :, :)
+   integer(c_int) :: stat
+
+   stat = c_solve(self%handle, to_c(mol), c_loc(cn), c_loc(qloc), opt3(dcndr), opt3(dcndL), &
+      & opt3(dqlocdr), opt3(dqlocdL), opt1(energy), opt2(gradient), opt2(sigma), opt1(qvec), &
+      & opt3(dqdr), opt3(dqdL))
+   if (stat > 0) then
+      call fatal_error(error, "Bunch-Kaufman factorization failed.")  ! type.F90:223
+   else if (stat < 0) then
+      call fatal_error(error, "mchrg_b200: "//c_message())
+   end if
+end subroutine b200_solve
+
+!> get_charges (src/multicharge/charge.f90:37-77) with the CN evaluated on the device
+subroutine b200_get_charges(model, mol, error, qvec, dqdr, dqdL)
+   type(b200_model_type), intent(in) :: model
+   type(structure_type), intent(in) :: mol
+   type(error_type), allocatable, intent(out) :: error
+   real(wp), intent(out), contiguous, target :: qvec(:)
+   real(wp), intent(out), contiguous, optional :: dqdr(:, :, :)
+   real(wp), intent(out), contiguous, optional :: dqdL(:, :, :)
+   integer(c_int) :: stat
+   stat = c_get_charges(model%handle, to_c(mol), c_loc(qvec), opt3(dqdr), opt3(dqdL))
+   if (stat > 0) then
+      call fatal_error(error, "Bunch-Kaufman factorization failed.")
+   else if (stat < 0) then
+      call fatal_error(error, "mchrg_b200: "//c_message())
+   end if
+end subroutine b200_get_charges
+
+subroutine b200_update(self, mol, cache, cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL)
+   class(b200_model_type), intent(in) :: self
+   type(structure_type), intent(in) :: mol
+   type(cache_container), intent(inout) :: cache
+   real(wp), intent(in), target :: cn(:)
+   real(wp), intent(in), optional, target :: qloc(:)
+   real(wp), intent(in), optional, target :: dcndr(:, :, :)
+   real(wp), intent(in), optional, target :: dcndL(:, :, :)
+   real(wp), intent(in), optional, target :: dqlocdr(:, :, :)
+   real(wp), intent(in), optional, target :: dqlocdL(:, :, :)
+   type(b200_cache), allocatable :: tmp
+   allocate(tmp)
+   tmp%cn => cn
+   if (present(qloc)) tmp%qloc => qloc
+   if (present(dcndr)) tmp%dcndr => dcndr
+   if (present(dcndL)) tmp%dcndL => dcndL
+   if (present(dqlocdr)) tmp%dqlocdr => dqlocdr
+   if (present(dqlocdL)) tmp%dqlocdL => dqlocdL
+   if (allocated(cache%raw)) deallocate(cache%raw)
+   call move_alloc(tmp, cache%raw)
+end subroutine b200_update
+
+function view(cache) result(ptr)
+   type(cache_container), target, intent(inout) :: cache
+   type(b200_cache), pointer :: ptr
+   nullify(ptr)
+   select type(target => cache%raw)
+   type is (b200_cache)
+      ptr => target
+   end select
+end function view
+
+function p1(a) result(p)
+   real(wp), pointer, intent(in) :: a(:)
+   type(c_ptr) :: p
+   p = c_null_ptr
+   if (associated(a)) p = c_loc(a)
+end function p1
+function p3(a) result(p)
+   real(wp), pointer, intent(in) :: a(:, :, :)
+   type(c_ptr) :: p
+   p = c_null_ptr
+   if (associated(a)) p = c_loc(a)
+end function p3
+
+subroutine b200_get_xvec(self, mol, cache, xvec)
+   class(b200_model_type), intent(in) :: self
+   type(structure_type), intent(in) :: mol
+   type(cache_container), intent(inout) :: cache
+   real(wp), intent(out), target :: xvec(:)
+   type(b200_cache), pointer :: c
+   integer(c_int) :: stat
+   c => view(cache)
+   stat = c_get_xvec(self%handle, to_c(mol), p1(c%cn), p1(c%qloc), c_loc(xvec))
+   if (stat /= 0) error stop "mchrg_b200: get_xvec failed"
+end subroutine b200_get_xvec
+
+subroutine b200_get_xvec_derivs(self, mol, cache, dxdr, dxdL)
+   class(b200_model_type), intent(in) :: self
+   type(structure_type), intent(in) :: mol
+   type(cache_container), intent(inout) :: cache
+   real(wp), intent(out), contiguous, target :: dxdr(:, :, :)
+   real(wp), intent(out), contiguous, target :: dxdL(:, :, :)
+   type(b200_cache), pointer :: c
+   integer(c_int) :: stat
+   c => view(cache)
+   stat = c_get_xvec_derivs(self%handle, to_c(mol), p1(c%cn), p1(c%qloc), p3(c%dcndr), p3(c%dcndL), &
+      & p3(c%dqlocdr), p3(c%dqlocdL), c_loc(dxdr), c_loc(dxdL))
+   if (stat /= 0) error stop "mchrg_b200: get_xvec_derivs failed"
+end subroutine b200_get_xvec_derivs
+
+subroutine b200_get_coulomb_matrix(self, mol, cache, amat)
+   class(b200_model_type), intent(in) :: self
+   type(structure_type), intent(in) :: mol
+   type(cache_container), intent(inout) :: cache
+   real(wp), intent(out), target :: amat(:, :)
+   type(b200_cache), pointer :: c
+   integer(c_int) :: stat
+   c => view(cache)
+   stat = c_get_coulomb_matrix(self%handle, to_c(mol), p1(c%cn), p1(c%qloc), c_loc(amat))
+   if (stat /= 0) error stop "mchrg_b200: get_coulomb_matrix failed"
+end subroutine b200_get_coulomb_matrix
+
+subroutine b200_get_coulomb_derivs(self, mol, cache, qvec, dadr, dadL, atrace)
+   class(b200_model_type), intent(in) :: self
+   type(structure_type), intent(in) :: mol
+   type(cache_container), intent(inout) :: cache
+   real(wp), intent(in), target :: qvec(:)
+   real(wp), intent(out), target :: dadr(:, :, :), dadL(:, :, :), atrace(:, :)
+   type(b200_cache), pointer :: c
+   integer(c_int) :: stat
+   c => view(cache)
+   stat = c_get_coulomb_derivs(self%handle, to_c(mol), p1(c%cn), p1(c%qloc), p3(c%dcndr), p3(c%dcndL), &
+      & p3(c%dqlocdr), p3(c%dqlocdL), c_loc(qvec), c_loc(dadr), c_loc(dadL), c_loc(atrace))
+   if (stat /= 0) error stop "mchrg_b200: get_coulomb_derivs failed"
+end subroutine b200_get_coulomb_derivs
+
+end module mchrg_b200_shim
