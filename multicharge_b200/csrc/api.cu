@@ -17,6 +17,7 @@
 
 #include "dense.cuh"
 #include "eeq.cuh"
+#include "eeq_pbc.cuh"
 #include "lattice.hpp"
 #include "param_tables.inc"
 
@@ -178,6 +179,27 @@ __global__ void xvec_derivs_kernel(int nat, const double* __restrict__ thalf, co
    }
 }
 
+// amat(nat+1, nat+1) <- J (padded work matrix) + constraint border (eeq.f90:303-305)
+__global__ void border_copy_kernel(int nat, const double* __restrict__ W, int64_t ldw, double* __restrict__ amat) {
+   const int64_t nd = nat + 1;
+   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t c = blockIdx.y;
+   if (r >= nd || c >= nd) return;
+   double v;
+   if (r < nat && c < nat) v = W[r + c * ldw];
+   else v = (r == nat && c == nat) ? 0.0 : 1.0;
+   amat[r + c * nd] = v;
+}
+
+// dadr(3, nat, nat+1) <- off-diagonal blocks of the padded B; diagonal blocks and last column zero
+__global__ void dadr_copy_kernel(int nat, const double* __restrict__ B, int64_t ldb, double* __restrict__ dadr) {
+   const int64_t n3 = 3 * (int64_t)nat;
+   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t k = blockIdx.y;
+   if (r >= n3 || k > nat) return;
+   dadr[r + k * n3] = (k < nat && r / 3 != k) ? B[r + k * ldb] : 0.0;
+}
+
 __global__ void fill_kernel(int64_t n, double v, double* __restrict__ p) {
    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (i < n) p[i] = v;
@@ -220,15 +242,25 @@ static DevMol stage_mol(mchrg_b200_context* ctx, const mchrg_b200_structure* mol
    return d;
 }
 
+// releases the periodic setup on every exit path
+struct PbcScope {
+   PbcHost host;
+   PbcWork work;
+   bool on = false;
+   ~PbcScope() {
+      if (on) pbc_end(work);
+   }
+};
+
 // the EEQ2019 solve on device arrays; returns LAPACK-style info (0 ok, > 0 failed pivot)
 static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, const AtomPar& ap, const SolveIO& io) {
    mchrg_b200_context* ctx = model->ctx;
-   if (mol.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ solve is not available in this build");
    const int nat = mol.nat;
    const int64_t npad = round_up(nat, TILE);
    const bool dcn = io.dcndr && io.dcndL;
    const bool grad = io.gradient && io.sigma && dcn;
    const bool cpq = io.dqdr && io.dqdL && dcn;
+   const bool pbc = mol.periodic;
 
    double* xvec = ctx->alloc<double>(nat + 1);
    double* thalf = ctx->alloc<double>(nat);
@@ -238,7 +270,19 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
    double* W = ctx->alloc<double>((size_t)npad * npad);
    double* dinv = ctx->alloc<double>((size_t)npad * TILE);
    int* info = ctx->alloc_zero<int>(1);
-   eeq_amat_0d(ctx, mol, ap.rad, ap.eta, W, npad, /*border=*/false, npad);
+   PbcScope ps;
+   double* Jc = nullptr;  // periodic: copy of J for the energy (type.F90:257-259)
+   if (pbc) {
+      pbc_begin(ctx, mol, ps.host, ps.work);
+      ps.on = true;
+      pbc_amat(ctx, mol, ap.rad, ap.eta, ps.work, W);
+      if (io.energy) {
+         Jc = ctx->alloc<double>((size_t)npad * npad);
+         MCHRG_CUDA(cudaMemcpyAsync(Jc, W, (size_t)npad * npad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+   } else {
+      eeq_amat_0d(ctx, mol, ap.rad, ap.eta, W, npad, /*border=*/false, npad);
+   }
    dpotrf_padded(ctx, npad, W, npad, dinv, info);
    int* h_info = static_cast<int*>(ctx->pinned_buf(sizeof(int)));
    MCHRG_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -256,20 +300,25 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
       double* jq = io.energy ? ctx->alloc<double>(nat) : nullptr;
       double* atrace = (grad || cpq) ? ctx->alloc<double>((size_t)3 * nat) : nullptr;
       double* dadL = (grad || cpq) ? ctx->alloc<double>((size_t)9 * nat) : nullptr;
-      eeq_pair_rows_0d(ctx, mol, ap.rad, ap.eta, vrhs, jq, atrace, dadL);
+      double* Bm = nullptr;
+      double* bz = nullptr;
+      int64_t mp = 0;
+      if (cpq) {
+         mp = round_up(3 * (int64_t)nat + 9, TILE);
+         Bm = ctx->alloc_zero<double>((size_t)mp * npad);
+         bz = ctx->alloc_zero<double>((size_t)mp);
+      }
+      if (pbc) {
+         if (io.energy) pbc_symv(ctx, nat, Jc, npad, vrhs, jq);
+         if (grad || cpq) pbc_derivs(ctx, mol, ap.rad, vrhs, ps.work, Bm, mp, mp, atrace, dadL);
+      } else {
+         eeq_pair_rows_0d(ctx, mol, ap.rad, ap.eta, vrhs, jq, atrace, dadL);
+      }
       if (io.energy) MCHRG_LAUNCH(ctx, energy_kernel, (nat + 255) / 256, 256, 0, nat, vrhs, jq, xvec, io.energy);
 
       if (grad || cpq) {
          double* gradx = grad ? ctx->alloc_zero<double>((size_t)3 * nat) : nullptr;
-         double* Bm = nullptr;
-         double* bz = nullptr;
-         int64_t mp = 0;
-         if (cpq) {
-            mp = round_up(3 * (int64_t)nat + 9, TILE);
-            Bm = ctx->alloc_zero<double>((size_t)mp * npad);
-            bz = ctx->alloc_zero<double>((size_t)mp);
-         }
-         eeq_build_b_0d(ctx, mol, ap.rad, vrhs, atrace, thalf, io.dcndr, Bm, mp, gradx, zvec, bz);
+         eeq_build_b_0d(ctx, mol, ap.rad, vrhs, atrace, thalf, io.dcndr, Bm, mp, gradx, zvec, bz, pbc && cpq);
          if (grad) {
             MCHRG_LAUNCH(ctx, gradient_kernel, (3 * nat + 255) / 256, 256, 0, nat, vrhs, atrace, gradx, io.gradient);
             MCHRG_LAUNCH(ctx, sigma_kernel, 1, 288, 0, nat, vrhs, dadL, thalf, io.dcndL, io.sigma);
@@ -478,10 +527,21 @@ int mchrg_b200_get_coulomb_matrix(const mchrg_b200_model* model, const mchrg_b20
       if (!amat) fail(MCHRG_B200_ERR_ARG, "get_coulomb_matrix: amat is required");
       if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "EEQ-BC get_coulomb_matrix is not available in this build");
       DevMol d = stage_mol(ctx, mol);
-      if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic get_coulomb_matrix is not available in this build");
       const size_t nd = (size_t)d.nat + 1;
       AtomPar ap = gather_eeq(model, d);
-      eeq_amat_0d(ctx, d, ap.rad, ap.eta, ctx->out(amat, nd * nd), (int64_t)nd, true, 0);
+      double* out = ctx->out(amat, nd * nd);
+      if (d.periodic) {
+         PbcScope ps;
+         pbc_begin(ctx, d, ps.host, ps.work);
+         ps.on = true;
+         const int64_t npad = ps.work.npad;
+         double* W = ctx->alloc<double>((size_t)npad * npad);
+         pbc_amat(ctx, d, ap.rad, ap.eta, ps.work, W);
+         MCHRG_LAUNCH(ctx, border_copy_kernel, dim3((unsigned)((nd + 255) / 256), (unsigned)nd), 256, 0, d.nat, W, npad, out);
+         ctx->finish();  // host setup arrays of `ps` are consumed by async copies
+      } else {
+         eeq_amat_0d(ctx, d, ap.rad, ap.eta, out, (int64_t)nd, true, 0);
+      }
       return 0;
    });
 }
@@ -496,7 +556,6 @@ int mchrg_b200_get_coulomb_derivs(const mchrg_b200_model* model, const mchrg_b20
       if (!qvec || !dadr || !dadL || !atrace) fail(MCHRG_B200_ERR_ARG, "get_coulomb_derivs: missing argument");
       if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "EEQ-BC get_coulomb_derivs is not available in this build");
       DevMol d = stage_mol(ctx, mol);
-      if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic get_coulomb_derivs is not available in this build");
       const size_t n = d.nat;
       AtomPar ap = gather_eeq(model, d);
       const double* q = ctx->in(qvec, n);
@@ -506,8 +565,20 @@ int mchrg_b200_get_coulomb_derivs(const mchrg_b200_model* model, const mchrg_b20
       // last column (the constraint) is zero in both arrays (eeq.f90:388-389)
       MCHRG_CUDA(cudaMemsetAsync(d_dadr + 3 * n * n, 0, 3 * n * sizeof(double), ctx->stream));
       MCHRG_CUDA(cudaMemsetAsync(d_dadL + 9 * n, 0, 9 * sizeof(double), ctx->stream));
-      eeq_pair_rows_0d(ctx, d, ap.rad, ap.eta, q, nullptr, d_atr, d_dadL);
-      eeq_build_b_0d(ctx, d, ap.rad, q, nullptr, nullptr, nullptr, d_dadr, 3 * (int64_t)n, nullptr, nullptr, nullptr);
+      if (d.periodic) {
+         PbcScope ps;
+         pbc_begin(ctx, d, ps.host, ps.work);
+         ps.on = true;
+         const int64_t npad = ps.work.npad, mp = round_up(3 * (int64_t)n + 9, TILE);
+         double* Bm = ctx->alloc_zero<double>((size_t)mp * npad);
+         pbc_derivs(ctx, d, ap.rad, q, ps.work, Bm, mp, mp, d_atr, d_dadL);
+         MCHRG_LAUNCH(ctx, dadr_copy_kernel, dim3((unsigned)((3 * n + 255) / 256), (unsigned)(n + 1)), 256, 0, d.nat, Bm, mp,
+                      d_dadr);
+         ctx->finish();
+      } else {
+         eeq_pair_rows_0d(ctx, d, ap.rad, ap.eta, q, nullptr, d_atr, d_dadL);
+         eeq_build_b_0d(ctx, d, ap.rad, q, nullptr, nullptr, nullptr, d_dadr, 3 * (int64_t)n, nullptr, nullptr, nullptr);
+      }
       return 0;
    });
 }

@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const doubl
                                                             const double* __restrict__ thalf,
                                                             const double* __restrict__ dcndr, double* __restrict__ Bout,
                                                             int64_t ldb, double* __restrict__ gradx,
-                                                            const double* __restrict__ zvec, double* __restrict__ bz) {
+                                                            const double* __restrict__ zvec, double* __restrict__ bz,
+                                                            int pair_in_b) {
    __shared__ double sk[BB_KCHUNK][8];  // x, y, z, rad^2, thalf, thalf*q, z, unused
    const int j = blockIdx.x * blockDim.x + threadIdx.x;
    const int k0 = blockIdx.y * BB_KCHUNK;
@@ -309,12 +310,18 @@ __global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const doubl
    const double xj = xyz[3 * j], yj = xyz[3 * j + 1], zj = xyz[3 * j + 2];
    const double rj2 = rad[j] * rad[j], qj = q[j];
    double gx[3] = {0.0, 0.0, 0.0}, uz[3] = {0.0, 0.0, 0.0};
+   const bool need_pair = (Bout != nullptr) || (bz != nullptr);
    for (int kk = 0; kk < kn; ++kk) {
       const int k = k0 + kk;
       double b0, b1, b2;
       if (k == j) {
          b0 = b1 = b2 = 0.0;
          if (atrace) { b0 = atrace[3 * j]; b1 = atrace[3 * j + 1]; b2 = atrace[3 * j + 2]; }
+      } else if (pair_in_b) {  // periodic: the pair term was written by the Ewald kernels
+         const double* o = Bout + (size_t)k * ldb + 3 * j;
+         b0 = o[0]; b1 = o[1]; b2 = o[2];
+      } else if (!need_pair) {
+         b0 = b1 = b2 = 0.0;
       } else {
          // dadr(:, j, k) = dtmp (r_j - r_k) q_j      (eeq.f90:412-413 for both orderings of the pair)
          const double vx = xj - sk[kk][0], vy = yj - sk[kk][1], vz = zj - sk[kk][2];
@@ -351,10 +358,10 @@ __global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const doubl
 
 void eeq_build_b_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q,
                     const double* atrace, const double* thalf, const double* dcndr, double* Bout, int64_t ldb,
-                    double* gradx, const double* zvec, double* bz) {
+                    double* gradx, const double* zvec, double* bz, bool pair_in_b) {
    dim3 grid((unsigned)((mol.nat + 127) / 128), (unsigned)((mol.nat + BB_KCHUNK - 1) / BB_KCHUNK));
    MCHRG_LAUNCH(ctx, eeq_build_b0d_kernel, grid, 128, 0, mol.nat, mol.xyz, rad_a, q, atrace, thalf, dcndr, Bout, ldb,
-                gradx, zvec, bz);
+                gradx, zvec, bz, pair_in_b ? 1 : 0);
 }
 
 }  // namespace mchrg

@@ -36,8 +36,10 @@ void eeq_pair_rows_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* 
 //   gradx[3j+c] += sum_k thalf_k q_k dcndr(c,j,k)      (the dxdr*q term of type.F90:278)
 //   bz[3j+c]    += sum_k B(3j+c, k) zvec_k             (rank-one Schur correction of dq/dr)
 // dcndr may be nullptr (pure dadr, get_coulomb_derivs); Bout may be nullptr (gradient only).
+// pair_in_b: the off-diagonal pair terms are already stored in Bout (periodic path) and are
+// updated in place instead of being evaluated from the non-periodic pair formula.
 void eeq_build_b_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q,
                     const double* atrace, const double* thalf, const double* dcndr, double* Bout, int64_t ldb,
-                    double* gradx, const double* zvec, double* bz);
+                    double* gradx, const double* zvec, double* bz, bool pair_in_b = false);
 
 }  // namespace mchrg

@@ -1,0 +1,466 @@
+// Periodic EEQ2019 on the device: Wigner-Seitz images on the fly, Ewald real-space lattice sums
+// per unique pair, reciprocal space as a G-vector factorisation (model/eeq.f90:244-352, 429-570;
+// wignerseitz.f90:40-117; model/type.F90:131-149).
+//
+// Real space: for every unique pair (i > j) the WSC images are re-derived from the 27 candidate
+// translations (no N^2 x 27 index array in HBM) and the 125-term direct sums are evaluated once;
+// both matrix entries / both dadr blocks / both rows' reductions are fed from that one evaluation.
+// Reciprocal space: the reference evaluates sum_G w_G cos(G.(r_j - r_i + T)) per pair and image.
+// T is a lattice vector, so G.T is a multiple of 2 pi and cos(G.(r_j - r_i)) = c_i c_j + s_i s_j with
+// c_i = cos(G.r_i), s_i = sin(G.r_i): the N x N reciprocal matrix is Phi W Phi^T (one DMMA GEMM with
+// K = 248 -> 256), the dadr block is Psi Phi^T, and all row reductions ((Jq)_i, atrace_i, dadL_i)
+// collapse to O(N * 124) sums over the structure factors  C_G = sum_b q_b c_b, S_G = sum_b q_b s_b.
+#include "dense.cuh"
+#include "eeq.cuh"
+#include "eeq_pbc.cuh"
+#include <cfloat>
+
+#include "lattice.hpp"
+
+namespace mchrg {
+
+#define SQRTPI 1.77245385090551602729816748334114518
+#define SQRT2PI 0.797884560802865355879892119868763737
+#define EPS_SQRT 1.4901161193847656e-08 /* sqrt(epsilon(1.0_wp)): eeq.f90:58, wignerseitz.f90:33 */
+#define WSC_TOL 0.01                    /* wignerseitz.f90:36 */
+// beyond this argument erf() is 1 to double precision and exp(-x^2) < 5e-19: terms that cannot
+// change any sum at the 1e-16 level are skipped (exact for the matrix, < 1e-18 relative for derivatives)
+#define PRUNE_ARG 6.5
+
+constexpr int NDT = 125, NRT = 124, KREC = 256;
+
+__device__ __forceinline__ double warp_sum_p(double v) {
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+   return v;
+}
+
+// get_pairs (wignerseitz.f90:75-117) for vecw = r_i - r_j: bit p of the result is set when the p-th
+// image that survives the r2 < thr skip lies within tol of the minimum.  The reference later uses
+// that COMPACTED position p as an index into the full translation list (eeq.f90:276,287); callers
+// reproduce this by reading wtrans[p].
+__device__ __forceinline__ unsigned wsc_select(const double* __restrict__ wt, int nw, double vx, double vy,
+                                               double vz) {
+   double dmin = 1.0e300;
+   for (int itr = 0; itr < nw; ++itr) {
+      const double x = vx - wt[3 * itr], y = vy - wt[3 * itr + 1], z = vz - wt[3 * itr + 2];
+      const double r2 = x * x + y * y + z * z;
+      if (r2 < EPS_SQRT) continue;
+      dmin = fmin(dmin, r2);
+   }
+   unsigned mask = 0;
+   int p = 0;
+   for (int itr = 0; itr < nw; ++itr) {
+      const double x = vx - wt[3 * itr], y = vy - wt[3 * itr + 1], z = vz - wt[3 * itr + 2];
+      const double r2 = x * x + y * y + z * z;
+      if (r2 < EPS_SQRT) continue;
+      if (fabs(r2 - dmin) <= WSC_TOL) mask |= 1u << p;
+      ++p;
+   }
+   return mask;
+}
+
+// get_amat_dir_3d (eeq.f90:309-329)
+__device__ __forceinline__ double dir_amat(const double* __restrict__ dt, double vx, double vy, double vz,
+                                           double gam, double alp) {
+   double acc = 0.0;
+   for (int itr = 0; itr < NDT; ++itr) {
+      const double x = vx + dt[3 * itr], y = vy + dt[3 * itr + 1], z = vz + dt[3 * itr + 2];
+      const double r1 = sqrt(x * x + y * y + z * z);
+      if (r1 < EPS_SQRT) continue;
+      if (gam * r1 > PRUNE_ARG && alp * r1 > PRUNE_ARG) continue;
+      acc += erf(gam * r1) / r1 - erf(alp * r1) / r1;
+   }
+   return acc;
+}
+
+// get_damat_dir_3d (eeq.f90:510-538): dg(3), ds as xx, xy, xz, yy, yz, zz
+__device__ __forceinline__ void dir_damat(const double* __restrict__ dt, double vx, double vy, double vz,
+                                          double gam, double alp, double* g, double* s) {
+   const double gam2 = gam * gam, alp2 = alp * alp;
+   for (int itr = 0; itr < NDT; ++itr) {
+      const double x = vx + dt[3 * itr], y = vy + dt[3 * itr + 1], z = vz + dt[3 * itr + 2];
+      const double r2 = x * x + y * y + z * z;
+      const double r1 = sqrt(r2);
+      if (r1 < EPS_SQRT) continue;
+      if (gam * r1 > PRUNE_ARG && alp * r1 > PRUNE_ARG) continue;
+      const double gtmp = +2 * gam * exp(-r2 * gam2) / (SQRTPI * r2) - erf(r1 * gam) / (r2 * r1);
+      const double atmp = -2 * alp * exp(-r2 * alp2) / (SQRTPI * r2) + erf(r1 * alp) / (r2 * r1);
+      const double f = gtmp + atmp;
+      g[0] += f * x; g[1] += f * y; g[2] += f * z;
+      s[0] += f * x * x; s[1] += f * x * y; s[2] += f * x * z;
+      s[3] += f * y * y; s[4] += f * y * z; s[5] += f * z * z;
+   }
+}
+
+struct PbcDev {
+   const double* wtrans;  // WSC candidate translations [3 * nw]
+   int nw;
+   const double* dtrans;  // [3 * 125]
+   const double* rtrans;  // [3 * 124]
+   const double* rcoef;   // [124]  4 pi / vol * exp(-g2 / (4 alpha^2)) / g2   (0 where g2 < eps)
+   double alpha;
+};
+
+// ---------------------------------------------------------------------------------------------
+// phases: Phi(a, G) = cos(G.r_a), Phi(a, 124 + G) = sin(G.r_a); PhiW = Phi * coef; padding zero
+// ---------------------------------------------------------------------------------------------
+__global__ void pbc_phase_kernel(int nat, int64_t npad, const double* __restrict__ xyz, PbcDev pb,
+                                 double* __restrict__ Phi, double* __restrict__ PhiW) {
+   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int col = blockIdx.y;  // 0..255
+   if (a >= npad) return;
+   double v = 0.0, w = 0.0;
+   if (a < nat && col < 2 * NRT) {
+      const int gidx = col % NRT;
+      const double* gv = pb.rtrans + 3 * gidx;
+      const double ph = gv[0] * xyz[3 * a] + gv[1] * xyz[3 * a + 1] + gv[2] * xyz[3 * a + 2];
+      v = (col < NRT) ? cos(ph) : sin(ph);
+      w = v * pb.rcoef[gidx];
+   }
+   Phi[a + (int64_t)col * npad] = v;
+   if (PhiW) PhiW[a + (int64_t)col * npad] = w;
+}
+
+// structure factors SF[col] = sum_b q_b Phi(b, col); one warp per column
+__global__ void __launch_bounds__(256) pbc_sfac_kernel(int nat, int64_t npad, const double* __restrict__ Phi,
+                                                       const double* __restrict__ q, double* __restrict__ sf) {
+   const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   const int lane = threadIdx.x & 31;
+   if (col >= KREC) return;
+   double acc = 0.0;
+   for (int b = lane; b < nat; b += 32) acc = fma(q[b], Phi[b + (int64_t)col * npad], acc);
+   acc = warp_sum_p(acc);
+   if (lane == 0) sf[col] = acc;
+}
+
+// reciprocal-space row sums from the structure factors: atrace_a, dadL_a (written, not accumulated)
+__global__ void pbc_rec_rows_kernel(int nat, int64_t npad, const double* __restrict__ Phi,
+                                    const double* __restrict__ sf, PbcDev pb, double* __restrict__ atrace,
+                                    double* __restrict__ dadL) {
+   const int a = blockIdx.x * blockDim.x + threadIdx.x;
+   if (a >= nat) return;
+   const double alp2 = pb.alpha * pb.alpha;
+   double at[3] = {0.0, 0.0, 0.0}, dl[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+   for (int gi = 0; gi < NRT; ++gi) {
+      const double coef = pb.rcoef[gi];
+      if (coef == 0.0) continue;
+      const double gx = pb.rtrans[3 * gi], gy = pb.rtrans[3 * gi + 1], gz = pb.rtrans[3 * gi + 2];
+      const double g2 = gx * gx + gy * gy + gz * gz;
+      const double ca = Phi[a + (int64_t)gi * npad], sa = Phi[a + (int64_t)(NRT + gi) * npad];
+      const double CG = sf[gi], SG = sf[NRT + gi];
+      // sum_b q_b sin(G.(r_a - r_b)) and sum_b q_b cos(G.(r_a - r_b))
+      const double ssum = sa * CG - ca * SG, csum = ca * CG + sa * SG;
+      const double t = -coef * ssum;  // dG_rec = -sin(G.v) etmp G   (eeq.f90:564-565)
+      at[0] += t * gx; at[1] += t * gy; at[2] += t * gz;
+      const double pre = 2.0 / g2 + 0.5 / alp2, u = coef * csum;  // eeq.f90:566-567
+      dl[0] += u * (pre * gx * gx - 1.0); dl[1] += u * (pre * gx * gy); dl[2] += u * (pre * gx * gz);
+      dl[3] += u * (pre * gy * gy - 1.0); dl[4] += u * (pre * gy * gz); dl[5] += u * (pre * gz * gz - 1.0);
+   }
+   atrace[3 * a] = at[0]; atrace[3 * a + 1] = at[1]; atrace[3 * a + 2] = at[2];
+   double* d = dadL + (size_t)9 * a;
+   d[0] = dl[0]; d[1] = dl[1]; d[2] = dl[2];
+   d[3] = dl[1]; d[4] = dl[3]; d[5] = dl[4];
+   d[6] = dl[2]; d[7] = dl[4]; d[8] = dl[5];
+}
+
+// Psi((3j+c), G) = -q_j coef_G G_c s_Gj ; Psi((3j+c), 124+G) = +q_j coef_G G_c c_Gj ; rest zero
+__global__ void pbc_psi_kernel(int nat, int64_t npad, int64_t mp, const double* __restrict__ Phi,
+                               const double* __restrict__ q, PbcDev pb, double* __restrict__ Psi) {
+   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int col = blockIdx.y;
+   if (r >= mp) return;
+   double v = 0.0;
+   if (r < 3 * (int64_t)nat && col < 2 * NRT) {
+      const int j = (int)(r / 3), c = (int)(r % 3), gi = col % NRT;
+      const double f = q[j] * pb.rcoef[gi] * pb.rtrans[3 * gi + c];
+      v = (col < NRT) ? -f * Phi[j + (int64_t)(NRT + gi) * npad] : f * Phi[j + (int64_t)gi * npad];
+   }
+   Psi[r + (int64_t)col * mp] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// real-space pair tiles: 32 x 32 atoms per CTA over the lower block triangle; warp = row i, lane = j
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_coords(int b, int& ti, int& tj) {
+   int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+   while ((int64_t)(r + 1) * (r + 2) / 2 <= b) ++r;
+   while ((int64_t)r * (r + 1) / 2 > b) --r;
+   ti = r;
+   tj = b - r * (r + 1) / 2;
+}
+
+// W(i, j) += direct part (both triangles); W is pre-filled with the reciprocal matrix
+__global__ void __launch_bounds__(256) pbc_amat_tiles_kernel(int nat, const double* __restrict__ xyz,
+                                                             const double* __restrict__ rad, PbcDev pb,
+                                                             double* __restrict__ W, int64_t ld) {
+   __shared__ double sdt[3 * NDT];
+   __shared__ double swt[3 * 27];
+   for (int k = threadIdx.x; k < 3 * NDT; k += blockDim.x) sdt[k] = pb.dtrans[k];
+   for (int k = threadIdx.x; k < 3 * pb.nw; k += blockDim.x) swt[k] = pb.wtrans[k];
+   __syncthreads();
+   int ti, tj;
+   tile_coords(blockIdx.x, ti, tj);
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   const int j = tj * 32 + lane;
+   for (int rr = 0; rr < 4; ++rr) {
+      const int i = ti * 32 + warp + 8 * rr;
+      if (i >= nat || j >= i) continue;  // strictly lower triangle
+      const double vx = xyz[3 * j] - xyz[3 * i], vy = xyz[3 * j + 1] - xyz[3 * i + 1], vz = xyz[3 * j + 2] - xyz[3 * i + 2];
+      const double gam = 1.0 / sqrt(rad[i] * rad[i] + rad[j] * rad[j]);
+      const unsigned mask = wsc_select(swt, pb.nw, -vx, -vy, -vz);  // wsc vec = r_i - r_j
+      const double wsw = 1.0 / (double)__popc(mask);
+      double acc = 0.0;
+      for (unsigned m = mask; m; m &= m - 1) {
+         const int p = __ffs(m) - 1;
+         acc += dir_amat(sdt, vx + swt[3 * p], vy + swt[3 * p + 1], vz + swt[3 * p + 2], gam, pb.alpha) * wsw;
+      }
+      W[i + (int64_t)j * ld] += acc;
+      W[j + (int64_t)i * ld] += acc;
+   }
+}
+
+// diagonal: self images (eeq.f90:284-294); padding rows become the identity
+__global__ void pbc_amat_diag_kernel(int nat, int64_t npad, const double* __restrict__ rad,
+                                     const double* __restrict__ eta, PbcDev pb, double* __restrict__ W, int64_t ld) {
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= npad) return;
+   if (i >= nat) {
+      W[i + i * ld] = 1.0;
+      return;
+   }
+   const double gam = 1.0 / sqrt(2.0 * rad[i] * rad[i]);
+   const unsigned mask = wsc_select(pb.wtrans, pb.nw, 0.0, 0.0, 0.0);
+   const double wsw = 1.0 / (double)__popc(mask);
+   double acc = 0.0;
+   for (unsigned m = mask; m; m &= m - 1) {
+      const int p = __ffs(m) - 1;
+      acc += dir_amat(pb.dtrans, pb.wtrans[3 * p], pb.wtrans[3 * p + 1], pb.wtrans[3 * p + 2], gam, pb.alpha) * wsw;
+   }
+   W[i + i * ld] += acc + eta[i] + SQRT2PI / rad[i] - 2.0 * pb.alpha / SQRTPI;
+}
+
+// derivative tiles: one evaluation of dG, dS per unique pair feeds
+//   B(3j+c, i) = +dG q_j, B(3i+c, j) = -dG q_i        (eeq.f90:482-483)
+//   atrace_i -= dG q_j, atrace_j += dG q_i            (eeq.f90:480-481)
+//   dadL_j += dS q_i, dadL_i += dS q_j                (eeq.f90:484-485)
+__global__ void __launch_bounds__(256) pbc_damat_tiles_kernel(int nat, const double* __restrict__ xyz,
+                                                              const double* __restrict__ rad,
+                                                              const double* __restrict__ q, PbcDev pb,
+                                                              double* __restrict__ B, int64_t ldb,
+                                                              double* __restrict__ atrace, double* __restrict__ dadL) {
+   __shared__ double sdt[3 * NDT];
+   __shared__ double swt[3 * 27];
+   for (int k = threadIdx.x; k < 3 * NDT; k += blockDim.x) sdt[k] = pb.dtrans[k];
+   for (int k = threadIdx.x; k < 3 * pb.nw; k += blockDim.x) swt[k] = pb.wtrans[k];
+   __syncthreads();
+   int ti, tj;
+   tile_coords(blockIdx.x, ti, tj);
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   const int j = tj * 32 + lane;
+   double aj[3] = {0.0, 0.0, 0.0}, lj[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+   const double qj = (j < nat) ? q[j] : 0.0;
+   for (int rr = 0; rr < 4; ++rr) {
+      const int i = ti * 32 + warp + 8 * rr;  // warp-uniform
+      if (i >= nat) continue;
+      double g[3] = {0.0, 0.0, 0.0}, s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      const bool active = (j < i);
+      const double qi = q[i];
+      if (active) {
+         const double vx = xyz[3 * j] - xyz[3 * i], vy = xyz[3 * j + 1] - xyz[3 * i + 1], vz = xyz[3 * j + 2] - xyz[3 * i + 2];
+         const double gam = 1.0 / sqrt(rad[i] * rad[i] + rad[j] * rad[j]);
+         const unsigned mask = wsc_select(swt, pb.nw, -vx, -vy, -vz);
+         const double wsw = 1.0 / (double)__popc(mask);
+         for (unsigned m = mask; m; m &= m - 1) {
+            const int p = __ffs(m) - 1;
+            dir_damat(sdt, vx + swt[3 * p], vy + swt[3 * p + 1], vz + swt[3 * p + 2], gam, pb.alpha, g, s);
+         }
+#pragma unroll
+         for (int c = 0; c < 3; ++c) g[c] *= wsw;
+#pragma unroll
+         for (int c = 0; c < 6; ++c) s[c] *= wsw;
+         if (B) {
+            double* bji = B + (int64_t)i * ldb + 3 * j;  // dadr(:, j, i)
+            double* bij = B + (int64_t)j * ldb + 3 * i;  // dadr(:, i, j)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+               bji[c] = g[c] * qj;
+               bij[c] = -g[c] * qi;
+            }
+         }
+#pragma unroll
+         for (int c = 0; c < 3; ++c) aj[c] += g[c] * qi;
+#pragma unroll
+         for (int c = 0; c < 6; ++c) lj[c] += s[c] * qi;
+      }
+      // row-i reductions over the lanes
+      double ri[9];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ri[c] = warp_sum_p(active ? -g[c] * qj : 0.0);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) ri[3 + c] = warp_sum_p(active ? s[c] * qj : 0.0);
+      if (lane == 0) {
+#pragma unroll
+         for (int c = 0; c < 3; ++c) atomicAdd(atrace + 3 * i + c, ri[c]);
+         double* d = dadL + (size_t)9 * i;
+         atomicAdd(d + 0, ri[3]); atomicAdd(d + 1, ri[4]); atomicAdd(d + 2, ri[5]);
+         atomicAdd(d + 3, ri[4]); atomicAdd(d + 4, ri[6]); atomicAdd(d + 5, ri[7]);
+         atomicAdd(d + 6, ri[5]); atomicAdd(d + 7, ri[7]); atomicAdd(d + 8, ri[8]);
+      }
+   }
+   if (j < nat) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+         if (aj[c] != 0.0) atomicAdd(atrace + 3 * j + c, aj[c]);
+      if (lj[0] != 0.0 || lj[3] != 0.0 || lj[5] != 0.0) {
+         double* d = dadL + (size_t)9 * j;
+         atomicAdd(d + 0, lj[0]); atomicAdd(d + 1, lj[1]); atomicAdd(d + 2, lj[2]);
+         atomicAdd(d + 3, lj[1]); atomicAdd(d + 4, lj[3]); atomicAdd(d + 5, lj[4]);
+         atomicAdd(d + 6, lj[2]); atomicAdd(d + 7, lj[4]); atomicAdd(d + 8, lj[5]);
+      }
+   }
+}
+
+// self-image stress term (eeq.f90:488-497), real-space part: dadL_i += dS_self q_i
+__global__ void pbc_damat_diag_kernel(int nat, const double* __restrict__ rad, const double* __restrict__ q,
+                                      PbcDev pb, double* __restrict__ dadL) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= nat) return;
+   const double gam = 1.0 / sqrt(2.0 * rad[i] * rad[i]);
+   const unsigned mask = wsc_select(pb.wtrans, pb.nw, 0.0, 0.0, 0.0);
+   const double wsw = 1.0 / (double)__popc(mask);
+   double g[3] = {0.0, 0.0, 0.0}, s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+   for (unsigned m = mask; m; m &= m - 1) {
+      const int p = __ffs(m) - 1;
+      dir_damat(pb.dtrans, pb.wtrans[3 * p], pb.wtrans[3 * p + 1], pb.wtrans[3 * p + 2], gam, pb.alpha, g, s);
+   }
+   const double f = wsw * q[i];
+   double* d = dadL + (size_t)9 * i;
+   atomicAdd(d + 0, s[0] * f); atomicAdd(d + 1, s[1] * f); atomicAdd(d + 2, s[2] * f);
+   atomicAdd(d + 3, s[1] * f); atomicAdd(d + 4, s[3] * f); atomicAdd(d + 5, s[4] * f);
+   atomicAdd(d + 6, s[2] * f); atomicAdd(d + 7, s[4] * f); atomicAdd(d + 8, s[5] * f);
+}
+
+// y_i = sum_j A(i, j) x_j for a full symmetric matrix (column-major): thread per row, coalesced
+__global__ void __launch_bounds__(256) symv_full_kernel(int nat, const double* __restrict__ A, int64_t ld,
+                                                        const double* __restrict__ x, double* __restrict__ y) {
+   __shared__ double part[8][32];
+   // CTA = 32 rows x 8 column slices
+   const int r = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+   double acc = 0.0;
+   if (r < nat)
+      for (int j = slice; j < nat; j += 8) acc = fma(A[r + (int64_t)j * ld], x[j], acc);
+   part[slice][threadIdx.x & 31] = acc;
+   __syncthreads();
+   if (slice == 0 && r < nat) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += part[k][threadIdx.x & 31];
+      y[r] = s;
+   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static PbcDev upload_pbc(mchrg_b200_context* ctx, const DevMol& mol, PbcHost& host) {
+   int periodic[3] = {1, 1, 1};
+   host.wtrans = lat::points_cutoff(periodic, mol.lattice, std::sqrt(DBL_EPSILON));  // wignerseitz.f90:53
+   if (host.wtrans.size() / 3 > 27) fail(MCHRG_B200_ERR_ARG, "unexpected number of Wigner-Seitz translations");
+   host.dtrans = lat::dir_trans(mol.lattice);
+   host.rtrans = lat::rec_trans(mol.lattice);
+   host.alpha = lat::ewald_alpha(mol.lattice);
+   const double vol = std::fabs(lat::det3(mol.lattice));
+   const double pi = 3.14159265358979323846264338327950288;
+   const double fac = 4.0 * pi / vol;
+   host.rcoef.assign(NRT, 0.0);
+   for (int g = 0; g < NRT; ++g) {
+      const double* v = &host.rtrans[3 * g];
+      const double g2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+      if (g2 < std::sqrt(DBL_EPSILON)) continue;  // eeq.f90:347
+      host.rcoef[g] = fac * std::exp(-0.25 * g2 / (host.alpha * host.alpha)) / g2;
+   }
+   host.packed.clear();
+   host.packed.insert(host.packed.end(), host.wtrans.begin(), host.wtrans.end());
+   host.packed.resize(81, 0.0);
+   host.packed.insert(host.packed.end(), host.dtrans.begin(), host.dtrans.end());
+   host.packed.insert(host.packed.end(), host.rtrans.begin(), host.rtrans.end());
+   host.packed.insert(host.packed.end(), host.rcoef.begin(), host.rcoef.end());
+   double* d = ctx->alloc<double>(host.packed.size());
+   MCHRG_CUDA(cudaMemcpyAsync(d, host.packed.data(), host.packed.size() * sizeof(double), cudaMemcpyHostToDevice,
+                              ctx->stream));
+   PbcDev pb;
+   pb.wtrans = d;
+   pb.nw = (int)(host.wtrans.size() / 3);
+   pb.dtrans = d + 81;
+   pb.rtrans = pb.dtrans + 3 * NDT;
+   pb.rcoef = pb.rtrans + 3 * NRT;
+   pb.alpha = host.alpha;
+   return pb;
+}
+
+struct PbcState {
+   PbcDev pb;
+   double* Phi;
+};
+
+void pbc_begin(mchrg_b200_context* ctx, const DevMol& mol, PbcHost& host, PbcWork& work) {
+   const int64_t npad = round_up(mol.nat, TILE);
+   auto* st = new PbcState();
+   st->pb = upload_pbc(ctx, mol, host);
+   st->Phi = ctx->alloc<double>((size_t)npad * KREC);
+   work.npad = npad;
+   work.state = st;
+}
+
+void pbc_end(PbcWork& work) {
+   delete static_cast<PbcState*>(work.state);
+   work.state = nullptr;
+}
+
+void pbc_amat(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a, PbcWork& work,
+              double* W) {
+   auto* st = static_cast<PbcState*>(work.state);
+   const int64_t npad = work.npad;
+   const int nat = mol.nat;
+   double* PhiW = ctx->alloc<double>((size_t)npad * KREC);
+   dim3 gp((unsigned)((npad + 255) / 256), KREC);
+   MCHRG_LAUNCH(ctx, pbc_phase_kernel, gp, 256, 0, nat, npad, mol.xyz, st->pb, st->Phi, PhiW);
+   dgemm_padded(ctx, true, npad, npad, KREC, 1.0, PhiW, npad, st->Phi, npad, 0.0, W, npad, false);
+   const int nt = (nat + 31) / 32;
+   MCHRG_LAUNCH(ctx, pbc_amat_tiles_kernel, (unsigned)(nt * (nt + 1) / 2), 256, 0, nat, mol.xyz, rad_a, st->pb, W, npad);
+   MCHRG_LAUNCH(ctx, pbc_amat_diag_kernel, (unsigned)((npad + 127) / 128), 128, 0, nat, npad, rad_a, eta_a, st->pb, W,
+                npad);
+   work.phase_ready = true;
+}
+
+void pbc_symv(mchrg_b200_context* ctx, int nat, const double* A, int64_t ld, const double* x, double* y) {
+   MCHRG_LAUNCH(ctx, symv_full_kernel, (unsigned)((nat + 31) / 32), 256, 0, nat, A, ld, x, y);
+}
+
+void pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q, PbcWork& work,
+                double* B, int64_t ldb, int64_t mp, double* atrace, double* dadL) {
+   auto* st = static_cast<PbcState*>(work.state);
+   const int64_t npad = work.npad;
+   const int nat = mol.nat;
+   if (!work.phase_ready) {
+      dim3 gp((unsigned)((npad + 255) / 256), KREC);
+      MCHRG_LAUNCH(ctx, pbc_phase_kernel, gp, 256, 0, nat, npad, mol.xyz, st->pb, st->Phi, (double*)nullptr);
+   }
+   double* sf = ctx->alloc<double>(KREC);
+   MCHRG_LAUNCH(ctx, pbc_sfac_kernel, KREC / 8, 256, 0, nat, npad, st->Phi, q, sf);
+   MCHRG_LAUNCH(ctx, pbc_rec_rows_kernel, (unsigned)((nat + 127) / 128), 128, 0, nat, npad, st->Phi, sf, st->pb, atrace,
+                dadL);
+   MCHRG_LAUNCH(ctx, pbc_damat_diag_kernel, (unsigned)((nat + 127) / 128), 128, 0, nat, rad_a, q, st->pb, dadL);
+   const int nt = (nat + 31) / 32;
+   MCHRG_LAUNCH(ctx, pbc_damat_tiles_kernel, (unsigned)(nt * (nt + 1) / 2), 256, 0, nat, mol.xyz, rad_a, q, st->pb, B, ldb,
+                atrace, dadL);
+   if (B) {
+      double* Psi = ctx->alloc<double>((size_t)mp * KREC);
+      dim3 gs((unsigned)((mp + 255) / 256), KREC);
+      MCHRG_LAUNCH(ctx, pbc_psi_kernel, gs, 256, 0, nat, npad, mp, st->Phi, q, st->pb, Psi);
+      dgemm_padded(ctx, true, mp, npad, KREC, 1.0, Psi, mp, st->Phi, npad, 1.0, B, ldb, false);
+   }
+}
+
+}  // namespace mchrg

@@ -1,0 +1,38 @@
+// Periodic EEQ2019 (Ewald) device pieces -- see eeq_pbc.cu.
+#pragma once
+#include <vector>
+
+#include "model.cuh"
+
+namespace mchrg {
+
+// host copies of the per-call periodic setup (kept alive until the stream has consumed them)
+struct PbcHost {
+   std::vector<double> wtrans, dtrans, rtrans, rcoef, packed;
+   double alpha = 0.0;
+};
+
+struct PbcWork {
+   int64_t npad = 0;
+   void* state = nullptr;     // device-side descriptors (PbcState)
+   bool phase_ready = false;  // Phi filled by pbc_amat
+};
+
+// update() of eeq.f90:119-123 for periodic structures: WSC candidate translations, Ewald alpha,
+// direct / reciprocal translations, G-vector coefficients -> device
+void pbc_begin(mchrg_b200_context* ctx, const DevMol& mol, PbcHost& host, PbcWork& work);
+void pbc_end(PbcWork& work);
+
+// get_amat_3d (eeq.f90:244-307): Coulomb block into W (order work.npad, ld = npad, identity padding)
+void pbc_amat(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a, PbcWork& work,
+              double* W);
+
+// y = A x for a full symmetric column-major matrix
+void pbc_symv(mchrg_b200_context* ctx, int nat, const double* A, int64_t ld, const double* x, double* y);
+
+// get_damat_3d (eeq.f90:429-508): atrace[3 nat], dadL[9 nat] (overwritten) and, when B != nullptr, the
+// off-diagonal blocks dadr(:, j, k) into B (ld = ldb, mp padded rows; B must be zero-initialised)
+void pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q, PbcWork& work,
+                double* B, int64_t ldb, int64_t mp, double* atrace, double* dadL);
+
+}  // namespace mchrg
