@@ -41,7 +41,8 @@ __global__ void rhs_init_kernel(int nat, int64_t npad, const double* __restrict_
 // scal[0] = s = 1^T z, scal[1] = lambda; vrhs[0..nat-1] = q, vrhs[nat] = lambda
 __global__ void __launch_bounds__(1024) schur_charges_kernel(int nat, int64_t npad, const double* __restrict__ R,
                                                              double charge, double* __restrict__ vrhs,
-                                                             double* __restrict__ qvec, double* __restrict__ scal) {
+                                                             double* __restrict__ qvec, double* __restrict__ scal,
+                                                             const double* __restrict__ shift) {
    __shared__ double sy[32], sz[32];
    __shared__ double lam;
    double ay = 0.0, az = 0.0;
@@ -64,10 +65,10 @@ __global__ void __launch_bounds__(1024) schur_charges_kernel(int nat, int64_t np
          ty += sy[w];
          tz += sz[w];
       }
-      lam = (ty - charge) / tz;
+      lam = (ty - charge) / tz;  // multiplier of the (possibly shifted) system
       scal[0] = tz;
-      scal[1] = lam;
-      vrhs[nat] = lam;
+      scal[1] = lam + shift[0] * charge;  // lambda of the reference's unshifted system
+      vrhs[nat] = scal[1];
    }
    __syncthreads();
    const double l = lam;
@@ -200,6 +201,39 @@ __global__ void dadr_copy_kernel(int nat, const double* __restrict__ B, int64_t 
    dadr[r + k * n3] = (k < nat && r / 3 != k) ? B[r + k * ldb] : 0.0;
 }
 
+// ---- rank-one shift of the Coulomb block:  J' = J + mu 1 1^T ---------------------------------
+// The constrained solution q (and the projected inverse J^-1 - z z^T / s that dq/dr needs) is invariant
+// under this shift; only the multiplier moves: lambda = lambda' + mu Q.  Periodic Ewald matrices are
+// indefinite along the constraint vector 1 (the omitted G = 0 term), which the reference's LDL^T
+// tolerates and a Cholesky factorisation does not.
+__global__ void __launch_bounds__(256) matsum_kernel(int nat, const double* __restrict__ W, int64_t ld,
+                                                     double* __restrict__ total) {
+   __shared__ double part[8];
+   const int col = blockIdx.x;
+   double acc = 0.0;
+   for (int r = threadIdx.x; r < nat; r += blockDim.x) acc += W[r + (int64_t)col * ld];
+   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += part[w];
+      atomicAdd(total, s);
+   }
+}
+// sh[0] = mu, sh[1] = 1^T J 1 (input).  first: mu from the Rayleigh quotient rho = 1^T J 1 / N along 1,
+// so that rho + mu N = 1 + |rho| when rho < 0; later calls (retry after a failed pivot) multiply by 8.
+__global__ void shift_update_kernel(int nat, double* __restrict__ sh) {
+   const double rho = sh[1] / (double)nat;
+   if (sh[0] == 0.0) sh[0] = (2.0 * fmax(0.0, -rho) + 1.0) / (double)nat;
+   else sh[0] *= 8.0;
+}
+__global__ void shift_apply_kernel(int nat, double* __restrict__ W, int64_t ld, const double* __restrict__ sh) {
+   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+   const int c = blockIdx.y;
+   if (r < nat && c < nat) W[r + (int64_t)c * ld] += sh[0];
+}
+
 __global__ void fill_kernel(int64_t n, double v, double* __restrict__ p) {
    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (i < n) p[i] = v;
@@ -272,20 +306,41 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
    int* info = ctx->alloc_zero<int>(1);
    PbcScope ps;
    double* Jc = nullptr;  // periodic: copy of J for the energy (type.F90:257-259)
+   double* shift = ctx->alloc_zero<double>(2);  // [0] mu of J' = J + mu 1 1^T, [1] 1^T J 1
    if (pbc) {
       pbc_begin(ctx, mol, ps.host, ps.work);
       ps.on = true;
-      pbc_amat(ctx, mol, ap.rad, ap.eta, ps.work, W);
-      if (io.energy) {
-         Jc = ctx->alloc<double>((size_t)npad * npad);
-         MCHRG_CUDA(cudaMemcpyAsync(Jc, W, (size_t)npad * npad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-      }
-   } else {
-      eeq_amat_0d(ctx, mol, ap.rad, ap.eta, W, npad, /*border=*/false, npad);
    }
-   dpotrf_padded(ctx, npad, W, npad, dinv, info);
+   auto assemble = [&]() {
+      if (pbc) pbc_amat(ctx, mol, ap.rad, ap.eta, ps.work, W);
+      else eeq_amat_0d(ctx, mol, ap.rad, ap.eta, W, npad, /*border=*/false, npad);
+   };
+   auto apply_shift = [&]() {
+      MCHRG_CUDA(cudaMemsetAsync(shift + 1, 0, sizeof(double), ctx->stream));
+      MCHRG_LAUNCH(ctx, matsum_kernel, (unsigned)nat, 256, 0, nat, W, npad, shift + 1);
+      MCHRG_LAUNCH(ctx, shift_update_kernel, 1, 1, 0, nat, shift);
+      MCHRG_LAUNCH(ctx, shift_apply_kernel, dim3((unsigned)((nat + 255) / 256), (unsigned)nat), 256, 0, nat, W, npad, shift);
+   };
+   assemble();
+   if (pbc && io.energy) {
+      Jc = ctx->alloc<double>((size_t)npad * npad);
+      MCHRG_CUDA(cudaMemcpyAsync(Jc, W, (size_t)npad * npad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+   }
+   if (pbc) apply_shift();  // Ewald matrices are indefinite along 1: shift up front
    int* h_info = static_cast<int*>(ctx->pinned_buf(sizeof(int)));
-   MCHRG_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+   for (int attempt = 0;; ++attempt) {
+      dpotrf_padded(ctx, npad, W, npad, dinv, info);
+      MCHRG_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (*h_info == 0) break;
+      if (attempt == 3) {  // not positive definite on the charge-conserving subspace either
+         ctx->copybacks.clear();
+         return *h_info;
+      }
+      MCHRG_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
+      assemble();
+      apply_shift();
+   }
 
    // y = J^-1 x, z = J^-1 1, Schur complement
    double* R = ctx->alloc<double>((size_t)npad * 2);
@@ -293,7 +348,7 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
    dpotrs_vec(ctx, npad, W, npad, dinv, R, npad, 2);
    double* vrhs = ctx->alloc<double>(nat + 1);
    double* scal = ctx->alloc<double>(2);
-   MCHRG_LAUNCH(ctx, schur_charges_kernel, 1, 1024, 0, nat, npad, R, mol.charge, vrhs, io.qvec, scal);
+   MCHRG_LAUNCH(ctx, schur_charges_kernel, 1, 1024, 0, nat, npad, R, mol.charge, vrhs, io.qvec, scal, shift);
    const double* zvec = R + npad;
 
    if (io.energy || grad || cpq) {
@@ -333,7 +388,7 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
       }
    }
    ctx->finish();
-   return *h_info;
+   return 0;
 }
 
 static void check_model(const mchrg_b200_model* model) {
