@@ -329,3 +329,39 @@ def singlepoint_batch(model, offsets, num, xyz, charge, gradient=True, out=None)
         _ptr(out.get("gradient")), _ptr(out["status"]))
     check(rc)
     return out
+
+
+def new_eeqbc_model(mol, chi, rad, eta, kcnchi, kqchi, kqeta, kcnrad, cap, avg_cn, rvdw, rcov, en,
+                    kbc=0.65, cutoff=25.0, cn_exp=2.0, norm_exp=1.0, ctx=None):
+    """new_eeqbc_model (model/eeqbc.f90:100-176); per-species arrays of length mol.nid, rvdw[nid, nid] per
+    species pair (the reference stores the same numbers per atom pair, param.f90:114-115)."""
+    ctx = ctx or default_context()
+    arrs = {k: _f64(v) for k, v in dict(chi=chi, rad=rad, eta=eta, kcnchi=kcnchi, kqchi=kqchi, kqeta=kqeta, cap=cap,
+                                        avg_cn=avg_cn, rcov=rcov, en=en).items()}
+    rvdw = _f64(rvdw)
+    if any(len(a) != mol.nid for a in arrs.values()) or rvdw.shape != (mol.nid, mol.nid):
+        raise ValueError("per-species parameter arrays must have length mol.nid (rvdw: nid x nid)")
+    h = C.c_void_p()
+    check(_lib.load().mchrg_b200_new_eeqbc_model(
+        ctx._h, mol.nid, _ptr(arrs["chi"]), _ptr(arrs["rad"]), _ptr(arrs["eta"]), _ptr(arrs["kcnchi"]),
+        _ptr(arrs["kqchi"]), _ptr(arrs["kqeta"]), float(kcnrad), _ptr(arrs["cap"]), _ptr(arrs["avg_cn"]), _ptr(rvdw),
+        float(kbc), float(cutoff), float(cn_exp), _ptr(arrs["rcov"]), _ptr(arrs["en"]), float(norm_exp), C.byref(h)))
+    return MchrgModel(h, ctx, 2)
+
+
+def new_eeqbc2025_model(mol, rvdw, en_pauling, ctx=None):
+    """new_eeqbc2025_model (param.f90:75-125).  The pairwise D3 vdW radii (get_vdw_rad * autoaa) and the
+    Pauling electronegativities live in mctc-lib and must be supplied: rvdw[nid, nid], en_pauling[nid]."""
+    ctx = ctx or default_context()
+    h = C.c_void_p()
+    num = np.ascontiguousarray(mol.num, dtype=np.int32)
+    rvdw, en = _f64(rvdw), _f64(en_pauling)
+    if rvdw.shape != (mol.nid, mol.nid) or len(en) != mol.nid:
+        raise ValueError("rvdw must be nid x nid and en_pauling of length nid")
+    check(_lib.load().mchrg_b200_new_eeqbc2025_model(ctx._h, mol.nid, _ptr(num), _ptr(rvdw), _ptr(en), C.byref(h)))
+    return MchrgModel(h, ctx, 2)
+
+
+def get_eeqbc_charges(mol, rvdw, en_pauling, grad=False, ctx=None):
+    """get_eeqbc_charges (charge.f90:108-131)."""
+    return get_charges(new_eeqbc2025_model(mol, rvdw, en_pauling, ctx), mol, grad)

@@ -18,6 +18,7 @@
 #include "dense.cuh"
 #include "eeq.cuh"
 #include "eeq_pbc.cuh"
+#include "eeqbc.cuh"
 #include "lattice.hpp"
 #include "param_tables.inc"
 
@@ -276,6 +277,65 @@ static DevMol stage_mol(mchrg_b200_context* ctx, const mchrg_b200_structure* mol
    return d;
 }
 
+// Factorisation + constrained solve shared by both models.
+//   assemble():  (re)build the Coulomb block into W (order npad, identity padding)
+//   pre_shift:   apply the rank-one shift before the first attempt (periodic Ewald matrices)
+// On success: W = L, dinv = inverted diagonal blocks, R(:,1) = z = J'^-1 1, vrhs = [q, lambda], scal = [s, lambda].
+struct Factor {
+   double *W = nullptr, *dinv = nullptr, *R = nullptr, *vrhs = nullptr, *scal = nullptr, *shift = nullptr;
+   int info = 0;
+   const double* z(int64_t npad) const { return R + npad; }
+};
+
+template <class Assemble, class AfterAssemble>
+static Factor factor_solve(mchrg_b200_context* ctx, int nat, int64_t npad, Assemble&& assemble, AfterAssemble&& after_first,
+                           bool pre_shift, const double* xvec, double charge, double* qvec_out) {
+   Factor f;
+   f.W = ctx->alloc<double>((size_t)npad * npad);
+   f.dinv = ctx->alloc<double>((size_t)npad * TILE);
+   int* info = ctx->alloc_zero<int>(1);
+   f.shift = ctx->alloc_zero<double>(2);  // [0] mu of J' = J + mu 1 1^T, [1] 1^T J 1
+   auto apply_shift = [&]() {
+      MCHRG_CUDA(cudaMemsetAsync(f.shift + 1, 0, sizeof(double), ctx->stream));
+      MCHRG_LAUNCH(ctx, matsum_kernel, (unsigned)nat, 256, 0, nat, f.W, npad, f.shift + 1);
+      MCHRG_LAUNCH(ctx, shift_update_kernel, 1, 1, 0, nat, f.shift);
+      MCHRG_LAUNCH(ctx, shift_apply_kernel, dim3((unsigned)((nat + 255) / 256), (unsigned)nat), 256, 0, nat, f.W, npad,
+                   f.shift);
+   };
+   assemble(f.W);
+   after_first(f.W);  // e.g. keep a copy of the unshifted matrix for the energy
+   if (pre_shift) apply_shift();
+   int* h_info = static_cast<int*>(ctx->pinned_buf(sizeof(int)));
+   for (int attempt = 0;; ++attempt) {
+      dpotrf_padded(ctx, npad, f.W, npad, f.dinv, info);
+      MCHRG_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
+      f.info = *h_info;
+      if (f.info == 0) break;
+      if (attempt == 3) return f;  // not positive definite on the charge-conserving subspace either
+      MCHRG_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
+      assemble(f.W);
+      apply_shift();
+   }
+   // y = J^-1 x, z = J^-1 1, Schur complement of the constraint
+   f.R = ctx->alloc<double>((size_t)npad * 2);
+   MCHRG_LAUNCH(ctx, rhs_init_kernel, (unsigned)((npad + 255) / 256), 256, 0, nat, npad, xvec, f.R);
+   dpotrs_vec(ctx, npad, f.W, npad, f.dinv, f.R, npad, 2);
+   f.vrhs = ctx->alloc<double>(nat + 1);
+   f.scal = ctx->alloc<double>(2);
+   MCHRG_LAUNCH(ctx, schur_charges_kernel, 1, 1024, 0, nat, npad, f.R, charge, f.vrhs, qvec_out, f.scal, f.shift);
+   return f;
+}
+
+// dq/dr, dq/dL from B (type.F90:283-291): X = B L^-T L^-1, dqdr = -X + (B z) z^T / s
+static void dq_tail(mchrg_b200_context* ctx, int nat, int64_t npad, int64_t mp, const Factor& f, double* Bm,
+                    const double* bz, double* dqdr, double* dqdL) {
+   dtrsm_right_lt(ctx, mp, npad, f.W, npad, f.dinv, Bm, mp);
+   dtrsm_right_ln(ctx, mp, npad, f.W, npad, f.dinv, Bm, mp);
+   dim3 grid((unsigned)((3 * (int64_t)nat + 9 + 255) / 256), (unsigned)((nat + 15) / 16));
+   MCHRG_LAUNCH(ctx, dq_epilogue_kernel, grid, 256, 0, nat, Bm, mp, bz, f.z(npad), f.scal, dqdr, dqdL);
+}
+
 // releases the periodic setup on every exit path
 struct PbcScope {
    PbcHost host;
@@ -300,56 +360,30 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
    double* thalf = ctx->alloc<double>(nat);
    eeq_xvec(ctx, mol, ap.chi, ap.kcnchi, io.cn, xvec, thalf);
 
-   // Coulomb block, factorisation
-   double* W = ctx->alloc<double>((size_t)npad * npad);
-   double* dinv = ctx->alloc<double>((size_t)npad * TILE);
-   int* info = ctx->alloc_zero<int>(1);
    PbcScope ps;
    double* Jc = nullptr;  // periodic: copy of J for the energy (type.F90:257-259)
-   double* shift = ctx->alloc_zero<double>(2);  // [0] mu of J' = J + mu 1 1^T, [1] 1^T J 1
    if (pbc) {
       pbc_begin(ctx, mol, ps.host, ps.work);
       ps.on = true;
    }
-   auto assemble = [&]() {
+   auto assemble = [&](double* W) {
       if (pbc) pbc_amat(ctx, mol, ap.rad, ap.eta, ps.work, W);
       else eeq_amat_0d(ctx, mol, ap.rad, ap.eta, W, npad, /*border=*/false, npad);
    };
-   auto apply_shift = [&]() {
-      MCHRG_CUDA(cudaMemsetAsync(shift + 1, 0, sizeof(double), ctx->stream));
-      MCHRG_LAUNCH(ctx, matsum_kernel, (unsigned)nat, 256, 0, nat, W, npad, shift + 1);
-      MCHRG_LAUNCH(ctx, shift_update_kernel, 1, 1, 0, nat, shift);
-      MCHRG_LAUNCH(ctx, shift_apply_kernel, dim3((unsigned)((nat + 255) / 256), (unsigned)nat), 256, 0, nat, W, npad, shift);
-   };
-   assemble();
-   if (pbc && io.energy) {
-      Jc = ctx->alloc<double>((size_t)npad * npad);
-      MCHRG_CUDA(cudaMemcpyAsync(Jc, W, (size_t)npad * npad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-   }
-   if (pbc) apply_shift();  // Ewald matrices are indefinite along 1: shift up front
-   int* h_info = static_cast<int*>(ctx->pinned_buf(sizeof(int)));
-   for (int attempt = 0;; ++attempt) {
-      dpotrf_padded(ctx, npad, W, npad, dinv, info);
-      MCHRG_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
-      if (*h_info == 0) break;
-      if (attempt == 3) {  // not positive definite on the charge-conserving subspace either
-         ctx->copybacks.clear();
-         return *h_info;
+   auto keep_copy = [&](double* W) {
+      if (pbc && io.energy) {
+         Jc = ctx->alloc<double>((size_t)npad * npad);
+         MCHRG_CUDA(cudaMemcpyAsync(Jc, W, (size_t)npad * npad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
       }
-      MCHRG_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
-      assemble();
-      apply_shift();
+   };
+   // Ewald matrices are indefinite along 1 (omitted G = 0 term): shift up front
+   Factor f = factor_solve(ctx, nat, npad, assemble, keep_copy, pbc, xvec, mol.charge, io.qvec);
+   if (f.info != 0) {
+      ctx->copybacks.clear();
+      return f.info;
    }
-
-   // y = J^-1 x, z = J^-1 1, Schur complement
-   double* R = ctx->alloc<double>((size_t)npad * 2);
-   MCHRG_LAUNCH(ctx, rhs_init_kernel, (unsigned)((npad + 255) / 256), 256, 0, nat, npad, xvec, R);
-   dpotrs_vec(ctx, npad, W, npad, dinv, R, npad, 2);
-   double* vrhs = ctx->alloc<double>(nat + 1);
-   double* scal = ctx->alloc<double>(2);
-   MCHRG_LAUNCH(ctx, schur_charges_kernel, 1, 1024, 0, nat, npad, R, mol.charge, vrhs, io.qvec, scal, shift);
-   const double* zvec = R + npad;
+   const double* vrhs = f.vrhs;
+   const double* zvec = f.z(npad);
 
    if (io.energy || grad || cpq) {
       double* jq = io.energy ? ctx->alloc<double>(nat) : nullptr;
@@ -380,12 +414,125 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
          }
          if (cpq) {
             MCHRG_LAUNCH(ctx, strain_rows_kernel, 1, 288, 0, nat, dadL, thalf, io.dcndL, zvec, Bm, mp, bz);
-            dtrsm_right_lt(ctx, mp, npad, W, npad, dinv, Bm, mp);
-            dtrsm_right_ln(ctx, mp, npad, W, npad, dinv, Bm, mp);
-            dim3 grid((unsigned)((3 * (int64_t)nat + 9 + 255) / 256), (unsigned)((nat + 15) / 16));
-            MCHRG_LAUNCH(ctx, dq_epilogue_kernel, grid, 256, 0, nat, Bm, mp, bz, zvec, scal, io.dqdr, io.dqdL);
+            dq_tail(ctx, nat, npad, mp, f, Bm, bz, io.dqdr, io.dqdL);
          }
       }
+   }
+   ctx->finish();
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// EEQ-BC (model/eeqbc.f90), non-periodic
+// ---------------------------------------------------------------------------------------------
+static BcAtoms gather_eeqbc(const mchrg_b200_model* model, const DevMol& mol) {
+   mchrg_b200_context* ctx = model->ctx;
+   auto g = [&](int slot) {
+      double* d = ctx->alloc<double>(mol.nat);
+      gather_species(ctx, mol.nat, mol.id, model->dev(slot), d);
+      return (const double*)d;
+   };
+   BcAtoms at;
+   at.chi = g(0); at.rad = g(1); at.eta = g(2); at.kcnchi = g(3);
+   at.kqchi = g(5); at.kqeta = g(6); at.cap = g(7); at.avg_cn = g(8);
+   return at;
+}
+
+// gradient = 0.5 ga - gx (type.F90:277-278)
+__global__ void bc_gradient_kernel(int n3, const double* __restrict__ ga, const double* __restrict__ gx,
+                                   double* __restrict__ gradient) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n3) gradient[i] = 0.5 * ga[i] - gx[i];
+}
+// sigma += sum_k q_k (0.5 dadL_k - dxdL_k); strain rows of B = dadL_k - dxdL_k and their z contraction
+__global__ void __launch_bounds__(288) bc_sigma_kernel(int nat, const double* __restrict__ q,
+                                                       const double* __restrict__ dadL, const double* __restrict__ dxdL,
+                                                       double* __restrict__ sigma, const double* __restrict__ zvec,
+                                                       double* __restrict__ B, int64_t ldb, double* __restrict__ bz) {
+   const int ab = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   double acc = 0.0, accz = 0.0;
+   for (int k = lane; k < nat; k += 32) {
+      const double da = dadL[(size_t)9 * k + ab], dx = dxdL[(size_t)9 * k + ab];
+      acc += q[k] * (0.5 * da - dx);
+      if (B) {
+         B[(size_t)k * ldb + 3 * (size_t)nat + ab] = da - dx;
+         accz = fma(da - dx, zvec[k], accz);
+      }
+   }
+   for (int o = 16; o > 0; o >>= 1) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      accz += __shfl_xor_sync(0xffffffffu, accz, o);
+   }
+   if (lane == 0) {
+      if (sigma) sigma[ab] += acc;
+      if (B) bz[3 * (size_t)nat + ab] = accz;
+   }
+}
+__global__ void set_last_kernel(int nat, double v, double* __restrict__ x) { x[nat] = v; }
+
+static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, const SolveIO& io) {
+   mchrg_b200_context* ctx = model->ctx;
+   if (mol.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC (get_amat_3d / get_cmat_3d, eeqbc.f90:532-632) is not built");
+   if (!io.qloc) fail(MCHRG_B200_ERR_MODEL, "qloc required for eeqbc");  // error stop, eeqbc.f90:202
+   const int nat = mol.nat;
+   const int64_t npad = round_up(nat, TILE);
+   // eeqbc.f90:195 (update) needs the local-charge derivatives for every derivative output
+   const bool dcn = io.dcndr && io.dcndL && io.dqlocdr && io.dqlocdL;
+   const bool grad = io.gradient && io.sigma && dcn;
+   const bool cpq = io.dqdr && io.dqdL && dcn;
+
+   BcAtoms at = gather_eeqbc(model, mol);
+   BcWork w;
+   bc_prepare(ctx, mol, model, at, io.cn, io.qloc, grad || cpq, w);
+   // xvec = C xtmp (eeqbc.f90:275-282); xtmp lives in w.atoms[5 i + 3]
+   double* xtmp = ctx->alloc<double>(nat + 1);
+   MCHRG_CUDA(cudaMemcpy2DAsync(xtmp, sizeof(double), w.atoms + 3, 5 * sizeof(double), sizeof(double), nat + 1,
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+   double* xvec = ctx->alloc<double>(nat + 1);
+   pbc_symv(ctx, nat, w.Cm, npad, xtmp, xvec);
+   MCHRG_LAUNCH(ctx, set_last_kernel, 1, 1, 0, nat, mol.charge, xvec);
+
+   double* Jc = nullptr;
+   auto assemble = [&](double* W) { bc_amat(ctx, mol, w, W); };
+   auto keep_copy = [&](double* W) {
+      if (io.energy) {
+         Jc = ctx->alloc<double>((size_t)npad * npad);
+         MCHRG_CUDA(cudaMemcpyAsync(Jc, W, (size_t)npad * npad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+   };
+   Factor f = factor_solve(ctx, nat, npad, assemble, keep_copy, false, xvec, mol.charge, io.qvec);
+   if (f.info != 0) {
+      ctx->copybacks.clear();
+      return f.info;
+   }
+   const double* q = f.vrhs;
+   if (io.energy) {
+      double* jq = ctx->alloc<double>(nat);
+      pbc_symv(ctx, nat, Jc, npad, q, jq);
+      MCHRG_LAUNCH(ctx, energy_kernel, (nat + 255) / 256, 256, 0, nat, q, jq, xvec, io.energy);
+   }
+   if (grad || cpq) {
+      double* rows = ctx->alloc<double>((size_t)24 * nat);
+      bc_rows(ctx, mol, model, w, q, io.dcndr, io.dcndL, rows);
+      double* dadL = ctx->alloc<double>((size_t)9 * nat);
+      double* dxdL = ctx->alloc<double>((size_t)9 * nat);
+      bc_strain(ctx, mol, at, w, q, rows, io.dcndL, io.dqlocdL, dadL, dxdL);
+      double* cq = ctx->alloc<double>(nat);
+      pbc_symv(ctx, nat, w.Cm, npad, q, cq);
+      double *Bm = nullptr, *bz = nullptr;
+      int64_t mp = 0;
+      if (cpq) {
+         mp = round_up(3 * (int64_t)nat + 9, TILE);
+         Bm = ctx->alloc<double>((size_t)mp * npad);
+         bz = ctx->alloc_zero<double>((size_t)mp);
+         bc_dxdr_gemm(ctx, mol, at, w, io.dcndr, io.dqlocdr, -1.0, Bm, mp);  // Bm = -dtmpdr C
+      }
+      double* ga = grad ? ctx->alloc_zero<double>((size_t)3 * nat) : nullptr;
+      double* gx = grad ? ctx->alloc_zero<double>((size_t)3 * nat) : nullptr;
+      bc_build_b(ctx, mol, model, at, w, q, cq, rows, io.dcndr, io.dqlocdr, 1.0, 1.0, true, Bm, mp, ga, gx, f.z(npad), bz);
+      if (grad) MCHRG_LAUNCH(ctx, bc_gradient_kernel, (3 * nat + 255) / 256, 256, 0, 3 * nat, ga, gx, io.gradient);
+      MCHRG_LAUNCH(ctx, bc_sigma_kernel, 1, 288, 0, nat, q, dadL, dxdL, grad ? io.sigma : nullptr, f.z(npad), Bm, mp, bz);
+      if (cpq) dq_tail(ctx, nat, npad, mp, f, Bm, bz, io.dqdr, io.dqdL);
    }
    ctx->finish();
    return 0;
@@ -401,7 +548,13 @@ static int solve_dispatch(const mchrg_b200_model* model, const DevMol& mol, cons
       AtomPar ap = gather_eeq(model, mol);
       return solve_eeq_device(model, mol, ap, io);
    }
-   fail(MCHRG_B200_ERR_MODEL, "EEQ-BC solve is not available in this build");
+   return solve_eeqbc_device(model, mol, io);
+}
+
+// qloc += charge / nat (type.F90:320)
+__global__ void add_const_kernel(int n, double v, double* __restrict__ x) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) x[i] += v;
 }
 
 // translations for the coordination number: get_lattice_points(periodic, lattice, cutoff) (charge.f90:70)
@@ -489,6 +642,80 @@ int mchrg_b200_new_eeq2019_model(mchrg_b200_context* ctx, int32_t nid, const int
                                    7.5, 8.0, model);
 }
 
+int mchrg_b200_new_eeqbc_model(mchrg_b200_context* ctx, int32_t nid, const double* chi, const double* rad,
+                               const double* eta, const double* kcnchi, const double* kqchi, const double* kqeta,
+                               double kcnrad, const double* cap, const double* avg_cn, const double* rvdw, double kbc,
+                               double cutoff, double cn_exp, const double* rcov, const double* en, double norm_exp,
+                               mchrg_b200_model** model) {
+   if (!ctx || !model || nid <= 0 || !chi || !rad || !eta || !kcnchi || !kqchi || !kqeta || !cap || !avg_cn || !rvdw ||
+       !rcov || !en) {
+      set_last_error("new_eeqbc_model: invalid argument");
+      return MCHRG_B200_ERR_ARG;
+   }
+   auto* m = new mchrg_b200_model();
+   m->ctx = ctx;
+   m->kind = 2;
+   m->nid = nid;
+   m->chi.assign(chi, chi + nid);
+   m->rad.assign(rad, rad + nid);
+   m->eta.assign(eta, eta + nid);
+   m->kcnchi.assign(kcnchi, kcnchi + nid);
+   m->kqchi.assign(kqchi, kqchi + nid);
+   m->kqeta.assign(kqeta, kqeta + nid);
+   m->cap.assign(cap, cap + nid);
+   m->avg_cn.assign(avg_cn, avg_cn + nid);
+   m->rvdw.assign(rvdw, rvdw + (size_t)nid * nid);
+   m->rcov.assign(rcov, rcov + nid);
+   m->en.assign(en, en + nid);
+   m->kcnrad = kcnrad;
+   m->kbc = kbc;
+   m->norm_exp = norm_exp;
+   m->ncoord.cutoff = m->ncoord_en.cutoff = cutoff;
+   m->ncoord.kcn = m->ncoord_en.kcn = cn_exp;
+   m->ncoord.norm_exp = m->ncoord_en.norm_exp = norm_exp;
+   m->ncoord.cut = m->ncoord_en.cut = -1.0;  // cn_max is absent in new_eeqbc2025_model (param.f90:118-122)
+   int rc = new_model_common(ctx, m, model);
+   if (rc != 0) delete m;
+   return rc;
+}
+
+int mchrg_b200_new_eeqbc2025_model(mchrg_b200_context* ctx, int32_t nid, const int32_t* num, const double* rvdw,
+                                   const double* en_pauling, mchrg_b200_model** model) {
+   if (!ctx || !model || nid <= 0 || !num || !rvdw || !en_pauling) {
+      set_last_error("new_eeqbc2025_model: invalid argument");
+      return MCHRG_B200_ERR_ARG;
+   }
+   std::vector<double> chi(nid), rad(nid), eta(nid), kcnchi(nid), kqchi(nid), kqeta(nid), cap(nid), avg_cn(nid),
+      rcov(nid), en(nid);
+   for (int i = 0; i < nid; ++i) {
+      const int z = num[i];
+      if (z < 1 || z > 103) {
+         set_last_error("new_eeqbc2025_model: atomic number out of range");
+         return MCHRG_B200_ERR_ARG;
+      }
+      chi[i] = mchrg_eeqbc_chi[z - 1];
+      eta[i] = mchrg_eeqbc_eta[z - 1];
+      rad[i] = mchrg_eeqbc_rad[z - 1];
+      kcnchi[i] = mchrg_eeqbc_kcnchi[z - 1];
+      kqchi[i] = mchrg_eeqbc_kqchi[z - 1];
+      kqeta[i] = mchrg_eeqbc_kqeta[z - 1];
+      cap[i] = mchrg_eeqbc_cap[z - 1];
+      rcov[i] = mchrg_eeqbc_cov_radii[z - 1];
+      avg_cn[i] = mchrg_eeqbc_avg_cn[z - 1];
+      // Pauling EN normalised to fluorine, actinide overrides of param.f90:105-113
+      double e = en_pauling[i];
+      if (z >= 90) e = 1.30;
+      if (z == 87) e = 0.80;
+      if (z == 89) e = 1.00;
+      if (z == 90 || z == 91 || z == 92 || z == 95) e = 1.10;
+      if (z == 93 || z == 94 || z == 97 || z == 103) e = 1.20;
+      en[i] = e / 3.98;
+   }
+   return mchrg_b200_new_eeqbc_model(ctx, nid, chi.data(), rad.data(), eta.data(), kcnchi.data(), kqchi.data(),
+                                     kqeta.data(), 0.14, cap.data(), avg_cn.data(), rvdw, 0.60, 25.0, 2.0, rcov.data(),
+                                     en.data(), 0.75, model);
+}
+
 void mchrg_b200_model_free(mchrg_b200_model* model) {
    if (!model) return;
    if (model->ctx) cudaSetDevice(model->ctx->device);
@@ -534,7 +761,18 @@ int mchrg_b200_local_charge(const mchrg_b200_model* model, const mchrg_b200_stru
          }
          return 0;
       }
-      fail(MCHRG_B200_ERR_MODEL, "EEQ-BC local_charge is not available in this build");
+      // EEQ-BC: electronegativity-weighted coordination number (cn_count%erf_en) + charge / nat
+      if ((dqlocdr == nullptr) != (dqlocdL == nullptr)) fail(MCHRG_B200_ERR_ARG, "local_charge: bad outputs");
+      int ntr = 0;
+      const double* trans = cn_translations(ctx, mol, model->ncoord_en.cutoff, &ntr);
+      double* rcov_a = ctx->alloc<double>(n);
+      double* en_a = ctx->alloc<double>(n);
+      gather_species(ctx, d.nat, d.id, model->dev(4), rcov_a);
+      gather_species(ctx, d.nat, d.id, model->dev(9), en_a);
+      ncoord_device(ctx, d, rcov_a, en_a, model->ncoord_en, ntr, trans, dq, ctx->out(dqlocdr, 3 * n * n),
+                    ctx->out(dqlocdL, 9 * n));
+      MCHRG_LAUNCH(ctx, add_const_kernel, (unsigned)((n + 255) / 256), 256, 0, d.nat, d.charge / (double)n, dq);
+      return 0;
    });
 }
 
@@ -544,8 +782,22 @@ int mchrg_b200_get_xvec(const mchrg_b200_model* model, const mchrg_b200_structur
    mchrg_b200_context* ctx = model->ctx;
    return guarded(ctx, [&]() {
       if (!cn || !xvec) fail(MCHRG_B200_ERR_ARG, "get_xvec: cn and xvec are required");
-      if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "EEQ-BC get_xvec is not available in this build");
       DevMol d = stage_mol(ctx, mol);
+      if (model->kind == 2) {
+         if (!qloc) fail(MCHRG_B200_ERR_MODEL, "qloc required for eeqbc");
+         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC is not built");
+         const size_t n = d.nat;
+         BcAtoms at = gather_eeqbc(model, d);
+         BcWork w;
+         bc_prepare(ctx, d, model, at, ctx->in(cn, n), ctx->in(qloc, n), false, w);
+         double* xtmp = ctx->alloc<double>(n + 1);
+         MCHRG_CUDA(cudaMemcpy2DAsync(xtmp, sizeof(double), w.atoms + 3, 5 * sizeof(double), sizeof(double), n + 1,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+         double* xv = ctx->out(xvec, n + 1);
+         pbc_symv(ctx, d.nat, w.Cm, w.npad, xtmp, xv);
+         MCHRG_LAUNCH(ctx, set_last_kernel, 1, 1, 0, d.nat, d.charge, xv);
+         return 0;
+      }
       AtomPar ap = gather_eeq(model, d);
       eeq_xvec(ctx, d, ap.chi, ap.kcnchi, ctx->in(cn, (size_t)d.nat), ctx->out(xvec, (size_t)d.nat + 1), nullptr);
       return 0;
@@ -559,9 +811,36 @@ int mchrg_b200_get_xvec_derivs(const mchrg_b200_model* model, const mchrg_b200_s
    mchrg_b200_context* ctx = model->ctx;
    return guarded(ctx, [&]() {
       if (!cn || !dcndr || !dcndL || !dxdr || !dxdL) fail(MCHRG_B200_ERR_ARG, "get_xvec_derivs: missing argument");
-      if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "EEQ-BC get_xvec_derivs is not available in this build");
       DevMol d = stage_mol(ctx, mol);
       const size_t n = d.nat;
+      if (model->kind == 2) {
+         if (!qloc || !dqlocdr || !dqlocdL) fail(MCHRG_B200_ERR_MODEL, "qloc and its derivatives required for eeqbc");
+         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC is not built");
+         BcAtoms at = gather_eeqbc(model, d);
+         BcWork w;
+         const double* dcn = ctx->in(dcndr, 3 * n * n);
+         const double* dcl = ctx->in(dcndL, 9 * n);
+         const double* dqr = ctx->in(dqlocdr, 3 * n * n);
+         const double* dql = ctx->in(dqlocdL, 9 * n);
+         bc_prepare(ctx, d, model, at, ctx->in(cn, n), ctx->in(qloc, n), true, w);
+         const int64_t mp = round_up(3 * (int64_t)n + 9, TILE);
+         double* zeros = ctx->alloc_zero<double>(n + 1);  // q = 0: only the q-independent (dxdr) parts survive
+         double* rows = ctx->alloc<double>(24 * n);
+         bc_rows(ctx, d, model, w, zeros, dcn, dcl, rows);
+         double* dadL_tmp = ctx->alloc<double>(9 * n);
+         double* d_dxdL = ctx->out(dxdL, 9 * (n + 1));
+         bc_strain(ctx, d, at, w, zeros, rows, dcl, dql, dadL_tmp, d_dxdL);
+         MCHRG_CUDA(cudaMemsetAsync(d_dxdL + 9 * n, 0, 9 * sizeof(double), ctx->stream));
+         double* Bm = ctx->alloc<double>((size_t)mp * w.npad);
+         bc_dxdr_gemm(ctx, d, at, w, dcn, dqr, 1.0, Bm, mp);  // Bm = +dtmpdr C
+         bc_build_b(ctx, d, model, at, w, zeros, nullptr, rows, dcn, dqr, 0.0, -1.0, false, Bm, mp, nullptr, nullptr,
+                    nullptr, nullptr);
+         double* d_dxdr = ctx->out(dxdr, 3 * n * (n + 1));
+         MCHRG_LAUNCH(ctx, unpad_copy_kernel, dim3((unsigned)((3 * n + 255) / 256), (unsigned)n), 256, 0, (int64_t)(3 * n),
+                      (int64_t)n, Bm, mp, d_dxdr, (int64_t)(3 * n), 0);
+         MCHRG_CUDA(cudaMemsetAsync(d_dxdr + 3 * n * n, 0, 3 * n * sizeof(double), ctx->stream));
+         return 0;
+      }
       AtomPar ap = gather_eeq(model, d);
       double* xv = ctx->alloc<double>(n + 1);
       double* thalf = ctx->alloc<double>(n);
@@ -580,9 +859,20 @@ int mchrg_b200_get_coulomb_matrix(const mchrg_b200_model* model, const mchrg_b20
    mchrg_b200_context* ctx = model->ctx;
    return guarded(ctx, [&]() {
       if (!amat) fail(MCHRG_B200_ERR_ARG, "get_coulomb_matrix: amat is required");
-      if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "EEQ-BC get_coulomb_matrix is not available in this build");
       DevMol d = stage_mol(ctx, mol);
       const size_t nd = (size_t)d.nat + 1;
+      if (model->kind == 2) {
+         if (!cn || !qloc) fail(MCHRG_B200_ERR_MODEL, "cn and qloc required for eeqbc");
+         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC is not built");
+         BcAtoms at = gather_eeqbc(model, d);
+         BcWork w;
+         bc_prepare(ctx, d, model, at, ctx->in(cn, (size_t)d.nat), ctx->in(qloc, (size_t)d.nat), false, w);
+         double* W = ctx->alloc<double>((size_t)w.npad * w.npad);
+         bc_amat(ctx, d, w, W);
+         MCHRG_LAUNCH(ctx, border_copy_kernel, dim3((unsigned)((nd + 255) / 256), (unsigned)nd), 256, 0, d.nat, W, w.npad,
+                      ctx->out(amat, nd * nd));
+         return 0;
+      }
       AtomPar ap = gather_eeq(model, d);
       double* out = ctx->out(amat, nd * nd);
       if (d.periodic) {
@@ -609,9 +899,35 @@ int mchrg_b200_get_coulomb_derivs(const mchrg_b200_model* model, const mchrg_b20
    mchrg_b200_context* ctx = model->ctx;
    return guarded(ctx, [&]() {
       if (!qvec || !dadr || !dadL || !atrace) fail(MCHRG_B200_ERR_ARG, "get_coulomb_derivs: missing argument");
-      if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "EEQ-BC get_coulomb_derivs is not available in this build");
       DevMol d = stage_mol(ctx, mol);
       const size_t n = d.nat;
+      if (model->kind == 2) {
+         if (!cn || !qloc || !dcndr || !dcndL || !dqlocdr || !dqlocdL)
+            fail(MCHRG_B200_ERR_MODEL, "cn, qloc and their derivatives required for eeqbc");
+         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC is not built");
+         BcAtoms at = gather_eeqbc(model, d);
+         BcWork w;
+         const double* dcn = ctx->in(dcndr, 3 * n * n);
+         const double* dcl = ctx->in(dcndL, 9 * n);
+         const double* dqr = ctx->in(dqlocdr, 3 * n * n);
+         const double* dql = ctx->in(dqlocdL, 9 * n);
+         const double* q = ctx->in(qvec, n);
+         bc_prepare(ctx, d, model, at, ctx->in(cn, n), ctx->in(qloc, n), true, w);
+         double* rows = ctx->alloc<double>(24 * n);
+         bc_rows(ctx, d, model, w, q, dcn, dcl, rows);
+         double* d_dadL = ctx->out(dadL, 9 * (n + 1));
+         double* dxdL_tmp = ctx->alloc<double>(9 * n);
+         bc_strain(ctx, d, at, w, q, rows, dcl, dql, d_dadL, dxdL_tmp);
+         MCHRG_CUDA(cudaMemsetAsync(d_dadL + 9 * n, 0, 9 * sizeof(double), ctx->stream));
+         double* d_dadr = ctx->out(dadr, 3 * n * (n + 1));
+         bc_build_b(ctx, d, model, at, w, q, nullptr, rows, dcn, dqr, 1.0, 0.0, false, d_dadr, 3 * (int64_t)n, nullptr,
+                    nullptr, nullptr, nullptr);
+         MCHRG_CUDA(cudaMemsetAsync(d_dadr + 3 * n * n, 0, 3 * n * sizeof(double), ctx->stream));
+         double* d_atr = ctx->out(atrace, 3 * n);
+         MCHRG_CUDA(cudaMemcpy2DAsync(d_atr, 3 * sizeof(double), rows, 24 * sizeof(double), 3 * sizeof(double), n,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+         return 0;
+      }
       AtomPar ap = gather_eeq(model, d);
       const double* q = ctx->in(qvec, n);
       double* d_dadr = ctx->out(dadr, 3 * n * (n + 1));
@@ -682,13 +998,26 @@ static int singlepoint_impl(const mchrg_b200_model* model, const mchrg_b200_stru
       double* d_dcndL = grad ? ctx->alloc<double>(9 * n) : nullptr;
       ncoord_device(ctx, d, rcov_a, nullptr, model->ncoord, ntr, trans, d_cn, d_dcndr, d_dcndL);
       double* d_qloc = qloc ? ctx->out(qloc, n) : ctx->alloc<double>(n);
-      if (model->kind == 1)
+      double *d_dqlr = nullptr, *d_dqlL = nullptr;
+      if (model->kind == 1) {
          MCHRG_LAUNCH(ctx, fill_kernel, (unsigned)((n + 255) / 256), 256, 0, (int64_t)n, d.charge / (double)n, d_qloc);
+      } else {
+         double* en_a = ctx->alloc<double>(n);
+         gather_species(ctx, d.nat, d.id, model->dev(9), en_a);
+         if (grad) {
+            d_dqlr = ctx->alloc<double>(3 * n * n);
+            d_dqlL = ctx->alloc<double>(9 * n);
+         }
+         ncoord_device(ctx, d, rcov_a, en_a, model->ncoord_en, ntr, trans, d_qloc, d_dqlr, d_dqlL);
+         MCHRG_LAUNCH(ctx, add_const_kernel, (unsigned)((n + 255) / 256), 256, 0, d.nat, d.charge / (double)n, d_qloc);
+      }
       SolveIO io;
       io.cn = d_cn;
       io.qloc = d_qloc;
       io.dcndr = d_dcndr;
       io.dcndL = d_dcndL;
+      io.dqlocdr = d_dqlr;
+      io.dqlocdL = d_dqlL;
       io.energy = ctx->out(energy, n, accumulate);
       io.gradient = ctx->out(gradient, 3 * n);
       io.sigma = ctx->out(sigma, 9, accumulate);
