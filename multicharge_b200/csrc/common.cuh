@@ -49,7 +49,12 @@ constexpr int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 // SURVEY 8b "Threading").
 struct mchrg_b200_context {
    int device = 0;
-   cudaStream_t stream = nullptr;
+   cudaStream_t stream = nullptr;     // main stream: every entry point is ordered on it
+   cudaStream_t stream_hi = nullptr;  // high-priority side stream (Cholesky panel look-ahead)
+   cudaStream_t active = nullptr;     // stream MCHRG_LAUNCH currently targets
+   std::vector<cudaEvent_t> events;   // reusable, timing disabled
+   size_t events_used = 0;
+   cudaEvent_t next_event();
    int sm_count = 148;
    size_t smem_optin = 0;
    std::mutex mu;
@@ -127,9 +132,17 @@ inline void after_launch(mchrg_b200_context* ctx, const char* name) {
 
 #define MCHRG_LAUNCH(ctx, kernel, grid, block, smem, ...)                       \
    do {                                                                          \
-      kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);           \
+      kernel<<<(grid), (block), (smem), (ctx)->active>>>(__VA_ARGS__);           \
       ::mchrg::after_launch((ctx), #kernel);                                     \
    } while (0)
+
+// switches the launch target of MCHRG_LAUNCH for a scope
+struct StreamScope {
+   mchrg_b200_context* ctx;
+   cudaStream_t prev;
+   StreamScope(mchrg_b200_context* c, cudaStream_t s) : ctx(c), prev(c->active) { c->active = s; }
+   ~StreamScope() { ctx->active = prev; }
+};
 
 // Runs `body` under the context lock with a fresh arena and converts exceptions to status codes.
 template <class F>
@@ -143,13 +156,17 @@ int guarded(mchrg_b200_context* ctx, F&& body) {
       ctx->use();
       ctx->arena_reset();
       ctx->copybacks.clear();
+      ctx->active = ctx->stream;
+      ctx->events_used = 0;
       int rc = body();
       ctx->finish();
       return rc;
    } catch (const Error& e) {
       set_last_error(e.msg);
       ctx->copybacks.clear();
+      ctx->active = ctx->stream;
       cudaStreamSynchronize(ctx->stream);
+      if (ctx->stream_hi) cudaStreamSynchronize(ctx->stream_hi);
       cudaGetLastError();
       return e.code;
    } catch (const std::exception& e) {

@@ -70,6 +70,15 @@ void mchrg_b200_context::finish() {
    MCHRG_CUDA(cudaStreamSynchronize(stream));
 }
 
+cudaEvent_t mchrg_b200_context::next_event() {
+   if (events_used == events.size()) {
+      cudaEvent_t e;
+      MCHRG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      events.push_back(e);
+   }
+   return events[events_used++];
+}
+
 void* mchrg_b200_context::pinned_buf(size_t bytes) {
    if (bytes > pinned_size) {
       if (pinned) cudaFreeHost(pinned);
@@ -120,7 +129,11 @@ int mchrg_b200_context_create(int device, mchrg_b200_context** out) {
               prop.major, prop.minor);
       ctx->sm_count = prop.multiProcessorCount;
       ctx->smem_optin = prop.sharedMemPerBlockOptin;
-      MCHRG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      int prio_lo = 0, prio_hi = 0;
+      MCHRG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo));
+      MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, prio_hi));
+      ctx->active = ctx->stream;
    } catch (const Error& e) {
       set_last_error(e.msg);
       delete ctx;
@@ -137,6 +150,11 @@ void mchrg_b200_context_destroy(mchrg_b200_context* ctx) {
       cudaStreamSynchronize(ctx->stream);
       cudaStreamDestroy(ctx->stream);
    }
+   if (ctx->stream_hi) {
+      cudaStreamSynchronize(ctx->stream_hi);
+      cudaStreamDestroy(ctx->stream_hi);
+   }
+   for (auto e : ctx->events) cudaEventDestroy(e);
    for (auto& s : ctx->slabs) cudaFree(s.base);
    if (ctx->pinned) cudaFreeHost(ctx->pinned);
    delete ctx;

@@ -6,6 +6,9 @@
 // and gemm/gemv/symv (blas.F90, called from model/type.F90:235-290).
 #include "dense.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace mchrg {
 
 // ------------------------------------------------------------------------------------------------
@@ -239,7 +242,7 @@ potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv
             failed = true;
             break;
          }
-         const double inv = 1.0 / sqrt(d);
+         const double inv = rsqrt(d);
          if (ty == jt) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
@@ -248,19 +251,19 @@ potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv
                else if (row == j) a[r][cj] = d * inv;
             }
          }
+         // masked column factors: zero for rows / columns <= j, so the rank-one update needs no predicates
          double lr[8], lc[8];
 #pragma unroll
-         for (int r = 0; r < 8; ++r) lr[r] = col[tx + 16 * r] * inv;
+         for (int r = 0; r < 8; ++r) lr[r] = (r >= cj && tx + 16 * r > j) ? -col[tx + 16 * r] * inv : 0.0;
 #pragma unroll
-         for (int c = 0; c < 8; ++c) lc[c] = col[ty + 16 * c] * inv;
+         for (int c = 0; c < 8; ++c) lc[c] = (c >= cj && ty + 16 * c > j) ? col[ty + 16 * c] * inv : 0.0;
 #pragma unroll
          for (int r = 0; r < 8; ++r) {
             if (r < cj) continue;  // rows tx + 16 r <= j for r < cj
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                if (c < cj) continue;
-               const int row = tx + 16 * r, cc = ty + 16 * c;
-               if (row > j && cc > j) a[r][c] = fma(-lr[r], lc[c], a[r][c]);
+               a[r][c] = fma(lr[r], lc[c], a[r][c]);
             }
          }
       }
@@ -381,10 +384,72 @@ static void potrf_rec(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw
    potrf_rec(ctx, n2, W22, ldw, dinv2, info, off + n1);
 }
 
+// Right-looking blocked Cholesky with one panel of look-ahead on two streams.
+//   P (high priority): diagonal block (recursive), panel TRSM, update of the NEXT block column
+//   U (main stream)  : the bulk trailing update (lower block triangle beyond the next block column)
+// leaf / skinny-GEMM latency of panel k+1 is hidden behind the bulk update of panel k.
+static int64_t panel_width() {  // tuning knob (multiple of 128); default chosen on B200 at n = 16384
+   static int64_t w = 0;
+   if (w == 0) {
+      const char* e = std::getenv("MCHRG_B200_PANEL");
+      w = e ? std::atoll(e) : 256;
+      if (w < TILE || w % TILE) w = 256;
+   }
+   return w;
+}
+
 void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info) {
    if (n % TILE || (ldw & 1)) fail(MCHRG_B200_ERR_ARG, "dpotrf_padded: n=%lld not a multiple of 128", (long long)n);
    leaf_setup_once();
-   potrf_rec(ctx, n, W, ldw, dinv, info, 0);
+   const int64_t PANEL = panel_width();
+   if (n <= 2 * PANEL) {  // small: plain recursion on the current stream
+      potrf_rec(ctx, n, W, ldw, dinv, info, 0);
+      return;
+   }
+   cudaStream_t U = ctx->active, P = ctx->stream_hi;
+   cudaEvent_t e0 = ctx->next_event();
+   MCHRG_CUDA(cudaEventRecord(e0, U));
+   MCHRG_CUDA(cudaStreamWaitEvent(P, e0, 0));
+   cudaEvent_t ev_upd_prev = nullptr;
+   for (int64_t c0 = 0; c0 < n;) {
+      const int64_t pw = std::min<int64_t>(PANEL, n - c0);
+      const int64_t rem = n - c0 - pw;
+      double* D = W + c0 + c0 * ldw;
+      double* dinv_k = dinv + (c0 / TILE) * TILE * TILE;
+      cudaEvent_t ev_panel = ctx->next_event();
+      {
+         StreamScope on_p(ctx, P);
+         potrf_rec(ctx, pw, D, ldw, dinv_k, info, c0);
+         if (rem > 0) dtrsm_right_lt(ctx, rem, pw, D, ldw, dinv_k, D + pw, ldw);
+         MCHRG_CUDA(cudaEventRecord(ev_panel, P));
+      }
+      if (rem == 0) break;
+      const int64_t pw2 = std::min<int64_t>(PANEL, rem);
+      double* A21 = D + pw;                   // (rem x pw) panel below the diagonal block
+      double* C1 = W + (c0 + pw) + (c0 + pw) * ldw;  // next block column (rem x pw2)
+      {
+         StreamScope on_p(ctx, P);
+         if (ev_upd_prev) MCHRG_CUDA(cudaStreamWaitEvent(P, ev_upd_prev, 0));
+         dgemm_padded(ctx, true, rem, pw2, pw, -1.0, A21, ldw, A21, ldw, 1.0, C1, ldw, false);
+      }
+      const int64_t rem2 = rem - pw2;
+      if (rem2 > 0) {
+         StreamScope on_u(ctx, U);
+         MCHRG_CUDA(cudaStreamWaitEvent(U, ev_panel, 0));
+         double* A2 = A21 + pw2;              // rows below the next block column
+         double* C2 = W + (c0 + pw + pw2) + (c0 + pw + pw2) * ldw;
+         dgemm_padded(ctx, true, rem2, rem2, pw, -1.0, A2, ldw, A2, ldw, 1.0, C2, ldw, /*lower_only=*/true);
+         cudaEvent_t ev_upd = ctx->next_event();
+         MCHRG_CUDA(cudaEventRecord(ev_upd, U));
+         ev_upd_prev = ev_upd;
+      } else {
+         ev_upd_prev = nullptr;
+      }
+      c0 += pw;
+   }
+   cudaEvent_t e1 = ctx->next_event();
+   MCHRG_CUDA(cudaEventRecord(e1, P));
+   MCHRG_CUDA(cudaStreamWaitEvent(U, e1, 0));
 }
 
 // ------------------------------------------------------------------------------------------------
