@@ -61,6 +61,78 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 
 __device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
 
+// decode a packed-lower index e -> (i, j), j <= i
+__device__ __forceinline__ void tri_decode(int e, int& i, int& j) {
+   i = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+   while (tri(i + 1) <= e) ++i;
+   while (tri(i) > e) --i;
+   j = e - tri(i);
+}
+
+// Cholesky of the 16 x 16 diagonal block at k0 by one warp: lane r < 16 owns row k0 + r in registers,
+// columns are broadcast with shuffles.  Publishes L into A, Ld (for the panel solve) and the reciprocal
+// pivots rd[k0 + c].  Returns 0 or the 1-based index of the first non-positive pivot.
+__device__ __forceinline__ int diag_block(double* __restrict__ A, double* __restrict__ Ld, double* __restrict__ rd, int k0,
+                                          int lane) {
+   const int r = lane & 15;
+   double d[KB];
+#pragma unroll
+   for (int c = 0; c < KB; ++c) d[c] = (c <= r) ? A[tri(k0 + r) + k0 + c] : 0.0;
+   int bad = 0;
+#pragma unroll
+   for (int c = 0; c < KB; ++c) {
+      const double piv = __shfl_sync(0xffffffffu, d[c], c);
+      if (!(piv > 0.0) && bad == 0) bad = k0 + c + 1;
+      const double rinv = rsqrt(piv);
+      if (r == c) {
+         d[c] = piv * rinv;
+         if (lane < KB) rd[k0 + c] = rinv;
+      } else if (r > c) {
+         d[c] *= rinv;
+      }
+#pragma unroll
+      for (int c2 = c + 1; c2 < KB; ++c2) {
+         const double l = __shfl_sync(0xffffffffu, d[c], c2);
+         if (r >= c2) d[c2] = fma(-d[c], l, d[c2]);
+      }
+   }
+   if (lane < KB) {
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+         if (c <= r) A[tri(k0 + r) + k0 + c] = d[c];
+         Ld[r * (KB + 1) + c] = (c <= r) ? d[c] : 0.0;
+      }
+   }
+   return bad;
+}
+
+// one 16 x 16 tile of the trailing update A(i0.., j0..) -= P(:, i0..)^T P(:, j0..) on DMMA
+__device__ __forceinline__ void update_tile(double* __restrict__ A, const double* __restrict__ P, int ldp, int i0, int j0,
+                                            int lane) {
+   const int g = lane >> 2, t = lane & 3;
+   double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+   for (int kk = 0; kk < KB / 4; ++kk) {
+      const double* pk = P + (4 * kk + t) * ldp;
+      const double a0 = pk[i0 + g], a1 = pk[i0 + 8 + g];
+      const double c0 = pk[j0 + g], c1 = pk[j0 + 8 + g];
+      dmma884(acc[0][0][0], acc[0][0][1], a0, c0);
+      dmma884(acc[0][1][0], acc[0][1][1], a0, c1);
+      dmma884(acc[1][0][0], acc[1][0][1], a1, c0);
+      dmma884(acc[1][1][0], acc[1][1][1], a1, c1);
+   }
+#pragma unroll
+   for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ntl = 0; ntl < 2; ++ntl) {
+         const int row = i0 + 8 * mt + g;
+         const int col = j0 + 8 * ntl + 2 * t;
+         double* dst = A + tri(row) + col;
+         if (col <= row) dst[0] -= acc[mt][ntl][0];
+         if (col + 1 <= row) dst[1] -= acc[mt][ntl][1];
+      }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
    extern __shared__ __align__(16) double sm[];
@@ -69,14 +141,14 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
    double* A = sm;                           // packed lower, row-major: A[tri(i) + j], j <= i
    double* P = A + (size_t)np * (np + 1) / 2;  // panel, k-major: P[c * ldp + i]
    double* Ld = P + (size_t)KB * ldp;        // diagonal block Ld[r * 17 + c]
-   double* rdiag = Ld + KB * (KB + 1);       // 1 / L(k0 + c, k0 + c)
-   double* vec = rdiag + KB;
+   double* spare = Ld + KB * (KB + 1);       // KB doubles, unused
+   double* vec = spare + KB;
    double* X = vec;            double* Y = X + np;        double* Z = Y + np;
    double* rad2 = Z + np;      double* dself = rad2 + np; double* rcov = dself + np;
    double* fcut = rcov + np;   double* xv = fcut + np;    double* th = xv + np;
    double* b0 = th + np;       double* b1 = b0 + np;      double* qv = b1 + np;
-   double* wf = qv + np;       // thalf * q * fcut
-   double* scal = wf + np;     // [0] lambda, [1] s
+   double* rd = qv + np;       // reciprocal pivots 1 / L(i, i); later reused for thalf * q * fcut
+   double* scal = rd + np;     // [0] lambda, [1] s
    __shared__ int sfail;
 
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -107,18 +179,30 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
    }
    __syncthreads();
 
-   // ---- erf coordination number with log-cut (mctc_ncoord), xvec (eeq.f90:127-150) ----
+   // ---- erf coordination number with log-cut (mctc_ncoord): every unique pair once, the counts are
+   //      parked in the (still unused) matrix storage and summed per row afterwards ----
+   const int ntri_n = tri(n);
+   for (int e = tid; e < ntri_n; e += NT) {
+      int i, j;
+      tri_decode(e, i, j);
+      double c = 0.0;
+      if (i != j) {
+         const double dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
+         const double r2 = dx * dx + dy * dy + dz * dz;
+         if (!(r2 > p.cutoff2 || r2 < 1.0e-12)) {
+            const double rc = rcov[i] + rcov[j];
+            c = 0.5 * (1.0 + erf(-p.kcn * (sqrt(r2) - rc) / rc));
+         }
+      }
+      A[e] = c;
+   }
+   __syncthreads();
    const double ecut = exp(p.cut);
    for (int i = warp; i < n; i += NW) {
-      const double xi = X[i], yi = Y[i], zi = Z[i], rci = rcov[i];
       double acc = 0.0;
-      for (int j = lane; j < n; j += 32) {
-         const double dx = xi - X[j], dy = yi - Y[j], dz = zi - Z[j];
-         const double r2 = dx * dx + dy * dy + dz * dz;
-         if (r2 > p.cutoff2 || r2 < 1.0e-12) continue;
-         const double rc = rci + rcov[j];
-         acc += 0.5 * (1.0 + erf(-p.kcn * (sqrt(r2) - rc) / rc));
-      }
+      const double* row = A + tri(i);
+      for (int j = lane; j < i; j += 32) acc += row[j];
+      for (int j = i + 1 + lane; j < n; j += 32) acc += A[tri(j) + i];
       acc = warp_sum(acc);
       if (lane == 0) {
          double cn = acc, f = 1.0;
@@ -127,19 +211,18 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
             cn = log(1.0 + ecut) - log(1.0 + exp(p.cut - acc));
          }
          const double tmp = th[i] / sqrt(cn + 1.0e-14);
-         xv[i] = -xv[i] + tmp * cn;
+         xv[i] = -xv[i] + tmp * cn;  // get_xvec, eeq.f90:127-150
          th[i] = 0.5 * tmp;
          fcut[i] = f;
       }
    }
+   __syncthreads();
 
    // ---- Coulomb block J, packed lower (eeq.f90:199-242); padding = identity ----
-   const int ntri = np * (np + 1) / 2;
+   const int ntri = tri(np);
    for (int e = tid; e < ntri; e += NT) {
-      int i = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
-      while (tri(i + 1) <= e) ++i;
-      while (tri(i) > e) --i;
-      const int j = e - tri(i);
+      int i, j;
+      tri_decode(e, i, j);
       double v;
       if (i == j) {
          v = dself[i];
@@ -154,45 +237,16 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
    }
    __syncthreads();
 
-   // ---- blocked Cholesky ----
-   for (int k0 = 0; k0 < np; k0 += KB) {
-      if (warp == 0) {  // diagonal block: lane r < 16 owns row k0 + r in registers
-         const int r = lane & 15;
-         double d[KB];
-#pragma unroll
-         for (int c = 0; c < KB; ++c) d[c] = (c <= r) ? A[tri(k0 + r) + k0 + c] : 0.0;
-         int bad = 0;
-#pragma unroll
-         for (int c = 0; c < KB; ++c) {
-            const double piv = __shfl_sync(0xffffffffu, d[c], c);
-            if (!(piv > 0.0) && bad == 0) bad = k0 + c + 1;
-            const double rinv = 1.0 / sqrt(piv);
-            if (r == c) {
-               d[c] = piv * rinv;
-               if (lane < KB) rdiag[c] = rinv;
-            } else if (r > c) {
-               d[c] *= rinv;
-            }
-#pragma unroll
-            for (int c2 = c + 1; c2 < KB; ++c2) {
-               const double l = __shfl_sync(0xffffffffu, d[c], c2);
-               if (r >= c2) d[c2] = fma(-d[c], l, d[c2]);
-            }
-         }
-         if (lane < KB) {
-#pragma unroll
-            for (int c = 0; c < KB; ++c) {
-               if (c <= r) A[tri(k0 + r) + k0 + c] = d[c];
-               Ld[r * (KB + 1) + c] = (c <= r) ? d[c] : 0.0;
-            }
-         }
-         if (bad && lane == 0) sfail = bad;
-      }
-      __syncthreads();
-      if (sfail) break;
+   // ---- blocked Cholesky, block 16, with look-ahead: the next diagonal block is factored by warp 0
+   //      while the other warps finish the trailing update ----
+   if (warp == 0) {
+      const int bad = diag_block(A, Ld, rd, 0, lane);
+      if (bad && lane == 0) sfail = bad;
+   }
+   __syncthreads();
+   for (int k0 = 0; k0 + KB < np && !sfail; k0 += KB) {
       const int t0 = k0 + KB;
-      if (t0 >= np) break;
-      // panel rows: one thread per row, a <- a * inv(Ld)^T
+      // panel rows: one thread per row, a <- a * inv(Ld)^T (right-looking inside the row)
       for (int i = t0 + tid; i < np; i += NT) {
          double a[KB];
          double* row = A + tri(i) + k0;
@@ -200,10 +254,9 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
          for (int c = 0; c < KB; ++c) a[c] = row[c];
 #pragma unroll
          for (int c = 0; c < KB; ++c) {
-            double s = a[c];
+            a[c] *= rd[k0 + c];
 #pragma unroll
-            for (int k = 0; k < c; ++k) s = fma(-a[k], Ld[c * (KB + 1) + k], s);
-            a[c] = s * rdiag[c];
+            for (int c2 = c + 1; c2 < KB; ++c2) a[c2] = fma(-a[c], Ld[c2 * (KB + 1) + c], a[c2]);
          }
 #pragma unroll
          for (int c = 0; c < KB; ++c) {
@@ -212,37 +265,29 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
          }
       }
       __syncthreads();
-      // trailing update on DMMA: 16x16 tiles of the lower block triangle, one per warp iteration
       const int nt = (np - t0) / KB;
-      const int ntile = nt * (nt + 1) / 2;
-      const int g = lane >> 2, t = lane & 3;
-      for (int tile = warp; tile < ntile; tile += NW) {
-         int ti = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
-         while (tri(ti + 1) <= tile) ++ti;
-         while (tri(ti) > tile) --ti;
-         const int tj = tile - tri(ti);
-         const int i0 = t0 + KB * ti, j0 = t0 + KB * tj;
-         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-#pragma unroll
-         for (int kk = 0; kk < KB / 4; ++kk) {
-            const double* pk = P + (4 * kk + t) * ldp;
-            const double a0 = pk[i0 + g], a1 = pk[i0 + 8 + g];
-            const double c0 = pk[j0 + g], c1 = pk[j0 + 8 + g];
-            dmma884(acc[0][0][0], acc[0][0][1], a0, c0);
-            dmma884(acc[0][1][0], acc[0][1][1], a0, c1);
-            dmma884(acc[1][0][0], acc[1][0][1], a1, c0);
-            dmma884(acc[1][1][0], acc[1][1][1], a1, c1);
-         }
-#pragma unroll
-         for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int ntl = 0; ntl < 2; ++ntl) {
-               const int row = i0 + 8 * mt + g;
-               const int col = j0 + 8 * ntl + 2 * t;
-               double* dst = A + tri(row) + col;
-               if (col <= row) dst[0] -= acc[mt][ntl][0];
-               if (col + 1 <= row) dst[1] -= acc[mt][ntl][1];
+      // first block column of the trailing matrix (needed by the next diagonal block and panel)
+      for (int ti = warp; ti < nt; ti += NW) update_tile(A, P, ldp, t0 + KB * ti, t0, lane);
+      __syncthreads();
+      // warp 0: next diagonal block; other warps: the rest of the trailing update
+      if (warp == 0) {
+         const int bad = diag_block(A, Ld, rd, t0, lane);
+         if (bad && lane == 0) sfail = bad;
+         if (NW == 1) {
+            const int nrest = tri(nt - 1);
+            for (int tile = 0; tile < nrest; ++tile) {
+               int a, b;
+               tri_decode(tile, a, b);
+               update_tile(A, P, ldp, t0 + KB * (a + 1), t0 + KB * (b + 1), lane);
             }
+         }
+      } else {
+         const int nrest = tri(nt - 1);  // tiles (ti, tj) with 1 <= tj <= ti <= nt - 1
+         for (int tile = warp - 1; tile < nrest; tile += NW - 1) {
+            int a, b;
+            tri_decode(tile, a, b);
+            update_tile(A, P, ldp, t0 + KB * (a + 1), t0 + KB * (b + 1), lane);
+         }
       }
       __syncthreads();
    }
@@ -269,7 +314,7 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
          double v0 = b0[k0 + r], v1 = b1[k0 + r];
 #pragma unroll
          for (int c = 0; c < KB; ++c) {
-            const double dinv = 1.0 / A[tri(k0 + c) + k0 + c];
+            const double dinv = rd[k0 + c];
             const double w0 = __shfl_sync(0xffffffffu, v0, c) * dinv;
             const double w1 = __shfl_sync(0xffffffffu, v1, c) * dinv;
             if (r == c) { v0 = w0; v1 = w1; }
@@ -300,7 +345,7 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
          double v0 = b0[k0 + r], v1 = b1[k0 + r];
 #pragma unroll
          for (int c = KB - 1; c >= 0; --c) {
-            const double dinv = 1.0 / A[tri(k0 + c) + k0 + c];
+            const double dinv = rd[k0 + c];
             const double w0 = __shfl_sync(0xffffffffu, v0, c) * dinv;
             const double w1 = __shfl_sync(0xffffffffu, v1, c) * dinv;
             if (r == c) { v0 = w0; v1 = w1; }
@@ -335,51 +380,57 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
    }
    __syncthreads();
    const double lam = scal[0];
+   double* wf = rd;  // pivots are no longer needed
    for (int i = tid; i < n; i += NT) {
       const double q = b0[i] - lam * b1[i];
       qv[i] = q;
       wf[i] = th[i] * q * fcut[i];
       p.qvec[off + i] = q;
+      // energy (type.F90:255-262): q_i (0.5 (J q)_i - x_i) with (J q)_i = x_i - lambda from the solved system
+      // J q + lambda 1 = x (residual of the Cholesky solve ~ n eps |J| |q|)
+      if (p.energy) p.energy[off + i] = q * (0.5 * (xv[i] - lam) - xv[i]);
    }
    if (tid == 0) p.status[mol] = 0;
-   if (!p.energy && !p.gradient) return;
+   if (!p.gradient) return;
    __syncthreads();
 
-   // ---- energy (type.F90:255-262) and gradient (type.F90:275-278) from one pair pass per row ----
-   for (int i = warp; i < n; i += NW) {
-      const double xi = X[i], yi = Y[i], zi = Z[i], ri2 = rad2[i], rci = rcov[i], qi = qv[i], wi = wf[i];
-      double jq = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
-      for (int j = lane; j < n; j += 32) {
-         if (j == i) continue;
-         const double vx = xi - X[j], vy = yi - Y[j], vz = zi - Z[j];
+   // ---- gradient (type.F90:275-278): g_i = sum_j f_ij (r_i - r_j) with the symmetric pair scalar
+   //        f_ij = dtmp_ij q_i q_j - dcount_ij / r_ij (w_i + w_j),   w = thalf * q * fcut
+   //      (q_i atrace_i minus the dcndr contraction; eeq.f90:403-411, mctc_ncoord); one evaluation per
+   //      unique pair, parked in the matrix storage, then summed per row ----
+   for (int e = tid; e < ntri_n; e += NT) {
+      int i, j;
+      tri_decode(e, i, j);
+      double f = 0.0;
+      if (i != j) {
+         const double vx = X[i] - X[j], vy = Y[i] - Y[j], vz = Z[i] - Z[j];
          const double r2 = vx * vx + vy * vy + vz * vz;
-         const double g2 = 1.0 / (ri2 + rad2[j]);
+         const double g2 = 1.0 / (rad2[i] + rad2[j]);
          const double arg = g2 * r2, r1 = sqrt(r2);
-         const double ef = erf(sqrt(arg));
-         const double qj = qv[j];
-         jq = fma(ef / r1, qj, jq);
-         if (p.gradient) {
-            // q_i * atrace_i : dtmp (r_i - r_j) q_i q_j   (eeq.f90:403-411)
-            double f = (2.0 * sqrt(g2) * exp(-arg) / (SQRTPI * r2) - ef / (r2 * r1)) * qi * qj;
-            // - sum_k thalf_k q_k dcndr(:, i, k)  =  - sum_j dcount_ij (r_i - r_j)/r (w_i + w_j)
-            if (r2 <= p.cutoff2 && r2 >= 1.0e-12) {
-               const double rc = rci + rcov[j];
-               const double a = p.kcn * (r1 - rc) / rc;
-               const double dc = -p.kcn / SQRTPI / rc * exp(-a * a);
-               f -= dc / r1 * (wi + wf[j]);
-            }
-            gx = fma(f, vx, gx); gy = fma(f, vy, gy); gz = fma(f, vz, gz);
+         f = (2.0 * sqrt(g2) * exp(-arg) / (SQRTPI * r2) - erf(sqrt(arg)) / (r2 * r1)) * qv[i] * qv[j];
+         if (r2 <= p.cutoff2 && r2 >= 1.0e-12) {
+            const double rc = rcov[i] + rcov[j];
+            const double a = p.kcn * (r1 - rc) / rc;
+            f -= -p.kcn / SQRTPI / rc * exp(-a * a) / r1 * (wf[i] + wf[j]);
          }
       }
-      jq = warp_sum(jq);
-      if (p.gradient) { gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz); }
+      A[e] = f;
+   }
+   __syncthreads();
+   for (int i = warp; i < n; i += NW) {
+      const double xi = X[i], yi = Y[i], zi = Z[i];
+      double gx = 0.0, gy = 0.0, gz = 0.0;
+      const double* row = A + tri(i);
+      for (int j = lane; j < n; j += 32) {
+         if (j == i) continue;
+         const double f = (j < i) ? row[j] : A[tri(j) + i];
+         gx = fma(f, xi - X[j], gx); gy = fma(f, yi - Y[j], gy); gz = fma(f, zi - Z[j], gz);
+      }
+      gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
       if (lane == 0) {
-         if (p.energy) p.energy[off + i] = qi * (0.5 * (jq + dself[i] * qi) - xv[i]);
-         if (p.gradient) {
-            p.gradient[3 * (off + i)] = gx;
-            p.gradient[3 * (off + i) + 1] = gy;
-            p.gradient[3 * (off + i) + 2] = gz;
-         }
+         p.gradient[3 * (off + i)] = gx;
+         p.gradient[3 * (off + i) + 1] = gy;
+         p.gradient[3 * (off + i) + 2] = gz;
       }
    }
 }
