@@ -61,47 +61,62 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 
 __device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
 
+// register-only broadcast of a double (the library overload goes through memory and forces arrays that are
+// shuffled element-wise into local memory)
+__device__ __forceinline__ double shfl_d(double v, int src) {
+   const int hi = __shfl_sync(0xffffffffu, __double2hiint(v), src);
+   const int lo = __shfl_sync(0xffffffffu, __double2loint(v), src);
+   return __hiloint2double(hi, lo);
+}
+
 // decode a packed-lower index e -> (i, j), j <= i
 __device__ __forceinline__ void tri_decode(int e, int& i, int& j) {
-   i = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+   i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);  // e < 2^15: the float estimate is within 1
    while (tri(i + 1) <= e) ++i;
    while (tri(i) > e) --i;
    j = e - tri(i);
 }
 
-// Cholesky of the 16 x 16 diagonal block at k0 by one warp: lane r < 16 owns row k0 + r in registers,
-// columns are broadcast with shuffles.  Publishes L into A, Ld (for the panel solve) and the reciprocal
-// pivots rd[k0 + c].  Returns 0 or the 1-based index of the first non-positive pivot.
+// Cholesky of the 16 x 16 diagonal block at k0 by one warp, register resident: lane = (row r = lane & 15,
+// column parity h = lane >> 4) holds the 8 entries m[k] = T(r, 2k + h).  Per column c the scaled column is
+// broadcast with shuffles from the lanes of parity c & 1 (register c >> 1) and every lane applies the
+// rank-one update to its 8 entries independently (no serial chain inside a column step).
+// Publishes L into A and Ld (row stride 17) and the reciprocal pivots rd[k0 + c].
+// Returns 0 or the 1-based index of the first non-positive pivot.
 __device__ __forceinline__ int diag_block(double* __restrict__ A, double* __restrict__ Ld, double* __restrict__ rd, int k0,
                                           int lane) {
-   const int r = lane & 15;
-   double d[KB];
+   const int r = lane & 15, h = lane >> 4;
+   double m[8];
 #pragma unroll
-   for (int c = 0; c < KB; ++c) d[c] = (c <= r) ? A[tri(k0 + r) + k0 + c] : 0.0;
+   for (int k = 0; k < 8; ++k) {
+      const int c = 2 * k + h;
+      m[k] = (c <= r) ? A[tri(k0 + r) + k0 + c] : 0.0;
+   }
    int bad = 0;
 #pragma unroll
    for (int c = 0; c < KB; ++c) {
-      const double piv = __shfl_sync(0xffffffffu, d[c], c);
-      if (!(piv > 0.0) && bad == 0) bad = k0 + c + 1;
+      const int src_h = (c & 1) << 4;  // lanes holding column c
+      const double piv = shfl_d(m[c >> 1], c + src_h);
+      bad = (!(piv > 0.0) && bad == 0) ? (k0 + c + 1) : bad;
       const double rinv = rsqrt(piv);
-      if (r == c) {
-         d[c] = piv * rinv;
-         if (lane < KB) rd[k0 + c] = rinv;
-      } else if (r > c) {
-         d[c] *= rinv;
-      }
+      const double lrc = shfl_d(m[c >> 1], r + src_h) * rinv;  // L(r, c) for r > c
 #pragma unroll
-      for (int c2 = c + 1; c2 < KB; ++c2) {
-         const double l = __shfl_sync(0xffffffffu, d[c], c2);
-         if (r >= c2) d[c2] = fma(-d[c], l, d[c2]);
+      for (int k = 0; k < 8; ++k) {
+         const int c2 = 2 * k + h;
+         const double lc2 = shfl_d(m[c >> 1], (c2 & 15) + src_h) * rinv;  // L(c2, c)
+         if (c2 > c && c2 <= r) m[k] = fma(-lrc, lc2, m[k]);
       }
+      if (h == (c & 1)) {  // owner lanes: store the scaled column entry / the pivot
+         if (r == c) m[c >> 1] = piv * rinv;
+         else if (r > c) m[c >> 1] = lrc;
+      }
+      if (lane == 0) rd[k0 + c] = rinv;
    }
-   if (lane < KB) {
 #pragma unroll
-      for (int c = 0; c < KB; ++c) {
-         if (c <= r) A[tri(k0 + r) + k0 + c] = d[c];
-         Ld[r * (KB + 1) + c] = (c <= r) ? d[c] : 0.0;
-      }
+   for (int k = 0; k < 8; ++k) {
+      const int c = 2 * k + h;
+      if (c <= r) A[tri(k0 + r) + k0 + c] = m[k];
+      Ld[r * (KB + 1) + c] = (c <= r) ? m[k] : 0.0;
    }
    return bad;
 }
@@ -134,7 +149,7 @@ __device__ __forceinline__ void update_tile(double* __restrict__ A, const double
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
+__global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    extern __shared__ __align__(16) double sm[];
    const int np = p.np;
    const int ldp = np + 4;
@@ -190,8 +205,9 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
          const double dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
          const double r2 = dx * dx + dy * dy + dz * dz;
          if (!(r2 > p.cutoff2 || r2 < 1.0e-12)) {
-            const double rc = rcov[i] + rcov[j];
-            c = 0.5 * (1.0 + erf(-p.kcn * (sqrt(r2) - rc) / rc));
+            // 1/2 (1 + erf(-kcn (r - rc)/rc)) = 1/2 erfc(kcn (r/rc - 1))
+            const double r1 = r2 * rsqrt(r2);
+            c = 0.5 * erfc(p.kcn * (r1 / (rcov[i] + rcov[j]) - 1.0));
          }
       }
       A[e] = c;
@@ -229,7 +245,8 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
       } else if (i < n) {
          const double dx = X[j] - X[i], dy = Y[j] - Y[i], dz = Z[j] - Z[i];
          const double r2 = dx * dx + dy * dy + dz * dz;
-         v = erf(sqrt(r2 / (rad2[i] + rad2[j]))) / sqrt(r2);
+         const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
+         v = erf(r2 * rinv * gam) * rinv;  // erf(gamma r) / r
       } else {
          v = 0.0;
       }
@@ -315,8 +332,8 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
 #pragma unroll
          for (int c = 0; c < KB; ++c) {
             const double dinv = rd[k0 + c];
-            const double w0 = __shfl_sync(0xffffffffu, v0, c) * dinv;
-            const double w1 = __shfl_sync(0xffffffffu, v1, c) * dinv;
+            const double w0 = shfl_d(v0, c) * dinv;
+            const double w1 = shfl_d(v1, c) * dinv;
             if (r == c) { v0 = w0; v1 = w1; }
             else if (r > c) {
                const double l = A[tri(k0 + r) + k0 + c];
@@ -346,8 +363,8 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
 #pragma unroll
          for (int c = KB - 1; c >= 0; --c) {
             const double dinv = rd[k0 + c];
-            const double w0 = __shfl_sync(0xffffffffu, v0, c) * dinv;
-            const double w1 = __shfl_sync(0xffffffffu, v1, c) * dinv;
+            const double w0 = shfl_d(v0, c) * dinv;
+            const double w1 = shfl_d(v1, c) * dinv;
             if (r == c) { v0 = w0; v1 = w1; }
             else if (r < c) {
                const double l = A[tri(k0 + c) + k0 + r];
@@ -405,13 +422,14 @@ __global__ void __launch_bounds__(NT) eeq_batch_kernel(Args p) {
       if (i != j) {
          const double vx = X[i] - X[j], vy = Y[i] - Y[j], vz = Z[i] - Z[j];
          const double r2 = vx * vx + vy * vy + vz * vz;
-         const double g2 = 1.0 / (rad2[i] + rad2[j]);
-         const double arg = g2 * r2, r1 = sqrt(r2);
-         f = (2.0 * sqrt(g2) * exp(-arg) / (SQRTPI * r2) - erf(sqrt(arg)) / (r2 * r1)) * qv[i] * qv[j];
+         const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
+         const double r1 = r2 * rinv, x = r1 * gam;  // x = gamma r
+         // dtmp = 2 gamma exp(-x^2) / (sqrt(pi) r^2) - erf(x) / r^3
+         f = rinv * rinv * (2.0 / SQRTPI * gam * exp(-x * x) - erf(x) * rinv) * qv[i] * qv[j];
          if (r2 <= p.cutoff2 && r2 >= 1.0e-12) {
-            const double rc = rcov[i] + rcov[j];
-            const double a = p.kcn * (r1 - rc) / rc;
-            f -= -p.kcn / SQRTPI / rc * exp(-a * a) / r1 * (wf[i] + wf[j]);
+            const double rci = 1.0 / (rcov[i] + rcov[j]);
+            const double a = p.kcn * (r1 * rci - 1.0);
+            f += p.kcn / SQRTPI * rci * exp(-a * a) * rinv * (wf[i] + wf[j]);
          }
       }
       A[e] = f;
@@ -505,16 +523,25 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
          order.push_back({c, start});
          start += cls[c].size();
       }
+      // Two streams: the shared-memory-heavy classes (one CTA per SM, latency bound in the factorisation)
+      // run next to the light classes, whose CTAs fit beside them and fill the idle FP64 issue slots.
+      cudaEvent_t staged = ctx->next_event();
+      MCHRG_CUDA(cudaEventRecord(staged, ctx->stream));
+      MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_aux, staged, 0));
       for (auto it = order.rbegin(); it != order.rend(); ++it) {
          const int c = it->first;
          const int count = (int)cls[c].size();
          if (count == 0) continue;
          a.np = c * batch::KB;
          a.perm = dperm + it->second;
+         StreamScope on(ctx, a.np > 112 ? ctx->stream : ctx->stream_aux);
          if (a.np <= 64) batch::launch_class<128>(ctx, a, count);
          else if (a.np <= 128) batch::launch_class<256>(ctx, a, count);
          else batch::launch_class<512>(ctx, a, count);
       }
+      cudaEvent_t aux_done = ctx->next_event();
+      MCHRG_CUDA(cudaEventRecord(aux_done, ctx->stream_aux));
+      MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream, aux_done, 0));
       MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));  // perm (host vector) must outlive the async copy
       return 0;
    });

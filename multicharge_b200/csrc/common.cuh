@@ -51,6 +51,7 @@ struct mchrg_b200_context {
    int device = 0;
    cudaStream_t stream = nullptr;     // main stream: every entry point is ordered on it
    cudaStream_t stream_hi = nullptr;  // high-priority side stream (Cholesky panel look-ahead)
+   cudaStream_t stream_aux = nullptr; // second normal-priority stream (batch size classes run concurrently)
    cudaStream_t active = nullptr;     // stream MCHRG_LAUNCH currently targets
    std::vector<cudaEvent_t> events;   // reusable, timing disabled
    size_t events_used = 0;
@@ -167,6 +168,7 @@ int guarded(mchrg_b200_context* ctx, F&& body) {
       ctx->active = ctx->stream;
       cudaStreamSynchronize(ctx->stream);
       if (ctx->stream_hi) cudaStreamSynchronize(ctx->stream_hi);
+      if (ctx->stream_aux) cudaStreamSynchronize(ctx->stream_aux);
       cudaGetLastError();
       return e.code;
    } catch (const std::exception& e) {

@@ -133,6 +133,7 @@ int mchrg_b200_context_create(int device, mchrg_b200_context** out) {
       MCHRG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo));
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, prio_hi));
+      MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, prio_lo));
       ctx->active = ctx->stream;
    } catch (const Error& e) {
       set_last_error(e.msg);
@@ -153,6 +154,10 @@ void mchrg_b200_context_destroy(mchrg_b200_context* ctx) {
    if (ctx->stream_hi) {
       cudaStreamSynchronize(ctx->stream_hi);
       cudaStreamDestroy(ctx->stream_hi);
+   }
+   if (ctx->stream_aux) {
+      cudaStreamSynchronize(ctx->stream_aux);
+      cudaStreamDestroy(ctx->stream_aux);
    }
    for (auto e : ctx->events) cudaEventDestroy(e);
    for (auto& s : ctx->slabs) cudaFree(s.base);
