@@ -334,6 +334,10 @@ def run_ours(args):
         time.sleep(0.3)
         clocks = sampler.stop(mark0, max(mark1, mark0 + 1))
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
 

@@ -465,6 +465,44 @@ static void launch_class(mchrg_b200_context* ctx, const Args& a, int count) {
    MCHRG_LAUNCH(ctx, eeq_batch_kernel<NT>, (unsigned)count, NT, smem, a);
 }
 
+
+
+// bucket the molecules [m0, m1) by padded order; returns the class-sorted permutation (chunk-local ids)
+// and the start of every class in it
+static void bucket(const std::vector<int64_t>& hoff, int32_t m0, int32_t m1, std::vector<int32_t>& perm,
+                   std::vector<size_t>& cls_start, std::vector<int>& cls_count) {
+   constexpr int NCLASS = NP_MAX / KB;
+   std::vector<std::vector<int32_t>> cls(NCLASS + 1);
+   for (int32_t m = m0; m < m1; ++m) {
+      const int64_t n = hoff[m + 1] - hoff[m];
+      cls[(n + KB - 1) / KB].push_back(m - m0);
+   }
+   perm.clear();
+   cls_start.assign(NCLASS + 1, 0);
+   cls_count.assign(NCLASS + 1, 0);
+   for (int c = 1; c <= NCLASS; ++c) {
+      cls_start[c] = perm.size();
+      cls_count[c] = (int)cls[c].size();
+      perm.insert(perm.end(), cls[c].begin(), cls[c].end());
+   }
+}
+
+// Launch every size class of one chunk: the shared-memory-heavy classes (one CTA per SM, latency bound in the
+// factorisation) on `big`, the light classes on `small`; their CTAs fit beside each other on an SM, so the
+// light ones fill the idle FP64 issue slots.  Largest classes first.
+static void launch_chunk(mchrg_b200_context* ctx, Args a, const int32_t* dperm, const std::vector<size_t>& cls_start,
+                         const std::vector<int>& cls_count, cudaStream_t big, cudaStream_t small) {
+   for (int c = NP_MAX / KB; c >= 1; --c) {
+      if (cls_count[c] == 0) continue;
+      a.np = c * KB;
+      a.perm = dperm + cls_start[c];
+      StreamScope on(ctx, a.np > 112 ? big : small);
+      if (a.np <= 64) launch_class<128>(ctx, a, cls_count[c]);
+      else if (a.np <= 128) launch_class<256>(ctx, a, cls_count[c]);
+      else launch_class<512>(ctx, a, cls_count[c]);
+   }
+}
+
 }  // namespace batch
 }  // namespace mchrg
 
@@ -486,63 +524,112 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
       else
          std::copy(offsets, offsets + nmol + 1, hoff.begin());
       const size_t ntot = (size_t)hoff[nmol];
-      constexpr int NCLASS = batch::NP_MAX / batch::KB;
-      std::vector<std::vector<int32_t>> cls(NCLASS + 1);
       for (int32_t m = 0; m < nmol; ++m) {
          const int64_t n = hoff[m + 1] - hoff[m];
          if (n <= 0) fail(MCHRG_B200_ERR_ARG, "singlepoint_batch: molecule %d is empty", m);
          if (n > batch::NP_MAX)
             fail(MCHRG_B200_ERR_ARG, "singlepoint_batch: molecule %d has %lld atoms (> %d); use mchrg_b200_singlepoint", m,
                  (long long)n, batch::NP_MAX);
-         cls[(n + batch::KB - 1) / batch::KB].push_back(m);
       }
-      std::vector<int32_t> perm;
-      perm.reserve(nmol);
-      for (auto& c : cls) perm.insert(perm.end(), c.begin(), c.end());
-      int32_t* dperm = ctx->alloc<int32_t>(nmol);
-      MCHRG_CUDA(cudaMemcpyAsync(dperm, perm.data(), perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-
       batch::Args a;
-      a.offsets = ctx->in(offsets, (size_t)nmol + 1);
-      a.num = ctx->in(num, ntot);
-      a.xyz = ctx->in(xyz, 3 * ntot);
-      a.charge = ctx->in(charge, (size_t)nmol);
-      a.qvec = ctx->out(qvec, ntot);
-      a.energy = ctx->out(energy, ntot);
-      a.gradient = ctx->out(gradient, 3 * ntot);
-      a.status = ctx->out(status, (size_t)nmol);
       a.par = model->d_par;
       a.nid = model->nid;
       a.kcn = model->ncoord.kcn;
       a.cutoff2 = model->ncoord.cutoff * model->ncoord.cutoff;
       a.cut = model->ncoord.cut;
-      size_t start = 0;
-      // largest classes first: their CTAs run longest, the small ones fill the tail
-      std::vector<std::pair<int, size_t>> order;
-      for (int c = 1; c <= NCLASS; ++c) {
-         order.push_back({c, start});
-         start += cls[c].size();
+      std::vector<int32_t> perm;
+      std::vector<size_t> cls_start;
+      std::vector<int> cls_count;
+
+      const bool host_io = !mchrg_b200_context::is_device_ptr(xyz) && !mchrg_b200_context::is_device_ptr(num) &&
+                           !mchrg_b200_context::is_device_ptr(charge) && !mchrg_b200_context::is_device_ptr(offsets) &&
+                           !mchrg_b200_context::is_device_ptr(qvec) && !mchrg_b200_context::is_device_ptr(status) &&
+                           (!energy || !mchrg_b200_context::is_device_ptr(energy)) &&
+                           (!gradient || !mchrg_b200_context::is_device_ptr(gradient));
+      if (!host_io || ntot < (size_t)1 << 18) {
+         // device-resident (or small) batch: one chunk, inputs staged on the main stream
+         batch::bucket(hoff, 0, nmol, perm, cls_start, cls_count);
+         int32_t* dperm = ctx->alloc<int32_t>(nmol);
+         MCHRG_CUDA(cudaMemcpyAsync(dperm, perm.data(), perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+         a.offsets = ctx->in(offsets, (size_t)nmol + 1);
+         a.num = ctx->in(num, ntot);
+         a.xyz = ctx->in(xyz, 3 * ntot);
+         a.charge = ctx->in(charge, (size_t)nmol);
+         a.qvec = ctx->out(qvec, ntot);
+         a.energy = ctx->out(energy, ntot);
+         a.gradient = ctx->out(gradient, 3 * ntot);
+         a.status = ctx->out(status, (size_t)nmol);
+         cudaEvent_t staged = ctx->next_event();
+         MCHRG_CUDA(cudaEventRecord(staged, ctx->stream));
+         MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_aux, staged, 0));
+         batch::launch_chunk(ctx, a, dperm, cls_start, cls_count, ctx->stream, ctx->stream_aux);
+         cudaEvent_t aux_done = ctx->next_event();
+         MCHRG_CUDA(cudaEventRecord(aux_done, ctx->stream_aux));
+         MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream, aux_done, 0));
+         MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));  // perm (host vector) must outlive the async copy
+         return 0;
       }
-      // Two streams: the shared-memory-heavy classes (one CTA per SM, latency bound in the factorisation)
-      // run next to the light classes, whose CTAs fit beside them and fill the idle FP64 issue slots.
-      cudaEvent_t staged = ctx->next_event();
-      MCHRG_CUDA(cudaEventRecord(staged, ctx->stream));
-      MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_aux, staged, 0));
-      for (auto it = order.rbegin(); it != order.rend(); ++it) {
-         const int c = it->first;
-         const int count = (int)cls[c].size();
-         if (count == 0) continue;
-         a.np = c * batch::KB;
-         a.perm = dperm + it->second;
-         StreamScope on(ctx, a.np > 112 ? ctx->stream : ctx->stream_aux);
-         if (a.np <= 64) batch::launch_class<128>(ctx, a, count);
-         else if (a.np <= 128) batch::launch_class<256>(ctx, a, count);
-         else batch::launch_class<512>(ctx, a, count);
+
+      // Host buffers: pipeline chunks of molecules so that the H2D copy of chunk c+1 and the D2H copy of
+      // chunk c-1 overlap the kernels of chunk c (asynchronous when the caller's buffers are pinned).
+      const int nchunk = (int)std::min<size_t>(8, std::max<size_t>(2, ntot >> 21));
+      std::vector<int32_t> bounds(nchunk + 1, 0);
+      for (int c = 1; c < nchunk; ++c) {  // split by atoms
+         const int64_t target = (int64_t)(ntot * (size_t)c / nchunk);
+         bounds[c] = (int32_t)(std::lower_bound(hoff.begin(), hoff.end(), target) - hoff.begin());
+         if (bounds[c] < bounds[c - 1]) bounds[c] = bounds[c - 1];
       }
-      cudaEvent_t aux_done = ctx->next_event();
-      MCHRG_CUDA(cudaEventRecord(aux_done, ctx->stream_aux));
-      MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream, aux_done, 0));
-      MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));  // perm (host vector) must outlive the async copy
+      bounds[nchunk] = nmol;
+      std::vector<std::vector<int64_t>> loc_off(nchunk);
+      std::vector<std::vector<int32_t>> loc_perm(nchunk);
+      cudaEvent_t start = ctx->next_event();
+      MCHRG_CUDA(cudaEventRecord(start, ctx->stream));
+      MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_in, start, 0));
+      MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_out, start, 0));
+      for (int c = 0; c < nchunk; ++c) {
+         const int32_t m0 = bounds[c], m1 = bounds[c + 1], mc = m1 - m0;
+         if (mc <= 0) continue;
+         const size_t a0 = (size_t)hoff[m0], na = (size_t)(hoff[m1] - hoff[m0]);
+         loc_off[c].resize((size_t)mc + 1);
+         for (int32_t m = 0; m <= mc; ++m) loc_off[c][m] = hoff[m0 + m] - hoff[m0];
+         batch::bucket(hoff, m0, m1, loc_perm[c], cls_start, cls_count);
+         int64_t* d_off = ctx->alloc<int64_t>((size_t)mc + 1);
+         int32_t* d_perm = ctx->alloc<int32_t>(mc);
+         int32_t* d_num = ctx->alloc<int32_t>(na);
+         double* d_xyz = ctx->alloc<double>(3 * na);
+         double* d_chg = ctx->alloc<double>(mc);
+         double* d_q = ctx->alloc<double>(na);
+         double* d_e = energy ? ctx->alloc<double>(na) : nullptr;
+         double* d_g = gradient ? ctx->alloc<double>(3 * na) : nullptr;
+         int32_t* d_st = ctx->alloc<int32_t>(mc);
+         cudaStream_t in = ctx->stream_in, out = ctx->stream_out;
+         MCHRG_CUDA(cudaMemcpyAsync(d_off, loc_off[c].data(), ((size_t)mc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, in));
+         MCHRG_CUDA(cudaMemcpyAsync(d_perm, loc_perm[c].data(), (size_t)mc * sizeof(int32_t), cudaMemcpyHostToDevice, in));
+         MCHRG_CUDA(cudaMemcpyAsync(d_num, num + a0, na * sizeof(int32_t), cudaMemcpyHostToDevice, in));
+         MCHRG_CUDA(cudaMemcpyAsync(d_xyz, xyz + 3 * a0, 3 * na * sizeof(double), cudaMemcpyHostToDevice, in));
+         MCHRG_CUDA(cudaMemcpyAsync(d_chg, charge + m0, (size_t)mc * sizeof(double), cudaMemcpyHostToDevice, in));
+         cudaEvent_t ev_in = ctx->next_event();
+         MCHRG_CUDA(cudaEventRecord(ev_in, in));
+         MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream, ev_in, 0));
+         MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_aux, ev_in, 0));
+         a.offsets = d_off; a.num = d_num; a.xyz = d_xyz; a.charge = d_chg;
+         a.qvec = d_q; a.energy = d_e; a.gradient = d_g; a.status = d_st;
+         batch::launch_chunk(ctx, a, d_perm, cls_start, cls_count, ctx->stream, ctx->stream_aux);
+         cudaEvent_t aux_done = ctx->next_event();
+         MCHRG_CUDA(cudaEventRecord(aux_done, ctx->stream_aux));
+         MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream, aux_done, 0));
+         cudaEvent_t ev_done = ctx->next_event();
+         MCHRG_CUDA(cudaEventRecord(ev_done, ctx->stream));
+         MCHRG_CUDA(cudaStreamWaitEvent(out, ev_done, 0));
+         MCHRG_CUDA(cudaMemcpyAsync(qvec + a0, d_q, na * sizeof(double), cudaMemcpyDeviceToHost, out));
+         if (energy) MCHRG_CUDA(cudaMemcpyAsync(energy + a0, d_e, na * sizeof(double), cudaMemcpyDeviceToHost, out));
+         if (gradient) MCHRG_CUDA(cudaMemcpyAsync(gradient + 3 * a0, d_g, 3 * na * sizeof(double), cudaMemcpyDeviceToHost, out));
+         MCHRG_CUDA(cudaMemcpyAsync(status + m0, d_st, (size_t)mc * sizeof(int32_t), cudaMemcpyDeviceToHost, out));
+      }
+      cudaEvent_t out_done = ctx->next_event();
+      MCHRG_CUDA(cudaEventRecord(out_done, ctx->stream_out));
+      MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream, out_done, 0));
+      MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging vectors must outlive the async copies
       return 0;
    });
 }

@@ -52,6 +52,8 @@ struct mchrg_b200_context {
    cudaStream_t stream = nullptr;     // main stream: every entry point is ordered on it
    cudaStream_t stream_hi = nullptr;  // high-priority side stream (Cholesky panel look-ahead)
    cudaStream_t stream_aux = nullptr; // second normal-priority stream (batch size classes run concurrently)
+   cudaStream_t stream_in = nullptr;  // host->device copies of pipelined batches
+   cudaStream_t stream_out = nullptr; // device->host copies of pipelined batches
    cudaStream_t active = nullptr;     // stream MCHRG_LAUNCH currently targets
    std::vector<cudaEvent_t> events;   // reusable, timing disabled
    size_t events_used = 0;
@@ -169,6 +171,8 @@ int guarded(mchrg_b200_context* ctx, F&& body) {
       cudaStreamSynchronize(ctx->stream);
       if (ctx->stream_hi) cudaStreamSynchronize(ctx->stream_hi);
       if (ctx->stream_aux) cudaStreamSynchronize(ctx->stream_aux);
+      if (ctx->stream_in) cudaStreamSynchronize(ctx->stream_in);
+      if (ctx->stream_out) cudaStreamSynchronize(ctx->stream_out);
       cudaGetLastError();
       return e.code;
    } catch (const std::exception& e) {

@@ -134,6 +134,8 @@ int mchrg_b200_context_create(int device, mchrg_b200_context** out) {
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo));
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, prio_hi));
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, prio_lo));
+      MCHRG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
+      MCHRG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
       ctx->active = ctx->stream;
    } catch (const Error& e) {
       set_last_error(e.msg);
@@ -155,9 +157,11 @@ void mchrg_b200_context_destroy(mchrg_b200_context* ctx) {
       cudaStreamSynchronize(ctx->stream_hi);
       cudaStreamDestroy(ctx->stream_hi);
    }
-   if (ctx->stream_aux) {
-      cudaStreamSynchronize(ctx->stream_aux);
-      cudaStreamDestroy(ctx->stream_aux);
+   for (cudaStream_t st : {ctx->stream_aux, ctx->stream_in, ctx->stream_out}) {
+      if (st) {
+         cudaStreamSynchronize(st);
+         cudaStreamDestroy(st);
+      }
    }
    for (auto e : ctx->events) cudaEventDestroy(e);
    for (auto& s : ctx->slabs) cudaFree(s.base);

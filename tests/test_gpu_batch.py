@@ -108,3 +108,23 @@ def test_batch_rejects_oversized_molecule(mc):
     offsets = np.array([0, 209], dtype=np.int64)
     with pytest.raises(mc.MchrgError):
         mc.singlepoint_batch(mc.new_eeq2019_batch_model(), offsets, num, xyz, np.zeros(1))
+
+
+def test_batch_pipelined_host_path_equals_device_path(mc):
+    """Large host batches are pipelined in chunks (H2D / kernels / D2H overlap): same bits as one device-resident pass."""
+    import torch
+    from synth import batch
+    offsets, num, xyz, charge = batch(3000, 9, nmin=30, nmax=200)
+    assert offsets[-1] > (1 << 18)
+    model = mc.new_eeq2019_batch_model()
+    host = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    dev = torch.device("cuda:0")
+    ntot = int(offsets[-1])
+    out = dict(qvec=torch.empty(ntot, dtype=torch.float64, device=dev), energy=torch.empty(ntot, dtype=torch.float64, device=dev),
+               gradient=torch.empty(ntot, 3, dtype=torch.float64, device=dev), status=torch.empty(3000, dtype=torch.int32, device=dev))
+    mc.singlepoint_batch(model, torch.tensor(offsets, device=dev), torch.tensor(num, device=dev), torch.tensor(xyz, device=dev),
+                         torch.tensor(charge, device=dev), out=out)
+    torch.cuda.synchronize()
+    assert np.all(host["status"] == 0)
+    for key in ("qvec", "energy", "gradient"):
+        assert np.array_equal(out[key].cpu().numpy(), host[key]), key
