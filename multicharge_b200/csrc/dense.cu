@@ -457,41 +457,51 @@ void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, d
 // ------------------------------------------------------------------------------------------------
 constexpr int MAX_RHS = 4;
 
-// r_k <- inv(L_kk) r_k  (forward)  or  inv(L_kk)^T r_k (backward); one CTA of 128 threads
-__global__ void __launch_bounds__(128) trsv_diag_kernel(const double* __restrict__ dinv_k, double* __restrict__ R,
+// r_k <- inv(L_kk) r_k  (forward)  or  inv(L_kk)^T r_k (backward); one CTA of 256 threads:
+// thread (i, h) accumulates half of the 128-term dot product of row i with independent, unrolled loads
+__global__ void __launch_bounds__(256) trsv_diag_kernel(const double* __restrict__ dinv_k, double* __restrict__ R,
                                                         int64_t ldr, int nrhs, int transpose) {
    __shared__ double v[MAX_RHS][TILE];
-   const int i = threadIdx.x;
-   for (int c = 0; c < nrhs; ++c) v[c][i] = R[i + c * ldr];
+   __shared__ double part[MAX_RHS][TILE];
+   const int i = threadIdx.x & (TILE - 1), h = threadIdx.x >> 7;
+   if (h == 0)
+      for (int c = 0; c < nrhs; ++c) v[c][i] = R[i + c * ldr];
    __syncthreads();
    double acc[MAX_RHS] = {0.0, 0.0, 0.0, 0.0};
-   if (!transpose) {
-      for (int k = 0; k <= i; ++k) {
-         const double l = dinv_k[i + k * TILE];
-         for (int c = 0; c < nrhs; ++c) acc[c] = fma(l, v[c][k], acc[c]);
-      }
-   } else {
-      for (int k = i; k < TILE; ++k) {
-         const double l = dinv_k[k + i * TILE];
-         for (int c = 0; c < nrhs; ++c) acc[c] = fma(l, v[c][k], acc[c]);
-      }
+   const int k0 = h * (TILE / 2);
+#pragma unroll 16
+   for (int kk = 0; kk < TILE / 2; ++kk) {
+      const int k = k0 + kk;
+      // the blocks are stored with an explicitly zero upper triangle, so no bounds on k are needed
+      const double l = transpose ? dinv_k[k + i * TILE] : dinv_k[i + k * TILE];
+#pragma unroll
+      for (int c = 0; c < MAX_RHS; ++c) acc[c] = fma(l, v[c][k], acc[c]);
    }
-   for (int c = 0; c < nrhs; ++c) R[i + c * ldr] = acc[c];
+   if (h == 1)
+      for (int c = 0; c < nrhs; ++c) part[c][i] = acc[c];
+   __syncthreads();
+   if (h == 0)
+      for (int c = 0; c < nrhs; ++c) R[i + c * ldr] = acc[c] + part[c][i];
 }
 
-// forward update: R[i] -= sum_j L(i, j) w_j  for rows i below the block (one thread per row)
+// forward update: R[i] -= sum_j L(i, j) w_j  for rows i below the block (one thread per row, unrolled loads)
 __global__ void __launch_bounds__(256) trsv_update_fwd_kernel(const double* __restrict__ Lcol, int64_t ldl,
                                                               const double* __restrict__ w, double* __restrict__ R,
                                                               int64_t ldr, int64_t nrows, int nrhs) {
    __shared__ double ws[MAX_RHS][TILE];
-   for (int idx = threadIdx.x; idx < nrhs * TILE; idx += blockDim.x) ws[idx / TILE][idx % TILE] = w[(idx % TILE) + (idx / TILE) * ldr];
+   for (int idx = threadIdx.x; idx < MAX_RHS * TILE; idx += blockDim.x) {
+      const int c = idx / TILE, j = idx % TILE;
+      ws[c][j] = (c < nrhs) ? w[j + c * ldr] : 0.0;
+   }
    __syncthreads();
    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= nrows) return;
    double acc[MAX_RHS] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 16
    for (int j = 0; j < TILE; ++j) {
       const double l = Lcol[i + (int64_t)j * ldl];
-      for (int c = 0; c < nrhs; ++c) acc[c] = fma(l, ws[c][j], acc[c]);
+#pragma unroll
+      for (int c = 0; c < MAX_RHS; ++c) acc[c] = fma(l, ws[c][j], acc[c]);
    }
    for (int c = 0; c < nrhs; ++c) R[i + c * ldr] -= acc[c];
 }
@@ -501,20 +511,27 @@ __global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __re
                                                               const double* __restrict__ w, double* __restrict__ R,
                                                               int64_t ldr, int64_t ncols, int nrhs) {
    __shared__ double ws[MAX_RHS][TILE];
-   for (int idx = threadIdx.x; idx < nrhs * TILE; idx += blockDim.x) ws[idx / TILE][idx % TILE] = w[(idx % TILE) + (idx / TILE) * ldr];
+   for (int idx = threadIdx.x; idx < MAX_RHS * TILE; idx += blockDim.x) {
+      const int c = idx / TILE, j = idx % TILE;
+      ws[c][j] = (c < nrhs) ? w[j + c * ldr] : 0.0;
+   }
    __syncthreads();
    const int lane = threadIdx.x & 31;
    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    if (j >= ncols) return;
    double acc[MAX_RHS] = {0.0, 0.0, 0.0, 0.0};
-   for (int i = lane; i < TILE; i += 32) {
+#pragma unroll
+   for (int ii = 0; ii < TILE / 32; ++ii) {
+      const int i = lane + 32 * ii;
       const double l = Lrow[i + j * ldl];
-      for (int c = 0; c < nrhs; ++c) acc[c] = fma(l, ws[c][i], acc[c]);
+#pragma unroll
+      for (int c = 0; c < MAX_RHS; ++c) acc[c] = fma(l, ws[c][i], acc[c]);
    }
-   for (int c = 0; c < nrhs; ++c) {
+#pragma unroll
+   for (int c = 0; c < MAX_RHS; ++c) {
       double v = acc[c];
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) R[j + c * ldr] -= v;
+      if (lane == 0 && c < nrhs) R[j + c * ldr] -= v;
    }
 }
 
@@ -524,7 +541,7 @@ void dpotrs_vec(mchrg_b200_context* ctx, int64_t n, const double* L, int64_t ldl
    const int64_t nb = n / TILE;
    for (int64_t k = 0; k < nb; ++k) {  // L w = r
       double* rk = R + k * TILE;
-      MCHRG_LAUNCH(ctx, trsv_diag_kernel, 1, 128, 0, dinv + k * TILE * TILE, rk, ldr, nrhs, 0);
+      MCHRG_LAUNCH(ctx, trsv_diag_kernel, 1, 256, 0, dinv + k * TILE * TILE, rk, ldr, nrhs, 0);
       const int64_t below = n - (k + 1) * TILE;
       if (below > 0)
          MCHRG_LAUNCH(ctx, trsv_update_fwd_kernel, (unsigned)((below + 255) / 256), 256, 0,
@@ -532,7 +549,7 @@ void dpotrs_vec(mchrg_b200_context* ctx, int64_t n, const double* L, int64_t ldl
    }
    for (int64_t k = nb - 1; k >= 0; --k) {  // L^T y = w
       double* rk = R + k * TILE;
-      MCHRG_LAUNCH(ctx, trsv_diag_kernel, 1, 128, 0, dinv + k * TILE * TILE, rk, ldr, nrhs, 1);
+      MCHRG_LAUNCH(ctx, trsv_diag_kernel, 1, 256, 0, dinv + k * TILE * TILE, rk, ldr, nrhs, 1);
       const int64_t left = k * TILE;
       if (left > 0)
          MCHRG_LAUNCH(ctx, trsv_update_bwd_kernel, (unsigned)((left + 7) / 8), 256, 0, L + k * TILE, ldl, rk, R, ldr,
