@@ -138,6 +138,18 @@ int mchrg_b200_singlepoint(const mchrg_b200_model* model, const mchrg_b200_struc
                            double* qloc, double* energy, double* gradient, double* sigma, double* qvec,
                            double* dqdr, double* dqdL);
 
+/* ---- one large system over several GPUs: row-sharded derivatives ----------------------
+ * mchrg_b200_singlepoint restricted to the atom block [row_begin, row_end) of the derivative outputs:
+ *   gradient_rows(3, nrows)      = gradient(:, row_begin+1 : row_end)
+ *   dqdr_rows(3, nrows, nat)     = dqdr(:, row_begin+1 : row_end, :)
+ * while cn, energy, sigma, qvec and dqdL are complete on every caller.  The right-side solves that
+ * produce dq/dr act on its rows independently, so ranks that own disjoint blocks need NO data-path
+ * collective; the O(N^3/3) factorisation is replicated (see DESIGN.md "Multi-GPU").  Non-periodic
+ * EEQ2019-type models only. */
+int mchrg_b200_singlepoint_rows(const mchrg_b200_model* model, const mchrg_b200_structure* mol, int32_t row_begin,
+                                int32_t row_end, double* cn, double* energy, double* gradient_rows, double* sigma,
+                                double* qvec, double* dqdr_rows, double* dqdL);
+
 /* ---- batches of independent non-periodic molecules (BASELINE.json configs[0..1]) -----------
  * get_charges / singlepoint over nmol molecules in one call: molecule m owns atoms
  * [offsets[m], offsets[m+1]).  num[] are ATOMIC NUMBERS per atom (the model must have been built

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "mchrg_b200_solve": (C.c_int, [c_vp, C.POINTER(Structure)] + [c_vp] * 12),
     "mchrg_b200_get_charges": (C.c_int, [c_vp, C.POINTER(Structure), c_vp, c_vp, c_vp]),
     "mchrg_b200_singlepoint": (C.c_int, [c_vp, C.POINTER(Structure)] + [c_vp] * 8),
+    "mchrg_b200_singlepoint_rows": (C.c_int, [c_vp, C.POINTER(Structure), C.c_int32, C.c_int32] + [c_vp] * 7),
     "mchrg_b200_singlepoint_batch": (C.c_int, [c_vp, C.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mchrg_b200_dpotrf": (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int64]),
     "mchrg_b200_dgemm": (C.c_int, [c_vp, C.c_char, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_vp, C.c_int64, c_vp,

@@ -260,6 +260,23 @@ class MchrgModel:
         return out
 
 
+def singlepoint_rows(model, mol, row_begin, row_end, dqdr=True, out=None, xyz=None, id=None):
+    """One rank's share of a single large system (mchrg_b200_singlepoint_rows): derivative outputs for the atom
+    block [row_begin, row_end) only -- gradient[nrows,3], dqdr[nat, nrows, 3] (dqdr[i, j - row_begin, c] =
+    d q_i / d r_jc); cn, qvec, energy, sigma, dqdL complete.  `out` may hold caller (device) buffers."""
+    n, nj = mol.nat, row_end - row_begin
+    if out is None:
+        out = SolveResult(cn=np.zeros(n), qvec=np.zeros(n), energy=np.zeros(n), gradient=np.zeros((nj, 3)),
+                          sigma=np.zeros((3, 3)), dqdr=np.zeros((n, nj, 3)) if dqdr else None,
+                          dqdL=np.zeros((n, 3, 3)) if dqdr else None)
+    s = mol._c(xyz=xyz, id=id)
+    rc = _lib.load().mchrg_b200_singlepoint_rows(
+        model._h, C.byref(s), int(row_begin), int(row_end), _ptr(out.get("cn")), _ptr(out.get("energy")),
+        _ptr(out.get("gradient")), _ptr(out.get("sigma")), _ptr(out.get("qvec")), _ptr(out.get("dqdr")), _ptr(out.get("dqdL")))
+    MchrgModel._status(rc)
+    return out
+
+
 def new_eeq_model(mol, chi, rad, eta, kcnchi, rcov, cutoff=25.0, cn_exp=7.5, cn_max=8.0, ctx=None):
     """new_eeq_model (model/eeq.f90:62-95); per-species arrays of length mol.nid."""
     ctx = ctx or default_context()

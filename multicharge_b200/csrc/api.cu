@@ -13,6 +13,7 @@
 //   dadr, dxdr (3 N (N+1) each), gemv x4          gradient = q * atrace - sum_k thalf_k q_k dcndr(:,:,k)
 //   dqdr = -(dadr - dxdr) * ainv(:, :N)  (gemm)   B = dadr - dxdr built once, X = B L^-T L^-1 (two
 //                                                 recursive right-side TRSMs), dqdr = -X + (B z) z^T / s
+#include <algorithm>
 #include <cmath>
 
 #include "dense.cuh"
@@ -88,10 +89,10 @@ __global__ void energy_kernel(int nat, const double* __restrict__ q, const doubl
 }
 
 // gradient(:, j) = q_j atrace(:, j) - gradx(:, j)    (type.F90:276-278 after eliminating dadr/dxdr)
-__global__ void gradient_kernel(int nat, const double* __restrict__ q, const double* __restrict__ atrace,
+__global__ void gradient_kernel(int jb, int nj, const double* __restrict__ q, const double* __restrict__ atrace,
                                 const double* __restrict__ gradx, double* __restrict__ gradient) {
-   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < 3 * nat) gradient[i] = q[i / 3] * atrace[i] - gradx[i];
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // row within the block [jb, jb + nj)
+   if (i < 3 * nj) gradient[i] = q[jb + i / 3] * atrace[3 * jb + i] - gradx[i];
 }
 
 // sigma(a,b) += sum_k q_k (0.5 dadL(a,b,k) - thalf_k dcndL(a,b,k))   (type.F90:279-280); 9 warps
@@ -111,26 +112,27 @@ __global__ void __launch_bounds__(288) strain_rows_kernel(int nat, const double*
                                                           const double* __restrict__ thalf,
                                                           const double* __restrict__ dcndL,
                                                           const double* __restrict__ zvec, double* __restrict__ B,
-                                                          int64_t ldb, double* __restrict__ bz) {
+                                                          int64_t ldb, double* __restrict__ bz, int64_t roff) {
    const int ab = threadIdx.x >> 5, lane = threadIdx.x & 31;
    double acc = 0.0;
    for (int k = lane; k < nat; k += 32) {
       const double v = dadL[(size_t)9 * k + ab] - thalf[k] * dcndL[(size_t)9 * k + ab];
-      B[(size_t)k * ldb + 3 * (size_t)nat + ab] = v;
+      B[(size_t)k * ldb + roff + ab] = v;
       acc = fma(v, zvec[k], acc);
    }
    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-   if (lane == 0) bz[3 * (size_t)nat + ab] = acc;
+   if (lane == 0) bz[roff + ab] = acc;
 }
 
 // dqdr(r, k) = -X(r, k) + bz_r z_k / s ; rows 3N.. go to dqdL     (type.F90:289-290 + Schur correction)
-__global__ void __launch_bounds__(256) dq_epilogue_kernel(int nat, const double* __restrict__ X, int64_t ldx,
+// nj = number of atoms in this row block (dqdr holds the rows of the block only, leading dimension 3 nj)
+__global__ void __launch_bounds__(256) dq_epilogue_kernel(int nat, int nj, const double* __restrict__ X, int64_t ldx,
                                                           const double* __restrict__ bz,
                                                           const double* __restrict__ zvec,
                                                           const double* __restrict__ scal, double* __restrict__ dqdr,
                                                           double* __restrict__ dqdL) {
    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   const int64_t nrow = 3 * (int64_t)nat + 9;
+   const int64_t n3 = 3 * (int64_t)nj, nrow = n3 + 9;
    if (r >= nrow) return;
    const double u = bz[r] / scal[0];
    const int k0 = blockIdx.y * 16;
@@ -139,8 +141,8 @@ __global__ void __launch_bounds__(256) dq_epilogue_kernel(int nat, const double*
       const int k = k0 + kk;
       if (k >= nat) break;
       const double v = fma(u, zvec[k], -X[r + (size_t)k * ldx]);
-      if (r < 3 * (int64_t)nat) dqdr[r + (size_t)k * 3 * nat] = v;
-      else dqdL[(r - 3 * (int64_t)nat) + (size_t)k * 9] = v;
+      if (r < n3) dqdr[r + (size_t)k * n3] = v;
+      else if (dqdL) dqdL[(r - n3) + (size_t)k * 9] = v;
    }
 }
 
@@ -246,6 +248,9 @@ struct SolveIO {
                 *dqlocdL = nullptr;
    double *energy = nullptr, *gradient = nullptr, *sigma = nullptr, *qvec = nullptr, *dqdr = nullptr,
           *dqdL = nullptr;
+   // row block [jb, je) of the derivative outputs (gradient rows, dq/dr rows); je < 0: all atoms.
+   // With a proper sub-block, gradient is (3, nj) and dqdr (3, nj, nat).
+   int jb = 0, je = -1;
 };
 
 static AtomPar gather_eeq(const mchrg_b200_model* model, const DevMol& mol) {
@@ -328,12 +333,12 @@ static Factor factor_solve(mchrg_b200_context* ctx, int nat, int64_t npad, Assem
 }
 
 // dq/dr, dq/dL from B (type.F90:283-291): X = B L^-T L^-1, dqdr = -X + (B z) z^T / s
-static void dq_tail(mchrg_b200_context* ctx, int nat, int64_t npad, int64_t mp, const Factor& f, double* Bm,
+static void dq_tail(mchrg_b200_context* ctx, int nat, int nj, int64_t npad, int64_t mp, const Factor& f, double* Bm,
                     const double* bz, double* dqdr, double* dqdL) {
    dtrsm_right_lt(ctx, mp, npad, f.W, npad, f.dinv, Bm, mp);
    dtrsm_right_ln(ctx, mp, npad, f.W, npad, f.dinv, Bm, mp);
-   dim3 grid((unsigned)((3 * (int64_t)nat + 9 + 255) / 256), (unsigned)((nat + 15) / 16));
-   MCHRG_LAUNCH(ctx, dq_epilogue_kernel, grid, 256, 0, nat, Bm, mp, bz, f.z(npad), f.scal, dqdr, dqdL);
+   dim3 grid((unsigned)((3 * (int64_t)nj + 9 + 255) / 256), (unsigned)((nat + 15) / 16));
+   MCHRG_LAUNCH(ctx, dq_epilogue_kernel, grid, 256, 0, nat, nj, Bm, mp, bz, f.z(npad), f.scal, dqdr, dqdL);
 }
 
 // releases the periodic setup on every exit path
@@ -355,6 +360,9 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
    const bool grad = io.gradient && io.sigma && dcn;
    const bool cpq = io.dqdr && io.dqdL && dcn;
    const bool pbc = mol.periodic;
+   const int jb = io.jb, je = io.je < 0 ? nat : io.je, nj = je - jb;
+   if (jb < 0 || je > nat || nj <= 0) fail(MCHRG_B200_ERR_ARG, "invalid row block [%d, %d)", jb, je);
+   if (pbc && nj != nat) fail(MCHRG_B200_ERR_MODEL, "row blocks are not available for periodic structures");
 
    double* xvec = ctx->alloc<double>(nat + 1);
    double* thalf = ctx->alloc<double>(nat);
@@ -393,7 +401,7 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
       double* bz = nullptr;
       int64_t mp = 0;
       if (cpq) {
-         mp = round_up(3 * (int64_t)nat + 9, TILE);
+         mp = round_up(3 * (int64_t)nj + 9, TILE);
          Bm = ctx->alloc_zero<double>((size_t)mp * npad);
          bz = ctx->alloc_zero<double>((size_t)mp);
       }
@@ -406,15 +414,16 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
       if (io.energy) MCHRG_LAUNCH(ctx, energy_kernel, (nat + 255) / 256, 256, 0, nat, vrhs, jq, xvec, io.energy);
 
       if (grad || cpq) {
-         double* gradx = grad ? ctx->alloc_zero<double>((size_t)3 * nat) : nullptr;
-         eeq_build_b_0d(ctx, mol, ap.rad, vrhs, atrace, thalf, io.dcndr, Bm, mp, gradx, zvec, bz, pbc && cpq);
+         double* gradx = grad ? ctx->alloc_zero<double>((size_t)3 * nj) : nullptr;
+         eeq_build_b_0d(ctx, mol, ap.rad, vrhs, atrace, thalf, io.dcndr, Bm, mp, gradx, zvec, bz, pbc && cpq, jb, je);
          if (grad) {
-            MCHRG_LAUNCH(ctx, gradient_kernel, (3 * nat + 255) / 256, 256, 0, nat, vrhs, atrace, gradx, io.gradient);
+            MCHRG_LAUNCH(ctx, gradient_kernel, (3 * nj + 255) / 256, 256, 0, jb, nj, vrhs, atrace, gradx, io.gradient);
             MCHRG_LAUNCH(ctx, sigma_kernel, 1, 288, 0, nat, vrhs, dadL, thalf, io.dcndL, io.sigma);
          }
          if (cpq) {
-            MCHRG_LAUNCH(ctx, strain_rows_kernel, 1, 288, 0, nat, dadL, thalf, io.dcndL, zvec, Bm, mp, bz);
-            dq_tail(ctx, nat, npad, mp, f, Bm, bz, io.dqdr, io.dqdL);
+            MCHRG_LAUNCH(ctx, strain_rows_kernel, 1, 288, 0, nat, dadL, thalf, io.dcndL, zvec, Bm, mp, bz,
+                         3 * (int64_t)nj);
+            dq_tail(ctx, nat, nj, npad, mp, f, Bm, bz, io.dqdr, io.dqdL);
          }
       }
    }
@@ -474,6 +483,7 @@ static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, 
    mchrg_b200_context* ctx = model->ctx;
    if (mol.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC (get_amat_3d / get_cmat_3d, eeqbc.f90:532-632) is not built");
    if (!io.qloc) fail(MCHRG_B200_ERR_MODEL, "qloc required for eeqbc");  // error stop, eeqbc.f90:202
+   if (io.je >= 0 && (io.jb != 0 || io.je != mol.nat)) fail(MCHRG_B200_ERR_MODEL, "row blocks are not available for EEQ-BC");
    const int nat = mol.nat;
    const int64_t npad = round_up(nat, TILE);
    // eeqbc.f90:195 (update) needs the local-charge derivatives for every derivative output
@@ -532,7 +542,7 @@ static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, 
       bc_build_b(ctx, mol, model, at, w, q, cq, rows, io.dcndr, io.dqlocdr, 1.0, 1.0, true, Bm, mp, ga, gx, f.z(npad), bz);
       if (grad) MCHRG_LAUNCH(ctx, bc_gradient_kernel, (3 * nat + 255) / 256, 256, 0, 3 * nat, ga, gx, io.gradient);
       MCHRG_LAUNCH(ctx, bc_sigma_kernel, 1, 288, 0, nat, q, dadL, dxdL, grad ? io.sigma : nullptr, f.z(npad), Bm, mp, bz);
-      if (cpq) dq_tail(ctx, nat, npad, mp, f, Bm, bz, io.dqdr, io.dqdL);
+      if (cpq) dq_tail(ctx, nat, nat, npad, mp, f, Bm, bz, io.dqdr, io.dqdL);
    }
    ctx->finish();
    return 0;
@@ -983,12 +993,12 @@ int mchrg_b200_solve(const mchrg_b200_model* model, const mchrg_b200_structure* 
 
 static int singlepoint_impl(const mchrg_b200_model* model, const mchrg_b200_structure* mol, double* cn, double* qloc,
                             double* energy, double* gradient, double* sigma, double* qvec, double* dqdr,
-                            double* dqdL, bool accumulate) {
+                            double* dqdL, bool accumulate, int jb = 0, int je = -1) {
    mchrg_b200_context* ctx = model->ctx;
    return guarded(ctx, [&]() {
       DevMol d = stage_mol(ctx, mol);
       const size_t n = d.nat;
-      const bool grad = (gradient && sigma) || (dqdr && dqdL);
+      const bool grad = (gradient && sigma) || dqdr;
       int ntr = 0;
       const double* trans = cn_translations(ctx, mol, model->ncoord.cutoff, &ntr);
       double* rcov_a = ctx->alloc<double>(n);
@@ -1018,14 +1028,30 @@ static int singlepoint_impl(const mchrg_b200_model* model, const mchrg_b200_stru
       io.dcndL = d_dcndL;
       io.dqlocdr = d_dqlr;
       io.dqlocdL = d_dqlL;
+      const size_t nj = (je < 0) ? n : (size_t)std::max(0, je - jb);
+      io.jb = jb;
+      io.je = je;
       io.energy = ctx->out(energy, n, accumulate);
-      io.gradient = ctx->out(gradient, 3 * n);
+      io.gradient = ctx->out(gradient, 3 * nj);
       io.sigma = ctx->out(sigma, 9, accumulate);
       io.qvec = ctx->out(qvec, n);
-      io.dqdr = ctx->out(dqdr, 3 * n * n);
+      io.dqdr = ctx->out(dqdr, 3 * nj * n);
       io.dqdL = ctx->out(dqdL, 9 * n);
+      if (io.dqdr && !io.dqdL) io.dqdL = ctx->alloc<double>(9 * n);  // dq/dL rides along with dq/dr
       return solve_dispatch(model, d, io);
    });
+}
+
+int mchrg_b200_singlepoint_rows(const mchrg_b200_model* model, const mchrg_b200_structure* mol, int32_t row_begin,
+                                int32_t row_end, double* cn, double* energy, double* gradient_rows, double* sigma,
+                                double* qvec, double* dqdr_rows, double* dqdL) {
+   if (!model) return MCHRG_B200_ERR_ARG;
+   if (!mol || row_begin < 0 || row_end > mol->nat || row_end <= row_begin) {
+      set_last_error("singlepoint_rows: invalid row block");
+      return MCHRG_B200_ERR_ARG;
+   }
+   return singlepoint_impl(model, mol, cn, nullptr, energy, gradient_rows, sigma, qvec, dqdr_rows, dqdL, true, row_begin,
+                           row_end);
 }
 
 int mchrg_b200_get_charges(const mchrg_b200_model* model, const mchrg_b200_structure* mol, double* qvec,

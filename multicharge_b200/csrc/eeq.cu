@@ -291,9 +291,11 @@ __global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const doubl
                                                             const double* __restrict__ dcndr, double* __restrict__ Bout,
                                                             int64_t ldb, double* __restrict__ gradx,
                                                             const double* __restrict__ zvec, double* __restrict__ bz,
-                                                            int pair_in_b) {
+                                                            int pair_in_b, int jb, int je) {
    __shared__ double sk[BB_KCHUNK][8];  // x, y, z, rad^2, thalf, thalf*q, z, unused
-   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+   // atom j of the row block [jb, je); rows of Bout / gradx / bz are numbered within the block
+   const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+   const int j = jb + jl;
    const int k0 = blockIdx.y * BB_KCHUNK;
    const int kn = min(BB_KCHUNK, nat - k0);
    for (int idx = threadIdx.x; idx < kn; idx += blockDim.x) {
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const doubl
       sk[idx][6] = zvec ? zvec[k] : 0.0;
    }
    __syncthreads();
-   if (j >= nat) return;
+   if (j >= je) return;
    const double xj = xyz[3 * j], yj = xyz[3 * j + 1], zj = xyz[3 * j + 2];
    const double rj2 = rad[j] * rad[j], qj = q[j];
    double gx[3] = {0.0, 0.0, 0.0}, uz[3] = {0.0, 0.0, 0.0};
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const doubl
          b0 = b1 = b2 = 0.0;
          if (atrace) { b0 = atrace[3 * j]; b1 = atrace[3 * j + 1]; b2 = atrace[3 * j + 2]; }
       } else if (pair_in_b) {  // periodic: the pair term was written by the Ewald kernels
-         const double* o = Bout + (size_t)k * ldb + 3 * j;
+         const double* o = Bout + (size_t)k * ldb + 3 * jl;
          b0 = o[0]; b1 = o[1]; b2 = o[2];
       } else if (!need_pair) {
          b0 = b1 = b2 = 0.0;
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const doubl
          gx[0] = fma(tq, d0, gx[0]); gx[1] = fma(tq, d1, gx[1]); gx[2] = fma(tq, d2, gx[2]);
       }
       if (Bout) {
-         double* o = Bout + (size_t)k * ldb + 3 * j;
+         double* o = Bout + (size_t)k * ldb + 3 * jl;
          o[0] = b0; o[1] = b1; o[2] = b2;
       }
       if (bz) {
@@ -349,19 +351,20 @@ __global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const doubl
       }
    }
    if (gradx && dcndr) {
-      atomicAdd(gradx + 3 * j, gx[0]); atomicAdd(gradx + 3 * j + 1, gx[1]); atomicAdd(gradx + 3 * j + 2, gx[2]);
+      atomicAdd(gradx + 3 * jl, gx[0]); atomicAdd(gradx + 3 * jl + 1, gx[1]); atomicAdd(gradx + 3 * jl + 2, gx[2]);
    }
    if (bz) {
-      atomicAdd(bz + 3 * j, uz[0]); atomicAdd(bz + 3 * j + 1, uz[1]); atomicAdd(bz + 3 * j + 2, uz[2]);
+      atomicAdd(bz + 3 * jl, uz[0]); atomicAdd(bz + 3 * jl + 1, uz[1]); atomicAdd(bz + 3 * jl + 2, uz[2]);
    }
 }
 
 void eeq_build_b_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q,
                     const double* atrace, const double* thalf, const double* dcndr, double* Bout, int64_t ldb,
-                    double* gradx, const double* zvec, double* bz, bool pair_in_b) {
-   dim3 grid((unsigned)((mol.nat + 127) / 128), (unsigned)((mol.nat + BB_KCHUNK - 1) / BB_KCHUNK));
+                    double* gradx, const double* zvec, double* bz, bool pair_in_b, int jb, int je) {
+   if (je < 0) je = mol.nat;
+   dim3 grid((unsigned)((je - jb + 127) / 128), (unsigned)((mol.nat + BB_KCHUNK - 1) / BB_KCHUNK));
    MCHRG_LAUNCH(ctx, eeq_build_b0d_kernel, grid, 128, 0, mol.nat, mol.xyz, rad_a, q, atrace, thalf, dcndr, Bout, ldb,
-                gradx, zvec, bz, pair_in_b ? 1 : 0);
+                gradx, zvec, bz, pair_in_b ? 1 : 0, jb, je);
 }
 
 }  // namespace mchrg

@@ -38,8 +38,10 @@ void eeq_pair_rows_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* 
 // dcndr may be nullptr (pure dadr, get_coulomb_derivs); Bout may be nullptr (gradient only).
 // pair_in_b: the off-diagonal pair terms are already stored in Bout (periodic path) and are
 // updated in place instead of being evaluated from the non-periodic pair formula.
+// [jb, je): atom (row) block to build; rows of Bout / gradx / bz are numbered within the block
+// (multi-GPU: every rank owns a block of dq/dr rows, the right-side solves act on rows independently).
 void eeq_build_b_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q,
                     const double* atrace, const double* thalf, const double* dcndr, double* Bout, int64_t ldb,
-                    double* gradx, const double* zvec, double* bz, bool pair_in_b = false);
+                    double* gradx, const double* zvec, double* bz, bool pair_in_b = false, int jb = 0, int je = -1);
 
 }  // namespace mchrg
