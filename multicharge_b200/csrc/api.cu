@@ -1101,7 +1101,7 @@ int mchrg_b200_dgemm(mchrg_b200_context* ctx, char transb, int64_t m, int64_t n,
    return guarded(ctx, [&]() {
       const bool tb = (transb == 't' || transb == 'T');
       if (m <= 0 || n <= 0 || k <= 0 || !a || !b || !c) fail(MCHRG_B200_ERR_ARG, "dgemm: invalid argument");
-      const int64_t mp = round_up(m, TILE), np = round_up(n, TILE), kp = round_up(k, 16);
+      const int64_t mp = round_up(m, TILE), np = round_up(n, TILE), kp = round_up(k, 32);
       const double* sa = ctx->in(a, (size_t)lda * k);
       const double* sb = ctx->in(b, (size_t)ldb * (tb ? k : n));
       double* dc = ctx->out(c, (size_t)ldc * n, /*preload=*/true);

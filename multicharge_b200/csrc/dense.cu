@@ -108,36 +108,40 @@ dgemm_dmma_kernel(int64_t kdim, double alpha, const double* __restrict__ A, int6
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-   const int nk = (int)(kdim / BK);
-#pragma unroll
-   for (int s = 0; s < STAGES - 1; ++s) {
-      if (s < nk) load_stage(s, (int64_t)s * BK);
-      cp_async_commit();
-   }
-
-   for (int kt = 0; kt < nk; ++kt) {
-      cp_async_wait<STAGES - 2>();
+   // Two super-stages of 2 x BK = 32 k-columns: one barrier and one cp.async group per 32 k-columns.
+   // While pair p is multiplied (8 k4-steps x 16 DMMA per warp, ~8k cycles per SM sub-partition) the
+   // loads of pair p+1 are in flight.
+   const int np2 = (int)(kdim / (2 * BK));
+   load_stage(0, 0);
+   load_stage(1, BK);
+   cp_async_commit();
+   for (int pr = 0; pr < np2; ++pr) {
+      cp_async_wait<0>();
       __syncthreads();
-      {
-         const int nxt = kt + STAGES - 1;
-         if (nxt < nk) load_stage(nxt % STAGES, (int64_t)nxt * BK);
+      if (pr + 1 < np2) {
+         const int sb = ((pr + 1) & 1) * 2;
+         load_stage(sb, (int64_t)(pr + 1) * 2 * BK);
+         load_stage(sb + 1, (int64_t)(pr + 1) * 2 * BK + BK);
          cp_async_commit();
       }
-      const double* As = smem + (size_t)(kt % STAGES) * STAGE;
-      const double* Bs = As + A_STAGE;
 #pragma unroll
-      for (int kk = 0; kk < BK / 4; ++kk) {
-         double a[4], b[4];
+      for (int half = 0; half < 2; ++half) {
+         const double* As = smem + (size_t)((pr & 1) * 2 + half) * STAGE;
+         const double* Bs = As + A_STAGE;
 #pragma unroll
-         for (int mt = 0; mt < 4; ++mt) a[mt] = As[(kk * 4 + t) * LDAS + wm * 32 + mt * 8 + g];
+         for (int kk = 0; kk < BK / 4; ++kk) {
+            double a[4], b[4];
 #pragma unroll
-         for (int nt = 0; nt < 4; ++nt)
-            b[nt] = TRANSB ? Bs[(kk * 4 + t) * LDBT + wn * 32 + nt * 8 + g]
-                           : Bs[(wn * 32 + nt * 8 + g) * LDBN + kk * 4 + t];
+            for (int mt = 0; mt < 4; ++mt) a[mt] = As[(kk * 4 + t) * LDAS + wm * 32 + mt * 8 + g];
 #pragma unroll
-         for (int mt = 0; mt < 4; ++mt)
+            for (int nt = 0; nt < 4; ++nt)
+               b[nt] = TRANSB ? Bs[(kk * 4 + t) * LDBT + wn * 32 + nt * 8 + g]
+                              : Bs[(wn * 32 + nt * 8 + g) * LDBN + kk * 4 + t];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+               for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+         }
       }
    }
    cp_async_wait<0>();
@@ -175,7 +179,7 @@ void dgemm_padded(mchrg_b200_context* ctx, bool transb, int64_t m, int64_t n, in
                   const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
                   int64_t ldc, bool lower_only) {
    if (m == 0 || n == 0) return;
-   if (m % gemm::BM || n % gemm::BN || k % gemm::BK || (lda & 1) || (ldb & 1))
+   if (m % gemm::BM || n % gemm::BN || k % (2 * gemm::BK) || (lda & 1) || (ldb & 1))
       fail(MCHRG_B200_ERR_ARG, "dgemm_padded: unpadded operand (m=%lld n=%lld k=%lld lda=%lld ldb=%lld)",
            (long long)m, (long long)n, (long long)k, (long long)lda, (long long)ldb);
    gemm_setup_once();
