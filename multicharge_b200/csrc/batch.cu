@@ -13,6 +13,7 @@
 // Molecules are grouped by padded order NP (one launch per class) so shared memory, and with it the
 // number of resident CTAs per SM, matches the molecule size.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "model.cuh"
@@ -40,7 +41,13 @@ struct Args {
    const double* par;    // model parameters [slot * nid + (Z-1)]
    int nid;
    double kcn, cutoff2, cut;
-   int np;               // padded order of the class (multiple of 16)
+   int np;               // padded order of the class (multiple of 16); split pair phases: capacity of the launch
+   // split path (PH != 0): the pair phases and the factorisation run as separate kernels
+   double* scratch;      // packed matrices of all molecules of the chunk
+   const int64_t* soff;  // [nmol_chunk] start of molecule m in scratch
+   double* vecg;         // [3 * ntot_chunk]: xvec | thalf | fcut per atom
+   double* lamg;         // [nmol_chunk] Lagrange multiplier
+   int64_t ntot;         // atoms in the chunk
 };
 
 __host__ __device__ inline size_t smem_doubles(int np) {
@@ -148,30 +155,42 @@ __device__ __forceinline__ void update_tile(double* __restrict__ A, const double
       }
 }
 
-template <int NT>
+// PH selects the phases a launch executes:
+//   0  everything in one kernel, matrix in shared memory (small batches)
+//   1  pair phase A: coordination number, xvec, Coulomb block -> global scratch           (light smem)
+//   2  factorisation + solves + Schur complement, matrix loaded from scratch into smem    (heavy smem)
+//   3  pair phase C: energy and gradient, pair scalars parked in scratch                  (light smem)
+// Split launches let the FP64-bound pair phases of one chunk of molecules co-reside on the SMs with the
+// latency-bound factorisation CTAs of another chunk.
+template <int NT, int PH>
 __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    extern __shared__ __align__(16) double sm[];
-   const int np = p.np;
-   const int ldp = np + 4;
-   double* A = sm;                           // packed lower, row-major: A[tri(i) + j], j <= i
-   double* P = A + (size_t)np * (np + 1) / 2;  // panel, k-major: P[c * ldp + i]
-   double* Ld = P + (size_t)KB * ldp;        // diagonal block Ld[r * 17 + c]
-   double* spare = Ld + KB * (KB + 1);       // KB doubles, unused
-   double* vec = spare + KB;
-   double* X = vec;            double* Y = X + np;        double* Z = Y + np;
-   double* rad2 = Z + np;      double* dself = rad2 + np; double* rcov = dself + np;
-   double* fcut = rcov + np;   double* xv = fcut + np;    double* th = xv + np;
-   double* b0 = th + np;       double* b1 = b0 + np;      double* qv = b1 + np;
-   double* rd = qv + np;       // reciprocal pivots 1 / L(i, i); later reused for thalf * q * fcut
-   double* scal = rd + np;     // [0] lambda, [1] s
-   __shared__ int sfail;
-
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    constexpr int NW = NT / 32;
    const int mol = p.perm[blockIdx.x];
    const int64_t off = p.offsets[mol];
    const int n = (int)(p.offsets[mol + 1] - off);
    const double charge = p.charge[mol];
+   constexpr bool MAT_IN_SMEM = (PH == 0 || PH == 2);
+   // pair phases work on the molecule's own padded order, the class launches on the class order
+   const int np = MAT_IN_SMEM ? p.np : ((n + KB - 1) / KB) * KB;
+   const int npv = p.np;  // stride of the per-atom vectors in shared memory
+   const int ldp = np + 4;
+   double* A = MAT_IN_SMEM ? sm : p.scratch + p.soff[mol];  // packed lower, row-major: A[tri(i) + j], j <= i
+   double* P = sm + (MAT_IN_SMEM ? (size_t)np * (np + 1) / 2 : 0);  // panel, k-major: P[c * ldp + i]
+   double* Ld = P + (MAT_IN_SMEM ? (size_t)KB * ldp : 0);            // diagonal block Ld[r * 17 + c]
+   double* spare = Ld + (MAT_IN_SMEM ? KB * (KB + 1) : 0);           // KB doubles, unused
+   double* vec = spare + (MAT_IN_SMEM ? KB : 0);
+   double* X = vec;            double* Y = X + npv;        double* Z = Y + npv;
+   double* rad2 = Z + npv;     double* dself = rad2 + npv; double* rcov = dself + npv;
+   double* fcut = rcov + npv;  double* xv = fcut + npv;    double* th = xv + npv;
+   double* b0 = th + npv;      double* b1 = b0 + npv;      double* qv = b1 + npv;
+   double* rd = qv + npv;      // reciprocal pivots 1 / L(i, i); later reused for thalf * q * fcut
+   double* scal = rd + npv;    // [0] lambda, [1] s
+   __shared__ int sfail;
+   double* xv_g = p.vecg + off;
+   double* th_g = p.vecg + p.ntot + off;
+   double* fc_g = p.vecg + 2 * p.ntot + off;
 
    // ---- load atoms and per-element parameters (chi, rad, eta, kcnchi, rcov = slots 0..4) ----
    if (tid == 0) sfail = 0;
@@ -194,9 +213,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    }
    __syncthreads();
 
+   const int ntri_n = tri(n);
+   if (PH == 0 || PH == 1) {
    // ---- erf coordination number with log-cut (mctc_ncoord): every unique pair once, the counts are
    //      parked in the (still unused) matrix storage and summed per row afterwards ----
-   const int ntri_n = tri(n);
    for (int e = tid; e < ntri_n; e += NT) {
       int i, j;
       tri_decode(e, i, j);
@@ -205,9 +225,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          const double dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
          const double r2 = dx * dx + dy * dy + dz * dz;
          if (!(r2 > p.cutoff2 || r2 < 1.0e-12)) {
-            // 1/2 (1 + erf(-kcn (r - rc)/rc)) = 1/2 erfc(kcn (r/rc - 1))
+            // 1/2 (1 + erf(-kcn (r - rc)/rc))
             const double r1 = r2 * rsqrt(r2);
-            c = 0.5 * erfc(p.kcn * (r1 / (rcov[i] + rcov[j]) - 1.0));
+            c = 0.5 + 0.5 * erf(p.kcn * (1.0 - r1 / (rcov[i] + rcov[j])));
          }
       }
       A[e] = c;
@@ -253,7 +273,25 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       A[e] = v;
    }
    __syncthreads();
+   }  // PH 0 / 1
+   if (PH == 1) {  // hand xvec, thalf, fcut to the later phases
+      for (int i = tid; i < n; i += NT) { xv_g[i] = xv[i]; th_g[i] = th[i]; fc_g[i] = fcut[i]; }
+      return;
+   }
+   if (PH == 2) {  // matrix and right-hand side from the pair phase
+      const double* src = p.scratch + p.soff[mol];
+      const int nsrc = tri(((n + KB - 1) / KB) * KB);  // molecule's own padded order (== class order here)
+      for (int e = tid; e < nsrc; e += NT) A[e] = src[e];
+      for (int i = tid; i < n; i += NT) xv[i] = xv_g[i];
+      __syncthreads();
+   }
+   if (PH == 3) {
+      for (int i = tid; i < n; i += NT) { xv[i] = xv_g[i]; th[i] = th_g[i]; fcut[i] = fc_g[i]; qv[i] = p.qvec[off + i]; }
+      if (tid == 0) scal[0] = p.lamg[mol];
+      __syncthreads();
+   }
 
+   if (PH == 0 || PH == 2) {
    // ---- blocked Cholesky, block 16, with look-ahead: the next diagonal block is factored by warp 0
    //      while the other warps finish the trailing update ----
    if (warp == 0) {
@@ -396,18 +434,31 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       if (lane == 0) { scal[0] = (sy - charge) / sz; scal[1] = sz; }
    }
    __syncthreads();
+   {
+      const double lam2 = scal[0];
+      for (int i = tid; i < n; i += NT) {
+         const double q = b0[i] - lam2 * b1[i];
+         qv[i] = q;
+         p.qvec[off + i] = q;
+      }
+      if (tid == 0) {
+         p.status[mol] = 0;
+         if (PH == 2) p.lamg[mol] = lam2;
+      }
+   }
+   if (PH == 2) return;
+   __syncthreads();
+   }  // PH 0 / 2
+
    const double lam = scal[0];
    double* wf = rd;  // pivots are no longer needed
    for (int i = tid; i < n; i += NT) {
-      const double q = b0[i] - lam * b1[i];
-      qv[i] = q;
+      const double q = qv[i];
       wf[i] = th[i] * q * fcut[i];
-      p.qvec[off + i] = q;
       // energy (type.F90:255-262): q_i (0.5 (J q)_i - x_i) with (J q)_i = x_i - lambda from the solved system
       // J q + lambda 1 = x (residual of the Cholesky solve ~ n eps |J| |q|)
       if (p.energy) p.energy[off + i] = q * (0.5 * (xv[i] - lam) - xv[i]);
    }
-   if (tid == 0) p.status[mol] = 0;
    if (!p.gradient) return;
    __syncthreads();
 
@@ -453,19 +504,258 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split path, factorisation phase: LEFT-LOOKING blocked Cholesky that leaves the matrix in the global
+// scratch (L2 resident: <= 174 KB per molecule) and keeps only the current 16-wide block column in
+// shared memory.  ~36 KB of shared memory per CTA instead of ~175 KB, so 6 CTAs are resident per SM
+// and the serial pieces of one molecule (diagonal block, row solves) hide behind the DMMA updates
+// of the others.
+//   per block column k0:  Cb = A(k0:, k0:k0+16) - L(k0:, :k0) L(k0:k0+16, :k0)^T      (DMMA, fragments
+//                          straight from global / L1)
+//                          diagonal block in one warp, row solves one thread per row, L written back
+//                          forward substitution of [x 1] fused (row-oriented)
+//   then the backward substitution by block columns and the Schur complement of the constraint.
+// ------------------------------------------------------------------------------------------------
+constexpr int CBS = KB + 1;  // row stride of the block column buffer
+
+__host__ __device__ inline size_t smem_doubles_ll(int np) { return (size_t)np * CBS + 3 * (size_t)np + 2 * 32 * 16 + 8; }
+
 template <int NT>
-static void launch_class(mchrg_b200_context* ctx, const Args& a, int count) {
-   const size_t smem = smem_doubles(a.np) * sizeof(double);
-   static size_t configured = 0;
-   if (smem > configured) {
-      MCHRG_CUDA(cudaFuncSetAttribute(eeq_batch_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(smem_doubles(NP_MAX) * sizeof(double))));
-      configured = smem_doubles(NP_MAX) * sizeof(double);
+__global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
+   extern __shared__ __align__(16) double sm[];
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   constexpr int NW = NT / 32;
+   const int mol = p.perm[blockIdx.x];
+   const int64_t off = p.offsets[mol];
+   const int n = (int)(p.offsets[mol + 1] - off);
+   const int np = p.np;
+   const double charge = p.charge[mol];
+   double* S = p.scratch + p.soff[mol];  // packed lower, row-major
+   double* Cb = sm;                      // Cb[(i - k0) * CBS + c]
+   double* b0 = Cb + (size_t)np * CBS;
+   double* b1 = b0 + np;
+   double* rd = b1 + np;
+   double* red = rd + np;                // [NW][32] partial sums of the backward substitution
+   double* scal = red + 2 * 32 * 16;
+   __shared__ int sfail;
+   __shared__ double fw[2 * KB];
+   const double* xv_g = p.vecg + off;
+   if (tid == 0) sfail = 0;
+   for (int i = tid; i < np; i += NT) {
+      b0[i] = (i < n) ? xv_g[i] : 0.0;
+      b1[i] = (i < n) ? 1.0 : 0.0;
    }
-   MCHRG_LAUNCH(ctx, eeq_batch_kernel<NT>, (unsigned)count, NT, smem, a);
+   __syncthreads();
+   const int g = lane >> 2, t = lane & 3;
+
+   for (int k0 = 0; k0 < np; k0 += KB) {
+      // ---- block column with the left-looking update, 16-row tiles per warp ----
+      const int nrt = (np - k0) / KB;
+      for (int ti = warp; ti < nrt; ti += NW) {
+         const int i0 = k0 + KB * ti;
+         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+         const double* ra0 = S + tri(i0 + g) + t;
+         const double* ra1 = S + tri(i0 + 8 + g) + t;
+         const double* rb0 = S + tri(k0 + g) + t;
+         const double* rb1 = S + tri(k0 + 8 + g) + t;
+#pragma unroll 4
+         for (int j0 = 0; j0 < k0; j0 += 4) {
+            const double a0 = ra0[j0], a1 = ra1[j0], c0 = rb0[j0], c1 = rb1[j0];
+            dmma884(acc[0][0][0], acc[0][0][1], a0, c0);
+            dmma884(acc[0][1][0], acc[0][1][1], a0, c1);
+            dmma884(acc[1][0][0], acc[1][0][1], a1, c0);
+            dmma884(acc[1][1][0], acc[1][1][1], a1, c1);
+         }
+#pragma unroll
+         for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ntl = 0; ntl < 2; ++ntl) {
+               const int row = i0 + 8 * mt + g, col = 8 * ntl + 2 * t;  // col within the block column
+               const double* src = S + tri(row) + k0 + col;
+               double* dst = Cb + (row - k0) * CBS + col;
+               // entries right of the diagonal do not exist in the packed storage (and are never used)
+               dst[0] = (k0 + col <= row) ? src[0] - acc[mt][ntl][0] : 0.0;
+               dst[1] = (k0 + col + 1 <= row) ? src[1] - acc[mt][ntl][1] : 0.0;
+            }
+      }
+      // row-oriented forward substitution, cooperative part: fw(r, h) = L(k0 + r, :k0) . w_h(:k0)
+      for (int rr = warp; rr < KB; rr += NW) {
+         const double* lrow = S + tri(k0 + rr);
+         double f0 = 0.0, f1 = 0.0;
+         for (int j = lane; j < k0; j += 32) {
+            const double l = lrow[j];
+            f0 = fma(l, b0[j], f0);
+            f1 = fma(l, b1[j], f1);
+         }
+         f0 = warp_sum(f0);
+         f1 = warp_sum(f1);
+         if (lane == 0) { fw[rr] = f0; fw[KB + rr] = f1; }
+      }
+      __syncthreads();
+      // ---- diagonal block (warp 0, registers + shuffles), fused forward substitution of [x 1] ----
+      if (warp == 0) {
+         const int r = lane & 15, h = lane >> 4;
+         double m[8];
+#pragma unroll
+         for (int k = 0; k < 8; ++k) m[k] = Cb[r * CBS + 2 * k + h];
+         int bad = 0;
+#pragma unroll
+         for (int c = 0; c < KB; ++c) {
+            const int src_h = (c & 1) << 4;
+            const double piv = shfl_d(m[c >> 1], c + src_h);
+            bad = (!(piv > 0.0) && bad == 0) ? (k0 + c + 1) : bad;
+            const double rinv = rsqrt(piv);
+            const double lrc = shfl_d(m[c >> 1], r + src_h) * rinv;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+               const int c2 = 2 * k + h;
+               const double lc2 = shfl_d(m[c >> 1], c2 + src_h) * rinv;
+               if (c2 > c && c2 <= r) m[k] = fma(-lrc, lc2, m[k]);
+            }
+            if (h == (c & 1)) {
+               if (r == c) m[c >> 1] = piv * rinv;
+               else if (r > c) m[c >> 1] = lrc;
+            }
+            if (lane == 0) rd[k0 + c] = rinv;
+         }
+#pragma unroll
+         for (int k = 0; k < 8; ++k) {
+            const int c = 2 * k + h;
+            Cb[r * CBS + c] = (c <= r) ? m[k] : 0.0;
+            if (c <= r) S[tri(k0 + r) + k0 + c] = m[k];
+         }
+         if (bad && lane == 0) sfail = bad;
+         // w(k0 + r) = (b(k0 + r) - L(k0 + r, :k0) w(:k0)), then the 16 x 16 triangular solve; lane = (row r, rhs h)
+         {
+            const double s = (h ? b1 : b0)[k0 + r] - fw[h * KB + r];
+            // triangular solve with the factored block: L(r, c) is read back from Cb (written above)
+            __syncwarp();
+            double v = s;
+#pragma unroll
+            for (int c = 0; c < KB; ++c) {
+               const double wc = shfl_d(v, c + (h << 4)) * rd[k0 + c];
+               if (r == c) v = wc;
+               else if (r > c) v = fma(-Cb[r * CBS + c], wc, v);
+            }
+            (h ? b1 : b0)[k0 + r] = v;
+         }
+      }
+      __syncthreads();
+      if (sfail) break;
+      // ---- rows below the diagonal block: a <- a * inv(L_kk)^T, written back to the scratch ----
+      // (NT >= np - 16 for every launch configuration: one row per thread, no loop for the compiler to hoist
+      //  the 120 block entries out of)
+      const int lr = KB + tid;
+      if (lr < np - k0) {
+         double a[KB];
+         const double* row = Cb + lr * CBS;
+#pragma unroll
+         for (int c = 0; c < KB; ++c) a[c] = row[c];
+#pragma unroll
+         for (int c = 0; c < KB; ++c) {
+            a[c] *= rd[k0 + c];
+#pragma unroll
+            for (int c2 = c + 1; c2 < KB; ++c2) a[c2] = fma(-a[c], Cb[c2 * CBS + c], a[c2]);
+         }
+         double* dst = S + tri(k0 + lr) + k0;
+#pragma unroll
+         for (int c = 0; c < KB; ++c) dst[c] = a[c];
+      }
+      __syncthreads();
+   }
+   if (sfail) {
+      const double nan = __longlong_as_double(0x7ff8000000000000LL);
+      for (int i = tid; i < n; i += NT) {
+         p.qvec[off + i] = nan;
+         if (p.energy) p.energy[off + i] = nan;
+         if (p.gradient) p.gradient[3 * (off + i)] = p.gradient[3 * (off + i) + 1] = p.gradient[3 * (off + i) + 2] = nan;
+      }
+      if (tid == 0) {
+         p.status[mol] = sfail;
+         p.lamg[mol] = nan;
+      }
+      return;
+   }
+
+   // ---- backward substitution L^T [y z] = [w_x w_1] by block columns ----
+   for (int k0 = np - KB; k0 >= 0; k0 -= KB) {
+      // t(c, h) = sum_{i > k0 + 15} L(i, k0 + c) y_h(i): lane = (column c, rhs h), warps stride the rows
+      // (one coalesced 128-byte read of L(i, k0:k0+16) per row), then a block reduction over the warps
+      {
+         const int c = lane & 15, h = lane >> 4;
+         const double* yv = h ? b1 : b0;
+         double acc0 = 0.0, acc1 = 0.0;
+         int i = k0 + KB + warp;
+         for (; i + NW < np; i += 2 * NW) {
+            acc0 = fma(S[tri(i) + k0 + c], yv[i], acc0);
+            acc1 = fma(S[tri(i + NW) + k0 + c], yv[i + NW], acc1);
+         }
+         if (i < np) acc0 = fma(S[tri(i) + k0 + c], yv[i], acc0);
+         red[warp * 32 + lane] = acc0 + acc1;
+      }
+      __syncthreads();
+      if (warp == 0) {
+         const int r = lane & 15, h = lane >> 4;
+         double v = (h ? b1 : b0)[k0 + r];
+         for (int w = 0; w < NW; ++w) v -= red[w * 32 + lane];
+#pragma unroll
+         for (int c = KB - 1; c >= 0; --c) {
+            const double yc = shfl_d(v, c + (h << 4)) * rd[k0 + c];
+            if (r == c) v = yc;
+            else if (r < c) v = fma(-S[tri(k0 + c) + k0 + r], yc, v);
+         }
+         (h ? b1 : b0)[k0 + r] = v;
+      }
+      __syncthreads();
+   }
+   if (warp == 0) {
+      double sy = 0.0, sz = 0.0;
+      for (int i = lane; i < n; i += 32) { sy += b0[i]; sz += b1[i]; }
+      sy = warp_sum(sy);
+      sz = warp_sum(sz);
+      if (lane == 0) scal[0] = (sy - charge) / sz;
+   }
+   __syncthreads();
+   const double lam = scal[0];
+   for (int i = tid; i < n; i += NT) p.qvec[off + i] = b0[i] - lam * b1[i];
+   if (tid == 0) {
+      p.status[mol] = 0;
+      p.lamg[mol] = lam;
+   }
 }
 
+template <int NT>
+static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count) {
+   const size_t smem = smem_doubles_ll(a.np) * sizeof(double);
+   static bool configured = false;
+   if (!configured) {
+      MCHRG_CUDA(cudaFuncSetAttribute(eeq_factor_ll_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(smem_doubles_ll(NP_MAX) * sizeof(double))));
+      configured = true;
+   }
+   MCHRG_LAUNCH(ctx, eeq_factor_ll_kernel<NT>, (unsigned)count, NT, smem, a);
+}
 
+__host__ inline size_t smem_doubles_pair(int npv) { return (size_t)NVEC * npv + 8; }
+
+template <int NT, int PH>
+static void launch_class(mchrg_b200_context* ctx, const Args& a, int count) {
+   const bool heavy = (PH == 0 || PH == 2);
+   const size_t smem = (heavy ? smem_doubles(a.np) : smem_doubles_pair(a.np)) * sizeof(double);
+   static size_t configured = 0;
+   if (smem > configured) {
+      const size_t cap = (heavy ? smem_doubles(NP_MAX) : smem_doubles_pair(NP_MAX)) * sizeof(double);
+      MCHRG_CUDA(cudaFuncSetAttribute(eeq_batch_kernel<NT, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+      configured = cap;
+   }
+   MCHRG_LAUNCH(ctx, (eeq_batch_kernel<NT, PH>), (unsigned)count, NT, smem, a);
+}
+
+}  // namespace batch
+}  // namespace mchrg
+
+namespace mchrg {
+namespace batch {
 
 // bucket the molecules [m0, m1) by padded order; returns the class-sorted permutation (chunk-local ids)
 // and the start of every class in it
@@ -490,6 +780,7 @@ static void bucket(const std::vector<int64_t>& hoff, int32_t m0, int32_t m1, std
 // Launch every size class of one chunk: the shared-memory-heavy classes (one CTA per SM, latency bound in the
 // factorisation) on `big`, the light classes on `small`; their CTAs fit beside each other on an SM, so the
 // light ones fill the idle FP64 issue slots.  Largest classes first.
+template <int PH>
 static void launch_chunk(mchrg_b200_context* ctx, Args a, const int32_t* dperm, const std::vector<size_t>& cls_start,
                          const std::vector<int>& cls_count, cudaStream_t big, cudaStream_t small) {
    for (int c = NP_MAX / KB; c >= 1; --c) {
@@ -497,10 +788,100 @@ static void launch_chunk(mchrg_b200_context* ctx, Args a, const int32_t* dperm, 
       a.np = c * KB;
       a.perm = dperm + cls_start[c];
       StreamScope on(ctx, a.np > 112 ? big : small);
-      if (a.np <= 64) launch_class<128>(ctx, a, cls_count[c]);
-      else if (a.np <= 128) launch_class<256>(ctx, a, cls_count[c]);
-      else launch_class<512>(ctx, a, cls_count[c]);
+      if (a.np <= 64) launch_class<128, PH>(ctx, a, cls_count[c]);
+      else if (a.np <= 128) launch_class<256, PH>(ctx, a, cls_count[c]);
+      else launch_class<512, PH>(ctx, a, cls_count[c]);
    }
+}
+
+// pair phases (PH 1 / 3): one launch over all molecules of the chunk (the class-sorted permutation keeps
+// neighbouring CTAs similar in cost); shared memory holds the per-atom vectors only
+template <int PH>
+static void launch_pairs(mchrg_b200_context* ctx, Args a, const int32_t* dperm, int count) {
+   a.np = NP_MAX;
+   a.perm = dperm;
+   launch_class<256, PH>(ctx, a, count);
+}
+
+
+// scratch layout of the split path for the molecules [m0, m1): soff[m - m0] = start of molecule m's packed
+// matrix (order padded to 16); returns the total number of doubles
+static int64_t plan_scratch(const std::vector<int64_t>& hoff, int32_t m0, int32_t m1, std::vector<int64_t>& soff) {
+   soff.resize((size_t)(m1 - m0));
+   int64_t total = 0;
+   for (int32_t m = m0; m < m1; ++m) {
+      const int64_t n = hoff[m + 1] - hoff[m];
+      const int64_t npm = (n + KB - 1) / KB * KB;
+      soff[m - m0] = total;
+      total += npm * (npm + 1) / 2;
+   }
+   return total;
+}
+
+// One chunk of the split path.  `a` addresses the chunk (offsets / perm ids in the same id space).
+//   pair phase A on `sa`  ->  factorisation classes on the two high-priority streams  ->  pair phase C on `sc`
+// `ready` (may be null) gates phase A (inputs staged); returns the event that marks the chunk's outputs complete.
+static bool factor_in_smem() {  // MCHRG_B200_FACTOR=smem selects the right-looking shared-memory kernel
+   const char* e = std::getenv("MCHRG_B200_FACTOR");
+   return e && e[0] == 's';
+}
+
+// `gate` (in/out): events recorded on the factorisation streams right before the previous chunk's
+// factorisation kernels; phase A of this chunk waits for them, so that those shared-memory-heavy CTAs are
+// placed on the SMs BEFORE this chunk's light pair CTAs can fill them (a heavy CTA only fits on an SM whose
+// shared memory is still free).
+static cudaEvent_t run_chunk_split(mchrg_b200_context* ctx, const Args& a, const int32_t* dperm, int count,
+                                   const std::vector<size_t>& cls_start, const std::vector<int>& cls_count,
+                                   cudaEvent_t ready, cudaStream_t sa, cudaStream_t sc, cudaEvent_t gate[2]) {
+   if (ready) MCHRG_CUDA(cudaStreamWaitEvent(sa, ready, 0));
+   if (gate[0]) MCHRG_CUDA(cudaStreamWaitEvent(sa, gate[0], 0));
+   if (gate[1]) MCHRG_CUDA(cudaStreamWaitEvent(sa, gate[1], 0));
+   {
+      StreamScope on(ctx, sa);
+      launch_pairs<1>(ctx, a, dperm, count);
+   }
+   cudaEvent_t eA = ctx->next_event();
+   MCHRG_CUDA(cudaEventRecord(eA, sa));
+   MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_hi, eA, 0));
+   MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_hi2, eA, 0));
+   gate[0] = ctx->next_event();
+   gate[1] = ctx->next_event();
+   MCHRG_CUDA(cudaEventRecord(gate[0], ctx->stream_hi));
+   MCHRG_CUDA(cudaEventRecord(gate[1], ctx->stream_hi2));
+   if (factor_in_smem()) {
+      launch_chunk<2>(ctx, a, dperm, cls_start, cls_count, ctx->stream_hi, ctx->stream_hi2);
+   } else {  // left-looking, matrix stays in the scratch: light CTAs, classes alternate between the two streams
+      Args b = a;
+      int flip = 0;
+      for (int c = NP_MAX / KB; c >= 1; --c) {
+         if (cls_count[c] == 0) continue;
+         b.np = c * KB;
+         b.perm = dperm + cls_start[c];
+         StreamScope on(ctx, (flip++ & 1) ? ctx->stream_hi2 : ctx->stream_hi);
+         if (b.np <= 96) launch_factor_ll<128>(ctx, b, cls_count[c]);
+         else launch_factor_ll<256>(ctx, b, cls_count[c]);
+      }
+   }
+   cudaEvent_t eB1 = ctx->next_event(), eB2 = ctx->next_event();
+   MCHRG_CUDA(cudaEventRecord(eB1, ctx->stream_hi));
+   MCHRG_CUDA(cudaEventRecord(eB2, ctx->stream_hi2));
+   MCHRG_CUDA(cudaStreamWaitEvent(sc, eB1, 0));
+   MCHRG_CUDA(cudaStreamWaitEvent(sc, eB2, 0));
+   if (a.energy || a.gradient) {
+      StreamScope on(ctx, sc);
+      launch_pairs<3>(ctx, a, dperm, count);
+   }
+   cudaEvent_t eC = ctx->next_event();
+   MCHRG_CUDA(cudaEventRecord(eC, sc));
+   return eC;
+}
+
+static int batch_mode() {  // 0 auto, 1 fused, 2 split  (MCHRG_B200_BATCH_MODE = fused | split)
+   const char* e = std::getenv("MCHRG_B200_BATCH_MODE");
+   if (!e) return 0;
+   if (e[0] == 'f') return 1;
+   if (e[0] == 's') return 2;
+   return 0;
 }
 
 }  // namespace batch
@@ -532,6 +913,7 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
                  (long long)n, batch::NP_MAX);
       }
       batch::Args a;
+      a.scratch = nullptr; a.soff = nullptr; a.vecg = nullptr; a.lamg = nullptr; a.ntot = 0;
       a.par = model->d_par;
       a.nid = model->nid;
       a.kcn = model->ncoord.kcn;
@@ -546,6 +928,90 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
                            !mchrg_b200_context::is_device_ptr(qvec) && !mchrg_b200_context::is_device_ptr(status) &&
                            (!energy || !mchrg_b200_context::is_device_ptr(energy)) &&
                            (!gradient || !mchrg_b200_context::is_device_ptr(gradient));
+      const int mode = batch::batch_mode();
+      const bool split = (mode == 2) || (mode == 0 && nmol >= 4096);
+      if (split && (!host_io || ntot < (size_t)1 << 18)) {
+         // Split path, data on the device (or small enough to stage at once): chunks of molecules flow through
+         //   pair phase A -> factorisation -> pair phase C   on different streams, so the FP64-bound pair
+         // kernels of one chunk share the SMs with the latency-bound factorisation CTAs of its neighbours.
+         a.offsets = ctx->in(offsets, (size_t)nmol + 1);
+         a.num = ctx->in(num, ntot);
+         a.xyz = ctx->in(xyz, 3 * ntot);
+         a.charge = ctx->in(charge, (size_t)nmol);
+         a.qvec = ctx->out(qvec, ntot);
+         a.energy = ctx->out(energy, ntot);
+         a.gradient = ctx->out(gradient, 3 * ntot);
+         a.status = ctx->out(status, (size_t)nmol);
+         std::vector<int64_t> soff;
+         const int64_t nscr = batch::plan_scratch(hoff, 0, nmol, soff);
+         a.scratch = ctx->alloc<double>((size_t)nscr);
+         int64_t* d_soff = ctx->alloc<int64_t>(nmol);
+         MCHRG_CUDA(cudaMemcpyAsync(d_soff, soff.data(), (size_t)nmol * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+         a.soff = d_soff;
+         a.vecg = ctx->alloc<double>(3 * ntot);
+         a.lamg = ctx->alloc<double>(nmol);
+         a.ntot = (int64_t)ntot;
+         const int nchunk = (int)std::min<int64_t>(16, std::max<int64_t>(1, nmol / 4096));
+         std::vector<int32_t> all_perm;
+         std::vector<std::vector<size_t>> starts(nchunk);
+         std::vector<std::vector<int>> counts(nchunk);
+         std::vector<size_t> chunk_off(nchunk + 1, 0);
+         for (int c = 0; c < nchunk; ++c) {
+            const int32_t m0 = (int32_t)((int64_t)nmol * c / nchunk), m1 = (int32_t)((int64_t)nmol * (c + 1) / nchunk);
+            batch::bucket(hoff, m0, m1, perm, starts[c], counts[c]);
+            for (auto& v : perm) v += m0;  // global molecule ids
+            chunk_off[c] = all_perm.size();
+            all_perm.insert(all_perm.end(), perm.begin(), perm.end());
+         }
+         chunk_off[nchunk] = all_perm.size();
+         int32_t* dperm = ctx->alloc<int32_t>(nmol);
+         MCHRG_CUDA(cudaMemcpyAsync(dperm, all_perm.data(), all_perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+         cudaEvent_t staged = ctx->next_event();
+         MCHRG_CUDA(cudaEventRecord(staged, ctx->stream));
+         if (std::getenv("MCHRG_B200_TRACE")) {  // debug: phases of the whole batch one after the other, timed
+            cudaEvent_t t[4];
+            for (auto& e : t) MCHRG_CUDA(cudaEventCreate(&e));
+            batch::Args b = a;
+            MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
+            MCHRG_CUDA(cudaEventRecord(t[0], ctx->stream));
+            for (int c = 0; c < nchunk; ++c) batch::launch_pairs<1>(ctx, b, dperm + chunk_off[c], (int)(chunk_off[c + 1] - chunk_off[c]));
+            MCHRG_CUDA(cudaEventRecord(t[1], ctx->stream));
+            for (int c = 0; c < nchunk; ++c) {
+               if (batch::factor_in_smem()) {
+                  batch::launch_chunk<2>(ctx, b, dperm + chunk_off[c], starts[c], counts[c], ctx->stream, ctx->stream);
+               } else {
+                  for (int k = batch::NP_MAX / batch::KB; k >= 1; --k) {
+                     if (counts[c][k] == 0) continue;
+                     batch::Args bb = b;
+                     bb.np = k * batch::KB;
+                     bb.perm = dperm + chunk_off[c] + starts[c][k];
+                     if (bb.np <= 96) batch::launch_factor_ll<128>(ctx, bb, counts[c][k]);
+                     else batch::launch_factor_ll<256>(ctx, bb, counts[c][k]);
+                  }
+               }
+            }
+            MCHRG_CUDA(cudaEventRecord(t[2], ctx->stream));
+            for (int c = 0; c < nchunk; ++c) batch::launch_pairs<3>(ctx, b, dperm + chunk_off[c], (int)(chunk_off[c + 1] - chunk_off[c]));
+            MCHRG_CUDA(cudaEventRecord(t[3], ctx->stream));
+            MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
+            float ms[3];
+            for (int k = 0; k < 3; ++k) MCHRG_CUDA(cudaEventElapsedTime(&ms[k], t[k], t[k + 1]));
+            fprintf(stderr, "[mchrg_b200 trace] nmol=%d pairA=%.2f ms factor=%.2f ms pairC=%.2f ms\n", nmol, ms[0], ms[1], ms[2]);
+            for (auto& e : t) cudaEventDestroy(e);
+            return 0;
+         }
+         cudaEvent_t last = nullptr;
+         cudaEvent_t gate[2] = {nullptr, nullptr};
+         for (int c = 0; c < nchunk; ++c) {
+            const int cnt = (int)(chunk_off[c + 1] - chunk_off[c]);
+            if (cnt == 0) continue;
+            last = batch::run_chunk_split(ctx, a, dperm + chunk_off[c], cnt, starts[c], counts[c], c == 0 ? staged : nullptr,
+                                          ctx->stream_aux, ctx->stream, gate);
+         }
+         (void)last;  // phase C runs on the main stream, which finish() synchronises
+         MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
+         return 0;
+      }
       if (!host_io || ntot < (size_t)1 << 18) {
          // device-resident (or small) batch: one chunk, inputs staged on the main stream
          batch::bucket(hoff, 0, nmol, perm, cls_start, cls_count);
@@ -562,7 +1028,7 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
          cudaEvent_t staged = ctx->next_event();
          MCHRG_CUDA(cudaEventRecord(staged, ctx->stream));
          MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_aux, staged, 0));
-         batch::launch_chunk(ctx, a, dperm, cls_start, cls_count, ctx->stream, ctx->stream_aux);
+         batch::launch_chunk<0>(ctx, a, dperm, cls_start, cls_count, ctx->stream, ctx->stream_aux);
          cudaEvent_t aux_done = ctx->next_event();
          MCHRG_CUDA(cudaEventRecord(aux_done, ctx->stream_aux));
          MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream, aux_done, 0));
@@ -582,6 +1048,8 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
       bounds[nchunk] = nmol;
       std::vector<std::vector<int64_t>> loc_off(nchunk);
       std::vector<std::vector<int32_t>> loc_perm(nchunk);
+      std::vector<std::vector<int64_t>> loc_soff(nchunk);
+      cudaEvent_t gate[2] = {nullptr, nullptr};
       cudaEvent_t start = ctx->next_event();
       MCHRG_CUDA(cudaEventRecord(start, ctx->stream));
       MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_in, start, 0));
@@ -614,12 +1082,29 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
          MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_aux, ev_in, 0));
          a.offsets = d_off; a.num = d_num; a.xyz = d_xyz; a.charge = d_chg;
          a.qvec = d_q; a.energy = d_e; a.gradient = d_g; a.status = d_st;
-         batch::launch_chunk(ctx, a, d_perm, cls_start, cls_count, ctx->stream, ctx->stream_aux);
-         cudaEvent_t aux_done = ctx->next_event();
-         MCHRG_CUDA(cudaEventRecord(aux_done, ctx->stream_aux));
-         MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream, aux_done, 0));
-         cudaEvent_t ev_done = ctx->next_event();
-         MCHRG_CUDA(cudaEventRecord(ev_done, ctx->stream));
+         cudaEvent_t ev_done;
+         if (split) {
+            std::vector<int64_t> soff;
+            const int64_t nscr = batch::plan_scratch(hoff, m0, m1, soff);
+            loc_soff[c] = soff;
+            a.scratch = ctx->alloc<double>((size_t)nscr);
+            int64_t* d_soff = ctx->alloc<int64_t>(mc);
+            MCHRG_CUDA(cudaMemcpyAsync(d_soff, loc_soff[c].data(), (size_t)mc * sizeof(int64_t), cudaMemcpyHostToDevice, in));
+            a.soff = d_soff;
+            a.vecg = ctx->alloc<double>(3 * na);
+            a.lamg = ctx->alloc<double>(mc);
+            a.ntot = (int64_t)na;
+            cudaEvent_t ev_in2 = ctx->next_event();
+            MCHRG_CUDA(cudaEventRecord(ev_in2, in));
+            ev_done = batch::run_chunk_split(ctx, a, d_perm, mc, cls_start, cls_count, ev_in2, ctx->stream_aux, ctx->stream, gate);
+         } else {
+            batch::launch_chunk<0>(ctx, a, d_perm, cls_start, cls_count, ctx->stream, ctx->stream_aux);
+            cudaEvent_t aux_done = ctx->next_event();
+            MCHRG_CUDA(cudaEventRecord(aux_done, ctx->stream_aux));
+            MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream, aux_done, 0));
+            ev_done = ctx->next_event();
+            MCHRG_CUDA(cudaEventRecord(ev_done, ctx->stream));
+         }
          MCHRG_CUDA(cudaStreamWaitEvent(out, ev_done, 0));
          MCHRG_CUDA(cudaMemcpyAsync(qvec + a0, d_q, na * sizeof(double), cudaMemcpyDeviceToHost, out));
          if (energy) MCHRG_CUDA(cudaMemcpyAsync(energy + a0, d_e, na * sizeof(double), cudaMemcpyDeviceToHost, out));

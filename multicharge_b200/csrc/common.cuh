@@ -51,6 +51,7 @@ struct mchrg_b200_context {
    int device = 0;
    cudaStream_t stream = nullptr;     // main stream: every entry point is ordered on it
    cudaStream_t stream_hi = nullptr;  // high-priority side stream (Cholesky panel look-ahead)
+   cudaStream_t stream_hi2 = nullptr; // second high-priority stream (batch factorisation kernels)
    cudaStream_t stream_aux = nullptr; // second normal-priority stream (batch size classes run concurrently)
    cudaStream_t stream_in = nullptr;  // host->device copies of pipelined batches
    cudaStream_t stream_out = nullptr; // device->host copies of pipelined batches
@@ -170,6 +171,7 @@ int guarded(mchrg_b200_context* ctx, F&& body) {
       ctx->active = ctx->stream;
       cudaStreamSynchronize(ctx->stream);
       if (ctx->stream_hi) cudaStreamSynchronize(ctx->stream_hi);
+      if (ctx->stream_hi2) cudaStreamSynchronize(ctx->stream_hi2);
       if (ctx->stream_aux) cudaStreamSynchronize(ctx->stream_aux);
       if (ctx->stream_in) cudaStreamSynchronize(ctx->stream_in);
       if (ctx->stream_out) cudaStreamSynchronize(ctx->stream_out);

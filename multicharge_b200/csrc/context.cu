@@ -133,6 +133,7 @@ int mchrg_b200_context_create(int device, mchrg_b200_context** out) {
       MCHRG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo));
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, prio_hi));
+      MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_hi2, cudaStreamNonBlocking, prio_hi));
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, prio_lo));
       MCHRG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
       MCHRG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
@@ -157,7 +158,7 @@ void mchrg_b200_context_destroy(mchrg_b200_context* ctx) {
       cudaStreamSynchronize(ctx->stream_hi);
       cudaStreamDestroy(ctx->stream_hi);
    }
-   for (cudaStream_t st : {ctx->stream_aux, ctx->stream_in, ctx->stream_out}) {
+   for (cudaStream_t st : {ctx->stream_aux, ctx->stream_in, ctx->stream_out, ctx->stream_hi2}) {
       if (st) {
          cudaStreamSynchronize(st);
          cudaStreamDestroy(st);

@@ -128,3 +128,44 @@ def test_batch_pipelined_host_path_equals_device_path(mc):
     assert np.all(host["status"] == 0)
     for key in ("qvec", "energy", "gradient"):
         assert np.array_equal(out[key].cpu().numpy(), host[key]), key
+
+
+def test_batch_split_path_equals_fused(mc, oracle, monkeypatch):
+    """The split path (pair phase A / factorisation / pair phase C as separate kernels on several streams)
+    produces the same bits as the fused one-kernel path, on host and on device buffers."""
+    import torch
+    from synth import batch
+    offsets, num, xyz, charge = batch(700, 31, nmin=1, nmax=208)
+    model = mc.new_eeq2019_batch_model()
+    monkeypatch.setenv("MCHRG_B200_BATCH_MODE", "fused")
+    fused = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    monkeypatch.setenv("MCHRG_B200_BATCH_MODE", "split")
+    split = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    assert np.array_equal(fused["status"], split["status"])
+    for key in ("qvec", "energy", "gradient"):  # different factorisation order: agreement to rounding, not to the bit
+        assert np.abs(fused[key] - split[key]).max() < 1e-12, key
+    dev = torch.device("cuda:0")
+    ntot = int(offsets[-1])
+    out = dict(qvec=torch.empty(ntot, dtype=torch.float64, device=dev), energy=torch.empty(ntot, dtype=torch.float64, device=dev),
+               gradient=torch.empty(ntot, 3, dtype=torch.float64, device=dev), status=torch.empty(700, dtype=torch.int32, device=dev))
+    mc.singlepoint_batch(model, torch.tensor(offsets, device=dev), torch.tensor(num, device=dev), torch.tensor(xyz, device=dev),
+                         torch.tensor(charge, device=dev), out=out)
+    torch.cuda.synchronize()
+    assert np.abs(out["gradient"].cpu().numpy() - fused["gradient"]).max() < 1e-12
+    # charges only (no pair phase C) and a failing molecule through the split path
+    q_only = mc.singlepoint_batch(model, offsets, num, xyz, charge, gradient=False)
+    assert np.abs(q_only["qvec"] - fused["qvec"]).max() < 1e-12 and np.abs(q_only["energy"] - fused["energy"]).max() < 1e-12
+    s = offsets[3]
+    num2, xyz2 = num.copy(), xyz.copy()
+    num2[s] = num2[s + 1] = 1
+    xyz2[s + 1] = xyz2[s] + np.array([0.4, 0.0, 0.0])
+    bad = mc.singlepoint_batch(model, offsets, num2, xyz2, charge)
+    assert bad["status"][3] > 0 and np.isnan(bad["qvec"][offsets[3]]) and np.isnan(bad["gradient"][offsets[3]]).all()
+    ok = np.ones(700, dtype=bool)
+    ok[3] = False
+    assert np.all(bad["status"][ok] == 0)
+    m = 10
+    sl = slice(offsets[m], offsets[m + 1])
+    mol = oracle.Mol(num[sl], xyz[sl], charge[m])
+    r = oracle.eeq_singlepoint(oracle.new_eeq2019_model(mol), mol)
+    assert np.abs(split["gradient"][sl] - r.gradient).max() < 1e-10
