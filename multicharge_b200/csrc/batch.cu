@@ -225,9 +225,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          const double dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
          const double r2 = dx * dx + dy * dy + dz * dz;
          if (!(r2 > p.cutoff2 || r2 < 1.0e-12)) {
-            // 1/2 (1 + erf(-kcn (r - rc)/rc))
+            // 1/2 (1 + erf(-kcn (r - rc)/rc)); beyond an argument of 6 erf is -1 to the last bit (count == 0)
             const double r1 = r2 * rsqrt(r2);
-            c = 0.5 + 0.5 * erf(p.kcn * (1.0 - r1 / (rcov[i] + rcov[j])));
+            const double a = p.kcn * (r1 / (rcov[i] + rcov[j]) - 1.0);
+            if (a < 6.0) c = 0.5 - 0.5 * erf(a);
          }
       }
       A[e] = c;
@@ -266,7 +267,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          const double dx = X[j] - X[i], dy = Y[j] - Y[i], dz = Z[j] - Z[i];
          const double r2 = dx * dx + dy * dy + dz * dz;
          const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
-         v = erf(r2 * rinv * gam) * rinv;  // erf(gamma r) / r
+         const double x = r2 * rinv * gam;
+         v = (x < 6.0) ? erf(x) * rinv : rinv;  // erf(gamma r) / r ; erf(x >= 6) == 1 in double precision
       } else {
          v = 0.0;
       }
@@ -475,12 +477,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          const double r2 = vx * vx + vy * vy + vz * vz;
          const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
          const double r1 = r2 * rinv, x = r1 * gam;  // x = gamma r
-         // dtmp = 2 gamma exp(-x^2) / (sqrt(pi) r^2) - erf(x) / r^3
-         f = rinv * rinv * (2.0 / SQRTPI * gam * exp(-x * x) - erf(x) * rinv) * qv[i] * qv[j];
+         // dtmp = 2 gamma exp(-x^2) / (sqrt(pi) r^2) - erf(x) / r^3 ; for x > 8.5: erf == 1, exp(-x^2) < 5e-32
+         const double dt = (x < 8.5) ? (2.0 / SQRTPI * gam * exp(-x * x) - erf(x) * rinv) : -rinv;
+         f = rinv * rinv * dt * qv[i] * qv[j];
          if (r2 <= p.cutoff2 && r2 >= 1.0e-12) {
             const double rci = 1.0 / (rcov[i] + rcov[j]);
             const double a = p.kcn * (r1 * rci - 1.0);
-            f += p.kcn / SQRTPI * rci * exp(-a * a) * rinv * (wf[i] + wf[j]);
+            if (a < 8.5) f += p.kcn / SQRTPI * rci * exp(-a * a) * rinv * (wf[i] + wf[j]);  // else < 5e-32
          }
       }
       A[e] = f;
@@ -643,23 +646,26 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
       __syncthreads();
       if (sfail) break;
       // ---- rows below the diagonal block: a <- a * inv(L_kk)^T, written back to the scratch ----
-      // (NT >= np - 16 for every launch configuration: one row per thread, no loop for the compiler to hoist
-      //  the 120 block entries out of)
-      const int lr = KB + tid;
-      if (lr < np - k0) {
-         double a[KB];
-         const double* row = Cb + lr * CBS;
+      // (2 NT >= np - 16 for every launch configuration: at most two rows per thread, written out as two
+      //  guarded blocks -- a loop would let the compiler hoist the 120 block entries into registers and spill)
 #pragma unroll
-         for (int c = 0; c < KB; ++c) a[c] = row[c];
+      for (int rep = 0; rep < 2; ++rep) {
+         const int lr = KB + tid + rep * NT;
+         if (lr < np - k0) {
+            double a[KB];
+            const double* row = Cb + lr * CBS;
 #pragma unroll
-         for (int c = 0; c < KB; ++c) {
-            a[c] *= rd[k0 + c];
+            for (int c = 0; c < KB; ++c) a[c] = row[c];
 #pragma unroll
-            for (int c2 = c + 1; c2 < KB; ++c2) a[c2] = fma(-a[c], Cb[c2 * CBS + c], a[c2]);
+            for (int c = 0; c < KB; ++c) {
+               a[c] *= rd[k0 + c];
+#pragma unroll
+               for (int c2 = c + 1; c2 < KB; ++c2) a[c2] = fma(-a[c], ((const volatile double*)Cb)[c2 * CBS + c], a[c2]);
+            }
+            double* dst = S + tri(k0 + lr) + k0;
+#pragma unroll
+            for (int c = 0; c < KB; ++c) dst[c] = a[c];
          }
-         double* dst = S + tri(k0 + lr) + k0;
-#pragma unroll
-         for (int c = 0; c < KB; ++c) dst[c] = a[c];
       }
       __syncthreads();
    }
@@ -731,6 +737,8 @@ static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count) 
    if (!configured) {
       MCHRG_CUDA(cudaFuncSetAttribute(eeq_factor_ll_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(smem_doubles_ll(NP_MAX) * sizeof(double))));
+      MCHRG_CUDA(cudaFuncSetAttribute(eeq_factor_ll_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      (int)cudaSharedmemCarveoutMaxShared));
       configured = true;
    }
    MCHRG_LAUNCH(ctx, eeq_factor_ll_kernel<NT>, (unsigned)count, NT, smem, a);
@@ -858,8 +866,7 @@ static cudaEvent_t run_chunk_split(mchrg_b200_context* ctx, const Args& a, const
          b.np = c * KB;
          b.perm = dperm + cls_start[c];
          StreamScope on(ctx, (flip++ & 1) ? ctx->stream_hi2 : ctx->stream_hi);
-         if (b.np <= 96) launch_factor_ll<128>(ctx, b, cls_count[c]);
-         else launch_factor_ll<256>(ctx, b, cls_count[c]);
+         launch_factor_ll<128>(ctx, b, cls_count[c]);
       }
    }
    cudaEvent_t eB1 = ctx->next_event(), eB2 = ctx->next_event();
@@ -985,8 +992,7 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
                      batch::Args bb = b;
                      bb.np = k * batch::KB;
                      bb.perm = dperm + chunk_off[c] + starts[c][k];
-                     if (bb.np <= 96) batch::launch_factor_ll<128>(ctx, bb, counts[c][k]);
-                     else batch::launch_factor_ll<256>(ctx, bb, counts[c][k]);
+                     batch::launch_factor_ll<128>(ctx, bb, counts[c][k]);
                   }
                }
             }
