@@ -40,7 +40,7 @@ UNIT = "molecules/s"
 NMOL = 100_000
 NMIN, NMAX = 30, 200
 SEED = 20250102
-CPU_SAMPLE = 20_000  # molecules in the bounded CPU sample (~10-30 s on the box's cores)
+CPU_SAMPLE = 100_000  # molecules in the bounded CPU sample (~10 s on the box's 16 cores: one full batch)
 
 # algorithmic FP64 work per molecule of n atoms (DESIGN.md "Algorithmic work"):
 #   Cholesky n^3/3 + two triangular solves with 2 right-hand sides 4 n^2 + C_PAIR per unique pair
@@ -444,7 +444,7 @@ def run_ours(args):
                 "steps": e_steps, "host_equals_device_result": same},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "eeq_batch_kernel (all size classes of one step)",
+        "roofline": {"bound": "tensor", "kernel": "batch kernels of one step: eeq_batch_kernel<.,1> (pair phase A) + eeq_factor_ll_kernel + eeq_batch_kernel<.,3> (pair phase C), all size classes",
                      "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                      "traffic": None,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "model.cuh"
+#include "erfgauss.cuh"
 
 namespace mchrg {
 namespace batch {
@@ -39,6 +40,8 @@ struct Args {
    int32_t* status;
    const int32_t* perm;  // molecule ids of this class
    const double* par;    // model parameters [slot * nid + (Z-1)]
+   const double2* etab;  // erfgauss.cuh node table
+   int debug;
    int nid;
    double kcn, cutoff2, cut;
    int np;               // padded order of the class (multiple of 16); split pair phases: capacity of the launch
@@ -50,8 +53,15 @@ struct Args {
    int64_t ntot;         // atoms in the chunk
 };
 
+// pair-phase auxiliaries: the erf/gauss node table and one 64-entry ring of deferred near pairs per warp
+constexpr int AUX_RING = 64;                                   // ints per warp
+constexpr int AUX_DOUBLES = 2 * eg::NTAB + 2 + 8 * AUX_RING / 2;  // table (417 double2) + 8 warps * 64 ints
+// In the heavy (matrix in shared memory) layout the auxiliaries live in the Cholesky panel buffer, which the
+// pair phases do not use, when it is large enough; small orders append them.
+__host__ __device__ inline bool aux_in_panel(int np) { return KB * (np + 4) >= AUX_DOUBLES; }
 __host__ __device__ inline size_t smem_doubles(int np) {
-   return (size_t)np * (np + 1) / 2 + (size_t)KB * (np + 4) + KB * (KB + 1) + KB + (size_t)NVEC * np + 8;
+   return (size_t)np * (np + 1) / 2 + (size_t)KB * (np + 4) + KB * (KB + 1) + KB + (size_t)NVEC * np + 8 +
+          (aux_in_panel(np) ? 0 : AUX_DOUBLES);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -187,6 +197,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    double* b0 = th + npv;      double* b1 = b0 + npv;      double* qv = b1 + npv;
    double* rd = qv + npv;      // reciprocal pivots 1 / L(i, i); later reused for thalf * q * fcut
    double* scal = rd + npv;    // [0] lambda, [1] s
+   double* aux = (MAT_IN_SMEM && aux_in_panel(np)) ? P : scal + 8;
+   double2* etab = reinterpret_cast<double2*>(aux);                 // erf / gauss nodes
+   int* ring = reinterpret_cast<int*>(aux + 2 * eg::NTAB + 2) + warp * AUX_RING;  // this warp's deferred pairs
+   unsigned long long* cnfix = reinterpret_cast<unsigned long long*>(b0);  // fixed-point CN sums (phase A)
    __shared__ int sfail;
    double* xv_g = p.vecg + off;
    double* th_g = p.vecg + p.ntot + off;
@@ -210,69 +224,87 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          X[i] = Y[i] = Z[i] = 0.0;
          rad2[i] = 1.0; dself[i] = 1.0; rcov[i] = 0.0; xv[i] = 0.0; th[i] = 0.0;
       }
+      if (PH == 0 || PH == 1) cnfix[i] = 0ull;
    }
+   if (PH != 2) eg::load_table(etab, p.etab, tid, NT);
    __syncthreads();
 
    const int ntri_n = tri(n);
+   constexpr unsigned FULL = 0xffffffffu;
+   const unsigned lt_mask = (1u << lane) - 1u;
    if (PH == 0 || PH == 1) {
-   // ---- erf coordination number with log-cut (mctc_ncoord): every unique pair once, the counts are
-   //      parked in the (still unused) matrix storage and summed per row afterwards ----
-   for (int e = tid; e < ntri_n; e += NT) {
-      int i, j;
-      tri_decode(e, i, j);
-      double c = 0.0;
-      if (i != j) {
-         const double dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
-         const double r2 = dx * dx + dy * dy + dz * dz;
-         if (!(r2 > p.cutoff2 || r2 < 1.0e-12)) {
-            // 1/2 (1 + erf(-kcn (r - rc)/rc)); beyond an argument of 6 erf is -1 to the last bit (count == 0)
-            const double r1 = r2 * rsqrt(r2);
-            const double a = p.kcn * (r1 / (rcov[i] + rcov[j]) - 1.0);
-            if (a < 6.0) c = 0.5 - 0.5 * erf(a);
+   // ---- one pass over the unique pairs: Coulomb block J, packed lower (eeq.f90:199-242; padding = identity),
+   //      and the erf coordination number (mctc_ncoord).  The counting function is exactly zero beyond
+   //      r = (1 + 6 / kcn) rc, so only the few bonded pairs need its erf: they are deferred into the warp's
+   //      ring and evaluated 32 at a time with all lanes busy.  Counts are summed in 2^-56 fixed point with
+   //      integer shared-memory atomics: associative, so the result does not depend on the arrival order.
+   const int ntri = tri(np);
+   const double near = 1.0 + 6.0 / p.kcn;
+   const double near2 = near * near;
+   constexpr double FIX = 72057594037927936.0;  // 2^56
+   int wr = 0, rdp = 0;
+   auto count_pairs = [&](int slot) {
+      const int ij = ring[slot & (AUX_RING - 1)];
+      const int i = ij >> 16, j = ij & 0xffff;
+      const double dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      const double r1 = r2 * rsqrt(r2);
+      // 1/2 (1 + erf(-kcn (r - rc)/rc))
+      const double a = p.kcn * (r1 / (rcov[i] + rcov[j]) - 1.0);
+      double g;
+      const double ea = eg::erf_gauss<6, false>(etab, fabs(a), g);
+      const double c = 0.5 - copysign(0.5, a) * ea;
+      const unsigned long long f = (unsigned long long)__double2ll_rn(c * FIX);
+      atomicAdd(&cnfix[i], f);
+      atomicAdd(&cnfix[j], f);
+   };
+   for (int base = warp * 32; base < ntri; base += NT) {
+      const int e = base + lane;
+      bool hit = false;
+      int i = 0, j = 0;
+      if (e < ntri) {
+         tri_decode(e, i, j);
+         double v;
+         if (i == j) {
+            v = dself[i];
+         } else if (i < n) {
+            const double dx = X[j] - X[i], dy = Y[j] - Y[i], dz = Z[j] - Z[i];
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
+            double g;
+            v = eg::erf_gauss<5, false>(etab, r2 * rinv * gam, g) * rinv;  // erf(gamma r) / r
+            const double rc = rcov[i] + rcov[j];
+            hit = r2 < near2 * rc * rc && !(r2 > p.cutoff2 || r2 < 1.0e-12);
+         } else {
+            v = 0.0;
          }
+         A[e] = v;
       }
-      A[e] = c;
+      const unsigned m = __ballot_sync(FULL, hit);
+      if (hit) ring[(wr + __popc(m & lt_mask)) & (AUX_RING - 1)] = (i << 16) | j;
+      wr += __popc(m);
+      if (wr - rdp >= 32) {
+         __syncwarp();
+         count_pairs(rdp + lane);
+         rdp += 32;
+         __syncwarp();
+      }
    }
+   __syncwarp();
+   if (lane < wr - rdp) count_pairs(rdp + lane);
    __syncthreads();
    const double ecut = exp(p.cut);
-   for (int i = warp; i < n; i += NW) {
-      double acc = 0.0;
-      const double* row = A + tri(i);
-      for (int j = lane; j < i; j += 32) acc += row[j];
-      for (int j = i + 1 + lane; j < n; j += 32) acc += A[tri(j) + i];
-      acc = warp_sum(acc);
-      if (lane == 0) {
-         double cn = acc, f = 1.0;
-         if (p.cut > 0.0) {
-            f = ecut / (ecut + exp(acc));
-            cn = log(1.0 + ecut) - log(1.0 + exp(p.cut - acc));
-         }
-         const double tmp = th[i] / sqrt(cn + 1.0e-14);
-         xv[i] = -xv[i] + tmp * cn;  // get_xvec, eeq.f90:127-150
-         th[i] = 0.5 * tmp;
-         fcut[i] = f;
+   for (int i = tid; i < n; i += NT) {
+      const double acc = (double)cnfix[i] * (1.0 / FIX);
+      double cn = acc, f = 1.0;
+      if (p.cut > 0.0) {
+         f = ecut / (ecut + exp(acc));
+         cn = log(1.0 + ecut) - log(1.0 + exp(p.cut - acc));
       }
-   }
-   __syncthreads();
-
-   // ---- Coulomb block J, packed lower (eeq.f90:199-242); padding = identity ----
-   const int ntri = tri(np);
-   for (int e = tid; e < ntri; e += NT) {
-      int i, j;
-      tri_decode(e, i, j);
-      double v;
-      if (i == j) {
-         v = dself[i];
-      } else if (i < n) {
-         const double dx = X[j] - X[i], dy = Y[j] - Y[i], dz = Z[j] - Z[i];
-         const double r2 = dx * dx + dy * dy + dz * dz;
-         const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
-         const double x = r2 * rinv * gam;
-         v = (x < 6.0) ? erf(x) * rinv : rinv;  // erf(gamma r) / r ; erf(x >= 6) == 1 in double precision
-      } else {
-         v = 0.0;
-      }
-      A[e] = v;
+      const double tmp = th[i] / sqrt(cn + 1.0e-14);
+      xv[i] = -xv[i] + tmp * cn;  // get_xvec, eeq.f90:127-150
+      th[i] = 0.5 * tmp;
+      fcut[i] = f;
    }
    __syncthreads();
    }  // PH 0 / 1
@@ -452,6 +484,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    __syncthreads();
    }  // PH 0 / 2
 
+   if (PH == 0 && aux_in_panel(np)) eg::load_table(etab, p.etab, tid, NT);  // the panel buffer held it before
    const double lam = scal[0];
    double* wf = rd;  // pivots are no longer needed
    for (int i = tid; i < n; i += NT) {
@@ -468,42 +501,100 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    //        f_ij = dtmp_ij q_i q_j - dcount_ij / r_ij (w_i + w_j),   w = thalf * q * fcut
    //      (q_i atrace_i minus the dcndr contraction; eeq.f90:403-411, mctc_ncoord); one evaluation per
    //      unique pair, parked in the matrix storage, then summed per row ----
-   for (int e = tid; e < ntri_n; e += NT) {
-      int i, j;
-      tri_decode(e, i, j);
-      double f = 0.0;
-      if (i != j) {
+   {
+      const double near = 1.0 + eg::XMAX / p.kcn;  // exp(-a^2) < 5e-19 beyond
+      const double near2 = near * near;
+      int wr = 0, rdp = 0;
+      auto dcount_pairs = [&](int slot) {  // coordination-number part of f for a deferred (bonded) pair
+         const int ij = ring[slot & (AUX_RING - 1)];
+         const int i = ij >> 16, j = ij & 0xffff;
          const double vx = X[i] - X[j], vy = Y[i] - Y[j], vz = Z[i] - Z[j];
          const double r2 = vx * vx + vy * vy + vz * vz;
-         const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
-         const double r1 = r2 * rinv, x = r1 * gam;  // x = gamma r
-         // dtmp = 2 gamma exp(-x^2) / (sqrt(pi) r^2) - erf(x) / r^3 ; for x > 8.5: erf == 1, exp(-x^2) < 5e-32
-         const double dt = (x < 8.5) ? (2.0 / SQRTPI * gam * exp(-x * x) - erf(x) * rinv) : -rinv;
-         f = rinv * rinv * dt * qv[i] * qv[j];
-         if (r2 <= p.cutoff2 && r2 >= 1.0e-12) {
-            const double rci = 1.0 / (rcov[i] + rcov[j]);
-            const double a = p.kcn * (r1 * rci - 1.0);
-            if (a < 8.5) f += p.kcn / SQRTPI * rci * exp(-a * a) * rinv * (wf[i] + wf[j]);  // else < 5e-32
+         const double rinv = rsqrt(r2);
+         const double rci = 1.0 / (rcov[i] + rcov[j]);
+         const double a = p.kcn * (r2 * rinv * rci - 1.0);
+         double g;
+         eg::erf_gauss<6, true>(etab, fabs(a), g);
+         A[tri(i) + j] += p.kcn / SQRTPI * rci * g * rinv * (wf[i] + wf[j]);
+      };
+      for (int base = warp * 32; base < ntri_n && !(p.debug & 2); base += NT) {
+         const int e = base + lane;
+         bool hit = false;
+         int i = 0, j = 0;
+         if (e < ntri_n) {
+            tri_decode(e, i, j);
+            double f = 0.0;
+            if (i != j) {
+               const double vx = X[i] - X[j], vy = Y[i] - Y[j], vz = Z[i] - Z[j];
+               const double r2 = vx * vx + vy * vy + vz * vz;
+               const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
+               // dtmp = 2 gamma exp(-x^2) / (sqrt(pi) r^2) - erf(x) / r^3,  x = gamma r
+               double g;
+               const double ex = eg::erf_gauss<6, true>(etab, r2 * rinv * gam, g);
+               const double dt = 2.0 / SQRTPI * gam * g - ex * rinv;
+               f = rinv * rinv * dt * qv[i] * qv[j];
+               const double rc = rcov[i] + rcov[j];
+               hit = r2 < near2 * rc * rc && r2 <= p.cutoff2 && r2 >= 1.0e-12;
+            }
+            A[e] = f;
+         }
+         const unsigned m = __ballot_sync(FULL, hit);
+         if (hit) ring[(wr + __popc(m & lt_mask)) & (AUX_RING - 1)] = (i << 16) | j;
+         wr += __popc(m);
+         if (wr - rdp >= 32) {
+            __syncwarp();
+            dcount_pairs(rdp + lane);
+            rdp += 32;
+            __syncwarp();
          }
       }
-      A[e] = f;
+      __syncwarp();
+      if (lane < wr - rdp) dcount_pairs(rdp + lane);
    }
    __syncthreads();
+   if (p.debug & 1) return;
+   // Row sums of the parked pair scalars, both halves with coalesced reads of the packed triangle:
+   //   j < i: one warp per row i, lanes over j (contiguous);
+   //   j > i: lanes over 32 consecutive atoms i (contiguous for fixed j), the warps share the j range and
+   //          their partial sums are combined through shared memory.
+   double* G = b0;           // [3][npv] (b0, b1, qv are free now; qv is re-read below before it is overwritten)
+   double* part = aux;       // [NW][3][32] partial sums (the node table is no longer needed)
    for (int i = warp; i < n; i += NW) {
       const double xi = X[i], yi = Y[i], zi = Z[i];
       double gx = 0.0, gy = 0.0, gz = 0.0;
       const double* row = A + tri(i);
-      for (int j = lane; j < n; j += 32) {
-         if (j == i) continue;
-         const double f = (j < i) ? row[j] : A[tri(j) + i];
+      for (int j = lane; j < i; j += 32) {
+         const double f = row[j];
          gx = fma(f, xi - X[j], gx); gy = fma(f, yi - Y[j], gy); gz = fma(f, zi - Z[j], gz);
       }
       gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
-      if (lane == 0) {
-         p.gradient[3 * (off + i)] = gx;
-         p.gradient[3 * (off + i) + 1] = gy;
-         p.gradient[3 * (off + i) + 2] = gz;
+      if (lane == 0) { G[i] = gx; G[npv + i] = gy; G[2 * npv + i] = gz; }
+   }
+   __syncthreads();
+   for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const int ic = min(i, n - 1);
+      const double xi = X[ic], yi = Y[ic], zi = Z[ic];
+      double gx = 0.0, gy = 0.0, gz = 0.0;
+#pragma unroll 4
+      for (int j = i0 + 1 + warp; j < n; j += NW) {
+         if (i < j) {
+            const double f = A[tri(j) + i];
+            gx = fma(f, xi - X[j], gx); gy = fma(f, yi - Y[j], gy); gz = fma(f, zi - Z[j], gz);
+         }
       }
+      part[(warp * 3 + 0) * 32 + lane] = gx;
+      part[(warp * 3 + 1) * 32 + lane] = gy;
+      part[(warp * 3 + 2) * 32 + lane] = gz;
+      __syncthreads();
+      if (tid < 96) {
+         const int c = tid >> 5;
+         double acc = 0.0;
+#pragma unroll
+         for (int w = 0; w < NW; ++w) acc += part[(w * 3 + c) * 32 + lane];
+         if (i < n) p.gradient[3 * (off + i) + c] = G[c * npv + i] + acc;
+      }
+      __syncthreads();
    }
 }
 
@@ -531,7 +622,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
    const int mol = p.perm[blockIdx.x];
    const int64_t off = p.offsets[mol];
    const int n = (int)(p.offsets[mol + 1] - off);
-   const int np = p.np;
+   const int np = ((n + KB - 1) / KB) * KB;  // the molecule's own padded order (one launch serves all sizes)
    const double charge = p.charge[mol];
    double* S = p.scratch + p.soff[mol];  // packed lower, row-major
    double* Cb = sm;                      // Cb[(i - k0) * CBS + c]
@@ -732,7 +823,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
 
 template <int NT>
 static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count) {
-   const size_t smem = smem_doubles_ll(a.np) * sizeof(double);
+   const size_t smem = smem_doubles_ll(NP_MAX) * sizeof(double);
    static bool configured = false;
    if (!configured) {
       MCHRG_CUDA(cudaFuncSetAttribute(eeq_factor_ll_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -744,16 +835,22 @@ static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count) 
    MCHRG_LAUNCH(ctx, eeq_factor_ll_kernel<NT>, (unsigned)count, NT, smem, a);
 }
 
-__host__ inline size_t smem_doubles_pair(int npv) { return (size_t)NVEC * npv + 8; }
+__host__ inline size_t smem_doubles_pair(int npv) { return (size_t)NVEC * npv + 8 + AUX_DOUBLES; }
 
 template <int NT, int PH>
 static void launch_class(mchrg_b200_context* ctx, const Args& a, int count) {
    const bool heavy = (PH == 0 || PH == 2);
-   const size_t smem = (heavy ? smem_doubles(a.np) : smem_doubles_pair(a.np)) * sizeof(double);
+   static const size_t pad = std::getenv("MCHRG_B200_PAIR_PAD") ? (size_t)atoi(std::getenv("MCHRG_B200_PAIR_PAD")) * 1024 : 0;
+   const size_t smem = (heavy ? smem_doubles(a.np) : smem_doubles_pair(a.np)) * sizeof(double) + (heavy ? 0 : pad);
    static size_t configured = 0;
    if (smem > configured) {
-      const size_t cap = (heavy ? smem_doubles(NP_MAX) : smem_doubles_pair(NP_MAX)) * sizeof(double);
+      const size_t cap = (heavy ? smem_doubles(NP_MAX) : smem_doubles_pair(NP_MAX)) * sizeof(double) + (heavy ? 0 : pad);
       MCHRG_CUDA(cudaFuncSetAttribute(eeq_batch_kernel<NT, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+      // same shared-memory carveout as the factorisation kernel: CTAs of kernels that ask for different
+      // L1/shared splits cannot share an SM
+      if (!std::getenv("MCHRG_B200_NO_CARVEOUT"))
+         MCHRG_CUDA(cudaFuncSetAttribute(eeq_batch_kernel<NT, PH>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         (int)cudaSharedmemCarveoutMaxShared));
       configured = cap;
    }
    MCHRG_LAUNCH(ctx, (eeq_batch_kernel<NT, PH>), (unsigned)count, NT, smem, a);
@@ -778,7 +875,7 @@ static void bucket(const std::vector<int64_t>& hoff, int32_t m0, int32_t m1, std
    perm.clear();
    cls_start.assign(NCLASS + 1, 0);
    cls_count.assign(NCLASS + 1, 0);
-   for (int c = 1; c <= NCLASS; ++c) {
+   for (int c = NCLASS; c >= 1; --c) {  // largest molecules first: their CTAs run longest
       cls_start[c] = perm.size();
       cls_count[c] = (int)cls[c].size();
       perm.insert(perm.end(), cls[c].begin(), cls[c].end());
@@ -834,6 +931,11 @@ static bool factor_in_smem() {  // MCHRG_B200_FACTOR=smem selects the right-look
    return e && e[0] == 's';
 }
 
+static bool factor_per_class() {  // MCHRG_B200_FACTOR=classes
+   const char* e = std::getenv("MCHRG_B200_FACTOR");
+   return e && e[0] == 'c';
+}
+
 // `gate` (in/out): events recorded on the factorisation streams right before the previous chunk's
 // factorisation kernels; phase A of this chunk waits for them, so that those shared-memory-heavy CTAs are
 // placed on the SMs BEFORE this chunk's light pair CTAs can fill them (a heavy CTA only fits on an SM whose
@@ -858,16 +960,22 @@ static cudaEvent_t run_chunk_split(mchrg_b200_context* ctx, const Args& a, const
    MCHRG_CUDA(cudaEventRecord(gate[1], ctx->stream_hi2));
    if (factor_in_smem()) {
       launch_chunk<2>(ctx, a, dperm, cls_start, cls_count, ctx->stream_hi, ctx->stream_hi2);
-   } else {  // left-looking, matrix stays in the scratch: light CTAs, classes alternate between the two streams
+   } else if (factor_per_class()) {  // A/B knob: one launch per size class, alternating streams
       Args b = a;
       int flip = 0;
       for (int c = NP_MAX / KB; c >= 1; --c) {
          if (cls_count[c] == 0) continue;
-         b.np = c * KB;
+         b.np = NP_MAX;
          b.perm = dperm + cls_start[c];
          StreamScope on(ctx, (flip++ & 1) ? ctx->stream_hi2 : ctx->stream_hi);
          launch_factor_ll<128>(ctx, b, cls_count[c]);
       }
+   } else {  // left-looking, matrix stays in the scratch: one launch for all sizes of the chunk (largest first)
+      Args b = a;
+      b.np = NP_MAX;
+      b.perm = dperm;
+      StreamScope on(ctx, ctx->stream_hi);
+      launch_factor_ll<128>(ctx, b, count);
    }
    cudaEvent_t eB1 = ctx->next_event(), eB2 = ctx->next_event();
    MCHRG_CUDA(cudaEventRecord(eB1, ctx->stream_hi));
@@ -922,6 +1030,8 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
       batch::Args a;
       a.scratch = nullptr; a.soff = nullptr; a.vecg = nullptr; a.lamg = nullptr; a.ntot = 0;
       a.par = model->d_par;
+      a.etab = ctx->erf_tab;
+      a.debug = std::getenv("MCHRG_B200_DEBUG") ? atoi(std::getenv("MCHRG_B200_DEBUG")) : 0;
       a.nid = model->nid;
       a.kcn = model->ncoord.kcn;
       a.cutoff2 = model->ncoord.cutoff * model->ncoord.cutoff;
@@ -958,7 +1068,8 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
          a.vecg = ctx->alloc<double>(3 * ntot);
          a.lamg = ctx->alloc<double>(nmol);
          a.ntot = (int64_t)ntot;
-         const int nchunk = (int)std::min<int64_t>(16, std::max<int64_t>(1, nmol / 4096));
+         const int maxchunk = std::getenv("MCHRG_B200_CHUNKS") ? std::max(1, atoi(std::getenv("MCHRG_B200_CHUNKS"))) : 16;
+         const int nchunk = (int)std::min<int64_t>(maxchunk, std::max<int64_t>(1, nmol / 4096));
          std::vector<int32_t> all_perm;
          std::vector<std::vector<size_t>> starts(nchunk);
          std::vector<std::vector<int>> counts(nchunk);
@@ -987,13 +1098,10 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
                if (batch::factor_in_smem()) {
                   batch::launch_chunk<2>(ctx, b, dperm + chunk_off[c], starts[c], counts[c], ctx->stream, ctx->stream);
                } else {
-                  for (int k = batch::NP_MAX / batch::KB; k >= 1; --k) {
-                     if (counts[c][k] == 0) continue;
-                     batch::Args bb = b;
-                     bb.np = k * batch::KB;
-                     bb.perm = dperm + chunk_off[c] + starts[c][k];
-                     batch::launch_factor_ll<128>(ctx, bb, counts[c][k]);
-                  }
+                  batch::Args bb = b;
+                  bb.np = batch::NP_MAX;
+                  bb.perm = dperm + chunk_off[c];
+                  batch::launch_factor_ll<128>(ctx, bb, (int)(chunk_off[c + 1] - chunk_off[c]));
                }
             }
             MCHRG_CUDA(cudaEventRecord(t[2], ctx->stream));

@@ -60,6 +60,7 @@ struct mchrg_b200_context {
    size_t events_used = 0;
    cudaEvent_t next_event();
    int sm_count = 148;
+   double2* erf_tab = nullptr;        // (erf, exp(-x^2)) nodes of erfgauss.cuh, device memory
    size_t smem_optin = 0;
    std::mutex mu;
    uint64_t launches = 0;

@@ -1,5 +1,6 @@
 // Context, arena and staging implementation (see common.cuh).
 #include "common.cuh"
+#include "erfgauss.cuh"
 
 namespace mchrg {
 
@@ -138,6 +139,11 @@ int mchrg_b200_context_create(int device, mchrg_b200_context** out) {
       MCHRG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
       MCHRG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
       ctx->active = ctx->stream;
+      {
+         const std::vector<double2> tab = mchrg::eg::host_table();
+         MCHRG_CUDA(cudaMalloc(&ctx->erf_tab, tab.size() * sizeof(double2)));
+         MCHRG_CUDA(cudaMemcpy(ctx->erf_tab, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+      }
    } catch (const Error& e) {
       set_last_error(e.msg);
       delete ctx;
@@ -165,6 +171,7 @@ void mchrg_b200_context_destroy(mchrg_b200_context* ctx) {
       }
    }
    for (auto e : ctx->events) cudaEventDestroy(e);
+   if (ctx->erf_tab) cudaFree(ctx->erf_tab);
    for (auto& s : ctx->slabs) cudaFree(s.base);
    if (ctx->pinned) cudaFreeHost(ctx->pinned);
    delete ctx;
