@@ -13,6 +13,7 @@
 // Molecules are grouped by padded order NP (one launch per class) so shared memory, and with it the
 // number of resident CTAs per SM, matches the molecule size.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -28,6 +29,9 @@ namespace batch {
 constexpr int KB = 16;        // Cholesky block
 constexpr int NP_MAX = 208;   // largest padded order that fits in 227 KB of shared memory
 constexpr int NVEC = 13;
+// split path: the matrix is augmented by two right-hand-side rows (see eeq_factor_ll_kernel)
+constexpr int NPA_MAX = NP_MAX + KB;
+__host__ __device__ inline int aug_order(int n) { return ((n + 2 + KB - 1) / KB) * KB; }
 
 struct Args {
    const int64_t* offsets;
@@ -41,7 +45,6 @@ struct Args {
    const int32_t* perm;  // molecule ids of this class
    const double* par;    // model parameters [slot * nid + (Z-1)]
    const double2* etab;  // erfgauss.cuh node table
-   int debug;
    int nid;
    double kcn, cutoff2, cut;
    int np;               // padded order of the class (multiple of 16); split pair phases: capacity of the launch
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    const double charge = p.charge[mol];
    constexpr bool MAT_IN_SMEM = (PH == 0 || PH == 2);
    // pair phases work on the molecule's own padded order, the class launches on the class order
-   const int np = MAT_IN_SMEM ? p.np : ((n + KB - 1) / KB) * KB;
+   const int np = MAT_IN_SMEM ? p.np : aug_order(n);  // split path: augmented order (see eeq_factor_ll_kernel)
    const int npv = p.np;  // stride of the per-atom vectors in shared memory
    const int ldp = np + 4;
    double* A = MAT_IN_SMEM ? sm : p.scratch + p.soff[mol];  // packed lower, row-major: A[tri(i) + j], j <= i
@@ -308,16 +311,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    }
    __syncthreads();
    }  // PH 0 / 1
-   if (PH == 1) {  // hand xvec, thalf, fcut to the later phases
-      for (int i = tid; i < n; i += NT) { xv_g[i] = xv[i]; th_g[i] = th[i]; fc_g[i] = fcut[i]; }
+   if (PH == 1) {  // hand xvec, thalf, fcut to the later phases; right-hand sides [x | 1] = last two matrix rows
+      for (int i = tid; i < n; i += NT) {
+         xv_g[i] = xv[i]; th_g[i] = th[i]; fc_g[i] = fcut[i];
+         A[tri(np - 2) + i] = xv[i];
+         A[tri(np - 1) + i] = 1.0;
+      }
       return;
-   }
-   if (PH == 2) {  // matrix and right-hand side from the pair phase
-      const double* src = p.scratch + p.soff[mol];
-      const int nsrc = tri(((n + KB - 1) / KB) * KB);  // molecule's own padded order (== class order here)
-      for (int e = tid; e < nsrc; e += NT) A[e] = src[e];
-      for (int i = tid; i < n; i += NT) xv[i] = xv_g[i];
-      __syncthreads();
    }
    if (PH == 3) {
       for (int i = tid; i < n; i += NT) { xv[i] = xv_g[i]; th[i] = th_g[i]; fcut[i] = fc_g[i]; qv[i] = p.qvec[off + i]; }
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          eg::erf_gauss<6, true>(etab, fabs(a), g);
          A[tri(i) + j] += p.kcn / SQRTPI * rci * g * rinv * (wf[i] + wf[j]);
       };
-      for (int base = warp * 32; base < ntri_n && !(p.debug & 2); base += NT) {
+      for (int base = warp * 32; base < ntri_n; base += NT) {
          const int e = base + lane;
          bool hit = false;
          int i = 0, j = 0;
@@ -552,7 +552,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       if (lane < wr - rdp) dcount_pairs(rdp + lane);
    }
    __syncthreads();
-   if (p.debug & 1) return;
    // Row sums of the parked pair scalars, both halves with coalesced reads of the packed triangle:
    //   j < i: one warp per row i, lanes over j (contiguous);
    //   j > i: lanes over 32 consecutive atoms i (contiguous for fixed j), the warps share the j range and
@@ -599,20 +598,90 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Split path, factorisation phase: LEFT-LOOKING blocked Cholesky that leaves the matrix in the global
-// scratch (L2 resident: <= 174 KB per molecule) and keeps only the current 16-wide block column in
-// shared memory.  ~36 KB of shared memory per CTA instead of ~175 KB, so 6 CTAs are resident per SM
-// and the serial pieces of one molecule (diagonal block, row solves) hide behind the DMMA updates
-// of the others.
-//   per block column k0:  Cb = A(k0:, k0:k0+16) - L(k0:, :k0) L(k0:k0+16, :k0)^T      (DMMA, fragments
-//                          straight from global / L1)
-//                          diagonal block in one warp, row solves one thread per row, L written back
-//                          forward substitution of [x 1] fused (row-oriented)
-//   then the backward substitution by block columns and the Schur complement of the constraint.
+// Split path, factorisation phase: LEFT-LOOKING blocked Cholesky (block 16) of the AUGMENTED matrix that
+// leaves the factor in the global scratch (L2 resident) and keeps one block column in shared memory.
+//
+//   augmented order npa = roundup(n + 2, 16): rows n .. npa-3 are identity padding, rows npa-2 / npa-1
+//   carry the right-hand sides [x | 1] (written by pair phase A), so the forward substitution
+//   w = L^-1 [x 1] falls out of the factorisation as the last two rows of L (their own columns are kept
+//   at identity).  Per block column k0:
+//     U  Cb = A(k0:, k0:k0+16) - L(k0:, :k0) L(k0:k0+16, :k0)^T          DMMA, operands from global / L2
+//     D  the 16 x 16 diagonal tile: Cholesky AND explicit inverse in one warp (lanes = row x column parity,
+//        column / row broadcasts through shared memory); the INVERSE replaces the diagonal block in global
+//        memory (later block columns never read the diagonal blocks of L)
+//     S  rows below: L(i, blk) = Cb(i, :) inv(L_kk)^T                     DMMA, operands from shared memory
+//   backward substitution, right-looking: y_blk = inv(L_kk)^T w_blk, then w(:k0) -= L(blk, :k0)^T y_blk with
+//   coalesced row reads.  ~32 KB of shared memory per CTA, so 6-7 molecules are resident per SM and hide
+//   each other's latencies.
 // ------------------------------------------------------------------------------------------------
-constexpr int CBS = KB + 1;  // row stride of the block column buffer
+constexpr int TS = KB + 1;            // row stride of the diagonal tile
 
-__host__ __device__ inline size_t smem_doubles_ll(int np) { return (size_t)np * CBS + 3 * (size_t)np + 2 * 32 * 16 + 8; }
+
+// doubles: block column below the diagonal tile (swizzled, stride 16) | diagonal tile | its inverse (swizzled)
+//          | column / row broadcast buffers (double buffered) | w of the last block | scalars
+__host__ __device__ inline size_t smem_doubles_ll(int npa) {
+   return (size_t)(npa > KB ? npa - KB : 2) * KB + KB * TS + KB * KB + 4 * KB + 2 * KB + 8 +
+          (npa <= 2 * KB ? 2 * (size_t)npa : 0);  // tiny orders: room for the two solution vectors
+}
+
+__device__ __forceinline__ int swz(int row, int col) { return row * KB + (col ^ ((row & 3) << 2)); }
+
+// Cholesky + inverse of the 16 x 16 tile T (stride TS; lower triangle valid) by one warp.
+// lane = (row r = lane & 15, column parity h = lane >> 4) holds m[k] = T(r, 2k + h) and x[k] = X(r, 2k + h),
+// X accumulating inv(L) by the same eliminations (Gauss-Jordan on [A | I]).  Columns >= nfree are kept at
+// identity (the right-hand-side rows of the augmented matrix).  Outputs: L in T, inv(L) in Li (swizzled).
+// Returns 0 or the 1-based local index of the first non-positive pivot.
+__device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cbuf, double* rbuf, int lane, int nfree) {
+   // (no __restrict__ here: the broadcast buffers are written by OTHER lanes between the warp barriers)
+   const int r = lane & 15, h = lane >> 4;
+   double m[8], x[8];
+#pragma unroll
+   for (int k = 0; k < 8; ++k) {
+      const int c = 2 * k + h;
+      m[k] = (c <= r) ? T[r * TS + c] : 0.0;
+      if (c >= nfree) m[k] = (c == r) ? 1.0 : 0.0;
+      x[k] = (c == r) ? 1.0 : 0.0;
+   }
+   int bad = 0;
+   const int myslot = (r & 1) * 8 + (r >> 1);  // parity-split position of row r in the column buffer
+#pragma unroll
+   for (int c = 0; c < KB; ++c) {
+      double* cb = cbuf + (c & 1) * KB;
+      double* rb = rbuf + (c & 1) * KB;
+      double piv = shfl_d(m[c >> 1], c + ((c & 1) << 4));
+      const bool forced = (c >= KB - 2) && (c >= nfree);  // right-hand-side rows: their own columns stay identity
+      if (forced) piv = 1.0;
+      bad = (!(piv > 0.0) && bad == 0) ? (c + 1) : bad;
+      const double rinv = rsqrt(piv);
+      if (h == (c & 1)) {  // owners of column c
+         double l = m[c >> 1] * rinv;  // r == c: sqrt(piv)
+         if (forced) l = (r == c) ? 1.0 : 0.0;
+         if (r >= c) m[c >> 1] = l;
+         cb[myslot] = (r > c) ? l : 0.0;
+      }
+      if (r == c) {  // row c of X, scaled
+#pragma unroll
+         for (int k = 0; k < 8; ++k) {
+            x[k] *= rinv;
+            rb[h * 8 + k] = x[k];
+         }
+      }
+      __syncwarp();
+      const double lrc = cb[myslot];  // 0 for r <= c: the updates below leave those rows alone
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+         m[k] = fma(-lrc, cb[h * 8 + k], m[k]);   // entries right of the diagonal collect garbage; never used
+         x[k] = fma(-lrc, rb[h * 8 + k], x[k]);
+      }
+   }
+#pragma unroll
+   for (int k = 0; k < 8; ++k) {
+      const int c = 2 * k + h;
+      T[r * TS + c] = (c <= r) ? m[k] : 0.0;
+      Li[swz(r, c)] = (c <= r) ? x[k] : 0.0;
+   }
+   return bad;
+}
 
 template <int NT>
 __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
@@ -622,29 +691,26 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
    const int mol = p.perm[blockIdx.x];
    const int64_t off = p.offsets[mol];
    const int n = (int)(p.offsets[mol + 1] - off);
-   const int np = ((n + KB - 1) / KB) * KB;  // the molecule's own padded order (one launch serves all sizes)
+   const int npa = aug_order(n);
    const double charge = p.charge[mol];
    double* S = p.scratch + p.soff[mol];  // packed lower, row-major
-   double* Cb = sm;                      // Cb[(i - k0) * CBS + c]
-   double* b0 = Cb + (size_t)np * CBS;
-   double* b1 = b0 + np;
-   double* rd = b1 + np;
-   double* red = rd + np;                // [NW][32] partial sums of the backward substitution
-   double* scal = red + 2 * 32 * 16;
+   double* Cb = sm;                      // rows below the diagonal tile: Cb[swz(i - k0 - 16, c)]
+   double* T = Cb + (size_t)(npa > KB ? npa - KB : 2) * KB;
+   double* Li = T + KB * TS;
+   double* cbuf = Li + KB * KB;
+   double* rbuf = cbuf + 2 * KB;
+   double* wl = rbuf + 2 * KB;           // w of the last block: wl[h * 16 + c]
+   double* scal = wl + 2 * KB;
+   double* b0 = (npa <= 2 * KB) ? scal + 8 : Cb;  // solution vectors alias the block column buffer
+   double* b1 = b0 + npa;
    __shared__ int sfail;
-   __shared__ double fw[2 * KB];
-   const double* xv_g = p.vecg + off;
    if (tid == 0) sfail = 0;
-   for (int i = tid; i < np; i += NT) {
-      b0[i] = (i < n) ? xv_g[i] : 0.0;
-      b1[i] = (i < n) ? 1.0 : 0.0;
-   }
    __syncthreads();
    const int g = lane >> 2, t = lane & 3;
 
-   for (int k0 = 0; k0 < np; k0 += KB) {
-      // ---- block column with the left-looking update, 16-row tiles per warp ----
-      const int nrt = (np - k0) / KB;
+   for (int k0 = 0; k0 < npa; k0 += KB) {
+      const int nrt = (npa - k0) / KB;
+      // ---- U: block column with the left-looking update, one 16-row tile per warp and turn ----
       for (int ti = warp; ti < nrt; ti += NW) {
          const int i0 = k0 + KB * ti;
          double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
@@ -664,99 +730,66 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int ntl = 0; ntl < 2; ++ntl) {
-               const int row = i0 + 8 * mt + g, col = 8 * ntl + 2 * t;  // col within the block column
+               const int lr = 8 * mt + g, col = 8 * ntl + 2 * t;  // within the tile / the block column
+               const int row = i0 + lr;
                const double* src = S + tri(row) + k0 + col;
-               double* dst = Cb + (row - k0) * CBS + col;
                // entries right of the diagonal do not exist in the packed storage (and are never used)
-               dst[0] = (k0 + col <= row) ? src[0] - acc[mt][ntl][0] : 0.0;
-               dst[1] = (k0 + col + 1 <= row) ? src[1] - acc[mt][ntl][1] : 0.0;
+               const double v0 = (k0 + col <= row) ? src[0] - acc[mt][ntl][0] : 0.0;
+               const double v1 = (k0 + col + 1 <= row) ? src[1] - acc[mt][ntl][1] : 0.0;
+               if (ti == 0) {
+                  T[lr * TS + col] = v0;
+                  T[lr * TS + col + 1] = v1;
+               } else {
+                  *reinterpret_cast<double2*>(Cb + swz(KB * (ti - 1) + lr, col)) = make_double2(v0, v1);
+               }
             }
-      }
-      // row-oriented forward substitution, cooperative part: fw(r, h) = L(k0 + r, :k0) . w_h(:k0)
-      for (int rr = warp; rr < KB; rr += NW) {
-         const double* lrow = S + tri(k0 + rr);
-         double f0 = 0.0, f1 = 0.0;
-         for (int j = lane; j < k0; j += 32) {
-            const double l = lrow[j];
-            f0 = fma(l, b0[j], f0);
-            f1 = fma(l, b1[j], f1);
-         }
-         f0 = warp_sum(f0);
-         f1 = warp_sum(f1);
-         if (lane == 0) { fw[rr] = f0; fw[KB + rr] = f1; }
       }
       __syncthreads();
-      // ---- diagonal block (warp 0, registers + shuffles), fused forward substitution of [x 1] ----
+      // ---- D: diagonal tile, Cholesky + inverse; the inverse goes to global in place of the block ----
       if (warp == 0) {
+         const bool last = (k0 + KB == npa);
+         const int bad = diag_factor_inv(T, Li, cbuf, rbuf, lane, last ? KB - 2 : KB);
+         if (bad && lane == 0) sfail = k0 + bad;
+         __syncwarp();
+         __syncwarp();
          const int r = lane & 15, h = lane >> 4;
-         double m[8];
-#pragma unroll
-         for (int k = 0; k < 8; ++k) m[k] = Cb[r * CBS + 2 * k + h];
-         int bad = 0;
-#pragma unroll
-         for (int c = 0; c < KB; ++c) {
-            const int src_h = (c & 1) << 4;
-            const double piv = shfl_d(m[c >> 1], c + src_h);
-            bad = (!(piv > 0.0) && bad == 0) ? (k0 + c + 1) : bad;
-            const double rinv = rsqrt(piv);
-            const double lrc = shfl_d(m[c >> 1], r + src_h) * rinv;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-               const int c2 = 2 * k + h;
-               const double lc2 = shfl_d(m[c >> 1], c2 + src_h) * rinv;
-               if (c2 > c && c2 <= r) m[k] = fma(-lrc, lc2, m[k]);
-            }
-            if (h == (c & 1)) {
-               if (r == c) m[c >> 1] = piv * rinv;
-               else if (r > c) m[c >> 1] = lrc;
-            }
-            if (lane == 0) rd[k0 + c] = rinv;
-         }
 #pragma unroll
          for (int k = 0; k < 8; ++k) {
             const int c = 2 * k + h;
-            Cb[r * CBS + c] = (c <= r) ? m[k] : 0.0;
-            if (c <= r) S[tri(k0 + r) + k0 + c] = m[k];
+            if (c <= r) S[tri(k0 + r) + k0 + c] = Li[swz(r, c)];
          }
-         if (bad && lane == 0) sfail = bad;
-         // w(k0 + r) = (b(k0 + r) - L(k0 + r, :k0) w(:k0)), then the 16 x 16 triangular solve; lane = (row r, rhs h)
-         {
-            const double s = (h ? b1 : b0)[k0 + r] - fw[h * KB + r];
-            // triangular solve with the factored block: L(r, c) is read back from Cb (written above)
-            __syncwarp();
-            double v = s;
-#pragma unroll
-            for (int c = 0; c < KB; ++c) {
-               const double wc = shfl_d(v, c + (h << 4)) * rd[k0 + c];
-               if (r == c) v = wc;
-               else if (r > c) v = fma(-Cb[r * CBS + c], wc, v);
-            }
-            (h ? b1 : b0)[k0 + r] = v;
+         if (last && lane < KB) {  // forward-substituted right-hand sides of the last block
+            wl[lane] = (lane < KB - 2) ? T[(KB - 2) * TS + lane] : 0.0;
+            wl[KB + lane] = (lane < KB - 2) ? T[(KB - 1) * TS + lane] : 0.0;
          }
       }
       __syncthreads();
       if (sfail) break;
-      // ---- rows below the diagonal block: a <- a * inv(L_kk)^T, written back to the scratch ----
-      // (2 NT >= np - 16 for every launch configuration: at most two rows per thread, written out as two
-      //  guarded blocks -- a loop would let the compiler hoist the 120 block entries into registers and spill)
+      // ---- S: rows below the diagonal tile, L(i, blk) = Cb(i, :) inv(L_kk)^T, straight to the scratch ----
+      for (int ti = 1 + warp; ti < nrt; ti += NW) {
+         const int lr0 = KB * (ti - 1);
+         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
 #pragma unroll
-      for (int rep = 0; rep < 2; ++rep) {
-         const int lr = KB + tid + rep * NT;
-         if (lr < np - k0) {
-            double a[KB];
-            const double* row = Cb + lr * CBS;
-#pragma unroll
-            for (int c = 0; c < KB; ++c) a[c] = row[c];
-#pragma unroll
-            for (int c = 0; c < KB; ++c) {
-               a[c] *= rd[k0 + c];
-#pragma unroll
-               for (int c2 = c + 1; c2 < KB; ++c2) a[c2] = fma(-a[c], ((const volatile double*)Cb)[c2 * CBS + c], a[c2]);
+         for (int kk = 0; kk < 4; ++kk) {
+            const int kc = (4 * kk + t) ^ ((g & 3) << 2);
+            const double a0 = Cb[(lr0 + g) * KB + kc], a1 = Cb[(lr0 + 8 + g) * KB + kc];
+            const double c1 = Li[(8 + g) * KB + kc];
+            if (kk < 2) {  // inv(L)(n, k) = 0 for k > n
+               const double c0 = Li[g * KB + kc];
+               dmma884(acc[0][0][0], acc[0][0][1], a0, c0);
+               dmma884(acc[1][0][0], acc[1][0][1], a1, c0);
             }
-            double* dst = S + tri(k0 + lr) + k0;
-#pragma unroll
-            for (int c = 0; c < KB; ++c) dst[c] = a[c];
+            dmma884(acc[0][1][0], acc[0][1][1], a0, c1);
+            dmma884(acc[1][1][0], acc[1][1][1], a1, c1);
          }
+#pragma unroll
+         for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ntl = 0; ntl < 2; ++ntl) {
+               double* dst = S + tri(k0 + KB + lr0 + 8 * mt + g) + k0 + 8 * ntl + 2 * t;
+               dst[0] = acc[mt][ntl][0];
+               dst[1] = acc[mt][ntl][1];
+            }
       }
       __syncthreads();
    }
@@ -774,34 +807,39 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
       return;
    }
 
-   // ---- backward substitution L^T [y z] = [w_x w_1] by block columns ----
-   for (int k0 = np - KB; k0 >= 0; k0 -= KB) {
-      // t(c, h) = sum_{i > k0 + 15} L(i, k0 + c) y_h(i): lane = (column c, rhs h), warps stride the rows
-      // (one coalesced 128-byte read of L(i, k0:k0+16) per row), then a block reduction over the warps
-      {
-         const int c = lane & 15, h = lane >> 4;
-         const double* yv = h ? b1 : b0;
-         double acc0 = 0.0, acc1 = 0.0;
-         int i = k0 + KB + warp;
-         for (; i + NW < np; i += 2 * NW) {
-            acc0 = fma(S[tri(i) + k0 + c], yv[i], acc0);
-            acc1 = fma(S[tri(i + NW) + k0 + c], yv[i + NW], acc1);
-         }
-         if (i < np) acc0 = fma(S[tri(i) + k0 + c], yv[i], acc0);
-         red[warp * 32 + lane] = acc0 + acc1;
+   // ---- backward substitution L^T [y z] = [w_x w_1], right-looking by blocks ----
+   {
+      const double* wx = S + tri(npa - 2);
+      const double* w1 = S + tri(npa - 1);
+      const int kl = npa - KB;
+      for (int i = tid; i < npa; i += NT) {
+         b0[i] = (i < kl) ? wx[i] : wl[i - kl];
+         b1[i] = (i < kl) ? w1[i] : wl[KB + i - kl];
+      }
+   }
+   __syncthreads();
+   for (int k0 = npa - KB; k0 >= 0; k0 -= KB) {
+      if (warp == 0) {  // y_blk = inv(L_kk)^T w_blk ; lane = (r, rhs h)
+         const int r = lane & 15, h = lane >> 4;
+         const double* wv = (h ? b1 : b0) + k0;
+         double v = 0.0;
+#pragma unroll
+         for (int c = 0; c < KB; ++c)
+            if (c >= r) v = fma(S[tri(k0 + c) + k0 + r], wv[c], v);
+         __syncwarp();
+         (h ? b1 : b0)[k0 + r] = v;
       }
       __syncthreads();
-      if (warp == 0) {
-         const int r = lane & 15, h = lane >> 4;
-         double v = (h ? b1 : b0)[k0 + r];
-         for (int w = 0; w < NW; ++w) v -= red[w * 32 + lane];
+      for (int j = tid; j < k0; j += NT) {  // w(:k0) -= L(blk, :k0)^T y_blk
+         double s0 = b0[j], s1 = b1[j];
 #pragma unroll
-         for (int c = KB - 1; c >= 0; --c) {
-            const double yc = shfl_d(v, c + (h << 4)) * rd[k0 + c];
-            if (r == c) v = yc;
-            else if (r < c) v = fma(-S[tri(k0 + c) + k0 + r], yc, v);
+         for (int r = 0; r < KB; ++r) {
+            const double l = S[tri(k0 + r) + j];
+            s0 = fma(-l, b0[k0 + r], s0);
+            s1 = fma(-l, b1[k0 + r], s1);
          }
-         (h ? b1 : b0)[k0 + r] = v;
+         b0[j] = s0;
+         b1[j] = s1;
       }
       __syncthreads();
    }
@@ -823,11 +861,11 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
 
 template <int NT>
 static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count) {
-   const size_t smem = smem_doubles_ll(NP_MAX) * sizeof(double);
+   const size_t smem = smem_doubles_ll(NPA_MAX) * sizeof(double);
    static bool configured = false;
    if (!configured) {
       MCHRG_CUDA(cudaFuncSetAttribute(eeq_factor_ll_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(smem_doubles_ll(NP_MAX) * sizeof(double))));
+                                      (int)(smem_doubles_ll(NPA_MAX) * sizeof(double))));
       MCHRG_CUDA(cudaFuncSetAttribute(eeq_factor_ll_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       (int)cudaSharedmemCarveoutMaxShared));
       configured = true;
@@ -844,7 +882,7 @@ static void launch_class(mchrg_b200_context* ctx, const Args& a, int count) {
    const size_t smem = (heavy ? smem_doubles(a.np) : smem_doubles_pair(a.np)) * sizeof(double) + (heavy ? 0 : pad);
    static size_t configured = 0;
    if (smem > configured) {
-      const size_t cap = (heavy ? smem_doubles(NP_MAX) : smem_doubles_pair(NP_MAX)) * sizeof(double) + (heavy ? 0 : pad);
+      const size_t cap = (heavy ? smem_doubles(NP_MAX) : smem_doubles_pair(NPA_MAX)) * sizeof(double) + (heavy ? 0 : pad);
       MCHRG_CUDA(cudaFuncSetAttribute(eeq_batch_kernel<NT, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
       // same shared-memory carveout as the factorisation kernel: CTAs of kernels that ask for different
       // L1/shared splits cannot share an SM
@@ -903,7 +941,7 @@ static void launch_chunk(mchrg_b200_context* ctx, Args a, const int32_t* dperm, 
 // neighbouring CTAs similar in cost); shared memory holds the per-atom vectors only
 template <int PH>
 static void launch_pairs(mchrg_b200_context* ctx, Args a, const int32_t* dperm, int count) {
-   a.np = NP_MAX;
+   a.np = NPA_MAX;
    a.perm = dperm;
    launch_class<256, PH>(ctx, a, count);
 }
@@ -916,7 +954,7 @@ static int64_t plan_scratch(const std::vector<int64_t>& hoff, int32_t m0, int32_
    int64_t total = 0;
    for (int32_t m = m0; m < m1; ++m) {
       const int64_t n = hoff[m + 1] - hoff[m];
-      const int64_t npm = (n + KB - 1) / KB * KB;
+      const int64_t npm = aug_order((int)n);
       soff[m - m0] = total;
       total += npm * (npm + 1) / 2;
    }
@@ -924,28 +962,11 @@ static int64_t plan_scratch(const std::vector<int64_t>& hoff, int32_t m0, int32_
 }
 
 // One chunk of the split path.  `a` addresses the chunk (offsets / perm ids in the same id space).
-//   pair phase A on `sa`  ->  factorisation classes on the two high-priority streams  ->  pair phase C on `sc`
+//   pair phase A on `sa`  ->  factorisation on the high-priority stream  ->  pair phase C on `sc`
 // `ready` (may be null) gates phase A (inputs staged); returns the event that marks the chunk's outputs complete.
-static bool factor_in_smem() {  // MCHRG_B200_FACTOR=smem selects the right-looking shared-memory kernel
-   const char* e = std::getenv("MCHRG_B200_FACTOR");
-   return e && e[0] == 's';
-}
-
-static bool factor_per_class() {  // MCHRG_B200_FACTOR=classes
-   const char* e = std::getenv("MCHRG_B200_FACTOR");
-   return e && e[0] == 'c';
-}
-
-// `gate` (in/out): events recorded on the factorisation streams right before the previous chunk's
-// factorisation kernels; phase A of this chunk waits for them, so that those shared-memory-heavy CTAs are
-// placed on the SMs BEFORE this chunk's light pair CTAs can fill them (a heavy CTA only fits on an SM whose
-// shared memory is still free).
 static cudaEvent_t run_chunk_split(mchrg_b200_context* ctx, const Args& a, const int32_t* dperm, int count,
-                                   const std::vector<size_t>& cls_start, const std::vector<int>& cls_count,
-                                   cudaEvent_t ready, cudaStream_t sa, cudaStream_t sc, cudaEvent_t gate[2]) {
+                                   cudaEvent_t ready, cudaStream_t sa, cudaStream_t sc) {
    if (ready) MCHRG_CUDA(cudaStreamWaitEvent(sa, ready, 0));
-   if (gate[0]) MCHRG_CUDA(cudaStreamWaitEvent(sa, gate[0], 0));
-   if (gate[1]) MCHRG_CUDA(cudaStreamWaitEvent(sa, gate[1], 0));
    {
       StreamScope on(ctx, sa);
       launch_pairs<1>(ctx, a, dperm, count);
@@ -953,35 +974,16 @@ static cudaEvent_t run_chunk_split(mchrg_b200_context* ctx, const Args& a, const
    cudaEvent_t eA = ctx->next_event();
    MCHRG_CUDA(cudaEventRecord(eA, sa));
    MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_hi, eA, 0));
-   MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_hi2, eA, 0));
-   gate[0] = ctx->next_event();
-   gate[1] = ctx->next_event();
-   MCHRG_CUDA(cudaEventRecord(gate[0], ctx->stream_hi));
-   MCHRG_CUDA(cudaEventRecord(gate[1], ctx->stream_hi2));
-   if (factor_in_smem()) {
-      launch_chunk<2>(ctx, a, dperm, cls_start, cls_count, ctx->stream_hi, ctx->stream_hi2);
-   } else if (factor_per_class()) {  // A/B knob: one launch per size class, alternating streams
+   {  // one launch for all sizes of the chunk (largest first)
       Args b = a;
-      int flip = 0;
-      for (int c = NP_MAX / KB; c >= 1; --c) {
-         if (cls_count[c] == 0) continue;
-         b.np = NP_MAX;
-         b.perm = dperm + cls_start[c];
-         StreamScope on(ctx, (flip++ & 1) ? ctx->stream_hi2 : ctx->stream_hi);
-         launch_factor_ll<128>(ctx, b, cls_count[c]);
-      }
-   } else {  // left-looking, matrix stays in the scratch: one launch for all sizes of the chunk (largest first)
-      Args b = a;
-      b.np = NP_MAX;
+      b.np = NPA_MAX;
       b.perm = dperm;
       StreamScope on(ctx, ctx->stream_hi);
       launch_factor_ll<128>(ctx, b, count);
    }
-   cudaEvent_t eB1 = ctx->next_event(), eB2 = ctx->next_event();
-   MCHRG_CUDA(cudaEventRecord(eB1, ctx->stream_hi));
-   MCHRG_CUDA(cudaEventRecord(eB2, ctx->stream_hi2));
-   MCHRG_CUDA(cudaStreamWaitEvent(sc, eB1, 0));
-   MCHRG_CUDA(cudaStreamWaitEvent(sc, eB2, 0));
+   cudaEvent_t eB = ctx->next_event();
+   MCHRG_CUDA(cudaEventRecord(eB, ctx->stream_hi));
+   MCHRG_CUDA(cudaStreamWaitEvent(sc, eB, 0));
    if (a.energy || a.gradient) {
       StreamScope on(ctx, sc);
       launch_pairs<3>(ctx, a, dperm, count);
@@ -1031,7 +1033,6 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
       a.scratch = nullptr; a.soff = nullptr; a.vecg = nullptr; a.lamg = nullptr; a.ntot = 0;
       a.par = model->d_par;
       a.etab = ctx->erf_tab;
-      a.debug = std::getenv("MCHRG_B200_DEBUG") ? atoi(std::getenv("MCHRG_B200_DEBUG")) : 0;
       a.nid = model->nid;
       a.kcn = model->ncoord.kcn;
       a.cutoff2 = model->ncoord.cutoff * model->ncoord.cutoff;
@@ -1095,14 +1096,10 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
             for (int c = 0; c < nchunk; ++c) batch::launch_pairs<1>(ctx, b, dperm + chunk_off[c], (int)(chunk_off[c + 1] - chunk_off[c]));
             MCHRG_CUDA(cudaEventRecord(t[1], ctx->stream));
             for (int c = 0; c < nchunk; ++c) {
-               if (batch::factor_in_smem()) {
-                  batch::launch_chunk<2>(ctx, b, dperm + chunk_off[c], starts[c], counts[c], ctx->stream, ctx->stream);
-               } else {
-                  batch::Args bb = b;
-                  bb.np = batch::NP_MAX;
-                  bb.perm = dperm + chunk_off[c];
-                  batch::launch_factor_ll<128>(ctx, bb, (int)(chunk_off[c + 1] - chunk_off[c]));
-               }
+               batch::Args bb = b;
+               bb.np = batch::NPA_MAX;
+               bb.perm = dperm + chunk_off[c];
+               batch::launch_factor_ll<128>(ctx, bb, (int)(chunk_off[c + 1] - chunk_off[c]));
             }
             MCHRG_CUDA(cudaEventRecord(t[2], ctx->stream));
             for (int c = 0; c < nchunk; ++c) batch::launch_pairs<3>(ctx, b, dperm + chunk_off[c], (int)(chunk_off[c + 1] - chunk_off[c]));
@@ -1115,12 +1112,11 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
             return 0;
          }
          cudaEvent_t last = nullptr;
-         cudaEvent_t gate[2] = {nullptr, nullptr};
          for (int c = 0; c < nchunk; ++c) {
             const int cnt = (int)(chunk_off[c + 1] - chunk_off[c]);
             if (cnt == 0) continue;
-            last = batch::run_chunk_split(ctx, a, dperm + chunk_off[c], cnt, starts[c], counts[c], c == 0 ? staged : nullptr,
-                                          ctx->stream_aux, ctx->stream, gate);
+            last = batch::run_chunk_split(ctx, a, dperm + chunk_off[c], cnt, c == 0 ? staged : nullptr, ctx->stream_aux,
+                                          ctx->stream);
          }
          (void)last;  // phase C runs on the main stream, which finish() synchronises
          MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1163,7 +1159,6 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
       std::vector<std::vector<int64_t>> loc_off(nchunk);
       std::vector<std::vector<int32_t>> loc_perm(nchunk);
       std::vector<std::vector<int64_t>> loc_soff(nchunk);
-      cudaEvent_t gate[2] = {nullptr, nullptr};
       cudaEvent_t start = ctx->next_event();
       MCHRG_CUDA(cudaEventRecord(start, ctx->stream));
       MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_in, start, 0));
@@ -1210,7 +1205,7 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
             a.ntot = (int64_t)na;
             cudaEvent_t ev_in2 = ctx->next_event();
             MCHRG_CUDA(cudaEventRecord(ev_in2, in));
-            ev_done = batch::run_chunk_split(ctx, a, d_perm, mc, cls_start, cls_count, ev_in2, ctx->stream_aux, ctx->stream, gate);
+            ev_done = batch::run_chunk_split(ctx, a, d_perm, mc, ev_in2, ctx->stream_aux, ctx->stream);
          } else {
             batch::launch_chunk<0>(ctx, a, d_perm, cls_start, cls_count, ctx->stream, ctx->stream_aux);
             cudaEvent_t aux_done = ctx->next_event();
