@@ -615,24 +615,32 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
 //   each other's latencies.
 // ------------------------------------------------------------------------------------------------
 constexpr int TS = KB + 1;            // row stride of the diagonal tile
+constexpr int CBW = 20;               // column buffer: 16 entries (parity-split) + [16] pivot + [17] next diagonal entry
 
 
 // doubles: block column below the diagonal tile (swizzled, stride 16) | diagonal tile | its inverse (swizzled)
 //          | column / row broadcast buffers (double buffered) | w of the last block | scalars
 __host__ __device__ inline size_t smem_doubles_ll(int npa) {
-   return (size_t)(npa > KB ? npa - KB : 2) * KB + KB * TS + KB * KB + 4 * KB + 2 * KB + 8 +
+   return (size_t)(npa > KB ? npa - KB : 2) * KB + KB * TS + KB * KB + 2 * CBW + 2 * KB + KB + 2 * KB + 8 +
           (npa <= 2 * KB ? 2 * (size_t)npa : 0);  // tiny orders: room for the two solution vectors
 }
 
 __device__ __forceinline__ int swz(int row, int col) { return row * KB + (col ^ ((row & 3) << 2)); }
 
 // Cholesky + inverse of the 16 x 16 tile T (stride TS; lower triangle valid) by one warp.
-// lane = (row r = lane & 15, column parity h = lane >> 4) holds m[k] = T(r, 2k + h) and x[k] = X(r, 2k + h),
-// X accumulating inv(L) by the same eliminations (Gauss-Jordan on [A | I]).  Columns >= nfree are kept at
-// identity (the right-hand-side rows of the augmented matrix).  Outputs: L in T, inv(L) in Li (swizzled).
+// lane = (row r = lane & 15, column parity h = lane >> 4) holds m[k] = A(r, 2k + h) and x[k] = X(r, 2k + h).
+// The elimination runs on UNSCALED columns (f_r = a_rc / a_cc, L(r, c) = a_rc / sqrt(a_cc) only at the end),
+// X collects inv(L) by the same row operations on [A | I] with its rows scaled at the end as well.  Per step
+// the owners publish column c (and row c of X) through shared memory; every lane then computes the NEXT
+// pivot a_{c+1,c+1} - a_{c+1,c}^2 / a_cc and its reciprocal redundantly, so the only serial dependence from
+// step to step is one FMA + one reciprocal (~90 cycles) and the shared-memory broadcast of the next column
+// runs in its shadow (measured: tools/micro/diag_latency.cu).
+// Columns >= nfree are kept at identity (the right-hand-side rows of the augmented matrix).
+// Outputs: inv(L) in Li (swizzled); L in T when want_l.  Scratch: cbuf[2][20], rbuf[2][16], dvec[16].
 // Returns 0 or the 1-based local index of the first non-positive pivot.
-__device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cbuf, double* rbuf, int lane, int nfree) {
-   // (no __restrict__ here: the broadcast buffers are written by OTHER lanes between the warp barriers)
+// (No __restrict__ on the broadcast buffers: they are written by OTHER lanes between the warp barriers.)
+__device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cbuf, double* rbuf, double* dvec, int lane,
+                                               int nfree, bool want_l) {
    const int r = lane & 15, h = lane >> 4;
    double m[8], x[8];
 #pragma unroll
@@ -642,43 +650,60 @@ __device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cb
       if (c >= nfree) m[k] = (c == r) ? 1.0 : 0.0;
       x[k] = (c == r) ? 1.0 : 0.0;
    }
-   int bad = 0;
    const int myslot = (r & 1) * 8 + (r >> 1);  // parity-split position of row r in the column buffer
+   auto publish = [&](const int c) {
+      double* cb = cbuf + (c & 1) * CBW;
+      const bool forced = (c >= KB - 2) && (c >= nfree);  // right-hand-side rows: their own columns stay identity
+      if (h == (c & 1)) {
+         cb[myslot] = (r > c && !forced) ? m[c >> 1] : 0.0;
+         if (r == c) cb[16] = forced ? 1.0 : m[c >> 1];
+      }
+      if (c + 1 < KB && r == c + 1 && h == ((c + 1) & 1)) cb[17] = m[(c + 1) >> 1];
+      if (r == c) {
+         double2* rb = reinterpret_cast<double2*>(rbuf + (c & 1) * KB + h * 8);
+#pragma unroll
+         for (int k = 0; k < 4; ++k) rb[k] = make_double2(x[2 * k], x[2 * k + 1]);
+      }
+   };
+   publish(0);
+   __syncwarp();
+   double piv = cbuf[16];
+   double d = 1.0 / piv;
+   int bad = !(piv > 0.0) ? 1 : 0;
 #pragma unroll
    for (int c = 0; c < KB; ++c) {
-      double* cb = cbuf + (c & 1) * KB;
-      double* rb = rbuf + (c & 1) * KB;
-      double piv = shfl_d(m[c >> 1], c + ((c & 1) << 4));
-      const bool forced = (c >= KB - 2) && (c >= nfree);  // right-hand-side rows: their own columns stay identity
-      if (forced) piv = 1.0;
-      bad = (!(piv > 0.0) && bad == 0) ? (c + 1) : bad;
-      const double rinv = rsqrt(piv);
-      if (h == (c & 1)) {  // owners of column c
-         double l = m[c >> 1] * rinv;  // r == c: sqrt(piv)
-         if (forced) l = (r == c) ? 1.0 : 0.0;
-         if (r >= c) m[c >> 1] = l;
-         cb[myslot] = (r > c) ? l : 0.0;
+      const double* cb = cbuf + (c & 1) * CBW;
+      const double* rb = rbuf + (c & 1) * KB;
+      if (lane == 0) dvec[c] = d;
+      double dn = 0.0;
+      if (c + 1 < KB) {  // next pivot, redundantly in every lane
+         const bool forced = (c + 1 >= KB - 2) && (c + 1 >= nfree);
+         const double u = cb[((c + 1) & 1) * 8 + ((c + 1) >> 1)];
+         piv = forced ? 1.0 : fma(-u * u, d, cb[17]);
+         bad = (!(piv > 0.0) && bad == 0) ? (c + 2) : bad;
+         dn = 1.0 / piv;
       }
-      if (r == c) {  // row c of X, scaled
-#pragma unroll
-         for (int k = 0; k < 8; ++k) {
-            x[k] *= rinv;
-            rb[h * 8 + k] = x[k];
-         }
-      }
-      __syncwarp();
-      const double lrc = cb[myslot];  // 0 for r <= c: the updates below leave those rows alone
+      const double f = cb[myslot] * d;  // 0 for r <= c: the updates below leave those rows alone
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-         m[k] = fma(-lrc, cb[h * 8 + k], m[k]);   // entries right of the diagonal collect garbage; never used
-         x[k] = fma(-lrc, rb[h * 8 + k], x[k]);
+         m[k] = fma(-f, cb[h * 8 + k], m[k]);  // entries right of the diagonal collect garbage; never used
+         x[k] = fma(-f, rb[h * 8 + k], x[k]);
+      }
+      if (c + 1 < KB) {
+         publish(c + 1);
+         __syncwarp();
+         d = dn;
       }
    }
+   __syncwarp();
+   if (lane < KB) dvec[lane] = sqrt(dvec[lane]);  // 1 / L(c, c)
+   __syncwarp();
+   const double rs = dvec[r];
 #pragma unroll
    for (int k = 0; k < 8; ++k) {
       const int c = 2 * k + h;
-      T[r * TS + c] = (c <= r) ? m[k] : 0.0;
-      Li[swz(r, c)] = (c <= r) ? x[k] : 0.0;
+      Li[swz(r, c)] = (c <= r) ? x[k] * rs : 0.0;
+      if (want_l) T[r * TS + c] = (c <= r) ? m[k] * dvec[c] : 0.0;
    }
    return bad;
 }
@@ -698,22 +723,34 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
    double* T = Cb + (size_t)(npa > KB ? npa - KB : 2) * KB;
    double* Li = T + KB * TS;
    double* cbuf = Li + KB * KB;
-   double* rbuf = cbuf + 2 * KB;
-   double* wl = rbuf + 2 * KB;           // w of the last block: wl[h * 16 + c]
+   double* rbuf = cbuf + 2 * CBW;
+   double* dvec = rbuf + 2 * KB;
+   double* wl = dvec + KB;               // w of the last block: wl[h * 16 + c]
    double* scal = wl + 2 * KB;
    double* b0 = (npa <= 2 * KB) ? scal + 8 : Cb;  // solution vectors alias the block column buffer
    double* b1 = b0 + npa;
-   __shared__ int sfail;
-   if (tid == 0) sfail = 0;
+   __shared__ int sfail, next_tile;
+   if (tid == 0) { sfail = 0; next_tile = 1; }
    __syncthreads();
    const int g = lane >> 2, t = lane & 3;
 
    for (int k0 = 0; k0 < npa; k0 += KB) {
       const int nrt = (npa - k0) / KB;
-      // ---- U: block column with the left-looking update, one 16-row tile per warp and turn ----
-      for (int ti = warp; ti < nrt; ti += NW) {
+      // ---- U: block column with the left-looking update, 16-row tiles handed out dynamically ----
+      auto u_tile = [&](const int ti) {
          const int i0 = k0 + KB * ti;
-         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+         double acc[2][2][2];
+         // original entries first (their loads overlap the first round of panel loads); entries right of the
+         // diagonal do not exist in the packed storage (and are never used)
+#pragma unroll
+         for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ntl = 0; ntl < 2; ++ntl) {
+               const int row = i0 + 8 * mt + g, col = 8 * ntl + 2 * t;
+               const double* src = S + tri(row) + k0 + col;
+               acc[mt][ntl][0] = (k0 + col <= row) ? -src[0] : 0.0;
+               acc[mt][ntl][1] = (k0 + col + 1 <= row) ? -src[1] : 0.0;
+            }
          const double* ra0 = S + tri(i0 + g) + t;
          const double* ra1 = S + tri(i0 + 8 + g) + t;
          const double* rb0 = S + tri(k0 + g) + t;
@@ -726,16 +763,15 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
             dmma884(acc[1][0][0], acc[1][0][1], a1, c0);
             dmma884(acc[1][1][0], acc[1][1][1], a1, c1);
          }
+         // acc = L L^T - A: store the negative
 #pragma unroll
          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int ntl = 0; ntl < 2; ++ntl) {
                const int lr = 8 * mt + g, col = 8 * ntl + 2 * t;  // within the tile / the block column
                const int row = i0 + lr;
-               const double* src = S + tri(row) + k0 + col;
-               // entries right of the diagonal do not exist in the packed storage (and are never used)
-               const double v0 = (k0 + col <= row) ? src[0] - acc[mt][ntl][0] : 0.0;
-               const double v1 = (k0 + col + 1 <= row) ? src[1] - acc[mt][ntl][1] : 0.0;
+               const double v0 = (k0 + col <= row) ? -acc[mt][ntl][0] : 0.0;
+               const double v1 = (k0 + col + 1 <= row) ? -acc[mt][ntl][1] : 0.0;
                if (ti == 0) {
                   T[lr * TS + col] = v0;
                   T[lr * TS + col + 1] = v1;
@@ -743,14 +779,15 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
                   *reinterpret_cast<double2*>(Cb + swz(KB * (ti - 1) + lr, col)) = make_double2(v0, v1);
                }
             }
-      }
-      __syncthreads();
-      // ---- D: diagonal tile, Cholesky + inverse; the inverse goes to global in place of the block ----
+      };
+      // warp 0: diagonal tile, then its factorisation (D) while the other warps update the rows below
       if (warp == 0) {
-         const bool last = (k0 + KB == npa);
-         const int bad = diag_factor_inv(T, Li, cbuf, rbuf, lane, last ? KB - 2 : KB);
-         if (bad && lane == 0) sfail = k0 + bad;
+         u_tile(0);
          __syncwarp();
+         // ---- D: diagonal tile, Cholesky + inverse; the inverse goes to global in place of the block ----
+         const bool last = (k0 + KB == npa);
+         const int bad = diag_factor_inv(T, Li, cbuf, rbuf, dvec, lane, last ? KB - 2 : KB, last);
+         if (bad && lane == 0) sfail = k0 + bad;
          __syncwarp();
          const int r = lane & 15, h = lane >> 4;
 #pragma unroll
@@ -762,6 +799,13 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
             wl[lane] = (lane < KB - 2) ? T[(KB - 2) * TS + lane] : 0.0;
             wl[KB + lane] = (lane < KB - 2) ? T[(KB - 1) * TS + lane] : 0.0;
          }
+      }
+      for (;;) {
+         int ti = 0;
+         if (lane == 0) ti = atomicAdd(&next_tile, 1);
+         ti = __shfl_sync(0xffffffffu, ti, 0);
+         if (ti >= nrt) break;
+         u_tile(ti);
       }
       __syncthreads();
       if (sfail) break;
@@ -791,6 +835,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
                dst[1] = acc[mt][ntl][1];
             }
       }
+      if (tid == 0) next_tile = 1;
       __syncthreads();
    }
    if (sfail) {
