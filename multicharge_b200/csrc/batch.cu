@@ -32,6 +32,15 @@ constexpr int NVEC = 13;
 // split path: the matrix is augmented by two right-hand-side rows (see eeq_factor_ll_kernel)
 constexpr int NPA_MAX = NP_MAX + KB;
 __host__ __device__ inline int aug_order(int n) { return ((n + 2 + KB - 1) / KB) * KB; }
+// Scratch layout of the split path: 8 x 8 blocks of the lower block triangle, block (R, C) at 64 (R (R + 1) / 2 + C),
+// inside a block the entry (g, c) sits at (g * 4 + (c & 3)) * 2 + (c >> 2) -- the order in which the 32 lanes
+// of an FP64 mma fragment (lane = g * 4 + t) consume it: one 16-byte load per lane fetches the operands of two
+// k-steps and a warp reads 512 contiguous bytes.
+__host__ __device__ inline int64_t lay_size(int npa) { return 32 * (int64_t)(npa / 8) * (npa / 8 + 1); }
+__device__ __forceinline__ int lay(int i, int j) {
+   const int R = i >> 3, C = j >> 3;
+   return 64 * (R * (R + 1) / 2 + C) + ((((i & 7) << 2) + (j & 3)) << 1) + ((j >> 2) & 1);
+}
 
 struct Args {
    const int64_t* offsets;
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          } else {
             v = 0.0;
          }
-         A[e] = v;
+         A[MAT_IN_SMEM ? e : lay(i, j)] = v;
       }
       const unsigned m = __ballot_sync(FULL, hit);
       if (hit) ring[(wr + __popc(m & lt_mask)) & (AUX_RING - 1)] = (i << 16) | j;
@@ -314,8 +323,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    if (PH == 1) {  // hand xvec, thalf, fcut to the later phases; right-hand sides [x | 1] = last two matrix rows
       for (int i = tid; i < n; i += NT) {
          xv_g[i] = xv[i]; th_g[i] = th[i]; fc_g[i] = fcut[i];
-         A[tri(np - 2) + i] = xv[i];
-         A[tri(np - 1) + i] = 1.0;
+         A[lay(np - 2, i)] = xv[i];
+         A[lay(np - 1, i)] = 1.0;
       }
       return;
    }
@@ -709,7 +718,7 @@ __device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cb
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
+__global__ void __launch_bounds__(NT, 896 / NT) eeq_factor_ll_kernel(Args p) {
    extern __shared__ __align__(16) double sm[];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    constexpr int NW = NT / 32;
@@ -747,21 +756,27 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
 #pragma unroll
             for (int ntl = 0; ntl < 2; ++ntl) {
                const int row = i0 + 8 * mt + g, col = 8 * ntl + 2 * t;
-               const double* src = S + tri(row) + k0 + col;
+               // (a block right of the diagonal block does not exist: keep the address inside the diagonal one)
+               const double* src = S + lay(row, (k0 + col <= row) ? k0 + col : k0);
                acc[mt][ntl][0] = (k0 + col <= row) ? -src[0] : 0.0;
-               acc[mt][ntl][1] = (k0 + col + 1 <= row) ? -src[1] : 0.0;
+               acc[mt][ntl][1] = (k0 + col + 1 <= row) ? -src[2] : 0.0;  // (g, c + 1) is 2 doubles on (c even)
             }
-         const double* ra0 = S + tri(i0 + g) + t;
-         const double* ra1 = S + tri(i0 + 8 + g) + t;
-         const double* rb0 = S + tri(k0 + g) + t;
-         const double* rb1 = S + tri(k0 + 8 + g) + t;
-#pragma unroll 4
-         for (int j0 = 0; j0 < k0; j0 += 4) {
-            const double a0 = ra0[j0], a1 = ra1[j0], c0 = rb0[j0], c1 = rb1[j0];
-            dmma884(acc[0][0][0], acc[0][0][1], a0, c0);
-            dmma884(acc[0][1][0], acc[0][1][1], a0, c1);
-            dmma884(acc[1][0][0], acc[1][0][1], a1, c0);
-            dmma884(acc[1][1][0], acc[1][1][1], a1, c1);
+         // fragments of two k-steps per 16-byte load, 512 contiguous bytes per warp and block
+         const double2* pa0 = reinterpret_cast<const double2*>(S + 64 * tri(i0 >> 3)) + lane;
+         const double2* pa1 = reinterpret_cast<const double2*>(S + 64 * tri((i0 >> 3) + 1)) + lane;
+         const double2* pb0 = reinterpret_cast<const double2*>(S + 64 * tri(k0 >> 3)) + lane;
+         const double2* pb1 = reinterpret_cast<const double2*>(S + 64 * tri((k0 >> 3) + 1)) + lane;
+#pragma unroll 2
+         for (int cb = 0; cb < (k0 >> 3); ++cb) {
+            const double2 a0 = pa0[32 * cb], a1 = pa1[32 * cb], c0 = pb0[32 * cb], c1 = pb1[32 * cb];
+            dmma884(acc[0][0][0], acc[0][0][1], a0.x, c0.x);
+            dmma884(acc[0][1][0], acc[0][1][1], a0.x, c1.x);
+            dmma884(acc[1][0][0], acc[1][0][1], a1.x, c0.x);
+            dmma884(acc[1][1][0], acc[1][1][1], a1.x, c1.x);
+            dmma884(acc[0][0][0], acc[0][0][1], a0.y, c0.y);
+            dmma884(acc[0][1][0], acc[0][1][1], a0.y, c1.y);
+            dmma884(acc[1][0][0], acc[1][0][1], a1.y, c0.y);
+            dmma884(acc[1][1][0], acc[1][1][1], a1.y, c1.y);
          }
          // acc = L L^T - A: store the negative
 #pragma unroll
@@ -793,7 +808,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
 #pragma unroll
          for (int k = 0; k < 8; ++k) {
             const int c = 2 * k + h;
-            if (c <= r) S[tri(k0 + r) + k0 + c] = Li[swz(r, c)];
+            if (c <= r) S[lay(k0 + r, k0 + c)] = Li[swz(r, c)];
          }
          if (last && lane < KB) {  // forward-substituted right-hand sides of the last block
             wl[lane] = (lane < KB - 2) ? T[(KB - 2) * TS + lane] : 0.0;
@@ -830,9 +845,9 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int ntl = 0; ntl < 2; ++ntl) {
-               double* dst = S + tri(k0 + KB + lr0 + 8 * mt + g) + k0 + 8 * ntl + 2 * t;
+               double* dst = S + lay(k0 + KB + lr0 + 8 * mt + g, k0 + 8 * ntl + 2 * t);
                dst[0] = acc[mt][ntl][0];
-               dst[1] = acc[mt][ntl][1];
+               dst[2] = acc[mt][ntl][1];
             }
       }
       if (tid == 0) next_tile = 1;
@@ -854,12 +869,10 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
 
    // ---- backward substitution L^T [y z] = [w_x w_1], right-looking by blocks ----
    {
-      const double* wx = S + tri(npa - 2);
-      const double* w1 = S + tri(npa - 1);
       const int kl = npa - KB;
       for (int i = tid; i < npa; i += NT) {
-         b0[i] = (i < kl) ? wx[i] : wl[i - kl];
-         b1[i] = (i < kl) ? w1[i] : wl[KB + i - kl];
+         b0[i] = (i < kl) ? S[lay(npa - 2, i)] : wl[i - kl];
+         b1[i] = (i < kl) ? S[lay(npa - 1, i)] : wl[KB + i - kl];
       }
    }
    __syncthreads();
@@ -870,7 +883,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
          double v = 0.0;
 #pragma unroll
          for (int c = 0; c < KB; ++c)
-            if (c >= r) v = fma(S[tri(k0 + c) + k0 + r], wv[c], v);
+            if (c >= r) v = fma(S[lay(k0 + c, k0 + r)], wv[c], v);
          __syncwarp();
          (h ? b1 : b0)[k0 + r] = v;
       }
@@ -879,7 +892,7 @@ __global__ void __launch_bounds__(NT, 768 / NT) eeq_factor_ll_kernel(Args p) {
          double s0 = b0[j], s1 = b1[j];
 #pragma unroll
          for (int r = 0; r < KB; ++r) {
-            const double l = S[tri(k0 + r) + j];
+            const double l = S[lay(k0 + r, j)];
             s0 = fma(-l, b0[k0 + r], s0);
             s1 = fma(-l, b1[k0 + r], s1);
          }
@@ -1001,7 +1014,7 @@ static int64_t plan_scratch(const std::vector<int64_t>& hoff, int32_t m0, int32_
       const int64_t n = hoff[m + 1] - hoff[m];
       const int64_t npm = aug_order((int)n);
       soff[m - m0] = total;
-      total += npm * (npm + 1) / 2;
+      total += lay_size((int)npm);
    }
    return total;
 }
