@@ -624,6 +624,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
 //   each other's latencies.
 // ------------------------------------------------------------------------------------------------
 constexpr int TS = KB + 1;            // row stride of the diagonal tile
+#ifndef LL_MINB
+#define LL_MINB 6
+#endif
 constexpr int CBW = 20;               // column buffer: 16 entries (parity-split) + [16] pivot + [17] next diagonal entry
 
 
@@ -718,7 +721,7 @@ __device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cb
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, 896 / NT) eeq_factor_ll_kernel(Args p) {
+__global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
    extern __shared__ __align__(16) double sm[];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    constexpr int NW = NT / 32;
@@ -738,34 +741,45 @@ __global__ void __launch_bounds__(NT, 896 / NT) eeq_factor_ll_kernel(Args p) {
    double* scal = wl + 2 * KB;
    double* b0 = (npa <= 2 * KB) ? scal + 8 : Cb;  // solution vectors alias the block column buffer
    double* b1 = b0 + npa;
-   __shared__ int sfail, next_tile;
-   if (tid == 0) { sfail = 0; next_tile = 1; }
-   __syncthreads();
+   __shared__ int sfail, next_job;
+   __shared__ double T2[KB * TS];  // next diagonal tile, updated one block column ahead
+   if (tid == 0) { sfail = 0; next_job = 0; }
    const int g = lane >> 2, t = lane & 3;
+   if (warp == 0) {  // first diagonal tile: nothing to its left
+      const int r = lane & 15, h = lane >> 4;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+         const int c = 2 * k + h;
+         T[r * TS + c] = (c <= r) ? S[lay(r, c)] : 0.0;
+      }
+   }
+   __syncthreads();
 
    for (int k0 = 0; k0 < npa; k0 += KB) {
       const int nrt = (npa - k0) / KB;
-      // ---- U: block column with the left-looking update, 16-row tiles handed out dynamically ----
-      auto u_tile = [&](const int ti) {
-         const int i0 = k0 + KB * ti;
+      // ---- U: left-looking updates of this block column's row tiles (jobs 1 .. nrt-1 -> Cb) and, one block
+      //      column ahead, of the NEXT diagonal tile with the columns [0, k0) (job 0 -> T2), handed out
+      //      dynamically; meanwhile warp 0 factors the current diagonal tile (D) ----
+      auto u_job = [&](const int job) {
+         const int i0 = k0 + KB * (job == 0 ? 1 : job);  // rows of the tile
+         const int j0 = (job == 0) ? k0 + KB : k0;       // columns of the tile = rows of the B strip
          double acc[2][2][2];
          // original entries first (their loads overlap the first round of panel loads); entries right of the
-         // diagonal do not exist in the packed storage (and are never used)
+         // diagonal do not exist in the storage (and are never used)
 #pragma unroll
          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int ntl = 0; ntl < 2; ++ntl) {
-               const int row = i0 + 8 * mt + g, col = 8 * ntl + 2 * t;
-               // (a block right of the diagonal block does not exist: keep the address inside the diagonal one)
-               const double* src = S + lay(row, (k0 + col <= row) ? k0 + col : k0);
-               acc[mt][ntl][0] = (k0 + col <= row) ? -src[0] : 0.0;
-               acc[mt][ntl][1] = (k0 + col + 1 <= row) ? -src[2] : 0.0;  // (g, c + 1) is 2 doubles on (c even)
+               const int row = i0 + 8 * mt + g, col = j0 + 8 * ntl + 2 * t;
+               const double* src = S + lay(row, (col <= row) ? col : j0);
+               acc[mt][ntl][0] = (col <= row) ? -src[0] : 0.0;
+               acc[mt][ntl][1] = (col + 1 <= row) ? -src[2] : 0.0;  // (g, c + 1) is 2 doubles on (c even)
             }
          // fragments of two k-steps per 16-byte load, 512 contiguous bytes per warp and block
          const double2* pa0 = reinterpret_cast<const double2*>(S + 64 * tri(i0 >> 3)) + lane;
          const double2* pa1 = reinterpret_cast<const double2*>(S + 64 * tri((i0 >> 3) + 1)) + lane;
-         const double2* pb0 = reinterpret_cast<const double2*>(S + 64 * tri(k0 >> 3)) + lane;
-         const double2* pb1 = reinterpret_cast<const double2*>(S + 64 * tri((k0 >> 3) + 1)) + lane;
+         const double2* pb0 = reinterpret_cast<const double2*>(S + 64 * tri(j0 >> 3)) + lane;
+         const double2* pb1 = reinterpret_cast<const double2*>(S + 64 * tri((j0 >> 3) + 1)) + lane;
 #pragma unroll 2
          for (int cb = 0; cb < (k0 >> 3); ++cb) {
             const double2 a0 = pa0[32 * cb], a1 = pa1[32 * cb], c0 = pb0[32 * cb], c1 = pb1[32 * cb];
@@ -783,22 +797,18 @@ __global__ void __launch_bounds__(NT, 896 / NT) eeq_factor_ll_kernel(Args p) {
          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int ntl = 0; ntl < 2; ++ntl) {
-               const int lr = 8 * mt + g, col = 8 * ntl + 2 * t;  // within the tile / the block column
-               const int row = i0 + lr;
-               const double v0 = (k0 + col <= row) ? -acc[mt][ntl][0] : 0.0;
-               const double v1 = (k0 + col + 1 <= row) ? -acc[mt][ntl][1] : 0.0;
-               if (ti == 0) {
-                  T[lr * TS + col] = v0;
-                  T[lr * TS + col + 1] = v1;
+               const int lr = 8 * mt + g, lc = 8 * ntl + 2 * t;  // within the tile
+               if (job == 0) {
+                  T2[lr * TS + lc] = (lc <= lr) ? -acc[mt][ntl][0] : 0.0;
+                  T2[lr * TS + lc + 1] = (lc + 1 <= lr) ? -acc[mt][ntl][1] : 0.0;
                } else {
-                  *reinterpret_cast<double2*>(Cb + swz(KB * (ti - 1) + lr, col)) = make_double2(v0, v1);
+                  *reinterpret_cast<double2*>(Cb + swz(KB * (job - 1) + lr, lc)) = make_double2(-acc[mt][ntl][0], -acc[mt][ntl][1]);
                }
             }
       };
-      // warp 0: diagonal tile, then its factorisation (D) while the other warps update the rows below
-      if (warp == 0) {
-         u_tile(0);
-         __syncwarp();
+      // (the warps of a CTA sit on different SM sub-partitions: rotate the serial FP64-heavy D step over them so
+      //  that the D chains of the co-resident molecules do not all queue on one FP64 pipe)
+      if (warp == ((blockIdx.x + (k0 >> 4)) & (NW - 1))) {
          // ---- D: diagonal tile, Cholesky + inverse; the inverse goes to global in place of the block ----
          const bool last = (k0 + KB == npa);
          const int bad = diag_factor_inv(T, Li, cbuf, rbuf, dvec, lane, last ? KB - 2 : KB, last);
@@ -815,16 +825,19 @@ __global__ void __launch_bounds__(NT, 896 / NT) eeq_factor_ll_kernel(Args p) {
             wl[KB + lane] = (lane < KB - 2) ? T[(KB - 1) * TS + lane] : 0.0;
          }
       }
-      for (;;) {
-         int ti = 0;
-         if (lane == 0) ti = atomicAdd(&next_tile, 1);
-         ti = __shfl_sync(0xffffffffu, ti, 0);
-         if (ti >= nrt) break;
-         u_tile(ti);
+      if (nrt > 1) {
+         for (;;) {
+            int job = 0;
+            if (lane == 0) job = atomicAdd(&next_job, 1);
+            job = __shfl_sync(0xffffffffu, job, 0);
+            if (job >= nrt) break;
+            u_job(job);
+         }
       }
       __syncthreads();
       if (sfail) break;
-      // ---- S: rows below the diagonal tile, L(i, blk) = Cb(i, :) inv(L_kk)^T, straight to the scratch ----
+      // ---- S: rows below the diagonal tile, L(i, blk) = Cb(i, :) inv(L_kk)^T, straight to the scratch; the warp
+      //      of the first tile also completes the next diagonal tile, T = T2 - L(tile, blk) L(tile, blk)^T ----
       for (int ti = 1 + warp; ti < nrt; ti += NW) {
          const int lr0 = KB * (ti - 1);
          double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
@@ -849,8 +862,35 @@ __global__ void __launch_bounds__(NT, 896 / NT) eeq_factor_ll_kernel(Args p) {
                dst[0] = acc[mt][ntl][0];
                dst[2] = acc[mt][ntl][1];
             }
+         if (ti == 1) {
+            __syncwarp();
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+               for (int ntl = 0; ntl < 2; ++ntl)
+                  *reinterpret_cast<double2*>(Cb + swz(8 * mt + g, 8 * ntl + 2 * t)) = make_double2(acc[mt][ntl][0], acc[mt][ntl][1]);
+            __syncwarp();
+            double d2[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+               const int kc = (4 * kk + t) ^ ((g & 3) << 2);
+               const double a0 = Cb[g * KB + kc], a1 = Cb[(8 + g) * KB + kc];  // A(m, k) and B(k, n) = A(n, k)
+               dmma884(d2[0][0][0], d2[0][0][1], a0, a0);
+               dmma884(d2[0][1][0], d2[0][1][1], a0, a1);
+               dmma884(d2[1][0][0], d2[1][0][1], a1, a0);
+               dmma884(d2[1][1][0], d2[1][1][1], a1, a1);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+               for (int ntl = 0; ntl < 2; ++ntl) {
+                  const int lr = 8 * mt + g, lc = 8 * ntl + 2 * t;
+                  T[lr * TS + lc] = (lc <= lr) ? T2[lr * TS + lc] - d2[mt][ntl][0] : 0.0;
+                  T[lr * TS + lc + 1] = (lc + 1 <= lr) ? T2[lr * TS + lc + 1] - d2[mt][ntl][1] : 0.0;
+               }
+         }
       }
-      if (tid == 0) next_tile = 1;
+      if (tid == 0) next_job = 0;
       __syncthreads();
    }
    if (sfail) {
@@ -877,7 +917,7 @@ __global__ void __launch_bounds__(NT, 896 / NT) eeq_factor_ll_kernel(Args p) {
    }
    __syncthreads();
    for (int k0 = npa - KB; k0 >= 0; k0 -= KB) {
-      if (warp == 0) {  // y_blk = inv(L_kk)^T w_blk ; lane = (r, rhs h)
+      if (warp == ((blockIdx.x + (k0 >> 4)) & (NW - 1))) {  // y_blk = inv(L_kk)^T w_blk ; lane = (r, rhs h)
          const int r = lane & 15, h = lane >> 4;
          const double* wv = (h ? b1 : b0) + k0;
          double v = 0.0;
@@ -918,8 +958,8 @@ __global__ void __launch_bounds__(NT, 896 / NT) eeq_factor_ll_kernel(Args p) {
 }
 
 template <int NT>
-static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count) {
-   const size_t smem = smem_doubles_ll(NPA_MAX) * sizeof(double);
+static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count, int npa_max) {
+   const size_t smem = smem_doubles_ll(npa_max) * sizeof(double);
    static bool configured = false;
    if (!configured) {
       MCHRG_CUDA(cudaFuncSetAttribute(eeq_factor_ll_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -929,6 +969,26 @@ static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count) 
       configured = true;
    }
    MCHRG_LAUNCH(ctx, eeq_factor_ll_kernel<NT>, (unsigned)count, NT, smem, a);
+}
+
+constexpr int LL_NT = 128;  // threads per molecule in the factorisation kernel
+
+// Factorisation launches of one chunk: the class-sorted permutation is cut into a few groups of size classes so
+// that the block column buffer (and with it the number of resident molecules per SM) matches the molecule size.
+static void launch_factor_groups(mchrg_b200_context* ctx, const Args& a, const int32_t* dperm,
+                                 const std::vector<size_t>& cls_start, const std::vector<int>& cls_count) {
+   constexpr int NCLASS = NP_MAX / KB;
+   static const int group = std::getenv("MCHRG_B200_FACTOR_GROUP") ? std::max(1, atoi(std::getenv("MCHRG_B200_FACTOR_GROUP"))) : 13;
+   for (int chi = NCLASS; chi >= 1; chi -= group) {  // perm holds the classes in descending order
+      const int clo = std::max(1, chi - group + 1);
+      int count = 0;
+      for (int c = clo; c <= chi; ++c) count += cls_count[c];
+      if (count == 0) continue;
+      Args b = a;
+      b.np = NPA_MAX;
+      b.perm = dperm + cls_start[chi];
+      launch_factor_ll<LL_NT>(ctx, b, count, std::min(NPA_MAX, KB * (chi + 1)));
+   }
 }
 
 __host__ inline size_t smem_doubles_pair(int npv) { return (size_t)NVEC * npv + 8 + AUX_DOUBLES; }
@@ -1023,6 +1083,7 @@ static int64_t plan_scratch(const std::vector<int64_t>& hoff, int32_t m0, int32_
 //   pair phase A on `sa`  ->  factorisation on the high-priority stream  ->  pair phase C on `sc`
 // `ready` (may be null) gates phase A (inputs staged); returns the event that marks the chunk's outputs complete.
 static cudaEvent_t run_chunk_split(mchrg_b200_context* ctx, const Args& a, const int32_t* dperm, int count,
+                                   const std::vector<size_t>& cls_start, const std::vector<int>& cls_count,
                                    cudaEvent_t ready, cudaStream_t sa, cudaStream_t sc) {
    if (ready) MCHRG_CUDA(cudaStreamWaitEvent(sa, ready, 0));
    {
@@ -1032,12 +1093,9 @@ static cudaEvent_t run_chunk_split(mchrg_b200_context* ctx, const Args& a, const
    cudaEvent_t eA = ctx->next_event();
    MCHRG_CUDA(cudaEventRecord(eA, sa));
    MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_hi, eA, 0));
-   {  // one launch for all sizes of the chunk (largest first)
-      Args b = a;
-      b.np = NPA_MAX;
-      b.perm = dperm;
+   {
       StreamScope on(ctx, ctx->stream_hi);
-      launch_factor_ll<128>(ctx, b, count);
+      launch_factor_groups(ctx, a, dperm, cls_start, cls_count);
    }
    cudaEvent_t eB = ctx->next_event();
    MCHRG_CUDA(cudaEventRecord(eB, ctx->stream_hi));
@@ -1154,10 +1212,7 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
             for (int c = 0; c < nchunk; ++c) batch::launch_pairs<1>(ctx, b, dperm + chunk_off[c], (int)(chunk_off[c + 1] - chunk_off[c]));
             MCHRG_CUDA(cudaEventRecord(t[1], ctx->stream));
             for (int c = 0; c < nchunk; ++c) {
-               batch::Args bb = b;
-               bb.np = batch::NPA_MAX;
-               bb.perm = dperm + chunk_off[c];
-               batch::launch_factor_ll<128>(ctx, bb, (int)(chunk_off[c + 1] - chunk_off[c]));
+               batch::launch_factor_groups(ctx, b, dperm + chunk_off[c], starts[c], counts[c]);
             }
             MCHRG_CUDA(cudaEventRecord(t[2], ctx->stream));
             for (int c = 0; c < nchunk; ++c) batch::launch_pairs<3>(ctx, b, dperm + chunk_off[c], (int)(chunk_off[c + 1] - chunk_off[c]));
@@ -1173,8 +1228,8 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
          for (int c = 0; c < nchunk; ++c) {
             const int cnt = (int)(chunk_off[c + 1] - chunk_off[c]);
             if (cnt == 0) continue;
-            last = batch::run_chunk_split(ctx, a, dperm + chunk_off[c], cnt, c == 0 ? staged : nullptr, ctx->stream_aux,
-                                          ctx->stream);
+            last = batch::run_chunk_split(ctx, a, dperm + chunk_off[c], cnt, starts[c], counts[c], c == 0 ? staged : nullptr,
+                                          ctx->stream_aux, ctx->stream);
          }
          (void)last;  // phase C runs on the main stream, which finish() synchronises
          MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1263,7 +1318,7 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
             a.ntot = (int64_t)na;
             cudaEvent_t ev_in2 = ctx->next_event();
             MCHRG_CUDA(cudaEventRecord(ev_in2, in));
-            ev_done = batch::run_chunk_split(ctx, a, d_perm, mc, ev_in2, ctx->stream_aux, ctx->stream);
+            ev_done = batch::run_chunk_split(ctx, a, d_perm, mc, cls_start, cls_count, ev_in2, ctx->stream_aux, ctx->stream);
          } else {
             batch::launch_chunk<0>(ctx, a, d_perm, cls_start, cls_count, ctx->stream, ctx->stream_aux);
             cudaEvent_t aux_done = ctx->next_event();

@@ -79,32 +79,64 @@ __device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cb
    return bad;
 }
 
-__global__ void k(const double* A, long long* cyc, int iters, double* sink) {
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// MODE 0: all warps run the diagonal routine.  MODE 1: warp 0 runs it, the other warps issue DMMA streams.
+// MODE 2: warp 0 runs it, the other warps stream global loads (L2 hits).
+template <int MODE>
+__global__ void k(const double* A, long long* cyc, int iters, double* sink, const double* big, size_t nbig) {
    __shared__ double T[4][KB * TS], Li[4][KB * KB], cb[4][40], rb[4][32], dv[4][16];
+   __shared__ volatile int done;
    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+   if (threadIdx.x == 0) done = 0;
+   __syncthreads();
    long long t = 0;
    int bad = 0;
-   for (int it = 0; it < iters; ++it) {
-      for (int i = lane; i < KB * TS; i += 32) T[w][i] = A[i];
-      __syncwarp();
-      const long long t0 = clock64();
-      bad += diag_factor_inv(T[w], Li[w], cb[w], rb[w], dv[w], lane, 16, false);
-      __syncwarp();
-      t += clock64() - t0;
+   if (MODE == 0 || w == 0) {
+      for (int it = 0; it < iters; ++it) {
+         for (int i = lane; i < KB * TS; i += 32) T[w][i] = A[i];
+         __syncwarp();
+         const long long t0 = clock64();
+         bad += diag_factor_inv(T[w], Li[w], cb[w], rb[w], dv[w], lane, 16, false);
+         __syncwarp();
+         t += clock64() - t0;
+      }
+      if (lane == 0) { cyc[blockIdx.x * 4 + w] = t / iters; sink[blockIdx.x * 4 + w] = Li[w][5] + bad; }
+      if (MODE != 0 && lane == 0) done = 1;
+   } else if (MODE == 1) {
+      double d0 = 0, d1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0, g0 = 0, g1 = 0;
+      const double a = 1.0 + lane * 1e-9, b = 1.0 - lane * 1e-9;
+      while (!done) {
+#pragma unroll
+         for (int i = 0; i < 8; ++i) { dmma884(d0, d1, a, b); dmma884(e0, e1, a, b); dmma884(f0, f1, b, a); dmma884(g0, g1, b, b); }
+      }
+      sink[1024 + threadIdx.x] = d0 + d1 + e0 + e1 + f0 + f1 + g0 + g1;
+   } else {
+      double s = 0;
+      size_t idx = ((size_t)blockIdx.x * 128 + threadIdx.x) * 2;
+      while (!done) {
+#pragma unroll
+         for (int i = 0; i < 8; ++i) { s += big[(idx + (size_t)i * 65536) % nbig]; }
+         idx = (idx + 8 * 65536) % nbig;
+      }
+      sink[1024 + threadIdx.x] = s;
    }
-   if (lane == 0) { cyc[blockIdx.x * 4 + w] = t / iters; sink[blockIdx.x * 4 + w] = Li[w][5] + bad; }
 }
 int main() {
    double hA[KB * TS];
    for (int r = 0; r < KB; ++r) for (int c = 0; c < TS; ++c) hA[r * TS + c] = (r == c) ? 4.0 : 0.1 / (1 + r + c);
-   double *dA, *sink; long long* cyc;
+   double *dA, *sink, *big; long long* cyc;
+   const size_t nbig = 8u << 20;  // 64 MB: L2 resident
    cudaMalloc(&dA, sizeof(hA)); cudaMemcpy(dA, hA, sizeof(hA), cudaMemcpyHostToDevice);
-   cudaMalloc(&cyc, 8 * 148 * 8 * 4); cudaMalloc(&sink, 8 * 148 * 8 * 4);
-   for (int nb : {1, 148, 148 * 6}) for (int nt : {32, 128}) {
-      k<<<nb, nt>>>(dA, cyc, 200, sink);
+   cudaMalloc(&cyc, 8 * 148 * 8 * 4); cudaMalloc(&sink, 8 * 4096); cudaMalloc(&big, nbig * 8); cudaMemset(big, 0, nbig * 8);
+   for (int mode = 0; mode < 3; ++mode) for (int nb : {148, 148 * 6}) {
+      if (mode == 0) k<0><<<nb, 128>>>(dA, cyc, 100, sink, big, nbig);
+      if (mode == 1) k<1><<<nb, 128>>>(dA, cyc, 100, sink, big, nbig);
+      if (mode == 2) k<2><<<nb, 128>>>(dA, cyc, 100, sink, big, nbig);
       cudaDeviceSynchronize();
       long long h[4]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
-      printf("blocks %d threads %d: cycles per call (warp 0) %lld  err %s\n", nb, nt, h[0], cudaGetErrorString(cudaGetLastError()));
+      printf("mode %d blocks %d: cycles per call (warp 0) %lld  err %s\n", mode, nb, h[0], cudaGetErrorString(cudaGetLastError()));
    }
    return 0;
 }
