@@ -250,7 +250,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    //      r = (1 + 6 / kcn) rc, so only the few bonded pairs need its erf: they are deferred into the warp's
    //      ring and evaluated 32 at a time with all lanes busy.  Counts are summed in 2^-56 fixed point with
    //      integer shared-memory atomics: associative, so the result does not depend on the arrival order.
-   const int ntri = tri(np);
    const double near = 1.0 + 6.0 / p.kcn;
    const double near2 = near * near;
    constexpr double FIX = 72057594037927936.0;  // 2^56
@@ -270,36 +269,39 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       atomicAdd(&cnfix[i], f);
       atomicAdd(&cnfix[j], f);
    };
-   for (int base = warp * 32; base < ntri; base += NT) {
-      const int e = base + lane;
-      bool hit = false;
-      int i = 0, j = 0;
-      if (e < ntri) {
-         tri_decode(e, i, j);
-         double v;
-         if (i == j) {
-            v = dself[i];
-         } else if (i < n) {
+   // diagonal and padding rows
+   for (int i = tid; i < n; i += NT) A[MAT_IN_SMEM ? tri(i) + i : lay(i, i)] = dself[i];
+   for (int i = n + warp; i < np; i += NW)
+      for (int j = lane; j <= i; j += 32) A[MAT_IN_SMEM ? tri(i) + j : lay(i, j)] = (i == j) ? 1.0 : 0.0;
+   // off-diagonal entries by rows, one warp per PAIR of rows (n-1-k, k): n-1 entries together, so every warp
+   // gets the same amount of work and the lanes stay busy; no index decoding, the row data are warp-uniform
+   for (int k = warp; 2 * k < n; k += NW) {
+      const int ia = n - 1 - k, ib = k;
+      const int len = (ia == ib) ? ia : ia + ib;
+      for (int t0 = 0; t0 < len; t0 += 32) {
+         const int tt = t0 + lane;
+         bool hit = false;
+         const int i = (tt < ia) ? ia : ib;
+         const int j = (tt < ia) ? tt : tt - ia;
+         if (tt < len) {
             const double dx = X[j] - X[i], dy = Y[j] - Y[i], dz = Z[j] - Z[i];
             const double r2 = dx * dx + dy * dy + dz * dz;
             const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
             double g;
-            v = eg::erf_gauss<5, false>(etab, r2 * rinv * gam, g) * rinv;  // erf(gamma r) / r
+            const double v = eg::erf_gauss<5, false>(etab, r2 * rinv * gam, g) * rinv;  // erf(gamma r) / r
             const double rc = rcov[i] + rcov[j];
             hit = r2 < near2 * rc * rc && !(r2 > p.cutoff2 || r2 < 1.0e-12);
-         } else {
-            v = 0.0;
+            A[MAT_IN_SMEM ? tri(i) + j : lay(i, j)] = v;
          }
-         A[MAT_IN_SMEM ? e : lay(i, j)] = v;
-      }
-      const unsigned m = __ballot_sync(FULL, hit);
-      if (hit) ring[(wr + __popc(m & lt_mask)) & (AUX_RING - 1)] = (i << 16) | j;
-      wr += __popc(m);
-      if (wr - rdp >= 32) {
-         __syncwarp();
-         count_pairs(rdp + lane);
-         rdp += 32;
-         __syncwarp();
+         const unsigned m = __ballot_sync(FULL, hit);
+         if (hit) ring[(wr + __popc(m & lt_mask)) & (AUX_RING - 1)] = (i << 16) | j;
+         wr += __popc(m);
+         if (wr - rdp >= 32) {
+            __syncwarp();
+            count_pairs(rdp + lane);
+            rdp += 32;
+            __syncwarp();
+         }
       }
    }
    __syncwarp();
@@ -329,6 +331,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       return;
    }
    if (PH == 3) {
+      if (p.status[mol] != 0) return;  // not positive definite: the factorisation kernel left NaNs
       for (int i = tid; i < n; i += NT) { xv[i] = xv_g[i]; th[i] = th_g[i]; fcut[i] = fc_g[i]; qv[i] = p.qvec[off + i]; }
       if (tid == 0) scal[0] = p.lamg[mol];
       __syncthreads();
@@ -509,31 +512,40 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    // ---- gradient (type.F90:275-278): g_i = sum_j f_ij (r_i - r_j) with the symmetric pair scalar
    //        f_ij = dtmp_ij q_i q_j - dcount_ij / r_ij (w_i + w_j),   w = thalf * q * fcut
    //      (q_i atrace_i minus the dcndr contraction; eeq.f90:403-411, mctc_ncoord); one evaluation per
-   //      unique pair, parked in the matrix storage, then summed per row ----
+   //      unique pair.  Rows are paired as in phase A.  The share of the ROW atom accumulates in registers;
+   //      f is parked in the matrix storage (packed, row-major) and the shares of the COLUMN atoms are
+   //      collected afterwards with coalesced reads ----
+   double* G = th;  // [3][npv] row shares: th, b0, b1 are free now
    {
       const double near = 1.0 + eg::XMAX / p.kcn;  // exp(-a^2) < 5e-19 beyond
       const double near2 = near * near;
-      int wr = 0, rdp = 0;
-      auto dcount_pairs = [&](int slot) {  // coordination-number part of f for a deferred (bonded) pair
-         const int ij = ring[slot & (AUX_RING - 1)];
-         const int i = ij >> 16, j = ij & 0xffff;
-         const double vx = X[i] - X[j], vy = Y[i] - Y[j], vz = Z[i] - Z[j];
-         const double r2 = vx * vx + vy * vy + vz * vz;
-         const double rinv = rsqrt(r2);
-         const double rci = 1.0 / (rcov[i] + rcov[j]);
-         const double a = p.kcn * (r2 * rinv * rci - 1.0);
-         double g;
-         eg::erf_gauss<6, true>(etab, fabs(a), g);
-         A[tri(i) + j] += p.kcn / SQRTPI * rci * g * rinv * (wf[i] + wf[j]);
-      };
-      for (int base = warp * 32; base < ntri_n; base += NT) {
-         const int e = base + lane;
-         bool hit = false;
-         int i = 0, j = 0;
-         if (e < ntri_n) {
-            tri_decode(e, i, j);
-            double f = 0.0;
-            if (i != j) {
+      for (int k = warp; 2 * k < n; k += NW) {
+         const int ia = n - 1 - k, ib = k;
+         const int len = (ia == ib) ? ia : ia + ib;
+         double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;  // shares of the rows ia / ib
+         int wr = 0, rdp = 0;
+         auto dcount_pairs = [&](int slot) {  // coordination-number part of f for a deferred (bonded) pair
+            const int ij = ring[slot & (AUX_RING - 1)];
+            const int i = ij >> 16, j = ij & 0xffff;
+            const double vx = X[i] - X[j], vy = Y[i] - Y[j], vz = Z[i] - Z[j];
+            const double r2 = vx * vx + vy * vy + vz * vz;
+            const double rinv = rsqrt(r2);
+            const double rci = 1.0 / (rcov[i] + rcov[j]);
+            const double a = p.kcn * (r2 * rinv * rci - 1.0);
+            double g;
+            eg::erf_gauss<6, true>(etab, fabs(a), g);
+            const double f = p.kcn / SQRTPI * rci * g * rinv * (wf[i] + wf[j]);
+            A[tri(i) + j] += f;
+            if (i == ia) { ax = fma(f, vx, ax); ay = fma(f, vy, ay); az = fma(f, vz, az); }
+            else { bx = fma(f, vx, bx); by = fma(f, vy, by); bz = fma(f, vz, bz); }
+         };
+         for (int t0 = 0; t0 < len; t0 += 32) {
+            const int tt = t0 + lane;
+            bool hit = false;
+            const bool first = tt < ia;
+            const int i = first ? ia : ib;
+            const int j = first ? tt : tt - ia;
+            if (tt < len) {
                const double vx = X[i] - X[j], vy = Y[i] - Y[j], vz = Z[i] - Z[j];
                const double r2 = vx * vx + vy * vy + vz * vz;
                const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
@@ -541,54 +553,48 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
                double g;
                const double ex = eg::erf_gauss<6, true>(etab, r2 * rinv * gam, g);
                const double dt = 2.0 / SQRTPI * gam * g - ex * rinv;
-               f = rinv * rinv * dt * qv[i] * qv[j];
+               const double f = rinv * rinv * dt * qv[i] * qv[j];
+               A[tri(i) + j] = f;
+               if (first) { ax = fma(f, vx, ax); ay = fma(f, vy, ay); az = fma(f, vz, az); }
+               else { bx = fma(f, vx, bx); by = fma(f, vy, by); bz = fma(f, vz, bz); }
                const double rc = rcov[i] + rcov[j];
                hit = r2 < near2 * rc * rc && r2 <= p.cutoff2 && r2 >= 1.0e-12;
             }
-            A[e] = f;
+            const unsigned m = __ballot_sync(FULL, hit);
+            if (hit) ring[(wr + __popc(m & lt_mask)) & (AUX_RING - 1)] = (i << 16) | j;
+            wr += __popc(m);
+            if (wr - rdp >= 32) {
+               __syncwarp();
+               dcount_pairs(rdp + lane);
+               rdp += 32;
+               __syncwarp();
+            }
          }
-         const unsigned m = __ballot_sync(FULL, hit);
-         if (hit) ring[(wr + __popc(m & lt_mask)) & (AUX_RING - 1)] = (i << 16) | j;
-         wr += __popc(m);
-         if (wr - rdp >= 32) {
-            __syncwarp();
-            dcount_pairs(rdp + lane);
-            rdp += 32;
-            __syncwarp();
+         __syncwarp();
+         if (lane < wr - rdp) dcount_pairs(rdp + lane);  // the rest of this pair of rows
+         __syncwarp();
+         ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+         bx = warp_sum(bx); by = warp_sum(by); bz = warp_sum(bz);
+         if (lane == 0) {
+            G[ia] = ax; G[npv + ia] = ay; G[2 * npv + ia] = az;
+            if (ia != ib) { G[ib] = bx; G[npv + ib] = by; G[2 * npv + ib] = bz; }
          }
       }
-      __syncwarp();
-      if (lane < wr - rdp) dcount_pairs(rdp + lane);
    }
    __syncthreads();
-   // Row sums of the parked pair scalars, both halves with coalesced reads of the packed triangle:
-   //   j < i: one warp per row i, lanes over j (contiguous);
-   //   j > i: lanes over 32 consecutive atoms i (contiguous for fixed j), the warps share the j range and
-   //          their partial sums are combined through shared memory.
-   double* G = b0;           // [3][npv] (b0, b1, qv are free now; qv is re-read below before it is overwritten)
+   // shares of the column atoms: -sum_{i > j} f_ij (r_i - r_j); lanes over 32 consecutive atoms j (contiguous
+   // reads for a fixed row i), the warps share the rows and combine their partial sums through shared memory
    double* part = aux;       // [NW][3][32] partial sums (the node table is no longer needed)
-   for (int i = warp; i < n; i += NW) {
-      const double xi = X[i], yi = Y[i], zi = Z[i];
-      double gx = 0.0, gy = 0.0, gz = 0.0;
-      const double* row = A + tri(i);
-      for (int j = lane; j < i; j += 32) {
-         const double f = row[j];
-         gx = fma(f, xi - X[j], gx); gy = fma(f, yi - Y[j], gy); gz = fma(f, zi - Z[j], gz);
-      }
-      gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
-      if (lane == 0) { G[i] = gx; G[npv + i] = gy; G[2 * npv + i] = gz; }
-   }
-   __syncthreads();
-   for (int i0 = 0; i0 < n; i0 += 32) {
-      const int i = i0 + lane;
-      const int ic = min(i, n - 1);
-      const double xi = X[ic], yi = Y[ic], zi = Z[ic];
+   for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      const int jc = min(j, n - 1);
+      const double xj = X[jc], yj = Y[jc], zj = Z[jc];
       double gx = 0.0, gy = 0.0, gz = 0.0;
 #pragma unroll 4
-      for (int j = i0 + 1 + warp; j < n; j += NW) {
-         if (i < j) {
-            const double f = A[tri(j) + i];
-            gx = fma(f, xi - X[j], gx); gy = fma(f, yi - Y[j], gy); gz = fma(f, zi - Z[j], gz);
+      for (int i = j0 + 1 + warp; i < n; i += NW) {
+         if (j < i) {
+            const double f = A[tri(i) + j];
+            gx = fma(f, xj - X[i], gx); gy = fma(f, yj - Y[i], gy); gz = fma(f, zj - Z[i], gz);
          }
       }
       part[(warp * 3 + 0) * 32 + lane] = gx;
@@ -600,7 +606,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          double acc = 0.0;
 #pragma unroll
          for (int w = 0; w < NW; ++w) acc += part[(w * 3 + c) * 32 + lane];
-         if (i < n) p.gradient[3 * (off + i) + c] = G[c * npv + i] + acc;
+         if (j < n) p.gradient[3 * (off + j) + c] = G[c * npv + j] + acc;
       }
       __syncthreads();
    }

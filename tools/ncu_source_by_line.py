@@ -46,7 +46,7 @@ def main():
                 cur["hdr"] = row
             elif row and cur is not None:
                 cur["rows"].append(row)
-    ktag = kernel.replace("Li", "(int)").rstrip("E")
+    ktag = os.environ.get("NCU_KERNEL_NAME") or kernel.replace("Li", "(int)").rstrip("E")
     blk = [b for b in blocks if ktag in b["name"]][which]
     hdr = blk["hdr"]
     ia, isamp, iinst = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
