@@ -1,17 +1,18 @@
-// Batches of independent non-periodic molecules (BASELINE.json configs[0..1]): ONE CTA PER MOLECULE,
-// the whole EEQ2019 single point (coordination number -> Coulomb block -> Cholesky + Schur
-// complement -> energy / gradient) inside one launch with the matrix resident in shared memory.
+// Batches of independent non-periodic molecules (BASELINE.json configs[0..1]): ONE CTA PER MOLECULE.
 //
-//   shared memory: packed lower triangle of J (row-major, order padded to a multiple of 16),
-//                  a 16 x (NP+4) k-major panel buffer, the 16x16 diagonal block, 13 per-atom vectors
-//   factorisation: right-looking blocked Cholesky, block 16: diagonal block in one warp (register
-//                  rows + shuffles), panel rows one thread each, trailing update on FP64 tensor
-//                  cores (mma.sync m8n8k4 DMMA, 16x16 tiles per warp, operands from the panel buffer)
 //   reference path replaced: app/main.f90:114-118 / charge.f90:37-77 per molecule, i.e.
 //                  mctc_ncoord (erf CN, log-cut), eeq.f90 get_xvec / get_amat_0d / get_damat_0d,
-//                  type.F90 solve (sytrf/sytrs -> Cholesky + Schur), energy and gradient.
-// Molecules are grouped by padded order NP (one launch per class) so shared memory, and with it the
-// number of resident CTAs per SM, matches the molecule size.
+//                  type.F90 solve (sytrf/sytrs -> Cholesky + Schur complement), energy and gradient.
+//
+//   fused path  (small batches)   eeq_batch_kernel<NT, 0>: the whole single point in one launch with the
+//                  packed matrix in shared memory (right-looking blocked Cholesky, block 16, trailing
+//                  update on FP64 tensor cores); one launch per size class of 16.
+//   split path  (>= 4096 molecules) three kernels per chunk of molecules on three streams:
+//                  eeq_batch_kernel<256, 1>  pair phase A: CN, xvec, Coulomb block -> global scratch
+//                  eeq_factor_ll_kernel      left-looking Cholesky of the augmented matrix in the scratch
+//                                            (L2 resident), forward/backward substitution, Schur complement
+//                  eeq_batch_kernel<256, 3>  pair phase C: energy, gradient
+//                  The scratch matrices are stored in FP64-mma fragment order (lay()).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -198,7 +199,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    const int np = MAT_IN_SMEM ? p.np : aug_order(n);  // split path: augmented order (see eeq_factor_ll_kernel)
    const int npv = p.np;  // stride of the per-atom vectors in shared memory
    const int ldp = np + 4;
-   double* A = MAT_IN_SMEM ? sm : p.scratch + p.soff[mol];  // packed lower, row-major: A[tri(i) + j], j <= i
+   // fused: packed lower, row-major A[tri(i) + j]; split: phase A writes A[lay(i, j)], phase C parks at A[tri(i) + j]
+   double* A = MAT_IN_SMEM ? sm : p.scratch + p.soff[mol];
    double* P = sm + (MAT_IN_SMEM ? (size_t)np * (np + 1) / 2 : 0);  // panel, k-major: P[c * ldp + i]
    double* Ld = P + (MAT_IN_SMEM ? (size_t)KB * ldp : 0);            // diagonal block Ld[r * 17 + c]
    double* spare = Ld + (MAT_IN_SMEM ? KB * (KB + 1) : 0);           // KB doubles, unused
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          if (tt < len) {
             const double dx = X[j] - X[i], dy = Y[j] - Y[i], dz = Z[j] - Z[i];
             const double r2 = dx * dx + dy * dy + dz * dz;
-            const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
+            const double rinv = eg::fast_rsqrt(r2), gam = eg::fast_rsqrt(rad2[i] + rad2[j]);
             double g;
             const double v = eg::erf_gauss<5, false>(etab, r2 * rinv * gam, g) * rinv;  // erf(gamma r) / r
             const double rc = rcov[i] + rcov[j];
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
             if (tt < len) {
                const double vx = X[i] - X[j], vy = Y[i] - Y[j], vz = Z[i] - Z[j];
                const double r2 = vx * vx + vy * vy + vz * vz;
-               const double rinv = rsqrt(r2), gam = rsqrt(rad2[i] + rad2[j]);
+               const double rinv = eg::fast_rsqrt(r2), gam = eg::fast_rsqrt(rad2[i] + rad2[j]);
                // dtmp = 2 gamma exp(-x^2) / (sqrt(pi) r^2) - erf(x) / r^3,  x = gamma r
                double g;
                const double ex = eg::erf_gauss<6, true>(etab, r2 * rinv * gam, g);
@@ -625,6 +627,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
 //        column / row broadcasts through shared memory); the INVERSE replaces the diagonal block in global
 //        memory (later block columns never read the diagonal blocks of L)
 //     S  rows below: L(i, blk) = Cb(i, :) inv(L_kk)^T                     DMMA, operands from shared memory
+//   The next diagonal tile is updated one block column ahead (job 0 -> T2, completed by the warp that solves
+//   the first row tile), so D(k0) runs while the other warps work on the row tiles; the D warp rotates over
+//   the four SM sub-partitions (measured: tools/micro/diag_latency.cu).
 //   backward substitution, right-looking: y_blk = inv(L_kk)^T w_blk, then w(:k0) -= L(blk, :k0)^T y_blk with
 //   coalesced row reads.  ~32 KB of shared memory per CTA, so 6-7 molecules are resident per SM and hide
 //   each other's latencies.
@@ -736,7 +741,7 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
    const int n = (int)(p.offsets[mol + 1] - off);
    const int npa = aug_order(n);
    const double charge = p.charge[mol];
-   double* S = p.scratch + p.soff[mol];  // packed lower, row-major
+   double* S = p.scratch + p.soff[mol];  // fragment-order blocks, S[lay(i, j)]
    double* Cb = sm;                      // rows below the diagonal tile: Cb[swz(i - k0 - 16, c)]
    double* T = Cb + (size_t)(npa > KB ? npa - KB : 2) * KB;
    double* Li = T + KB * TS;
