@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    constexpr bool MAT_IN_SMEM = (PH == 0 || PH == 2);
    // pair phases work on the molecule's own padded order, the class launches on the class order
    const int np = MAT_IN_SMEM ? p.np : aug_order(n);  // split path: augmented order (see eeq_factor_ll_kernel)
-   const int npv = p.np;  // stride of the per-atom vectors in shared memory
+   const int npv = MAT_IN_SMEM ? p.np : NPA_MAX;  // stride of the per-atom vectors (compile-time in the split path)
    const int ldp = np + 4;
    // fused: packed lower, row-major A[tri(i) + j]; split: phase A writes A[lay(i, j)], phase C parks at A[tri(i) + j]
    double* A = MAT_IN_SMEM ? sm : p.scratch + p.soff[mol];
@@ -277,14 +277,19 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       for (int j = lane; j <= i; j += 32) A[MAT_IN_SMEM ? tri(i) + j : lay(i, j)] = (i == j) ? 1.0 : 0.0;
    // off-diagonal entries by rows, one warp per PAIR of rows (n-1-k, k): n-1 entries together, so every warp
    // gets the same amount of work and the lanes stay busy; no index decoding, the row data are warp-uniform
+   auto col_off = [](int j) { return 64 * (j >> 3) + ((j & 3) << 1) + ((j >> 2) & 1); };  // lay() = row part + this
    for (int k = warp; 2 * k < n; k += NW) {
       const int ia = n - 1 - k, ib = k;
       const int len = (ia == ib) ? ia : ia + ib;
+      // storage index of (i, j): both column walks advance by 32 columns = 256 doubles per step
+      const int offA = MAT_IN_SMEM ? tri(ia) + lane : lay(ia, 0) + col_off(lane);
+      const int offB = MAT_IN_SMEM ? tri(ib) + lane - ia : lay(ib, 0) + col_off(lane - ia);
       for (int t0 = 0; t0 < len; t0 += 32) {
          const int tt = t0 + lane;
          bool hit = false;
          const int i = (tt < ia) ? ia : ib;
          const int j = (tt < ia) ? tt : tt - ia;
+         const int idx = ((tt < ia) ? offA : offB) + (MAT_IN_SMEM ? t0 : 8 * t0);
          if (tt < len) {
             const double dx = X[j] - X[i], dy = Y[j] - Y[i], dz = Z[j] - Z[i];
             const double r2 = dx * dx + dy * dy + dz * dz;
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
             const double v = eg::erf_gauss<5, false>(etab, r2 * rinv * gam, g) * rinv;  // erf(gamma r) / r
             const double rc = rcov[i] + rcov[j];
             hit = r2 < near2 * rc * rc && !(r2 > p.cutoff2 || r2 < 1.0e-12);
-            A[MAT_IN_SMEM ? tri(i) + j : lay(i, j)] = v;
+            A[idx] = v;
          }
          const unsigned m = __ballot_sync(FULL, hit);
          if (hit) ring[(wr + __popc(m & lt_mask)) & (AUX_RING - 1)] = (i << 16) | j;
