@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    double* aux = (MAT_IN_SMEM && aux_in_panel(np)) ? P : scal + 8;
    double2* etab = reinterpret_cast<double2*>(aux);                 // erf / gauss nodes
    int* ring = reinterpret_cast<int*>(aux + 2 * eg::NTAB + 2) + warp * AUX_RING;  // this warp's deferred pairs
-   unsigned long long* cnfix = reinterpret_cast<unsigned long long*>(b0);  // fixed-point CN sums (phase A)
+   unsigned* cnfix = reinterpret_cast<unsigned*>(b0);  // fixed-point CN sums, three 20-bit limbs [3][npv] (b0, b1; phase A)
    __shared__ int sfail;
    double* xv_g = p.vecg + off;
    double* th_g = p.vecg + p.ntot + off;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          X[i] = Y[i] = Z[i] = 0.0;
          rad2[i] = 1.0; dself[i] = 1.0; rcov[i] = 0.0; xv[i] = 0.0; th[i] = 0.0;
       }
-      if (PH == 0 || PH == 1) cnfix[i] = 0ull;
+      if (PH == 0 || PH == 1) cnfix[i] = cnfix[npv + i] = cnfix[2 * npv + i] = 0u;
    }
    if (PH != 2) eg::load_table(etab, p.etab, tid, NT);
    __syncthreads();
@@ -250,11 +250,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    // ---- one pass over the unique pairs: Coulomb block J, packed lower (eeq.f90:199-242; padding = identity),
    //      and the erf coordination number (mctc_ncoord).  The counting function is exactly zero beyond
    //      r = (1 + 6 / kcn) rc, so only the few bonded pairs need its erf: they are deferred into the warp's
-   //      ring and evaluated 32 at a time with all lanes busy.  Counts are summed in 2^-56 fixed point with
+   //      ring and evaluated 32 at a time with all lanes busy.  Counts are summed in 2^-52 fixed point with
    //      integer shared-memory atomics: associative, so the result does not depend on the arrival order.
    const double near = 1.0 + 6.0 / p.kcn;
    const double near2 = near * near;
-   constexpr double FIX = 72057594037927936.0;  // 2^56
+   constexpr double FIX = 4503599627370496.0;  // 2^52
    int wr = 0, rdp = 0;
    auto count_pairs = [&](int slot) {
       const int ij = ring[slot & (AUX_RING - 1)];
@@ -267,9 +267,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       double g;
       const double ea = eg::erf_gauss<6, false>(etab, fabs(a), g);
       const double c = 0.5 - copysign(0.5, a) * ea;
+      // (64-bit shared-memory atomics are compare-and-swap loops; 32-bit adds are native: each limb sums at
+      //  most 224 values < 2^20, so nothing carries)
       const unsigned long long f = (unsigned long long)__double2ll_rn(c * FIX);
-      atomicAdd(&cnfix[i], f);
-      atomicAdd(&cnfix[j], f);
+      const unsigned f0 = (unsigned)f & 0xfffffu, f1 = (unsigned)(f >> 20) & 0xfffffu, f2 = (unsigned)(f >> 40);
+      atomicAdd(&cnfix[i], f0); atomicAdd(&cnfix[npv + i], f1); atomicAdd(&cnfix[2 * npv + i], f2);
+      atomicAdd(&cnfix[j], f0); atomicAdd(&cnfix[npv + j], f1); atomicAdd(&cnfix[2 * npv + j], f2);
    };
    // diagonal and padding rows
    for (int i = tid; i < n; i += NT) A[MAT_IN_SMEM ? tri(i) + i : lay(i, i)] = dself[i];
@@ -316,7 +319,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    __syncthreads();
    const double ecut = exp(p.cut);
    for (int i = tid; i < n; i += NT) {
-      const double acc = (double)cnfix[i] * (1.0 / FIX);
+      const double acc = (double)((unsigned long long)cnfix[i] + ((unsigned long long)cnfix[npv + i] << 20) +
+                                  ((unsigned long long)cnfix[2 * npv + i] << 40)) * (1.0 / FIX);
       double cn = acc, f = 1.0;
       if (p.cut > 0.0) {
          f = ecut / (ecut + exp(acc));

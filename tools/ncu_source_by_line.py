@@ -67,7 +67,7 @@ def main():
         tot_s += s
         tot_i += n
     print(f"kernel {blk['name']}  samples={tot_s} warp-instructions={tot_i}")
-    for line, (s, n, st) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:400]:
+    for line, (s, n, st) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
         top = ", ".join(f"{k[6:]}={v}" for k, v in st.most_common(3))
         print(f"  {str(line):32s} samples {100 * s / tot_s:5.1f}%  inst {100 * n / max(tot_i, 1):5.1f}%   {top}")
 
