@@ -67,6 +67,24 @@ int mchrg_b200_version(void); /* 10000*major + 100*minor + patch */
 int mchrg_b200_synchronize(mchrg_b200_context* ctx);
 /* stream the context launches on (cudaStream_t as void*), for callers that time with events */
 void* mchrg_b200_stream(mchrg_b200_context* ctx);
+/* second stream of the context; panel exchanges (below) are ordered on it */
+void* mchrg_b200_side_stream(mchrg_b200_context* ctx);
+
+/* ---- multi-GPU factorisation of ONE large system ("one exchange per panel") -------------
+ * The reference factors the bordered matrix with one LAPACK call (dsytrf, model/type.F90:221,
+ * lapack.F90:165-201).  With an exchange installed, every rank of a replicated solve owns the block columns
+ * b % nranks == rank of the Cholesky factorisation (block-cyclic, 256 wide): the owner factors panel b,
+ * `start` broadcasts it (device pointer, bytes, root rank, slot id) and `wait` orders the context's main
+ * stream after the transfer of that slot; ranks update only the columns they own.  The callbacks are the
+ * caller's collective (torch.distributed / NCCL broadcast in multicharge_b200/api.py); the library itself
+ * links no communication library.  `start` must enqueue on mchrg_b200_side_stream, `wait` on
+ * mchrg_b200_stream.  All ranks must make the same sequence of library calls with the same inputs.
+ * nranks <= 1 or start == NULL removes the exchange. */
+typedef void (*mchrg_b200_exchange_start_fn)(void* user, void* dev_ptr, int64_t bytes, int32_t root, int32_t slot);
+typedef void (*mchrg_b200_exchange_wait_fn)(void* user, int32_t slot);
+int mchrg_b200_set_exchange(mchrg_b200_context* ctx, int32_t rank, int32_t nranks, mchrg_b200_exchange_start_fn start,
+                            mchrg_b200_exchange_wait_fn wait, void* user);
+
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 uint64_t mchrg_b200_launch_count(const mchrg_b200_context* ctx);
 

@@ -32,6 +32,8 @@ PROTOTYPES = {
     "mchrg_b200_synchronize": (C.c_int, [c_vp]),
     "mchrg_b200_stream": (c_vp, [c_vp]),
     "mchrg_b200_launch_count": (C.c_uint64, [c_vp]),
+    "mchrg_b200_side_stream": (c_vp, [c_vp]),
+    "mchrg_b200_set_exchange": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp, c_vp, c_vp]),
     "mchrg_b200_new_eeq_model": (C.c_int, [c_vp, C.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_double,
                                            C.c_double, C.POINTER(c_vp)]),
     "mchrg_b200_new_eeq2019_model": (C.c_int, [c_vp, C.c_int32, c_vp, C.POINTER(c_vp)]),
@@ -57,6 +59,9 @@ PROTOTYPES = {
                                    C.c_int64, C.c_double, c_vp, C.c_int64]),
     "mchrg_b200_dpotrs_right": (C.c_int, [c_vp, C.c_int64, C.c_int64, c_vp, C.c_int64, c_vp, C.c_int64]),
 }
+
+EXCHANGE_START_FN = C.CFUNCTYPE(None, c_vp, c_vp, C.c_int64, C.c_int32, C.c_int32)
+EXCHANGE_WAIT_FN = C.CFUNCTYPE(None, c_vp, C.c_int32)
 
 _lib = None
 

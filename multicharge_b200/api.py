@@ -88,6 +88,24 @@ class Context:
     def synchronize(self):
         check(_lib.load().mchrg_b200_synchronize(self._h))
 
+    @property
+    def side_stream(self):
+        return _lib.load().mchrg_b200_side_stream(self._h)
+
+    def set_exchange(self, exchange):
+        """Install (or, with None, remove) the panel exchange of the multi-GPU factorisation: `exchange` is a
+        PanelExchange (or any object with rank, world, start(ptr, nbytes, root, slot), wait(slot))."""
+        lib = _lib.load()
+        if exchange is None or exchange.world <= 1:
+            self._exchange = None
+            check(lib.mchrg_b200_set_exchange(self._h, 0, 1, None, None, None))
+            return
+        start = _lib.EXCHANGE_START_FN(lambda user, ptr, nbytes, root, slot: exchange.start(ptr, nbytes, root, slot))
+        wait = _lib.EXCHANGE_WAIT_FN(lambda user, slot: exchange.wait(slot))
+        self._exchange = (exchange, start, wait)  # keep the ctypes thunks alive
+        check(lib.mchrg_b200_set_exchange(self._h, exchange.rank, exchange.world, C.cast(start, C.c_void_p),
+                                          C.cast(wait, C.c_void_p), None))
+
     # dense building blocks (tests)
     def dpotrf(self, a):
         """In-place lower Cholesky of a column-major n x n matrix given as a[n,n] Fortran-ordered view."""
@@ -100,6 +118,59 @@ class Context:
 
     def dpotrs_right(self, m, n, l, ldl, x, ldx):
         return check(_lib.load().mchrg_b200_dpotrs_right(self._h, m, n, _ptr(l), ldl, _ptr(x), ldx))
+
+
+class _DeviceBytes:
+    """Zero-copy view of raw device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PanelExchange:
+    """The collective behind mchrg_b200_set_exchange: torch.distributed broadcasts of the factored panels.
+
+    `start` enqueues an asynchronous broadcast on the context's side stream (the library has ordered that stream
+    after the kernels that produced the panel), `wait` makes the context's main stream wait for it.  With the
+    NCCL backend the data moves GPU to GPU over NVLink; `as_tensor` is replaceable so that the bookkeeping can be
+    exercised with the gloo backend on host buffers (tests/test_exchange_gloo.py)."""
+
+    def __init__(self, ctx=None, group=None, as_tensor=None):
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.pending = {}
+        self.started = 0
+        self.bytes_moved = 0
+        if ctx is not None:
+            dev = torch.device("cuda", ctx.device)
+            self._main = torch.cuda.ExternalStream(ctx.stream, device=dev)
+            self._side = torch.cuda.ExternalStream(ctx.side_stream, device=dev)
+            self._as_tensor = as_tensor or (lambda ptr, n: torch.as_tensor(_DeviceBytes(ptr, n), device=dev))
+        else:  # host buffers (gloo): no streams
+            self._main = self._side = None
+            self._as_tensor = as_tensor
+
+    def _on(self, stream):
+        import contextlib
+        return self._torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
+    def start(self, ptr, nbytes, root, slot):
+        t = self._as_tensor(ptr, nbytes)
+        src = root if self.group is None else self._dist.get_global_rank(self.group, root)
+        with self._on(self._side):
+            work = self._dist.broadcast(t, src=src, group=self.group, async_op=True)
+        self.pending[slot] = (work, t)
+        self.started += 1
+        self.bytes_moved += int(nbytes)
+
+    def wait(self, slot):
+        work, _t = self.pending.pop(slot)
+        with self._on(self._main):
+            work.wait()
 
 
 _default_ctx = {}

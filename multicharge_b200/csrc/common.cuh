@@ -61,6 +61,14 @@ struct mchrg_b200_context {
    cudaEvent_t next_event();
    int sm_count = 148;
    double2* erf_tab = nullptr;        // (erf, exp(-x^2)) nodes of erfgauss.cuh, device memory
+   // panel exchange of the multi-GPU factorisation (mchrg_b200_set_exchange); nranks == 1: single GPU
+   struct Exchange {
+      int rank = 0, nranks = 1;
+      void (*start)(void*, void*, int64_t, int32_t, int32_t) = nullptr;
+      void (*wait)(void*, int32_t) = nullptr;
+      void* user = nullptr;
+      bool on() const { return nranks > 1 && start && wait; }
+   } xch;
    size_t smem_optin = 0;
    std::mutex mu;
    uint64_t launches = 0;

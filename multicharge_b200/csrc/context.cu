@@ -189,6 +189,27 @@ int mchrg_b200_synchronize(mchrg_b200_context* ctx) {
 }
 
 void* mchrg_b200_stream(mchrg_b200_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+void* mchrg_b200_side_stream(mchrg_b200_context* ctx) { return ctx ? (void*)ctx->stream_aux : nullptr; }
+
+int mchrg_b200_set_exchange(mchrg_b200_context* ctx, int32_t rank, int32_t nranks, mchrg_b200_exchange_start_fn start,
+                            mchrg_b200_exchange_wait_fn wait, void* user) {
+   if (!ctx) return MCHRG_B200_ERR_ARG;
+   std::lock_guard<std::mutex> lock(ctx->mu);
+   if (nranks <= 1 || !start || !wait) {
+      ctx->xch = mchrg_b200_context::Exchange();
+      return 0;
+   }
+   if (rank < 0 || rank >= nranks) {
+      mchrg::set_last_error("set_exchange: rank outside [0, nranks)");
+      return MCHRG_B200_ERR_ARG;
+   }
+   ctx->xch.rank = rank;
+   ctx->xch.nranks = nranks;
+   ctx->xch.start = start;
+   ctx->xch.wait = wait;
+   ctx->xch.user = user;
+   return 0;
+}
 
 uint64_t mchrg_b200_launch_count(const mchrg_b200_context* ctx) { return ctx ? ctx->launches : 0; }
 

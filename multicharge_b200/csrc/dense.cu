@@ -51,12 +51,25 @@ template <bool TRANSB>
 __global__ void __launch_bounds__(gemm::THREADS, 1)
 dgemm_dmma_kernel(int64_t kdim, double alpha, const double* __restrict__ A, int64_t lda,
                   const double* __restrict__ B, int64_t ldb, double beta, double* C, int64_t ldc,
-                  int lower_only) {
+                  int lower_only, int4 cyc) {
    using namespace gemm;
    extern __shared__ __align__(16) double smem[];
 
    int tm, tn;
-   if (lower_only) {  // linear index over the lower block triangle
+   if (lower_only == 2) {
+      // block-cyclic trailing update of the multi-GPU factorisation: the owned block columns are cyc.w tiles wide,
+      // start at tile column cyc.x and repeat every cyc.y tile columns; cyc.z = tile rows of the matrix.
+      // Lower tiles (tm >= tn) only, numbered column by column.
+      int b = blockIdx.x, t0 = cyc.x;
+      tm = tn = 0;
+      for (bool found = false; !found; t0 += cyc.y) {
+         for (int w = 0; w < cyc.w && t0 + w < cyc.z; ++w) {
+            const int cnt = cyc.z - t0 - w;  // lower tiles of tile column t0 + w
+            if (b < cnt) { tn = t0 + w; tm = tn + b; found = true; break; }
+            b -= cnt;
+         }
+      }
+   } else if (lower_only) {  // linear index over the lower block triangle
       const int b = blockIdx.x;
       int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
       while ((int64_t)(r + 1) * (r + 2) / 2 <= b) ++r;
@@ -190,12 +203,28 @@ void dgemm_padded(mchrg_b200_context* ctx, bool transb, int64_t m, int64_t n, in
    } else {
       grid = dim3((unsigned)(m / gemm::BM), (unsigned)(n / gemm::BN), 1);
    }
+   const int4 none = make_int4(0, 0, 0, 0);
    if (transb)
       MCHRG_LAUNCH(ctx, dgemm_dmma_kernel<true>, grid, gemm::THREADS, gemm::SMEM_BYTES, k, alpha, A, lda, B, ldb,
-                   beta, C, ldc, lower_only ? 1 : 0);
+                   beta, C, ldc, lower_only ? 1 : 0, none);
    else
       MCHRG_LAUNCH(ctx, dgemm_dmma_kernel<false>, grid, gemm::THREADS, gemm::SMEM_BYTES, k, alpha, A, lda, B, ldb,
-                   beta, C, ldc, lower_only ? 1 : 0);
+                   beta, C, ldc, lower_only ? 1 : 0, none);
+}
+
+// W(:, owned block columns) -= P P^T restricted to the lower tiles, P = W(:, c0 : c0 + k) (n x k panel, global
+// rows): one launch for all block columns (two tiles wide) starting at tile column t0 and repeating every
+// `stride` tile columns.  Multi-GPU factorisation only.
+static void dsyrk_cyclic(mchrg_b200_context* ctx, int64_t n, int64_t k, const double* P, double* W, int64_t ldw, int t0,
+                         int stride, int wt) {
+   const int T = (int)(n / gemm::BM);
+   int64_t tiles = 0;
+   for (int t = t0; t < T; t += stride)
+      for (int w = 0; w < wt && t + w < T; ++w) tiles += T - t - w;
+   if (tiles == 0) return;
+   gemm_setup_once();
+   MCHRG_LAUNCH(ctx, dgemm_dmma_kernel<true>, dim3((unsigned)tiles), gemm::THREADS, gemm::SMEM_BYTES, k, -1.0, P, ldw, P, ldw,
+                1.0, W, ldw, 2, make_int4(t0, stride, T, wt));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -402,10 +431,90 @@ static int64_t panel_width() {  // tuning knob (multiple of 128); default chosen
    return w;
 }
 
+// smallest nonzero entry of the ranks' pivot reports
+__global__ void info_combine_kernel(const int* __restrict__ xinfo, int nranks, int* __restrict__ info) {
+   int v = 0;
+   for (int r = 0; r < nranks; ++r)
+      if (xinfo[r] != 0 && (v == 0 || xinfo[r] < v)) v = xinfo[r];
+   *info = v;
+}
+
+// Multi-GPU right-looking Cholesky of a REPLICATED matrix: block columns of PANEL columns are
+// owned block-cyclically (owner(b) = b % nranks).  Every rank keeps only its own block columns up to date;
+// the owner factors panel b (diagonal block + triangular solve of the rows below) and broadcasts it together
+// with its inverted diagonal blocks, so that at the end EVERY rank holds the complete factor and the solves
+// that follow stay replicated.  The broadcast of panel b+1 is started as soon as its owner has factored it
+// (the owner updates that column first) and overlaps the trailing updates with panel b on all ranks.
+static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info) {
+   const auto& x = ctx->xch;
+   static const int64_t PANEL = std::getenv("MCHRG_B200_DIST_PANEL") ? std::max<int64_t>(TILE, atoll(std::getenv("MCHRG_B200_DIST_PANEL")) / TILE * TILE) : 2 * TILE;
+   const int nblk = (int)((n + PANEL - 1) / PANEL);
+   auto c0_of = [&](int b) { return (int64_t)b * PANEL; };
+   auto pw_of = [&](int b) { return std::min<int64_t>(PANEL, n - c0_of(b)); };
+   auto owner = [&](int b) { return b % x.nranks; };
+   auto factor_panel = [&](int b) {
+      const int64_t c0 = c0_of(b), pw = pw_of(b), rem = n - c0 - pw;
+      double* D = W + c0 + c0 * ldw;
+      double* dinv_k = dinv + (c0 / TILE) * TILE * TILE;
+      potrf_rec(ctx, pw, D, ldw, dinv_k, info, c0);
+      if (rem > 0) dtrsm_right_lt(ctx, rem, pw, D, ldw, dinv_k, D + pw, ldw);
+   };
+   auto start_panel = [&](int b) {
+      const int64_t c0 = c0_of(b), pw = pw_of(b);
+      cudaEvent_t e = ctx->next_event();  // the exchange runs on the side stream, after what is queued here
+      MCHRG_CUDA(cudaEventRecord(e, ctx->active));
+      MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_aux, e, 0));
+      // block column from its diagonal element to the end of its last column (one contiguous range)
+      x.start(x.user, W + c0 + c0 * ldw, (int64_t)(((pw - 1) * ldw + (n - c0)) * sizeof(double)), owner(b), 2 * b);
+      x.start(x.user, dinv + (c0 / TILE) * TILE * TILE, (int64_t)((pw / TILE) * TILE * TILE * sizeof(double)), owner(b),
+              2 * b + 1);
+   };
+   auto wait_panel = [&](int b) {
+      x.wait(x.user, 2 * b);
+      x.wait(x.user, 2 * b + 1);
+   };
+   auto update = [&](int b, int j) {  // block column j -= L(rows of j.., panel b) L(block j, panel b)^T
+      const int64_t c0 = c0_of(b), cj = c0_of(j);
+      const double* A21 = W + cj + c0 * ldw;
+      dgemm_padded(ctx, true, n - cj, pw_of(j), pw_of(b), -1.0, A21, ldw, A21, ldw, 1.0, W + cj + cj * ldw, ldw, false);
+   };
+   if (owner(0) == x.rank) factor_panel(0);
+   start_panel(0);
+   for (int b = 0; b < nblk; ++b) {
+      wait_panel(b);
+      if (b + 1 < nblk) {
+         if (owner(b + 1) == x.rank) {
+            update(b, b + 1);
+            factor_panel(b + 1);
+         }
+         start_panel(b + 1);
+      }
+      // all other owned block columns behind the look-ahead column in one launch
+      int j0 = b + 2;
+      while (j0 < nblk && owner(j0) != x.rank) ++j0;
+      if (j0 < nblk)
+         dsyrk_cyclic(ctx, n, pw_of(b), W + c0_of(b) * ldw, W, ldw, (int)(c0_of(j0) / TILE), (int)(x.nranks * PANEL / TILE),
+                      (int)(PANEL / TILE));
+   }
+   // every rank reports the same pivot failure
+   int* xinfo = ctx->alloc_zero<int>((size_t)x.nranks);
+   MCHRG_CUDA(cudaMemcpyAsync(xinfo + x.rank, info, sizeof(int), cudaMemcpyDeviceToDevice, ctx->active));
+   cudaEvent_t e = ctx->next_event();
+   MCHRG_CUDA(cudaEventRecord(e, ctx->active));
+   MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_aux, e, 0));
+   for (int r = 0; r < x.nranks; ++r) x.start(x.user, xinfo + r, (int64_t)sizeof(int), r, 2 * nblk + r);
+   for (int r = 0; r < x.nranks; ++r) x.wait(x.user, 2 * nblk + r);
+   MCHRG_LAUNCH(ctx, info_combine_kernel, 1, 1, 0, xinfo, x.nranks, info);
+}
+
 void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info) {
    if (n % TILE || (ldw & 1)) fail(MCHRG_B200_ERR_ARG, "dpotrf_padded: n=%lld not a multiple of 128", (long long)n);
    leaf_setup_once();
    const int64_t PANEL = panel_width();
+   if (ctx->xch.on() && n >= 8 * TILE && ctx->active == ctx->stream) {  // large replicated system on several GPUs
+      dpotrf_dist(ctx, n, W, ldw, dinv, info);
+      return;
+   }
    if (n <= 2 * PANEL) {  // small: plain recursion on the current stream
       potrf_rec(ctx, n, W, ldw, dinv, info, 0);
       return;

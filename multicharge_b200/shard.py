@@ -48,3 +48,48 @@ def scatter_results(nmol_total, offsets_total, idx, shard_offsets, shard_out, ou
                 out[key][d] = shard_out[key][s]
         out["status"][m] = shard_out["status"][k]
     return out
+
+
+def block_cyclic_cholesky_host(w, n, panel, exchange):
+    """Host (numpy) mirror of the multi-GPU factorisation schedule in csrc/dense.cu (dpotrf_dist): the matrix is
+    replicated, block column b is owned by rank b % world, the owner factors panel b and the exchange broadcasts
+    it; the broadcast of panel b+1 is started before the remaining trailing updates with panel b.  `w` is the flat
+    column-major n x n matrix (lower triangle referenced), factored in place on every rank.  The device code makes
+    exactly this sequence of exchange.start / exchange.wait calls (plus one more slot per panel for the inverted
+    diagonal blocks); tests/test_exchange_gloo.py runs it over gloo with two ranks."""
+    import numpy as np
+    rank, world = exchange.rank, exchange.world
+    a = w.reshape(n, n).T  # a[i, j] view of the column-major storage
+    nblk = (n + panel - 1) // panel
+    c0 = lambda b: b * panel  # noqa: E731
+    pw = lambda b: min(panel, n - c0(b))  # noqa: E731
+
+    def factor_panel(b):
+        s, e = c0(b), c0(b) + pw(b)
+        a[s:e, s:e] = np.linalg.cholesky(a[s:e, s:e])
+        if e < n:
+            a[e:, s:e] = np.linalg.solve(a[s:e, s:e], a[e:, s:e].T).T  # X L^T = B
+
+    def start_panel(b):
+        s = c0(b)
+        lo, hi = s + s * n, (s + pw(b) - 1) * n + n  # diagonal element .. end of the last column: contiguous
+        exchange.start(w[lo:hi], (hi - lo) * 8, b % world, b)
+
+    def update(b, j):
+        s, e, sj, ej = c0(b), c0(b) + pw(b), c0(j), c0(j) + pw(j)
+        a[sj:, sj:ej] -= a[sj:, s:e] @ a[sj:ej, s:e].T
+
+    if rank == 0 % world:
+        factor_panel(0)
+    start_panel(0)
+    for b in range(nblk):
+        exchange.wait(b)
+        if b + 1 < nblk:
+            if (b + 1) % world == rank:
+                update(b, b + 1)
+                factor_panel(b + 1)
+            start_panel(b + 1)
+        for j in range(b + 2, nblk):
+            if j % world == rank:
+                update(b, j)
+    return w
