@@ -432,7 +432,7 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// EEQ-BC (model/eeqbc.f90), non-periodic
+// EEQ-BC (model/eeqbc.f90); periodic structures: charge / energy path only
 // ---------------------------------------------------------------------------------------------
 static BcAtoms gather_eeqbc(const mchrg_b200_model* model, const DevMol& mol) {
    mchrg_b200_context* ctx = model->ctx;
@@ -481,8 +481,11 @@ __global__ void set_last_kernel(int nat, double v, double* __restrict__ x) { x[n
 
 static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, const SolveIO& io) {
    mchrg_b200_context* ctx = model->ctx;
-   if (mol.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC (get_amat_3d / get_cmat_3d, eeqbc.f90:532-632) is not built");
    if (!io.qloc) fail(MCHRG_B200_ERR_MODEL, "qloc required for eeqbc");  // error stop, eeqbc.f90:202
+   if (mol.periodic && (io.gradient || io.sigma || io.dqdr || io.dqdL))
+      fail(MCHRG_B200_ERR_MODEL,
+           "periodic EEQ-BC derivatives (get_damat_3d / get_dcmat_3d, eeqbc.f90:789-1013, 1243-1333) are not built: "
+           "charges and energy only");
    if (io.je >= 0 && (io.jb != 0 || io.je != mol.nat)) fail(MCHRG_B200_ERR_MODEL, "row blocks are not available for EEQ-BC");
    const int nat = mol.nat;
    const int64_t npad = round_up(nat, TILE);
@@ -494,16 +497,31 @@ static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, 
    BcAtoms at = gather_eeqbc(model, mol);
    BcWork w;
    bc_prepare(ctx, mol, model, at, io.cn, io.qloc, grad || cpq, w);
+   PbcScope pbc;
+   double *cself = nullptr, *Wpbc = nullptr;
+   if (mol.periodic) {  // get_cmat_3d + get_amat_3d in one pass over the unique pairs
+      pbc_begin(ctx, mol, pbc.host, pbc.work);
+      pbc.on = true;
+      cself = ctx->alloc<double>(nat);
+      Wpbc = ctx->alloc<double>((size_t)npad * npad);
+      bc_pbc_matrices(ctx, mol, w.atoms, model->dev_rvdw(), model->nid, model->kbc, pbc.work, w.Cm, Wpbc, cself);
+   }
    // xvec = C xtmp (eeqbc.f90:275-282); xtmp lives in w.atoms[5 i + 3]
    double* xtmp = ctx->alloc<double>(nat + 1);
    MCHRG_CUDA(cudaMemcpy2DAsync(xtmp, sizeof(double), w.atoms + 3, 5 * sizeof(double), sizeof(double), nat + 1,
                                 cudaMemcpyDeviceToDevice, ctx->stream));
    double* xvec = ctx->alloc<double>(nat + 1);
    pbc_symv(ctx, nat, w.Cm, npad, xtmp, xvec);
+   if (mol.periodic) bc_pbc_xvec_fix(ctx, nat, w.atoms, cself, xvec);
    MCHRG_LAUNCH(ctx, set_last_kernel, 1, 1, 0, nat, mol.charge, xvec);
 
    double* Jc = nullptr;
-   auto assemble = [&](double* W) { bc_amat(ctx, mol, w, W); };
+   auto assemble = [&](double* W) {
+      if (mol.periodic)
+         MCHRG_CUDA(cudaMemcpyAsync(W, Wpbc, (size_t)npad * npad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      else
+         bc_amat(ctx, mol, w, W);
+   };
    auto keep_copy = [&](double* W) {
       if (io.energy) {
          Jc = ctx->alloc<double>((size_t)npad * npad);
@@ -795,17 +813,27 @@ int mchrg_b200_get_xvec(const mchrg_b200_model* model, const mchrg_b200_structur
       DevMol d = stage_mol(ctx, mol);
       if (model->kind == 2) {
          if (!qloc) fail(MCHRG_B200_ERR_MODEL, "qloc required for eeqbc");
-         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC is not built");
          const size_t n = d.nat;
          BcAtoms at = gather_eeqbc(model, d);
          BcWork w;
          bc_prepare(ctx, d, model, at, ctx->in(cn, n), ctx->in(qloc, n), false, w);
+         PbcScope ps;
+         double* cself = nullptr;
+         if (d.periodic) {
+            pbc_begin(ctx, d, ps.host, ps.work);
+            ps.on = true;
+            cself = ctx->alloc<double>(n);
+            double* W = ctx->alloc<double>((size_t)w.npad * w.npad);
+            bc_pbc_matrices(ctx, d, w.atoms, model->dev_rvdw(), model->nid, model->kbc, ps.work, w.Cm, W, cself);
+         }
          double* xtmp = ctx->alloc<double>(n + 1);
          MCHRG_CUDA(cudaMemcpy2DAsync(xtmp, sizeof(double), w.atoms + 3, 5 * sizeof(double), sizeof(double), n + 1,
                                       cudaMemcpyDeviceToDevice, ctx->stream));
          double* xv = ctx->out(xvec, n + 1);
          pbc_symv(ctx, d.nat, w.Cm, w.npad, xtmp, xv);
+         if (d.periodic) bc_pbc_xvec_fix(ctx, d.nat, w.atoms, cself, xv);
          MCHRG_LAUNCH(ctx, set_last_kernel, 1, 1, 0, d.nat, d.charge, xv);
+         if (d.periodic) ctx->finish();  // host setup arrays of `ps` are consumed by async copies
          return 0;
       }
       AtomPar ap = gather_eeq(model, d);
@@ -825,7 +853,7 @@ int mchrg_b200_get_xvec_derivs(const mchrg_b200_model* model, const mchrg_b200_s
       const size_t n = d.nat;
       if (model->kind == 2) {
          if (!qloc || !dqlocdr || !dqlocdL) fail(MCHRG_B200_ERR_MODEL, "qloc and its derivatives required for eeqbc");
-         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC is not built");
+         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC derivatives are not built (charges and energy only)");
          BcAtoms at = gather_eeqbc(model, d);
          BcWork w;
          const double* dcn = ctx->in(dcndr, 3 * n * n);
@@ -873,14 +901,22 @@ int mchrg_b200_get_coulomb_matrix(const mchrg_b200_model* model, const mchrg_b20
       const size_t nd = (size_t)d.nat + 1;
       if (model->kind == 2) {
          if (!cn || !qloc) fail(MCHRG_B200_ERR_MODEL, "cn and qloc required for eeqbc");
-         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC is not built");
          BcAtoms at = gather_eeqbc(model, d);
          BcWork w;
          bc_prepare(ctx, d, model, at, ctx->in(cn, (size_t)d.nat), ctx->in(qloc, (size_t)d.nat), false, w);
          double* W = ctx->alloc<double>((size_t)w.npad * w.npad);
-         bc_amat(ctx, d, w, W);
+         PbcScope ps;
+         if (d.periodic) {
+            pbc_begin(ctx, d, ps.host, ps.work);
+            ps.on = true;
+            double* cself = ctx->alloc<double>((size_t)d.nat);
+            bc_pbc_matrices(ctx, d, w.atoms, model->dev_rvdw(), model->nid, model->kbc, ps.work, w.Cm, W, cself);
+         } else {
+            bc_amat(ctx, d, w, W);
+         }
          MCHRG_LAUNCH(ctx, border_copy_kernel, dim3((unsigned)((nd + 255) / 256), (unsigned)nd), 256, 0, d.nat, W, w.npad,
                       ctx->out(amat, nd * nd));
+         if (d.periodic) ctx->finish();  // host setup arrays of `ps` are consumed by async copies
          return 0;
       }
       AtomPar ap = gather_eeq(model, d);
@@ -914,7 +950,7 @@ int mchrg_b200_get_coulomb_derivs(const mchrg_b200_model* model, const mchrg_b20
       if (model->kind == 2) {
          if (!cn || !qloc || !dcndr || !dcndL || !dqlocdr || !dqlocdL)
             fail(MCHRG_B200_ERR_MODEL, "cn, qloc and their derivatives required for eeqbc");
-         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC is not built");
+         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC derivatives are not built (charges and energy only)");
          BcAtoms at = gather_eeqbc(model, d);
          BcWork w;
          const double* dcn = ctx->in(dcndr, 3 * n * n);

@@ -434,6 +434,137 @@ void pbc_amat(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, c
    work.phase_ready = true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Periodic EEQ-BC, charge / energy path (eeqbc.f90:532-627, 1065-1165, 283-311).  The bond capacity
+// c(r) = sqrt(cap_i cap_j) / 2 (1 + erf(-kbc (r - rvdw) / rvdw)) is short ranged, so the reference uses plain
+// direct sums (no Ewald split): per WSC image the 125 direct translations.  One evaluation per unique pair
+// feeds C(i, j) = C(j, i) = -sum c and A(i, j) = A(j, i) = -sum c erf(gamma r) / r.
+// atoms[5 a + 0] = rad_eff(a), [2] = effective hardness h_a, [4] = cap_a (bc_atom_kernel in eeqbc.cu).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bc_dir_sums(const double* __restrict__ dt, double vx, double vy, double vz, double gam,
+                                            double kbc, double rv, double sc, double& csum, double& asum) {
+   for (int itr = 0; itr < NDT; ++itr) {
+      const double x = vx + dt[3 * itr], y = vy + dt[3 * itr + 1], z = vz + dt[3 * itr + 2];
+      const double r1 = sqrt(x * x + y * y + z * z);
+      if (r1 < EPS_SQRT) continue;
+      const double targ = kbc * (r1 - rv) / rv;
+      if (targ > PRUNE_ARG) continue;  // 1 + erf(-t) == 0 to double precision beyond
+      const double c = sc * 0.5 * (1.0 + erf(-targ));  // get_cpair, eeqbc.f90:1130-1143
+      csum += c;
+      asum -= c * erf(gam * r1) / r1;  // get_amat_dir_3d, eeqbc.f90:600-627
+   }
+}
+
+__global__ void __launch_bounds__(256) bc_pbc_pair_tiles_kernel(int nat, const double* __restrict__ xyz,
+                                                                const int* __restrict__ id,
+                                                                const double* __restrict__ atoms,
+                                                                const double* __restrict__ rvdw, int nid, double kbc,
+                                                                PbcDev pb, double* __restrict__ Cm,
+                                                                double* __restrict__ W, int64_t ld) {
+   __shared__ double sdt[3 * NDT];
+   __shared__ double swt[3 * 27];
+   for (int k = threadIdx.x; k < 3 * NDT; k += blockDim.x) sdt[k] = pb.dtrans[k];
+   for (int k = threadIdx.x; k < 3 * pb.nw; k += blockDim.x) swt[k] = pb.wtrans[k];
+   __syncthreads();
+   int ti, tj;
+   tile_coords(blockIdx.x, ti, tj);
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   const int j = tj * 32 + lane;
+   for (int rr = 0; rr < 4; ++rr) {
+      const int i = ti * 32 + warp + 8 * rr;
+      if (i >= nat || j >= i) continue;  // strictly lower triangle
+      const double vx = xyz[3 * j] - xyz[3 * i], vy = xyz[3 * j + 1] - xyz[3 * i + 1], vz = xyz[3 * j + 2] - xyz[3 * i + 2];
+      const double ri = atoms[5 * i], rj = atoms[5 * j];
+      const double gam = 1.0 / sqrt(ri * ri + rj * rj);
+      const double sc = sqrt(atoms[5 * i + 4] * atoms[5 * j + 4]);
+      const double rv = rvdw[(id[i] - 1) + (size_t)nid * (id[j] - 1)];
+      const unsigned mask = wsc_select(swt, pb.nw, -vx, -vy, -vz);  // wsc vec = r_i - r_j
+      const double wsw = 1.0 / (double)__popc(mask);
+      double csum = 0.0, asum = 0.0;
+      for (unsigned m = mask; m; m &= m - 1) {
+         const int p = __ffs(m) - 1;
+         bc_dir_sums(sdt, vx + swt[3 * p], vy + swt[3 * p + 1], vz + swt[3 * p + 2], gam, kbc, rv, sc, csum, asum);
+      }
+      Cm[i + (int64_t)j * ld] = Cm[j + (int64_t)i * ld] = -csum * wsw;
+      W[i + (int64_t)j * ld] = W[j + (int64_t)i * ld] = asum * wsw;
+   }
+}
+
+// diagonal: C(a, a) = sum_b c_ab + self images, A(a, a) = self images + h_a C(a, a) + 1; cself(a) for get_xvec;
+// padding: C = 0, A = identity.  One warp per row (the off-diagonal entries of the row are summed).
+__global__ void __launch_bounds__(256) bc_pbc_diag_kernel(int nat, int64_t npad, const int* __restrict__ id,
+                                                          const double* __restrict__ atoms,
+                                                          const double* __restrict__ rvdw, int nid, double kbc,
+                                                          PbcDev pb, double* __restrict__ Cm, double* __restrict__ W,
+                                                          int64_t ld, double* __restrict__ cself) {
+   const int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   const int lane = threadIdx.x & 31;
+   if (a >= npad) return;
+   if (a >= nat) {
+      for (int64_t b = lane; b < npad; b += 32) {
+         Cm[b + a * ld] = 0.0;
+         Cm[a + b * ld] = 0.0;
+         W[b + a * ld] = (b == a) ? 1.0 : 0.0;
+         W[a + b * ld] = (b == a) ? 1.0 : 0.0;
+      }
+      return;
+   }
+   double rowsum = 0.0;
+   for (int b = lane; b < nat; b += 32)
+      if (b != a) rowsum -= Cm[b + a * ld];  // C(a, b) = -c_ab
+   rowsum = warp_sum_p(rowsum);
+   // self images: the 125 direct translations are split over the lanes
+   const double ra = atoms[5 * a], capa = atoms[5 * a + 4];
+   const double gam = 1.0 / sqrt(2.0 * ra * ra);
+   const double rv = rvdw[(id[a] - 1) + (size_t)nid * (id[a] - 1)];
+   const unsigned mask = wsc_select(pb.wtrans, pb.nw, 0.0, 0.0, 0.0);
+   const double wsw = 1.0 / (double)__popc(mask);
+   double cs = 0.0, as = 0.0;
+   for (unsigned m = mask; m; m &= m - 1) {
+      const int p = __ffs(m) - 1;
+      for (int itr = lane; itr < NDT; itr += 32) {
+         const double x = pb.wtrans[3 * p] + pb.dtrans[3 * itr], y = pb.wtrans[3 * p + 1] + pb.dtrans[3 * itr + 1],
+                      z = pb.wtrans[3 * p + 2] + pb.dtrans[3 * itr + 2];
+         const double r1 = sqrt(x * x + y * y + z * z);
+         if (r1 < EPS_SQRT) continue;
+         const double c = capa * 0.5 * (1.0 + erf(-kbc * (r1 - rv) / rv));
+         cs += c;
+         as -= c * erf(gam * r1) / r1;
+      }
+   }
+   cs = warp_sum_p(cs) * wsw;
+   as = warp_sum_p(as) * wsw;
+   if (lane == 0) {
+      const double caa = rowsum + cs;
+      Cm[a + a * ld] = caa;
+      W[a + a * ld] = as + caa * atoms[5 * a + 2] + 1.0;
+      cself[a] = cs;
+   }
+}
+
+// xvec(a) -= cself(a) xtmp(a): eliminate the self interaction (eeqbc.f90:283-311)
+__global__ void bc_pbc_xvec_fix_kernel(int nat, const double* __restrict__ atoms, const double* __restrict__ cself,
+                                       double* __restrict__ xvec) {
+   const int a = blockIdx.x * blockDim.x + threadIdx.x;
+   if (a < nat) xvec[a] -= cself[a] * atoms[5 * a + 3];
+}
+
+void bc_pbc_matrices(mchrg_b200_context* ctx, const DevMol& mol, const double* atoms, const double* rvdw, int nid,
+                     double kbc, PbcWork& work, double* Cm, double* W, double* cself) {
+   auto* st = static_cast<PbcState*>(work.state);
+   const int64_t npad = work.npad;
+   const int nat = mol.nat;
+   const int nt = (nat + 31) / 32;
+   MCHRG_LAUNCH(ctx, bc_pbc_pair_tiles_kernel, (unsigned)(nt * (nt + 1) / 2), 256, 0, nat, mol.xyz, mol.id, atoms, rvdw, nid,
+                kbc, st->pb, Cm, W, npad);
+   MCHRG_LAUNCH(ctx, bc_pbc_diag_kernel, (unsigned)((npad + 7) / 8), 256, 0, nat, npad, mol.id, atoms, rvdw, nid, kbc, st->pb,
+                Cm, W, npad, cself);
+}
+
+void bc_pbc_xvec_fix(mchrg_b200_context* ctx, int nat, const double* atoms, const double* cself, double* xvec) {
+   MCHRG_LAUNCH(ctx, bc_pbc_xvec_fix_kernel, (unsigned)((nat + 255) / 256), 256, 0, nat, atoms, cself, xvec);
+}
+
 void pbc_symv(mchrg_b200_context* ctx, int nat, const double* A, int64_t ld, const double* x, double* y) {
    MCHRG_LAUNCH(ctx, symv_full_kernel, (unsigned)((nat + 31) / 32), 256, 0, nat, A, ld, x, y);
 }

@@ -35,4 +35,12 @@ void pbc_symv(mchrg_b200_context* ctx, int nat, const double* A, int64_t ld, con
 void pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q, PbcWork& work,
                 double* B, int64_t ldb, int64_t mp, double* atrace, double* dadL);
 
+// Periodic EEQ-BC, charge / energy path (get_cmat_3d eeqbc.f90:1065-1128, get_amat_3d :532-598): fills the
+// capacitance matrix Cm and the Coulomb block W (both order work.npad, ld = npad; padding: Cm zero, W identity)
+// and cself(a) = capacitance of atom a with its own images; `atoms` as produced by bc_atom_kernel (eeqbc.cu)
+void bc_pbc_matrices(mchrg_b200_context* ctx, const DevMol& mol, const double* atoms, const double* rvdw, int nid,
+                     double kbc, PbcWork& work, double* Cm, double* W, double* cself);
+// xvec(a) -= cself(a) xtmp(a)   (the periodic part of get_xvec, eeqbc.f90:283-311)
+void bc_pbc_xvec_fix(mchrg_b200_context* ctx, int nat, const double* atoms, const double* cself, double* xvec);
+
 }  // namespace mchrg

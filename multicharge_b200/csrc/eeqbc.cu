@@ -381,6 +381,7 @@ void bc_prepare(mchrg_b200_context* ctx, const DevMol& mol, const mchrg_b200_mod
    MCHRG_LAUNCH(ctx, bc_atom_kernel, (nat + 1 + 127) / 128, 128, 0, nat, at, model->kcnrad, model->norm_exp, cn, qloc,
                 mol.charge, w.atoms);
    w.Cm = ctx->alloc<double>((size_t)w.npad * w.npad);
+   if (mol.periodic) return;  // the periodic capacitance matrix comes from bc_pbc_matrices (eeq_pbc.cu)
    w.dcdr_diag = grad ? ctx->alloc<double>((size_t)3 * nat) : nullptr;
    w.dcdL = grad ? ctx->alloc<double>((size_t)9 * nat) : nullptr;
    MCHRG_LAUNCH(ctx, bc_cmat_kernel, (unsigned)((w.npad + 7) / 8), 256, 0, nat, w.npad, mol.xyz, mol.id, w.atoms,

@@ -15,7 +15,10 @@
  * PARITY UNPINNED against reference numbers: the EEQ-BC known answers of the reference need the
  * pairwise D3 vdW radii and Pauling EN tables of mctc-lib, which are not available offline.  The
  * restatement is checked by the reference's finite-difference methodology (tests/test_oracle_eeqbc.py).
- * The periodic EEQ-BC branch (get_*_3d) is not restated.
+ * Periodic EEQ-BC: the charge / energy path is restated (get_cmat_3d eeqbc.f90:1065-1128, get_cpair_dir :1145-1165,
+ * the periodic part of get_xvec :283-311, get_amat_3d / get_amat_dir_3d :532-627); the periodic DERIVATIVE routines
+ * (get_damat_3d, get_dcmat_3d, periodic get_xvec_derivs) are not restated -- a periodic solve with derivative
+ * outputs returns -1.
  */
 #include "mchrg_oracle.h"
 
@@ -46,6 +49,8 @@ int orc_solve_core(const void* model, const orc_mol* mol, const void* cache, con
 typedef struct {
    const double *cn, *qloc, *dcndr, *dcndL, *dqlocdr, *dqlocdL;
    double *cmat, *dcdr, *dcdL, *xtmp;
+   orc_wsc wsc; /* periodic only */
+   int periodic;
 } bc_cache;
 
 static double rvdw_of(const orc_eeqbc_model* m, const orc_mol* mol, int iat, int jat) {
@@ -67,6 +72,58 @@ static void dcpair(double kbc, const double* vec, double rvdw, double capi, doub
    for (int c = 0; c < 3; ++c) dg[c] = dtmp * vec[c] / r1;
    for (int b = 0; b < 3; ++b)
       for (int a = 0; a < 3; ++a) ds[a + 3 * b] = dg[b] * vec[a];
+}
+
+#define BC_EPS 1.4901161193847656e-08 /* sqrt(epsilon(0.0_wp)), eeqbc.f90:90 */
+
+/* get_cpair_dir, eeqbc.f90:1145-1165 */
+static double cpair_dir(double kbc, const double* rij, const double* dtrans, double rvdw, double capi, double capj) {
+   double sum = 0.0;
+   for (int itr = 0; itr < 125; ++itr) {
+      const double v0 = rij[0] + dtrans[3 * itr], v1 = rij[1] + dtrans[3 * itr + 1], v2 = rij[2] + dtrans[3 * itr + 2];
+      const double r1 = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+      if (r1 < BC_EPS) continue;
+      sum += cpair(kbc, r1, rvdw, capi, capj);
+   }
+   return sum;
+}
+
+/* get_cmat_3d, eeqbc.f90:1065-1128 */
+static void cmat_3d(const orc_eeqbc_model* m, const orc_mol* mol, const orc_wsc* wsc, double* cmat) {
+   const int nat = mol->nat, nd = nat + 1, ntw = wsc->ntr;
+   double dtrans[3 * 125];
+   orc_get_dir_trans(mol->lattice, dtrans);
+   memset(cmat, 0, sizeof(double) * (size_t)nd * nd);
+   for (int iat = 0; iat < nat; ++iat) {
+      const double capi = m->cap[mol->id[iat] - 1];
+      for (int jat = 0; jat < iat; ++jat) {
+         const double capj = m->cap[mol->id[jat] - 1];
+         const double rvdw = rvdw_of(m, mol, iat, jat);
+         const int nimg = wsc->nimg[jat + (size_t)nat * iat];
+         const int* tri = wsc->tridx + (size_t)ntw * (jat + (size_t)nat * iat);
+         const double wsw = 1.0 / (double)nimg;
+         for (int img = 0; img < nimg; ++img) {
+            const double* t = wsc->trans + 3 * (tri[img] - 1);
+            double vec[3];
+            for (int c = 0; c < 3; ++c) vec[c] = mol->xyz[3 * iat + c] - mol->xyz[3 * jat + c] - t[c];
+            const double tmp = cpair_dir(m->kbc, vec, dtrans, rvdw, capi, capj);
+            cmat[jat + (size_t)nd * iat] -= tmp * wsw;
+            cmat[iat + (size_t)nd * jat] -= tmp * wsw;
+            cmat[iat + (size_t)nd * iat] += tmp * wsw;
+            cmat[jat + (size_t)nd * jat] += tmp * wsw;
+         }
+      }
+      /* diagonal capacitance (interaction with images) */
+      const double rvdw = rvdw_of(m, mol, iat, iat);
+      const int nimg = wsc->nimg[iat + (size_t)nat * iat];
+      const int* tri = wsc->tridx + (size_t)ntw * (iat + (size_t)nat * iat);
+      const double wsw = 1.0 / (double)nimg;
+      for (int img = 0; img < nimg; ++img) {
+         const double tmp = cpair_dir(m->kbc, wsc->trans + 3 * (tri[img] - 1), dtrans, rvdw, capi, capi);
+         cmat[iat + (size_t)nd * iat] += tmp * wsw;
+      }
+   }
+   cmat[nat + (size_t)nd * nat] = 1.0;
 }
 
 /* get_cmat_0d, eeqbc.f90:1015-1063 */
@@ -127,6 +184,12 @@ static void bc_update(const orc_eeqbc_model* m, const orc_mol* mol, bc_cache* c,
    if (grad) { c->dcndr = dcndr; c->dcndL = dcndL; c->dqlocdr = dqlocdr; c->dqlocdL = dqlocdL; }
    c->xtmp = (double*)calloc(nd, sizeof(double));
    c->cmat = (double*)malloc(sizeof(double) * (size_t)nd * nd);
+   c->periodic = mol->periodic[0] || mol->periodic[1] || mol->periodic[2];
+   if (c->periodic) { /* eeqbc.f90:222-236; the derivative branch (get_dcmat_3d) is not restated */
+      orc_wsc_new(mol, &c->wsc);
+      cmat_3d(m, mol, &c->wsc, c->cmat);
+      return;
+   }
    cmat_0d(m, mol, c->cmat);
    if (grad) {
       c->dcdr = (double*)malloc(sizeof(double) * 3 * (size_t)nat * nd);
@@ -134,7 +197,10 @@ static void bc_update(const orc_eeqbc_model* m, const orc_mol* mol, bc_cache* c,
       dcmat_0d(m, mol, c->dcdr, c->dcdL);
    }
 }
-static void bc_free(bc_cache* c) { free(c->xtmp); free(c->cmat); free(c->dcdr); free(c->dcdL); }
+static void bc_free(bc_cache* c) {
+   free(c->xtmp); free(c->cmat); free(c->dcdr); free(c->dcdL);
+   if (c->periodic) orc_wsc_free(&c->wsc);
+}
 
 /* get_xvec, eeqbc.f90:254-312 */
 static void bc_get_xvec(const orc_eeqbc_model* m, const orc_mol* mol, bc_cache* c, double* xvec) {
@@ -147,6 +213,22 @@ static void bc_get_xvec(const orc_eeqbc_model* m, const orc_mol* mol, bc_cache* 
    const double a1 = 1.0, b0 = 0.0;
    memset(xvec, 0, sizeof(double) * nd);
    scipy_dgemv_("n", &nd, &nd, &a1, c->cmat, &nd, c->xtmp, &one, &b0, xvec, &one, 1);
+   if (c->periodic) { /* eliminate self-interaction (quasi off-diagonal), eeqbc.f90:283-311 */
+      double dtrans[3 * 125];
+      orc_get_dir_trans(mol->lattice, dtrans);
+      const int ntw = c->wsc.ntr;
+      for (int iat = 0; iat < nat; ++iat) {
+         const double capi = m->cap[mol->id[iat] - 1];
+         const double rvdw = rvdw_of(m, mol, iat, iat);
+         const int nimg = c->wsc.nimg[iat + (size_t)nat * iat];
+         const int* tri = c->wsc.tridx + (size_t)ntw * (iat + (size_t)nat * iat);
+         const double wsw = 1.0 / (double)nimg;
+         for (int img = 0; img < nimg; ++img) {
+            const double ctmp = cpair_dir(m->kbc, c->wsc.trans + 3 * (tri[img] - 1), dtrans, rvdw, capi, capi);
+            xvec[iat] -= wsw * ctmp * c->xtmp[iat];
+         }
+      }
+   }
 }
 
 /* get_xvec_derivs, eeqbc.f90:314-457 (non-periodic branch) */
@@ -200,6 +282,67 @@ static double rad_i(const orc_eeqbc_model* m, int izp, double cn) {
 static double rad_j(const orc_eeqbc_model* m, int jzp, double cn) {
    const double norm_cn = cn / pow(m->avg_cn[jzp], m->norm_exp);
    return m->rad[jzp] * (1.0 - m->kcnrad * norm_cn);
+}
+
+/* get_amat_dir_3d, eeqbc.f90:600-627 */
+static double amat_dir_3d(const double* rij, double gam, const double* dtrans, double kbc, double rvdw, double capi,
+                          double capj) {
+   double amat = 0.0;
+   for (int itr = 0; itr < 125; ++itr) {
+      const double v0 = rij[0] + dtrans[3 * itr], v1 = rij[1] + dtrans[3 * itr + 1], v2 = rij[2] + dtrans[3 * itr + 2];
+      const double r1 = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+      if (r1 < BC_EPS) continue;
+      amat += -cpair(kbc, r1, rvdw, capi, capj) * erf(gam * r1) / r1;
+   }
+   return amat;
+}
+
+/* get_amat_3d, eeqbc.f90:532-598 */
+static void bc_amat_3d(const orc_eeqbc_model* m, const orc_mol* mol, const orc_wsc* wsc, const double* cn,
+                       const double* qloc, const double* cmat, double* amat) {
+   const int nat = mol->nat, nd = nat + 1, ntw = wsc->ntr;
+   double dtrans[3 * 125];
+   orc_get_dir_trans(mol->lattice, dtrans);
+   memset(amat, 0, sizeof(double) * (size_t)nd * nd);
+   for (int iat = 0; iat < nat; ++iat) {
+      const int izp = mol->id[iat] - 1;
+      const double radi = rad_i(m, izp, cn[iat]);
+      const double capi = m->cap[izp];
+      for (int jat = 0; jat < iat; ++jat) {
+         const int jzp = mol->id[jat] - 1;
+         const double rvdw = rvdw_of(m, mol, iat, jat);
+         const double radj = rad_j(m, jzp, cn[jat]);
+         const double capj = m->cap[jzp];
+         const double gam = 1.0 / sqrt(radi * radi + radj * radj);
+         const int nimg = wsc->nimg[jat + (size_t)nat * iat];
+         const int* tri = wsc->tridx + (size_t)ntw * (jat + (size_t)nat * iat);
+         const double wsw = 1.0 / (double)nimg;
+         for (int img = 0; img < nimg; ++img) {
+            const double* t = wsc->trans + 3 * (tri[img] - 1);
+            double vec[3];
+            for (int c = 0; c < 3; ++c) vec[c] = mol->xyz[3 * jat + c] - mol->xyz[3 * iat + c] + t[c];
+            const double dtmp = amat_dir_3d(vec, gam, dtrans, m->kbc, rvdw, capi, capj);
+            amat[jat + (size_t)nd * iat] += dtmp * wsw;
+            amat[iat + (size_t)nd * jat] += dtmp * wsw;
+         }
+      }
+      /* diagonal Coulomb interaction terms */
+      const double gam = 1.0 / sqrt(2.0 * radi * radi);
+      const double rvdw = rvdw_of(m, mol, iat, iat);
+      const int nimg = wsc->nimg[iat + (size_t)nat * iat];
+      const int* tri = wsc->tridx + (size_t)ntw * (iat + (size_t)nat * iat);
+      const double wsw = 1.0 / (double)nimg;
+      for (int img = 0; img < nimg; ++img)
+         amat[iat + (size_t)nd * iat] += amat_dir_3d(wsc->trans + 3 * (tri[img] - 1), gam, dtrans, m->kbc, rvdw, capi, capi) * wsw;
+      /* effective hardness */
+      const double dtmp = m->eta[izp] + m->kqeta[izp] * qloc[iat] + SQRT2PI / radi;
+      amat[iat + (size_t)nd * iat] += cmat[iat + (size_t)nd * iat] * dtmp + 1.0;
+   }
+   for (int k = 0; k <= nat; ++k) {
+      amat[nat + (size_t)nd * k] = 1.0;
+      amat[k + (size_t)nd * nat] = 1.0;
+   }
+   amat[nat + (size_t)nd * nat] = 0.0;
 }
 
 /* get_amat_0d, eeqbc.f90:475-530 */
@@ -352,11 +495,19 @@ void orc_eeqbc_get_coulomb_matrix(const orc_eeqbc_model* m, const orc_mol* mol, 
                                   const double* qloc, double* amat) {
    bc_cache c;
    bc_update(m, mol, &c, cn, qloc, NULL, NULL, NULL, NULL);
-   bc_amat_0d(m, mol, cn, qloc, c.cmat, amat);
+   if (c.periodic) bc_amat_3d(m, mol, &c.wsc, cn, qloc, c.cmat, amat);
+   else bc_amat_0d(m, mol, cn, qloc, c.cmat, amat);
    bc_free(&c);
 }
 
 void orc_eeqbc_get_cmat(const orc_eeqbc_model* m, const orc_mol* mol, double* cmat, double* dcdr, double* dcdL) {
+   if (mol->periodic[0] || mol->periodic[1] || mol->periodic[2]) { /* value only */
+      orc_wsc wsc;
+      orc_wsc_new(mol, &wsc);
+      cmat_3d(m, mol, &wsc, cmat);
+      orc_wsc_free(&wsc);
+      return;
+   }
    cmat_0d(m, mol, cmat);
    if (dcdr && dcdL) dcmat_0d(m, mol, dcdr, dcdL);
 }
@@ -394,15 +545,18 @@ static void bc_vt_coulomb_derivs(const void* model, const orc_mol* mol, const vo
 int orc_eeqbc_solve(const orc_eeqbc_model* m, const orc_mol* mol, const double* cn, const double* qloc,
                     const double* dcndr, const double* dcndL, const double* dqlocdr, const double* dqlocdL,
                     double* energy, double* gradient, double* sigma, double* qvec, double* dqdr, double* dqdL) {
-   if (mol->periodic[0] || mol->periodic[1] || mol->periodic[2]) return -1; /* not restated */
-   if (!qloc) return -2;                                                     /* error stop, eeqbc.f90:202 */
+   const int pbc = mol->periodic[0] || mol->periodic[1] || mol->periodic[2];
+   if (pbc && (gradient || sigma || dqdr || dqdL)) return -1; /* periodic derivatives are not restated */
+   if (pbc) { dcndr = dcndL = dqlocdr = dqlocdL = NULL; }
+   if (!qloc) return -2;                                      /* error stop, eeqbc.f90:202 */
    const int nd = mol->nat + 1;
    const orc_solve_vtbl vt = {bc_vt_xvec_derivs, bc_vt_coulomb_derivs};
    bc_cache c;
    bc_update(m, mol, &c, cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL);
    double* amat = (double*)malloc(sizeof(double) * (size_t)nd * nd);
    double* xvec = (double*)malloc(sizeof(double) * nd);
-   bc_amat_0d(m, mol, cn, qloc, c.cmat, amat);
+   if (c.periodic) bc_amat_3d(m, mol, &c.wsc, cn, qloc, c.cmat, amat);
+   else bc_amat_0d(m, mol, cn, qloc, c.cmat, amat);
    bc_get_xvec(m, mol, &c, xvec);
    /* solve()'s `grad`/`cpq` only test dcndr/dcndL (type.F90:199-201); the EEQ-BC derivative routines
     * additionally need the local-charge derivatives */

@@ -97,3 +97,30 @@ def test_eeqbc_fd_gradient_dqdr_sigma(oracle):
                     q.append(r2.qvec)
                 assert abs((e[0] - e[1]) / (2 * STEP) - r.sigma[b, a]) < 3 * tol * max(1.0, np.abs(r.sigma).max()), (name, a, b)
                 assert np.abs((q[0] - q[1]) / (2 * STEP) - r.dqdL[:, b, a]).max() < 3 * tol * max(1.0, np.abs(r.dqdL).max())
+
+
+def test_oracle_eeqbc_periodic_charge_path():
+    """Periodic EEQ-BC (charge / energy path; parity unpinned against reference numbers like the 0-D branch): in a
+    cell much larger than the range of the bond capacity the periodic branch must reproduce the molecular result
+    exactly, lattice translations of single atoms must not change anything, and derivative outputs are refused."""
+    import oracle as orc
+    from synth import cluster
+    num, xyz = cluster(12, 5)
+    m0 = orc.Mol(num, xyz, 1.0)
+    model = orc.new_eeqbc2025_model(m0)
+    r0 = orc.eeqbc_singlepoint(model, m0, want=("qvec", "energy"))
+    big = orc.Mol(num, xyz, 1.0, lattice=np.eye(3) * 80.0, periodic=[True] * 3)
+    rb = orc.eeqbc_singlepoint(model, big, want=("qvec", "energy"))
+    assert r0.stat == 0 and rb.stat == 0
+    assert np.abs(r0.qvec - rb.qvec).max() < 1e-13 and np.abs(r0.energy - rb.energy).max() < 1e-13
+    lat = np.array([[11.0, 0.0, 0.0], [0.6, 10.0, 0.0], [0.3, 0.4, 12.0]])
+    m1 = orc.Mol(num, xyz, 1.0, lattice=lat, periodic=[True] * 3)
+    r1 = orc.eeqbc_singlepoint(model, m1, want=("qvec", "energy"))
+    xyz2 = xyz.copy()
+    xyz2[2] += lat[0] - lat[2]
+    xyz2[7] -= lat[1]  # (one cell: the Wigner-Seitz search of the reference covers the 27 neighbouring cells)
+    r2 = orc.eeqbc_singlepoint(model, orc.Mol(num, xyz2, 1.0, lattice=lat, periodic=[True] * 3), want=("qvec", "energy"))
+    assert r1.stat == 0 and abs(r1.qvec.sum() - 1.0) < 1e-12
+    assert np.abs(r1.qvec - r2.qvec).max() < 1e-12 and abs(r1.energy.sum() - r2.energy.sum()) < 1e-11
+    assert np.abs(r1.qvec - r0.qvec).max() > 1e-4  # the images matter in the small cell
+    assert orc.eeqbc_singlepoint(model, m1, want=("qvec", "energy", "gradient")).stat == -1
