@@ -6,6 +6,7 @@
 // These kernels are FP64-ALU bound (erf/exp are polynomial sequences on the FMA pipe) until the
 // 24 N^2-byte stores dominate.
 #include "eeq.cuh"
+#include "erfgauss.cuh"
 
 namespace mchrg {
 
@@ -40,10 +41,18 @@ struct NcDev {
    int use_en;
 };
 
+// erf / exp(-x^2) through the node table of erfgauss.cuh (shared-memory copy per CTA) and 1/sqrt through the
+// hardware seed + one third-order step: ~4x fewer instructions per pair than the library functions
+#define MCHRG_LOAD_ERF_TABLE(etab_global)                                            \
+   __shared__ double2 setab[eg::NTAB];                                               \
+   eg::load_table(setab, etab_global, (int)threadIdx.x, (int)blockDim.x);            \
+   __syncthreads()
+
 __global__ void __launch_bounds__(256) cn_rows_kernel(int nat, const double* __restrict__ xyz,
                                                       const double* __restrict__ rcov, const double* __restrict__ en,
                                                       NcDev p, int ntr, const double* __restrict__ trans,
-                                                      double* __restrict__ cn_raw) {
+                                                      double* __restrict__ cn_raw, const double2* __restrict__ etab) {
+   MCHRG_LOAD_ERF_TABLE(etab);
    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    const int lane = threadIdx.x & 31;
    if (i >= nat) return;
@@ -60,8 +69,10 @@ __global__ void __launch_bounds__(256) cn_rows_kernel(int nat, const double* __r
          const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
          const double r2 = rx * rx + ry * ry + rz * rz;
          if (r2 > p.cutoff2 || r2 < 1.0e-12) continue;
-         const double r1 = sqrt(r2);
-         acc += den * 0.5 * (1.0 + erf(-p.kcn * (r1 - rc) / rcn));
+         const double r1 = r2 * eg::fast_rsqrt(r2);
+         const double a = p.kcn * (r1 - rc) / rcn;
+         double g;
+         acc += den * (0.5 - copysign(0.5, a) * eg::erf_gauss<6, false>(setab, fabs(a), g));  // 1/2 (1 + erf(-a))
       }
    }
    acc = warp_sum(acc);
@@ -72,7 +83,8 @@ __global__ void __launch_bounds__(256) cn_derivs_kernel(int nat, const double* _
                                                         const double* __restrict__ rcov, const double* __restrict__ en,
                                                         NcDev p, int ntr, const double* __restrict__ trans,
                                                         const double* __restrict__ cn_raw, double* __restrict__ dcndr,
-                                                        double* __restrict__ dcndL) {
+                                                        double* __restrict__ dcndL, const double2* __restrict__ etab) {
+   MCHRG_LOAD_ERF_TABLE(etab);
    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    const int lane = threadIdx.x & 31;
    if (i >= nat) return;
@@ -97,9 +109,11 @@ __global__ void __launch_bounds__(256) cn_derivs_kernel(int nat, const double* _
          const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
          const double r2 = rx * rx + ry * ry + rz * rz;
          if (r2 > p.cutoff2 || r2 < 1.0e-12) continue;
-         const double r1 = sqrt(r2);
-         const double arg = p.kcn * (r1 - rc) / rcn;
-         const double dc = den * (-p.kcn / SQRTPI / rcn * exp(-arg * arg)) / r1;
+         const double rinv = eg::fast_rsqrt(r2);
+         const double arg = p.kcn * (r2 * rinv - rc) / rcn;
+         double g;
+         eg::erf_gauss<6, true>(setab, fabs(arg), g);  // g = exp(-arg^2)
+         const double dc = den * (-p.kcn / SQRTPI / rcn * g) * rinv;
          const double c0 = dc * rx, c1 = dc * ry, c2 = dc * rz;  // countd
          g0 += c0; g1 += c1; g2 += c2;
          dl[0] += c0 * rx; dl[1] += c0 * ry; dl[2] += c0 * rz;
@@ -139,9 +153,10 @@ void ncoord_device(mchrg_b200_context* ctx, const DevMol& mol, const double* rco
    double* cn_raw = ctx->alloc<double>(nat);
    const int rows_per_cta = 8;
    const unsigned grid = (nat + rows_per_cta - 1) / rows_per_cta;
-   MCHRG_LAUNCH(ctx, cn_rows_kernel, grid, 256, 0, nat, mol.xyz, rcov_a, en_a, p, ntr, trans, cn_raw);
+   MCHRG_LAUNCH(ctx, cn_rows_kernel, grid, 256, 0, nat, mol.xyz, rcov_a, en_a, p, ntr, trans, cn_raw, ctx->erf_tab);
    if (dcndr && dcndL)
-      MCHRG_LAUNCH(ctx, cn_derivs_kernel, grid, 256, 0, nat, mol.xyz, rcov_a, en_a, p, ntr, trans, cn_raw, dcndr, dcndL);
+      MCHRG_LAUNCH(ctx, cn_derivs_kernel, grid, 256, 0, nat, mol.xyz, rcov_a, en_a, p, ntr, trans, cn_raw, dcndr, dcndL,
+                   ctx->erf_tab);
    MCHRG_LAUNCH(ctx, cn_cut_kernel, (nat + 255) / 256, 256, 0, nat, par.cut, cn_raw, cn);
 }
 
@@ -172,7 +187,9 @@ void eeq_xvec(mchrg_b200_context* ctx, const DevMol& mol, const double* chi_a, c
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) eeq_amat0d_kernel(int nat, const double* __restrict__ xyz,
                                                          const double* __restrict__ rad, const double* __restrict__ eta,
-                                                         double* __restrict__ out, int64_t ld, int border, int64_t npad) {
+                                                         double* __restrict__ out, int64_t ld, int border, int64_t npad,
+                                                         const double2* __restrict__ etab) {
+   MCHRG_LOAD_ERF_TABLE(etab);
    const int64_t nrow = border ? nat + 1 : npad;
    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (r >= nrow) return;
@@ -193,8 +210,9 @@ __global__ void __launch_bounds__(128) eeq_amat0d_kernel(int nat, const double* 
          } else {
             const double dx = xyz[3 * c] - xr, dy = xyz[3 * c + 1] - yr, dz = xyz[3 * c + 2] - zr;
             const double r2 = dx * dx + dy * dy + dz * dz;
-            const double gam = 1.0 / (rr + rad[c] * rad[c]);
-            v = erf(sqrt(r2 * gam)) / sqrt(r2);
+            const double rinv = eg::fast_rsqrt(r2), gam = eg::fast_rsqrt(rr + rad[c] * rad[c]);
+            double g;
+            v = eg::erf_gauss<5, false>(setab, r2 * rinv * gam, g) * rinv;  // erf(gamma r) / r
          }
       } else if (border) {
          v = (r == nat && c == nat) ? 0.0 : 1.0;
@@ -209,7 +227,8 @@ void eeq_amat_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a
                  int64_t ld, bool border, int64_t npad) {
    const int64_t nrow = border ? mol.nat + 1 : npad;
    dim3 grid((unsigned)((nrow + 127) / 128), (unsigned)((nrow + 7) / 8));
-   MCHRG_LAUNCH(ctx, eeq_amat0d_kernel, grid, 128, 0, mol.nat, mol.xyz, rad_a, eta_a, out, ld, border ? 1 : 0, npad);
+   MCHRG_LAUNCH(ctx, eeq_amat0d_kernel, grid, 128, 0, mol.nat, mol.xyz, rad_a, eta_a, out, ld, border ? 1 : 0, npad,
+                ctx->erf_tab);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -219,7 +238,9 @@ __global__ void __launch_bounds__(256) eeq_pair_rows0d_kernel(int nat, const dou
                                                               const double* __restrict__ rad,
                                                               const double* __restrict__ eta,
                                                               const double* __restrict__ q, double* __restrict__ jq,
-                                                              double* __restrict__ atrace, double* __restrict__ dadL) {
+                                                              double* __restrict__ atrace, double* __restrict__ dadL,
+                                                              const double2* __restrict__ etab) {
+   MCHRG_LOAD_ERF_TABLE(etab);
    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    const int lane = threadIdx.x & 31;
    if (i >= nat) return;
@@ -232,15 +253,13 @@ __global__ void __launch_bounds__(256) eeq_pair_rows0d_kernel(int nat, const dou
       // vec = r_j - r_i as in eeq.f90:221,403 (every term is even or odd in vec, the sign is kept)
       const double vx = xyz[3 * j] - xi, vy = xyz[3 * j + 1] - yi, vz = xyz[3 * j + 2] - zi;
       const double r2 = vx * vx + vy * vy + vz * vz;
-      const double g2 = 1.0 / (ri2 + rad[j] * rad[j]);
-      const double arg = g2 * r2;
-      const double r1 = sqrt(r2);
-      const double ef = erf(sqrt(arg));
+      const double rinv = eg::fast_rsqrt(r2), gam = eg::fast_rsqrt(ri2 + rad[j] * rad[j]);
+      double gs;
+      const double ef = eg::erf_gauss<6, true>(setab, r2 * rinv * gam, gs);  // erf(x), exp(-x^2), x = gamma r
       const double qj = q[j];
-      sj = fma(ef / r1, qj, sj);
+      sj = fma(ef * rinv, qj, sj);
       if (want_d) {
-         const double gam = sqrt(g2);
-         const double dtmp = 2.0 * gam * exp(-arg) / (SQRTPI * r2) - ef / (r2 * r1);
+         const double dtmp = (2.0 / SQRTPI * gam * gs - ef * rinv) * rinv * rinv;
          // atrace(:, i) = sum_j dtmp (r_i - r_j) q_j = -dG q_j with dG = dtmp * vec
          const double gx = dtmp * vx, gy = dtmp * vy, gz = dtmp * vz;
          at[0] -= gx * qj; at[1] -= gy * qj; at[2] -= gz * qj;
@@ -273,7 +292,7 @@ __global__ void __launch_bounds__(256) eeq_pair_rows0d_kernel(int nat, const dou
 void eeq_pair_rows_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a,
                       const double* q, double* jq, double* atrace, double* dadL) {
    const unsigned grid = (mol.nat + 7) / 8;
-   MCHRG_LAUNCH(ctx, eeq_pair_rows0d_kernel, grid, 256, 0, mol.nat, mol.xyz, rad_a, eta_a, q, jq, atrace, dadL);
+   MCHRG_LAUNCH(ctx, eeq_pair_rows0d_kernel, grid, 256, 0, mol.nat, mol.xyz, rad_a, eta_a, q, jq, atrace, dadL, ctx->erf_tab);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -291,7 +310,9 @@ __global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const doubl
                                                             const double* __restrict__ dcndr, double* __restrict__ Bout,
                                                             int64_t ldb, double* __restrict__ gradx,
                                                             const double* __restrict__ zvec, double* __restrict__ bz,
-                                                            int pair_in_b, int jb, int je) {
+                                                            int pair_in_b, int jb, int je, const double2* __restrict__ etab) {
+   __shared__ double2 setab[eg::NTAB];
+   eg::load_table(setab, etab, (int)threadIdx.x, (int)blockDim.x);
    __shared__ double sk[BB_KCHUNK][8];  // x, y, z, rad^2, thalf, thalf*q, z, unused
    // atom j of the row block [jb, je); rows of Bout / gradx / bz are numbered within the block
    const int jl = blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,10 +349,10 @@ __global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const doubl
          // dadr(:, j, k) = dtmp (r_j - r_k) q_j      (eeq.f90:412-413 for both orderings of the pair)
          const double vx = xj - sk[kk][0], vy = yj - sk[kk][1], vz = zj - sk[kk][2];
          const double r2 = vx * vx + vy * vy + vz * vz;
-         const double g2 = 1.0 / (rj2 + sk[kk][3]);
-         const double arg = g2 * r2;
-         const double gam = sqrt(g2);
-         const double dtmp = (2.0 * gam * exp(-arg) / (SQRTPI * r2) - erf(sqrt(arg)) / (r2 * sqrt(r2))) * qj;
+         const double rinv = eg::fast_rsqrt(r2), gam = eg::fast_rsqrt(rj2 + sk[kk][3]);
+         double gs;
+         const double ef = eg::erf_gauss<6, true>(setab, r2 * rinv * gam, gs);
+         const double dtmp = (2.0 / SQRTPI * gam * gs - ef * rinv) * rinv * rinv * qj;
          b0 = dtmp * vx; b1 = dtmp * vy; b2 = dtmp * vz;
       }
       if (dcndr) {
@@ -364,7 +385,7 @@ void eeq_build_b_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* ra
    if (je < 0) je = mol.nat;
    dim3 grid((unsigned)((je - jb + 127) / 128), (unsigned)((mol.nat + BB_KCHUNK - 1) / BB_KCHUNK));
    MCHRG_LAUNCH(ctx, eeq_build_b0d_kernel, grid, 128, 0, mol.nat, mol.xyz, rad_a, q, atrace, thalf, dcndr, Bout, ldb,
-                gradx, zvec, bz, pair_in_b ? 1 : 0, jb, je);
+                gradx, zvec, bz, pair_in_b ? 1 : 0, jb, je, ctx->erf_tab);
 }
 
 }  // namespace mchrg
