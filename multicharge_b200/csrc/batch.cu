@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
       };
       // (the warps of a CTA sit on different SM sub-partitions: rotate the serial FP64-heavy D step over them so
       //  that the D chains of the co-resident molecules do not all queue on one FP64 pipe)
-      if (warp == ((blockIdx.x + (k0 >> 4)) & (NW - 1))) {
+      if (warp == ((blockIdx.x + (k0 >> 4)) % NW)) {
          // ---- D: diagonal tile, Cholesky + inverse; the inverse goes to global in place of the block ----
          const bool last = (k0 + KB == npa);
          const int bad = diag_factor_inv(T, Li, cbuf, rbuf, dvec, lane, last ? KB - 2 : KB, last);
@@ -937,7 +937,7 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
    }
    __syncthreads();
    for (int k0 = npa - KB; k0 >= 0; k0 -= KB) {
-      if (warp == ((blockIdx.x + (k0 >> 4)) & (NW - 1))) {  // y_blk = inv(L_kk)^T w_blk ; lane = (r, rhs h)
+      if (warp == ((blockIdx.x + (k0 >> 4)) % NW)) {  // y_blk = inv(L_kk)^T w_blk ; lane = (r, rhs h)
          const int r = lane & 15, h = lane >> 4;
          const double* wv = (h ? b1 : b0) + k0;
          double v = 0.0;
@@ -991,7 +991,10 @@ static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count, 
    MCHRG_LAUNCH(ctx, eeq_factor_ll_kernel<NT>, (unsigned)count, NT, smem, a);
 }
 
-constexpr int LL_NT = 128;  // threads per molecule in the factorisation kernel
+#ifndef LL_NT_DEF
+#define LL_NT_DEF 128
+#endif
+constexpr int LL_NT = LL_NT_DEF;  // threads per molecule in the factorisation kernel
 
 // Factorisation launches of one chunk: the class-sorted permutation is cut into a few groups of size classes so
 // that the block column buffer (and with it the number of resident molecules per SM) matches the molecule size.
