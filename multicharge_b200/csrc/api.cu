@@ -432,7 +432,7 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// EEQ-BC (model/eeqbc.f90); periodic structures: charge / energy path only
+// EEQ-BC (model/eeqbc.f90), molecular and periodic
 // ---------------------------------------------------------------------------------------------
 static BcAtoms gather_eeqbc(const mchrg_b200_model* model, const DevMol& mol) {
    mchrg_b200_context* ctx = model->ctx;
@@ -482,10 +482,6 @@ __global__ void set_last_kernel(int nat, double v, double* __restrict__ x) { x[n
 static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, const SolveIO& io) {
    mchrg_b200_context* ctx = model->ctx;
    if (!io.qloc) fail(MCHRG_B200_ERR_MODEL, "qloc required for eeqbc");  // error stop, eeqbc.f90:202
-   if (mol.periodic && (io.gradient || io.sigma || io.dqdr || io.dqdL))
-      fail(MCHRG_B200_ERR_MODEL,
-           "periodic EEQ-BC derivatives (get_damat_3d / get_dcmat_3d, eeqbc.f90:789-1013, 1243-1333) are not built: "
-           "charges and energy only");
    if (io.je >= 0 && (io.jb != 0 || io.je != mol.nat)) fail(MCHRG_B200_ERR_MODEL, "row blocks are not available for EEQ-BC");
    const int nat = mol.nat;
    const int64_t npad = round_up(nat, TILE);
@@ -539,7 +535,28 @@ static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, 
       pbc_symv(ctx, nat, Jc, npad, q, jq);
       MCHRG_LAUNCH(ctx, energy_kernel, (nat + 255) / 256, 256, 0, nat, q, jq, xvec, io.energy);
    }
-   if (grad || cpq) {
+   if ((grad || cpq) && mol.periodic) {
+      // get_damat_3d / get_dcmat_3d / periodic get_xvec_derivs: everything is assembled by bc_pbc_derivs (eeq_pbc.cu)
+      double* dadL = ctx->alloc_zero<double>((size_t)9 * nat);
+      double* dxdL = ctx->alloc_zero<double>((size_t)9 * nat);
+      double* cq = ctx->alloc<double>(nat);
+      pbc_symv(ctx, nat, w.Cm, npad, q, cq);
+      double *Bm = nullptr, *bz = nullptr;
+      int64_t mp = 0;
+      if (cpq) {
+         mp = round_up(3 * (int64_t)nat + 9, TILE);
+         Bm = ctx->alloc<double>((size_t)mp * npad);
+         bz = ctx->alloc_zero<double>((size_t)mp);
+         bc_dxdr_gemm(ctx, mol, at, w, io.dcndr, io.dqlocdr, -1.0, Bm, mp);  // Bm = -dtmpdr C
+      }
+      double* ga = ctx->alloc_zero<double>((size_t)3 * nat);
+      double* gx = ctx->alloc_zero<double>((size_t)3 * nat);
+      bc_pbc_derivs(ctx, mol, w.atoms, model->dev_rvdw(), model->nid, model->kbc, at.kcnchi, at.kqchi, at.kqeta, q, cq, w.Cm,
+                    cself, io.dcndr, io.dcndL, io.dqlocdr, io.dqlocdL, f.z(npad), pbc.work, Bm, mp, ga, gx, dadL, dxdL, bz);
+      if (grad) MCHRG_LAUNCH(ctx, bc_gradient_kernel, (3 * nat + 255) / 256, 256, 0, 3 * nat, ga, gx, io.gradient);
+      MCHRG_LAUNCH(ctx, bc_sigma_kernel, 1, 288, 0, nat, q, dadL, dxdL, grad ? io.sigma : nullptr, f.z(npad), Bm, mp, bz);
+      if (cpq) dq_tail(ctx, nat, nat, npad, mp, f, Bm, bz, io.dqdr, io.dqdL);
+   } else if (grad || cpq) {
       double* rows = ctx->alloc<double>((size_t)24 * nat);
       bc_rows(ctx, mol, model, w, q, io.dcndr, io.dcndL, rows);
       double* dadL = ctx->alloc<double>((size_t)9 * nat);
@@ -853,7 +870,7 @@ int mchrg_b200_get_xvec_derivs(const mchrg_b200_model* model, const mchrg_b200_s
       const size_t n = d.nat;
       if (model->kind == 2) {
          if (!qloc || !dqlocdr || !dqlocdL) fail(MCHRG_B200_ERR_MODEL, "qloc and its derivatives required for eeqbc");
-         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC derivatives are not built (charges and energy only)");
+         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "the piecewise derivative accessors are not built for periodic EEQ-BC (use solve / singlepoint / get_charges)");
          BcAtoms at = gather_eeqbc(model, d);
          BcWork w;
          const double* dcn = ctx->in(dcndr, 3 * n * n);
@@ -950,7 +967,7 @@ int mchrg_b200_get_coulomb_derivs(const mchrg_b200_model* model, const mchrg_b20
       if (model->kind == 2) {
          if (!cn || !qloc || !dcndr || !dcndL || !dqlocdr || !dqlocdL)
             fail(MCHRG_B200_ERR_MODEL, "cn, qloc and their derivatives required for eeqbc");
-         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "periodic EEQ-BC derivatives are not built (charges and energy only)");
+         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "the piecewise derivative accessors are not built for periodic EEQ-BC (use solve / singlepoint / get_charges)");
          BcAtoms at = gather_eeqbc(model, d);
          BcWork w;
          const double* dcn = ctx->in(dcndr, 3 * n * n);

@@ -565,6 +565,281 @@ void bc_pbc_xvec_fix(mchrg_b200_context* ctx, int nat, const double* atoms, cons
    MCHRG_LAUNCH(ctx, bc_pbc_xvec_fix_kernel, (unsigned)((nat + 255) / 256), 256, 0, nat, atoms, cself, xvec);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Periodic EEQ-BC derivatives (get_damat_3d eeqbc.f90:789-924 with get_damat_dir :926-957 and get_damat_dc_dir
+// :959-985, get_dcmat_3d :1243-1313, the periodic branch of get_xvec_derivs :364-418), assembled directly into
+//   B(3k+c, i) = [dadr + diag(atrace)](c, k, i) - dxdr(c, k, i)          (type.F90:267-269, 283-286)
+// and the contractions  ga = dadr q, gx = dxdr q  (type.F90:277-278), dadL, dxdL per atom.
+// Per unique pair (i > j) ONE pass over the images x 125 translations yields the seven lattice sums
+//   D1, S1, g1 (get_damat_dir), D2, S2 (get_damat_dc_dir), D3, S3 (get_dcpair_dir);   all S are symmetric.
+// ---------------------------------------------------------------------------------------------
+struct BcSums {
+   double d1[3], s1[6], g1, d2[3], s2[6], d3[3], s3[6];
+};
+
+__device__ __forceinline__ void bc_dir_deriv_sums(const double* __restrict__ dt, double vx, double vy, double vz,
+                                                  double gam, double kbc, double rv, double sc, double w, BcSums& o) {
+   const double gam2 = gam * gam;
+   for (int itr = 0; itr < NDT; ++itr) {
+      const double x = vx + dt[3 * itr], y = vy + dt[3 * itr + 1], z = vz + dt[3 * itr + 2];
+      const double r2 = x * x + y * y + z * z;
+      const double r1 = sqrt(r2);
+      if (r1 < EPS_SQRT) continue;
+      const double t = kbc * (r1 - rv) / rv;
+      if (t > PRUNE_ARG) continue;  // capacity and its derivative vanish to double precision
+      const double c = sc * 0.5 * (1.0 + erf(-t));                             // get_cpair
+      const double dc = -sc * kbc * exp(-(t * t)) / (SQRTPI * rv) / r1;        // get_dcpair: gradient = dc * vec
+      const double e = exp(-r2 * gam2), ef = erf(r1 * gam);
+      const double gtmp = 2.0 * gam * e / (SQRTPI * r2) - ef / (r2 * r1);
+      const double f1 = -c * gtmp * w, f2 = ef / r1 * dc * w, f3 = dc * w;
+      const double xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+      o.d1[0] += f1 * x; o.d1[1] += f1 * y; o.d1[2] += f1 * z;
+      o.s1[0] += f1 * xx; o.s1[1] += f1 * xy; o.s1[2] += f1 * xz; o.s1[3] += f1 * yy; o.s1[4] += f1 * yz; o.s1[5] += f1 * zz;
+      o.g1 += c * 2.0 * e / SQRTPI * w;
+      o.d2[0] += f2 * x; o.d2[1] += f2 * y; o.d2[2] += f2 * z;
+      o.s2[0] += f2 * xx; o.s2[1] += f2 * xy; o.s2[2] += f2 * xz; o.s2[3] += f2 * yy; o.s2[4] += f2 * yz; o.s2[5] += f2 * zz;
+      o.d3[0] += f3 * x; o.d3[1] += f3 * y; o.d3[2] += f3 * z;
+      o.s3[0] += f3 * xx; o.s3[1] += f3 * xy; o.s3[2] += f3 * xz; o.s3[3] += f3 * yy; o.s3[4] += f3 * yz; o.s3[5] += f3 * zz;
+   }
+}
+
+// symmetric 6-vector (xx, xy, xz, yy, yz, zz) -> entry k = a + 3 b of the 3 x 3 array
+__device__ __forceinline__ double sym9(const double* s6, int k) {
+   constexpr int map[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+   return s6[map[k]];
+}
+
+// per-atom accumulators of the derivative path
+struct BcDerivAcc {
+   double* bdiag;   // [3 nat]  diagonal blocks B(3i+c, i)
+   double* ga;      // [3 nat]  dadr q (with atrace on the diagonal)
+   double* gx;      // [3 nat]  dxdr q
+   double* dadL;    // [9 nat]
+   double* dxdL;    // [9 nat]
+   double* dcdrd;   // [3 nat]  dcdr(:, i, i)
+   double* dcdLs;   // [9 nat]  dcdL(:, :, i)
+};
+
+__global__ void __launch_bounds__(256) bc_pbc_deriv_tiles_kernel(int nat, const double* __restrict__ xyz,
+                                                                 const int* __restrict__ id,
+                                                                 const double* __restrict__ atoms,
+                                                                 const double* __restrict__ rvdw, int nid, double kbc,
+                                                                 const double* __restrict__ q,
+                                                                 const double* __restrict__ dcndr,
+                                                                 const double* __restrict__ dcndL, PbcDev pb,
+                                                                 double* __restrict__ B, int64_t ldb, BcDerivAcc acc) {
+   __shared__ double sdt[3 * NDT];
+   __shared__ double swt[3 * 27];
+   for (int k = threadIdx.x; k < 3 * NDT; k += blockDim.x) sdt[k] = pb.dtrans[k];
+   for (int k = threadIdx.x; k < 3 * pb.nw; k += blockDim.x) swt[k] = pb.wtrans[k];
+   __syncthreads();
+   int ti, tj;
+   tile_coords(blockIdx.x, ti, tj);
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   const int j = tj * 32 + lane;
+   const size_t n3 = 3 * (size_t)nat;
+   for (int rr = 0; rr < 4; ++rr) {
+      const int i = ti * 32 + warp + 8 * rr;
+      if (i >= nat || j >= i) continue;  // strictly lower triangle
+      const double vx = xyz[3 * j] - xyz[3 * i], vy = xyz[3 * j + 1] - xyz[3 * i + 1], vz = xyz[3 * j + 2] - xyz[3 * i + 2];
+      const double ri = atoms[5 * i], dri = atoms[5 * i + 1], hi = atoms[5 * i + 2], xti = atoms[5 * i + 3];
+      const double rj = atoms[5 * j], drj = atoms[5 * j + 1], hj = atoms[5 * j + 2], xtj = atoms[5 * j + 3];
+      const double gam = 1.0 / sqrt(ri * ri + rj * rj);
+      const double sc = sqrt(atoms[5 * i + 4] * atoms[5 * j + 4]);
+      const double rv = rvdw[(id[i] - 1) + (size_t)nid * (id[j] - 1)];
+      const unsigned mask = wsc_select(swt, pb.nw, -vx, -vy, -vz);  // wsc vec = r_i - r_j
+      const double wsw = 1.0 / (double)__popc(mask);
+      BcSums sm = {};
+      for (unsigned m = mask; m; m &= m - 1) {
+         const int p = __ffs(m) - 1;
+         bc_dir_deriv_sums(sdt, vx + swt[3 * p], vy + swt[3 * p + 1], vz + swt[3 * p + 2], gam, kbc, rv, sc, wsw, sm);
+      }
+      const double qi = q[i], qj = q[j], gam3 = gam * gam * gam;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+         // the two columns of the pair's dgamdr that the reference reads (eeqbc.f90:847-850, 873-878)
+         const double dgi = -(ri * dri * dcndr[c + 3 * (i + (size_t)nat * i)] + rj * drj * dcndr[c + 3 * (i + (size_t)nat * j)]) * gam3;
+         const double dgj = -(ri * dri * dcndr[c + 3 * (j + (size_t)nat * i)] + rj * drj * dcndr[c + 3 * (j + (size_t)nat * j)]) * gam3;
+         const double a_ij = -sm.d1[c] * qi - sm.g1 * qi * dgi + qi * sm.d2[c] - hj * qj * sm.d3[c];  // dadr(c, i, j)
+         const double a_ji = +sm.d1[c] * qj - sm.g1 * qj * dgj - qj * sm.d2[c] + hi * qi * sm.d3[c];  // dadr(c, j, i)
+         const double at_i = -sm.d1[c] * qj + sm.g1 * qj * dgj + qj * sm.d2[c];                      // atrace(c, i)
+         const double at_j = +sm.d1[c] * qi + sm.g1 * qi * dgi - qi * sm.d2[c];                      // atrace(c, j)
+         const double x_off = (xti - xtj) * sm.d3[c];                                               // dxdr(c, i, j) = dxdr(c, j, i)
+         const double x_ii = xtj * sm.d3[c], x_jj = -xti * sm.d3[c];                                // dxdr(c, i, i), dxdr(c, j, j)
+         if (B) {
+            B[(3 * (size_t)i + c) + (size_t)j * ldb] += a_ij - x_off;
+            B[(3 * (size_t)j + c) + (size_t)i * ldb] += a_ji - x_off;
+         }
+         atomicAdd(acc.bdiag + 3 * i + c, at_i - x_ii);
+         atomicAdd(acc.bdiag + 3 * j + c, at_j - x_jj);
+         atomicAdd(acc.ga + 3 * i + c, a_ij * qj + at_i * qi);
+         atomicAdd(acc.ga + 3 * j + c, a_ji * qi + at_j * qj);
+         atomicAdd(acc.gx + 3 * i + c, x_off * qj + x_ii * qi);
+         atomicAdd(acc.gx + 3 * j + c, x_off * qi + x_jj * qj);
+         atomicAdd(acc.dcdrd + 3 * i + c, -sm.d3[c]);
+         atomicAdd(acc.dcdrd + 3 * j + c, +sm.d3[c]);
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+         const double dgl = -(ri * dri * dcndL[k + 9 * (size_t)i] + rj * drj * dcndL[k + 9 * (size_t)j]) * gam3;
+         const double s1 = sym9(sm.s1, k), s2 = sym9(sm.s2, k), s3 = sym9(sm.s3, k);
+         atomicAdd(acc.dadL + 9 * (size_t)j + k, s1 * qi - sm.g1 * qi * dgl - qi * s2);
+         atomicAdd(acc.dadL + 9 * (size_t)i + k, s1 * qj - sm.g1 * qj * dgl - qj * s2);
+         atomicAdd(acc.dxdL + 9 * (size_t)i + k, -s3 * xtj);
+         atomicAdd(acc.dxdL + 9 * (size_t)j + k, -s3 * xti);
+         atomicAdd(acc.dcdLs + 9 * (size_t)i + k, s3);
+         atomicAdd(acc.dcdLs + 9 * (size_t)j + k, s3);
+      }
+      (void)n3;
+   }
+}
+
+// per atom (one warp): self-image sums, the diagonal / per-atom terms of get_damat_3d and of the periodic
+// get_xvec_derivs, the dense part of dxdL (dtmpdL C).  Runs after the pair kernel (needs the complete
+// dcdr(:, i, i), dcdL(:, :, i)).
+__global__ void __launch_bounds__(256) bc_pbc_deriv_self_kernel(int nat, int64_t npad, const int* __restrict__ id,
+                                                                const double* __restrict__ atoms,
+                                                                const double* __restrict__ rvdw, int nid, double kbc,
+                                                                const double* __restrict__ q, const double* __restrict__ Cm,
+                                                                const double* __restrict__ cself,
+                                                                const double* __restrict__ kcnchi,
+                                                                const double* __restrict__ kqchi,
+                                                                const double* __restrict__ kqeta,
+                                                                const double* __restrict__ dcndL,
+                                                                const double* __restrict__ dqlocdL, PbcDev pb,
+                                                                BcDerivAcc acc) {
+   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   const int lane = threadIdx.x & 31;
+   if (i >= nat) return;
+   const double ri = atoms[5 * i], dri = atoms[5 * i + 1], hi = atoms[5 * i + 2], xti = atoms[5 * i + 3], capi = atoms[5 * i + 4];
+   const double qi = q[i];
+   const double gam = 1.0 / sqrt(2.0 * ri * ri);
+   const double rv = rvdw[(id[i] - 1) + (size_t)nid * (id[i] - 1)];
+   const unsigned mask = wsc_select(pb.wtrans, pb.nw, 0.0, 0.0, 0.0);
+   const double wsw = 1.0 / (double)__popc(mask);
+   // self images, the 125 translations split over the lanes (same sums as bc_dir_deriv_sums)
+   double s1[6] = {0, 0, 0, 0, 0, 0}, s2[6] = {0, 0, 0, 0, 0, 0}, s3[6] = {0, 0, 0, 0, 0, 0}, g1 = 0.0;
+   const double gam2 = gam * gam;
+   for (unsigned m = mask; m; m &= m - 1) {
+      const int p = __ffs(m) - 1;
+      for (int itr = lane; itr < NDT; itr += 32) {
+         const double x = pb.wtrans[3 * p] + pb.dtrans[3 * itr], y = pb.wtrans[3 * p + 1] + pb.dtrans[3 * itr + 1],
+                      z = pb.wtrans[3 * p + 2] + pb.dtrans[3 * itr + 2];
+         const double r2 = x * x + y * y + z * z, r1 = sqrt(r2);
+         if (r1 < EPS_SQRT) continue;
+         const double t = kbc * (r1 - rv) / rv;
+         const double c = capi * 0.5 * (1.0 + erf(-t));
+         const double dc = -capi * kbc * exp(-(t * t)) / (SQRTPI * rv) / r1;
+         const double e = exp(-r2 * gam2), ef = erf(r1 * gam);
+         const double gtmp = 2.0 * gam * e / (SQRTPI * r2) - ef / (r2 * r1);
+         const double f1 = -c * gtmp * wsw, f2 = ef / r1 * dc * wsw, f3 = dc * wsw;
+         const double xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+         s1[0] += f1 * xx; s1[1] += f1 * xy; s1[2] += f1 * xz; s1[3] += f1 * yy; s1[4] += f1 * yz; s1[5] += f1 * zz;
+         s2[0] += f2 * xx; s2[1] += f2 * xy; s2[2] += f2 * xz; s2[3] += f2 * yy; s2[4] += f2 * yz; s2[5] += f2 * zz;
+         s3[0] += f3 * xx; s3[1] += f3 * xy; s3[2] += f3 * xz; s3[3] += f3 * yy; s3[4] += f3 * yz; s3[5] += f3 * zz;
+         g1 += c * 2.0 * e / SQRTPI * wsw;
+      }
+   }
+#pragma unroll
+   for (int k = 0; k < 6; ++k) { s1[k] = warp_sum_p(s1[k]); s2[k] = warp_sum_p(s2[k]); s3[k] = warp_sum_p(s3[k]); }
+   g1 = warp_sum_p(g1);
+   // dense part of dxdL: dxdL(:, :, i) = sum_a dtmpdL(:, :, a) C(a, i)   (eeqbc.f90:362)
+   double dl[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+   for (int a = lane; a < nat; a += 32) {
+      const double ca = Cm[a + (int64_t)i * npad];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) dl[k] += (kcnchi[a] * dcndL[k + 9 * (size_t)a] + kqchi[a] * dqlocdL[k + 9 * (size_t)a]) * ca;
+   }
+#pragma unroll
+   for (int k = 0; k < 9; ++k) dl[k] = warp_sum_p(dl[k]);
+   if (lane != 0) return;
+   const double cii = Cm[i + (int64_t)i * npad];
+   const double dtw = -SQRT2PI * dri / (ri * ri) * qi;
+   const double s1c = kqeta[i] * qi * cii, s2c = dtw * cii, cs = cself[i];
+#pragma unroll
+   for (int k = 0; k < 9; ++k) {
+      const double dcdl = acc.dcdLs[9 * (size_t)i + k] + sym9(s3, k);  // + positive diagonal elements (self images)
+      const double cnl = dcndL[k + 9 * (size_t)i], qll = dqlocdL[k + 9 * (size_t)i];
+      acc.dadL[9 * (size_t)i + k] += sym9(s1, k) * qi - dtw * cnl * g1 - qi * sym9(s2, k)  // self images
+                                     + s1c * qll + s2c * cnl                               // hardness, charge width
+                                     + hi * qi * dcdl;                                     // capacitance
+      acc.dxdL[9 * (size_t)i + k] += dl[k] - sym9(s3, k) * xti + xti * dcdl - cs * (kcnchi[i] * cnl + kqchi[i] * qll);
+   }
+#pragma unroll
+   for (int c = 0; c < 3; ++c) {
+      const double dd = acc.dcdrd[3 * i + c];
+      // dadr(c, i, i) += h_i q_i dcdr(c, i, i); dxdr(c, i, i) += xtmp_i dcdr(c, i, i)   (the atrace / dadr self terms cancel)
+      acc.bdiag[3 * i + c] += hi * qi * dd - xti * dd;
+      acc.ga[3 * i + c] += hi * qi * dd * qi;
+      acc.gx[3 * i + c] += xti * dd * qi;
+   }
+}
+
+// thread per row r = 3k+c: the column-scaled terms of dadr / dxdr, the diagonal fold, ga / gx / bz.
+//   dadr(r, i) += s1_i dqlocdr(r, i) + s2_i dcndr(r, i),  s1_i = kqeta_i q_i C_ii, s2_i = -sqrt(2/pi) drad_i / rad_i^2 q_i C_ii
+//   dxdr(r, i) += -cself_i (kcnchi_i dcndr(r, i) + kqchi_i dqlocdr(r, i))           (self images, eeqbc.f90:407-416)
+//   gx(r)      += sum_a dtmpdr(r, a) (C q)_a                                          (the dense part, contracted)
+__global__ void __launch_bounds__(128) bc_pbc_deriv_rows_kernel(int nat, int64_t npad, const double* __restrict__ atoms,
+                                                                const double* __restrict__ q, const double* __restrict__ cq,
+                                                                const double* __restrict__ Cm,
+                                                                const double* __restrict__ cself,
+                                                                const double* __restrict__ kcnchi,
+                                                                const double* __restrict__ kqchi,
+                                                                const double* __restrict__ kqeta,
+                                                                const double* __restrict__ dcndr,
+                                                                const double* __restrict__ dqlocdr,
+                                                                const double* __restrict__ zvec, double* __restrict__ B,
+                                                                int64_t ldb, BcDerivAcc acc, double* __restrict__ bz) {
+   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const size_t n3 = 3 * (size_t)nat;
+   if (r >= (int64_t)n3) return;
+   const int k = (int)(r / 3);
+   double ga = 0.0, gx = 0.0, z = 0.0;
+   for (int i = 0; i < nat; ++i) {
+      const double ri = atoms[5 * i], dri = atoms[5 * i + 1], qi = q[i];
+      const double cii = Cm[i + (int64_t)i * npad];
+      const double cn = dcndr[r + n3 * i], ql = dqlocdr[r + n3 * i];
+      const double v = kqeta[i] * qi * cii * ql + (-SQRT2PI * dri / (ri * ri) * qi * cii) * cn;
+      const double u = -cself[i] * (kcnchi[i] * cn + kqchi[i] * ql);
+      ga = fma(v, qi, ga);
+      gx = fma(u, qi, gx);
+      gx = fma(kcnchi[i] * cn + kqchi[i] * ql, cq[i], gx);
+      if (B) {
+         double b = B[r + (size_t)i * ldb] + v - u;
+         if (i == k) b += acc.bdiag[r];
+         B[r + (size_t)i * ldb] = b;
+         z = fma(b, zvec[i], z);
+      }
+   }
+   acc.ga[r] += ga;
+   acc.gx[r] += gx;
+   if (B) bz[r] = z;
+}
+
+void bc_pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* atoms, const double* rvdw, int nid, double kbc,
+                   const double* kcnchi, const double* kqchi, const double* kqeta, const double* q, const double* cq,
+                   const double* Cm, const double* cself, const double* dcndr, const double* dcndL, const double* dqlocdr,
+                   const double* dqlocdL, const double* zvec, PbcWork& work, double* B, int64_t ldb, double* ga, double* gx,
+                   double* dadL, double* dxdL, double* bz) {
+   auto* st = static_cast<PbcState*>(work.state);
+   const int nat = mol.nat;
+   BcDerivAcc acc;
+   acc.bdiag = ctx->alloc_zero<double>((size_t)3 * nat);
+   acc.dcdrd = ctx->alloc_zero<double>((size_t)3 * nat);
+   acc.dcdLs = ctx->alloc_zero<double>((size_t)9 * nat);
+   acc.ga = ga;
+   acc.gx = gx;
+   acc.dadL = dadL;
+   acc.dxdL = dxdL;
+   const int nt = (nat + 31) / 32;
+   MCHRG_LAUNCH(ctx, bc_pbc_deriv_tiles_kernel, (unsigned)(nt * (nt + 1) / 2), 256, 0, nat, mol.xyz, mol.id, atoms, rvdw, nid,
+                kbc, q, dcndr, dcndL, st->pb, B, ldb, acc);
+   MCHRG_LAUNCH(ctx, bc_pbc_deriv_self_kernel, (unsigned)((nat + 7) / 8), 256, 0, nat, work.npad, mol.id, atoms, rvdw, nid,
+                kbc, q, Cm, cself, kcnchi, kqchi, kqeta, dcndL, dqlocdL, st->pb, acc);
+   MCHRG_LAUNCH(ctx, bc_pbc_deriv_rows_kernel, (unsigned)((3 * (int64_t)nat + 127) / 128), 128, 0, nat, work.npad, atoms, q, cq,
+                Cm, cself, kcnchi, kqchi, kqeta, dcndr, dqlocdr, zvec, B, ldb, acc, bz);
+}
+
 void pbc_symv(mchrg_b200_context* ctx, int nat, const double* A, int64_t ld, const double* x, double* y) {
    MCHRG_LAUNCH(ctx, symv_full_kernel, (unsigned)((nat + 31) / 32), 256, 0, nat, A, ld, x, y);
 }

@@ -43,4 +43,14 @@ void bc_pbc_matrices(mchrg_b200_context* ctx, const DevMol& mol, const double* a
 // xvec(a) -= cself(a) xtmp(a)   (the periodic part of get_xvec, eeqbc.f90:283-311)
 void bc_pbc_xvec_fix(mchrg_b200_context* ctx, int nat, const double* atoms, const double* cself, double* xvec);
 
+// Periodic EEQ-BC derivatives (get_damat_3d, get_dcmat_3d, periodic get_xvec_derivs): adds everything except the
+// dense part dtmpdr C (expected in B already, scaled by -1) to B = dadr + diag(atrace) - dxdr (may be null),
+// accumulates ga = dadr q, gx = dxdr q (zero-initialised by the caller), writes dadL, dxdL per atom (zero-initialised
+// by the caller) and bz = B z for the rows < 3 nat.  cq = C q, cself from bc_pbc_matrices.
+void bc_pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* atoms, const double* rvdw, int nid, double kbc,
+                   const double* kcnchi, const double* kqchi, const double* kqeta, const double* q, const double* cq,
+                   const double* Cm, const double* cself, const double* dcndr, const double* dcndL, const double* dqlocdr,
+                   const double* dqlocdL, const double* zvec, PbcWork& work, double* B, int64_t ldb, double* ga, double* gx,
+                   double* dadL, double* dxdL, double* bz);
+
 }  // namespace mchrg

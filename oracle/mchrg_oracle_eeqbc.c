@@ -15,10 +15,9 @@
  * PARITY UNPINNED against reference numbers: the EEQ-BC known answers of the reference need the
  * pairwise D3 vdW radii and Pauling EN tables of mctc-lib, which are not available offline.  The
  * restatement is checked by the reference's finite-difference methodology (tests/test_oracle_eeqbc.py).
- * Periodic EEQ-BC: the charge / energy path is restated (get_cmat_3d eeqbc.f90:1065-1128, get_cpair_dir :1145-1165,
- * the periodic part of get_xvec :283-311, get_amat_3d / get_amat_dir_3d :532-627); the periodic DERIVATIVE routines
- * (get_damat_3d, get_dcmat_3d, periodic get_xvec_derivs) are not restated -- a periodic solve with derivative
- * outputs returns -1.
+ * Periodic EEQ-BC is restated as well: get_cmat_3d eeqbc.f90:1065-1128, get_cpair_dir :1145-1165, the periodic parts
+ * of get_xvec :283-311 and get_xvec_derivs :364-418, get_amat_3d / get_amat_dir_3d :532-627, get_damat_3d :789-924 with
+ * get_damat_dir :926-957 and get_damat_dc_dir :959-985, get_dcmat_3d :1243-1313, get_dcpair_dir :1315-1333.
  */
 #include "mchrg_oracle.h"
 
@@ -126,6 +125,66 @@ static void cmat_3d(const orc_eeqbc_model* m, const orc_mol* mol, const orc_wsc*
    cmat[nat + (size_t)nd * nat] = 1.0;
 }
 
+/* get_dcpair_dir, eeqbc.f90:1315-1333 */
+static void dcpair_dir(double kbc, const double* rij, const double* dtrans, double rvdw, double capi, double capj,
+                       double* dg, double* ds) {
+   memset(dg, 0, 3 * sizeof(double));
+   memset(ds, 0, 9 * sizeof(double));
+   for (int itr = 0; itr < 125; ++itr) {
+      double vec[3], gt[3], st[9];
+      for (int c = 0; c < 3; ++c) vec[c] = rij[c] + dtrans[3 * itr + c];
+      const double r1 = sqrt(vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2]);
+      if (r1 < BC_EPS) continue;
+      dcpair(kbc, vec, rvdw, capi, capj, gt, st);
+      for (int c = 0; c < 3; ++c) dg[c] += gt[c];
+      for (int k = 0; k < 9; ++k) ds[k] += st[k];
+   }
+}
+
+/* get_dcmat_3d, eeqbc.f90:1243-1313 */
+static void dcmat_3d(const orc_eeqbc_model* m, const orc_mol* mol, const orc_wsc* wsc, double* dcdr, double* dcdL) {
+   const int nat = mol->nat, nd = nat + 1, ntw = wsc->ntr;
+   double dtrans[3 * 125];
+   orc_get_dir_trans(mol->lattice, dtrans);
+   memset(dcdr, 0, sizeof(double) * 3 * (size_t)nat * nd);
+   memset(dcdL, 0, sizeof(double) * 9 * (size_t)nd);
+   for (int iat = 0; iat < nat; ++iat) {
+      const double capi = m->cap[mol->id[iat] - 1];
+      for (int jat = 0; jat < iat; ++jat) {
+         const double capj = m->cap[mol->id[jat] - 1];
+         const double rvdw = rvdw_of(m, mol, iat, jat);
+         const int nimg = wsc->nimg[jat + (size_t)nat * iat];
+         const int* tri = wsc->tridx + (size_t)ntw * (jat + (size_t)nat * iat);
+         const double wsw = 1.0 / (double)nimg;
+         for (int img = 0; img < nimg; ++img) {
+            const double* t = wsc->trans + 3 * (tri[img] - 1);
+            double vec[3], dG[3], dS[9];
+            for (int c = 0; c < 3; ++c) vec[c] = mol->xyz[3 * jat + c] - mol->xyz[3 * iat + c] + t[c];
+            dcpair_dir(m->kbc, vec, dtrans, rvdw, capi, capj, dG, dS);
+            for (int c = 0; c < 3; ++c) {
+               dcdr[c + 3 * ((size_t)iat + (size_t)nat * jat)] += +dG[c] * wsw;
+               dcdr[c + 3 * ((size_t)jat + (size_t)nat * iat)] += -dG[c] * wsw;
+               dcdr[c + 3 * ((size_t)iat + (size_t)nat * iat)] += -dG[c] * wsw;
+               dcdr[c + 3 * ((size_t)jat + (size_t)nat * jat)] += +dG[c] * wsw;
+            }
+            for (int k = 0; k < 9; ++k) {
+               dcdL[k + 9 * (size_t)jat] += dS[k] * wsw;
+               dcdL[k + 9 * (size_t)iat] += dS[k] * wsw;
+            }
+         }
+      }
+      const double rvdw = rvdw_of(m, mol, iat, iat);
+      const int nimg = wsc->nimg[iat + (size_t)nat * iat];
+      const int* tri = wsc->tridx + (size_t)ntw * (iat + (size_t)nat * iat);
+      const double wsw = 1.0 / (double)nimg;
+      for (int img = 0; img < nimg; ++img) {
+         double dG[3], dS[9];
+         dcpair_dir(m->kbc, wsc->trans + 3 * (tri[img] - 1), dtrans, rvdw, capi, capi, dG, dS);
+         for (int k = 0; k < 9; ++k) dcdL[k + 9 * (size_t)iat] += dS[k] * wsw; /* positive diagonal elements */
+      }
+   }
+}
+
 /* get_cmat_0d, eeqbc.f90:1015-1063 */
 static void cmat_0d(const orc_eeqbc_model* m, const orc_mol* mol, double* cmat) {
    const int nat = mol->nat, nd = nat + 1;
@@ -185,9 +244,14 @@ static void bc_update(const orc_eeqbc_model* m, const orc_mol* mol, bc_cache* c,
    c->xtmp = (double*)calloc(nd, sizeof(double));
    c->cmat = (double*)malloc(sizeof(double) * (size_t)nd * nd);
    c->periodic = mol->periodic[0] || mol->periodic[1] || mol->periodic[2];
-   if (c->periodic) { /* eeqbc.f90:222-236; the derivative branch (get_dcmat_3d) is not restated */
+   if (c->periodic) { /* eeqbc.f90:222-236 */
       orc_wsc_new(mol, &c->wsc);
       cmat_3d(m, mol, &c->wsc, c->cmat);
+      if (grad) {
+         c->dcdr = (double*)malloc(sizeof(double) * 3 * (size_t)nat * nd);
+         c->dcdL = (double*)malloc(sizeof(double) * 9 * (size_t)nd);
+         dcmat_3d(m, mol, &c->wsc, c->dcdr, c->dcdL);
+      }
       return;
    }
    cmat_0d(m, mol, c->cmat);
@@ -252,6 +316,48 @@ static void bc_get_xvec_derivs(const orc_eeqbc_model* m, const orc_mol* mol, con
    free(dtmpdL);
 #define DCDR(cc, a, b) c->dcdr[(cc) + 3 * ((size_t)(a) + (size_t)nat * (b))]
 #define DXDR(cc, a, b) dxdr[(cc) + 3 * ((size_t)(a) + (size_t)nat * (b))]
+   if (c->periodic) { /* eeqbc.f90:364-418, including its index conventions (nimg(iat, jat) with tridx(img, jat, iat)) */
+      double dtrans[3 * 125];
+      orc_get_dir_trans(mol->lattice, dtrans);
+      const orc_wsc* wsc = &c->wsc;
+      const int ntw = wsc->ntr;
+      for (int iat = 0; iat < nat; ++iat) {
+         const int izp = mol->id[iat] - 1;
+         const double capi = m->cap[izp];
+         for (int jat = 0; jat < nat; ++jat) {
+            const double rvdw = rvdw_of(m, mol, iat, jat);
+            const double capj = m->cap[mol->id[jat] - 1];
+            for (int cc = 0; cc < 3; ++cc) {
+               DXDR(cc, iat, iat) += c->xtmp[jat] * DCDR(cc, iat, jat);
+               DXDR(cc, iat, jat) += (c->xtmp[iat] - c->xtmp[jat]) * DCDR(cc, iat, jat);
+            }
+            const int nimg = wsc->nimg[iat + (size_t)nat * jat];
+            const int* tri = wsc->tridx + (size_t)ntw * (jat + (size_t)nat * iat);
+            const double wsw = 1.0 / (double)nimg;
+            for (int img = 0; img < nimg; ++img) {
+               const double* t = wsc->trans + 3 * (tri[img] - 1);
+               double vec[3], dG[3], dS[9];
+               for (int cc = 0; cc < 3; ++cc) vec[cc] = mol->xyz[3 * jat + cc] - mol->xyz[3 * iat + cc] + t[cc];
+               dcpair_dir(m->kbc, vec, dtrans, rvdw, capi, capj, dG, dS);
+               for (int k = 0; k < 9; ++k) dxdL[k + 9 * (size_t)iat] -= wsw * dS[k] * c->xtmp[jat];
+            }
+         }
+         for (int k = 0; k < 9; ++k) dxdL[k + 9 * (size_t)iat] += c->xtmp[iat] * c->dcdL[k + 9 * (size_t)iat];
+         /* capacitance terms for i = j, T != 0 */
+         const double rvdw = rvdw_of(m, mol, iat, iat);
+         const int nimg = wsc->nimg[iat + (size_t)nat * iat];
+         const int* tri = wsc->tridx + (size_t)ntw * (iat + (size_t)nat * iat);
+         const double wsw = 1.0 / (double)nimg;
+         for (int img = 0; img < nimg; ++img) {
+            const double ctmp = cpair_dir(m->kbc, wsc->trans + 3 * (tri[img] - 1), dtrans, rvdw, capi, capi) * wsw;
+            for (size_t k = 0; k < n3; ++k)
+               dxdr[k + n3 * iat] -= ctmp * (m->kcnchi[izp] * c->dcndr[k + n3 * iat] + m->kqchi[izp] * c->dqlocdr[k + n3 * iat]);
+            for (int k = 0; k < 9; ++k)
+               dxdL[k + 9 * (size_t)iat] -= ctmp * (m->kcnchi[izp] * c->dcndL[k + 9 * (size_t)iat] + m->kqchi[izp] * c->dqlocdL[k + 9 * (size_t)iat]);
+         }
+      }
+      return;
+   }
    for (int iat = 0; iat < nat; ++iat) {
       for (int jat = 0; jat < iat; ++jat) {
          double vec[3];
@@ -476,6 +582,177 @@ static void bc_damat_0d(const orc_eeqbc_model* m, const orc_mol* mol, const bc_c
 #undef DCDR
 }
 
+/* get_damat_dir, eeqbc.f90:926-957 */
+static void damat_dir(const double* rij, const double* dtrans, double capi, double capj, double rvdw, double kbc,
+                      double gam, double* dG, double* dS, double* dgam) {
+   memset(dG, 0, 3 * sizeof(double));
+   memset(dS, 0, 9 * sizeof(double));
+   *dgam = 0.0;
+   const double gam2 = gam * gam;
+   for (int itr = 0; itr < 125; ++itr) {
+      double vec[3];
+      for (int c = 0; c < 3; ++c) vec[c] = rij[c] + dtrans[3 * itr + c];
+      const double r1 = sqrt(vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2]);
+      if (r1 < BC_EPS) continue;
+      const double r2 = r1 * r1;
+      const double cm = cpair(kbc, r1, rvdw, capi, capj);
+      const double gtmp = 2.0 * gam * exp(-r2 * gam2) / (SQRTPI * r2) - erf(r1 * gam) / (r2 * r1);
+      for (int c = 0; c < 3; ++c) dG[c] -= cm * gtmp * vec[c];
+      for (int b = 0; b < 3; ++b)
+         for (int a = 0; a < 3; ++a) dS[a + 3 * b] -= cm * gtmp * vec[b] * vec[a]; /* spread(vec,1,3)*spread(vec,2,3) */
+      *dgam += cm * 2.0 * exp(-gam2 * r2) / SQRTPI;
+   }
+}
+
+/* get_damat_dc_dir, eeqbc.f90:959-985 */
+static void damat_dc_dir(const double* rij, const double* dtrans, double capi, double capj, double rvdw, double kbc,
+                         double gam, double* dG, double* dS) {
+   memset(dG, 0, 3 * sizeof(double));
+   memset(dS, 0, 9 * sizeof(double));
+   for (int itr = 0; itr < 125; ++itr) {
+      double vec[3], gt[3], st[9];
+      for (int c = 0; c < 3; ++c) vec[c] = rij[c] + dtrans[3 * itr + c];
+      const double r1 = sqrt(vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2]);
+      if (r1 < BC_EPS) continue;
+      dcpair(kbc, vec, rvdw, capi, capj, gt, st);
+      const double tmp = erf(gam * r1) / r1;
+      for (int c = 0; c < 3; ++c) dG[c] += tmp * gt[c];
+      for (int k = 0; k < 9; ++k) dS[k] += tmp * st[k];
+   }
+}
+
+/* get_damat_3d, eeqbc.f90:789-924 */
+static void bc_damat_3d(const orc_eeqbc_model* m, const orc_mol* mol, const bc_cache* c, const double* qvec,
+                        double* dadr, double* dadL, double* atrace) {
+   const int nat = mol->nat, nd = nat + 1;
+   const size_t n3 = 3 * (size_t)nat;
+   const double* cmat = c->cmat;
+   const orc_wsc* wsc = &c->wsc;
+   const int ntw = wsc->ntr;
+   double dtrans[3 * 125];
+   orc_get_dir_trans(mol->lattice, dtrans);
+   memset(atrace, 0, sizeof(double) * n3);
+   memset(dadr, 0, sizeof(double) * n3 * nd);
+   memset(dadL, 0, sizeof(double) * 9 * (size_t)nd);
+#define CM(a, b) cmat[(a) + (size_t)nd * (b)]
+#define DADR(cc, a, b) dadr[(cc) + 3 * ((size_t)(a) + (size_t)nat * (b))]
+#define DCN(cc, a, b) c->dcndr[(cc) + 3 * ((size_t)(a) + (size_t)nat * (b))]
+   for (int iat = 0; iat < nat; ++iat) {
+      const int izp = mol->id[iat] - 1;
+      double norm_cn = 1.0 / pow(m->avg_cn[izp], m->norm_exp);
+      const double radi = m->rad[izp] * (1.0 - m->kcnrad * c->cn[iat] * norm_cn);
+      const double dradi = -m->rad[izp] * m->kcnrad * norm_cn;
+      const double capi = m->cap[izp];
+      for (int jat = 0; jat < iat; ++jat) {
+         const int jzp = mol->id[jat] - 1;
+         const double capj = m->cap[jzp];
+         const double rvdw = rvdw_of(m, mol, iat, jat);
+         norm_cn = 1.0 / pow(m->avg_cn[jzp], m->norm_exp);
+         const double radj = m->rad[jzp] * (1.0 - m->kcnrad * c->cn[jat] * norm_cn);
+         const double dradj = -m->rad[jzp] * m->kcnrad * norm_cn;
+         const double gam = 1.0 / sqrt(radi * radi + radj * radj);
+         const double gam3 = pow(gam, 3.0);
+         double dgam_i[3], dgam_j[3], dgamdL[9];
+         for (int cc = 0; cc < 3; ++cc) { /* the two columns of dgamdr that are read */
+            dgam_i[cc] = -(radi * dradi * DCN(cc, iat, iat) + radj * dradj * DCN(cc, iat, jat)) * gam3;
+            dgam_j[cc] = -(radi * dradi * DCN(cc, jat, iat) + radj * dradj * DCN(cc, jat, jat)) * gam3;
+         }
+         for (int k = 0; k < 9; ++k)
+            dgamdL[k] = -(radi * dradi * c->dcndL[k + 9 * (size_t)iat] + radj * dradj * c->dcndL[k + 9 * (size_t)jat]) * gam3;
+         const int nimg = wsc->nimg[jat + (size_t)nat * iat];
+         const int* tri = wsc->tridx + (size_t)ntw * (jat + (size_t)nat * iat);
+         const double wsw = 1.0 / (double)nimg;
+         for (int img = 0; img < nimg; ++img) {
+            const double* t = wsc->trans + 3 * (tri[img] - 1);
+            double vec[3], dG[3], dS[9], dgam;
+            for (int cc = 0; cc < 3; ++cc) vec[cc] = mol->xyz[3 * jat + cc] - mol->xyz[3 * iat + cc] + t[cc];
+            damat_dir(vec, dtrans, capi, capj, rvdw, m->kbc, gam, dG, dS, &dgam);
+            for (int cc = 0; cc < 3; ++cc) dG[cc] *= wsw;
+            for (int k = 0; k < 9; ++k) dS[k] *= wsw;
+            dgam *= wsw;
+            /* explicit derivative */
+            for (int cc = 0; cc < 3; ++cc) {
+               atrace[cc + 3 * iat] += -dG[cc] * qvec[jat];
+               atrace[cc + 3 * jat] += +dG[cc] * qvec[iat];
+               DADR(cc, iat, jat) += -dG[cc] * qvec[iat];
+               DADR(cc, jat, iat) += +dG[cc] * qvec[jat];
+            }
+            for (int k = 0; k < 9; ++k) {
+               dadL[k + 9 * (size_t)jat] += dS[k] * qvec[iat];
+               dadL[k + 9 * (size_t)iat] += dS[k] * qvec[jat];
+            }
+            /* effective charge width derivative */
+            for (int cc = 0; cc < 3; ++cc) {
+               atrace[cc + 3 * iat] += +dgam * qvec[jat] * dgam_j[cc];
+               atrace[cc + 3 * jat] += +dgam * qvec[iat] * dgam_i[cc];
+               DADR(cc, iat, jat) += -dgam * qvec[iat] * dgam_i[cc];
+               DADR(cc, jat, iat) += -dgam * qvec[jat] * dgam_j[cc];
+            }
+            for (int k = 0; k < 9; ++k) {
+               dadL[k + 9 * (size_t)iat] += -dgam * qvec[jat] * dgamdL[k];
+               dadL[k + 9 * (size_t)jat] += -dgam * qvec[iat] * dgamdL[k];
+            }
+            damat_dc_dir(vec, dtrans, capi, capj, rvdw, m->kbc, gam, dG, dS);
+            for (int cc = 0; cc < 3; ++cc) dG[cc] *= wsw;
+            for (int k = 0; k < 9; ++k) dS[k] *= wsw;
+            /* capacitance derivative, off-diagonal */
+            for (int cc = 0; cc < 3; ++cc) {
+               atrace[cc + 3 * iat] += +qvec[jat] * dG[cc];
+               atrace[cc + 3 * jat] += -qvec[iat] * dG[cc];
+               DADR(cc, jat, iat) += -qvec[jat] * dG[cc];
+               DADR(cc, iat, jat) += +qvec[iat] * dG[cc];
+            }
+            for (int k = 0; k < 9; ++k) {
+               dadL[k + 9 * (size_t)jat] += -qvec[iat] * dS[k];
+               dadL[k + 9 * (size_t)iat] += -qvec[jat] * dS[k];
+            }
+            dcpair_dir(m->kbc, vec, dtrans, rvdw, capi, capj, dG, dS);
+            for (int cc = 0; cc < 3; ++cc) dG[cc] *= wsw;
+            /* capacitance derivative, diagonal */
+            double dtmp = (m->eta[izp] + m->kqeta[izp] * c->qloc[iat] + SQRT2PI / radi) * qvec[iat];
+            for (int cc = 0; cc < 3; ++cc) DADR(cc, jat, iat) += +dtmp * dG[cc];
+            dtmp = (m->eta[jzp] + m->kqeta[jzp] * c->qloc[jat] + SQRT2PI / radj) * qvec[jat];
+            for (int cc = 0; cc < 3; ++cc) DADR(cc, iat, jat) += -dtmp * dG[cc];
+         }
+      }
+      /* diagonal explicit, charge width, and capacitance derivative terms */
+      const double gam = 1.0 / sqrt(2.0 * radi * radi);
+      double dtmp = -SQRT2PI * dradi / (radi * radi) * qvec[iat];
+      const double rvdw = rvdw_of(m, mol, iat, iat);
+      const int nimg = wsc->nimg[iat + (size_t)nat * iat];
+      const int* tri = wsc->tridx + (size_t)ntw * (iat + (size_t)nat * iat);
+      const double wsw = 1.0 / (double)nimg;
+      for (int img = 0; img < nimg; ++img) {
+         const double* vec = wsc->trans + 3 * (tri[img] - 1);
+         double dG[3], dS[9], dgam;
+         damat_dir(vec, dtrans, capi, capi, rvdw, m->kbc, gam, dG, dS, &dgam);
+         dgam *= wsw;
+         for (int k = 0; k < 9; ++k) dadL[k + 9 * (size_t)iat] += dS[k] * wsw * qvec[iat];
+         for (int cc = 0; cc < 3; ++cc) {
+            atrace[cc + 3 * iat] += dtmp * DCN(cc, iat, iat) * dgam;
+            DADR(cc, iat, iat) += -dtmp * DCN(cc, iat, iat) * dgam;
+         }
+         for (int k = 0; k < 9; ++k) dadL[k + 9 * (size_t)iat] += -dtmp * c->dcndL[k + 9 * (size_t)iat] * dgam;
+         damat_dc_dir(vec, dtrans, capi, capi, rvdw, m->kbc, gam, dG, dS);
+         for (int k = 0; k < 9; ++k) dadL[k + 9 * (size_t)iat] += -qvec[iat] * dS[k] * wsw;
+      }
+      /* hardness derivative */
+      dtmp = m->kqeta[izp] * qvec[iat] * CM(iat, iat);
+      for (size_t k = 0; k < n3; ++k) dadr[k + n3 * iat] += dtmp * c->dqlocdr[k + n3 * iat];
+      for (int k = 0; k < 9; ++k) dadL[k + 9 * (size_t)iat] += dtmp * c->dqlocdL[k + 9 * (size_t)iat];
+      /* effective charge width derivative */
+      dtmp = -SQRT2PI * dradi / (radi * radi) * qvec[iat] * CM(iat, iat);
+      for (size_t k = 0; k < n3; ++k) dadr[k + n3 * iat] += dtmp * c->dcndr[k + n3 * iat];
+      for (int k = 0; k < 9; ++k) dadL[k + 9 * (size_t)iat] += dtmp * c->dcndL[k + 9 * (size_t)iat];
+      dtmp = (m->eta[izp] + m->kqeta[izp] * c->qloc[iat] + SQRT2PI / radi) * qvec[iat];
+      for (int cc = 0; cc < 3; ++cc) DADR(cc, iat, iat) += dtmp * c->dcdr[cc + 3 * ((size_t)iat + (size_t)nat * iat)];
+      for (int k = 0; k < 9; ++k) dadL[k + 9 * (size_t)iat] += dtmp * c->dcdL[k + 9 * (size_t)iat];
+   }
+#undef CM
+#undef DADR
+#undef DCN
+}
+
 /* ---- public wrappers -------------------------------------------------------------------- */
 
 void orc_eeqbc_local_charge(const orc_eeqbc_model* m, const orc_mol* mol, int ntr, const double* trans,
@@ -501,10 +778,11 @@ void orc_eeqbc_get_coulomb_matrix(const orc_eeqbc_model* m, const orc_mol* mol, 
 }
 
 void orc_eeqbc_get_cmat(const orc_eeqbc_model* m, const orc_mol* mol, double* cmat, double* dcdr, double* dcdL) {
-   if (mol->periodic[0] || mol->periodic[1] || mol->periodic[2]) { /* value only */
+   if (mol->periodic[0] || mol->periodic[1] || mol->periodic[2]) {
       orc_wsc wsc;
       orc_wsc_new(mol, &wsc);
       cmat_3d(m, mol, &wsc, cmat);
+      if (dcdr && dcdL) dcmat_3d(m, mol, &wsc, dcdr, dcdL);
       orc_wsc_free(&wsc);
       return;
    }
@@ -530,7 +808,8 @@ void orc_eeqbc_get_coulomb_derivs(const orc_eeqbc_model* m, const orc_mol* mol, 
                                   double* atrace) {
    bc_cache c;
    bc_update(m, mol, &c, cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL);
-   bc_damat_0d(m, mol, &c, qvec, dadr, dadL, atrace);
+   if (c.periodic) bc_damat_3d(m, mol, &c, qvec, dadr, dadL, atrace);
+   else bc_damat_0d(m, mol, &c, qvec, dadr, dadL, atrace);
    bc_free(&c);
 }
 
@@ -539,16 +818,15 @@ static void bc_vt_xvec_derivs(const void* model, const orc_mol* mol, const void*
 }
 static void bc_vt_coulomb_derivs(const void* model, const orc_mol* mol, const void* cache, const double* vrhs,
                                  double* dadr, double* dadL, double* atrace) {
-   bc_damat_0d((const orc_eeqbc_model*)model, mol, (const bc_cache*)cache, vrhs, dadr, dadL, atrace);
+   const bc_cache* c = (const bc_cache*)cache;
+   if (c->periodic) bc_damat_3d((const orc_eeqbc_model*)model, mol, c, vrhs, dadr, dadL, atrace);
+   else bc_damat_0d((const orc_eeqbc_model*)model, mol, c, vrhs, dadr, dadL, atrace);
 }
 
 int orc_eeqbc_solve(const orc_eeqbc_model* m, const orc_mol* mol, const double* cn, const double* qloc,
                     const double* dcndr, const double* dcndL, const double* dqlocdr, const double* dqlocdL,
                     double* energy, double* gradient, double* sigma, double* qvec, double* dqdr, double* dqdL) {
-   const int pbc = mol->periodic[0] || mol->periodic[1] || mol->periodic[2];
-   if (pbc && (gradient || sigma || dqdr || dqdL)) return -1; /* periodic derivatives are not restated */
-   if (pbc) { dcndr = dcndL = dqlocdr = dqlocdL = NULL; }
-   if (!qloc) return -2;                                      /* error stop, eeqbc.f90:202 */
+   if (!qloc) return -2; /* error stop, eeqbc.f90:202 */
    const int nd = mol->nat + 1;
    const orc_solve_vtbl vt = {bc_vt_xvec_derivs, bc_vt_coulomb_derivs};
    bc_cache c;

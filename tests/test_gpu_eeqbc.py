@@ -1,4 +1,4 @@
-"""Parity of the EEQ-BC (non-periodic) device path against the CPU oracle, 1e-10 relative.
+"""Parity of the EEQ-BC device path (molecular and periodic) against the CPU oracle, 1e-10 relative.
 
 The oracle's EEQ-BC branch is "parity unpinned" against reference numbers (tests/test_oracle_eeqbc.py):
 the mctc-lib vdW / EN tables are replaced by fixed synthetic stand-ins shared by both sides."""
@@ -121,8 +121,8 @@ def pbc_cells():
 
 
 @pytest.mark.parametrize("case", pbc_cells(), ids=lambda c: c[0])
-def test_eeqbc_periodic_charges_energy(mc, oracle, case):
-    """Periodic EEQ-BC, charge / energy path (get_cmat_3d, periodic get_xvec, get_amat_3d): device vs oracle."""
+def test_eeqbc_periodic(mc, oracle, case):
+    """Periodic EEQ-BC (get_cmat_3d, get_amat_3d, get_damat_3d, get_dcmat_3d, periodic get_xvec / _derivs): device vs oracle."""
     _, num, xyz, lat, chg = case
     mol = mc.Structure(num, xyz, chg, lattice=lat)
     omol = oracle.Mol(num, xyz, chg, lattice=lat)
@@ -146,7 +146,20 @@ def test_eeqbc_periodic_charges_energy(mc, oracle, case):
     o = oracle.eeqbc_singlepoint(omodel, omol, want=("qvec", "energy"))
     assert close(r.qvec, o.qvec) and close(r.energy, o.energy)
     assert close(mc.get_charges(model, mol), o.qvec)
-    # the periodic derivative routines are not built: refused loudly, not approximated
-    with pytest.raises(mc.MchrgError) as exc:
-        model.singlepoint(mol, want=("qvec", "energy", "gradient"))
-    assert "derivatives" in str(exc.value)
+    # derivatives: get_damat_3d, get_dcmat_3d, periodic get_xvec_derivs
+    odcn = oracle.get_cn(omodel, omol, grad=True)
+    odq = oracle.eeqbc_local_charge(omodel, omol, grad=True)
+    ref = oracle.eeqbc_solve(omodel, omol, odcn[0], odq[0], odcn[1], odcn[2], odq[1], odq[2])
+    assert ref.stat == 0
+    out = dict(energy=np.zeros(n), gradient=np.zeros((n, 3)), sigma=np.zeros((3, 3)), qvec=np.zeros(n),
+               dqdr=np.zeros((n, n, 3)), dqdL=np.zeros((n, 3, 3)))
+    model.solve(mol, odcn[0], odq[0], odcn[1], odcn[2], odq[1], odq[2], **out)
+    for key in ("qvec", "energy", "gradient", "sigma", "dqdr", "dqdL"):
+        assert close(out[key], ref[key]), key
+    r = model.singlepoint(mol, want=("qvec", "energy", "gradient"))
+    o = oracle.eeqbc_singlepoint(omodel, omol, want=("qvec", "energy", "gradient"))
+    for key in ("qvec", "energy", "gradient", "sigma"):
+        assert close(r[key], o[key]), key
+    q, dqdr, dqdL = mc.get_charges(model, mol, grad=True)
+    o = oracle.eeqbc_singlepoint(omodel, omol, want=("qvec", "dqdr"))
+    assert close(q, o.qvec) and close(dqdr, o.dqdr) and close(dqdL, o.dqdL)

@@ -1,4 +1,4 @@
-"""EEQ-BC (non-periodic) oracle: PARITY UNPINNED against reference numbers (the reference's EEQ-BC known
+"""EEQ-BC oracle (molecular and periodic): PARITY UNPINNED against reference numbers (the reference's EEQ-BC known
 answers need mctc-lib's pairwise vdW radii / Pauling EN, not available offline), so the restatement is
 checked with the reference's own finite-difference methodology (test/unit/test_model.f90:89-797,
 thresholds thr2 = sqrt(eps), x3 for dadr) on synthetic vdW / EN tables.
@@ -100,9 +100,10 @@ def test_eeqbc_fd_gradient_dqdr_sigma(oracle):
 
 
 def test_oracle_eeqbc_periodic_charge_path():
+    import numpy as np
     """Periodic EEQ-BC (charge / energy path; parity unpinned against reference numbers like the 0-D branch): in a
     cell much larger than the range of the bond capacity the periodic branch must reproduce the molecular result
-    exactly, lattice translations of single atoms must not change anything, and derivative outputs are refused."""
+    exactly and lattice translations of single atoms must not change anything."""
     import oracle as orc
     from synth import cluster
     num, xyz = cluster(12, 5)
@@ -123,4 +124,38 @@ def test_oracle_eeqbc_periodic_charge_path():
     assert r1.stat == 0 and abs(r1.qvec.sum() - 1.0) < 1e-12
     assert np.abs(r1.qvec - r2.qvec).max() < 1e-12 and abs(r1.energy.sum() - r2.energy.sum()) < 1e-11
     assert np.abs(r1.qvec - r0.qvec).max() > 1e-4  # the images matter in the small cell
-    assert orc.eeqbc_singlepoint(model, m1, want=("qvec", "energy", "gradient")).stat == -1
+
+
+def test_oracle_eeqbc_periodic_fd_gradient_dqdr_sigma(oracle):
+    """Periodic EEQ-BC derivatives (get_damat_3d, get_dcmat_3d, periodic get_xvec_derivs) by the reference's
+    finite-difference methodology: gradient, dq/dr against displaced atoms; sigma, dq/dL against strained cells."""
+    from synth import periodic_cell
+    num, xyz, lat = periodic_cell(2, 4, shear=0.1)
+    mk = lambda x, l: oracle.Mol(num, x, 1.0, lattice=l, periodic=[True] * 3)  # noqa: E731
+    mol = mk(xyz, lat)
+    model = oracle.new_eeqbc2025_model(mol)
+    r = oracle.eeqbc_singlepoint(model, mol, want=("qvec", "energy", "gradient", "dqdr"))
+    assert r.stat == 0 and abs(r.qvec.sum() - 1.0) < 1e-12
+    gs, qs = max(1.0, np.abs(r.gradient).max()), max(1.0, np.abs(r.dqdr).max())
+    for j in range(3):
+        for c in range(3):
+            e, q = [], []
+            for s in (+1, -1):
+                x = xyz.copy()
+                x[j, c] += s * STEP
+                r2 = oracle.eeqbc_singlepoint(model, mk(x, lat), want=("qvec", "energy"))
+                e.append(r2.energy.sum())
+                q.append(r2.qvec)
+            assert abs((e[0] - e[1]) / (2 * STEP) - r.gradient[j, c]) < THR2 * gs, (j, c)
+            assert np.abs((q[0] - q[1]) / (2 * STEP) - r.dqdr[:, j, c]).max() < THR2 * qs, (j, c)
+    for a in range(3):
+        for b in range(3):
+            e, q = [], []
+            for s in (+1, -1):
+                eps = np.eye(3)
+                eps[b, a] += s * STEP
+                r2 = oracle.eeqbc_singlepoint(model, mk(xyz @ eps, lat @ eps), want=("qvec", "energy"))
+                e.append(r2.energy.sum())
+                q.append(r2.qvec)
+            assert abs((e[0] - e[1]) / (2 * STEP) - r.sigma[b, a]) < 3 * THR2 * max(1.0, np.abs(r.sigma).max()), (a, b)
+            assert np.abs((q[0] - q[1]) / (2 * STEP) - r.dqdL[:, b, a]).max() < 3 * THR2 * max(1.0, np.abs(r.dqdL).max())
