@@ -1,4 +1,5 @@
-// EEQ-BC 2025 bond-capacity model, non-periodic, on the device (model/eeqbc.f90).
+// EEQ-BC 2025 bond-capacity model, molecular (0-D) structures, on the device (model/eeqbc.f90); the periodic
+// branch (get_*_3d) lives in eeq_pbc.cu next to the Wigner-Seitz / lattice-sum helpers it shares with EEQ2019.
 //
 // Everything is expressed per ORDERED pair (a, b) so that one warp owns one row a and one thread
 // owns one row of B -- the same decomposition as the EEQ2019 kernels in eeq.cu.  With v = r_b - r_a,

@@ -1,4 +1,4 @@
-// EEQ-BC (model/eeqbc.f90), non-periodic device pieces -- see eeqbc.cu.
+// EEQ-BC (model/eeqbc.f90), molecular (0-D) device pieces -- see eeqbc.cu; the periodic ones are in eeq_pbc.cu.
 #pragma once
 #include "model.cuh"
 
