@@ -71,10 +71,10 @@ num, xyz = cluster(nbc, 20250105)
 mol = mc.Structure(num, xyz, 0.0)
 rvdw, en = orc.synthetic_vdw_en(mol.num)
 model = mc.new_eeqbc2025_model(mol, rvdw, en * 3.98)
-for dq in (False, True):
+for dq in ((False, True) if os.environ.get("NBC_DQ", "1") == "1" else (False,)):
     b = bufs(mol.nat, dq)
     b["_xyz"], b["_id"] = torch.tensor(mol.xyz, device=dev), torch.tensor(mol.id, device=dev)
-    t = timed(lambda: run_sp(model, mol, b))
+    t = timed(lambda: run_sp(model, mol, b), reps=1)
     out[f"eeqbc_n{mol.nat}_{'dqdr' if dq else 'grad'}_s"] = t
     del b
 print(json.dumps(out, indent=1))
