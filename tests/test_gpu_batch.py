@@ -169,3 +169,35 @@ def test_batch_split_path_equals_fused(mc, oracle, monkeypatch):
     mol = oracle.Mol(num[sl], xyz[sl], charge[m])
     r = oracle.eeq_singlepoint(oracle.new_eeq2019_model(mol), mol)
     assert np.abs(split["gradient"][sl] - r.gradient).max() < 1e-10
+
+
+def test_batch_full_size_properties(mc):
+    """BASELINE.json configs[1] at its full size (100 000 molecules of 30-200 atoms, the bench workload), checked
+    through size-independent properties: charge conservation per molecule, vanishing net force (translational
+    invariance), invariance of q and E under a rigid rotation + translation of every molecule with the gradient
+    rotating along, and independence of the batch order."""
+    from synth import batch
+    nmol = 100_000
+    offsets, num, xyz, charge = batch(nmol, 20250102, 30, 200)
+    model = mc.new_eeq2019_batch_model()
+    r = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    assert int((r["status"] != 0).sum()) == 0
+    seg = np.repeat(np.arange(nmol), np.diff(offsets))
+    qsum = np.bincount(seg, weights=r["qvec"], minlength=nmol)
+    assert np.abs(qsum - charge).max() < 1e-11
+    fnet = np.stack([np.bincount(seg, weights=r["gradient"][:, c], minlength=nmol) for c in range(3)], axis=1)
+    assert np.abs(fnet).max() < 1e-10
+    # rigid motion (one rotation for all, a different translation per molecule) and reversed molecule order
+    rng = np.random.default_rng(5)
+    rot, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    shift = rng.uniform(-20.0, 20.0, (nmol, 3))
+    xyz2 = xyz @ rot.T + shift[seg]
+    order = np.arange(nmol)[::-1]
+    sizes = np.diff(offsets)
+    off2 = np.concatenate([[0], np.cumsum(sizes[order])])
+    idx = np.concatenate([np.arange(offsets[m], offsets[m + 1]) for m in order])
+    r2 = mc.singlepoint_batch(model, off2, num[idx], xyz2[idx], charge[order])
+    assert int((r2["status"] != 0).sum()) == 0
+    assert np.abs(r2["qvec"] - r["qvec"][idx]).max() < 1e-11
+    assert np.abs(r2["energy"] - r["energy"][idx]).max() < 1e-11
+    assert np.abs(r2["gradient"] - (r["gradient"] @ rot.T)[idx]).max() < 1e-10

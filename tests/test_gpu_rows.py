@@ -40,3 +40,39 @@ def test_row_block_rejects_bad_ranges(mc):
     for jb, je in ((-1, 5), (5, 5), (3, 21)):
         with pytest.raises(mc.MchrgError):
             mc.singlepoint_rows(model, mol, jb, je)
+
+
+def test_cluster_full_size_properties(mc):
+    """BASELINE.json configs[2] at its full size (N = 16384 cluster) through size-independent properties:
+    charge conservation, vanishing net force and virial symmetry of q + E + gradient, and -- on one 512-row block
+    of dq/dr (the full tensor is 6.4 GB) -- d(sum_i q_i)/dr_j = 0 plus agreement of the block's gradient rows with
+    the full gradient."""
+    import torch
+    from synth import cluster
+    nat = 16384
+    num, xyz = cluster(nat, 20250103)
+    mol = mc.Structure(num, xyz, -1.0)
+    ctx = mc.default_context(0)
+    model = mc.new_eeq2019_model(mol, ctx)
+    dev = torch.device("cuda", 0)
+    f64 = dict(dtype=torch.float64, device=dev)
+    txyz, tid = torch.tensor(mol.xyz, device=dev), torch.tensor(mol.id, device=dev)
+    full = mc.api.SolveResult(cn=torch.empty(nat, **f64), qvec=torch.empty(nat, **f64), energy=torch.zeros(nat, **f64),
+                              gradient=torch.empty(nat, 3, **f64), sigma=torch.zeros(3, 3, **f64))
+    mc.singlepoint_rows(model, mol, 0, nat, out=full, xyz=txyz, id=tid)
+    torch.cuda.synchronize()
+    q, g, sig = full["qvec"].cpu().numpy(), full["gradient"].cpu().numpy(), full["sigma"].cpu().numpy()
+    assert abs(q.sum() + 1.0) < 1e-10
+    assert np.abs(g.sum(axis=0)).max() < 1e-9 * max(1.0, np.abs(g).max())
+    assert np.abs(sig - sig.T).max() < 1e-9 * max(1.0, np.abs(sig).max())
+    jb, je = 4096, 4608
+    blk = mc.api.SolveResult(cn=torch.empty(nat, **f64), qvec=torch.empty(nat, **f64), energy=torch.zeros(nat, **f64),
+                             gradient=torch.empty(je - jb, 3, **f64), sigma=torch.zeros(3, 3, **f64),
+                             dqdr=torch.empty(nat, je - jb, 3, **f64), dqdL=torch.empty(nat, 3, 3, **f64))
+    mc.singlepoint_rows(model, mol, jb, je, out=blk, xyz=txyz, id=tid)
+    torch.cuda.synchronize()
+    dq = blk["dqdr"]
+    assert float(dq.sum(dim=0).abs().max()) < 1e-10 * max(1.0, float(dq.abs().max()))
+    assert float(blk["dqdL"].sum(dim=0).abs().max()) < 1e-9 * max(1.0, float(blk["dqdL"].abs().max()))
+    assert np.abs(blk["gradient"].cpu().numpy() - g[jb:je]).max() < 1e-11 * max(1.0, np.abs(g).max())
+    assert np.abs(blk["qvec"].cpu().numpy() - q).max() < 1e-12
