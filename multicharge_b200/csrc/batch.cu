@@ -181,10 +181,9 @@ __device__ __forceinline__ void update_tile(double* __restrict__ A, const double
 // PH selects the phases a launch executes:
 //   0  everything in one kernel, matrix in shared memory (small batches)
 //   1  pair phase A: coordination number, xvec, Coulomb block -> global scratch           (light smem)
-//   2  factorisation + solves + Schur complement, matrix loaded from scratch into smem    (heavy smem)
 //   3  pair phase C: energy and gradient, pair scalars parked in scratch                  (light smem)
-// Split launches let the FP64-bound pair phases of one chunk of molecules co-reside on the SMs with the
-// latency-bound factorisation CTAs of another chunk.
+// (between 1 and 3 the split path runs eeq_factor_ll_kernel; the former phase 2 -- the in-kernel factorisation
+//  with the matrix reloaded into shared memory -- was replaced by it)
 template <int NT, int PH>
 __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    extern __shared__ __align__(16) double sm[];
@@ -194,7 +193,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
    const int64_t off = p.offsets[mol];
    const int n = (int)(p.offsets[mol + 1] - off);
    const double charge = p.charge[mol];
-   constexpr bool MAT_IN_SMEM = (PH == 0 || PH == 2);
+   constexpr bool MAT_IN_SMEM = (PH == 0);
    // pair phases work on the molecule's own padded order, the class launches on the class order
    const int np = MAT_IN_SMEM ? p.np : aug_order(n);  // split path: augmented order (see eeq_factor_ll_kernel)
    const int npv = MAT_IN_SMEM ? p.np : NPA_MAX;  // stride of the per-atom vectors (compile-time in the split path)
@@ -240,7 +239,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       }
       if (PH == 0 || PH == 1) cnfix[i] = cnfix[npv + i] = cnfix[2 * npv + i] = 0u;
    }
-   if (PH != 2) eg::load_table(etab, p.etab, tid, NT);
+   eg::load_table(etab, p.etab, tid, NT);
    __syncthreads();
 
    const int ntri_n = tri(n);
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       __syncthreads();
    }
 
-   if (PH == 0 || PH == 2) {
+   if (PH == 0) {
    // ---- blocked Cholesky, block 16, with look-ahead: the next diagonal block is factored by warp 0
    //      while the other warps finish the trailing update ----
    if (warp == 0) {
@@ -500,12 +499,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       }
       if (tid == 0) {
          p.status[mol] = 0;
-         if (PH == 2) p.lamg[mol] = lam2;
       }
    }
-   if (PH == 2) return;
    __syncthreads();
-   }  // PH 0 / 2
+   }  // PH 0
 
    if (PH == 0 && aux_in_panel(np)) eg::load_table(etab, p.etab, tid, NT);  // the panel buffer held it before
    const double lam = scal[0];
@@ -1018,7 +1015,7 @@ __host__ inline size_t smem_doubles_pair(int npv) { return (size_t)NVEC * npv + 
 
 template <int NT, int PH>
 static void launch_class(mchrg_b200_context* ctx, const Args& a, int count) {
-   const bool heavy = (PH == 0 || PH == 2);
+   const bool heavy = (PH == 0);
    static const size_t pad = std::getenv("MCHRG_B200_PAIR_PAD") ? (size_t)atoi(std::getenv("MCHRG_B200_PAIR_PAD")) * 1024 : 0;
    const size_t smem = (heavy ? smem_doubles(a.np) : smem_doubles_pair(a.np)) * sizeof(double) + (heavy ? 0 : pad);
    static size_t configured = 0;
