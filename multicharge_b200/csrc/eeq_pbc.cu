@@ -13,6 +13,7 @@
 #include "dense.cuh"
 #include "eeq.cuh"
 #include "eeq_pbc.cuh"
+#include "erfgauss.cuh"
 #include <cfloat>
 
 #include "lattice.hpp"
@@ -93,6 +94,40 @@ __device__ __forceinline__ void dir_damat(const double* __restrict__ dt, double 
    }
 }
 
+// the same sums with the table-driven erf / exp(-x^2) and the hardware-seeded rsqrt of erfgauss.cuh (pair tiles)
+__device__ __forceinline__ double dir_amat_fast(const double2* __restrict__ tab, const double* __restrict__ dt, double vx,
+                                                double vy, double vz, double gam, double alp) {
+   double acc = 0.0;
+   for (int itr = 0; itr < NDT; ++itr) {
+      const double x = vx + dt[3 * itr], y = vy + dt[3 * itr + 1], z = vz + dt[3 * itr + 2];
+      const double r2 = x * x + y * y + z * z;
+      if (r2 < EPS_SQRT * EPS_SQRT) continue;
+      const double rinv = eg::fast_rsqrt(r2), r1 = r2 * rinv;
+      if (gam * r1 > PRUNE_ARG && alp * r1 > PRUNE_ARG) continue;
+      double g;
+      acc += (eg::erf_gauss<5, false>(tab, gam * r1, g) - eg::erf_gauss<5, false>(tab, alp * r1, g)) * rinv;
+   }
+   return acc;
+}
+
+__device__ __forceinline__ void dir_damat_fast(const double2* __restrict__ tab, const double* __restrict__ dt, double vx,
+                                               double vy, double vz, double gam, double alp, double* g, double* s) {
+   for (int itr = 0; itr < NDT; ++itr) {
+      const double x = vx + dt[3 * itr], y = vy + dt[3 * itr + 1], z = vz + dt[3 * itr + 2];
+      const double r2 = x * x + y * y + z * z;
+      if (r2 < EPS_SQRT * EPS_SQRT) continue;
+      const double rinv = eg::fast_rsqrt(r2), r1 = r2 * rinv;
+      if (gam * r1 > PRUNE_ARG && alp * r1 > PRUNE_ARG) continue;
+      double eg_, ea_;
+      const double fg = eg::erf_gauss<6, true>(tab, gam * r1, eg_), fa = eg::erf_gauss<6, true>(tab, alp * r1, ea_);
+      // gtmp + atmp of get_damat_dir_3d: (2 gam e_g - 2 alp e_a) / (sqrt(pi) r^2) - (erf_g - erf_a) / r^3
+      const double f = ((2.0 / SQRTPI) * (gam * eg_ - alp * ea_) - (fg - fa) * rinv) * rinv * rinv;
+      g[0] += f * x; g[1] += f * y; g[2] += f * z;
+      s[0] += f * x * x; s[1] += f * x * y; s[2] += f * x * z;
+      s[3] += f * y * y; s[4] += f * y * z; s[5] += f * z * z;
+   }
+}
+
 struct PbcDev {
    const double* wtrans;  // WSC candidate translations [3 * nw]
    int nw;
@@ -100,6 +135,7 @@ struct PbcDev {
    const double* rtrans;  // [3 * 124]
    const double* rcoef;   // [124]  4 pi / vol * exp(-g2 / (4 alpha^2)) / g2   (0 where g2 < eps)
    double alpha;
+   const double2* etab;   // erf / exp(-x^2) node table (erfgauss.cuh)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -196,6 +232,8 @@ __global__ void __launch_bounds__(256) pbc_amat_tiles_kernel(int nat, const doub
                                                              double* __restrict__ W, int64_t ld) {
    __shared__ double sdt[3 * NDT];
    __shared__ double swt[3 * 27];
+   __shared__ double2 setab[eg::NTAB];
+   eg::load_table(setab, pb.etab, (int)threadIdx.x, (int)blockDim.x);
    for (int k = threadIdx.x; k < 3 * NDT; k += blockDim.x) sdt[k] = pb.dtrans[k];
    for (int k = threadIdx.x; k < 3 * pb.nw; k += blockDim.x) swt[k] = pb.wtrans[k];
    __syncthreads();
@@ -213,7 +251,7 @@ __global__ void __launch_bounds__(256) pbc_amat_tiles_kernel(int nat, const doub
       double acc = 0.0;
       for (unsigned m = mask; m; m &= m - 1) {
          const int p = __ffs(m) - 1;
-         acc += dir_amat(sdt, vx + swt[3 * p], vy + swt[3 * p + 1], vz + swt[3 * p + 2], gam, pb.alpha) * wsw;
+         acc += dir_amat_fast(setab, sdt, vx + swt[3 * p], vy + swt[3 * p + 1], vz + swt[3 * p + 2], gam, pb.alpha) * wsw;
       }
       W[i + (int64_t)j * ld] += acc;
       W[j + (int64_t)i * ld] += acc;
@@ -251,6 +289,8 @@ __global__ void __launch_bounds__(256) pbc_damat_tiles_kernel(int nat, const dou
                                                               double* __restrict__ atrace, double* __restrict__ dadL) {
    __shared__ double sdt[3 * NDT];
    __shared__ double swt[3 * 27];
+   __shared__ double2 setab[eg::NTAB];
+   eg::load_table(setab, pb.etab, (int)threadIdx.x, (int)blockDim.x);
    for (int k = threadIdx.x; k < 3 * NDT; k += blockDim.x) sdt[k] = pb.dtrans[k];
    for (int k = threadIdx.x; k < 3 * pb.nw; k += blockDim.x) swt[k] = pb.wtrans[k];
    __syncthreads();
@@ -273,7 +313,7 @@ __global__ void __launch_bounds__(256) pbc_damat_tiles_kernel(int nat, const dou
          const double wsw = 1.0 / (double)__popc(mask);
          for (unsigned m = mask; m; m &= m - 1) {
             const int p = __ffs(m) - 1;
-            dir_damat(sdt, vx + swt[3 * p], vy + swt[3 * p + 1], vz + swt[3 * p + 2], gam, pb.alpha, g, s);
+            dir_damat_fast(setab, sdt, vx + swt[3 * p], vy + swt[3 * p + 1], vz + swt[3 * p + 2], gam, pb.alpha, g, s);
          }
 #pragma unroll
          for (int c = 0; c < 3; ++c) g[c] *= wsw;
@@ -396,6 +436,7 @@ static PbcDev upload_pbc(mchrg_b200_context* ctx, const DevMol& mol, PbcHost& ho
    pb.rtrans = pb.dtrans + 3 * NDT;
    pb.rcoef = pb.rtrans + 3 * NRT;
    pb.alpha = host.alpha;
+   pb.etab = ctx->erf_tab;
    return pb;
 }
 

@@ -74,7 +74,7 @@ model = mc.new_eeqbc2025_model(mol, rvdw, en * 3.98)
 for dq in ((False, True) if os.environ.get("NBC_DQ", "1") == "1" else (False,)):
     b = bufs(mol.nat, dq)
     b["_xyz"], b["_id"] = torch.tensor(mol.xyz, device=dev), torch.tensor(mol.id, device=dev)
-    t = timed(lambda: run_sp(model, mol, b), reps=1)
+    t = timed(lambda: run_sp(model, mol, b), reps=int(os.environ.get("NBC_REPS", "2")))
     out[f"eeqbc_n{mol.nat}_{'dqdr' if dq else 'grad'}_s"] = t
     del b
 print(json.dumps(out, indent=1))
