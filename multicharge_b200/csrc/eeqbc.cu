@@ -19,6 +19,7 @@
 #include "dense.cuh"
 #include "eeq.cuh"
 #include "eeqbc.cuh"
+#include "erfgauss.cuh"
 
 namespace mchrg {
 
@@ -62,7 +63,10 @@ __global__ void __launch_bounds__(256) bc_cmat_kernel(int nat, int64_t npad, con
                                                       const int* __restrict__ id, const double* __restrict__ atoms,
                                                       const double* __restrict__ rvdw, int nid, double kbc,
                                                       double* __restrict__ Cm, double* __restrict__ dcdr_diag,
-                                                      double* __restrict__ dcdL) {
+                                                      double* __restrict__ dcdL, const double2* __restrict__ etab) {
+   __shared__ double2 setab[eg::NTAB];
+   eg::load_table(setab, etab, (int)threadIdx.x, (int)blockDim.x);
+   __syncthreads();
    const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    const int lane = threadIdx.x & 31;
    if (a >= npad) return;
@@ -80,15 +84,17 @@ __global__ void __launch_bounds__(256) bc_cmat_kernel(int nat, int64_t npad, con
       }
       if (b == a) continue;
       const double vx = xyz[3 * b] - xa, vy = xyz[3 * b + 1] - ya, vz = xyz[3 * b + 2] - za;
-      const double r1 = sqrt(vx * vx + vy * vy + vz * vz);
+      const double r2 = vx * vx + vy * vy + vz * vz;
+      const double rinv = eg::fast_rsqrt(r2), r1 = r2 * rinv;
       const double rv = rvdw_pair(rvdw, nid, id, a, b);
       const double sc = sqrt(capa * atoms[5 * b + 4]);
       const double t = kbc * (r1 - rv) / rv;
-      const double c = sc * 0.5 * (1.0 + erf(-t));  // get_cpair, eeqbc.f90:1130-1143
+      double et;
+      const double c = sc * (0.5 - copysign(0.5, t) * eg::erf_gauss<6, true>(setab, fabs(t), et));  // get_cpair, eeqbc.f90:1130-1143
       col[b] = -c;
       csum += c;
       if (dcdr_diag) {
-         const double d = -sc * kbc * exp(-(t * t)) / (SQRTPI * rv) / r1;  // get_dcpair: D = d * v
+         const double d = -sc * kbc * et / (SQRTPI * rv) * rinv;  // get_dcpair: D = d * v
          const double gx = d * vx, gy = d * vy, gz = d * vz;
          dg[0] -= gx; dg[1] -= gy; dg[2] -= gz;  // dcdr(:, a, a) = -sum_b D_ab
          dl[0] += gx * vx; dl[1] += gx * vy; dl[2] += gx * vz;  // dS(al, be) = D(be) v(al)
@@ -117,7 +123,10 @@ __global__ void __launch_bounds__(256) bc_cmat_kernel(int nat, int64_t npad, con
 // get_amat_0d (eeqbc.f90:475-530) into the padded work matrix (identity padding)
 __global__ void __launch_bounds__(128) bc_amat_kernel(int nat, int64_t npad, const double* __restrict__ xyz,
                                                       const double* __restrict__ atoms, const double* __restrict__ Cm,
-                                                      double* __restrict__ W) {
+                                                      double* __restrict__ W, const double2* __restrict__ etab) {
+   __shared__ double2 setab[eg::NTAB];
+   eg::load_table(setab, etab, (int)threadIdx.x, (int)blockDim.x);
+   __syncthreads();
    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (r >= npad) return;
    const int64_t c0 = (int64_t)blockIdx.y * 8;
@@ -134,8 +143,9 @@ __global__ void __launch_bounds__(128) bc_amat_kernel(int nat, int64_t npad, con
             const double dx = xyz[3 * c] - xyz[3 * r], dy = xyz[3 * c + 1] - xyz[3 * r + 1], dz = xyz[3 * c + 2] - xyz[3 * r + 2];
             const double r2 = dx * dx + dy * dy + dz * dz;
             const double ra = atoms[5 * r], rb = atoms[5 * c];
-            const double gam2 = 1.0 / (ra * ra + rb * rb);
-            v = erf(sqrt(r2 * gam2)) / sqrt(r2) * cm;
+            const double rinv = eg::fast_rsqrt(r2), gam = eg::fast_rsqrt(ra * ra + rb * rb);
+            double g;
+            v = eg::erf_gauss<5, false>(setab, r2 * rinv * gam, g) * rinv * cm;
          }
       } else {
          v = (r == c) ? 1.0 : 0.0;
@@ -149,21 +159,26 @@ struct BcPair {
    double vx, vy, vz, r1, t1, t2, t3, gam3;
    double Dx, Dy, Dz;  // dcdr(:, a, b)
 };
-__device__ __forceinline__ BcPair bc_pair(double xa, double ya, double za, double rada, double capa, double xb,
-                                          double yb, double zb, double radb, double capb, double rv, double kbc) {
+// (erf, exp(-x^2) from the node table `tab` in shared memory, 1/sqrt from the hardware seed: erfgauss.cuh)
+__device__ __forceinline__ BcPair bc_pair(const double2* __restrict__ tab, double xa, double ya, double za, double rada,
+                                          double capa, double xb, double yb, double zb, double radb, double capb, double rv,
+                                          double kbc) {
    BcPair p;
    p.vx = xb - xa; p.vy = yb - ya; p.vz = zb - za;
    const double r2 = p.vx * p.vx + p.vy * p.vy + p.vz * p.vz;
-   p.r1 = sqrt(r2);
-   const double gam = 1.0 / sqrt(rada * rada + radb * radb);
-   const double arg = gam * gam * r2;
-   const double e = exp(-arg), ef = erf(sqrt(arg));
-   p.t1 = 2.0 * gam * e / (SQRTPI * r2) - ef / (r2 * p.r1);
+   const double rinv = eg::fast_rsqrt(r2);
+   p.r1 = r2 * rinv;
+   const double gam = eg::fast_rsqrt(rada * rada + radb * radb);
+   double e;
+   const double ef = eg::erf_gauss<6, true>(tab, gam * p.r1, e);
+   p.t1 = (2.0 / SQRTPI * gam * e - ef * rinv) * rinv * rinv;
    p.t2 = 2.0 * e / SQRTPI;
-   p.t3 = ef / p.r1;
+   p.t3 = ef * rinv;
    p.gam3 = gam * gam * gam;
    const double t = kbc * (p.r1 - rv) / rv;
-   const double d = -sqrt(capa * capb) * kbc * exp(-(t * t)) / (SQRTPI * rv) / p.r1;
+   double et;
+   eg::erf_gauss<6, true>(tab, fabs(t), et);  // et = exp(-t^2)
+   const double d = -sqrt(capa * capb) * kbc * et / (SQRTPI * rv) * rinv;
    p.Dx = d * p.vx; p.Dy = d * p.vy; p.Dz = d * p.vz;
    return p;
 }
@@ -175,7 +190,11 @@ __global__ void __launch_bounds__(256) bc_rows_kernel(int nat, int64_t npad, con
                                                       const double* __restrict__ rvdw, int nid, double kbc,
                                                       const double* __restrict__ Cm, const double* __restrict__ q,
                                                       const double* __restrict__ dcndr,
-                                                      const double* __restrict__ dcndL, double* __restrict__ rows) {
+                                                      const double* __restrict__ dcndL, double* __restrict__ rows,
+                                                      const double2* __restrict__ etab) {
+   __shared__ double2 setab[eg::NTAB];
+   eg::load_table(setab, etab, (int)threadIdx.x, (int)blockDim.x);
+   __syncthreads();
    const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    const int lane = threadIdx.x & 31;
    if (a >= nat) return;
@@ -191,7 +210,7 @@ __global__ void __launch_bounds__(256) bc_rows_kernel(int nat, int64_t npad, con
    for (int b = lane; b < nat; b += 32) {
       if (b == a) continue;
       const double radb = atoms[5 * b], dradb = atoms[5 * b + 1];
-      const BcPair p = bc_pair(xa, ya, za, rada, capa, xyz[3 * b], xyz[3 * b + 1], xyz[3 * b + 2], radb, atoms[5 * b + 4],
+      const BcPair p = bc_pair(setab, xa, ya, za, rada, capa, xyz[3 * b], xyz[3 * b + 1], xyz[3 * b + 2], radb, atoms[5 * b + 4],
                                rvdw_pair(rvdw, nid, id, a, b), kbc);
       const double cab = Cm[b + (int64_t)a * npad], qb = q[b], xb = atoms[5 * b + 3];
       // dgam_ab(:, b) = -(rad_a drad_a dcndr(:, b, a) + rad_b drad_b dcndr(:, b, b)) gamma^3
@@ -291,7 +310,10 @@ __global__ void __launch_bounds__(128) bc_build_b_kernel(int nat, int64_t npad, 
                                                          const double* __restrict__ dqlocdr, double sa, double sx,
                                                          int add_atrace, double* __restrict__ Bout, int64_t ldb,
                                                          double* __restrict__ ga, double* __restrict__ gx,
-                                                         const double* __restrict__ zvec, double* __restrict__ bz) {
+                                                         const double* __restrict__ zvec, double* __restrict__ bz,
+                                                         const double2* __restrict__ etab) {
+   __shared__ double2 setab[eg::NTAB];
+   eg::load_table(setab, etab, (int)threadIdx.x, (int)blockDim.x);
    __shared__ double sk[BCK][12];  // x y z rad drad h xtmp cap | q C_bb-weights(2) z
    const int a = blockIdx.x * blockDim.x + threadIdx.x;
    const int b0 = blockIdx.y * BCK;
@@ -334,7 +356,7 @@ __global__ void __launch_bounds__(128) bc_build_b_kernel(int nat, int64_t npad, 
          dx2 = rw[14] + xtmpa * dcdr_diag[3 * a + 2];
       } else {
          const double radb = sk[kk][3], dradb = sk[kk][4];
-         const BcPair p = bc_pair(xa, ya, za, rada, capa, sk[kk][0], sk[kk][1], sk[kk][2], radb, sk[kk][7],
+         const BcPair p = bc_pair(setab, xa, ya, za, rada, capa, sk[kk][0], sk[kk][1], sk[kk][2], radb, sk[kk][7],
                                   rvdw_pair(rvdw, nid, id, a, b), kbc);
          const double cab = Cm[a + (int64_t)b * npad];
          const double wa = rada * drada, wb = radb * dradb;
@@ -386,18 +408,18 @@ void bc_prepare(mchrg_b200_context* ctx, const DevMol& mol, const mchrg_b200_mod
    w.dcdr_diag = grad ? ctx->alloc<double>((size_t)3 * nat) : nullptr;
    w.dcdL = grad ? ctx->alloc<double>((size_t)9 * nat) : nullptr;
    MCHRG_LAUNCH(ctx, bc_cmat_kernel, (unsigned)((w.npad + 7) / 8), 256, 0, nat, w.npad, mol.xyz, mol.id, w.atoms,
-                model->dev_rvdw(), model->nid, model->kbc, w.Cm, w.dcdr_diag, w.dcdL);
+                model->dev_rvdw(), model->nid, model->kbc, w.Cm, w.dcdr_diag, w.dcdL, ctx->erf_tab);
 }
 
 void bc_amat(mchrg_b200_context* ctx, const DevMol& mol, const BcWork& w, double* W) {
    dim3 grid((unsigned)((w.npad + 127) / 128), (unsigned)((w.npad + 7) / 8));
-   MCHRG_LAUNCH(ctx, bc_amat_kernel, grid, 128, 0, mol.nat, w.npad, mol.xyz, w.atoms, w.Cm, W);
+   MCHRG_LAUNCH(ctx, bc_amat_kernel, grid, 128, 0, mol.nat, w.npad, mol.xyz, w.atoms, w.Cm, W, ctx->erf_tab);
 }
 
 void bc_rows(mchrg_b200_context* ctx, const DevMol& mol, const mchrg_b200_model* model, const BcWork& w,
              const double* q, const double* dcndr, const double* dcndL, double* rows) {
    MCHRG_LAUNCH(ctx, bc_rows_kernel, (unsigned)((mol.nat + 7) / 8), 256, 0, mol.nat, w.npad, mol.xyz, mol.id, w.atoms,
-                model->dev_rvdw(), model->nid, model->kbc, w.Cm, q, dcndr, dcndL, rows);
+                model->dev_rvdw(), model->nid, model->kbc, w.Cm, q, dcndr, dcndL, rows, ctx->erf_tab);
 }
 
 void bc_strain(mchrg_b200_context* ctx, const DevMol& mol, const BcAtoms& at, const BcWork& w, const double* q,
@@ -422,7 +444,7 @@ void bc_build_b(mchrg_b200_context* ctx, const DevMol& mol, const mchrg_b200_mod
    dim3 grid((unsigned)((mol.nat + 127) / 128), (unsigned)((mol.nat + BCK - 1) / BCK));
    MCHRG_LAUNCH(ctx, bc_build_b_kernel, grid, 128, 0, mol.nat, w.npad, mol.xyz, mol.id, w.atoms, at, model->dev_rvdw(),
                 model->nid, model->kbc, w.Cm, q, cq, rows, w.dcdr_diag, dcndr, dqlocdr, sa, sx, add_atrace ? 1 : 0, Bout,
-                ldb, ga, gx, zvec, bz);
+                ldb, ga, gx, zvec, bz, ctx->erf_tab);
 }
 
 }  // namespace mchrg
