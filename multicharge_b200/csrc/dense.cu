@@ -597,26 +597,66 @@ __global__ void __launch_bounds__(256) trsv_diag_kernel(const double* __restrict
       for (int c = 0; c < nrhs; ++c) R[i + c * ldr] = acc[c] + part[c][i];
 }
 
-// forward update: R[i] -= sum_j L(i, j) w_j  for rows i below the block (one thread per row, unrolled loads)
-__global__ void __launch_bounds__(256) trsv_update_fwd_kernel(const double* __restrict__ Lcol, int64_t ldl,
-                                                              const double* __restrict__ w, double* __restrict__ R,
-                                                              int64_t ldr, int64_t nrows, int nrhs) {
+// forward step k: R[i] -= sum_j L(i, j) w_j for the rows i below block k (w = solved block k), CTA = 128 rows x
+// 2 column slices of 64 (two batches of 32 loads in flight per thread, coalesced over the rows); the first
+// CTA owns exactly the rows of block k+1 and applies inv(L_{k+1,k+1}) to them right away, so that one launch per
+// block step remains (no separate single-CTA kernel between the steps).
+__global__ void __launch_bounds__(256) trsv_fwd_fused_kernel(const double* __restrict__ Lcol, int64_t ldl,
+                                                             const double* __restrict__ w, double* __restrict__ R,
+                                                             int64_t ldr, int64_t nrows, int nrhs,
+                                                             const double* __restrict__ dinv_next) {
    __shared__ double ws[MAX_RHS][TILE];
+   __shared__ double part[MAX_RHS][TILE];
+   __shared__ double rn[MAX_RHS][TILE];
    for (int idx = threadIdx.x; idx < MAX_RHS * TILE; idx += blockDim.x) {
       const int c = idx / TILE, j = idx % TILE;
       ws[c][j] = (c < nrhs) ? w[j + c * ldr] : 0.0;
    }
    __syncthreads();
-   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= nrows) return;
+   const int rl = threadIdx.x & (TILE - 1), slice = threadIdx.x >> 7;
+   const int64_t i = (int64_t)blockIdx.x * TILE + rl;
+   const bool solve_next = (blockIdx.x == 0) && (dinv_next != nullptr);
    double acc[MAX_RHS] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 16
-   for (int j = 0; j < TILE; ++j) {
-      const double l = Lcol[i + (int64_t)j * ldl];
+   if (i < nrows) {
 #pragma unroll
-      for (int c = 0; c < MAX_RHS; ++c) acc[c] = fma(l, ws[c][j], acc[c]);
+      for (int half = 0; half < 2; ++half) {
+         double l[32];
+         const int j0 = 64 * slice + 32 * half;
+#pragma unroll
+         for (int j = 0; j < 32; ++j) l[j] = Lcol[i + (int64_t)(j0 + j) * ldl];
+#pragma unroll
+         for (int j = 0; j < 32; ++j)
+#pragma unroll
+            for (int c = 0; c < MAX_RHS; ++c) acc[c] = fma(l[j], ws[c][j0 + j], acc[c]);
+      }
    }
-   for (int c = 0; c < nrhs; ++c) R[i + c * ldr] -= acc[c];
+   if (slice == 1)
+#pragma unroll
+      for (int c = 0; c < MAX_RHS; ++c) part[c][rl] = acc[c];
+   __syncthreads();
+   if (slice == 0 && i < nrows) {
+      for (int c = 0; c < nrhs; ++c) {
+         const double r = R[i + c * ldr] - (acc[c] + part[c][rl]);
+         if (solve_next) rn[c][rl] = r;
+         else R[i + c * ldr] = r;
+      }
+   }
+   if (!solve_next) return;
+   __syncthreads();
+   // block k+1: w = inv(L_{k+1,k+1}) r  (blocks are stored with an explicitly zero upper triangle)
+   double a2[MAX_RHS] = {0.0, 0.0, 0.0, 0.0};
+   const int k0 = slice * (TILE / 2);
+#pragma unroll 16
+   for (int kk = 0; kk < TILE / 2; ++kk) {
+      const double d = dinv_next[rl + (k0 + kk) * TILE];
+#pragma unroll
+      for (int c = 0; c < MAX_RHS; ++c) a2[c] = fma(d, rn[c][k0 + kk], a2[c]);
+   }
+   if (slice == 1)
+      for (int c = 0; c < nrhs; ++c) part[c][rl] = a2[c];
+   __syncthreads();
+   if (slice == 0)
+      for (int c = 0; c < nrhs; ++c) R[rl + c * ldr] = a2[c] + part[c][rl];
 }
 
 // backward update: R[j] -= sum_i L(k0 + i, j) w_i  for columns j left of the block (one warp per column)
@@ -652,13 +692,12 @@ void dpotrs_vec(mchrg_b200_context* ctx, int64_t n, const double* L, int64_t ldl
                 double* R, int64_t ldr, int nrhs) {
    if (nrhs > MAX_RHS || n % TILE) fail(MCHRG_B200_ERR_ARG, "dpotrs_vec: bad arguments");
    const int64_t nb = n / TILE;
-   for (int64_t k = 0; k < nb; ++k) {  // L w = r
+   MCHRG_LAUNCH(ctx, trsv_diag_kernel, 1, 256, 0, dinv, R, ldr, nrhs, 0);
+   for (int64_t k = 0; k + 1 < nb; ++k) {  // L w = r: update the rows below block k, solve block k+1 on the way
       double* rk = R + k * TILE;
-      MCHRG_LAUNCH(ctx, trsv_diag_kernel, 1, 256, 0, dinv + k * TILE * TILE, rk, ldr, nrhs, 0);
       const int64_t below = n - (k + 1) * TILE;
-      if (below > 0)
-         MCHRG_LAUNCH(ctx, trsv_update_fwd_kernel, (unsigned)((below + 255) / 256), 256, 0,
-                      L + (k + 1) * TILE + k * TILE * ldl, ldl, rk, rk + TILE, ldr, below, nrhs);
+      MCHRG_LAUNCH(ctx, trsv_fwd_fused_kernel, (unsigned)(below / TILE), 256, 0, L + (k + 1) * TILE + k * TILE * ldl, ldl, rk,
+                   rk + TILE, ldr, below, nrhs, dinv + (k + 1) * TILE * TILE);
    }
    for (int64_t k = nb - 1; k >= 0; --k) {  // L^T y = w
       double* rk = R + k * TILE;
