@@ -1016,17 +1016,15 @@ __host__ inline size_t smem_doubles_pair(int npv) { return (size_t)NVEC * npv + 
 template <int NT, int PH>
 static void launch_class(mchrg_b200_context* ctx, const Args& a, int count) {
    const bool heavy = (PH == 0);
-   static const size_t pad = std::getenv("MCHRG_B200_PAIR_PAD") ? (size_t)atoi(std::getenv("MCHRG_B200_PAIR_PAD")) * 1024 : 0;
-   const size_t smem = (heavy ? smem_doubles(a.np) : smem_doubles_pair(a.np)) * sizeof(double) + (heavy ? 0 : pad);
+   const size_t smem = (heavy ? smem_doubles(a.np) : smem_doubles_pair(a.np)) * sizeof(double);
    static size_t configured = 0;
    if (smem > configured) {
-      const size_t cap = (heavy ? smem_doubles(NP_MAX) : smem_doubles_pair(NPA_MAX)) * sizeof(double) + (heavy ? 0 : pad);
+      const size_t cap = (heavy ? smem_doubles(NP_MAX) : smem_doubles_pair(NPA_MAX)) * sizeof(double);
       MCHRG_CUDA(cudaFuncSetAttribute(eeq_batch_kernel<NT, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
       // same shared-memory carveout as the factorisation kernel: CTAs of kernels that ask for different
       // L1/shared splits cannot share an SM
-      if (!std::getenv("MCHRG_B200_NO_CARVEOUT"))
-         MCHRG_CUDA(cudaFuncSetAttribute(eeq_batch_kernel<NT, PH>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         (int)cudaSharedmemCarveoutMaxShared));
+      MCHRG_CUDA(cudaFuncSetAttribute(eeq_batch_kernel<NT, PH>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      (int)cudaSharedmemCarveoutMaxShared));
       configured = cap;
    }
    MCHRG_LAUNCH(ctx, (eeq_batch_kernel<NT, PH>), (unsigned)count, NT, smem, a);
