@@ -870,7 +870,6 @@ int mchrg_b200_get_xvec_derivs(const mchrg_b200_model* model, const mchrg_b200_s
       const size_t n = d.nat;
       if (model->kind == 2) {
          if (!qloc || !dqlocdr || !dqlocdL) fail(MCHRG_B200_ERR_MODEL, "qloc and its derivatives required for eeqbc");
-         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "the piecewise derivative accessors are not built for periodic EEQ-BC (use solve / singlepoint / get_charges)");
          BcAtoms at = gather_eeqbc(model, d);
          BcWork w;
          const double* dcn = ctx->in(dcndr, 3 * n * n);
@@ -880,6 +879,30 @@ int mchrg_b200_get_xvec_derivs(const mchrg_b200_model* model, const mchrg_b200_s
          bc_prepare(ctx, d, model, at, ctx->in(cn, n), ctx->in(qloc, n), true, w);
          const int64_t mp = round_up(3 * (int64_t)n + 9, TILE);
          double* zeros = ctx->alloc_zero<double>(n + 1);  // q = 0: only the q-independent (dxdr) parts survive
+         if (d.periodic) {  // periodic branch of get_xvec_derivs (eeqbc.f90:364-418)
+            PbcScope ps;
+            pbc_begin(ctx, d, ps.host, ps.work);
+            ps.on = true;
+            double* cself = ctx->alloc<double>(n);
+            double* Wtmp = ctx->alloc<double>((size_t)w.npad * w.npad);
+            bc_pbc_matrices(ctx, d, w.atoms, model->dev_rvdw(), model->nid, model->kbc, ps.work, w.Cm, Wtmp, cself);
+            double* Bm = ctx->alloc<double>((size_t)mp * w.npad);
+            bc_dxdr_gemm(ctx, d, at, w, dcn, dqr, 1.0, Bm, mp);  // Bm = +dtmpdr C
+            double* ga = ctx->alloc_zero<double>(3 * n);
+            double* gx = ctx->alloc_zero<double>(3 * n);
+            double* dadL_tmp = ctx->alloc_zero<double>(9 * n);
+            double* d_dxdL = ctx->out(dxdL, 9 * (n + 1));
+            MCHRG_CUDA(cudaMemsetAsync(d_dxdL, 0, 9 * (n + 1) * sizeof(double), ctx->stream));
+            bc_pbc_derivs(ctx, d, w.atoms, model->dev_rvdw(), model->nid, model->kbc, at.kcnchi, at.kqchi, at.kqeta, zeros, zeros,
+                          w.Cm, cself, dcn, dcl, dqr, dql, nullptr, ps.work, Bm, mp, ga, gx, dadL_tmp, d_dxdL, nullptr, 0.0,
+                          -1.0, false, nullptr);
+            double* d_dxdr = ctx->out(dxdr, 3 * n * (n + 1));
+            MCHRG_LAUNCH(ctx, unpad_copy_kernel, dim3((unsigned)((3 * n + 255) / 256), (unsigned)n), 256, 0, (int64_t)(3 * n),
+                         (int64_t)n, Bm, mp, d_dxdr, (int64_t)(3 * n), 0);
+            MCHRG_CUDA(cudaMemsetAsync(d_dxdr + 3 * n * n, 0, 3 * n * sizeof(double), ctx->stream));
+            ctx->finish();  // host setup arrays of `ps` are consumed by async copies
+            return 0;
+         }
          double* rows = ctx->alloc<double>(24 * n);
          bc_rows(ctx, d, model, w, zeros, dcn, dcl, rows);
          double* dadL_tmp = ctx->alloc<double>(9 * n);
@@ -967,7 +990,6 @@ int mchrg_b200_get_coulomb_derivs(const mchrg_b200_model* model, const mchrg_b20
       if (model->kind == 2) {
          if (!cn || !qloc || !dcndr || !dcndL || !dqlocdr || !dqlocdL)
             fail(MCHRG_B200_ERR_MODEL, "cn, qloc and their derivatives required for eeqbc");
-         if (d.periodic) fail(MCHRG_B200_ERR_MODEL, "the piecewise derivative accessors are not built for periodic EEQ-BC (use solve / singlepoint / get_charges)");
          BcAtoms at = gather_eeqbc(model, d);
          BcWork w;
          const double* dcn = ctx->in(dcndr, 3 * n * n);
@@ -976,6 +998,34 @@ int mchrg_b200_get_coulomb_derivs(const mchrg_b200_model* model, const mchrg_b20
          const double* dql = ctx->in(dqlocdL, 9 * n);
          const double* q = ctx->in(qvec, n);
          bc_prepare(ctx, d, model, at, ctx->in(cn, n), ctx->in(qloc, n), true, w);
+         if (d.periodic) {  // get_damat_3d (eeqbc.f90:789-924)
+            PbcScope ps;
+            pbc_begin(ctx, d, ps.host, ps.work);
+            ps.on = true;
+            const int64_t mp = round_up(3 * (int64_t)n + 9, TILE);
+            double* cself = ctx->alloc<double>(n);
+            double* Wtmp = ctx->alloc<double>((size_t)w.npad * w.npad);
+            bc_pbc_matrices(ctx, d, w.atoms, model->dev_rvdw(), model->nid, model->kbc, ps.work, w.Cm, Wtmp, cself);
+            double* cq = ctx->alloc<double>(n);
+            pbc_symv(ctx, d.nat, w.Cm, w.npad, q, cq);
+            double* Bm = ctx->alloc_zero<double>((size_t)mp * w.npad);
+            double* ga = ctx->alloc_zero<double>(3 * n);
+            double* gx = ctx->alloc_zero<double>(3 * n);
+            double* dxdL_tmp = ctx->alloc_zero<double>(9 * n);
+            double* d_dadL = ctx->out(dadL, 9 * (n + 1));
+            MCHRG_CUDA(cudaMemsetAsync(d_dadL, 0, 9 * (n + 1) * sizeof(double), ctx->stream));
+            double* d_atr = ctx->out(atrace, 3 * n);
+            MCHRG_CUDA(cudaMemsetAsync(d_atr, 0, 3 * n * sizeof(double), ctx->stream));
+            bc_pbc_derivs(ctx, d, w.atoms, model->dev_rvdw(), model->nid, model->kbc, at.kcnchi, at.kqchi, at.kqeta, q, cq, w.Cm,
+                          cself, dcn, dcl, dqr, dql, nullptr, ps.work, Bm, mp, ga, gx, d_dadL, dxdL_tmp, nullptr, 1.0, 0.0,
+                          false, d_atr);
+            double* d_dadr = ctx->out(dadr, 3 * n * (n + 1));
+            MCHRG_LAUNCH(ctx, unpad_copy_kernel, dim3((unsigned)((3 * n + 255) / 256), (unsigned)n), 256, 0, (int64_t)(3 * n),
+                         (int64_t)n, Bm, mp, d_dadr, (int64_t)(3 * n), 0);
+            MCHRG_CUDA(cudaMemsetAsync(d_dadr + 3 * n * n, 0, 3 * n * sizeof(double), ctx->stream));
+            ctx->finish();  // host setup arrays of `ps` are consumed by async copies
+            return 0;
+         }
          double* rows = ctx->alloc<double>(24 * n);
          bc_rows(ctx, d, model, w, q, dcn, dcl, rows);
          double* d_dadL = ctx->out(dadL, 9 * (n + 1));

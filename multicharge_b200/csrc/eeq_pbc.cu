@@ -659,6 +659,11 @@ struct BcDerivAcc {
    double* dxdL;    // [9 nat]
    double* dcdrd;   // [3 nat]  dcdr(:, i, i)
    double* dcdLs;   // [9 nat]  dcdL(:, :, i)
+   double* atr;     // [3 nat]  atrace (may be null)
+   // B = sa (dadr + add_atrace diag(atrace)) - sx dxdr: the solve uses (1, 1, true); the piecewise accessors
+   // get_coulomb_derivs (1, 0, false) and get_xvec_derivs (0, -1, false; q = 0)
+   double sa, sx;
+   int add_atrace;
 };
 
 __global__ void __launch_bounds__(256) bc_pbc_deriv_tiles_kernel(int nat, const double* __restrict__ xyz,
@@ -708,11 +713,15 @@ __global__ void __launch_bounds__(256) bc_pbc_deriv_tiles_kernel(int nat, const 
          const double x_off = (xti - xtj) * sm.d3[c];                                               // dxdr(c, i, j) = dxdr(c, j, i)
          const double x_ii = xtj * sm.d3[c], x_jj = -xti * sm.d3[c];                                // dxdr(c, i, i), dxdr(c, j, j)
          if (B) {
-            B[(3 * (size_t)i + c) + (size_t)j * ldb] += a_ij - x_off;
-            B[(3 * (size_t)j + c) + (size_t)i * ldb] += a_ji - x_off;
+            B[(3 * (size_t)i + c) + (size_t)j * ldb] += acc.sa * a_ij - acc.sx * x_off;
+            B[(3 * (size_t)j + c) + (size_t)i * ldb] += acc.sa * a_ji - acc.sx * x_off;
          }
-         atomicAdd(acc.bdiag + 3 * i + c, at_i - x_ii);
-         atomicAdd(acc.bdiag + 3 * j + c, at_j - x_jj);
+         atomicAdd(acc.bdiag + 3 * i + c, (acc.add_atrace ? acc.sa * at_i : 0.0) - acc.sx * x_ii);
+         atomicAdd(acc.bdiag + 3 * j + c, (acc.add_atrace ? acc.sa * at_j : 0.0) - acc.sx * x_jj);
+         if (acc.atr) {
+            atomicAdd(acc.atr + 3 * i + c, at_i);
+            atomicAdd(acc.atr + 3 * j + c, at_j);
+         }
          atomicAdd(acc.ga + 3 * i + c, a_ij * qj + at_i * qi);
          atomicAdd(acc.ga + 3 * j + c, a_ji * qi + at_j * qj);
          atomicAdd(acc.gx + 3 * i + c, x_off * qj + x_ii * qi);
@@ -746,6 +755,7 @@ __global__ void __launch_bounds__(256) bc_pbc_deriv_self_kernel(int nat, int64_t
                                                                 const double* __restrict__ kcnchi,
                                                                 const double* __restrict__ kqchi,
                                                                 const double* __restrict__ kqeta,
+                                                                const double* __restrict__ dcndr,
                                                                 const double* __restrict__ dcndL,
                                                                 const double* __restrict__ dqlocdL, PbcDev pb,
                                                                 BcDerivAcc acc) {
@@ -809,8 +819,11 @@ __global__ void __launch_bounds__(256) bc_pbc_deriv_self_kernel(int nat, int64_t
 #pragma unroll
    for (int c = 0; c < 3; ++c) {
       const double dd = acc.dcdrd[3 * i + c];
-      // dadr(c, i, i) += h_i q_i dcdr(c, i, i); dxdr(c, i, i) += xtmp_i dcdr(c, i, i)   (the atrace / dadr self terms cancel)
-      acc.bdiag[3 * i + c] += hi * qi * dd - xti * dd;
+      // dadr(c, i, i) += h_i q_i dcdr(c, i, i); dxdr(c, i, i) += xtmp_i dcdr(c, i, i);
+      // self images: atrace(c, i) += t, dadr(c, i, i) -= t with t = dtw dcndr(c, i, i) g1 (they cancel in the solve)
+      const double tself = dtw * dcndr[c + 3 * (i + (size_t)nat * i)] * g1;
+      acc.bdiag[3 * i + c] += acc.sa * (hi * qi * dd - tself + (acc.add_atrace ? tself : 0.0)) - acc.sx * xti * dd;
+      if (acc.atr) acc.atr[3 * i + c] += tself;
       acc.ga[3 * i + c] += hi * qi * dd * qi;
       acc.gx[3 * i + c] += xti * dd * qi;
    }
@@ -846,25 +859,29 @@ __global__ void __launch_bounds__(128) bc_pbc_deriv_rows_kernel(int nat, int64_t
       gx = fma(u, qi, gx);
       gx = fma(kcnchi[i] * cn + kqchi[i] * ql, cq[i], gx);
       if (B) {
-         double b = B[r + (size_t)i * ldb] + v - u;
+         double b = B[r + (size_t)i * ldb] + acc.sa * v - acc.sx * u;
          if (i == k) b += acc.bdiag[r];
          B[r + (size_t)i * ldb] = b;
-         z = fma(b, zvec[i], z);
+         if (zvec) z = fma(b, zvec[i], z);
       }
    }
    acc.ga[r] += ga;
    acc.gx[r] += gx;
-   if (B) bz[r] = z;
+   if (B && bz) bz[r] = z;
 }
 
 void bc_pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* atoms, const double* rvdw, int nid, double kbc,
                    const double* kcnchi, const double* kqchi, const double* kqeta, const double* q, const double* cq,
                    const double* Cm, const double* cself, const double* dcndr, const double* dcndL, const double* dqlocdr,
                    const double* dqlocdL, const double* zvec, PbcWork& work, double* B, int64_t ldb, double* ga, double* gx,
-                   double* dadL, double* dxdL, double* bz) {
+                   double* dadL, double* dxdL, double* bz, double sa, double sx, bool add_atrace, double* atrace) {
    auto* st = static_cast<PbcState*>(work.state);
    const int nat = mol.nat;
    BcDerivAcc acc;
+   acc.sa = sa;
+   acc.sx = sx;
+   acc.add_atrace = add_atrace ? 1 : 0;
+   acc.atr = atrace;
    acc.bdiag = ctx->alloc_zero<double>((size_t)3 * nat);
    acc.dcdrd = ctx->alloc_zero<double>((size_t)3 * nat);
    acc.dcdLs = ctx->alloc_zero<double>((size_t)9 * nat);
@@ -876,7 +893,7 @@ void bc_pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* ato
    MCHRG_LAUNCH(ctx, bc_pbc_deriv_tiles_kernel, (unsigned)(nt * (nt + 1) / 2), 256, 0, nat, mol.xyz, mol.id, atoms, rvdw, nid,
                 kbc, q, dcndr, dcndL, st->pb, B, ldb, acc);
    MCHRG_LAUNCH(ctx, bc_pbc_deriv_self_kernel, (unsigned)((nat + 7) / 8), 256, 0, nat, work.npad, mol.id, atoms, rvdw, nid,
-                kbc, q, Cm, cself, kcnchi, kqchi, kqeta, dcndL, dqlocdL, st->pb, acc);
+                kbc, q, Cm, cself, kcnchi, kqchi, kqeta, dcndr, dcndL, dqlocdL, st->pb, acc);
    MCHRG_LAUNCH(ctx, bc_pbc_deriv_rows_kernel, (unsigned)((3 * (int64_t)nat + 127) / 128), 128, 0, nat, work.npad, atoms, q, cq,
                 Cm, cself, kcnchi, kqchi, kqeta, dcndr, dqlocdr, zvec, B, ldb, acc, bz);
 }

@@ -51,6 +51,9 @@ void bc_pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* ato
                    const double* kcnchi, const double* kqchi, const double* kqeta, const double* q, const double* cq,
                    const double* Cm, const double* cself, const double* dcndr, const double* dcndL, const double* dqlocdr,
                    const double* dqlocdL, const double* zvec, PbcWork& work, double* B, int64_t ldb, double* ga, double* gx,
-                   double* dadL, double* dxdL, double* bz);
+                   double* dadL, double* dxdL, double* bz, double sa = 1.0, double sx = 1.0, bool add_atrace = true,
+                   double* atrace = nullptr);
+// (sa, sx, add_atrace) select B = sa (dadr + add_atrace diag(atrace)) - sx dxdr for the piecewise accessors;
+// atrace (zero-initialised by the caller) receives get_damat_3d's atrace when given; zvec / bz may be null.
 
 }  // namespace mchrg

@@ -149,6 +149,13 @@ def test_eeqbc_periodic(mc, oracle, case):
     # derivatives: get_damat_3d, get_dcmat_3d, periodic get_xvec_derivs
     odcn = oracle.get_cn(omodel, omol, grad=True)
     odq = oracle.eeqbc_local_charge(omodel, omol, grad=True)
+    dxdr, dxdL = model.get_xvec_derivs(mol, odcn[0], odcn[1], odcn[2], odq[0], odq[1], odq[2])
+    odxdr, odxdL = oracle.eeqbc_get_xvec_derivs(omodel, omol, odcn[0], odq[0], odcn[1], odcn[2], odq[1], odq[2])
+    assert close(dxdr, odxdr) and close(dxdL, odxdL)
+    qr = np.random.default_rng(n).standard_normal(n)
+    dadr, dadL, atrace = model.get_coulomb_derivs(mol, qr, odcn[0], odq[0], odcn[1], odcn[2], odq[1], odq[2])
+    odadr, odadL, oatrace = oracle.eeqbc_get_coulomb_derivs(omodel, omol, odcn[0], odq[0], odcn[1], odcn[2], odq[1], odq[2], qr)
+    assert close(dadr, odadr) and close(dadL, odadL) and close(atrace, oatrace)
     ref = oracle.eeqbc_solve(omodel, omol, odcn[0], odq[0], odcn[1], odcn[2], odq[1], odq[2])
     assert ref.stat == 0
     out = dict(energy=np.zeros(n), gradient=np.zeros((n, 3)), sigma=np.zeros((3, 3)), qvec=np.zeros(n),
