@@ -20,9 +20,14 @@ def oracle_batch(oracle, offsets, num, xyz, charge):
     return q, e, g
 
 
-def test_batch_matches_oracle_all_size_classes(mc, oracle):
+@pytest.mark.parametrize("mode", ["fused", "split"])
+def test_batch_matches_oracle_all_size_classes(mc, oracle, monkeypatch, mode):
+    """Every size class through both schedules (the split path pads to the augmented order ceil((n + 2) / 16) * 16:
+    sizes around n mod 16 in {13, 14, 15, 0, 1} are the edges)."""
     from synth import cluster
-    sizes = [1, 2, 3, 15, 16, 17, 31, 32, 33, 47, 64, 65, 80, 96, 100, 112, 127, 128, 129, 144, 160, 161, 176, 192, 200, 207, 208]
+    monkeypatch.setenv("MCHRG_B200_BATCH_MODE", mode)
+    sizes = [1, 2, 3, 13, 14, 15, 16, 17, 29, 30, 31, 32, 33, 46, 47, 48, 49, 64, 65, 80, 96, 100, 112, 127, 128, 129, 144, 160,
+             161, 176, 192, 200, 205, 206, 207, 208]
     nums, xyzs = [], []
     for k, n in enumerate(sizes):
         num, xyz = cluster(n, 100 + k)
