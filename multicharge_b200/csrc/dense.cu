@@ -4,6 +4,7 @@
 //
 // Replaces, on the device: sytrf/sytri/sytrs (lapack.F90:165-363, called from model/type.F90:221-243)
 // and gemm/gemv/symv (blas.F90, called from model/type.F90:235-290).
+#include <cstdio>
 #include "dense.cuh"
 
 #include <algorithm>
@@ -524,8 +525,29 @@ void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, d
    MCHRG_CUDA(cudaEventRecord(e0, U));
    MCHRG_CUDA(cudaStreamWaitEvent(P, e0, 0));
    cudaEvent_t ev_upd_prev = nullptr;
+   // panel width: MCHRG_B200_PANEL fixes it; MCHRG_B200_PANEL_ADAPT=hi,lo widens the panels while the trailing
+   // matrix is large (fewer read-modify-write passes over it) and narrows them in the tail (shorter serial chain)
+   // (default measured at n = 16384 on B200: 512-wide panels while more than 7168 columns are left, 256 down to
+   //  2048, 128 in the tail: 67.4 -> 62.2 ms)
+   static const char* adapt_env = std::getenv("MCHRG_B200_PANEL_ADAPT");
+   static const bool adapt = adapt_env != nullptr || std::getenv("MCHRG_B200_PANEL") == nullptr;
+   static long thr4 = 1L << 60, thr_hi = 7168, thr_lo = 2048;
+   static bool parsed = false;
+   if (adapt_env && !parsed) {
+      long a = 0, b = 0, c = 0;
+      const int got = sscanf(adapt_env, "%ld,%ld,%ld", &a, &b, &c);
+      if (got == 3) { thr4 = a; thr_hi = b; thr_lo = c; }
+      else if (got == 2) { thr_hi = a; thr_lo = b; }
+      parsed = true;
+   }
+   auto pw_at = [&](int64_t c) -> int64_t {
+      const int64_t left = n - c;
+      if (!adapt) return std::min<int64_t>(PANEL, left);
+      const int64_t w = left > thr4 ? 4 * PANEL : (left > thr_hi ? 2 * PANEL : (left > thr_lo ? PANEL : TILE));
+      return std::min<int64_t>(w, left);
+   };
    for (int64_t c0 = 0; c0 < n;) {
-      const int64_t pw = std::min<int64_t>(PANEL, n - c0);
+      const int64_t pw = pw_at(c0);
       const int64_t rem = n - c0 - pw;
       double* D = W + c0 + c0 * ldw;
       double* dinv_k = dinv + (c0 / TILE) * TILE * TILE;
@@ -537,7 +559,7 @@ void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, d
          MCHRG_CUDA(cudaEventRecord(ev_panel, P));
       }
       if (rem == 0) break;
-      const int64_t pw2 = std::min<int64_t>(PANEL, rem);
+      const int64_t pw2 = pw_at(c0 + pw);
       double* A21 = D + pw;                   // (rem x pw) panel below the diagonal block
       double* C1 = W + (c0 + pw) + (c0 + pw) * ldw;  // next block column (rem x pw2)
       {
