@@ -110,6 +110,21 @@ module mchrg_b200_shim
          type(c_ptr), value :: cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL, qvec, dadr, dadL, atrace
          integer(c_int) :: stat
       end function
+      !> multi-GPU factorisation of one large system: install the panel exchange (e.g. thunks around
+      !> MPI_Ibcast / MPI_Wait of a CUDA-aware MPI; see include/mchrg_b200.h)
+      function c_set_exchange(ctx, rank, nranks, start, wait, user) result(stat) bind(C, name="mchrg_b200_set_exchange")
+         import :: c_ptr, c_funptr, c_int, c_int32_t
+         type(c_ptr), value :: ctx
+         integer(c_int32_t), value :: rank, nranks
+         type(c_funptr), value :: start, wait
+         type(c_ptr), value :: user
+         integer(c_int) :: stat
+      end function c_set_exchange
+      function c_side_stream(ctx) result(stream) bind(C, name="mchrg_b200_side_stream")
+         import :: c_ptr
+         type(c_ptr), value :: ctx
+         type(c_ptr) :: stream
+      end function c_side_stream
    end interface
 
    !> per-solve cache payload: the B200 path rebuilds its device workspace per call, so the cache only
