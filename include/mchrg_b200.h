@@ -173,7 +173,9 @@ int mchrg_b200_singlepoint_rows(const mchrg_b200_model* model, const mchrg_b200_
  * [offsets[m], offsets[m+1]).  num[] are ATOMIC NUMBERS per atom (the model must have been built
  * by *_new_eeq2019_model with num = 1..103, i.e. species index == atomic number).  Outputs are
  * concatenated per atom; energy is per atom and overwritten; status[m] follows the return-value
- * convention above per molecule.  gradient may be NULL (charges + energy only). */
+ * convention above per molecule.  gradient may be NULL (charges + energy only).  Molecules of up to
+ * 208 atoms run in the one-CTA-per-molecule kernels; larger ones are solved one after the other by
+ * the single-system path (mchrg_b200_singlepoint) inside the same call. */
 int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32_t nmol, const int64_t* offsets,
                                  const int32_t* num, const double* xyz, const double* charge,
                                  double* qvec, double* energy, double* gradient, int32_t* status);

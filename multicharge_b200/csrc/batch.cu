@@ -1037,13 +1037,15 @@ namespace mchrg {
 namespace batch {
 
 // bucket the molecules [m0, m1) by padded order; returns the class-sorted permutation (chunk-local ids)
-// and the start of every class in it
+// and the start of every class in it.  Molecules above NP_MAX atoms are left out (the entry point sends
+// them through the single-system path afterwards).
 static void bucket(const std::vector<int64_t>& hoff, int32_t m0, int32_t m1, std::vector<int32_t>& perm,
                    std::vector<size_t>& cls_start, std::vector<int>& cls_count) {
    constexpr int NCLASS = NP_MAX / KB;
    std::vector<std::vector<int32_t>> cls(NCLASS + 1);
    for (int32_t m = m0; m < m1; ++m) {
       const int64_t n = hoff[m + 1] - hoff[m];
+      if (n > NP_MAX) continue;
       cls[(n + KB - 1) / KB].push_back(m - m0);
    }
    perm.clear();
@@ -1090,9 +1092,9 @@ static int64_t plan_scratch(const std::vector<int64_t>& hoff, int32_t m0, int32_
    int64_t total = 0;
    for (int32_t m = m0; m < m1; ++m) {
       const int64_t n = hoff[m + 1] - hoff[m];
-      const int64_t npm = aug_order((int)n);
       soff[m - m0] = total;
-      total += lay_size((int)npm);
+      if (n > NP_MAX) continue;  // not served by the batch kernels
+      total += lay_size(aug_order((int)n));
    }
    return total;
 }
@@ -1145,12 +1147,14 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
                                             double* energy, double* gradient, int32_t* status) {
    if (!model) return MCHRG_B200_ERR_ARG;
    mchrg_b200_context* ctx = model->ctx;
-   return guarded(ctx, [&]() {
+   std::vector<int32_t> large;  // molecules above NP_MAX atoms: single-system path, after the batch kernels
+   std::vector<int64_t> hoff;
+   const int rc = guarded(ctx, [&]() {
       if (nmol <= 0 || !offsets || !num || !xyz || !charge || !qvec || !status)
          fail(MCHRG_B200_ERR_ARG, "singlepoint_batch: missing argument");
       if (model->kind != 1) fail(MCHRG_B200_ERR_MODEL, "singlepoint_batch serves EEQ2019-type models only");
       // molecule sizes are needed on the host to form the size classes
-      std::vector<int64_t> hoff((size_t)nmol + 1);
+      hoff.resize((size_t)nmol + 1);
       if (mchrg_b200_context::is_device_ptr(offsets))
          MCHRG_CUDA(cudaMemcpy(hoff.data(), offsets, hoff.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
       else
@@ -1159,10 +1163,10 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
       for (int32_t m = 0; m < nmol; ++m) {
          const int64_t n = hoff[m + 1] - hoff[m];
          if (n <= 0) fail(MCHRG_B200_ERR_ARG, "singlepoint_batch: molecule %d is empty", m);
-         if (n > batch::NP_MAX)
-            fail(MCHRG_B200_ERR_ARG, "singlepoint_batch: molecule %d has %lld atoms (> %d); use mchrg_b200_singlepoint", m,
-                 (long long)n, batch::NP_MAX);
+         if (n > INT32_MAX) fail(MCHRG_B200_ERR_ARG, "singlepoint_batch: molecule %d is too large", m);
+         if (n > batch::NP_MAX) large.push_back(m);
       }
+      if (large.size() == (size_t)nmol) return 0;
       batch::Args a;
       a.scratch = nullptr; a.soff = nullptr; a.vecg = nullptr; a.lamg = nullptr; a.ntot = 0;
       a.par = model->d_par;
@@ -1301,11 +1305,13 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
          const int32_t m0 = bounds[c], m1 = bounds[c + 1], mc = m1 - m0;
          if (mc <= 0) continue;
          const size_t a0 = (size_t)hoff[m0], na = (size_t)(hoff[m1] - hoff[m0]);
+         batch::bucket(hoff, m0, m1, loc_perm[c], cls_start, cls_count);
+         const int nserved = (int)loc_perm[c].size();
+         if (nserved == 0) continue;  // only molecules above NP_MAX atoms here
          loc_off[c].resize((size_t)mc + 1);
          for (int32_t m = 0; m <= mc; ++m) loc_off[c][m] = hoff[m0 + m] - hoff[m0];
-         batch::bucket(hoff, m0, m1, loc_perm[c], cls_start, cls_count);
          int64_t* d_off = ctx->alloc<int64_t>((size_t)mc + 1);
-         int32_t* d_perm = ctx->alloc<int32_t>(mc);
+         int32_t* d_perm = ctx->alloc<int32_t>(nserved);
          int32_t* d_num = ctx->alloc<int32_t>(na);
          double* d_xyz = ctx->alloc<double>(3 * na);
          double* d_chg = ctx->alloc<double>(mc);
@@ -1315,7 +1321,7 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
          int32_t* d_st = ctx->alloc<int32_t>(mc);
          cudaStream_t in = ctx->stream_in, out = ctx->stream_out;
          MCHRG_CUDA(cudaMemcpyAsync(d_off, loc_off[c].data(), ((size_t)mc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, in));
-         MCHRG_CUDA(cudaMemcpyAsync(d_perm, loc_perm[c].data(), (size_t)mc * sizeof(int32_t), cudaMemcpyHostToDevice, in));
+         MCHRG_CUDA(cudaMemcpyAsync(d_perm, loc_perm[c].data(), (size_t)nserved * sizeof(int32_t), cudaMemcpyHostToDevice, in));
          MCHRG_CUDA(cudaMemcpyAsync(d_num, num + a0, na * sizeof(int32_t), cudaMemcpyHostToDevice, in));
          MCHRG_CUDA(cudaMemcpyAsync(d_xyz, xyz + 3 * a0, 3 * na * sizeof(double), cudaMemcpyHostToDevice, in));
          MCHRG_CUDA(cudaMemcpyAsync(d_chg, charge + m0, (size_t)mc * sizeof(double), cudaMemcpyHostToDevice, in));
@@ -1339,7 +1345,7 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
             a.ntot = (int64_t)na;
             cudaEvent_t ev_in2 = ctx->next_event();
             MCHRG_CUDA(cudaEventRecord(ev_in2, in));
-            ev_done = batch::run_chunk_split(ctx, a, d_perm, mc, cls_start, cls_count, ev_in2, ctx->stream_aux, ctx->stream);
+            ev_done = batch::run_chunk_split(ctx, a, d_perm, nserved, cls_start, cls_count, ev_in2, ctx->stream_aux, ctx->stream);
          } else {
             batch::launch_chunk<0>(ctx, a, d_perm, cls_start, cls_count, ctx->stream, ctx->stream_aux);
             cudaEvent_t aux_done = ctx->next_event();
@@ -1360,4 +1366,32 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
       MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));  // host staging vectors must outlive the async copies
       return 0;
    });
+   if (rc != 0 || large.empty()) return rc;
+   // Molecules the one-CTA-per-molecule kernels cannot hold: the single-system path (blocked Cholesky in HBM),
+   // one after the other, on the same slices of the caller's arrays (host or device).
+   for (int32_t m : large) {
+      const size_t a0 = (size_t)hoff[m], n = (size_t)(hoff[m + 1] - hoff[m]);
+      mchrg_b200_structure mol{};
+      mol.nat = (int32_t)n;
+      mol.nid = model->nid;
+      mol.id = num + a0;  // species index == atomic number for the models this entry point serves
+      mol.xyz = xyz + 3 * a0;
+      if (mchrg_b200_context::is_device_ptr(charge))
+         cudaMemcpy(&mol.charge, charge + m, sizeof(double), cudaMemcpyDeviceToHost);
+      else
+         mol.charge = charge[m];
+      if (energy) {  // the single-system entry point accumulates the energy; the batch overwrites it
+         if (mchrg_b200_context::is_device_ptr(energy)) cudaMemset(energy + a0, 0, n * sizeof(double));
+         else std::fill(energy + a0, energy + a0 + n, 0.0);
+      }
+      double sigma[9] = {0};
+      const int32_t st = mchrg_b200_singlepoint(model, &mol, nullptr, nullptr, energy ? energy + a0 : nullptr,
+                                                gradient ? gradient + 3 * a0 : nullptr, gradient ? sigma : nullptr,
+                                                qvec + a0, nullptr, nullptr);
+      if (mchrg_b200_context::is_device_ptr(status))
+         cudaMemcpy(status + m, &st, sizeof(int32_t), cudaMemcpyHostToDevice);
+      else
+         status[m] = st;
+   }
+   return 0;
 }

@@ -107,12 +107,40 @@ def test_batch_device_resident(mc, oracle):
     assert np.array_equal(out["gradient"].cpu().numpy(), ref["gradient"])
 
 
-def test_batch_rejects_oversized_molecule(mc):
+def test_batch_with_molecules_above_kernel_limit(mc, oracle):
+    """Molecules above the 208 atoms one CTA holds go through the single-system path inside the same call
+    (host and device buffers); their neighbours are unaffected.  Also: a batch made of large molecules only."""
+    import torch
     from synth import cluster
-    num, xyz = cluster(209, 1)
-    offsets = np.array([0, 209], dtype=np.int64)
-    with pytest.raises(mc.MchrgError):
-        mc.singlepoint_batch(mc.new_eeq2019_batch_model(), offsets, num, xyz, np.zeros(1))
+    sizes = [40, 209, 17, 300, 208, 256, 5]
+    nums, xyzs = zip(*[cluster(n, 700 + k) for k, n in enumerate(sizes)])
+    offsets = np.zeros(len(sizes) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    num, xyz = np.concatenate(nums), np.concatenate(xyzs)
+    charge = np.array([(k % 3) - 1.0 for k in range(len(sizes))])
+    model = mc.new_eeq2019_batch_model()
+    q, e, g = oracle_batch(oracle, offsets, num, xyz, charge)
+    out = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    assert np.all(out["status"] == 0)
+    for key, ref in (("qvec", q), ("energy", e), ("gradient", g)):
+        assert np.abs(out[key] - ref).max() < TOL * max(1.0, np.abs(ref).max()), key
+    out2 = mc.singlepoint_batch(model, offsets, num, xyz, charge, gradient=False)
+    assert np.abs(out2["qvec"] - q).max() < TOL and np.abs(out2["energy"] - e).max() < TOL
+    dev = torch.device("cuda:0")
+    ntot = int(offsets[-1])
+    dout = dict(qvec=torch.full((ntot,), 7.0, dtype=torch.float64, device=dev), energy=torch.full((ntot,), 7.0, dtype=torch.float64, device=dev),
+                gradient=torch.full((ntot, 3), 7.0, dtype=torch.float64, device=dev), status=torch.full((len(sizes),), 7, dtype=torch.int32, device=dev))
+    mc.singlepoint_batch(model, torch.tensor(offsets, device=dev), torch.tensor(num, device=dev), torch.tensor(xyz, device=dev),
+                         torch.tensor(charge, device=dev), out=dout)
+    torch.cuda.synchronize()
+    assert np.all(dout["status"].cpu().numpy() == 0)
+    for key in ("qvec", "energy", "gradient"):  # (the single-system gradient sums in a run-dependent order)
+        assert np.abs(dout[key].cpu().numpy() - out[key]).max() < 1e-12, key
+    # large molecules only
+    sl = slice(offsets[3], offsets[4])
+    only = mc.singlepoint_batch(model, np.array([0, 300], dtype=np.int64), num[sl], xyz[sl], charge[3:4])
+    assert only["status"][0] == 0
+    assert np.abs(only["qvec"] - out["qvec"][sl]).max() < 1e-12 and np.abs(only["gradient"] - out["gradient"][sl]).max() < 1e-12
 
 
 def test_batch_pipelined_host_path_equals_device_path(mc):
