@@ -95,16 +95,22 @@ __global__ void gradient_kernel(int jb, int nj, const double* __restrict__ q, co
    if (i < 3 * nj) gradient[i] = q[jb + i / 3] * atrace[3 * jb + i] - gradx[i];
 }
 
-// sigma(a,b) += sum_k q_k (0.5 dadL(a,b,k) - thalf_k dcndL(a,b,k))   (type.F90:279-280); 9 warps
+// sigma(a,b) += sum_k q_k (0.5 dadL(a,b,k) - thalf_k dcndL(a,b,k))   (type.F90:279-280); 9 warps.
+// dcndL == nullptr: the second sum arrives contracted in sig_cn (cn_gradient_device).
 __global__ void __launch_bounds__(288) sigma_kernel(int nat, const double* __restrict__ q,
                                                     const double* __restrict__ dadL, const double* __restrict__ thalf,
-                                                    const double* __restrict__ dcndL, double* __restrict__ sigma) {
+                                                    const double* __restrict__ dcndL, const double* __restrict__ sig_cn,
+                                                    double* __restrict__ sigma) {
    const int ab = threadIdx.x >> 5, lane = threadIdx.x & 31;
    double acc = 0.0;
-   for (int k = lane; k < nat; k += 32)
-      acc += q[k] * (0.5 * dadL[(size_t)9 * k + ab] - thalf[k] * dcndL[(size_t)9 * k + ab]);
+   if (dcndL) {
+      for (int k = lane; k < nat; k += 32)
+         acc += q[k] * (0.5 * dadL[(size_t)9 * k + ab] - thalf[k] * dcndL[(size_t)9 * k + ab]);
+   } else {
+      for (int k = lane; k < nat; k += 32) acc += q[k] * (0.5 * dadL[(size_t)9 * k + ab]);
+   }
    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-   if (lane == 0) sigma[ab] += acc;
+   if (lane == 0) sigma[ab] += acc - (dcndL ? 0.0 : sig_cn[ab]);
 }
 
 // rows 3N..3N+8 of B: dadL(:,:,k) - dxdL(:,:,k) (type.F90:286), and their z-contraction
@@ -251,6 +257,8 @@ struct SolveIO {
    // row block [jb, je) of the derivative outputs (gradient rows, dq/dr rows); je < 0: all atoms.
    // With a proper sub-block, gradient is (3, nj) and dqdr (3, nj, nat).
    int jb = 0, je = -1;
+   // EEQ2019 gradient without dq/dr: CN derivatives contracted on the fly instead of dcndr / dcndL
+   const CnLazy* lazy = nullptr;
 };
 
 static AtomPar gather_eeq(const mchrg_b200_model* model, const DevMol& mol) {
@@ -357,8 +365,9 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
    const int nat = mol.nat;
    const int64_t npad = round_up(nat, TILE);
    const bool dcn = io.dcndr && io.dcndL;
-   const bool grad = io.gradient && io.sigma && dcn;
    const bool cpq = io.dqdr && io.dqdL && dcn;
+   const bool lazy = io.lazy && !cpq;
+   const bool grad = io.gradient && io.sigma && (dcn || lazy);
    const bool pbc = mol.periodic;
    const int jb = io.jb, je = io.je < 0 ? nat : io.je, nj = je - jb;
    if (jb < 0 || je > nat || nj <= 0) fail(MCHRG_B200_ERR_ARG, "invalid row block [%d, %d)", jb, je);
@@ -415,10 +424,16 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
 
       if (grad || cpq) {
          double* gradx = grad ? ctx->alloc_zero<double>((size_t)3 * nj) : nullptr;
-         eeq_build_b_0d(ctx, mol, ap.rad, vrhs, atrace, thalf, io.dcndr, Bm, mp, gradx, zvec, bz, pbc && cpq, jb, je);
+         double* sig_cn = nullptr;
+         if (lazy) {
+            sig_cn = ctx->alloc<double>(9);
+            cn_gradient_device(ctx, mol, *io.lazy, thalf, vrhs, jb, je, gradx, sig_cn);
+         } else {
+            eeq_build_b_0d(ctx, mol, ap.rad, vrhs, atrace, thalf, io.dcndr, Bm, mp, gradx, zvec, bz, pbc && cpq, jb, je);
+         }
          if (grad) {
             MCHRG_LAUNCH(ctx, gradient_kernel, (3 * nj + 255) / 256, 256, 0, jb, nj, vrhs, atrace, gradx, io.gradient);
-            MCHRG_LAUNCH(ctx, sigma_kernel, 1, 288, 0, nat, vrhs, dadL, thalf, io.dcndL, io.sigma);
+            MCHRG_LAUNCH(ctx, sigma_kernel, 1, 288, 0, nat, vrhs, dadL, thalf, lazy ? nullptr : io.dcndL, sig_cn, io.sigma);
          }
          if (cpq) {
             MCHRG_LAUNCH(ctx, strain_rows_kernel, 1, 288, 0, nat, dadL, thalf, io.dcndL, zvec, Bm, mp, bz,
@@ -1094,6 +1109,12 @@ int mchrg_b200_solve(const mchrg_b200_model* model, const mchrg_b200_structure* 
    });
 }
 
+// MCHRG_B200_CN_DERIVS=dense keeps the (3, N, N) CN derivative array on the gradient-only path (A/B timing, tests)
+static bool lazy_cn_enabled() {
+   const char* e = std::getenv("MCHRG_B200_CN_DERIVS");
+   return !(e && e[0] == 'd');
+}
+
 static int singlepoint_impl(const mchrg_b200_model* model, const mchrg_b200_structure* mol, double* cn, double* qloc,
                             double* energy, double* gradient, double* sigma, double* qvec, double* dqdr,
                             double* dqdL, bool accumulate, int jb = 0, int je = -1) {
@@ -1107,9 +1128,16 @@ static int singlepoint_impl(const mchrg_b200_model* model, const mchrg_b200_stru
       double* rcov_a = ctx->alloc<double>(n);
       gather_species(ctx, d.nat, d.id, model->dev(4), rcov_a);
       double* d_cn = cn ? ctx->out(cn, n) : ctx->alloc<double>(n);
-      double* d_dcndr = grad ? ctx->alloc<double>(3 * n * n) : nullptr;
-      double* d_dcndL = grad ? ctx->alloc<double>(9 * n) : nullptr;
-      ncoord_device(ctx, d, rcov_a, nullptr, model->ncoord, ntr, trans, d_cn, d_dcndr, d_dcndL);
+      // EEQ2019 without dq/dr: the CN derivatives are contracted pair by pair after the solve (CnLazy)
+      const bool lazy = grad && !dqdr && model->kind == 1 && lazy_cn_enabled();
+      double* d_dcndr = (grad && !lazy) ? ctx->alloc<double>(3 * n * n) : nullptr;
+      double* d_dcndL = (grad && !lazy) ? ctx->alloc<double>(9 * n) : nullptr;
+      CnLazy lz;
+      ncoord_device(ctx, d, rcov_a, nullptr, model->ncoord, ntr, trans, d_cn, d_dcndr, d_dcndL, &lz.cn_raw);
+      lz.par = model->ncoord;
+      lz.rcov_a = rcov_a;
+      lz.trans = trans;
+      lz.ntr = ntr;
       double* d_qloc = qloc ? ctx->out(qloc, n) : ctx->alloc<double>(n);
       double *d_dqlr = nullptr, *d_dqlL = nullptr;
       if (model->kind == 1) {
@@ -1134,6 +1162,7 @@ static int singlepoint_impl(const mchrg_b200_model* model, const mchrg_b200_stru
       const size_t nj = (je < 0) ? n : (size_t)std::max(0, je - jb);
       io.jb = jb;
       io.je = je;
+      io.lazy = lazy ? &lz : nullptr;
       io.energy = ctx->out(energy, n, accumulate);
       io.gradient = ctx->out(gradient, 3 * nj);
       io.sigma = ctx->out(sigma, 9, accumulate);

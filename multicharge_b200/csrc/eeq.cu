@@ -41,6 +41,14 @@ struct NcDev {
    int use_en;
 };
 
+// Range of the erf counting function: for kcn (r - rc) / rcn > XMAX the count 1/2 (1 - erf) is zero to the last
+// bit and its derivative below 5e-19 (the table clamps there), so pairs beyond rc + XMAX rcn / kcn (~ 2 rc for
+// kcn = 7.5, far inside the 25 Bohr cutoff of the reference) contribute nothing.  Returns the squared range.
+__device__ __forceinline__ double count_range2(const NcDev& p, double rc, double rcn) {
+   const double rmax = fma(eg::XMAX / p.kcn, rcn, rc);
+   return fmin(p.cutoff2, rmax * rmax);
+}
+
 // erf / exp(-x^2) through the node table of erfgauss.cuh (shared-memory copy per CTA) and 1/sqrt through the
 // hardware seed + one third-order step: ~4x fewer instructions per pair than the library functions
 #define MCHRG_LOAD_ERF_TABLE(etab_global)                                            \
@@ -65,10 +73,11 @@ __global__ void __launch_bounds__(256) cn_rows_kernel(int nat, const double* __r
       const double rcn = (p.norm_exp == 1.0) ? rc : pow(rc, p.norm_exp);
       const double den = p.use_en ? (en[j] - eni) : 1.0;
       const double dx = xi - xyz[3 * j], dy = yi - xyz[3 * j + 1], dz = zi - xyz[3 * j + 2];
+      const double cut2 = count_range2(p, rc, rcn);
       for (int itr = 0; itr < ntr; ++itr) {
          const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
          const double r2 = rx * rx + ry * ry + rz * rz;
-         if (r2 > p.cutoff2 || r2 < 1.0e-12) continue;
+         if (r2 > cut2 || r2 < 1.0e-12) continue;
          const double r1 = r2 * eg::fast_rsqrt(r2);
          const double a = p.kcn * (r1 - rc) / rcn;
          double g;
@@ -105,10 +114,11 @@ __global__ void __launch_bounds__(256) cn_derivs_kernel(int nat, const double* _
       const double den = p.use_en ? (en[j] - eni) : 1.0;
       const double dx = xi - xyz[3 * j], dy = yi - xyz[3 * j + 1], dz = zi - xyz[3 * j + 2];
       double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+      const double cut2 = count_range2(p, rc, rcn);
       for (int itr = 0; itr < ntr; ++itr) {
          const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
          const double r2 = rx * rx + ry * ry + rz * rz;
-         if (r2 > p.cutoff2 || r2 < 1.0e-12) continue;
+         if (r2 > cut2 || r2 < 1.0e-12) continue;
          const double rinv = eg::fast_rsqrt(r2);
          const double arg = p.kcn * (r2 * rinv - rc) / rcn;
          double g;
@@ -147,10 +157,12 @@ __global__ void cn_cut_kernel(int nat, double cut, const double* __restrict__ cn
 }
 
 void ncoord_device(mchrg_b200_context* ctx, const DevMol& mol, const double* rcov_a, const double* en_a,
-                   const NcoordPar& par, int ntr, const double* trans, double* cn, double* dcndr, double* dcndL) {
+                   const NcoordPar& par, int ntr, const double* trans, double* cn, double* dcndr, double* dcndL,
+                   const double** cn_raw_out) {
    const int nat = mol.nat;
    NcDev p{par.kcn, par.norm_exp, par.cutoff * par.cutoff, par.cut, en_a != nullptr};
    double* cn_raw = ctx->alloc<double>(nat);
+   if (cn_raw_out) *cn_raw_out = cn_raw;
    const int rows_per_cta = 8;
    const unsigned grid = (nat + rows_per_cta - 1) / rows_per_cta;
    MCHRG_LAUNCH(ctx, cn_rows_kernel, grid, 256, 0, nat, mol.xyz, rcov_a, en_a, p, ntr, trans, cn_raw, ctx->erf_tab);
@@ -158,6 +170,99 @@ void ncoord_device(mchrg_b200_context* ctx, const DevMol& mol, const double* rco
       MCHRG_LAUNCH(ctx, cn_derivs_kernel, grid, 256, 0, nat, mol.xyz, rcov_a, en_a, p, ntr, trans, cn_raw, dcndr, dcndL,
                    ctx->erf_tab);
    MCHRG_LAUNCH(ctx, cn_cut_kernel, (nat + 255) / 256, 256, 0, nat, par.cut, cn_raw, cn);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The dcndr / dcndL contractions of the gradient and the stress WITHOUT the (3, N, N) array (6.4 GB at
+// N = 16384): with w_k = thalf_k q_k (type.F90:277-280 with dxdr of eeq.f90:172-177) and the log-cut factor f_k,
+//    gradx_j  = sum_k w_k dcndr(:, j, k) = sum_{k != j} (w_j f_j + w_k f_k) G_jk ,
+//    sig_cn   = sum_k w_k dcndL(:, :, k) = sum_j w_j f_j sum_k sum_t c_jk(t) (x) r_jk(t) ,
+// G_jk = sum_t c_jk(t), c_jk(t) = countd(|r_jk(t)|) r_jk(t) / |r_jk(t)|, r_jk(t) = r_j - r_k - t
+// (dcn_k/dr_j = -f_k G_kj = +f_k G_jk: the translation set of get_lattice_points is symmetric, t <-> -t).
+// One warp per atom j; same pair arithmetic as cn_derivs_kernel.  cn_count%erf only (no EN weights).
+// ---------------------------------------------------------------------------------------------
+__global__ void cn_weight_kernel(int nat, double cut, const double* __restrict__ cn_raw, const double* __restrict__ thalf,
+                                 const double* __restrict__ q, double* __restrict__ wf) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= nat) return;
+   double fcut = 1.0;
+   if (cut > 0.0) {
+      const double ecut = exp(cut);
+      fcut = ecut / (ecut + exp(cn_raw[i]));
+   }
+   wf[i] = thalf[i] * q[i] * fcut;
+}
+
+__global__ void __launch_bounds__(256) cn_grad_rows_kernel(int nat, const double* __restrict__ xyz,
+                                                           const double* __restrict__ rcov, NcDev p, int ntr,
+                                                           const double* __restrict__ trans,
+                                                           const double* __restrict__ wf, int jb, int je,
+                                                           double* __restrict__ gradx, double* __restrict__ sig_cn,
+                                                           const double2* __restrict__ etab) {
+   MCHRG_LOAD_ERF_TABLE(etab);
+   __shared__ double sred[8][9];
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const int j = blockIdx.x * 8 + warp;
+   double gs[3] = {0.0, 0.0, 0.0};
+   double dl[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+   if (j < nat) {
+      const double xj = xyz[3 * j], yj = xyz[3 * j + 1], zj = xyz[3 * j + 2];
+      const double rcj = rcov[j], wj = wf[j];
+      for (int k = lane; k < nat; k += 32) {
+         const double rc = rcj + rcov[k];
+         const double rcn = (p.norm_exp == 1.0) ? rc : pow(rc, p.norm_exp);
+         const double dx = xj - xyz[3 * k], dy = yj - xyz[3 * k + 1], dz = zj - xyz[3 * k + 2];
+         const double wjk = (k != j) ? wj + wf[k] : 0.0;  // self images cancel in dcndr
+         const double pre = -p.kcn / SQRTPI / rcn;
+         const double cut2 = count_range2(p, rc, rcn);
+         for (int itr = 0; itr < ntr; ++itr) {
+            const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
+            const double r2 = rx * rx + ry * ry + rz * rz;
+            if (r2 > cut2 || r2 < 1.0e-12) continue;
+            const double rinv = eg::fast_rsqrt(r2);
+            const double arg = p.kcn * (r2 * rinv - rc) / rcn;
+            double g;
+            eg::erf_gauss<6, true>(setab, fabs(arg), g);  // g = exp(-arg^2)
+            const double dc = pre * g * rinv;
+            const double c0 = dc * rx, c1 = dc * ry, c2 = dc * rz;  // countd
+            gs[0] = fma(wjk, c0, gs[0]); gs[1] = fma(wjk, c1, gs[1]); gs[2] = fma(wjk, c2, gs[2]);
+            dl[0] += c0 * rx; dl[1] += c0 * ry; dl[2] += c0 * rz;
+            dl[3] += c1 * rx; dl[4] += c1 * ry; dl[5] += c1 * rz;
+            dl[6] += c2 * rx; dl[7] += c2 * ry; dl[8] += c2 * rz;
+         }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gs[c] = warp_sum(gs[c]);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) dl[c] = warp_sum(dl[c]) * wj;
+      if (lane == 0 && j >= jb && j < je) {
+#pragma unroll
+         for (int c = 0; c < 3; ++c) gradx[3 * (size_t)(j - jb) + c] = gs[c];
+      }
+   }
+   if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) sred[warp][c] = dl[c];
+   }
+   __syncthreads();
+   if (threadIdx.x < 9) {
+      double acc = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) acc += sred[w][threadIdx.x];
+      atomicAdd(sig_cn + threadIdx.x, acc);
+   }
+}
+
+void cn_gradient_device(mchrg_b200_context* ctx, const DevMol& mol, const CnLazy& lz, const double* thalf, const double* q,
+                        int jb, int je, double* gradx, double* sig_cn) {
+   const int nat = mol.nat;
+   if (je < 0) je = nat;
+   NcDev p{lz.par.kcn, lz.par.norm_exp, lz.par.cutoff * lz.par.cutoff, lz.par.cut, 0};
+   double* wf = ctx->alloc<double>(nat);
+   MCHRG_LAUNCH(ctx, cn_weight_kernel, (nat + 255) / 256, 256, 0, nat, lz.par.cut, lz.cn_raw, thalf, q, wf);
+   MCHRG_CUDA(cudaMemsetAsync(sig_cn, 0, 9 * sizeof(double), ctx->active));
+   MCHRG_LAUNCH(ctx, cn_grad_rows_kernel, (unsigned)((nat + 7) / 8), 256, 0, nat, mol.xyz, lz.rcov_a, p, lz.ntr, lz.trans, wf,
+                jb, je, gradx, sig_cn, ctx->erf_tab);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -11,8 +11,23 @@ void gather_species(mchrg_b200_context* ctx, int nat, const int* id, const doubl
 // ---- mctc_ncoord%get_coordination_number -----------------------------------------------------
 // cn[nat]; dcndr[3*nat*nat], dcndL[9*nat] optional (both or none).  en_a == nullptr: cn_count%erf,
 // else erf_en (directed, weighted by en_j - en_i).  trans: device [3*ntr].
+// cn_raw_out (optional) receives the device array of the CN before the log cut (lives in the call's arena).
 void ncoord_device(mchrg_b200_context* ctx, const DevMol& mol, const double* rcov_a, const double* en_a,
-                   const NcoordPar& par, int ntr, const double* trans, double* cn, double* dcndr, double* dcndL);
+                   const NcoordPar& par, int ntr, const double* trans, double* cn, double* dcndr, double* dcndL,
+                   const double** cn_raw_out = nullptr);
+
+// What the solve needs to contract the CN derivatives on the fly instead of reading dcndr / dcndL
+// (single points without dq/dr: the (3, N, N) array is never formed).
+struct CnLazy {
+   NcoordPar par;
+   const double* rcov_a = nullptr;
+   const double* cn_raw = nullptr;
+   const double* trans = nullptr;
+   int ntr = 0;
+};
+// gradx(3, je - jb) = sum_k thalf_k q_k dcndr(:, j, k) for the rows [jb, je);  sig_cn(3, 3) = sum_k thalf_k q_k dcndL(:, :, k)
+void cn_gradient_device(mchrg_b200_context* ctx, const DevMol& mol, const CnLazy& lz, const double* thalf, const double* q,
+                        int jb, int je, double* gradx, double* sig_cn);
 
 // ---- EEQ2019 -----------------------------------------------------------------------------------
 // get_xvec (eeq.f90:127-150): xvec[nat+1]; thalf[nat] (optional) = 0.5 * kcnchi / sqrt(cn + reg),

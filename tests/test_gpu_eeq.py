@@ -132,3 +132,22 @@ def test_device_resident_inputs(mc, oracle):
     r = model.singlepoint(mol, xyz=txyz, id=tid)
     for key in ("qvec", "energy", "gradient"):
         assert np.abs(r[key] - o[key]).max() < TOL * max(1.0, np.abs(o[key]).max()), key
+
+
+def test_gradient_without_dcndr(mc, oracle, monkeypatch):
+    """Single points without dq/dr contract the CN derivatives pair by pair (no (3, N, N) array): gradient and
+    sigma against the oracle, against the dense-dcndr route (MCHRG_B200_CN_DERIVS=dense), and for a row block."""
+    from synth import cluster
+    num, xyz = cluster(777, 31)
+    mol, model, omol, omodel = both(mc, oracle, num, xyz, -1.0)
+    o = oracle.eeq_singlepoint(omodel, omol, want=("qvec", "energy", "gradient"))
+    r = model.singlepoint(mol, want=("qvec", "energy", "gradient"))
+    rows = mc.singlepoint_rows(model, mol, 100, 333, dqdr=False)
+    monkeypatch.setenv("MCHRG_B200_CN_DERIVS", "dense")
+    d = model.singlepoint(mol, want=("qvec", "energy", "gradient"))
+    for key in ("qvec", "energy", "gradient", "sigma"):
+        scale = max(1.0, np.abs(o[key]).max())
+        assert np.abs(r[key] - o[key]).max() < TOL * scale, key
+        assert np.abs(r[key] - d[key]).max() < 1e-12 * scale, key
+    assert np.abs(rows["gradient"] - o.gradient[100:333]).max() < TOL
+    assert np.abs(rows["sigma"] - o.sigma).max() < TOL * max(1.0, np.abs(o.sigma).max())

@@ -72,3 +72,20 @@ def test_periodic_medium(mc, oracle):
     o = oracle.eeq_singlepoint(oracle.new_eeq2019_model(omol), omol, want=("qvec", "energy", "gradient", "dqdr"))
     for key in ("qvec", "energy", "gradient", "sigma", "dqdr", "dqdL"):
         assert close(r[key], o[key]), key
+
+
+@pytest.mark.parametrize("case", cells(), ids=lambda c: c[0])
+def test_periodic_gradient_without_dcndr(mc, oracle, case, monkeypatch):
+    """Single points without dq/dr contract the CN derivatives pair by pair (no (3, N, N) array): gradient and
+    sigma against the oracle, and against the dense-dcndr route (MCHRG_B200_CN_DERIVS=dense)."""
+    _, num, xyz, lat, chg = case
+    mol = mc.Structure(num, xyz, chg, lattice=lat)
+    omol = oracle.Mol(num, xyz, chg, lattice=lat)
+    model, omodel = mc.new_eeq2019_model(mol), oracle.new_eeq2019_model(omol)
+    o = oracle.eeq_singlepoint(omodel, omol, want=("qvec", "energy", "gradient"))
+    r = model.singlepoint(mol, want=("qvec", "energy", "gradient"))
+    monkeypatch.setenv("MCHRG_B200_CN_DERIVS", "dense")
+    d = model.singlepoint(mol, want=("qvec", "energy", "gradient"))
+    for key in ("qvec", "energy", "gradient", "sigma"):
+        assert close(r[key], o[key]), key
+        assert close(r[key], d[key], 1e-12), key

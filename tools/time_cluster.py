@@ -28,7 +28,9 @@ for nat in [int(a) for a in sys.argv[1:]] or [4096, 8192, 16384]:
     f64 = dict(dtype=torch.float64, device=dev)
     bufs = dict(cn=torch.empty(nat, **f64), qloc=torch.empty(nat, **f64), energy=torch.zeros(nat, **f64),
                 gradient=torch.empty(nat, 3, **f64), sigma=torch.zeros(3, 3, **f64), qvec=torch.empty(nat, **f64),
-                dqdr=torch.empty(nat, nat, 3, **f64), dqdL=torch.empty(nat, 3, 3, **f64))
+                dqdL=torch.empty(nat, 3, 3, **f64))
+    if not os.environ.get("NO_DQ"):
+        bufs["dqdr"] = torch.empty(nat, nat, 3, **f64)
     s = mol._c(xyz=txyz, id=tid)
     p = lambda k: bufs[k].data_ptr()  # noqa: E731
 
@@ -37,7 +39,7 @@ for nat in [int(a) for a in sys.argv[1:]] or [4096, 8192, 16384]:
                                                 p("qvec"), p("dqdr") if dq else None, p("dqdL") if dq else None)
         assert rc == 0, rc
 
-    for dq in (False, True):
+    for dq in ((False,) if os.environ.get("NO_DQ") else (False, True)):
         run(dq)
         best = 1e30
         for _ in range(2):
