@@ -474,7 +474,10 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "batch kernels of one step: eeq_batch_kernel<.,1> (pair phase A) + eeq_factor_ll_kernel + eeq_batch_kernel<.,3> (pair phase C), all size classes",
                      "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                     "traffic": None,
+                     "traffic": NCU_DRAM_BYTES_PER_MOLECULE * nmol,
+                     "traffic_source": "DRAM bytes of the three kernels from one ncu --set full capture of 5000 molecules of this "
+                                       "distribution (profiles/r1_final_batch_kernels_ncu_key_metrics.txt: 0.370 + 0.822 + 0.352 GB), "
+                                       "scaled to the molecules of one launch set; compute bound, so well under peak HBM rate",
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                      "algorithmic_flops_per_launch_set": flops, "seconds_per_launch_set": kernel_s},
         "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cpu_thr, "kind": "port",
@@ -485,6 +488,11 @@ def run_ours(args):
         line["extra"] = extra
     print(json.dumps(line), flush=True)
     return 0
+
+
+# DRAM traffic of pair phase A + factorisation + pair phase C per molecule of the bench distribution, from the ncu
+# --set full capture under profiles/ (DRAM throughput x duration of one launch of each kernel over 5000 molecules)
+NCU_DRAM_BYTES_PER_MOLECULE = (1.12e12 * 330.62e-6 + 1.53e12 * 537.18e-6 + 742.31e9 * 474.62e-6) / 5000
 
 
 def main():

@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(128) eeq_amat0d_kernel(int nat, const double* 
             const double r2 = dx * dx + dy * dy + dz * dz;
             const double rinv = eg::fast_rsqrt(r2), gam = eg::fast_rsqrt(rr + rad[c] * rad[c]);
             double g;
-            v = eg::erf_gauss<5, false>(setab, r2 * rinv * gam, g) * rinv;  // erf(gamma r) / r
+            const double x = r2 * rinv * gam;  // far field: erf == 1 to the last bit beyond the table range
+            v = (x < eg::XMAX) ? eg::erf_gauss<5, false>(setab, x, g) * rinv : rinv;  // erf(gamma r) / r
          }
       } else if (border) {
          v = (r == nat && c == nat) ? 0.0 : 1.0;
@@ -359,8 +360,10 @@ __global__ void __launch_bounds__(256) eeq_pair_rows0d_kernel(int nat, const dou
       const double vx = xyz[3 * j] - xi, vy = xyz[3 * j + 1] - yi, vz = xyz[3 * j + 2] - zi;
       const double r2 = vx * vx + vy * vy + vz * vz;
       const double rinv = eg::fast_rsqrt(r2), gam = eg::fast_rsqrt(ri2 + rad[j] * rad[j]);
-      double gs;
-      const double ef = eg::erf_gauss<6, true>(setab, r2 * rinv * gam, gs);  // erf(x), exp(-x^2), x = gamma r
+      // erf(x), exp(-x^2), x = gamma r; far field (x beyond the table range): erf == 1 to the last bit, exp(-x^2) < 5e-19
+      const double x = r2 * rinv * gam;
+      double gs = 0.0, ef = 1.0;
+      if (x < eg::XMAX) ef = eg::erf_gauss<6, true>(setab, x, gs);
       const double qj = q[j];
       sj = fma(ef * rinv, qj, sj);
       if (want_d) {
@@ -455,8 +458,9 @@ __global__ void __launch_bounds__(128) eeq_build_b0d_kernel(int nat, const doubl
          const double vx = xj - sk[kk][0], vy = yj - sk[kk][1], vz = zj - sk[kk][2];
          const double r2 = vx * vx + vy * vy + vz * vz;
          const double rinv = eg::fast_rsqrt(r2), gam = eg::fast_rsqrt(rj2 + sk[kk][3]);
-         double gs;
-         const double ef = eg::erf_gauss<6, true>(setab, r2 * rinv * gam, gs);
+         const double x = r2 * rinv * gam;
+         double gs = 0.0, ef = 1.0;
+         if (x < eg::XMAX) ef = eg::erf_gauss<6, true>(setab, x, gs);  // far field: erf == 1, exp(-x^2) < 5e-19
          const double dtmp = (2.0 / SQRTPI * gam * gs - ef * rinv) * rinv * rinv * qj;
          b0 = dtmp * vx; b1 = dtmp * vy; b2 = dtmp * vz;
       }
