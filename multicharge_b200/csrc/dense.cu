@@ -6,6 +6,7 @@
 // and gemm/gemv/symv (blas.F90, called from model/type.F90:235-290).
 #include <cstdio>
 #include "dense.cuh"
+#include "erfgauss.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -24,12 +25,18 @@ namespace mchrg {
 namespace gemm {
 constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 512;
 constexpr int LDAS = BM + 4;
-constexpr int LDBT = BN + 4;
 constexpr int LDBN = BK + 4;
 constexpr int A_STAGE = BK * LDAS;                                             // 2112 doubles
-constexpr int B_STAGE = (BK * LDBT > BN * LDBN) ? BK * LDBT : BN * LDBN;       // 2560 doubles
-constexpr int STAGE = A_STAGE + B_STAGE;
-constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE * sizeof(double);         // 149504 B
+// CTA tile 128 x BNT (BNT = 128: 16 warps, one CTA per SM; BNT = 64: 8 warps, two CTAs per SM, so that the
+// C read-modify-write and the pipeline fill of one CTA hide behind the DMMA loop of the other)
+template <int BNT>
+struct Cfg {
+   static constexpr int LDBT = BNT + 4;
+   static constexpr int B_STAGE = (BK * LDBT > BNT * LDBN) ? BK * LDBT : BNT * LDBN;
+   static constexpr int STAGE = A_STAGE + B_STAGE;
+   static constexpr int NTHREADS = 4 * BNT;  // 4 x (BNT / 32) warps of 32 x 32
+   static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE * sizeof(double);  // 149504 B / 108544 B
+};
 }  // namespace gemm
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -48,20 +55,24 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                 : "d"(a), "d"(b));
 }
 
-template <bool TRANSB>
-__global__ void __launch_bounds__(gemm::THREADS, 1)
+template <bool TRANSB, int BNT>
+__global__ void __launch_bounds__(gemm::Cfg<BNT>::NTHREADS, 128 / BNT)
 dgemm_dmma_kernel(int64_t kdim, double alpha, const double* __restrict__ A, int64_t lda,
                   const double* __restrict__ B, int64_t ldb, double beta, double* C, int64_t ldc,
                   int lower_only, int4 cyc) {
    using namespace gemm;
+   constexpr int LDBT = Cfg<BNT>::LDBT, STAGE = Cfg<BNT>::STAGE, NTHR = Cfg<BNT>::NTHREADS;
+   constexpr int NSPLIT = BN / BNT;  // column slices of a 128 x 128 tile (one CTA each)
    extern __shared__ __align__(16) double smem[];
 
+   const int bx = (lower_only ? (int)blockIdx.x / NSPLIT : (int)blockIdx.x);
+   const int slice = lower_only ? (int)blockIdx.x % NSPLIT : 0;
    int tm, tn;
    if (lower_only == 2) {
       // block-cyclic trailing update of the multi-GPU factorisation: the owned block columns are cyc.w tiles wide,
       // start at tile column cyc.x and repeat every cyc.y tile columns; cyc.z = tile rows of the matrix.
       // Lower tiles (tm >= tn) only, numbered column by column.
-      int b = blockIdx.x, t0 = cyc.x;
+      int b = bx, t0 = cyc.x;
       tm = tn = 0;
       for (bool found = false; !found; t0 += cyc.y) {
          for (int w = 0; w < cyc.w && t0 + w < cyc.z; ++w) {
@@ -71,7 +82,7 @@ dgemm_dmma_kernel(int64_t kdim, double alpha, const double* __restrict__ A, int6
          }
       }
    } else if (lower_only) {  // linear index over the lower block triangle
-      const int b = blockIdx.x;
+      const int b = bx;
       int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
       while ((int64_t)(r + 1) * (r + 2) / 2 <= b) ++r;
       while ((int64_t)r * (r + 1) / 2 > b) --r;
@@ -79,9 +90,9 @@ dgemm_dmma_kernel(int64_t kdim, double alpha, const double* __restrict__ A, int6
       tn = b - r * (r + 1) / 2;
    } else {
       tm = blockIdx.x;
-      tn = blockIdx.y;
+      tn = blockIdx.y;  // in units of BNT columns
    }
-   const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+   const int64_t m0 = (int64_t)tm * BM, n0 = lower_only ? (int64_t)tn * BN + slice * BNT : (int64_t)tn * BNT;
    const int tid = threadIdx.x;
    const int lane = tid & 31, warp = tid >> 5;
    const int wm = warp & 3, wn = warp >> 2;
@@ -94,22 +105,22 @@ dgemm_dmma_kernel(int64_t kdim, double alpha, const double* __restrict__ A, int6
       double* As = smem + (size_t)stage * STAGE;
       double* Bs = As + A_STAGE;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {  // A: 16 k-columns x 64 16-byte chunks
-         const int c = tid + i * THREADS;
+      for (int i = 0; i < BK * (BM / 2) / NTHR; ++i) {  // A: 16 k-columns x 64 16-byte chunks
+         const int c = tid + i * NTHR;
          const int k = c >> 6, m2 = (c & 63) * 2;
          cp_async16(As + k * LDAS + m2, Ag + (k0 + k) * lda + m2);
       }
       if (TRANSB) {
 #pragma unroll
-         for (int i = 0; i < 2; ++i) {
-            const int c = tid + i * THREADS;
-            const int k = c >> 6, n2 = (c & 63) * 2;
+         for (int i = 0; i < BK * (BNT / 2) / NTHR; ++i) {  // B: 16 k-columns x BNT / 2 chunks
+            const int c = tid + i * NTHR;
+            const int k = c / (BNT / 2), n2 = (c % (BNT / 2)) * 2;
             cp_async16(Bs + k * LDBT + n2, Bg + (k0 + k) * ldb + n2);
          }
       } else {
 #pragma unroll
-         for (int i = 0; i < 2; ++i) {  // B: 128 n-columns x 8 chunks along k
-            const int c = tid + i * THREADS;
+         for (int i = 0; i < BNT * (BK / 2) / NTHR; ++i) {  // B: BNT n-columns x 8 chunks along k
+            const int c = tid + i * NTHR;
             const int n = c >> 3, k2 = (c & 7) * 2;
             cp_async16(Bs + n * LDBN + k2, Bg + (int64_t)n * ldb + k0 + k2);
          }
@@ -179,14 +190,36 @@ dgemm_dmma_kernel(int64_t kdim, double alpha, const double* __restrict__ A, int6
       }
 }
 
+// MCHRG_B200_GEMM_BN = 64 | 128 (A/B timing); default chosen on B200
+static int gemm_bn() {
+   static const int v = std::getenv("MCHRG_B200_GEMM_BN") ? atoi(std::getenv("MCHRG_B200_GEMM_BN")) : 64;
+   return v == 128 ? 128 : 64;
+}
+
 static void gemm_setup_once() {
    static bool done = false;
    if (done) return;
-   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)gemm::SMEM_BYTES));
-   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)gemm::SMEM_BYTES));
+   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)gemm::Cfg<128>::SMEM_BYTES));
+   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)gemm::Cfg<128>::SMEM_BYTES));
+   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)gemm::Cfg<64>::SMEM_BYTES));
+   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)gemm::Cfg<64>::SMEM_BYTES));
    done = true;
+}
+
+template <int BNT>
+static void gemm_launch(mchrg_b200_context* ctx, bool transb, dim3 grid, int64_t k, double alpha, const double* A,
+                        int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int mode, int4 cyc) {
+   using cfg = gemm::Cfg<BNT>;
+   if (transb)
+      MCHRG_LAUNCH(ctx, (dgemm_dmma_kernel<true, BNT>), grid, cfg::NTHREADS, cfg::SMEM_BYTES, k, alpha, A, lda, B, ldb, beta,
+                   C, ldc, mode, cyc);
+   else
+      MCHRG_LAUNCH(ctx, (dgemm_dmma_kernel<false, BNT>), grid, cfg::NTHREADS, cfg::SMEM_BYTES, k, alpha, A, lda, B, ldb, beta,
+                   C, ldc, mode, cyc);
 }
 
 void dgemm_padded(mchrg_b200_context* ctx, bool transb, int64_t m, int64_t n, int64_t k, double alpha,
@@ -197,20 +230,19 @@ void dgemm_padded(mchrg_b200_context* ctx, bool transb, int64_t m, int64_t n, in
       fail(MCHRG_B200_ERR_ARG, "dgemm_padded: unpadded operand (m=%lld n=%lld k=%lld lda=%lld ldb=%lld)",
            (long long)m, (long long)n, (long long)k, (long long)lda, (long long)ldb);
    gemm_setup_once();
+   // in-place products (X <- X inv(L)^T: every CTA reads the whole row block of X) need one CTA per row block
+   const int bnt = (A == C || B == C) ? 128 : gemm_bn();
+   const unsigned nsplit = (unsigned)(gemm::BN / bnt);
    dim3 grid;
    if (lower_only) {
       const int64_t tiles = m / gemm::BM;
-      grid = dim3((unsigned)(tiles * (tiles + 1) / 2), 1, 1);
+      grid = dim3((unsigned)(tiles * (tiles + 1) / 2) * nsplit, 1, 1);
    } else {
-      grid = dim3((unsigned)(m / gemm::BM), (unsigned)(n / gemm::BN), 1);
+      grid = dim3((unsigned)(m / gemm::BM), (unsigned)(n / bnt), 1);
    }
    const int4 none = make_int4(0, 0, 0, 0);
-   if (transb)
-      MCHRG_LAUNCH(ctx, dgemm_dmma_kernel<true>, grid, gemm::THREADS, gemm::SMEM_BYTES, k, alpha, A, lda, B, ldb,
-                   beta, C, ldc, lower_only ? 1 : 0, none);
-   else
-      MCHRG_LAUNCH(ctx, dgemm_dmma_kernel<false>, grid, gemm::THREADS, gemm::SMEM_BYTES, k, alpha, A, lda, B, ldb,
-                   beta, C, ldc, lower_only ? 1 : 0, none);
+   if (bnt == 64) gemm_launch<64>(ctx, transb, grid, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0, none);
+   else gemm_launch<128>(ctx, transb, grid, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0, none);
 }
 
 // W(:, owned block columns) -= P P^T restricted to the lower tiles, P = W(:, c0 : c0 + k) (n x k panel, global
@@ -224,8 +256,9 @@ static void dsyrk_cyclic(mchrg_b200_context* ctx, int64_t n, int64_t k, const do
       for (int w = 0; w < wt && t + w < T; ++w) tiles += T - t - w;
    if (tiles == 0) return;
    gemm_setup_once();
-   MCHRG_LAUNCH(ctx, dgemm_dmma_kernel<true>, dim3((unsigned)tiles), gemm::THREADS, gemm::SMEM_BYTES, k, -1.0, P, ldw, P, ldw,
-                1.0, W, ldw, 2, make_int4(t0, stride, T, wt));
+   const int4 cyc = make_int4(t0, stride, T, wt);
+   if (gemm_bn() == 64) gemm_launch<64>(ctx, true, dim3((unsigned)tiles * 2), k, -1.0, P, ldw, P, ldw, 1.0, W, ldw, 2, cyc);
+   else gemm_launch<128>(ctx, true, dim3((unsigned)tiles), k, -1.0, P, ldw, P, ldw, 1.0, W, ldw, 2, cyc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -276,7 +309,7 @@ potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv
             failed = true;
             break;
          }
-         const double inv = rsqrt(d);
+         const double inv = eg::fast_rsqrt(d);  // hardware seed + one third-order step (1.4e-16 rel.)
          if (ty == jt) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
