@@ -315,7 +315,7 @@ static Factor factor_solve(mchrg_b200_context* ctx, int nat, int64_t npad, Assem
       MCHRG_LAUNCH(ctx, shift_apply_kernel, dim3((unsigned)((nat + 255) / 256), (unsigned)nat), 256, 0, nat, f.W, npad,
                    f.shift);
    };
-   assemble(f.W);
+   assemble(f.W, /*first=*/true);
    after_first(f.W);  // e.g. keep a copy of the unshifted matrix for the energy
    if (pre_shift) apply_shift();
    int* h_info = static_cast<int*>(ctx->pinned_buf(sizeof(int)));
@@ -327,7 +327,7 @@ static Factor factor_solve(mchrg_b200_context* ctx, int nat, int64_t npad, Assem
       if (f.info == 0) break;
       if (attempt == 3) return f;  // not positive definite on the charge-conserving subspace either
       MCHRG_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
-      assemble(f.W);
+      assemble(f.W, /*first=*/false);
       apply_shift();
    }
    // y = J^-1 x, z = J^-1 1, Schur complement of the constraint
@@ -383,9 +383,11 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
       pbc_begin(ctx, mol, ps.host, ps.work);
       ps.on = true;
    }
-   auto assemble = [&](double* W) {
+   auto assemble = [&](double* W, bool first) {
+      // first attempt on several GPUs: every rank assembles only the block columns it owns in the factorisation;
+      // the shifted retries sum over the whole matrix and need all of it
       if (pbc) pbc_amat(ctx, mol, ap.rad, ap.eta, ps.work, W);
-      else eeq_amat_0d(ctx, mol, ap.rad, ap.eta, W, npad, /*border=*/false, npad);
+      else eeq_amat_0d(ctx, mol, ap.rad, ap.eta, W, npad, /*border=*/false, npad, first ? dpotrf_dist_panel(ctx, npad) : 0);
    };
    auto keep_copy = [&](double* W) {
       if (pbc && io.energy) {
@@ -527,7 +529,7 @@ static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, 
    MCHRG_LAUNCH(ctx, set_last_kernel, 1, 1, 0, nat, mol.charge, xvec);
 
    double* Jc = nullptr;
-   auto assemble = [&](double* W) {
+   auto assemble = [&](double* W, bool) {
       if (mol.periodic)
          MCHRG_CUDA(cudaMemcpyAsync(W, Wpbc, (size_t)npad * npad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
       else

@@ -473,15 +473,32 @@ __global__ void info_combine_kernel(const int* __restrict__ xinfo, int nranks, i
    *info = v;
 }
 
+static int64_t dist_panel_width() {  // MCHRG_B200_DIST_PANEL: columns per block column (multiple of 128), default 256
+   static const int64_t w = std::getenv("MCHRG_B200_DIST_PANEL")
+                               ? std::max<int64_t>(TILE, atoll(std::getenv("MCHRG_B200_DIST_PANEL")) / TILE * TILE)
+                               : 2 * TILE;
+   return w;
+}
+
+// Below ~8k the serial panel chain plus one broadcast per panel outlasts what the shared trailing updates save
+// (measured on 2 B200: N = 3000 5.3 ms distributed vs 4.3 ms replicated; N = 16384 63 vs 68 ms, 4 GPUs 51.5 ms).
+static bool dist_applies(const mchrg_b200_context* ctx, int64_t n) {
+   static const int64_t nmin = std::getenv("MCHRG_B200_DIST_MIN") ? atoll(std::getenv("MCHRG_B200_DIST_MIN")) : 8192;
+   return ctx->xch.on() && n >= std::max<int64_t>(nmin, 8 * TILE) && ctx->active == ctx->stream;
+}
+
+int64_t dpotrf_dist_panel(const mchrg_b200_context* ctx, int64_t n) { return dist_applies(ctx, n) ? dist_panel_width() : 0; }
+
 // Multi-GPU right-looking Cholesky of a REPLICATED matrix: block columns of PANEL columns are
-// owned block-cyclically (owner(b) = b % nranks).  Every rank keeps only its own block columns up to date;
+// owned block-cyclically (owner(b) = b % nranks).  Every rank keeps only its own block columns up to date (and
+// needs only those assembled on entry: dpotrf_dist_panel tells the assembly which ones);
 // the owner factors panel b (diagonal block + triangular solve of the rows below) and broadcasts it together
 // with its inverted diagonal blocks, so that at the end EVERY rank holds the complete factor and the solves
 // that follow stay replicated.  The broadcast of panel b+1 is started as soon as its owner has factored it
 // (the owner updates that column first) and overlaps the trailing updates with panel b on all ranks.
 static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info) {
    const auto& x = ctx->xch;
-   static const int64_t PANEL = std::getenv("MCHRG_B200_DIST_PANEL") ? std::max<int64_t>(TILE, atoll(std::getenv("MCHRG_B200_DIST_PANEL")) / TILE * TILE) : 2 * TILE;
+   const int64_t PANEL = dist_panel_width();
    const int nblk = (int)((n + PANEL - 1) / PANEL);
    auto c0_of = [&](int b) { return (int64_t)b * PANEL; };
    auto pw_of = [&](int b) { return std::min<int64_t>(PANEL, n - c0_of(b)); };
@@ -545,7 +562,7 @@ void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, d
    if (n % TILE || (ldw & 1)) fail(MCHRG_B200_ERR_ARG, "dpotrf_padded: n=%lld not a multiple of 128", (long long)n);
    leaf_setup_once();
    const int64_t PANEL = panel_width();
-   if (ctx->xch.on() && n >= 8 * TILE && ctx->active == ctx->stream) {  // large replicated system on several GPUs
+   if (dist_applies(ctx, n)) {  // large replicated system on several GPUs
       dpotrf_dist(ctx, n, W, ldw, dinv, info);
       return;
    }

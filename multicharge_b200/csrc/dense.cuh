@@ -21,6 +21,10 @@ void dgemm_padded(mchrg_b200_context* ctx, bool transb, int64_t m, int64_t n, in
 // of the 128x128 diagonal blocks of L (n/128 blocks of 128*128 doubles, column-major, lower).
 // info (device int) is set to the 1-based index of the first non-positive pivot, else left 0.
 void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info);
+// Width (columns) of the block columns dpotrf_padded would distribute block-cyclically over the ranks of the panel
+// exchange (owner(b) = b % nranks) for an order-n matrix issued on the current stream; 0: not distributed.  A rank
+// reads only the lower part of its OWN block columns on entry, so the assembly may skip the others.
+int64_t dpotrf_dist_panel(const mchrg_b200_context* ctx, int64_t n);
 
 // X (m x n) <- X * L^{-T} and X <- X * L^{-1} (right-side solves with the Cholesky factor);
 // together X <- X * (L L^T)^{-1}.  m, n multiples of 128.

@@ -293,7 +293,10 @@ void eeq_xvec(mchrg_b200_context* ctx, const DevMol& mol, const double* chi_a, c
 __global__ void __launch_bounds__(128) eeq_amat0d_kernel(int nat, const double* __restrict__ xyz,
                                                          const double* __restrict__ rad, const double* __restrict__ eta,
                                                          double* __restrict__ out, int64_t ld, int border, int64_t npad,
-                                                         const double2* __restrict__ etab) {
+                                                         const double2* __restrict__ etab, int own_panel, int nranks,
+                                                         int rank) {
+   // multi-GPU factorisation: only the block columns this rank owns (block-cyclic, own_panel columns wide)
+   if (own_panel > 0 && (int)(((int64_t)blockIdx.y * 8) / own_panel) % nranks != rank) return;
    MCHRG_LOAD_ERF_TABLE(etab);
    const int64_t nrow = border ? nat + 1 : npad;
    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -330,11 +333,12 @@ __global__ void __launch_bounds__(128) eeq_amat0d_kernel(int nat, const double* 
 }
 
 void eeq_amat_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a, double* out,
-                 int64_t ld, bool border, int64_t npad) {
+                 int64_t ld, bool border, int64_t npad, int64_t own_panel) {
    const int64_t nrow = border ? mol.nat + 1 : npad;
    dim3 grid((unsigned)((nrow + 127) / 128), (unsigned)((nrow + 7) / 8));
+   if (own_panel % 8) own_panel = 0;
    MCHRG_LAUNCH(ctx, eeq_amat0d_kernel, grid, 128, 0, mol.nat, mol.xyz, rad_a, eta_a, out, ld, border ? 1 : 0, npad,
-                ctx->erf_tab);
+                ctx->erf_tab, (int)own_panel, ctx->xch.nranks, ctx->xch.rank);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -37,9 +37,11 @@ void eeq_xvec(mchrg_b200_context* ctx, const DevMol& mol, const double* chi_a, c
 
 // get_amat_0d (eeq.f90:199-242).  border=true: full (nat+1)^2 matrix with the constraint row/column,
 // ld = nat+1.  border=false: the nat x nat Coulomb block J into a buffer of order npad >= nat
-// (ld = npad) whose padding is the identity (solver work matrix).
+// (ld = npad) whose padding is the identity (solver work matrix).  own_panel > 0 (multi-GPU factorisation,
+// dpotrf_dist_panel): only the block columns of that width this rank owns block-cyclically are assembled
+// (SURVEY.md 8e "assembly": pair tiles sharded by ownership of the factorisation, no collective).
 void eeq_amat_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a, double* out,
-                 int64_t ld, bool border, int64_t npad);
+                 int64_t ld, bool border, int64_t npad, int64_t own_panel = 0);
 
 // One pass over all pairs of row i (0-D): jq[i] = (J q)_i, atrace[3*nat] (eeq.f90:410-411),
 // dadL[9*nat] (eeq.f90:414-415).  Any output may be nullptr.
