@@ -600,10 +600,6 @@ static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, 
    return 0;
 }
 
-static void check_model(const mchrg_b200_model* model) {
-   if (model == nullptr || model->ctx == nullptr) fail(MCHRG_B200_ERR_ARG, "null model");
-}
-
 static int solve_dispatch(const mchrg_b200_model* model, const DevMol& mol, const SolveIO& io) {
    if (io.cn == nullptr) fail(MCHRG_B200_ERR_ARG, "cn is required");
    if (model->kind == 1) {

@@ -1246,14 +1246,13 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
             for (auto& e : t) cudaEventDestroy(e);
             return 0;
          }
-         cudaEvent_t last = nullptr;
          for (int c = 0; c < nchunk; ++c) {
             const int cnt = (int)(chunk_off[c + 1] - chunk_off[c]);
             if (cnt == 0) continue;
-            last = batch::run_chunk_split(ctx, a, dperm + chunk_off[c], cnt, starts[c], counts[c], c == 0 ? staged : nullptr,
-                                          ctx->stream_aux, ctx->stream);
+            // phase C runs on the main stream, which finish() synchronises: the returned event is not needed
+            batch::run_chunk_split(ctx, a, dperm + chunk_off[c], cnt, starts[c], counts[c], c == 0 ? staged : nullptr,
+                                   ctx->stream_aux, ctx->stream);
          }
-         (void)last;  // phase C runs on the main stream, which finish() synchronises
          MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
          return 0;
       }

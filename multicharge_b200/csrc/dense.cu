@@ -23,7 +23,7 @@ namespace mchrg {
 //   Bs[n][k] (no trans: B given as k x n)    leading dimension 20  (20 mod 16 == 4)
 // ------------------------------------------------------------------------------------------------
 namespace gemm {
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 512;
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
 constexpr int LDAS = BM + 4;
 constexpr int LDBN = BK + 4;
 constexpr int A_STAGE = BK * LDAS;                                             // 2112 doubles
