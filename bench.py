@@ -185,8 +185,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * nsample / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: batch of synthetic 30-200-atom molecules, EEQ2019 q+E+gradient",
-                       "sample_per_step": nsample},
+            "config": {"workload": "configs[1]: 100k synthetic 30-200-atom molecules per GPU, EEQ2019 q+E+gradient",
+                       "sample_per_step": nsample, "seed": SEED},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
