@@ -147,6 +147,8 @@ int mchrg_b200_solve(const mchrg_b200_model* model, const mchrg_b200_structure* 
                      double* dqdr, double* dqdL);
 
 /* ---- get_charges (charge.f90:37-77): lattice points -> CN -> local charge -> solve -------- */
+/* Without derivatives, for a non-periodic EEQ2019-type structure of at most 208 atoms, this is ONE kernel launch
+ * (the fused one-CTA-per-molecule kernel of the batch path). */
 int mchrg_b200_get_charges(const mchrg_b200_model* model, const mchrg_b200_structure* mol, double* qvec,
                            double* dqdr, double* dqdL);
 

@@ -1113,10 +1113,27 @@ static bool lazy_cn_enabled() {
    return !(e && e[0] == 'd');
 }
 
+static bool small_fused_enabled() {
+   const char* e = std::getenv("MCHRG_B200_SMALL_FUSED");
+   return !(e && e[0] == '0');
+}
+
 static int singlepoint_impl(const mchrg_b200_model* model, const mchrg_b200_structure* mol, double* cn, double* qloc,
                             double* energy, double* gradient, double* sigma, double* qvec, double* dqdr,
                             double* dqdL, bool accumulate, int jb = 0, int je = -1) {
    mchrg_b200_context* ctx = model->ctx;
+   // Charges only, of a small molecule (what get_charges is called for most): ONE launch of the fused
+   // one-CTA-per-molecule kernel (batch.cu) instead of the ~40 launches of the blocked single-system path.
+   // MCHRG_B200_SMALL_FUSED=0 keeps the general path (A/B timing).
+   if (mol && mol->id && mol->xyz && qvec && !cn && !qloc && !energy && !gradient && !sigma && !dqdr && !dqdL && jb == 0 &&
+       je < 0 && model->kind == 1 && mol->nat > 0 && mol->nat <= BATCH_MAX_ATOMS &&
+       !(mol->periodic[0] || mol->periodic[1] || mol->periodic[2]) && small_fused_enabled()) {
+      const int64_t offsets[2] = {0, mol->nat};
+      const double charge = mol->charge;
+      int32_t status = 0;
+      const int rc = mchrg_b200_singlepoint_batch(model, 1, offsets, mol->id, mol->xyz, &charge, qvec, nullptr, nullptr, &status);
+      return rc != 0 ? rc : status;
+   }
    return guarded(ctx, [&]() {
       DevMol d = stage_mol(ctx, mol);
       const size_t n = d.nat;

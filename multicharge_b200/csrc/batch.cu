@@ -32,6 +32,7 @@ constexpr int NP_MAX = 208;   // largest padded order that fits in 227 KB of sha
 constexpr int NVEC = 13;
 // split path: the matrix is augmented by two right-hand-side rows (see eeq_factor_ll_kernel)
 constexpr int NPA_MAX = NP_MAX + KB;
+static_assert(NP_MAX == BATCH_MAX_ATOMS, "eeq.cuh: BATCH_MAX_ATOMS must match NP_MAX");
 __host__ __device__ inline int aug_order(int n) { return ((n + 2 + KB - 1) / KB) * KB; }
 // Scratch layout of the split path: 8 x 8 blocks of the lower block triangle, block (R, C) at 64 (R (R + 1) / 2 + C),
 // inside a block the entry (g, c) sits at (g * 4 + (c & 3)) * 2 + (c >> 2) -- the order in which the 32 lanes

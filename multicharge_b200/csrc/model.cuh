@@ -6,6 +6,9 @@
 
 namespace mchrg {
 
+// largest molecule the one-CTA-per-molecule kernels of batch.cu hold (batch::NP_MAX)
+constexpr int BATCH_MAX_ATOMS = 208;
+
 // mctc_ncoord parameters (cn_count%erf / erf_en), SURVEY.md 3.4
 struct NcoordPar {
    double kcn = 7.5;

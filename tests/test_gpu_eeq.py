@@ -97,7 +97,7 @@ def test_golden_vectors(mc, name):
         assert np.abs(r.gradient.ravel() - np.array(g["gradient"])).max() < 5e-11
     q, dqdr, dqdL = mc.get_charges(model, mol, grad=True)
     assert np.abs(q - r.qvec).max() < 1e-13
-    assert np.abs(mc.get_eeq_charges(mol) - r.qvec).max() < 1e-13
+    assert np.abs(mc.get_eeq_charges(mol) - r.qvec).max() < 1e-12  # (charges only: the fused one-launch kernel)
 
 
 def test_medium_cluster_full_path(mc, oracle):
@@ -151,3 +151,24 @@ def test_gradient_without_dcndr(mc, oracle, monkeypatch):
         assert np.abs(r[key] - d[key]).max() < 1e-12 * scale, key
     assert np.abs(rows["gradient"] - o.gradient[100:333]).max() < TOL
     assert np.abs(rows["sigma"] - o.sigma).max() < TOL * max(1.0, np.abs(o.sigma).max())
+
+
+def test_small_charges_only_route(mc, oracle, monkeypatch):
+    """get_charges without derivatives on a molecule of at most 208 atoms runs as ONE launch of the fused batch kernel;
+    same charges as the general path (MCHRG_B200_SMALL_FUSED=0) and the oracle, species in order of appearance."""
+    from synth import cluster
+    for nat, seed, chg in ((1, 41, 0.0), (16, 42, 1.0), (97, 43, -1.0), (208, 44, 0.0), (209, 45, 0.0)):
+        num, xyz = cluster(nat, seed)
+        mol, model, omol, omodel = both(mc, oracle, num, xyz, chg)
+        o = oracle.eeq_singlepoint(omodel, omol, want=("qvec",))
+        n0 = mc.default_context().launch_count
+        q = mc.get_charges(model, mol)
+        fused_launches = mc.default_context().launch_count - n0
+        monkeypatch.setenv("MCHRG_B200_SMALL_FUSED", "0")
+        n0 = mc.default_context().launch_count
+        q_general = mc.get_charges(model, mol)
+        general_launches = mc.default_context().launch_count - n0
+        monkeypatch.delenv("MCHRG_B200_SMALL_FUSED")
+        assert np.abs(q - o.qvec).max() < TOL and np.abs(q - q_general).max() < 1e-12
+        assert (fused_launches == 1) == (nat <= 208), (nat, fused_launches, general_launches)
+        assert general_launches > 10
