@@ -130,3 +130,34 @@ def test_fd_sigma_and_dqdL(oracle):
                     q.append(r2.qvec)
                 assert abs((e[0] - e[1]) / (2 * step) - r.sigma[b, a]) < 3 * THR2, (name, a, b)
                 assert np.abs((q[0] - q[1]) / (2 * step) - r.dqdL[:, b, a]).max() < 3 * THR2, (name, a, b)
+
+
+def test_oracle_invariances(oracle):
+    """Size-independent properties of the path (the same ones the full-size GPU property tests use): atom
+    permutation, rigid translation and rotation of a molecule; rotation of a periodic cell together with its atoms."""
+    from synth import cluster, periodic_cell
+    rng = np.random.default_rng(5)
+    qm, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    num, xyz = cluster(37, 19)
+    mol = oracle.Mol(num, xyz, -1.0)
+    r = oracle.eeq_singlepoint(oracle.new_eeq2019_model(mol), mol, want=("qvec", "energy", "gradient", "dqdr"))
+    perm = rng.permutation(len(num))
+    pm = oracle.Mol(np.asarray(num)[perm], xyz[perm], -1.0)
+    rp = oracle.eeq_singlepoint(oracle.new_eeq2019_model(pm), pm, want=("qvec", "energy", "gradient", "dqdr"))
+    assert np.abs(rp.qvec - r.qvec[perm]).max() < 1e-12 and np.abs(rp.gradient - r.gradient[perm]).max() < 1e-12
+    assert np.abs(rp.dqdr - r.dqdr[np.ix_(perm, perm)]).max() < 1e-11
+    tm = oracle.Mol(num, xyz @ qm.T + np.array([3.0, -7.0, 11.0]), -1.0)
+    rt = oracle.eeq_singlepoint(oracle.new_eeq2019_model(tm), tm, want=("qvec", "energy", "gradient", "dqdr"))
+    assert np.abs(rt.qvec - r.qvec).max() < 1e-12 and abs(rt.energy.sum() - r.energy.sum()) < 1e-12
+    assert np.abs(rt.gradient - r.gradient @ qm.T).max() < 1e-12
+    assert np.abs(rt.sigma - qm @ r.sigma @ qm.T).max() < 1e-11
+    assert np.abs(rt.dqdr - r.dqdr @ qm.T).max() < 1e-11
+    assert np.abs(r.gradient.sum(axis=0)).max() < 1e-12 and np.abs(r.dqdr.sum(axis=1)).max() < 1e-12  # translation
+    num, xyz, lat = periodic_cell(2, 8, shear=0.1)
+    pc = oracle.Mol(num, xyz, 0.0, lattice=lat)
+    r3 = oracle.eeq_singlepoint(oracle.new_eeq2019_model(pc), pc, want=("qvec", "energy", "gradient"))
+    pr = oracle.Mol(num, xyz @ qm.T, 0.0, lattice=lat @ qm.T)
+    r3r = oracle.eeq_singlepoint(oracle.new_eeq2019_model(pr), pr, want=("qvec", "energy", "gradient"))
+    assert np.abs(r3r.qvec - r3.qvec).max() < 1e-11 and abs(r3r.energy.sum() - r3.energy.sum()) < 1e-11
+    assert np.abs(r3r.gradient - r3.gradient @ qm.T).max() < 1e-11
+    assert np.abs(r3r.sigma - qm @ r3.sigma @ qm.T).max() < 1e-10
