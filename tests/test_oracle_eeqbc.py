@@ -159,3 +159,32 @@ def test_oracle_eeqbc_periodic_fd_gradient_dqdr_sigma(oracle):
                 q.append(r2.qvec)
             assert abs((e[0] - e[1]) / (2 * STEP) - r.sigma[b, a]) < 3 * THR2 * max(1.0, np.abs(r.sigma).max()), (a, b)
             assert np.abs((q[0] - q[1]) / (2 * STEP) - r.dqdL[:, b, a]).max() < 3 * THR2 * max(1.0, np.abs(r.dqdL).max())
+
+
+def test_oracle_eeqbc_invariances(oracle):
+    """Rigid translation + rotation of a molecule and rotation of a periodic cell with its atoms leave charges and
+    energy unchanged and rotate gradient, virial and dq/dr (further pins for the unpinned EEQ-BC restatement)."""
+    from synth import cluster, periodic_cell
+    rng = np.random.default_rng(11)
+    qm, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    num, xyz = cluster(14, 23)
+    mol = oracle.Mol(num, xyz, 1.0)
+    model = oracle.new_eeqbc2025_model(mol)
+    r = oracle.eeqbc_singlepoint(model, mol, want=("qvec", "energy", "gradient", "dqdr"))
+    tm = oracle.Mol(num, xyz @ qm.T + np.array([1.0, 2.0, -3.0]), 1.0)
+    rt = oracle.eeqbc_singlepoint(model, tm, want=("qvec", "energy", "gradient", "dqdr"))
+    assert r.stat == 0 and rt.stat == 0
+    assert np.abs(rt.qvec - r.qvec).max() < 1e-12 and abs(rt.energy.sum() - r.energy.sum()) < 1e-12
+    assert np.abs(rt.gradient - r.gradient @ qm.T).max() < 1e-11
+    assert np.abs(rt.sigma - qm @ r.sigma @ qm.T).max() < 1e-10
+    assert np.abs(rt.dqdr - r.dqdr @ qm.T).max() < 1e-10
+    assert np.abs(r.gradient.sum(axis=0)).max() < 1e-11 and np.abs(r.dqdr.sum(axis=1)).max() < 1e-11
+    num, xyz, lat = periodic_cell(2, 4, shear=0.1)
+    pc = oracle.Mol(num, xyz, 1.0, lattice=lat, periodic=[True] * 3)
+    pmodel = oracle.new_eeqbc2025_model(pc)
+    r3 = oracle.eeqbc_singlepoint(pmodel, pc, want=("qvec", "energy", "gradient"))
+    pr = oracle.Mol(num, xyz @ qm.T, 1.0, lattice=lat @ qm.T, periodic=[True] * 3)
+    r3r = oracle.eeqbc_singlepoint(pmodel, pr, want=("qvec", "energy", "gradient"))
+    assert np.abs(r3r.qvec - r3.qvec).max() < 1e-11 and abs(r3r.energy.sum() - r3.energy.sum()) < 1e-11
+    assert np.abs(r3r.gradient - r3.gradient @ qm.T).max() < 1e-10
+    assert np.abs(r3r.sigma - qm @ r3.sigma @ qm.T).max() < 1e-9
