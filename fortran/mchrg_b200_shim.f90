@@ -110,16 +110,32 @@ module mchrg_b200_shim
          type(c_ptr), value :: cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL, qvec, dadr, dadL, atrace
          integer(c_int) :: stat
       end function
-      !> multi-GPU factorisation of one large system: install the panel exchange (e.g. thunks around
-      !> MPI_Ibcast / MPI_Wait of a CUDA-aware MPI; see include/mchrg_b200.h)
-      function c_set_exchange(ctx, rank, nranks, start, wait, user) result(stat) bind(C, name="mchrg_b200_set_exchange")
-         import :: c_ptr, c_funptr, c_int, c_int32_t
+      !> one large system over several GPUs: the library's communicator (include/mchrg_b200.h).  An MPI caller
+      !> obtains the 128-byte id on rank 0 (c_comm_unique_id), MPI_Bcast's it and joins with c_comm_init_nccl;
+      !> an OpenMP caller with one thread per GPU ties its contexts together with c_comm_init_local.
+      function c_comm_unique_id(id) result(stat) bind(C, name="mchrg_b200_comm_unique_id")
+         import :: c_ptr, c_int
+         type(c_ptr), value :: id
+         integer(c_int) :: stat
+      end function c_comm_unique_id
+      function c_comm_init_nccl(ctx, rank, nranks, id) result(stat) bind(C, name="mchrg_b200_comm_init_nccl")
+         import :: c_ptr, c_int, c_int32_t
          type(c_ptr), value :: ctx
          integer(c_int32_t), value :: rank, nranks
-         type(c_funptr), value :: start, wait
-         type(c_ptr), value :: user
+         type(c_ptr), value :: id
          integer(c_int) :: stat
-      end function c_set_exchange
+      end function c_comm_init_nccl
+      function c_comm_init_local(ctxs, n) result(stat) bind(C, name="mchrg_b200_comm_init_local")
+         import :: c_ptr, c_int, c_int32_t
+         type(c_ptr), intent(in) :: ctxs(*)
+         integer(c_int32_t), value :: n
+         integer(c_int) :: stat
+      end function c_comm_init_local
+      function c_comm_destroy(ctx) result(stat) bind(C, name="mchrg_b200_comm_destroy")
+         import :: c_ptr, c_int
+         type(c_ptr), value :: ctx
+         integer(c_int) :: stat
+      end function c_comm_destroy
       function c_side_stream(ctx) result(stream) bind(C, name="mchrg_b200_side_stream")
          import :: c_ptr
          type(c_ptr), value :: ctx

@@ -67,26 +67,47 @@ int mchrg_b200_version(void); /* 10000*major + 100*minor + patch */
 int mchrg_b200_synchronize(mchrg_b200_context* ctx);
 /* stream the context launches on (cudaStream_t as void*), for callers that time with events */
 void* mchrg_b200_stream(mchrg_b200_context* ctx);
-/* second stream of the context; panel exchanges (below) are ordered on it */
+/* second stream of the context (batch size classes, pair phase A) */
 void* mchrg_b200_side_stream(mchrg_b200_context* ctx);
 
-/* ---- multi-GPU factorisation of ONE large system ("one exchange per panel") -------------
+/* ---- one large system over several GPUs: the communicator ------------------------------
  * The reference factors the bordered matrix with one LAPACK call (dsytrf, model/type.F90:221,
- * lapack.F90:165-201).  With an exchange installed, every rank of a replicated solve owns the block columns
- * b % nranks == rank of the Cholesky factorisation (block-cyclic, 256 wide): the owner factors panel b,
- * `start` broadcasts it (device pointer, bytes, root rank, slot id) and `wait` orders the context's main
- * stream after the transfer of that slot; ranks update only the columns they own.  The callbacks are the
- * caller's collective (torch.distributed / NCCL broadcast in multicharge_b200/api.py); the library itself
- * links no communication library.  `start` must enqueue on mchrg_b200_side_stream, `wait` on
- * mchrg_b200_stream.  All ranks must make the same sequence of library calls with the same inputs.
- * nranks <= 1 or start == NULL removes the exchange. */
-typedef void (*mchrg_b200_exchange_start_fn)(void* user, void* dev_ptr, int64_t bytes, int32_t root, int32_t slot);
-typedef void (*mchrg_b200_exchange_wait_fn)(void* user, int32_t slot);
-int mchrg_b200_set_exchange(mchrg_b200_context* ctx, int32_t rank, int32_t nranks, mchrg_b200_exchange_start_fn start,
-                            mchrg_b200_exchange_wait_fn wait, void* user);
+ * lapack.F90:165-201) and has no distributed path.  With a communicator installed on its context, every
+ * single-system entry point (solve, singlepoint, singlepoint_rows, get_charges) of a structure with at least
+ * MCHRG_B200_DIST_MIN (default 8192) atoms shares the work between the ranks:
+ *   - Cholesky: column groups are owned block-cyclically (owner(g) = g % nranks), factored sub-panels are
+ *     broadcast, every rank updates only the groups it owns (csrc/dense.cu);
+ *   - the O(N^2) row passes (coordination number, (J q) / atrace / dadL, CN-gradient contraction) are
+ *     row-sharded and joined by one all-reduce each;
+ *   - dq/dr is row-sharded by the caller through mchrg_b200_singlepoint_rows (no collective).
+ * All ranks must make the same sequence of library calls with the same inputs.
+ * Two backends:
+ *   NCCL  -- one process per GPU: rank 0 calls comm_unique_id, distributes the 128 bytes by its own means
+ *            (MPI_Bcast, torch.distributed, a file), every rank calls comm_init_nccl.  libnccl.so.2 is loaded
+ *            with dlopen at that moment (MCHRG_B200_NCCL_LIB overrides the path); the library links no
+ *            communication library.
+ *   local -- one process, one host thread per context (several GPUs, or several contexts on one GPU):
+ *            comm_init_local(ctxs, n) ties n contexts together; collectives are stream-ordered peer copies. */
+#define MCHRG_B200_COMM_ID_BYTES 128
+int mchrg_b200_comm_unique_id(void* id /* [MCHRG_B200_COMM_ID_BYTES] out */);
+int mchrg_b200_comm_init_nccl(mchrg_b200_context* ctx, int32_t rank, int32_t nranks, const void* id);
+int mchrg_b200_comm_init_local(mchrg_b200_context** ctxs, int32_t n);
+int mchrg_b200_comm_destroy(mchrg_b200_context* ctx);
+int32_t mchrg_b200_comm_rank(const mchrg_b200_context* ctx);
+int32_t mchrg_b200_comm_size(const mchrg_b200_context* ctx);
+/* the collectives themselves on device buffers (tests; gathering row-sharded results): ordered on the
+ * context's stream, synchronous for the host */
+int mchrg_b200_comm_bcast(mchrg_b200_context* ctx, void* dev_buf, int64_t bytes, int32_t root);
+int mchrg_b200_comm_allreduce_sum(mchrg_b200_context* ctx, double* dev_buf, int64_t count);
+int mchrg_b200_comm_allgather(mchrg_b200_context* ctx, const void* dev_send, void* dev_recv, int64_t bytes_per_rank);
 
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 uint64_t mchrg_b200_launch_count(const mchrg_b200_context* ctx);
+/* With MCHRG_B200_TRACE=1 in the environment a large batch call (singlepoint_batch, split path) runs its three
+ * kernels one after the other over the whole batch (same results), each timed alone with CUDA events on the
+ * launching stream instead of overlapping them chunk by chunk.  This returns those times: ms[3] =
+ * pair phase A, factorisation, pair phase C; launches[3] = kernel launches of each (bench.py's per-kernel roofline). */
+int mchrg_b200_batch_trace(const mchrg_b200_context* ctx, double* ms, int32_t* launches);
 
 /* ---- constructors ------------------------------------------------------------------------ */
 /* new_eeq_model (model/eeq.f90:62-95): per-species chi, rad, eta, kcnchi, rcov; cutoff, cn_exp,
@@ -164,8 +185,8 @@ int mchrg_b200_singlepoint(const mchrg_b200_model* model, const mchrg_b200_struc
  *   dqdr_rows(3, nrows, nat)     = dqdr(:, row_begin+1 : row_end, :)
  * while cn, energy, sigma, qvec and dqdL are complete on every caller.  The right-side solves that
  * produce dq/dr act on its rows independently, so ranks that own disjoint blocks need NO data-path
- * collective; the O(N^3/3) factorisation is replicated (see DESIGN.md "Multi-GPU").  Non-periodic
- * EEQ2019-type models only. */
+ * collective; with a communicator on the context the factorisation and the O(N^2) row passes are shared as
+ * described above (see DESIGN.md "Multi-GPU").  Non-periodic structures only. */
 int mchrg_b200_singlepoint_rows(const mchrg_b200_model* model, const mchrg_b200_structure* mol, int32_t row_begin,
                                 int32_t row_end, double* cn, double* energy, double* gradient_rows, double* sigma,
                                 double* qvec, double* dqdr_rows, double* dqdL);

@@ -8,7 +8,8 @@ from ._lib import MchrgError  # noqa: F401
 from .api import (Context, FactorizationError, MchrgModel, Structure, default_context,  # noqa: F401
                   get_charges, get_eeq_charges, get_eeqbc_charges, new_eeq2019_batch_model, new_eeqbc2025_model,
                   new_eeqbc_model, new_eeq2019_model, new_eeq_model,
-                  singlepoint_batch, singlepoint_rows, PanelExchange)
+                  singlepoint_batch, singlepoint_rows)
+from .dist import init_comm_from_torch  # noqa: F401
 
 mchrg_model_type = MchrgModel  # reference type name
 

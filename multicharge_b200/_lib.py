@@ -33,7 +33,16 @@ PROTOTYPES = {
     "mchrg_b200_stream": (c_vp, [c_vp]),
     "mchrg_b200_launch_count": (C.c_uint64, [c_vp]),
     "mchrg_b200_side_stream": (c_vp, [c_vp]),
-    "mchrg_b200_set_exchange": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp, c_vp, c_vp]),
+    "mchrg_b200_batch_trace": (C.c_int, [c_vp, c_vp, c_vp]),
+    "mchrg_b200_comm_unique_id": (C.c_int, [c_vp]),
+    "mchrg_b200_comm_init_nccl": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp]),
+    "mchrg_b200_comm_init_local": (C.c_int, [C.POINTER(c_vp), C.c_int32]),
+    "mchrg_b200_comm_destroy": (C.c_int, [c_vp]),
+    "mchrg_b200_comm_rank": (C.c_int32, [c_vp]),
+    "mchrg_b200_comm_size": (C.c_int32, [c_vp]),
+    "mchrg_b200_comm_bcast": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int32]),
+    "mchrg_b200_comm_allreduce_sum": (C.c_int, [c_vp, c_vp, C.c_int64]),
+    "mchrg_b200_comm_allgather": (C.c_int, [c_vp, c_vp, c_vp, C.c_int64]),
     "mchrg_b200_new_eeq_model": (C.c_int, [c_vp, C.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_double,
                                            C.c_double, C.POINTER(c_vp)]),
     "mchrg_b200_new_eeq2019_model": (C.c_int, [c_vp, C.c_int32, c_vp, C.POINTER(c_vp)]),
@@ -60,8 +69,7 @@ PROTOTYPES = {
     "mchrg_b200_dpotrs_right": (C.c_int, [c_vp, C.c_int64, C.c_int64, c_vp, C.c_int64, c_vp, C.c_int64]),
 }
 
-EXCHANGE_START_FN = C.CFUNCTYPE(None, c_vp, c_vp, C.c_int64, C.c_int32, C.c_int32)
-EXCHANGE_WAIT_FN = C.CFUNCTYPE(None, c_vp, C.c_int32)
+COMM_ID_BYTES = 128
 
 _lib = None
 

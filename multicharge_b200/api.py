@@ -38,17 +38,31 @@ class FactorizationError(MchrgError):
         self.info = info
 
 
-def _ptr(a):
+class _Ptr(C.c_void_p):
+    """void* that keeps the array it points into alive for as long as the argument object lives (ctypes holds
+    the argument objects until the foreign call returns), so temporaries such as `_ptr(_f64(x))` are safe."""
+
+
+def _ptr(a, dtype=None):
+    """Address of a host (numpy) or device (torch) array for the C ABI; `dtype` is enforced when given."""
     if a is None:
         return None
     if isinstance(a, np.ndarray):
         if not a.flags["C_CONTIGUOUS"]:
             raise ValueError("array must be C-contiguous")
-        return a.ctypes.data
+        if dtype is not None and a.dtype != np.dtype(dtype):
+            raise TypeError(f"array must have dtype {np.dtype(dtype)}, got {a.dtype}")
+        p = _Ptr(a.ctypes.data)
+        p._keep = a
+        return p
     if hasattr(a, "data_ptr"):  # torch tensor
         if not a.is_contiguous():
             raise ValueError("tensor must be contiguous")
-        return a.data_ptr()
+        if dtype is not None and str(a.dtype).replace("torch.", "") != np.dtype(dtype).name:
+            raise TypeError(f"tensor must have dtype {np.dtype(dtype)}, got {a.dtype}")
+        p = _Ptr(a.data_ptr())
+        p._keep = a
+        return p
     raise TypeError(f"unsupported array type {type(a)}")
 
 
@@ -88,23 +102,63 @@ class Context:
     def synchronize(self):
         check(_lib.load().mchrg_b200_synchronize(self._h))
 
+    def batch_trace(self):
+        """Per-kernel times (ms) and launch counts of the last large batch call made with MCHRG_B200_TRACE=1:
+        (pair phase A, factorisation, pair phase C)."""
+        ms = (C.c_double * 3)()
+        nl = (C.c_int32 * 3)()
+        check(_lib.load().mchrg_b200_batch_trace(self._h, ms, nl))
+        return list(ms), list(nl)
+
     @property
     def side_stream(self):
         return _lib.load().mchrg_b200_side_stream(self._h)
 
-    def set_exchange(self, exchange):
-        """Install (or, with None, remove) the panel exchange of the multi-GPU factorisation: `exchange` is a
-        PanelExchange (or any object with rank, world, start(ptr, nbytes, root, slot), wait(slot))."""
-        lib = _lib.load()
-        if exchange is None or exchange.world <= 1:
-            self._exchange = None
-            check(lib.mchrg_b200_set_exchange(self._h, 0, 1, None, None, None))
-            return
-        start = _lib.EXCHANGE_START_FN(lambda user, ptr, nbytes, root, slot: exchange.start(ptr, nbytes, root, slot))
-        wait = _lib.EXCHANGE_WAIT_FN(lambda user, slot: exchange.wait(slot))
-        self._exchange = (exchange, start, wait)  # keep the ctypes thunks alive
-        check(lib.mchrg_b200_set_exchange(self._h, exchange.rank, exchange.world, C.cast(start, C.c_void_p),
-                                          C.cast(wait, C.c_void_p), None))
+    # --- communicator of the multi-GPU single-system path (mchrg_b200_comm_*) -------------------------
+    @staticmethod
+    def comm_unique_id():
+        """ncclGetUniqueId through the library: 128 bytes that rank 0 hands to every rank."""
+        buf = C.create_string_buffer(_lib.COMM_ID_BYTES)
+        check(_lib.load().mchrg_b200_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init_nccl(self, rank, world, unique_id):
+        """One process per GPU: join the NCCL communicator described by `unique_id` as `rank` of `world`."""
+        if len(unique_id) != _lib.COMM_ID_BYTES:
+            raise ValueError("unique_id must be the 128 bytes of comm_unique_id()")
+        check(_lib.load().mchrg_b200_comm_init_nccl(self._h, int(rank), int(world), C.c_char_p(bytes(unique_id))))
+
+    @staticmethod
+    def comm_init_local(contexts):
+        """One process, one host thread per context: tie `contexts` together (rank = position in the list)."""
+        arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+        check(_lib.load().mchrg_b200_comm_init_local(arr, len(contexts)))
+
+    def comm_destroy(self):
+        check(_lib.load().mchrg_b200_comm_destroy(self._h))
+
+    @property
+    def comm_rank(self):
+        return int(_lib.load().mchrg_b200_comm_rank(self._h))
+
+    @property
+    def comm_size(self):
+        return int(_lib.load().mchrg_b200_comm_size(self._h))
+
+    def comm_bcast(self, t, root):
+        """Broadcast the device tensor `t` of rank `root` to every rank, in place."""
+        check(_lib.load().mchrg_b200_comm_bcast(self._h, _ptr(t), t.numel() * t.element_size(), int(root)))
+
+    def comm_allreduce_sum(self, t):
+        """In-place sum over ranks of a float64 device tensor."""
+        check(_lib.load().mchrg_b200_comm_allreduce_sum(self._h, _ptr(t, np.float64), t.numel()))
+
+    def comm_allgather(self, send, recv):
+        """recv[r] = send of rank r (device tensors; recv holds comm_size times the bytes of send)."""
+        nbytes = send.numel() * send.element_size()
+        if recv.numel() * recv.element_size() != nbytes * self.comm_size:
+            raise ValueError("recv must hold comm_size * send bytes")
+        check(_lib.load().mchrg_b200_comm_allgather(self._h, _ptr(send), _ptr(recv), nbytes))
 
     # dense building blocks (tests)
     def dpotrf(self, a):
@@ -118,59 +172,6 @@ class Context:
 
     def dpotrs_right(self, m, n, l, ldl, x, ldx):
         return check(_lib.load().mchrg_b200_dpotrs_right(self._h, m, n, _ptr(l), ldl, _ptr(x), ldx))
-
-
-class _DeviceBytes:
-    """Zero-copy view of raw device memory for torch (CUDA array interface)."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
-
-
-class PanelExchange:
-    """The collective behind mchrg_b200_set_exchange: torch.distributed broadcasts of the factored panels.
-
-    `start` enqueues an asynchronous broadcast on the context's side stream (the library has ordered that stream
-    after the kernels that produced the panel), `wait` makes the context's main stream wait for it.  With the
-    NCCL backend the data moves GPU to GPU over NVLink; `as_tensor` is replaceable so that the bookkeeping can be
-    exercised with the gloo backend on host buffers (tests/test_exchange_gloo.py)."""
-
-    def __init__(self, ctx=None, group=None, as_tensor=None):
-        import torch
-        import torch.distributed as dist
-        self._torch, self._dist = torch, dist
-        self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
-        self.pending = {}
-        self.started = 0
-        self.bytes_moved = 0
-        if ctx is not None:
-            dev = torch.device("cuda", ctx.device)
-            self._main = torch.cuda.ExternalStream(ctx.stream, device=dev)
-            self._side = torch.cuda.ExternalStream(ctx.side_stream, device=dev)
-            self._as_tensor = as_tensor or (lambda ptr, n: torch.as_tensor(_DeviceBytes(ptr, n), device=dev))
-        else:  # host buffers (gloo): no streams
-            self._main = self._side = None
-            self._as_tensor = as_tensor
-
-    def _on(self, stream):
-        import contextlib
-        return self._torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
-
-    def start(self, ptr, nbytes, root, slot):
-        t = self._as_tensor(ptr, nbytes)
-        src = root if self.group is None else self._dist.get_global_rank(self.group, root)
-        with self._on(self._side):
-            work = self._dist.broadcast(t, src=src, group=self.group, async_op=True)
-        self.pending[slot] = (work, t)
-        self.started += 1
-        self.bytes_moved += int(nbytes)
-
-    def wait(self, slot):
-        work, _t = self.pending.pop(slot)
-        with self._on(self._main):
-            work.wait()
 
 
 _default_ctx = {}
@@ -210,8 +211,8 @@ class Structure:
     def _c(self, xyz=None, id=None):
         s = _lib.Structure()
         s.nat, s.nid = self.nat, self.nid
-        s.id = _ptr(self.id if id is None else id)
-        s.xyz = _ptr(self.xyz if xyz is None else xyz)
+        s.id = _ptr(self.id if id is None else id, np.int32)      # the arrays outlive the call: members of self
+        s.xyz = _ptr(self.xyz if xyz is None else xyz, np.float64)  # or the caller's own tensors
         s.charge = self.charge
         s.periodic = (C.c_int32 * 3)(*[int(p) for p in self.periodic])
         s.lattice = (C.c_double * 9)(*self.lattice.ravel().tolist())
@@ -412,9 +413,10 @@ def singlepoint_batch(model, offsets, num, xyz, charge, gradient=True, out=None)
         out = SolveResult(qvec=np.empty(ntot), energy=np.empty(ntot),
                           gradient=np.empty((ntot, 3)) if gradient else None,
                           status=np.empty(nmol, dtype=np.int32))
+    f8, i4, i8 = np.float64, np.int32, np.int64
     rc = _lib.load().mchrg_b200_singlepoint_batch(
-        model._h, nmol, _ptr(offsets), _ptr(num), _ptr(xyz), _ptr(charge), _ptr(out["qvec"]), _ptr(out["energy"]),
-        _ptr(out.get("gradient")), _ptr(out["status"]))
+        model._h, nmol, _ptr(offsets, i8), _ptr(num, i4), _ptr(xyz, f8), _ptr(charge, f8), _ptr(out["qvec"], f8),
+        _ptr(out["energy"], f8), _ptr(out.get("gradient"), f8), _ptr(out["status"], i4))
     check(rc)
     return out
 

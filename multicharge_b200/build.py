@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmchrg_b200.so")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["context.cu", "dense.cu", "eeq.cu", "eeq_pbc.cu", "eeqbc.cu", "batch.cu", "api.cu"]
+SOURCES = ["context.cu", "comm.cu", "dense.cu", "eeq.cu", "eeq_pbc.cu", "eeqbc.cu", "batch.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-warn-spills"]
 
@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(run, jobs))
     if jobs or not os.path.exists(OUT):
-        run([nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
+        run([nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"])
     return OUT
 
 

@@ -39,6 +39,31 @@ __global__ void rhs_init_kernel(int nat, int64_t npad, const double* __restrict_
    R[i + npad] = (i < nat) ? 1.0 : 0.0;
 }
 
+// Augmented system: rows npad-2 / npad-1 of the work matrix carry the right-hand sides [x | 1], so the forward
+// substitution falls out of the factorisation (the leaf keeps those rows' own columns at identity).
+__global__ void aug_rows_kernel(int nat, int64_t npad, const double* __restrict__ xvec, double* __restrict__ W) {
+   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (j >= npad) return;
+   W[npad - 2 + j * npad] = (j < nat) ? xvec[j] : (j == npad - 2 ? 1.0 : 0.0);
+   W[npad - 1 + j * npad] = (j < nat) ? 1.0 : (j == npad - 1 ? 1.0 : 0.0);
+}
+// R(:,0) = L^-1 x, R(:,1) = L^-1 1 from the last two rows of L; those rows (and the matching rows of the last
+// inverted diagonal block) are cleared, which leaves L = blockdiag(L_J, I) for the dq/dr sweeps
+__global__ void aug_extract_kernel(int64_t npad, double* __restrict__ W, double* __restrict__ dinv_last,
+                                   double* __restrict__ R) {
+   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (j >= npad) return;
+   const bool body = j < npad - 2;
+   R[j] = body ? W[npad - 2 + j * npad] : 0.0;
+   R[j + npad] = body ? W[npad - 1 + j * npad] : 0.0;
+   if (body) {
+      W[npad - 2 + j * npad] = 0.0;
+      W[npad - 1 + j * npad] = 0.0;
+      const int64_t jl = j - (npad - TILE);
+      if (jl >= 0) dinv_last[TILE - 2 + jl * TILE] = dinv_last[TILE - 1 + jl * TILE] = 0.0;
+   }
+}
+
 // Schur complement of the total-charge constraint: one CTA.
 // scal[0] = s = 1^T z, scal[1] = lambda; vrhs[0..nat-1] = q, vrhs[nat] = lambda
 __global__ void __launch_bounds__(1024) schur_charges_kernel(int nat, int64_t npad, const double* __restrict__ R,
@@ -300,9 +325,18 @@ struct Factor {
    const double* z(int64_t npad) const { return R + npad; }
 };
 
+// Augmented right-hand-side rows (MCHRG_B200_AUG=0 switches them off): used when they cost no extra tile (nat + 2
+// fits the padded order anyway) or when the system is shared by several ranks (one replicated substitution sweep
+// less per rank).
+static bool aug_enabled(const mchrg_b200_context* ctx, int nat) {
+   if (env_ll("MCHRG_B200_AUG", 1) == 0) return false;
+   return round_up(nat + 2, TILE) == round_up(nat, TILE) || dist_rows_apply(ctx, nat);
+}
+
 template <class Assemble, class AfterAssemble>
 static Factor factor_solve(mchrg_b200_context* ctx, int nat, int64_t npad, Assemble&& assemble, AfterAssemble&& after_first,
-                           bool pre_shift, const double* xvec, double charge, double* qvec_out) {
+                           bool pre_shift, const double* xvec, double charge, double* qvec_out, bool aug = false) {
+   if (aug && npad < nat + 2) fail(MCHRG_B200_ERR_ARG, "factor_solve: augmented order too small");
    Factor f;
    f.W = ctx->alloc<double>((size_t)npad * npad);
    f.dinv = ctx->alloc<double>((size_t)npad * TILE);
@@ -320,7 +354,8 @@ static Factor factor_solve(mchrg_b200_context* ctx, int nat, int64_t npad, Assem
    if (pre_shift) apply_shift();
    int* h_info = static_cast<int*>(ctx->pinned_buf(sizeof(int)));
    for (int attempt = 0;; ++attempt) {
-      dpotrf_padded(ctx, npad, f.W, npad, f.dinv, info);
+      if (aug) MCHRG_LAUNCH(ctx, aug_rows_kernel, (unsigned)((npad + 255) / 256), 256, 0, nat, npad, xvec, f.W);
+      dpotrf_padded(ctx, npad, f.W, npad, f.dinv, info, aug);
       MCHRG_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
       f.info = *h_info;
@@ -332,8 +367,12 @@ static Factor factor_solve(mchrg_b200_context* ctx, int nat, int64_t npad, Assem
    }
    // y = J^-1 x, z = J^-1 1, Schur complement of the constraint
    f.R = ctx->alloc<double>((size_t)npad * 2);
-   MCHRG_LAUNCH(ctx, rhs_init_kernel, (unsigned)((npad + 255) / 256), 256, 0, nat, npad, xvec, f.R);
-   dpotrs_vec(ctx, npad, f.W, npad, f.dinv, f.R, npad, 2);
+   if (aug)
+      MCHRG_LAUNCH(ctx, aug_extract_kernel, (unsigned)((npad + 255) / 256), 256, 0, npad, f.W,
+                   f.dinv + (npad / TILE - 1) * TILE * TILE, f.R);
+   else
+      MCHRG_LAUNCH(ctx, rhs_init_kernel, (unsigned)((npad + 255) / 256), 256, 0, nat, npad, xvec, f.R);
+   dpotrs_vec(ctx, npad, f.W, npad, f.dinv, f.R, npad, 2, /*forward=*/!aug);
    f.vrhs = ctx->alloc<double>(nat + 1);
    f.scal = ctx->alloc<double>(2);
    MCHRG_LAUNCH(ctx, schur_charges_kernel, 1, 1024, 0, nat, npad, f.R, charge, f.vrhs, qvec_out, f.scal, f.shift);
@@ -363,15 +402,21 @@ struct PbcScope {
 static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, const AtomPar& ap, const SolveIO& io) {
    mchrg_b200_context* ctx = model->ctx;
    const int nat = mol.nat;
-   const int64_t npad = round_up(nat, TILE);
+   const bool pbc = mol.periodic;
+   // augmented right-hand-side rows: non-periodic path only (the periodic kernels pad to round_up(nat) themselves)
+   const bool aug = !pbc && aug_enabled(ctx, nat);
+   const int64_t npad = aug ? round_up(nat + 2, TILE) : round_up(nat, TILE);
    const bool dcn = io.dcndr && io.dcndL;
    const bool cpq = io.dqdr && io.dqdL && dcn;
    const bool lazy = io.lazy && !cpq;
    const bool grad = io.gradient && io.sigma && (dcn || lazy);
-   const bool pbc = mol.periodic;
    const int jb = io.jb, je = io.je < 0 ? nat : io.je, nj = je - jb;
    if (jb < 0 || je > nat || nj <= 0) fail(MCHRG_B200_ERR_ARG, "invalid row block [%d, %d)", jb, je);
    if (pbc && nj != nat) fail(MCHRG_B200_ERR_MODEL, "row blocks are not available for periodic structures");
+   // one large system on several GPUs: the O(N^2) row passes are row-sharded and joined by one all-reduce
+   const bool shard = !pbc && dist_rows_apply(ctx, nat);
+   int row0 = 0, row1 = nat;
+   if (shard) row_share(ctx, nat, &row0, &row1);
 
    double* xvec = ctx->alloc<double>(nat + 1);
    double* thalf = ctx->alloc<double>(nat);
@@ -384,7 +429,7 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
       ps.on = true;
    }
    auto assemble = [&](double* W, bool first) {
-      // first attempt on several GPUs: every rank assembles only the block columns it owns in the factorisation;
+      // first attempt on several GPUs: every rank assembles only the column groups it owns in the factorisation;
       // the shifted retries sum over the whole matrix and need all of it
       if (pbc) pbc_amat(ctx, mol, ap.rad, ap.eta, ps.work, W);
       else eeq_amat_0d(ctx, mol, ap.rad, ap.eta, W, npad, /*border=*/false, npad, first ? dpotrf_dist_panel(ctx, npad) : 0);
@@ -396,7 +441,7 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
       }
    };
    // Ewald matrices are indefinite along 1 (omitted G = 0 term): shift up front
-   Factor f = factor_solve(ctx, nat, npad, assemble, keep_copy, pbc, xvec, mol.charge, io.qvec);
+   Factor f = factor_solve(ctx, nat, npad, assemble, keep_copy, pbc, xvec, mol.charge, io.qvec, aug);
    if (f.info != 0) {
       ctx->copybacks.clear();
       return f.info;
@@ -405,9 +450,12 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
    const double* zvec = f.z(npad);
 
    if (io.energy || grad || cpq) {
-      double* jq = io.energy ? ctx->alloc<double>(nat) : nullptr;
-      double* atrace = (grad || cpq) ? ctx->alloc<double>((size_t)3 * nat) : nullptr;
-      double* dadL = (grad || cpq) ? ctx->alloc<double>((size_t)9 * nat) : nullptr;
+      // [jq | atrace | dadL | gradx (all atoms) | sig_cn]: one buffer, so that row shards are joined by ONE all-reduce
+      const size_t n1 = (size_t)nat;
+      double* pack = shard ? ctx->alloc_zero<double>(16 * n1 + 16) : nullptr;
+      double* jq = io.energy ? (shard ? pack : ctx->alloc<double>(nat)) : nullptr;
+      double* atrace = (grad || cpq) ? (shard ? pack + n1 : ctx->alloc<double>((size_t)3 * nat)) : nullptr;
+      double* dadL = (grad || cpq) ? (shard ? pack + 4 * n1 : ctx->alloc<double>((size_t)9 * nat)) : nullptr;
       double* Bm = nullptr;
       double* bz = nullptr;
       int64_t mp = 0;
@@ -420,17 +468,28 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
          if (io.energy) pbc_symv(ctx, nat, Jc, npad, vrhs, jq);
          if (grad || cpq) pbc_derivs(ctx, mol, ap.rad, vrhs, ps.work, Bm, mp, mp, atrace, dadL);
       } else {
-         eeq_pair_rows_0d(ctx, mol, ap.rad, ap.eta, vrhs, jq, atrace, dadL);
+         eeq_pair_rows_0d(ctx, mol, ap.rad, ap.eta, vrhs, jq, atrace, dadL, row0, row1);
       }
+      double* gradx = nullptr;
+      double* sig_cn = nullptr;
+      if (grad && lazy) {
+         if (shard) {
+            gradx = pack + 13 * n1;  // all atoms; the caller's rows are picked below
+            sig_cn = pack + 16 * n1;
+            cn_gradient_device(ctx, mol, *io.lazy, thalf, vrhs, 0, nat, gradx, sig_cn, row0, row1);
+            gradx += 3 * (size_t)jb;
+         } else {
+            gradx = ctx->alloc_zero<double>((size_t)3 * nj);
+            sig_cn = ctx->alloc<double>(9);
+            cn_gradient_device(ctx, mol, *io.lazy, thalf, vrhs, jb, je, gradx, sig_cn);
+         }
+      }
+      if (shard) comm_allreduce_sum(ctx, pack, (lazy && grad) ? 16 * n1 + 9 : 13 * n1);
       if (io.energy) MCHRG_LAUNCH(ctx, energy_kernel, (nat + 255) / 256, 256, 0, nat, vrhs, jq, xvec, io.energy);
 
       if (grad || cpq) {
-         double* gradx = grad ? ctx->alloc_zero<double>((size_t)3 * nj) : nullptr;
-         double* sig_cn = nullptr;
-         if (lazy) {
-            sig_cn = ctx->alloc<double>(9);
-            cn_gradient_device(ctx, mol, *io.lazy, thalf, vrhs, jb, je, gradx, sig_cn);
-         } else {
+         if (!lazy) {
+            gradx = grad ? ctx->alloc_zero<double>((size_t)3 * nj) : nullptr;
             eeq_build_b_0d(ctx, mol, ap.rad, vrhs, atrace, thalf, io.dcndr, Bm, mp, gradx, zvec, bz, pbc && cpq, jb, je);
          }
          if (grad) {

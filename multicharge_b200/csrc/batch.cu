@@ -20,6 +20,7 @@
 
 #include "model.cuh"
 #include "erfgauss.cuh"
+#include "diag16.cuh"
 
 namespace mchrg {
 namespace batch {
@@ -645,7 +646,8 @@ constexpr int TS = KB + 1;            // row stride of the diagonal tile
 #ifndef LL_MINB
 #define LL_MINB 6
 #endif
-constexpr int CBW = 20;               // column buffer: 16 entries (parity-split) + [16] pivot + [17] next diagonal entry
+using d16::CBW;              // column buffer of the diagonal-tile routine (diag16.cuh)
+using d16::swz;
 
 
 // doubles: block column below the diagonal tile (swizzled, stride 16) | diagonal tile | its inverse (swizzled)
@@ -655,87 +657,11 @@ __host__ __device__ inline size_t smem_doubles_ll(int npa) {
           (npa <= 2 * KB ? 2 * (size_t)npa : 0);  // tiny orders: room for the two solution vectors
 }
 
-__device__ __forceinline__ int swz(int row, int col) { return row * KB + (col ^ ((row & 3) << 2)); }
-
-// Cholesky + inverse of the 16 x 16 tile T (stride TS; lower triangle valid) by one warp.
-// lane = (row r = lane & 15, column parity h = lane >> 4) holds m[k] = A(r, 2k + h) and x[k] = X(r, 2k + h).
-// The elimination runs on UNSCALED columns (f_r = a_rc / a_cc, L(r, c) = a_rc / sqrt(a_cc) only at the end),
-// X collects inv(L) by the same row operations on [A | I] with its rows scaled at the end as well.  Per step
-// the owners publish column c (and row c of X) through shared memory; every lane then computes the NEXT
-// pivot a_{c+1,c+1} - a_{c+1,c}^2 / a_cc and its reciprocal redundantly, so the only serial dependence from
-// step to step is one FMA + one reciprocal (~90 cycles) and the shared-memory broadcast of the next column
-// runs in its shadow (measured: tools/micro/diag_latency.cu).
-// Columns >= nfree are kept at identity (the right-hand-side rows of the augmented matrix).
-// Outputs: inv(L) in Li (swizzled); L in T when want_l.  Scratch: cbuf[2][20], rbuf[2][16], dvec[16].
-// Returns 0 or the 1-based local index of the first non-positive pivot.
-// (No __restrict__ on the broadcast buffers: they are written by OTHER lanes between the warp barriers.)
+// Cholesky + inverse of the 16 x 16 diagonal tile by one warp: d16::diag_factor_inv (diag16.cuh), tile stride TS,
+// inverse in the swizzled layout the DMMA row solves read
 __device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cbuf, double* rbuf, double* dvec, int lane,
                                                int nfree, bool want_l) {
-   const int r = lane & 15, h = lane >> 4;
-   double m[8], x[8];
-#pragma unroll
-   for (int k = 0; k < 8; ++k) {
-      const int c = 2 * k + h;
-      m[k] = (c <= r) ? T[r * TS + c] : 0.0;
-      if (c >= nfree) m[k] = (c == r) ? 1.0 : 0.0;
-      x[k] = (c == r) ? 1.0 : 0.0;
-   }
-   const int myslot = (r & 1) * 8 + (r >> 1);  // parity-split position of row r in the column buffer
-   auto publish = [&](const int c) {
-      double* cb = cbuf + (c & 1) * CBW;
-      const bool forced = (c >= KB - 2) && (c >= nfree);  // right-hand-side rows: their own columns stay identity
-      if (h == (c & 1)) {
-         cb[myslot] = (r > c && !forced) ? m[c >> 1] : 0.0;
-         if (r == c) cb[16] = forced ? 1.0 : m[c >> 1];
-      }
-      if (c + 1 < KB && r == c + 1 && h == ((c + 1) & 1)) cb[17] = m[(c + 1) >> 1];
-      if (r == c) {
-         double2* rb = reinterpret_cast<double2*>(rbuf + (c & 1) * KB + h * 8);
-#pragma unroll
-         for (int k = 0; k < 4; ++k) rb[k] = make_double2(x[2 * k], x[2 * k + 1]);
-      }
-   };
-   publish(0);
-   __syncwarp();
-   double piv = cbuf[16];
-   double d = 1.0 / piv;
-   int bad = !(piv > 0.0) ? 1 : 0;
-#pragma unroll
-   for (int c = 0; c < KB; ++c) {
-      const double* cb = cbuf + (c & 1) * CBW;
-      const double* rb = rbuf + (c & 1) * KB;
-      if (lane == 0) dvec[c] = d;
-      double dn = 0.0;
-      if (c + 1 < KB) {  // next pivot, redundantly in every lane
-         const bool forced = (c + 1 >= KB - 2) && (c + 1 >= nfree);
-         const double u = cb[((c + 1) & 1) * 8 + ((c + 1) >> 1)];
-         piv = forced ? 1.0 : fma(-u * u, d, cb[17]);
-         bad = (!(piv > 0.0) && bad == 0) ? (c + 2) : bad;
-         dn = 1.0 / piv;
-      }
-      const double f = cb[myslot] * d;  // 0 for r <= c: the updates below leave those rows alone
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-         m[k] = fma(-f, cb[h * 8 + k], m[k]);  // entries right of the diagonal collect garbage; never used
-         x[k] = fma(-f, rb[h * 8 + k], x[k]);
-      }
-      if (c + 1 < KB) {
-         publish(c + 1);
-         __syncwarp();
-         d = dn;
-      }
-   }
-   __syncwarp();
-   if (lane < KB) dvec[lane] = sqrt(dvec[lane]);  // 1 / L(c, c)
-   __syncwarp();
-   const double rs = dvec[r];
-#pragma unroll
-   for (int k = 0; k < 8; ++k) {
-      const int c = 2 * k + h;
-      Li[swz(r, c)] = (c <= r) ? x[k] * rs : 0.0;
-      if (want_l) T[r * TS + c] = (c <= r) ? m[k] * dvec[c] : 0.0;
-   }
-   return bad;
+   return d16::diag_factor_inv<TS, true, KB>(T, Li, cbuf, rbuf, dvec, lane, nfree, want_l);
 }
 
 template <int NT>
@@ -978,14 +904,7 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
 template <int NT>
 static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count, int npa_max) {
    const size_t smem = smem_doubles_ll(npa_max) * sizeof(double);
-   static bool configured = false;
-   if (!configured) {
-      MCHRG_CUDA(cudaFuncSetAttribute(eeq_factor_ll_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(smem_doubles_ll(NPA_MAX) * sizeof(double))));
-      MCHRG_CUDA(cudaFuncSetAttribute(eeq_factor_ll_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      (int)cudaSharedmemCarveoutMaxShared));
-      configured = true;
-   }
+   ctx->ensure_smem(eeq_factor_ll_kernel<NT>, smem_doubles_ll(NPA_MAX) * sizeof(double), /*max_carveout=*/true);
    MCHRG_LAUNCH(ctx, eeq_factor_ll_kernel<NT>, (unsigned)count, NT, smem, a);
 }
 
@@ -999,7 +918,7 @@ constexpr int LL_NT = LL_NT_DEF;  // threads per molecule in the factorisation k
 static void launch_factor_groups(mchrg_b200_context* ctx, const Args& a, const int32_t* dperm,
                                  const std::vector<size_t>& cls_start, const std::vector<int>& cls_count) {
    constexpr int NCLASS = NP_MAX / KB;
-   static const int group = std::getenv("MCHRG_B200_FACTOR_GROUP") ? std::max(1, atoi(std::getenv("MCHRG_B200_FACTOR_GROUP"))) : 13;
+   const int group = (int)std::max<long long>(1, env_ll("MCHRG_B200_FACTOR_GROUP", 13));
    for (int chi = NCLASS; chi >= 1; chi -= group) {  // perm holds the classes in descending order
       const int clo = std::max(1, chi - group + 1);
       int count = 0;
@@ -1018,16 +937,10 @@ template <int NT, int PH>
 static void launch_class(mchrg_b200_context* ctx, const Args& a, int count) {
    const bool heavy = (PH == 0);
    const size_t smem = (heavy ? smem_doubles(a.np) : smem_doubles_pair(a.np)) * sizeof(double);
-   static size_t configured = 0;
-   if (smem > configured) {
-      const size_t cap = (heavy ? smem_doubles(NP_MAX) : smem_doubles_pair(NPA_MAX)) * sizeof(double);
-      MCHRG_CUDA(cudaFuncSetAttribute(eeq_batch_kernel<NT, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
-      // same shared-memory carveout as the factorisation kernel: CTAs of kernels that ask for different
-      // L1/shared splits cannot share an SM
-      MCHRG_CUDA(cudaFuncSetAttribute(eeq_batch_kernel<NT, PH>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      (int)cudaSharedmemCarveoutMaxShared));
-      configured = cap;
-   }
+   // same shared-memory carveout as the factorisation kernel: CTAs of kernels that ask for different
+   // L1/shared splits cannot share an SM
+   ctx->ensure_smem(eeq_batch_kernel<NT, PH>, (heavy ? smem_doubles(NP_MAX) : smem_doubles_pair(NPA_MAX)) * sizeof(double),
+                    /*max_carveout=*/true);
    MCHRG_LAUNCH(ctx, (eeq_batch_kernel<NT, PH>), (unsigned)count, NT, smem, a);
 }
 
@@ -1208,7 +1121,7 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
          a.vecg = ctx->alloc<double>(3 * ntot);
          a.lamg = ctx->alloc<double>(nmol);
          a.ntot = (int64_t)ntot;
-         const int maxchunk = std::getenv("MCHRG_B200_CHUNKS") ? std::max(1, atoi(std::getenv("MCHRG_B200_CHUNKS"))) : 16;
+         const int maxchunk = (int)std::max<long long>(1, env_ll("MCHRG_B200_CHUNKS", 16));
          const int nchunk = (int)std::min<int64_t>(maxchunk, std::max<int64_t>(1, nmol / 4096));
          std::vector<int32_t> all_perm;
          std::vector<std::vector<size_t>> starts(nchunk);
@@ -1226,24 +1139,32 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
          MCHRG_CUDA(cudaMemcpyAsync(dperm, all_perm.data(), all_perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
          cudaEvent_t staged = ctx->next_event();
          MCHRG_CUDA(cudaEventRecord(staged, ctx->stream));
-         if (std::getenv("MCHRG_B200_TRACE")) {  // debug: phases of the whole batch one after the other, timed
+         if (env_ll("MCHRG_B200_TRACE", 0) > 0) {  // phases of the whole batch one after the other, each timed on its own
             cudaEvent_t t[4];
             for (auto& e : t) MCHRG_CUDA(cudaEventCreate(&e));
             batch::Args b = a;
             MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
+            const uint64_t l0 = ctx->launches;
             MCHRG_CUDA(cudaEventRecord(t[0], ctx->stream));
             for (int c = 0; c < nchunk; ++c) batch::launch_pairs<1>(ctx, b, dperm + chunk_off[c], (int)(chunk_off[c + 1] - chunk_off[c]));
             MCHRG_CUDA(cudaEventRecord(t[1], ctx->stream));
+            const uint64_t l1 = ctx->launches;
             for (int c = 0; c < nchunk; ++c) {
                batch::launch_factor_groups(ctx, b, dperm + chunk_off[c], starts[c], counts[c]);
             }
             MCHRG_CUDA(cudaEventRecord(t[2], ctx->stream));
+            const uint64_t l2 = ctx->launches;
+            ctx->trace_launches[0] = (int)(l1 - l0);
+            ctx->trace_launches[1] = (int)(l2 - l1);
+            ctx->trace_launches[2] = (int)(l1 - l0);
             for (int c = 0; c < nchunk; ++c) batch::launch_pairs<3>(ctx, b, dperm + chunk_off[c], (int)(chunk_off[c + 1] - chunk_off[c]));
             MCHRG_CUDA(cudaEventRecord(t[3], ctx->stream));
             MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
             float ms[3];
             for (int k = 0; k < 3; ++k) MCHRG_CUDA(cudaEventElapsedTime(&ms[k], t[k], t[k + 1]));
-            fprintf(stderr, "[mchrg_b200 trace] nmol=%d pairA=%.2f ms factor=%.2f ms pairC=%.2f ms\n", nmol, ms[0], ms[1], ms[2]);
+            for (int k = 0; k < 3; ++k) ctx->trace_ms[k] = ms[k];
+            if (env_ll("MCHRG_B200_TRACE", 0) > 1)
+               fprintf(stderr, "[mchrg_b200 trace] nmol=%d pairA=%.2f ms factor=%.2f ms pairC=%.2f ms\n", nmol, ms[0], ms[1], ms[2]);
             for (auto& e : t) cudaEventDestroy(e);
             return 0;
          }
@@ -1283,7 +1204,7 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
 
       // Host buffers: pipeline chunks of molecules so that the H2D copy of chunk c+1 and the D2H copy of
       // chunk c-1 overlap the kernels of chunk c (asynchronous when the caller's buffers are pinned).
-      static const int host_chunks = std::getenv("MCHRG_B200_HOST_CHUNKS") ? std::max(1, atoi(std::getenv("MCHRG_B200_HOST_CHUNKS"))) : 0;
+      const int host_chunks = (int)std::max<long long>(0, env_ll("MCHRG_B200_HOST_CHUNKS", 0));
       // ~256k atoms per chunk (measured on the 100k-molecule bench: 5 / 12 / 24 / 48 chunks give 3.57 / 3.80 /
       // 3.92 / 3.94 M molecules/s end to end: only the first H2D and the last D2H chunk stay exposed)
       const int nchunk = host_chunks ? host_chunks : (int)std::min<size_t>(32, std::max<size_t>(2, ntot >> 18));

@@ -9,10 +9,13 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <cstdlib>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mchrg_b200.h"
+#include "comm.cuh"
 
 namespace mchrg {
 
@@ -42,6 +45,13 @@ void set_last_error(const std::string& msg);
 
 constexpr int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// tuning knobs are read from the environment on every call (no process-wide caching: tests and callers may
+// change them between calls)
+inline long long env_ll(const char* name, long long def) {
+   const char* e = std::getenv(name);
+   return (e && *e) ? std::atoll(e) : def;
+}
+
 }  // namespace mchrg
 
 // One GPU + one stream + a grow-only bump arena.  Calls on one context are serialised by `mu`;
@@ -61,17 +71,31 @@ struct mchrg_b200_context {
    cudaEvent_t next_event();
    int sm_count = 148;
    double2* erf_tab = nullptr;        // (erf, exp(-x^2)) nodes of erfgauss.cuh, device memory
-   // panel exchange of the multi-GPU factorisation (mchrg_b200_set_exchange); nranks == 1: single GPU
-   struct Exchange {
-      int rank = 0, nranks = 1;
-      void (*start)(void*, void*, int64_t, int32_t, int32_t) = nullptr;
-      void (*wait)(void*, int32_t) = nullptr;
-      void* user = nullptr;
-      bool on() const { return nranks > 1 && start && wait; }
-   } xch;
+   // collectives of the multi-GPU single-system path (comm.cuh); nullptr: single GPU.  Every collective is
+   // enqueued on stream_comm and tied to the compute streams with events.
+   mchrg::Comm* comm = nullptr;
+   cudaStream_t stream_comm = nullptr;
+   int nranks() const;
+   int rank() const;
    size_t smem_optin = 0;
+   // kernels whose dynamic shared-memory limit has been raised through THIS context (cudaFuncSetAttribute acts on
+   // the current device only, so the record is per context, not per process)
+   std::unordered_map<const void*, size_t> func_smem;
+   template <class K>
+   void ensure_smem(K* kernel, size_t bytes, bool max_carveout = false) {
+      auto it = func_smem.find((const void*)kernel);
+      if (it != func_smem.end() && it->second >= bytes) return;
+      MCHRG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      if (max_carveout)
+         MCHRG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         (int)cudaSharedmemCarveoutMaxShared));
+      func_smem[(const void*)kernel] = bytes;
+   }
    std::mutex mu;
    uint64_t launches = 0;
+   // MCHRG_B200_TRACE=1: serial per-phase times of the last split-path batch (pair A, factorisation, pair C)
+   double trace_ms[3] = {0.0, 0.0, 0.0};
+   int trace_launches[3] = {0, 0, 0};
 
    // bump arena: one cudaMalloc'ed slab, reset at the start of every entry point; when a call
    // needs more than the slab holds, extra slabs are chained and merged on the next reset.
@@ -184,6 +208,7 @@ int guarded(mchrg_b200_context* ctx, F&& body) {
       if (ctx->stream_aux) cudaStreamSynchronize(ctx->stream_aux);
       if (ctx->stream_in) cudaStreamSynchronize(ctx->stream_in);
       if (ctx->stream_out) cudaStreamSynchronize(ctx->stream_out);
+      if (ctx->stream_comm) cudaStreamSynchronize(ctx->stream_comm);
       cudaGetLastError();
       return e.code;
    } catch (const std::exception& e) {

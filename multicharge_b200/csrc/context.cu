@@ -71,6 +71,9 @@ void mchrg_b200_context::finish() {
    MCHRG_CUDA(cudaStreamSynchronize(stream));
 }
 
+int mchrg_b200_context::nranks() const { return comm ? comm->nranks : 1; }
+int mchrg_b200_context::rank() const { return comm ? comm->rank : 0; }
+
 cudaEvent_t mchrg_b200_context::next_event() {
    if (events_used == events.size()) {
       cudaEvent_t e;
@@ -138,6 +141,7 @@ int mchrg_b200_context_create(int device, mchrg_b200_context** out) {
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, prio_lo));
       MCHRG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
       MCHRG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
+      MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_comm, cudaStreamNonBlocking, prio_hi));
       ctx->active = ctx->stream;
       {
          const std::vector<double2> tab = mchrg::eg::host_table();
@@ -164,7 +168,12 @@ void mchrg_b200_context_destroy(mchrg_b200_context* ctx) {
       cudaStreamSynchronize(ctx->stream_hi);
       cudaStreamDestroy(ctx->stream_hi);
    }
-   for (cudaStream_t st : {ctx->stream_aux, ctx->stream_in, ctx->stream_out, ctx->stream_hi2}) {
+   if (ctx->comm) {
+      if (ctx->stream_comm) cudaStreamSynchronize(ctx->stream_comm);
+      delete ctx->comm;
+      ctx->comm = nullptr;
+   }
+   for (cudaStream_t st : {ctx->stream_aux, ctx->stream_in, ctx->stream_out, ctx->stream_hi2, ctx->stream_comm}) {
       if (st) {
          cudaStreamSynchronize(st);
          cudaStreamDestroy(st);
@@ -191,26 +200,15 @@ int mchrg_b200_synchronize(mchrg_b200_context* ctx) {
 void* mchrg_b200_stream(mchrg_b200_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 void* mchrg_b200_side_stream(mchrg_b200_context* ctx) { return ctx ? (void*)ctx->stream_aux : nullptr; }
 
-int mchrg_b200_set_exchange(mchrg_b200_context* ctx, int32_t rank, int32_t nranks, mchrg_b200_exchange_start_fn start,
-                            mchrg_b200_exchange_wait_fn wait, void* user) {
-   if (!ctx) return MCHRG_B200_ERR_ARG;
-   std::lock_guard<std::mutex> lock(ctx->mu);
-   if (nranks <= 1 || !start || !wait) {
-      ctx->xch = mchrg_b200_context::Exchange();
-      return 0;
+uint64_t mchrg_b200_launch_count(const mchrg_b200_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int mchrg_b200_batch_trace(const mchrg_b200_context* ctx, double* ms, int32_t* launches) {
+   if (!ctx || !ms || !launches) return MCHRG_B200_ERR_ARG;
+   for (int k = 0; k < 3; ++k) {
+      ms[k] = ctx->trace_ms[k];
+      launches[k] = ctx->trace_launches[k];
    }
-   if (rank < 0 || rank >= nranks) {
-      mchrg::set_last_error("set_exchange: rank outside [0, nranks)");
-      return MCHRG_B200_ERR_ARG;
-   }
-   ctx->xch.rank = rank;
-   ctx->xch.nranks = nranks;
-   ctx->xch.start = start;
-   ctx->xch.wait = wait;
-   ctx->xch.user = user;
    return 0;
 }
-
-uint64_t mchrg_b200_launch_count(const mchrg_b200_context* ctx) { return ctx ? ctx->launches : 0; }
 
 }  // extern "C"

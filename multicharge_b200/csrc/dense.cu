@@ -7,6 +7,7 @@
 #include <cstdio>
 #include "dense.cuh"
 #include "erfgauss.cuh"
+#include "diag16.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -191,23 +192,13 @@ dgemm_dmma_kernel(int64_t kdim, double alpha, const double* __restrict__ A, int6
 }
 
 // MCHRG_B200_GEMM_BN = 64 | 128 (A/B timing); default chosen on B200
-static int gemm_bn() {
-   static const int v = std::getenv("MCHRG_B200_GEMM_BN") ? atoi(std::getenv("MCHRG_B200_GEMM_BN")) : 64;
-   return v == 128 ? 128 : 64;
-}
+static int gemm_bn() { return env_ll("MCHRG_B200_GEMM_BN", 64) == 128 ? 128 : 64; }
 
-static void gemm_setup_once() {
-   static bool done = false;
-   if (done) return;
-   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)gemm::Cfg<128>::SMEM_BYTES));
-   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)gemm::Cfg<128>::SMEM_BYTES));
-   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)gemm::Cfg<64>::SMEM_BYTES));
-   MCHRG_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)gemm::Cfg<64>::SMEM_BYTES));
-   done = true;
+static void gemm_setup(mchrg_b200_context* ctx) {
+   ctx->ensure_smem(dgemm_dmma_kernel<true, 128>, gemm::Cfg<128>::SMEM_BYTES);
+   ctx->ensure_smem(dgemm_dmma_kernel<false, 128>, gemm::Cfg<128>::SMEM_BYTES);
+   ctx->ensure_smem(dgemm_dmma_kernel<true, 64>, gemm::Cfg<64>::SMEM_BYTES);
+   ctx->ensure_smem(dgemm_dmma_kernel<false, 64>, gemm::Cfg<64>::SMEM_BYTES);
 }
 
 template <int BNT>
@@ -229,7 +220,7 @@ void dgemm_padded(mchrg_b200_context* ctx, bool transb, int64_t m, int64_t n, in
    if (m % gemm::BM || n % gemm::BN || k % (2 * gemm::BK) || (lda & 1) || (ldb & 1))
       fail(MCHRG_B200_ERR_ARG, "dgemm_padded: unpadded operand (m=%lld n=%lld k=%lld lda=%lld ldb=%lld)",
            (long long)m, (long long)n, (long long)k, (long long)lda, (long long)ldb);
-   gemm_setup_once();
+   gemm_setup(ctx);
    // in-place products (X <- X inv(L)^T: every CTA reads the whole row block of X) need one CTA per row block
    const int bnt = (A == C || B == C) ? 128 : gemm_bn();
    const unsigned nsplit = (unsigned)(gemm::BN / bnt);
@@ -255,153 +246,173 @@ static void dsyrk_cyclic(mchrg_b200_context* ctx, int64_t n, int64_t k, const do
    for (int t = t0; t < T; t += stride)
       for (int w = 0; w < wt && t + w < T; ++w) tiles += T - t - w;
    if (tiles == 0) return;
-   gemm_setup_once();
+   gemm_setup(ctx);
    const int4 cyc = make_int4(t0, stride, T, wt);
    if (gemm_bn() == 64) gemm_launch<64>(ctx, true, dim3((unsigned)tiles * 2), k, -1.0, P, ldw, P, ldw, 1.0, W, ldw, 2, cyc);
    else gemm_launch<128>(ctx, true, dim3((unsigned)tiles), k, -1.0, P, ldw, P, ldw, 1.0, W, ldw, 2, cyc);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cholesky leaf: factor one 128 x 128 diagonal block and invert its factor, one CTA of 256
-// threads.  Thread (tx, ty) = (tid & 15, tid >> 4) keeps the cyclic sub-matrix
-// rows {tx + 16 r}, cols {ty + 16 c} (r, c = 0..7) in registers; every elimination step
-// broadcasts one column (factorisation) or one row (Gauss-Jordan inversion) through shared memory,
-// one barrier per step.
+// Cholesky leaf: factor one 128 x 128 diagonal block and invert its factor in ONE CTA (8 warps), everything in
+// shared memory as 16 x 16 tiles (row stride 20: conflict-free FP64 mma fragment loads in both orientations).
+//   Cholesky, right-looking over 8 tile columns:
+//     D  diagonal tile: Cholesky + explicit inverse by one warp (d16::diag_factor_inv, a chain of 16 pivot steps)
+//     S  tiles below:   L(i,k) = A(i,k) inv(L_kk)^T                    one DMMA tile product per warp
+//     U  trailing tiles A(i,j) -= L(i,k) L(j,k)^T  on DMMA; warp 0 takes the next diagonal tile first and factors
+//        it while the other warps finish the update (look-ahead), so a tile column costs ~ one D chain
+//   inverse by recursive doubling over the tile grid (h = 1, 2, 4 tiles): X21 = -X22 (L21 X11), two DMMA stages
+//   per level; X21 replaces the (dead) L21 tiles, the diagonal tiles of X come from D.
+// aug != 0: the last two rows are right-hand sides of an augmented system (their own columns stay identity, so
+// the forward substitution falls out of the factorisation; see dpotrf_dist).
+// ~18 us (the register-cyclic rank-one version it replaces: 78 us = 128 barrier-separated column steps twice).
 // ------------------------------------------------------------------------------------------------
 namespace leaf {
-constexpr int N = 128, THREADS = 256;
-constexpr size_t SMEM_BYTES = (size_t(N) * N + 2 * N + N) * sizeof(double);  // Ls + bcast[2] + 1/diag
+constexpr int N = 128, T16 = 16, NTL = N / T16, TLD = 20, TSZ = T16 * TLD;
+constexpr int THREADS = 256, NW = THREADS / 32;
+constexpr int NTRI = NTL * (NTL + 1) / 2;
+// doubles: L tiles (lower block triangle) | diagonal tiles of the inverse | product scratch (16 tiles) | D scratch
+constexpr size_t SMEM_BYTES = ((size_t)(NTRI + NTL + 16) * TSZ + 2 * d16::CBW + 2 * T16 + T16) * sizeof(double);
+__device__ __forceinline__ int tix(int R, int C) { return R * (R + 1) / 2 + C; }
+
+// acc += A B^T for 16 x 16 tiles (row stride TLD): D[m][n] = sum_c A[m][c] B[n][c]
+__device__ __forceinline__ void mma_nt(double (&acc)[2][2][2], const double* A, const double* B, int g, int t) {
+#pragma unroll
+   for (int kk = 0; kk < 4; ++kk) {
+      const double a0 = A[g * TLD + 4 * kk + t], a1 = A[(8 + g) * TLD + 4 * kk + t];
+      const double b0 = B[g * TLD + 4 * kk + t], b1 = B[(8 + g) * TLD + 4 * kk + t];
+      dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+      dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+      dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+      dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+   }
+}
+// acc += A B: D[m][n] = sum_k A[m][k] B[k][n]
+__device__ __forceinline__ void mma_nn(double (&acc)[2][2][2], const double* A, const double* B, int g, int t) {
+#pragma unroll
+   for (int kk = 0; kk < 4; ++kk) {
+      const double a0 = A[g * TLD + 4 * kk + t], a1 = A[(8 + g) * TLD + 4 * kk + t];
+      const double b0 = B[(4 * kk + t) * TLD + g], b1 = B[(4 * kk + t) * TLD + 8 + g];
+      dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+      dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+      dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+      dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+   }
+}
+// tile = sign * acc  /  tile -= acc   (lane holds rows 8 mt + g, columns 8 nt + 2 t, + 1)
+__device__ __forceinline__ void put(double* tile, const double (&acc)[2][2][2], double sign, int g, int t) {
+#pragma unroll
+   for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+         *reinterpret_cast<double2*>(tile + (8 * mt + g) * TLD + 8 * nt + 2 * t) =
+            make_double2(sign * acc[mt][nt][0], sign * acc[mt][nt][1]);
+}
+__device__ __forceinline__ void sub(double* tile, const double (&acc)[2][2][2], int g, int t) {
+#pragma unroll
+   for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+         double2* d = reinterpret_cast<double2*>(tile + (8 * mt + g) * TLD + 8 * nt + 2 * t);
+         double2 v = *d;
+         v.x -= acc[mt][nt][0];
+         v.y -= acc[mt][nt][1];
+         *d = v;
+      }
+}
 }  // namespace leaf
 
 __global__ void __launch_bounds__(leaf::THREADS, 1)
 potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv, int* __restrict__ info,
-                  int pivot_base) {
+                  int pivot_base, int aug) {
    using namespace leaf;
    extern __shared__ __align__(16) double smem[];
-   double* Ls = smem;                // Ls[col * N + row] = L(row, col)
-   double* bc = smem + N * N;        // bc[2][N] broadcast buffers
-   double* invd = bc + 2 * N;        // 1 / L(j, j)
-   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-
-   double a[8][8];
-#pragma unroll
-   for (int r = 0; r < 8; ++r)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-         const int row = tx + 16 * r, col = ty + 16 * c;
-         a[r][c] = (row >= col) ? W[row + (int64_t)col * ldw] : W[col + (int64_t)row * ldw];
-      }
-
-   bool failed = false;
-#pragma unroll
-   for (int cj = 0; cj < 8; ++cj) {
-      for (int jt = 0; jt < 16; ++jt) {
-         const int j = 16 * cj + jt;
-         double* col = bc + (j & 1) * N;
-         if (ty == jt) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) col[tx + 16 * r] = a[r][cj];
-         }
-         __syncthreads();
-         const double d = col[j];
-         if (!(d > 0.0)) {  // also catches NaN; uniform across the CTA
-            if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
-            failed = true;
-            break;
-         }
-         const double inv = eg::fast_rsqrt(d);  // hardware seed + one third-order step (1.4e-16 rel.)
-         if (ty == jt) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-               const int row = tx + 16 * r;
-               if (row > j) a[r][cj] *= inv;
-               else if (row == j) a[r][cj] = d * inv;
-            }
-         }
-         // masked column factors: zero for rows / columns <= j, so the rank-one update needs no predicates
-         double lr[8], lc[8];
-#pragma unroll
-         for (int r = 0; r < 8; ++r) lr[r] = (r >= cj && tx + 16 * r > j) ? -col[tx + 16 * r] * inv : 0.0;
-#pragma unroll
-         for (int c = 0; c < 8; ++c) lc[c] = (c >= cj && ty + 16 * c > j) ? col[ty + 16 * c] * inv : 0.0;
-#pragma unroll
-         for (int r = 0; r < 8; ++r) {
-            if (r < cj) continue;  // rows tx + 16 r <= j for r < cj
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-               if (c < cj) continue;
-               a[r][c] = fma(lr[r], lc[c], a[r][c]);
-            }
-         }
-      }
-      if (failed) break;
+   double* Lt = smem;               // tile (R, C), R >= C, at tix(R, C) * TSZ; later the off-diagonal tiles of inv(L)
+   double* Xd = Lt + NTRI * TSZ;    // diagonal tiles of inv(L)
+   double* Ts = Xd + NTL * TSZ;     // products L21 X11 of the inversion
+   double* cbuf = Ts + 16 * TSZ;
+   double* rbuf = cbuf + 2 * d16::CBW;
+   double* dvec = rbuf + 2 * T16;
+   __shared__ int sfail;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int g = lane >> 2, t = lane & 3;
+   if (tid == 0) sfail = 0;
+   for (int e = tid; e < N * N; e += THREADS) {  // consecutive threads walk down a column: coalesced
+      const int r = e & (N - 1), c = e >> 7, R = r >> 4, C = c >> 4;
+      if (R >= C) Lt[tix(R, C) * TSZ + (r & 15) * TLD + (c & 15)] = (r >= c) ? W[r + (int64_t)c * ldw] : 0.0;
    }
-
-   // publish L (lower triangle only) to global memory and shared memory
-#pragma unroll
-   for (int r = 0; r < 8; ++r)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-         const int row = tx + 16 * r, col = ty + 16 * c;
-         if (row >= col) {
-            W[row + (int64_t)col * ldw] = a[r][c];
-            Ls[col * N + row] = a[r][c];
-            if (row == col) invd[row] = 1.0 / a[r][c];
-         }
-      }
    __syncthreads();
-
-   // Gauss-Jordan: X = inv(L), starting from the identity
-   double x[8][8];
-#pragma unroll
-   for (int r = 0; r < 8; ++r)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) x[r][c] = (tx + 16 * r == ty + 16 * c) ? 1.0 : 0.0;
-
-#pragma unroll
-   for (int cj = 0; cj < 8; ++cj) {
-      for (int jt = 0; jt < 16; ++jt) {
-         const int j = 16 * cj + jt;
-         double* rowb = bc + (j & 1) * N;
-         if (tx == jt) {
-            const double s = invd[j];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-               x[cj][c] *= s;
-               rowb[ty + 16 * c] = x[cj][c];
-            }
-         }
-         __syncthreads();
-#pragma unroll
-         for (int r = 0; r < 8; ++r) {
-            if (r < cj) continue;
-            const int row = tx + 16 * r;
-            if (row > j) {
-               const double l = Ls[j * N + row];
-#pragma unroll
-               for (int c = 0; c < 8; ++c) {
-                  if (c > cj) continue;  // X(j, col) == 0 for col > j
-                  x[r][c] = fma(-l, rowb[ty + 16 * c], x[r][c]);
-               }
-            }
-         }
-      }
+   if (warp == 0) {
+      const int bad = d16::diag_factor_inv<TLD, false, TLD>(Lt, Xd, cbuf, rbuf, dvec, lane, T16, true);
+      if (bad && lane == 0) sfail = bad;
    }
-#pragma unroll
-   for (int r = 0; r < 8; ++r)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-         const int row = tx + 16 * r, col = ty + 16 * c;
-         dinv[row + col * N] = (row >= col && !failed) ? x[r][c] : 0.0;
+   __syncthreads();
+   for (int k = 0; k + 1 < NTL && !sfail; ++k) {
+      const int nrem = NTL - 1 - k;
+      if (warp < nrem) {  // S: one tile below the diagonal per warp, in place
+         double* A = Lt + tix(k + 1 + warp, k) * TSZ;
+         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+         mma_nt(acc, A, Xd + k * TSZ, g, t);
+         __syncwarp();
+         put(A, acc, 1.0, g, t);
       }
-}
-
-static void leaf_setup_once() {
-   static bool done = false;
-   if (done) return;
-   MCHRG_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)leaf::SMEM_BYTES));
-   done = true;
+      __syncthreads();
+      // U: tiles (k+1+a, k+1+b), 0 <= b <= a < nrem, numbered u = a (a + 1) / 2 + b; u = 0 is the next diagonal tile
+      const int ntile = nrem * (nrem + 1) / 2;
+      if (warp == 0) {
+         double* A = Lt + tix(k + 1, k + 1) * TSZ;
+         const double* P = Lt + tix(k + 1, k) * TSZ;
+         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+         mma_nt(acc, P, P, g, t);
+         sub(A, acc, g, t);
+         __syncwarp();
+         const int nfree = (aug && k + 2 == NTL) ? T16 - 2 : T16;
+         const int bad = d16::diag_factor_inv<TLD, false, TLD>(A, Xd + (k + 1) * TSZ, cbuf, rbuf, dvec, lane, nfree, true);
+         if (bad && lane == 0) sfail = T16 * (k + 1) + bad;
+      } else {
+         for (int u = warp; u < ntile; u += NW - 1) {
+            int a = 0;
+            while ((a + 1) * (a + 2) / 2 <= u) ++a;
+            const int b = u - a * (a + 1) / 2;
+            double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+            mma_nt(acc, Lt + tix(k + 1 + a, k) * TSZ, Lt + tix(k + 1 + b, k) * TSZ, g, t);
+            sub(Lt + tix(k + 1 + a, k + 1 + b) * TSZ, acc, g, t);
+         }
+      }
+      __syncthreads();
+   }
+   if (sfail) {  // not positive definite: report the pivot; the caller re-assembles the matrix
+      if (tid == 0) atomicCAS(info, 0, pivot_base + sfail);
+      for (int e = tid; e < N * N; e += THREADS) dinv[e] = 0.0;
+      return;
+   }
+   // publish L (lower triangle only)
+   for (int e = tid; e < N * N; e += THREADS) {
+      const int r = e & (N - 1), c = e >> 7;
+      if (r >= c) W[r + (int64_t)c * ldw] = Lt[tix(r >> 4, c >> 4) * TSZ + (r & 15) * TLD + (c & 15)];
+   }
+   // inverse: blocks of h tiles are merged pairwise, X21 = -X22 (L21 X11); tile (R, C) of X: Xd when R == C
+   auto xt = [&](int R, int C) -> const double* { return (R == C) ? Xd + R * TSZ : Lt + tix(R, C) * TSZ; };
+   for (int h = 1; h < NTL; h *= 2) {
+      const int nitems = (NTL / 2) * h, hh = h * h;  // (pair p, tile row i, tile column j) of the h x h tile block X21
+      for (int item = warp; item < nitems; item += NW) {
+         const int p = item / hh, i = (item % hh) / h, j = item % h, b0 = 2 * h * p;
+         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+         for (int k = j; k < h; ++k) mma_nn(acc, Lt + tix(b0 + h + i, b0 + k) * TSZ, xt(b0 + k, b0 + j), g, t);
+         put(Ts + item * TSZ, acc, 1.0, g, t);
+      }
+      __syncthreads();
+      for (int item = warp; item < nitems; item += NW) {
+         const int p = item / hh, i = (item % hh) / h, j = item % h, b0 = 2 * h * p;
+         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+         for (int k = 0; k <= i; ++k) mma_nn(acc, xt(b0 + h + i, b0 + h + k), Ts + (p * hh + k * h + j) * TSZ, g, t);
+         put(Lt + tix(b0 + h + i, b0 + j) * TSZ, acc, -1.0, g, t);
+      }
+      __syncthreads();
+   }
+   for (int e = tid; e < N * N; e += THREADS) {
+      const int r = e & (N - 1), c = e >> 7;
+      dinv[e] = (r >= c) ? xt(r >> 4, c >> 4)[(r & 15) * TLD + (c & 15)] : 0.0;
+   }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -435,141 +446,208 @@ void dtrsm_right_ln(mchrg_b200_context* ctx, int64_t m, int64_t n, const double*
    dtrsm_right_ln(ctx, m, n1, L, ldl, dinv, X, ldx);
 }
 
+// aug_end: order of the whole matrix when its last two rows are right-hand sides (augmented system), else -1;
+// the leaf that ends there keeps those rows' own columns at identity
 static void potrf_rec(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info,
-                      int64_t off) {
+                      int64_t off, int64_t aug_end) {
    if (n == TILE) {
-      MCHRG_LAUNCH(ctx, potrf_leaf_kernel, 1, leaf::THREADS, leaf::SMEM_BYTES, W, ldw, dinv, info, (int)off);
+      ctx->ensure_smem(potrf_leaf_kernel, leaf::SMEM_BYTES);
+      MCHRG_LAUNCH(ctx, potrf_leaf_kernel, 1, leaf::THREADS, leaf::SMEM_BYTES, W, ldw, dinv, info, (int)off,
+                   (off + TILE == aug_end) ? 1 : 0);
       return;
    }
    const int64_t n1 = split(n), n2 = n - n1;
    double* W21 = W + n1;
    double* W22 = W + n1 + n1 * ldw;
    double* dinv2 = dinv + (n1 / TILE) * TILE * TILE;
-   potrf_rec(ctx, n1, W, ldw, dinv, info, off);
+   potrf_rec(ctx, n1, W, ldw, dinv, info, off, aug_end);
    dtrsm_right_lt(ctx, n2, n1, W, ldw, dinv, W21, ldw);
    dgemm_padded(ctx, true, n2, n2, n1, -1.0, W21, ldw, W21, ldw, 1.0, W22, ldw, /*lower_only=*/true);
-   potrf_rec(ctx, n2, W22, ldw, dinv2, info, off + n1);
+   potrf_rec(ctx, n2, W22, ldw, dinv2, info, off + n1, aug_end);
 }
 
-// Right-looking blocked Cholesky with one panel of look-ahead on two streams.
-//   P (high priority): diagonal block (recursive), panel TRSM, update of the NEXT block column
-//   U (main stream)  : the bulk trailing update (lower block triangle beyond the next block column)
-// leaf / skinny-GEMM latency of panel k+1 is hidden behind the bulk update of panel k.
-static int64_t panel_width() {  // tuning knob (multiple of 128); default chosen on B200 at n = 16384
-   static int64_t w = 0;
-   if (w == 0) {
-      const char* e = std::getenv("MCHRG_B200_PANEL");
-      w = e ? std::atoll(e) : 256;
-      if (w < TILE || w % TILE) w = 256;
-   }
-   return w;
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU right-looking Cholesky, 1 x R process grid, block-cyclic by column groups:
+//   group g = columns [g DB, (g + 1) DB), owner(g) = g % R;  a group is factored in sub-panels of PW columns
+//   (PW | DB).  Only the owner keeps a group up to date and only the owner's copy is read on entry (the assembly
+//   skips the other groups, dpotrf_dist_panel); factored sub-panels are broadcast (NCCL / peer copies, comm.cuh)
+//   into place, so every rank ends with the complete factor: the solves and the row-sharded dq/dr sweeps that
+//   follow read all of L and need no further exchange.
+// Why 1 x R and not P x Q: on NVSwitch a broadcast costs the same for 2 or 8 receivers, and a 2-D grid puts
+// three collectives (diagonal block down the column, panel along the row, transposed panel down the columns)
+// on the per-panel critical path where this layout has one; at N = 16k..32k on 8 GPUs that path, not the
+// broadcast volume, bounds the factorisation (DESIGN.md "Multi-GPU").
+// Per rank, three streams:
+//   P (high priority) the critical path: for the owner, sub-panel factorisation (leaf + row solve) and the update
+//                     of the rest of its group; for the owner of the NEXT group, the update of that group with
+//                     every sub-panel as it arrives (so only the last sub-panel's update trails the broadcast)
+//   C (communication) one grouped broadcast per sub-panel (panel + its inverted diagonal blocks)
+//   U (bulk)          per completed group ONE rank-DB update of all later owned groups (strided-tile GEMM), the
+//                     first of them -- the next one this rank will have to factor -- as its own launch
+// ------------------------------------------------------------------------------------------------
+__global__ void info_to_slot_kernel(const int* __restrict__ info, int rank, int nranks, double* __restrict__ slots) {
+   for (int r = 0; r < nranks; ++r) slots[r] = (r == rank) ? (double)*info : 0.0;
 }
-
 // smallest nonzero entry of the ranks' pivot reports
-__global__ void info_combine_kernel(const int* __restrict__ xinfo, int nranks, int* __restrict__ info) {
+__global__ void info_combine_kernel(const double* __restrict__ slots, int nranks, int* __restrict__ info) {
    int v = 0;
-   for (int r = 0; r < nranks; ++r)
-      if (xinfo[r] != 0 && (v == 0 || xinfo[r] < v)) v = xinfo[r];
+   for (int r = 0; r < nranks; ++r) {
+      const int x = (int)slots[r];
+      if (x != 0 && (v == 0 || x < v)) v = x;
+   }
    *info = v;
 }
 
-static int64_t dist_panel_width() {  // MCHRG_B200_DIST_PANEL: columns per block column (multiple of 128), default 256
-   static const int64_t w = std::getenv("MCHRG_B200_DIST_PANEL")
-                               ? std::max<int64_t>(TILE, atoll(std::getenv("MCHRG_B200_DIST_PANEL")) / TILE * TILE)
-                               : 2 * TILE;
-   return w;
-}
-
 // Below ~8k the serial panel chain plus one broadcast per panel outlasts what the shared trailing updates save
-// (measured on 2 B200: N = 3000 5.3 ms distributed vs 4.3 ms replicated; N = 16384 63 vs 68 ms, 4 GPUs 51.5 ms).
-static bool dist_applies(const mchrg_b200_context* ctx, int64_t n) {
-   static const int64_t nmin = std::getenv("MCHRG_B200_DIST_MIN") ? atoll(std::getenv("MCHRG_B200_DIST_MIN")) : 8192;
-   return ctx->xch.on() && n >= std::max<int64_t>(nmin, 8 * TILE) && ctx->active == ctx->stream;
+bool dist_rows_apply(const mchrg_b200_context* ctx, int64_t nat) {
+   return ctx->comm != nullptr && ctx->comm->nranks > 1 && nat >= env_ll("MCHRG_B200_DIST_MIN", 8192);
 }
-
-int64_t dpotrf_dist_panel(const mchrg_b200_context* ctx, int64_t n) { return dist_applies(ctx, n) ? dist_panel_width() : 0; }
-
-// Multi-GPU right-looking Cholesky of a REPLICATED matrix: block columns of PANEL columns are
-// owned block-cyclically (owner(b) = b % nranks).  Every rank keeps only its own block columns up to date (and
-// needs only those assembled on entry: dpotrf_dist_panel tells the assembly which ones);
-// the owner factors panel b (diagonal block + triangular solve of the rows below) and broadcasts it together
-// with its inverted diagonal blocks, so that at the end EVERY rank holds the complete factor and the solves
-// that follow stay replicated.  The broadcast of panel b+1 is started as soon as its owner has factored it
-// (the owner updates that column first) and overlaps the trailing updates with panel b on all ranks.
-static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info) {
-   const auto& x = ctx->xch;
-   const int64_t PANEL = dist_panel_width();
-   const int nblk = (int)((n + PANEL - 1) / PANEL);
-   auto c0_of = [&](int b) { return (int64_t)b * PANEL; };
-   auto pw_of = [&](int b) { return std::min<int64_t>(PANEL, n - c0_of(b)); };
-   auto owner = [&](int b) { return b % x.nranks; };
-   auto factor_panel = [&](int b) {
-      const int64_t c0 = c0_of(b), pw = pw_of(b), rem = n - c0 - pw;
-      double* D = W + c0 + c0 * ldw;
-      double* dinv_k = dinv + (c0 / TILE) * TILE * TILE;
-      potrf_rec(ctx, pw, D, ldw, dinv_k, info, c0);
-      if (rem > 0) dtrsm_right_lt(ctx, rem, pw, D, ldw, dinv_k, D + pw, ldw);
-   };
-   auto start_panel = [&](int b) {
-      const int64_t c0 = c0_of(b), pw = pw_of(b);
-      cudaEvent_t e = ctx->next_event();  // the exchange runs on the side stream, after what is queued here
-      MCHRG_CUDA(cudaEventRecord(e, ctx->active));
-      MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_aux, e, 0));
-      // block column from its diagonal element to the end of its last column (one contiguous range)
-      x.start(x.user, W + c0 + c0 * ldw, (int64_t)(((pw - 1) * ldw + (n - c0)) * sizeof(double)), owner(b), 2 * b);
-      x.start(x.user, dinv + (c0 / TILE) * TILE * TILE, (int64_t)((pw / TILE) * TILE * TILE * sizeof(double)), owner(b),
-              2 * b + 1);
-   };
-   auto wait_panel = [&](int b) {
-      x.wait(x.user, 2 * b);
-      x.wait(x.user, 2 * b + 1);
-   };
-   auto update = [&](int b, int j) {  // block column j -= L(rows of j.., panel b) L(block j, panel b)^T
-      const int64_t c0 = c0_of(b), cj = c0_of(j);
-      const double* A21 = W + cj + c0 * ldw;
-      dgemm_padded(ctx, true, n - cj, pw_of(j), pw_of(b), -1.0, A21, ldw, A21, ldw, 1.0, W + cj + cj * ldw, ldw, false);
-   };
-   if (owner(0) == x.rank) factor_panel(0);
-   start_panel(0);
-   for (int b = 0; b < nblk; ++b) {
-      wait_panel(b);
-      if (b + 1 < nblk) {
-         if (owner(b + 1) == x.rank) {
-            update(b, b + 1);
-            factor_panel(b + 1);
-         }
-         start_panel(b + 1);
-      }
-      // all other owned block columns behind the look-ahead column in one launch
-      int j0 = b + 2;
-      while (j0 < nblk && owner(j0) != x.rank) ++j0;
-      if (j0 < nblk)
-         dsyrk_cyclic(ctx, n, pw_of(b), W + c0_of(b) * ldw, W, ldw, (int)(c0_of(j0) / TILE), (int)(x.nranks * PANEL / TILE),
-                      (int)(PANEL / TILE));
-   }
-   // every rank reports the same pivot failure
-   int* xinfo = ctx->alloc_zero<int>((size_t)x.nranks);
-   MCHRG_CUDA(cudaMemcpyAsync(xinfo + x.rank, info, sizeof(int), cudaMemcpyDeviceToDevice, ctx->active));
+void row_share(const mchrg_b200_context* ctx, int nat, int* row0, int* row1) {
+   const int64_t R = ctx->nranks(), r = ctx->rank();
+   auto bound = [&](int64_t k) { return (int)std::min<int64_t>(nat, round_up((nat * k + R - 1) / R, 8)); };
+   *row0 = bound(r);
+   *row1 = (r + 1 == R) ? nat : bound(r + 1);
+}
+void comm_allreduce_sum(mchrg_b200_context* ctx, double* buf, size_t count) {
    cudaEvent_t e = ctx->next_event();
    MCHRG_CUDA(cudaEventRecord(e, ctx->active));
-   MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_aux, e, 0));
-   for (int r = 0; r < x.nranks; ++r) x.start(x.user, xinfo + r, (int64_t)sizeof(int), r, 2 * nblk + r);
-   for (int r = 0; r < x.nranks; ++r) x.wait(x.user, 2 * nblk + r);
-   MCHRG_LAUNCH(ctx, info_combine_kernel, 1, 1, 0, xinfo, x.nranks, info);
+   MCHRG_CUDA(cudaStreamWaitEvent(ctx->stream_comm, e, 0));
+   ctx->comm->allreduce_sum(buf, count, ctx->stream_comm);
+   cudaEvent_t e2 = ctx->next_event();
+   MCHRG_CUDA(cudaEventRecord(e2, ctx->stream_comm));
+   MCHRG_CUDA(cudaStreamWaitEvent(ctx->active, e2, 0));
+}
+static bool dist_applies(const mchrg_b200_context* ctx, int64_t n) {
+   return dist_rows_apply(ctx, n) && n >= 4 * TILE && ctx->active == ctx->stream;
+}
+static int64_t dist_group_width(const mchrg_b200_context* ctx, int64_t n) {
+   // MCHRG_B200_DIST_GROUP: columns per ownership group (multiple of the sub-panel width)
+   int64_t db = env_ll("MCHRG_B200_DIST_GROUP", 512) / TILE * TILE;
+   // every rank should own at least two groups
+   while (db > TILE && n / db < 2 * (int64_t)ctx->comm->nranks) db -= TILE;
+   return std::max<int64_t>(db, TILE);
+}
+static int64_t dist_sub_width(int64_t db) {
+   int64_t pw = env_ll("MCHRG_B200_DIST_PANEL", 128) / TILE * TILE;
+   pw = std::min(std::max<int64_t>(pw, TILE), db);
+   while (db % pw) pw -= TILE;
+   return pw;
 }
 
-void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info) {
+int64_t dpotrf_dist_panel(const mchrg_b200_context* ctx, int64_t n) { return dist_applies(ctx, n) ? dist_group_width(ctx, n) : 0; }
+
+static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info, int64_t aug_end) {
+   Comm* cm = ctx->comm;
+   const int R = cm->nranks, me = cm->rank;
+   const int64_t DB = dist_group_width(ctx, n), PW = dist_sub_width(DB);
+   const int ngrp = (int)((n + DB - 1) / DB);
+   cudaStream_t U = ctx->active, P = ctx->stream_hi, C = ctx->stream_comm;
+   auto g0_of = [&](int g) { return (int64_t)g * DB; };
+   auto gw_of = [&](int g) { return std::min<int64_t>(DB, n - g0_of(g)); };
+   auto owner = [&](int g) { return g % R; };
+   auto rec = [&](cudaStream_t s) {
+      cudaEvent_t e = ctx->next_event();
+      MCHRG_CUDA(cudaEventRecord(e, s));
+      return e;
+   };
+   auto wait = [&](cudaStream_t s, cudaEvent_t e) {
+      if (e) MCHRG_CUDA(cudaStreamWaitEvent(s, e, 0));
+   };
+   // everything queued on U so far (the assembly) precedes the factorisation on P and the broadcasts on C
+   cudaEvent_t e_begin = rec(U);
+   wait(P, e_begin);
+   wait(C, e_begin);
+   // first_upd[g]: event after which this rank's copy of group g carries every bulk update issued so far
+   std::vector<cudaEvent_t> bulk_done(ngrp, nullptr);
+   cudaEvent_t last_bulk = nullptr;
+   for (int g = 0; g < ngrp; ++g) {
+      const int64_t g0 = g0_of(g), gw = gw_of(g), gend = g0 + gw;
+      const bool mine = owner(g) == me;
+      const bool next_mine = g + 1 < ngrp && owner(g + 1) == me;
+      const int64_t h0 = gend, hw = (g + 1 < ngrp) ? gw_of(g + 1) : 0;  // the next group
+      // P works on this rank's copy of group g (owner) / g + 1 (next owner): the bulk updates of U come first
+      if (mine) wait(P, bulk_done[g]);
+      if (next_mine) wait(P, bulk_done[g + 1]);
+      cudaEvent_t e_last = nullptr;  // arrival of the group's last sub-panel
+      for (int64_t c0 = g0; c0 < gend; c0 += PW) {
+         const int64_t pw = std::min<int64_t>(PW, gend - c0), rem = n - c0 - pw;
+         double* D = W + c0 + c0 * ldw;
+         double* dinv_k = dinv + (c0 / TILE) * TILE * TILE;
+         if (mine) {
+            StreamScope on_p(ctx, P);
+            potrf_rec(ctx, pw, D, ldw, dinv_k, info, c0, aug_end);
+            if (rem > 0) dtrsm_right_lt(ctx, rem, pw, D, ldw, dinv_k, D + pw, ldw);
+            wait(C, rec(P));
+         }
+         // sub-panel from its diagonal element to the end of its last column (one contiguous range) + inverted blocks
+         cm->group_begin();
+         cm->bcast(D, (size_t)(((pw - 1) * ldw + (n - c0)) * sizeof(double)), owner(g), C);
+         cm->bcast(dinv_k, (size_t)((pw / TILE) * TILE * TILE * sizeof(double)), owner(g), C);
+         cm->group_end();
+         cudaEvent_t e_arr = rec(C);
+         e_last = e_arr;
+         if (rem == 0) break;
+         const double* A21 = D + pw;  // rows below the sub-panel's diagonal block
+         if (mine && c0 + pw < gend) {  // rest of the own group
+            StreamScope on_p(ctx, P);
+            dgemm_padded(ctx, true, rem, gend - c0 - pw, pw, -1.0, A21, ldw, A21, ldw, 1.0, W + (c0 + pw) + (c0 + pw) * ldw, ldw,
+                         false);
+         }
+         if (next_mine) {  // the group this rank factors next, sub-panel by sub-panel as they arrive
+            StreamScope on_p(ctx, P);
+            wait(P, e_arr);
+            const double* Ah = W + h0 + c0 * ldw;
+            dgemm_padded(ctx, true, n - h0, hw, pw, -1.0, Ah, ldw, Ah, ldw, 1.0, W + h0 + h0 * ldw, ldw, false);
+         }
+      }
+      // bulk: all owned groups behind the next one, with the whole group g at once (rank-gw update)
+      int j1 = g + 2;
+      while (j1 < ngrp && owner(j1) != me) ++j1;
+      if (j1 < ngrp) {
+         StreamScope on_u(ctx, U);
+         wait(U, e_last);
+         const double* Pg = W + g0 * ldw;  // panel of the group, global rows
+         const int64_t j0 = g0_of(j1);
+         const double* Aj = Pg + j0;
+         dgemm_padded(ctx, true, n - j0, gw_of(j1), gw, -1.0, Aj, ldw, Aj, ldw, 1.0, W + j0 + j0 * ldw, ldw, false);
+         bulk_done[j1] = rec(U);
+         if (j1 + R < ngrp) {
+            dsyrk_cyclic(ctx, n, gw, Pg, W, ldw, (int)(g0_of(j1 + R) / TILE), (int)(R * DB / TILE), (int)(DB / TILE));
+            last_bulk = rec(U);
+            for (int j = j1 + R; j < ngrp; j += R) bulk_done[j] = last_bulk;
+         }
+      }
+   }
+   (void)last_bulk;
+   // the factor is complete on this rank when the last broadcast has arrived and P has drained
+   wait(U, rec(P));
+   wait(U, rec(C));
+   // every rank reports the same pivot failure
+   double* slots = ctx->alloc<double>((size_t)R);
+   MCHRG_LAUNCH(ctx, info_to_slot_kernel, 1, 1, 0, info, me, R, slots);
+   wait(C, rec(U));
+   cm->allreduce_sum(slots, (size_t)R, C);
+   wait(U, rec(C));
+   MCHRG_LAUNCH(ctx, info_combine_kernel, 1, 1, 0, slots, R, info);
+}
+
+void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info, bool aug) {
    if (n % TILE || (ldw & 1)) fail(MCHRG_B200_ERR_ARG, "dpotrf_padded: n=%lld not a multiple of 128", (long long)n);
-   leaf_setup_once();
-   const int64_t PANEL = panel_width();
-   if (dist_applies(ctx, n)) {  // large replicated system on several GPUs
-      dpotrf_dist(ctx, n, W, ldw, dinv, info);
+   const int64_t aug_end = aug ? n : -1;
+   int64_t PANEL = env_ll("MCHRG_B200_PANEL", 256);  // tuning knob (multiple of 128); default chosen on B200 at n = 16384
+   if (PANEL < TILE || PANEL % TILE) PANEL = 256;
+   if (dist_applies(ctx, n)) {  // large system on several GPUs
+      dpotrf_dist(ctx, n, W, ldw, dinv, info, aug_end);
       return;
    }
    if (n <= 2 * PANEL) {  // small: plain recursion on the current stream
-      potrf_rec(ctx, n, W, ldw, dinv, info, 0);
+      potrf_rec(ctx, n, W, ldw, dinv, info, 0, aug_end);
       return;
    }
+   // Right-looking blocked Cholesky with one panel of look-ahead on two streams.
+   //   P (high priority): diagonal block (recursive), panel TRSM, update of the NEXT block column
+   //   U (main stream)  : the bulk trailing update (lower block triangle beyond the next block column)
+   // leaf / skinny-GEMM latency of panel k+1 is hidden behind the bulk update of panel k.
    cudaStream_t U = ctx->active, P = ctx->stream_hi;
    cudaEvent_t e0 = ctx->next_event();
    MCHRG_CUDA(cudaEventRecord(e0, U));
@@ -579,16 +657,14 @@ void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, d
    // matrix is large (fewer read-modify-write passes over it) and narrows them in the tail (shorter serial chain)
    // (default measured at n = 16384 on B200: 512-wide panels while more than 7168 columns are left, 256 down to
    //  2048, 128 in the tail: 67.4 -> 62.2 ms)
-   static const char* adapt_env = std::getenv("MCHRG_B200_PANEL_ADAPT");
-   static const bool adapt = adapt_env != nullptr || std::getenv("MCHRG_B200_PANEL") == nullptr;
-   static long thr4 = 1L << 60, thr_hi = 7168, thr_lo = 2048;
-   static bool parsed = false;
-   if (adapt_env && !parsed) {
+   const char* adapt_env = std::getenv("MCHRG_B200_PANEL_ADAPT");
+   const bool adapt = adapt_env != nullptr || std::getenv("MCHRG_B200_PANEL") == nullptr;
+   long thr4 = 1L << 60, thr_hi = 7168, thr_lo = 2048;
+   if (adapt_env) {
       long a = 0, b = 0, c = 0;
       const int got = sscanf(adapt_env, "%ld,%ld,%ld", &a, &b, &c);
       if (got == 3) { thr4 = a; thr_hi = b; thr_lo = c; }
       else if (got == 2) { thr_hi = a; thr_lo = b; }
-      parsed = true;
    }
    auto pw_at = [&](int64_t c) -> int64_t {
       const int64_t left = n - c;
@@ -604,7 +680,7 @@ void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, d
       cudaEvent_t ev_panel = ctx->next_event();
       {
          StreamScope on_p(ctx, P);
-         potrf_rec(ctx, pw, D, ldw, dinv_k, info, c0);
+         potrf_rec(ctx, pw, D, ldw, dinv_k, info, c0, aug_end);
          if (rem > 0) dtrsm_right_lt(ctx, rem, pw, D, ldw, dinv_k, D + pw, ldw);
          MCHRG_CUDA(cudaEventRecord(ev_panel, P));
       }
@@ -761,11 +837,11 @@ __global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __re
 }
 
 void dpotrs_vec(mchrg_b200_context* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv,
-                double* R, int64_t ldr, int nrhs) {
+                double* R, int64_t ldr, int nrhs, bool forward) {
    if (nrhs > MAX_RHS || n % TILE) fail(MCHRG_B200_ERR_ARG, "dpotrs_vec: bad arguments");
    const int64_t nb = n / TILE;
-   MCHRG_LAUNCH(ctx, trsv_diag_kernel, 1, 256, 0, dinv, R, ldr, nrhs, 0);
-   for (int64_t k = 0; k + 1 < nb; ++k) {  // L w = r: update the rows below block k, solve block k+1 on the way
+   if (forward) MCHRG_LAUNCH(ctx, trsv_diag_kernel, 1, 256, 0, dinv, R, ldr, nrhs, 0);
+   for (int64_t k = 0; forward && k + 1 < nb; ++k) {  // L w = r: update the rows below block k, solve block k+1 on the way
       double* rk = R + k * TILE;
       const int64_t below = n - (k + 1) * TILE;
       MCHRG_LAUNCH(ctx, trsv_fwd_fused_kernel, (unsigned)(below / TILE), 256, 0, L + (k + 1) * TILE + k * TILE * ldl, ldl, rk,

@@ -6,6 +6,7 @@
 // These kernels are FP64-ALU bound (erf/exp are polynomial sequences on the FMA pipe) until the
 // 24 N^2-byte stores dominate.
 #include "eeq.cuh"
+#include "dense.cuh"
 #include "erfgauss.cuh"
 
 namespace mchrg {
@@ -59,11 +60,12 @@ __device__ __forceinline__ double count_range2(const NcDev& p, double rc, double
 __global__ void __launch_bounds__(256) cn_rows_kernel(int nat, const double* __restrict__ xyz,
                                                       const double* __restrict__ rcov, const double* __restrict__ en,
                                                       NcDev p, int ntr, const double* __restrict__ trans,
-                                                      double* __restrict__ cn_raw, const double2* __restrict__ etab) {
+                                                      double* __restrict__ cn_raw, const double2* __restrict__ etab,
+                                                      int row0, int row1) {
    MCHRG_LOAD_ERF_TABLE(etab);
-   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   const int i = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    const int lane = threadIdx.x & 31;
-   if (i >= nat) return;
+   if (i >= row1) return;
    const double xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2];
    const double rci = rcov[i];
    const double eni = p.use_en ? en[i] : 0.0;
@@ -165,7 +167,18 @@ void ncoord_device(mchrg_b200_context* ctx, const DevMol& mol, const double* rco
    if (cn_raw_out) *cn_raw_out = cn_raw;
    const int rows_per_cta = 8;
    const unsigned grid = (nat + rows_per_cta - 1) / rows_per_cta;
-   MCHRG_LAUNCH(ctx, cn_rows_kernel, grid, 256, 0, nat, mol.xyz, rcov_a, en_a, p, ntr, trans, cn_raw, ctx->erf_tab);
+   // one large system on several GPUs: every rank counts its share of the rows, one all-reduce joins them
+   // (every entry has exactly one non-zero contribution, so the sum is exact and identical on all ranks)
+   int row0 = 0, row1 = nat;
+   const bool shard = dist_rows_apply(ctx, nat) && ctx->active == ctx->stream;
+   if (shard) {
+      row_share(ctx, nat, &row0, &row1);
+      MCHRG_CUDA(cudaMemsetAsync(cn_raw, 0, (size_t)nat * sizeof(double), ctx->active));
+   }
+   if (row1 > row0)
+      MCHRG_LAUNCH(ctx, cn_rows_kernel, (unsigned)((row1 - row0 + rows_per_cta - 1) / rows_per_cta), 256, 0, nat, mol.xyz, rcov_a,
+                   en_a, p, ntr, trans, cn_raw, ctx->erf_tab, row0, row1);
+   if (shard) comm_allreduce_sum(ctx, cn_raw, (size_t)nat);
    if (dcndr && dcndL)
       MCHRG_LAUNCH(ctx, cn_derivs_kernel, grid, 256, 0, nat, mol.xyz, rcov_a, en_a, p, ntr, trans, cn_raw, dcndr, dcndL,
                    ctx->erf_tab);
@@ -198,14 +211,14 @@ __global__ void __launch_bounds__(256) cn_grad_rows_kernel(int nat, const double
                                                            const double* __restrict__ trans,
                                                            const double* __restrict__ wf, int jb, int je,
                                                            double* __restrict__ gradx, double* __restrict__ sig_cn,
-                                                           const double2* __restrict__ etab) {
+                                                           const double2* __restrict__ etab, int row0, int row1) {
    MCHRG_LOAD_ERF_TABLE(etab);
    __shared__ double sred[8][9];
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-   const int j = blockIdx.x * 8 + warp;
+   const int j = row0 + blockIdx.x * 8 + warp;
    double gs[3] = {0.0, 0.0, 0.0};
    double dl[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-   if (j < nat) {
+   if (j < row1) {
       const double xj = xyz[3 * j], yj = xyz[3 * j + 1], zj = xyz[3 * j + 2];
       const double rcj = rcov[j], wj = wf[j];
       for (int k = lane; k < nat; k += 32) {
@@ -254,15 +267,17 @@ __global__ void __launch_bounds__(256) cn_grad_rows_kernel(int nat, const double
 }
 
 void cn_gradient_device(mchrg_b200_context* ctx, const DevMol& mol, const CnLazy& lz, const double* thalf, const double* q,
-                        int jb, int je, double* gradx, double* sig_cn) {
+                        int jb, int je, double* gradx, double* sig_cn, int row0, int row1) {
    const int nat = mol.nat;
    if (je < 0) je = nat;
+   if (row1 < 0) { row0 = 0; row1 = nat; }
    NcDev p{lz.par.kcn, lz.par.norm_exp, lz.par.cutoff * lz.par.cutoff, lz.par.cut, 0};
    double* wf = ctx->alloc<double>(nat);
    MCHRG_LAUNCH(ctx, cn_weight_kernel, (nat + 255) / 256, 256, 0, nat, lz.par.cut, lz.cn_raw, thalf, q, wf);
    MCHRG_CUDA(cudaMemsetAsync(sig_cn, 0, 9 * sizeof(double), ctx->active));
-   MCHRG_LAUNCH(ctx, cn_grad_rows_kernel, (unsigned)((nat + 7) / 8), 256, 0, nat, mol.xyz, lz.rcov_a, p, lz.ntr, lz.trans, wf,
-                jb, je, gradx, sig_cn, ctx->erf_tab);
+   if (row1 > row0)
+      MCHRG_LAUNCH(ctx, cn_grad_rows_kernel, (unsigned)((row1 - row0 + 7) / 8), 256, 0, nat, mol.xyz, lz.rcov_a, p, lz.ntr,
+                   lz.trans, wf, jb, je, gradx, sig_cn, ctx->erf_tab, row0, row1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -338,7 +353,7 @@ void eeq_amat_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a
    dim3 grid((unsigned)((nrow + 127) / 128), (unsigned)((nrow + 7) / 8));
    if (own_panel % 8) own_panel = 0;
    MCHRG_LAUNCH(ctx, eeq_amat0d_kernel, grid, 128, 0, mol.nat, mol.xyz, rad_a, eta_a, out, ld, border ? 1 : 0, npad,
-                ctx->erf_tab, (int)own_panel, ctx->xch.nranks, ctx->xch.rank);
+                ctx->erf_tab, (int)own_panel, ctx->nranks(), ctx->rank());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -349,11 +364,11 @@ __global__ void __launch_bounds__(256) eeq_pair_rows0d_kernel(int nat, const dou
                                                               const double* __restrict__ eta,
                                                               const double* __restrict__ q, double* __restrict__ jq,
                                                               double* __restrict__ atrace, double* __restrict__ dadL,
-                                                              const double2* __restrict__ etab) {
+                                                              const double2* __restrict__ etab, int row0, int row1) {
    MCHRG_LOAD_ERF_TABLE(etab);
-   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   const int i = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    const int lane = threadIdx.x & 31;
-   if (i >= nat) return;
+   if (i >= row1) return;
    const double xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2];
    const double ri2 = rad[i] * rad[i];
    const bool want_d = (atrace != nullptr) || (dadL != nullptr);
@@ -402,9 +417,12 @@ __global__ void __launch_bounds__(256) eeq_pair_rows0d_kernel(int nat, const dou
 }
 
 void eeq_pair_rows_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a,
-                      const double* q, double* jq, double* atrace, double* dadL) {
-   const unsigned grid = (mol.nat + 7) / 8;
-   MCHRG_LAUNCH(ctx, eeq_pair_rows0d_kernel, grid, 256, 0, mol.nat, mol.xyz, rad_a, eta_a, q, jq, atrace, dadL, ctx->erf_tab);
+                      const double* q, double* jq, double* atrace, double* dadL, int row0, int row1) {
+   if (row1 < 0) { row0 = 0; row1 = mol.nat; }
+   if (row1 <= row0) return;
+   const unsigned grid = (row1 - row0 + 7) / 8;
+   MCHRG_LAUNCH(ctx, eeq_pair_rows0d_kernel, grid, 256, 0, mol.nat, mol.xyz, rad_a, eta_a, q, jq, atrace, dadL, ctx->erf_tab,
+                row0, row1);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -26,8 +26,10 @@ struct CnLazy {
    int ntr = 0;
 };
 // gradx(3, je - jb) = sum_k thalf_k q_k dcndr(:, j, k) for the rows [jb, je);  sig_cn(3, 3) = sum_k thalf_k q_k dcndL(:, :, k)
+// [row0, row1) (row1 < 0: all): the atoms this call evaluates -- one large system on several GPUs: every rank takes a
+// share, writes its rows of the (then full-length, zeroed) gradx and its partial sig_cn, and one all-reduce joins them.
 void cn_gradient_device(mchrg_b200_context* ctx, const DevMol& mol, const CnLazy& lz, const double* thalf, const double* q,
-                        int jb, int je, double* gradx, double* sig_cn);
+                        int jb, int je, double* gradx, double* sig_cn, int row0 = 0, int row1 = -1);
 
 // ---- EEQ2019 -----------------------------------------------------------------------------------
 // get_xvec (eeq.f90:127-150): xvec[nat+1]; thalf[nat] (optional) = 0.5 * kcnchi / sqrt(cn + reg),
@@ -45,8 +47,9 @@ void eeq_amat_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a
 
 // One pass over all pairs of row i (0-D): jq[i] = (J q)_i, atrace[3*nat] (eeq.f90:410-411),
 // dadL[9*nat] (eeq.f90:414-415).  Any output may be nullptr.
+// [row0, row1) (row1 < 0: all): rows evaluated by this call (row shards of one large system, see above).
 void eeq_pair_rows_0d(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a,
-                      const double* q, double* jq, double* atrace, double* dadL);
+                      const double* q, double* jq, double* atrace, double* dadL, int row0 = 0, int row1 = -1);
 
 // B(3j+c, k) = dadr(c,j,k) [+ atrace on the diagonal] - thalf_k * dcndr(c,j,k)   (type.F90:270-287)
 // written with leading dimension ldb; optionally accumulates

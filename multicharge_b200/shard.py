@@ -50,46 +50,58 @@ def scatter_results(nmol_total, offsets_total, idx, shard_offsets, shard_out, ou
     return out
 
 
-def block_cyclic_cholesky_host(w, n, panel, exchange):
-    """Host (numpy) mirror of the multi-GPU factorisation schedule in csrc/dense.cu (dpotrf_dist): the matrix is
-    replicated, block column b is owned by rank b % world, the owner factors panel b and the exchange broadcasts
-    it; the broadcast of panel b+1 is started before the remaining trailing updates with panel b.  `w` is the flat
-    column-major n x n matrix (lower triangle referenced), factored in place on every rank.  The device code makes
-    exactly this sequence of exchange.start / exchange.wait calls (plus one more slot per panel for the inverted
-    diagonal blocks); tests/test_exchange_gloo.py runs it over gloo with two ranks."""
-    import numpy as np
-    rank, world = exchange.rank, exchange.world
+def row_bounds(nat, world, multiple=128):
+    """Contiguous atom blocks of the row-sharded dq/dr solve (mchrg_b200_singlepoint_rows): world + 1 bounds,
+    interior ones rounded down to a multiple of `multiple` (whole GEMM tiles per rank)."""
+    b = np.linspace(0, nat, world + 1).astype(np.int64)
+    b = (b // multiple) * multiple
+    b[0], b[-1] = 0, nat
+    return b
+
+
+def group_width(n, world, group=512, tile=128):
+    """Width of the column groups of the multi-GPU factorisation (dist_group_width in csrc/dense.cu): `group`
+    columns, narrowed until every rank owns at least two groups."""
+    db = group // tile * tile
+    while db > tile and n // db < 2 * world:
+        db -= tile
+    return max(db, tile)
+
+
+def block_cyclic_cholesky_host(w, n, group, sub, rank, world, bcast):
+    """Host (numpy) mirror of the multi-GPU factorisation schedule in csrc/dense.cu (dpotrf_dist).
+
+    Column group g = columns [g*group, (g+1)*group) is owned by rank g % world and factored in sub-panels of
+    `sub` columns.  On entry a rank needs only the groups it owns (`w` may hold anything else elsewhere); the owner
+    factors a sub-panel and `bcast(view, root)` sends it -- one contiguous range of the column-major storage, from
+    the diagonal element to the end of the sub-panel's last column -- to every rank, in place.  The owner then
+    updates the rest of its group, the owner of the NEXT group updates that group sub-panel by sub-panel, and once
+    a group is complete every rank applies it to all later groups it owns (one rank-`group` update).  Every rank
+    ends with the complete factor.  `w` is the flat column-major n x n matrix (lower triangle referenced), factored
+    in place.  tests/test_dist_gloo.py runs this over gloo with two and three ranks."""
     a = w.reshape(n, n).T  # a[i, j] view of the column-major storage
-    nblk = (n + panel - 1) // panel
-    c0 = lambda b: b * panel  # noqa: E731
-    pw = lambda b: min(panel, n - c0(b))  # noqa: E731
-
-    def factor_panel(b):
-        s, e = c0(b), c0(b) + pw(b)
-        a[s:e, s:e] = np.linalg.cholesky(a[s:e, s:e])
-        if e < n:
-            a[e:, s:e] = np.linalg.solve(a[s:e, s:e], a[e:, s:e].T).T  # X L^T = B
-
-    def start_panel(b):
-        s = c0(b)
-        lo, hi = s + s * n, (s + pw(b) - 1) * n + n  # diagonal element .. end of the last column: contiguous
-        exchange.start(w[lo:hi], (hi - lo) * 8, b % world, b)
-
-    def update(b, j):
-        s, e, sj, ej = c0(b), c0(b) + pw(b), c0(j), c0(j) + pw(j)
-        a[sj:, sj:ej] -= a[sj:, s:e] @ a[sj:ej, s:e].T
-
-    if rank == 0 % world:
-        factor_panel(0)
-    start_panel(0)
-    for b in range(nblk):
-        exchange.wait(b)
-        if b + 1 < nblk:
-            if (b + 1) % world == rank:
-                update(b, b + 1)
-                factor_panel(b + 1)
-            start_panel(b + 1)
-        for j in range(b + 2, nblk):
+    ngrp = (n + group - 1) // group
+    nbcast = 0
+    for g in range(ngrp):
+        g0, gend = g * group, min(n, (g + 1) * group)
+        mine = g % world == rank
+        next_mine = g + 1 < ngrp and (g + 1) % world == rank
+        h0, hend = gend, min(n, gend + group)
+        for c0 in range(g0, gend, sub):
+            c1 = min(gend, c0 + sub)
+            if mine:
+                a[c0:c1, c0:c1] = np.linalg.cholesky(np.tril(a[c0:c1, c0:c1]) + np.tril(a[c0:c1, c0:c1], -1).T)
+                if c1 < n:
+                    a[c1:, c0:c1] = np.linalg.solve(a[c0:c1, c0:c1], a[c1:, c0:c1].T).T  # X L^T = B
+            lo, hi = c0 + c0 * n, (c1 - 1) * n + n  # diagonal element .. end of the last column: contiguous
+            bcast(w[lo:hi], g % world)
+            nbcast += 1
+            if mine and c1 < gend:
+                a[c1:, c1:gend] -= a[c1:, c0:c1] @ a[c1:gend, c0:c1].T
+            if next_mine:
+                a[h0:, h0:hend] -= a[h0:, c0:c1] @ a[h0:hend, c0:c1].T
+        for j in range(g + 2, ngrp):
             if j % world == rank:
-                update(b, j)
-    return w
+                j0, jend = j * group, min(n, (j + 1) * group)
+                a[j0:, j0:jend] -= a[j0:, g0:gend] @ a[j0:jend, g0:gend].T
+    return nbcast

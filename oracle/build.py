@@ -29,13 +29,13 @@ def find_openblas():
 
 def build(force=False, verbose=False):
     srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
-    deps = srcs + [os.path.join(HERE, "mchrg_oracle.h"), os.path.abspath(__file__)]
+    deps = srcs + [os.path.join(HERE, "mchrg_oracle.h"), os.path.join(HERE, "param_tables_oracle.inc"),
+                   os.path.abspath(__file__)]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     blas = find_openblas()
     cmd = ["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-std=c11", "-fno-fast-math", "-ffp-contract=off",
            "-Wall", "-Wextra", "-Wno-unused-parameter",
-           "-I", os.path.join(ROOT, "multicharge_b200", "csrc"),
            "-o", OUT] + srcs + [blas, "-Wl,-rpath," + os.path.dirname(blas), "-lm"]
     if verbose:
         print(" ".join(cmd))

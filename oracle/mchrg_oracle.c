@@ -845,7 +845,7 @@ int orc_eeq_singlepoint(const orc_eeq_model* m, const orc_mol* mol, double* cn_o
 }
 
 /* ================= element tables (param/eeq2019.f90, param/eeqbc2025.f90, mctc_data) ================= */
-#include "param_tables.inc"
+#include "param_tables_oracle.inc" /* the oracle's own tables (oracle/gen_tables.py), not the product's */
 
 #define ORC_AATOAU (1.0 / 0.529177210903)
 
@@ -853,26 +853,26 @@ int orc_eeq_singlepoint(const orc_eeq_model* m, const orc_mol* mol, double* cn_o
  * returns -1 for an unknown element like the reference getters. */
 int orc_param_eeq2019(int z, double* out) {
    if (z < 1 || z > 103) { for (int k = 0; k < 5; ++k) out[k] = -1.0; return -1; }
-   out[0] = mchrg_eeq_chi[z - 1];
-   out[1] = mchrg_eeq_eta[z - 1];
-   out[2] = mchrg_eeq_kcnchi[z - 1];
-   out[3] = mchrg_eeq_rad[z - 1];
-   out[4] = mchrg_pa2009_covrad_aa[z - 1] * ORC_AATOAU * 4.0 / 3.0;
+   out[0] = orc_eeq_chi[z - 1];
+   out[1] = orc_eeq_eta[z - 1];
+   out[2] = orc_eeq_kcnchi[z - 1];
+   out[3] = orc_eeq_rad[z - 1];
+   out[4] = orc_d3_rcov_angstrom[z - 1] * ORC_AATOAU * 4.0 / 3.0;
    return 0;
 }
 
 /* out = {chi, eta, rad, kcnchi, kqchi, kqeta, cap, cov_radii, avg_cn} (param/eeqbc2025.f90) */
 int orc_param_eeqbc2025(int z, double* out) {
    if (z < 1 || z > 103) { for (int k = 0; k < 9; ++k) out[k] = -1.0; return -1; }
-   out[0] = mchrg_eeqbc_chi[z - 1];
-   out[1] = mchrg_eeqbc_eta[z - 1];
-   out[2] = mchrg_eeqbc_rad[z - 1];
-   out[3] = mchrg_eeqbc_kcnchi[z - 1];
-   out[4] = mchrg_eeqbc_kqchi[z - 1];
-   out[5] = mchrg_eeqbc_kqeta[z - 1];
-   out[6] = mchrg_eeqbc_cap[z - 1];
-   out[7] = mchrg_eeqbc_cov_radii[z - 1];
-   out[8] = mchrg_eeqbc_avg_cn[z - 1];
+   out[0] = orc_eeqbc_chi[z - 1];
+   out[1] = orc_eeqbc_eta[z - 1];
+   out[2] = orc_eeqbc_rad[z - 1];
+   out[3] = orc_eeqbc_kcnchi[z - 1];
+   out[4] = orc_eeqbc_kqchi[z - 1];
+   out[5] = orc_eeqbc_kqeta[z - 1];
+   out[6] = orc_eeqbc_cap[z - 1];
+   out[7] = orc_eeqbc_cov_radii[z - 1];
+   out[8] = orc_eeqbc_avg_cn[z - 1];
    return 0;
 }
 

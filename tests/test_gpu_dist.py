@@ -1,0 +1,207 @@
+"""The multi-GPU single-system code on ONE GPU: R contexts driven by R host threads and tied together by the
+library's local communicator (mchrg_b200_comm_init_local -- the same schedule, kernels and stream choreography as
+the NCCL backend, with stream-ordered copies standing in for the NVLink transfers).
+
+  * collectives (broadcast / all-reduce / all-gather) against numpy;
+  * block-cyclic Cholesky (dpotrf_dist) against numpy/LAPACK, every rank starting with ONLY its own column groups;
+  * the whole single point (q, E, gradient, sigma; dq/dr rows) with the row-sharded O(N^2) passes against the
+    one-context result and the CPU oracle (tolerance 1e-10, BASELINE.json);
+  * two contexts used from two threads without a communicator (per-context kernel attributes, re-entrancy).
+"""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def fort(a):
+    return np.ascontiguousarray(a.T)
+
+
+def run_ranks(world, body):
+    """body(rank) on `world` threads; re-raises the first exception."""
+    err = [None] * world
+    out = [None] * world
+
+    def run(r):
+        try:
+            out[r] = body(r)
+        except BaseException as exc:  # noqa: BLE001
+            err[r] = exc
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+@pytest.fixture()
+def dist_env(monkeypatch):
+    """Lower the size threshold of the distributed route so that small systems take it (knobs are read per call)."""
+    monkeypatch.setenv("MCHRG_B200_DIST_MIN", "512")
+    yield
+
+
+@pytest.fixture(params=[2, 3])
+def group(request, mc):
+    ctxs = [mc.Context(0) for _ in range(request.param)]
+    mc.Context.comm_init_local(ctxs)
+    yield ctxs
+    for c in ctxs:
+        c.comm_destroy()
+        c.close()
+
+
+def test_local_collectives(mc, group):
+    import torch
+    world = len(group)
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((world, 1000))
+
+    def body(r):
+        ctx = group[r]
+        assert ctx.comm_rank == r and ctx.comm_size == world
+        t = torch.tensor(base[r], device=dev)
+        ctx.comm_bcast(t, world - 1)
+        b = t.cpu().numpy().copy()
+        t = torch.tensor(base[r], device=dev)
+        ctx.comm_allreduce_sum(t)
+        s = t.cpu().numpy().copy()
+        send = torch.tensor(base[r], device=dev)
+        recv = torch.empty(world, 1000, dtype=torch.float64, device=dev)
+        ctx.comm_allgather(send, recv)
+        return b, s, recv.cpu().numpy()
+
+    for b, s, g in run_ranks(world, body):
+        assert np.array_equal(b, base[world - 1])
+        assert np.abs(s - base.sum(axis=0)).max() < 1e-14
+        assert np.array_equal(g, base)
+
+
+@pytest.mark.parametrize("n", [1024, 1500, 2176])
+def test_block_cyclic_cholesky_vs_lapack(mc, group, dist_env, n, monkeypatch):
+    world = len(group)
+    monkeypatch.setenv("MCHRG_B200_DIST_GROUP", "256")
+    rng = np.random.default_rng(n)
+    M = rng.standard_normal((n, n))
+    S = M @ M.T + n * np.eye(n)
+    Lref = np.linalg.cholesky(S)
+    from multicharge_b200.shard import group_width
+    npad = -(-n // 128) * 128
+    gw = group_width(npad, world, 256)
+
+    def body(r):
+        a = S.copy()
+        for g in range(-(-npad // gw)):  # a rank may only read its own column groups
+            if g % world != r:
+                a[:, g * gw:(g + 1) * gw] = np.nan
+        buf = fort(a)
+        info = group[r].dpotrf(buf)
+        return info, np.tril(buf.T)
+
+    for info, L in run_ranks(world, body):
+        assert info == 0
+        assert np.abs(L - Lref).max() < 1e-12 * np.abs(Lref).max()
+
+
+def test_block_cyclic_cholesky_reports_pivot_on_every_rank(mc, group, dist_env):
+    n = 1024
+    S = np.eye(n) * 2.0
+    S[700, 700] = -1.0
+
+    def body(r):
+        return group[r].dpotrf(fort(S.copy()))
+
+    assert run_ranks(len(group), body) == [701] * len(group)
+
+
+@pytest.mark.parametrize("nat", [1100, 1536])
+def test_sharded_singlepoint_vs_oracle(mc, oracle, group, dist_env, nat):
+    """q + E + gradient + sigma with the distributed factorisation and the row-sharded pair / CN passes; then dq/dr
+    by row blocks (one block per rank), against the one-context result and the oracle."""
+    from synth import cluster
+    from multicharge_b200.shard import row_bounds
+    world = len(group)
+    num, xyz = cluster(nat, 70 + nat)
+    mol = mc.Structure(num, xyz, -1.0)
+    single = mc.new_eeq2019_model(mol).singlepoint(mol, want=("qvec", "energy", "gradient", "dqdr"))
+    bounds = row_bounds(nat, world)
+
+    def body(r):
+        model = mc.new_eeq2019_model(mol, group[r])
+        a = mc.singlepoint_rows(model, mol, 0, nat, dqdr=False)
+        b = mc.singlepoint_rows(model, mol, int(bounds[r]), int(bounds[r + 1]))
+        return a, b
+
+    res = run_ranks(world, body)
+    omol = oracle.Mol(num, xyz, -1.0)
+    o = oracle.eeq_singlepoint(oracle.new_eeq2019_model(omol), omol, want=("qvec", "energy", "gradient", "dqdr"))
+    grad = np.zeros((nat, 3))
+    dqdr = np.zeros((nat, nat, 3))
+    for r, (a, b) in enumerate(res):
+        for key in ("cn", "qvec", "energy", "gradient", "sigma"):
+            scale = max(1.0, np.abs(o[key]).max())
+            assert np.abs(a[key] - o[key]).max() < 1e-10 * scale, (r, key)
+            assert np.abs(a[key] - single[key]).max() < 1e-11 * scale, (r, key)
+        jb, je = int(bounds[r]), int(bounds[r + 1])
+        grad[jb:je] = b["gradient"]
+        dqdr[:, jb:je, :] = b["dqdr"]
+        assert np.abs(b["dqdL"] - o["dqdL"]).max() < 1e-10 * max(1.0, np.abs(o["dqdL"]).max())
+    assert np.abs(grad - o["gradient"]).max() < 1e-10 * max(1.0, np.abs(o["gradient"]).max())
+    assert np.abs(dqdr - o["dqdr"]).max() < 1e-10 * max(1.0, np.abs(o["dqdr"]).max())
+
+
+def test_two_contexts_two_threads(mc, oracle):
+    """A second context in the same process (what a Fortran caller driving several GPUs with OpenMP threads does):
+    shared-memory attributes and launch state are per context, the calls are re-entrant."""
+    from synth import batch, cluster
+    ctxs = [mc.Context(0), mc.Context(0)]
+    num, xyz = cluster(700, 9)
+    mol = mc.Structure(num, xyz, 0.0)
+    offsets, bnum, bxyz, charge = batch(300, 5, 20, 150)
+    ref_b = oracle.eeq2019_singlepoint_batch(offsets, bnum, bxyz, charge)
+    omol = oracle.Mol(num, xyz, 0.0)
+    ref_c = oracle.eeq_singlepoint(oracle.new_eeq2019_model(omol), omol, want=("qvec", "energy", "gradient"))
+
+    def body(r):
+        ctx = ctxs[r]
+        outs = []
+        for _ in range(3):
+            c = mc.new_eeq2019_model(mol, ctx).singlepoint(mol, want=("qvec", "energy", "gradient"))
+            b = mc.singlepoint_batch(mc.new_eeq2019_batch_model(ctx), offsets, bnum, bxyz, charge)
+            outs.append((c, b))
+        return outs
+
+    for outs in run_ranks(2, body):
+        for c, b in outs:
+            for key in ("qvec", "energy", "gradient"):
+                assert np.abs(c[key] - ref_c[key]).max() < 1e-10 * max(1.0, np.abs(ref_c[key]).max())
+                assert np.abs(b[key] - ref_b[key]).max() < 1e-10 * max(1.0, np.abs(ref_b[key]).max())
+            assert int((b["status"] != 0).sum()) == 0
+    for c in ctxs:
+        c.close()
+
+
+def test_env_knobs_are_read_per_call(mc, monkeypatch):
+    """Tuning knobs must take effect between calls of one process (no process-wide caching)."""
+    ctx = mc.default_context(0)
+    n = 1024
+    rng = np.random.default_rng(1)
+    M = rng.standard_normal((n, n))
+    S = M @ M.T + n * np.eye(n)
+    counts = []
+    for panel in ("128", "512"):
+        monkeypatch.setenv("MCHRG_B200_PANEL", panel)
+        l0 = ctx.launch_count
+        assert ctx.dpotrf(fort(S)) == 0
+        counts.append(ctx.launch_count - l0)
+    assert counts[0] != counts[1]

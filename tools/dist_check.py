@@ -1,7 +1,8 @@
 """Multi-GPU factorisation check (run under torchrun, one rank per GPU):
    torchrun --nproc-per-node N tools/dist_check.py [nat]
 Every rank solves the same cluster twice -- replicated single-GPU factorisation, then the block-cyclic
-factorisation with NCCL panel broadcasts (mchrg_b200_set_exchange) -- and compares q, E, gradient; then times both."""
+factorisation and row-sharded passes over the library's native NCCL communicator (mchrg_b200_comm_init_nccl) --
+and compares q, E, gradient; then times both."""
 import os
 import sys
 import time
@@ -39,8 +40,7 @@ def main():
         return out
 
     ref = run()
-    xch = mc.PanelExchange(ctx)
-    ctx.set_exchange(xch)
+    mc.init_comm_from_torch(ctx)
     got = run()
     err = {k: float((got[k] - ref[k]).abs().max() / ref[k].abs().max()) for k in ("qvec", "energy", "gradient")}
     worst = torch.tensor([max(err.values())], **f64)
@@ -69,13 +69,13 @@ def main():
         dist.broadcast(buf, src=b % world)
     torch.cuda.synchronize()
     t_bc = time.perf_counter() - t0
-    ctx.set_exchange(None)
+    ctx.comm_destroy()
     t_rep = timed()
     if rank == 0:
         print(f"64 broadcasts of 33.5 MB: {1e3 * t_bc:.1f} ms ({64 * buf.numel() * 8 / t_bc / 1e9:.0f} GB/s)")
     if rank == 0:
         print(f"nat {nat} world {world}: rel err vs replicated {err}  worst over ranks {float(worst):.2e}  "
-              f"rank-to-rank |dq| {same:.1e}  exchanges {xch.started} ({xch.bytes_moved / 1e9:.2f} GB)")
+              f"rank-to-rank |dq| {same:.1e}")
         print(f"q+E+gradient: distributed factorisation {1e3 * t_dist:.1f} ms, replicated {1e3 * t_rep:.1f} ms")
     dist.barrier()
     dist.destroy_process_group()

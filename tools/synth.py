@@ -66,3 +66,14 @@ def batch(nmol, seed, nmin=30, nmax=200):
     xyz += rng.uniform(-JITTER, JITTER, size=xyz.shape)
     charge = rng.integers(-1, 2, size=nmol).astype(np.float64)
     return offsets, num, xyz, charge
+
+
+def synthetic_vdw_en(num):
+    """Deterministic stand-ins for the mctc-lib tables that are not available offline (pairwise D3 vdW radii
+    x autoaa, Pauling EN / 3.98), per species: NOT the reference's numbers, only fixed inputs (SURVEY.md 8d,
+    "rvdw from per-species table (synthetic but fixed)").  Same formula as the oracle's helper of that name."""
+    z = np.asarray(num, dtype=np.float64)
+    r = 1.1 + 0.35 * np.log1p(z)
+    rvdw = 0.5 * (r[:, None] + r[None, :]) * 0.529177210903 * 3.2
+    en = (0.8 + 2.6 * np.exp(-((z % 8) - 6.5) ** 2 / 18.0)) / 3.98
+    return np.ascontiguousarray(rvdw), en
