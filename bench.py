@@ -388,31 +388,43 @@ def periodic_block(torch, mc, ctx, ext, dev, fp64_peak):
 
 def eeqbc_block(torch, mc, ctx, ext, dev, rank, world, nat, fp64_peak, dq):
     """configs[4]: EEQ-BC 2025 on a synthetic cluster (vdW radii / EN from the fixed synthetic species tables of
-    tools/synth.py: the mctc-lib tables are not available offline)."""
+    tools/synth.py: the mctc-lib tables are not available offline).  q+E+gradient on every rank (distributed
+    factorisation, row-sharded O(N^2) passes when world > 1); with dq: + dq/dr, rows sharded over the ranks."""
     from synth import cluster, synthetic_vdw_en
+    from multicharge_b200.shard import row_bounds
     num, xyz = cluster(nat, 20250105)
     mol = mc.Structure(num, xyz, 0.0)
     rvdw, en = synthetic_vdw_en(mol.num)
     model = mc.new_eeqbc2025_model(mol, rvdw, en * 3.98, ctx)
+    txyz, tid = torch.tensor(mol.xyz, device=dev), torch.tensor(mol.id, device=dev)
+    f64 = dict(dtype=torch.float64, device=dev)
     res = {"nat": nat, "n_gpus": world}
-    run = _singlepoint_device(torch, mc, model, mol, dev, False)
-    res["q_e_grad_seconds"] = _timed(torch, ext, run, 1, world, dev)
-    del run
-    torch.cuda.empty_cache()
     n = float(nat)
-    res["roofline_q_e_grad"] = {"bound": "tensor", "kernel": "dpotrf (DMMA) + bc_* pair kernels (FP64 ALU)",
-                                "achieved": n ** 3 / 3.0 / res["q_e_grad_seconds"] / 1e12 / world, "peak": fp64_peak,
-                                "unit": "TFLOP/s per GPU (Cholesky flops only)",
-                                "frac": n ** 3 / 3.0 / res["q_e_grad_seconds"] / 1e12 / world / fp64_peak, "traffic": None}
-    if dq:
-        run = _singlepoint_device(torch, mc, model, mol, dev, True)
-        res["q_e_grad_dqdr_seconds"] = _timed(torch, ext, run, 1, world, dev)
-        fl = n ** 3 / 3.0 + 12.0 * n ** 3  # Cholesky + dtmpdr C GEMM (6 n^3) + two TRSM sweeps (6 n^3)
-        res["roofline_dqdr"] = {"bound": "tensor", "kernel": "dgemm_dmma_kernel (dtmpdr C, TRSM sweeps)",
-                                "achieved": fl / res["q_e_grad_dqdr_seconds"] / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                                "frac": fl / res["q_e_grad_dqdr_seconds"] / 1e12 / fp64_peak, "traffic": None}
-        del run
-        torch.cuda.empty_cache()
+    if not dq:
+        o = mc.api.SolveResult(cn=torch.empty(nat, **f64), qvec=torch.empty(nat, **f64), energy=torch.zeros(nat, **f64),
+                               gradient=torch.empty(nat, 3, **f64), sigma=torch.zeros(3, 3, **f64))
+        res["q_e_grad_seconds"] = _timed(torch, ext, lambda: mc.singlepoint_rows(model, mol, 0, nat, out=o, xyz=txyz, id=tid),
+                                         1, world, dev)
+        res["charge_sum"] = float(o["qvec"].sum().item())
+        res["roofline_q_e_grad"] = {"bound": "tensor", "kernel": "dpotrf (DMMA) + bc_* pair kernels (FP64 ALU)",
+                                    "achieved": n ** 3 / 3.0 / res["q_e_grad_seconds"] / 1e12 / world, "peak": fp64_peak,
+                                    "unit": "TFLOP/s per GPU (Cholesky flops only)",
+                                    "frac": n ** 3 / 3.0 / res["q_e_grad_seconds"] / 1e12 / world / fp64_peak, "traffic": None}
+        return res
+    bounds = row_bounds(nat, world)
+    jb, je = int(bounds[rank]), int(bounds[rank + 1])
+    nj = je - jb
+    out = mc.api.SolveResult(cn=torch.empty(nat, **f64), qvec=torch.empty(nat, **f64), energy=torch.zeros(nat, **f64),
+                             gradient=torch.empty(nj, 3, **f64), sigma=torch.zeros(3, 3, **f64),
+                             dqdr=torch.empty(nat, nj, 3, **f64), dqdL=torch.empty(nat, 3, 3, **f64))
+    res["q_e_grad_dqdr_seconds"] = _timed(torch, ext, lambda: mc.singlepoint_rows(model, mol, jb, je, out=out, xyz=txyz, id=tid),
+                                          1, world, dev)
+    res["rows_per_rank"] = [int(x) for x in np.diff(bounds)]
+    fl = n ** 3 / 3.0 + 12.0 * n ** 3  # Cholesky + dtmpdr C GEMM (6 n^3) + two TRSM sweeps (6 n^3)
+    res["roofline_dqdr"] = {"bound": "tensor", "kernel": "dgemm_dmma_kernel (dtmpdr C, TRSM sweeps)",
+                            "achieved": fl / res["q_e_grad_dqdr_seconds"] / 1e12 / world, "peak": fp64_peak,
+                            "unit": "TFLOP/s per GPU", "frac": fl / res["q_e_grad_dqdr_seconds"] / 1e12 / world / fp64_peak,
+                            "traffic": None}
     return res
 
 
@@ -598,10 +610,11 @@ def run_ours(args):
                   ("cluster", lambda: cluster_block(torch, mc, ctx, ext, dev, rank, world, args.nat, fp64_peak))]
         if world == 1:
             blocks.append(("periodic", lambda: periodic_block(torch, mc, ctx, ext, dev, fp64_peak)))
-            blocks.append(("eeqbc", lambda: eeqbc_block(torch, mc, ctx, ext, dev, rank, world, args.nat_bc, fp64_peak, False)))
-            blocks.append(("eeqbc_dqdr", lambda: eeqbc_block(torch, mc, ctx, ext, dev, rank, world, 8192, fp64_peak, True)))
-        else:
-            blocks.append(("eeqbc", lambda: eeqbc_block(torch, mc, ctx, ext, dev, rank, world, args.nat_bc, fp64_peak, False)))
+        # configs[4]: N = 32768; the full dq/dr of that size needs the ranks' memory and flops together (25.8 GB per
+        # (3, N, N) array, 4.6e14 flop): one GPU reports it at N = 8192
+        nat_dq = args.nat_bc if world >= 2 else min(args.nat_bc, 8192)
+        blocks.append(("eeqbc", lambda: eeqbc_block(torch, mc, ctx, ext, dev, rank, world, args.nat_bc, fp64_peak, False)))
+        blocks.append(("eeqbc_dqdr", lambda: eeqbc_block(torch, mc, ctx, ext, dev, rank, world, nat_dq, fp64_peak, True)))
         for name, fn in blocks:
             # a failure on one rank would leave the others inside a collective: agree on the outcome per block
             try:

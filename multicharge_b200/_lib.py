@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmchrg_b200.so")
+# MCHRG_B200_LIB: alternative build of the same library (A/B timing of kernel variants); default: the in-tree one
+LIB_PATH = os.environ.get("MCHRG_B200_LIB") or os.path.join(_HERE, "libmchrg_b200.so")
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)

@@ -27,7 +27,19 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None, objdir=None):
+    """defines / out / objdir: variant builds for A/B timing, e.g. build(defines=["LEAF_PROF"], out=".../libx.so",
+    objdir=".../build_x"); the default build is the product."""
+    global OUT, OBJDIR
+    if out or objdir or defines:
+        saved = (OUT, OBJDIR)
+        OUT, OBJDIR = out or OUT, objdir or OBJDIR
+        NVCC_FLAGS.extend("-D" + d for d in defines)
+        try:
+            return build(force=True, verbose=verbose)
+        finally:
+            OUT, OBJDIR = saved
+            del NVCC_FLAGS[len(NVCC_FLAGS) - len(defines):]
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".inc", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "mchrg_b200.h"))
@@ -61,4 +73,10 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    tag = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--tag=")), None)
+    if tag:
+        print(build(verbose="-v" in sys.argv, defines=defs, out=os.path.join(HERE, f"libmchrg_b200_{tag}.so"),
+                    objdir=os.path.join(HERE, "build", tag)))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv))

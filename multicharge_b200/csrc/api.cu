@@ -533,14 +533,15 @@ __global__ void bc_gradient_kernel(int n3, const double* __restrict__ ga, const 
 __global__ void __launch_bounds__(288) bc_sigma_kernel(int nat, const double* __restrict__ q,
                                                        const double* __restrict__ dadL, const double* __restrict__ dxdL,
                                                        double* __restrict__ sigma, const double* __restrict__ zvec,
-                                                       double* __restrict__ B, int64_t ldb, double* __restrict__ bz) {
+                                                       double* __restrict__ B, int64_t ldb, double* __restrict__ bz,
+                                                       int64_t roff) {
    const int ab = threadIdx.x >> 5, lane = threadIdx.x & 31;
    double acc = 0.0, accz = 0.0;
    for (int k = lane; k < nat; k += 32) {
       const double da = dadL[(size_t)9 * k + ab], dx = dxdL[(size_t)9 * k + ab];
       acc += q[k] * (0.5 * da - dx);
       if (B) {
-         B[(size_t)k * ldb + 3 * (size_t)nat + ab] = da - dx;
+         B[(size_t)k * ldb + roff + ab] = da - dx;
          accz = fma(da - dx, zvec[k], accz);
       }
    }
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(288) bc_sigma_kernel(int nat, const double* __
    }
    if (lane == 0) {
       if (sigma) sigma[ab] += acc;
-      if (B) bz[3 * (size_t)nat + ab] = accz;
+      if (B) bz[roff + ab] = accz;
    }
 }
 __global__ void set_last_kernel(int nat, double v, double* __restrict__ x) { x[nat] = v; }
@@ -558,9 +559,15 @@ __global__ void set_last_kernel(int nat, double v, double* __restrict__ x) { x[n
 static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, const SolveIO& io) {
    mchrg_b200_context* ctx = model->ctx;
    if (!io.qloc) fail(MCHRG_B200_ERR_MODEL, "qloc required for eeqbc");  // error stop, eeqbc.f90:202
-   if (io.je >= 0 && (io.jb != 0 || io.je != mol.nat)) fail(MCHRG_B200_ERR_MODEL, "row blocks are not available for EEQ-BC");
    const int nat = mol.nat;
    const int64_t npad = round_up(nat, TILE);
+   const int jb = io.jb, je = io.je < 0 ? nat : io.je, nj = je - jb;
+   if (jb < 0 || je > nat || nj <= 0) fail(MCHRG_B200_ERR_ARG, "invalid row block [%d, %d)", jb, je);
+   if (mol.periodic && nj != nat) fail(MCHRG_B200_ERR_MODEL, "row blocks are not available for periodic structures");
+   // one large system on several GPUs: the O(N^2) row passes are row-sharded and joined by one all-reduce
+   const bool shard = !mol.periodic && dist_rows_apply(ctx, nat);
+   int row0 = 0, row1 = nat;
+   if (shard) row_share(ctx, nat, &row0, &row1);
    // eeqbc.f90:195 (update) needs the local-charge derivatives for every derivative output
    const bool dcn = io.dcndr && io.dcndL && io.dqlocdr && io.dqlocdL;
    const bool grad = io.gradient && io.sigma && dcn;
@@ -588,14 +595,14 @@ static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, 
    MCHRG_LAUNCH(ctx, set_last_kernel, 1, 1, 0, nat, mol.charge, xvec);
 
    double* Jc = nullptr;
-   auto assemble = [&](double* W, bool) {
+   auto assemble = [&](double* W, bool first) {
       if (mol.periodic)
          MCHRG_CUDA(cudaMemcpyAsync(W, Wpbc, (size_t)npad * npad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-      else
-         bc_amat(ctx, mol, w, W);
+      else  // several GPUs: only the column groups this rank owns in the factorisation (the shifted retries need all)
+         bc_amat(ctx, mol, w, W, first ? dpotrf_dist_panel(ctx, npad) : 0);
    };
    auto keep_copy = [&](double* W) {
-      if (io.energy) {
+      if (io.energy && mol.periodic) {  // molecular: (A q) is re-evaluated from the pair formula (bc_jq_rows)
          Jc = ctx->alloc<double>((size_t)npad * npad);
          MCHRG_CUDA(cudaMemcpyAsync(Jc, W, (size_t)npad * npad * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
       }
@@ -606,7 +613,10 @@ static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, 
       return f.info;
    }
    const double* q = f.vrhs;
-   if (io.energy) {
+   // molecular: [jq | rows (24 N) | dadL (9 N) | dxdL (9 N)] in one buffer, so that row shards are joined by ONE all-reduce
+   const size_t n1 = (size_t)nat;
+   double* pack = (!mol.periodic && (io.energy || grad || cpq)) ? ctx->alloc_zero<double>(43 * n1) : nullptr;
+   if (io.energy && mol.periodic) {
       double* jq = ctx->alloc<double>(nat);
       pbc_symv(ctx, nat, Jc, npad, q, jq);
       MCHRG_LAUNCH(ctx, energy_kernel, (nat + 255) / 256, 256, 0, nat, q, jq, xvec, io.energy);
@@ -630,30 +640,38 @@ static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, 
       bc_pbc_derivs(ctx, mol, w.atoms, model->dev_rvdw(), model->nid, model->kbc, at.kcnchi, at.kqchi, at.kqeta, q, cq, w.Cm,
                     cself, io.dcndr, io.dcndL, io.dqlocdr, io.dqlocdL, f.z(npad), pbc.work, Bm, mp, ga, gx, dadL, dxdL, bz);
       if (grad) MCHRG_LAUNCH(ctx, bc_gradient_kernel, (3 * nat + 255) / 256, 256, 0, 3 * nat, ga, gx, io.gradient);
-      MCHRG_LAUNCH(ctx, bc_sigma_kernel, 1, 288, 0, nat, q, dadL, dxdL, grad ? io.sigma : nullptr, f.z(npad), Bm, mp, bz);
+      MCHRG_LAUNCH(ctx, bc_sigma_kernel, 1, 288, 0, nat, q, dadL, dxdL, grad ? io.sigma : nullptr, f.z(npad), Bm, mp, bz,
+                   3 * (int64_t)nat);
       if (cpq) dq_tail(ctx, nat, nat, npad, mp, f, Bm, bz, io.dqdr, io.dqdL);
-   } else if (grad || cpq) {
-      double* rows = ctx->alloc<double>((size_t)24 * nat);
-      bc_rows(ctx, mol, model, w, q, io.dcndr, io.dcndL, rows);
-      double* dadL = ctx->alloc<double>((size_t)9 * nat);
-      double* dxdL = ctx->alloc<double>((size_t)9 * nat);
-      bc_strain(ctx, mol, at, w, q, rows, io.dcndL, io.dqlocdL, dadL, dxdL);
-      double* cq = ctx->alloc<double>(nat);
-      pbc_symv(ctx, nat, w.Cm, npad, q, cq);
-      double *Bm = nullptr, *bz = nullptr;
-      int64_t mp = 0;
-      if (cpq) {
-         mp = round_up(3 * (int64_t)nat + 9, TILE);
-         Bm = ctx->alloc<double>((size_t)mp * npad);
-         bz = ctx->alloc_zero<double>((size_t)mp);
-         bc_dxdr_gemm(ctx, mol, at, w, io.dcndr, io.dqlocdr, -1.0, Bm, mp);  // Bm = -dtmpdr C
+   } else if (!mol.periodic && (io.energy || grad || cpq)) {
+      double *jq = pack, *rows = pack + n1, *dadL = pack + 25 * n1, *dxdL = pack + 34 * n1;
+      if (io.energy) bc_jq_rows(ctx, mol, w, q, jq, row0, row1);
+      if (grad || cpq) {
+         bc_rows(ctx, mol, model, w, q, io.dcndr, io.dcndL, rows, row0, row1);
+         bc_strain(ctx, mol, at, w, q, rows, io.dcndL, io.dqlocdL, dadL, dxdL, row0, row1);
       }
-      double* ga = grad ? ctx->alloc_zero<double>((size_t)3 * nat) : nullptr;
-      double* gx = grad ? ctx->alloc_zero<double>((size_t)3 * nat) : nullptr;
-      bc_build_b(ctx, mol, model, at, w, q, cq, rows, io.dcndr, io.dqlocdr, 1.0, 1.0, true, Bm, mp, ga, gx, f.z(npad), bz);
-      if (grad) MCHRG_LAUNCH(ctx, bc_gradient_kernel, (3 * nat + 255) / 256, 256, 0, 3 * nat, ga, gx, io.gradient);
-      MCHRG_LAUNCH(ctx, bc_sigma_kernel, 1, 288, 0, nat, q, dadL, dxdL, grad ? io.sigma : nullptr, f.z(npad), Bm, mp, bz);
-      if (cpq) dq_tail(ctx, nat, nat, npad, mp, f, Bm, bz, io.dqdr, io.dqdL);
+      if (shard) comm_allreduce_sum(ctx, pack, (grad || cpq) ? 43 * n1 : n1);
+      if (io.energy) MCHRG_LAUNCH(ctx, energy_kernel, (nat + 255) / 256, 256, 0, nat, q, jq, xvec, io.energy);
+      if (grad || cpq) {
+         double* cq = ctx->alloc<double>(nat);
+         pbc_symv(ctx, nat, w.Cm, npad, q, cq);
+         double *Bm = nullptr, *bz = nullptr;
+         int64_t mp = 0;
+         if (cpq) {
+            mp = round_up(3 * (int64_t)nj + 9, TILE);
+            Bm = ctx->alloc<double>((size_t)mp * npad);
+            bz = ctx->alloc_zero<double>((size_t)mp);
+            bc_dxdr_gemm(ctx, mol, at, w, io.dcndr, io.dqlocdr, -1.0, Bm, mp, jb, je);  // Bm = -dtmpdr C, rows of the block
+         }
+         double* ga = grad ? ctx->alloc_zero<double>((size_t)3 * nj) : nullptr;
+         double* gx = grad ? ctx->alloc_zero<double>((size_t)3 * nj) : nullptr;
+         bc_build_b(ctx, mol, model, at, w, q, cq, rows, io.dcndr, io.dqlocdr, 1.0, 1.0, true, Bm, mp, ga, gx, f.z(npad), bz, jb,
+                    je);
+         if (grad) MCHRG_LAUNCH(ctx, bc_gradient_kernel, (3 * nj + 255) / 256, 256, 0, 3 * nj, ga, gx, io.gradient);
+         MCHRG_LAUNCH(ctx, bc_sigma_kernel, 1, 288, 0, nat, q, dadL, dxdL, grad ? io.sigma : nullptr, f.z(npad), Bm, mp, bz,
+                      3 * (int64_t)nj);
+         if (cpq) dq_tail(ctx, nat, nj, npad, mp, f, Bm, bz, io.dqdr, io.dqdL);
+      }
    }
    ctx->finish();
    return 0;

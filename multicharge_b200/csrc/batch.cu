@@ -901,6 +901,512 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
    }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split path, factorisation phase, TMA-fed variant of eeq_factor_ll_kernel (same algorithm, same scratch layout).
+//
+// What bounds the kernel above is latency: every 16 x 16 update tile walks its two row strips of L through
+// dependent 16-byte loads from L2 (~0.3 us each round), and the backward substitution does the same per block row.
+// Here a PRODUCER warp streams those strips -- contiguous runs of fragment-ordered 8 x 8 blocks -- into shared
+// memory with bulk asynchronous copies (cp.async.bulk, completion on mbarriers) one block column AHEAD of the
+// consumers, so the DMMA warps read their operands from shared memory and never wait for L2:
+//   * left-looking update of block column k0 = [old part: columns < k0 - 16, streamed] + [newest block column
+//     k0 - 16, still in shared memory: the row solves write L back into the block column buffer Cb];
+//   * chunk-major order: per chunk of 64 columns one B chunk (rows of the current block column) is shared by all
+//     row tiles, whose A chunks follow; every consumer warp keeps the accumulators of its (<= 4) row tiles in
+//     registers across the chunks;
+//   * per step ONE consumer warp (rotating) factors the diagonal tile (D) and takes no update work; the other
+//     three consume the ring (the empty barriers count three arrivals); row solves (S) use all four;
+//   * backward substitution: the strip L(blk, :k0) and the inverted diagonal tile of every step arrive through the
+//     same ring, the solving warp rotates as D does.
+// Rings: A (NA slots) and B (NB slots) of 8 KB = two block rows x 8 blocks, a 1.5 KB diagonal-tile ring.
+// A failed pivot does not stop the pipeline (the copies in flight must land); the molecule is finished with NaNs
+// and reports the pivot.
+// ------------------------------------------------------------------------------------------------
+namespace tma {
+constexpr int NCONS = 4;                        // consumer warps
+constexpr int NTHREADS = 32 * (NCONS + 1);      // + producer warp
+constexpr int CHB = 8;                          // 8 x 8 blocks per chunk and block row (64 columns)
+constexpr int SLOT = 2 * CHB * 64;              // doubles per ring slot
+constexpr int NA = 3, NB = 2, ND = 2;           // ring depths
+constexpr int DSLOT = 3 * 64;                   // diagonal tile: blocks (R,R), (R+1,R), (R+1,R+1)
+constexpr int NBAR = 2 * (NA + NB + ND);
+__host__ __device__ inline size_t smem_doubles(int npa) {
+   return (size_t)(NA + NB) * SLOT + (size_t)ND * DSLOT + (size_t)npa * KB + KB * TS + KB * KB + 2 * CBW + 2 * KB + KB +
+          2 * KB + 8 + KB * TS + NBAR + 8;
+}
+__device__ __forceinline__ unsigned sa(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sa(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sa(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sa(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+   unsigned ok = 0;
+   for (unsigned spin = 0; !ok; ++spin) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(ok) : "r"(sa(bar)), "r"(parity) : "memory");
+      if (spin > (1u << 24)) __trap();  // a broken pipeline must not hang the device
+   }
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(sa(dst)), "l"(src), "r"(bytes), "r"(sa(bar)) : "memory");
+}
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+}  // namespace tma
+
+__global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p) {
+   using namespace tma;
+   extern __shared__ __align__(128) double sm[];
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int mol = p.perm[blockIdx.x];
+   const int64_t off = p.offsets[mol];
+   const int n = (int)(p.offsets[mol + 1] - off);
+   const int npa = aug_order(n);
+   const int nblk = npa / KB;
+   const double charge = p.charge[mol];
+   double* S = p.scratch + p.soff[mol];  // fragment-order blocks, S[lay(i, j)]
+   double* ringA = sm;
+   double* ringB = ringA + NA * SLOT;
+   double* ringD = ringB + NB * SLOT;
+   double* Cb = ringD + ND * DSLOT;      // block column buffer, ABSOLUTE rows: Cb[swz(row, c)]; later b0 | b1
+   double* T = Cb + (size_t)p.np * KB;   // p.np: capacity (padded order) of this launch
+   double* Li = T + KB * TS;
+   double* cbuf = Li + KB * KB;
+   double* rbuf = cbuf + 2 * CBW;
+   double* dvec = rbuf + 2 * KB;
+   double* wl = dvec + KB;
+   double* scal = wl + 2 * KB;
+   double* T2 = scal + 8;
+   uint64_t* bars = reinterpret_cast<uint64_t*>(T2 + KB * TS);
+   uint64_t *fullA = bars, *emptyA = fullA + NA, *fullB = emptyA + NA, *emptyB = fullB + NB, *fullD = emptyB + NB,
+            *emptyD = fullD + ND;
+   __shared__ int sfail;
+   __shared__ int steps_done;  // factor steps whose row solves are complete and visible to the bulk copies
+   if (tid == 0) {
+      sfail = 0;
+      steps_done = 0;
+      for (int i = 0; i < NA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, NCONS - 1); }
+      for (int i = 0; i < NB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, NCONS - 1); }
+      for (int i = 0; i < ND; ++i) { mbar_init(fullD + i, 1); mbar_init(emptyD + i, 1); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");
+   }
+   if (warp == 0) {  // first diagonal tile: nothing to its left
+      const int r = lane & 15, h = lane >> 4;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+         const int c = 2 * k + h;
+         T[r * TS + c] = (c <= r) ? S[lay(r, c)] : 0.0;
+      }
+   }
+   __syncthreads();
+
+   // =================================== producer ===================================
+   if (warp == NCONS) {
+      if (lane != 0) return;
+      unsigned ia = 0, ib = 0, id = 0;
+      auto wait_steps = [&](int want) {
+         for (unsigned spin = 0;; ++spin) {
+            int v;
+            asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(sa(&steps_done)) : "memory");
+            if (v >= want) break;
+            if (spin > (1u << 26)) __trap();
+         }
+      };
+      // one 64-column chunk of the two block rows R, R + 1 (blocks cb0 .. of each row, as far as the row has them up
+      // to block `lim`, exclusive) into a ring slot
+      auto load_chunk = [&](double* slot, uint64_t* full, int R, int cb0, int lim0, int lim1) {
+         const int nb0 = min(CHB, lim0 - cb0), nb1 = min(CHB, lim1 - cb0);
+         const unsigned bytes = (unsigned)((max(nb0, 0) + max(nb1, 0)) * 512);
+         mbar_expect_tx(full, bytes);
+         if (nb0 > 0) bulk_load(slot, S + 64 * (tri(R) + cb0), (unsigned)(nb0 * 512), full);
+         if (nb1 > 0) bulk_load(slot + CHB * 64, S + 64 * (tri(R + 1) + cb0), (unsigned)(nb1 * 512), full);
+      };
+      for (int k0 = 2 * KB; k0 < npa; k0 += KB) {  // factor steps with an old part: columns [0, k0 - 16)
+         const int nrt = (npa - k0) / KB;
+         if (nrt <= 1) break;
+         const int kob = (k0 - KB) >> 3;  // blocks of the old part per block row
+         wait_steps((k0 >> 4) - 1);       // block column k0 - 32 is final in global memory
+         asm volatile("fence.proxy.async;" ::: "memory");
+         for (int cb0 = 0; cb0 < kob; cb0 += CHB) {
+            {
+               const unsigned slot = ib % NB, use = ib / NB;
+               if (use > 0) mbar_wait(emptyB + slot, (use - 1) & 1);
+               load_chunk(ringB + slot * SLOT, fullB + slot, k0 >> 3, cb0, kob, kob);
+               ++ib;
+            }
+            for (int ti = 1; ti < nrt; ++ti) {
+               const unsigned slot = ia % NA, use = ia / NA;
+               if (use > 0) mbar_wait(emptyA + slot, (use - 1) & 1);
+               load_chunk(ringA + slot * SLOT, fullA + slot, (k0 + KB * ti) >> 3, cb0, kob, kob);
+               ++ia;
+            }
+         }
+      }
+      // backward substitution: per step the diagonal tile (inverse) and the strip L(blk, :k0), highest columns first
+      wait_steps(nblk);
+      asm volatile("fence.proxy.async;" ::: "memory");
+      for (int k0 = npa - KB; k0 >= 0; k0 -= KB) {
+         const int R = k0 >> 3;
+         {
+            const unsigned slot = id % ND, use = id / ND;
+            if (use > 0) mbar_wait(emptyD + slot, (use - 1) & 1);
+            double* d = ringD + slot * DSLOT;
+            mbar_expect_tx(fullD + slot, 3 * 512);
+            bulk_load(d, S + 64 * (tri(R) + R), 512, fullD + slot);
+            bulk_load(d + 64, S + 64 * (tri(R + 1) + R), 1024, fullD + slot);
+            ++id;
+         }
+         for (int cb0 = ((R - 1) / CHB) * CHB; cb0 >= 0 && R > 0; cb0 -= CHB) {
+            const unsigned slot = ia % NA, use = ia / NA;
+            if (use > 0) mbar_wait(emptyA + slot, (use - 1) & 1);
+            load_chunk(ringA + slot * SLOT, fullA + slot, R, cb0, R, R);
+            ++ia;
+         }
+      }
+      return;
+   }
+
+   // =================================== consumers ===================================
+   const int g = lane >> 2, t = lane & 3;
+   unsigned ia = 0, ib = 0, id = 0;  // ring positions, in lockstep with the producer
+   for (int k0 = 0; k0 < npa; k0 += KB) {
+      const int nrt = (npa - k0) / KB;
+      const int kob = (nrt > 1 && k0 >= 2 * KB) ? (k0 - KB) >> 3 : 0;
+      const int nch = (kob + CHB - 1) / CHB;
+      const int dwarp = (blockIdx.x + (k0 >> 4)) & 3;
+      if (warp == dwarp) {
+         // ---- D: diagonal tile, Cholesky + inverse; the inverse goes to global in place of the block ----
+         const bool last = (k0 + KB == npa);
+         const int bad = diag_factor_inv(T, Li, cbuf, rbuf, dvec, lane, last ? KB - 2 : KB, last);
+         if (bad && lane == 0 && sfail == 0) sfail = k0 + bad;
+         __syncwarp();
+         const int r = lane & 15, h = lane >> 4;
+#pragma unroll
+         for (int k = 0; k < 8; ++k) {
+            const int c = 2 * k + h;
+            if (c <= r) S[lay(k0 + r, k0 + c)] = Li[swz(r, c)];
+         }
+         if (last && lane < KB) {  // forward-substituted right-hand sides of the last block
+            wl[lane] = (lane < KB - 2) ? T[(KB - 2) * TS + lane] : 0.0;
+            wl[KB + lane] = (lane < KB - 2) ? T[(KB - 1) * TS + lane] : 0.0;
+         }
+         ia += (unsigned)(nch * (nrt - 1));
+         ib += (unsigned)nch;
+      } else if (nrt > 1) {
+         // ---- U: left-looking update of the row tiles ti = 1 + idx + 3 m of this block column (and, with tile 1, of
+         //      the next diagonal tile -> T2); idx = position among the three updating warps ----
+         const int idx = (warp - dwarp - 1) & 3;
+         double acc[4][2][2][2], acc0[2][2][2];
+         // original entries first: their loads overlap the wait for the first chunk
+#pragma unroll
+         for (int m = 0; m < 4; ++m) {
+            const int ti = 1 + idx + 3 * m;
+            const int i0 = k0 + KB * ti;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+               for (int ntl = 0; ntl < 2; ++ntl) {
+                  const int row = i0 + 8 * mt + g, col = k0 + 8 * ntl + 2 * t;
+                  if (ti < nrt) {
+                     const double* src = S + lay(row, col);
+                     acc[m][mt][ntl][0] = -src[0];
+                     acc[m][mt][ntl][1] = -src[2];  // (g, c + 1) is 2 doubles on (c even); rows are below the block
+                  } else {
+                     acc[m][mt][ntl][0] = acc[m][mt][ntl][1] = 0.0;
+                  }
+               }
+         }
+         if (idx == 0) {  // next diagonal tile, rows and columns k0 + 16 ..
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+               for (int ntl = 0; ntl < 2; ++ntl) {
+                  const int row = k0 + KB + 8 * mt + g, col = k0 + KB + 8 * ntl + 2 * t;
+                  const double* src = S + lay(row, (col <= row) ? col : k0 + KB);
+                  acc0[mt][ntl][0] = (col <= row) ? -src[0] : 0.0;
+                  acc0[mt][ntl][1] = (col + 1 <= row) ? -src[2] : 0.0;
+               }
+         }
+         // old part: columns [0, k0 - 16) through the rings
+         for (int c = 0; c < nch; ++c) {
+            const int nb = min(CHB, kob - c * CHB);
+            const unsigned sb = ib % NB;
+            mbar_wait(fullB + sb, (ib / NB) & 1);
+            const double2* Bs = reinterpret_cast<const double2*>(ringB + sb * SLOT) + lane;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+#pragma unroll
+               for (int sub = 0; sub < 3; ++sub) {
+                  const int ti = 1 + 3 * m + sub;
+                  if (ti < nrt) {
+                     const unsigned sl = ia % NA;
+                     mbar_wait(fullA + sl, (ia / NA) & 1);
+                     if (sub == idx) {
+                        const double2* As = reinterpret_cast<const double2*>(ringA + sl * SLOT) + lane;
+                        for (int b = 0; b < nb; ++b) {
+                           const double2 a0 = As[32 * b], a1 = As[32 * (CHB + b)];
+                           const double2 c0 = Bs[32 * b], c1 = Bs[32 * (CHB + b)];
+                           dmma884(acc[m][0][0][0], acc[m][0][0][1], a0.x, c0.x);
+                           dmma884(acc[m][0][1][0], acc[m][0][1][1], a0.x, c1.x);
+                           dmma884(acc[m][1][0][0], acc[m][1][0][1], a1.x, c0.x);
+                           dmma884(acc[m][1][1][0], acc[m][1][1][1], a1.x, c1.x);
+                           dmma884(acc[m][0][0][0], acc[m][0][0][1], a0.y, c0.y);
+                           dmma884(acc[m][0][1][0], acc[m][0][1][1], a0.y, c1.y);
+                           dmma884(acc[m][1][0][0], acc[m][1][0][1], a1.y, c0.y);
+                           dmma884(acc[m][1][1][0], acc[m][1][1][1], a1.y, c1.y);
+                           if (m == 0 && sub == 0) {  // tile 1 with itself: the next diagonal tile
+                              dmma884(acc0[0][0][0], acc0[0][0][1], a0.x, a0.x);
+                              dmma884(acc0[0][1][0], acc0[0][1][1], a0.x, a1.x);
+                              dmma884(acc0[1][0][0], acc0[1][0][1], a1.x, a0.x);
+                              dmma884(acc0[1][1][0], acc0[1][1][1], a1.x, a1.x);
+                              dmma884(acc0[0][0][0], acc0[0][0][1], a0.y, a0.y);
+                              dmma884(acc0[0][1][0], acc0[0][1][1], a0.y, a1.y);
+                              dmma884(acc0[1][0][0], acc0[1][0][1], a1.y, a0.y);
+                              dmma884(acc0[1][1][0], acc0[1][1][1], a1.y, a1.y);
+                           }
+                        }
+                     }
+                     __syncwarp();
+                     if (lane == 0) mbar_arrive(emptyA + sl);
+                     ++ia;
+                  }
+               }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(emptyB + sb);
+            ++ib;
+         }
+         // newest part: block column k0 - 16, whose rows (L after the row solves) are still in Cb
+         if (k0 >= KB) {
+            double bn[4][2];  // rows k0 .. k0 + 15 of it: the B operand of every tile
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+               const int kc = (4 * kk + t) ^ ((g & 3) << 2);
+               bn[kk][0] = Cb[(k0 + g) * KB + kc];
+               bn[kk][1] = Cb[(k0 + 8 + g) * KB + kc];
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+               const int ti = 1 + idx + 3 * m;
+               if (ti < nrt) {
+                  const int i0 = k0 + KB * ti;
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                     const int kc = (4 * kk + t) ^ ((g & 3) << 2);
+                     const double a0 = Cb[(i0 + g) * KB + kc], a1 = Cb[(i0 + 8 + g) * KB + kc];
+                     dmma884(acc[m][0][0][0], acc[m][0][0][1], a0, bn[kk][0]);
+                     dmma884(acc[m][0][1][0], acc[m][0][1][1], a0, bn[kk][1]);
+                     dmma884(acc[m][1][0][0], acc[m][1][0][1], a1, bn[kk][0]);
+                     dmma884(acc[m][1][1][0], acc[m][1][1][1], a1, bn[kk][1]);
+                     if (m == 0 && idx == 0) {
+                        dmma884(acc0[0][0][0], acc0[0][0][1], a0, a0);
+                        dmma884(acc0[0][1][0], acc0[0][1][1], a0, a1);
+                        dmma884(acc0[1][0][0], acc0[1][0][1], a1, a0);
+                        dmma884(acc0[1][1][0], acc0[1][1][1], a1, a1);
+                     }
+                  }
+               }
+            }
+         }
+         __syncwarp();
+         // acc = L L^T - A: store the negative into Cb (own rows) / T2
+#pragma unroll
+         for (int m = 0; m < 4; ++m) {
+            const int ti = 1 + idx + 3 * m;
+            if (ti < nrt) {
+               const int i0 = k0 + KB * ti;
+#pragma unroll
+               for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                  for (int ntl = 0; ntl < 2; ++ntl)
+                     *reinterpret_cast<double2*>(Cb + swz(i0 + 8 * mt + g, 8 * ntl + 2 * t)) =
+                        make_double2(-acc[m][mt][ntl][0], -acc[m][mt][ntl][1]);
+            }
+         }
+         if (idx == 0) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+               for (int ntl = 0; ntl < 2; ++ntl) {
+                  const int lr = 8 * mt + g, lc = 8 * ntl + 2 * t;
+                  T2[lr * TS + lc] = (lc <= lr) ? -acc0[mt][ntl][0] : 0.0;
+                  T2[lr * TS + lc + 1] = (lc + 1 <= lr) ? -acc0[mt][ntl][1] : 0.0;
+               }
+         }
+      }
+      cons_sync();
+      // ---- S: rows below the diagonal tile, L(i, blk) = Cb(i, :) inv(L_kk)^T, to the scratch AND back into Cb (the
+      //      newest part of the next step); the warp of the first tile also completes the next diagonal tile ----
+      for (int ti = 1 + warp; ti < nrt; ti += NCONS) {
+         const int i0 = k0 + KB * ti;
+         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+         for (int kk = 0; kk < 4; ++kk) {
+            const int kc = (4 * kk + t) ^ ((g & 3) << 2);
+            const double a0 = Cb[(i0 + g) * KB + kc], a1 = Cb[(i0 + 8 + g) * KB + kc];
+            const double c1 = Li[(8 + g) * KB + kc];
+            if (kk < 2) {  // inv(L)(n, k) = 0 for k > n
+               const double c0 = Li[g * KB + kc];
+               dmma884(acc[0][0][0], acc[0][0][1], a0, c0);
+               dmma884(acc[1][0][0], acc[1][0][1], a1, c0);
+            }
+            dmma884(acc[0][1][0], acc[0][1][1], a0, c1);
+            dmma884(acc[1][1][0], acc[1][1][1], a1, c1);
+         }
+         __syncwarp();
+#pragma unroll
+         for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ntl = 0; ntl < 2; ++ntl) {
+               double* dst = S + lay(i0 + 8 * mt + g, k0 + 8 * ntl + 2 * t);
+               dst[0] = acc[mt][ntl][0];
+               dst[2] = acc[mt][ntl][1];
+               *reinterpret_cast<double2*>(Cb + swz(i0 + 8 * mt + g, 8 * ntl + 2 * t)) = make_double2(acc[mt][ntl][0], acc[mt][ntl][1]);
+            }
+         if (ti == 1) {
+            __syncwarp();
+            double d2[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+               const int kc = (4 * kk + t) ^ ((g & 3) << 2);
+               const double a0 = Cb[(i0 + g) * KB + kc], a1 = Cb[(i0 + 8 + g) * KB + kc];  // A(m, k) and B(k, n) = A(n, k)
+               dmma884(d2[0][0][0], d2[0][0][1], a0, a0);
+               dmma884(d2[0][1][0], d2[0][1][1], a0, a1);
+               dmma884(d2[1][0][0], d2[1][0][1], a1, a0);
+               dmma884(d2[1][1][0], d2[1][1][1], a1, a1);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+               for (int ntl = 0; ntl < 2; ++ntl) {
+                  const int lr = 8 * mt + g, lc = 8 * ntl + 2 * t;
+                  T[lr * TS + lc] = (lc <= lr) ? T2[lr * TS + lc] - d2[mt][ntl][0] : 0.0;
+                  T[lr * TS + lc + 1] = (lc + 1 <= lr) ? T2[lr * TS + lc + 1] - d2[mt][ntl][1] : 0.0;
+               }
+         }
+      }
+      // what this step wrote to the scratch must be visible to the bulk copies (async proxy) the producer issues next
+      asm volatile("fence.proxy.async;" ::: "memory");
+      cons_sync();
+      if (tid == 0) asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(sa(&steps_done)), "r"((k0 >> 4) + 1) : "memory");
+   }
+
+   // ---- backward substitution L^T [y z] = [w_x w_1], right-looking by blocks; Cb is free now: b0 | b1 ----
+   double* b0 = Cb;
+   double* b1 = Cb + npa;
+   {
+      const int kl = npa - KB;
+      for (int i = tid; i < npa; i += 32 * NCONS) {
+         b0[i] = (i < kl) ? S[lay(npa - 2, i)] : wl[i - kl];
+         b1[i] = (i < kl) ? S[lay(npa - 1, i)] : wl[KB + i - kl];
+      }
+   }
+   cons_sync();
+   for (int k0 = npa - KB; k0 >= 0; k0 -= KB) {
+      const int R = k0 >> 3;
+      const int solver = (blockIdx.x + (k0 >> 4)) & 3;
+      const int nchb = (R > 0) ? (R - 1) / CHB + 1 : 0;
+      if (warp == solver) {  // y_blk = inv(L_kk)^T w_blk ; lane = (r, rhs h); inverse tile from the diagonal ring
+         const unsigned sd = id % ND;
+         mbar_wait(fullD + sd, (id / ND) & 1);
+         const double* dt = ringD + sd * DSLOT;
+         const int r = lane & 15, h = lane >> 4;
+         const double* wv = (h ? b1 : b0) + k0;
+         double v = 0.0;
+#pragma unroll
+         for (int c = 0; c < KB; ++c)
+            if (c >= r) {  // entry (k0 + c, k0 + r): block (R,R) | (R+1,R) | (R+1,R+1)
+               const int blk = (c < 8) ? 0 : ((r < 8) ? 1 : 2);
+               v = fma(dt[64 * blk + ((((c & 7) << 2) + (r & 3)) << 1) + ((r >> 2) & 1)], wv[c], v);
+            }
+         __syncwarp();
+         (h ? b1 : b0)[k0 + r] = v;
+         __syncwarp();
+         if (lane == 0) mbar_arrive(emptyD + sd);
+      }
+      ++id;
+      cons_sync();
+      if (warp != solver) {  // w(:k0) -= L(blk, :k0)^T y_blk ; blocks of 8 columns dealt to the three warps
+         const int idx = (warp - solver - 1) & 3;
+         const int cc = lane & 7, rg = lane >> 3;  // column within the block, group of 4 rows
+         for (int c = 0; c < nchb; ++c) {
+            const int cb0 = ((R - 1) / CHB) * CHB - c * CHB;  // highest columns first
+            const int nb = min(CHB, R - cb0);
+            const unsigned sl = ia % NA;
+            mbar_wait(fullA + sl, (ia / NA) & 1);
+            const double* As = ringA + sl * SLOT;
+            for (int b = idx; b < nb; b += 3) {
+               double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+               for (int q = 0; q < 4; ++q) {
+                  const int r = 4 * rg + q;  // row within the 16
+                  const double l = As[(r >> 3) * CHB * 64 + 64 * b + ((((r & 7) << 2) + (cc & 3)) << 1) + ((cc >> 2) & 1)];
+                  s0 = fma(l, b0[k0 + r], s0);
+                  s1 = fma(l, b1[k0 + r], s1);
+               }
+               s0 += __shfl_xor_sync(0xffffffffu, s0, 8);
+               s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+               s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+               s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+               if (rg == 0) {
+                  const int j = 8 * (cb0 + b) + cc;
+                  b0[j] -= s0;
+                  b1[j] -= s1;
+               }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(emptyA + sl);
+            ++ia;
+         }
+      } else {
+         ia += (unsigned)nchb;
+      }
+      cons_sync();
+   }
+   const int bad = sfail;
+   if (bad) {
+      const double nan = __longlong_as_double(0x7ff8000000000000LL);
+      for (int i = tid; i < n; i += 32 * NCONS) {
+         p.qvec[off + i] = nan;
+         if (p.energy) p.energy[off + i] = nan;
+         if (p.gradient) p.gradient[3 * (off + i)] = p.gradient[3 * (off + i) + 1] = p.gradient[3 * (off + i) + 2] = nan;
+      }
+      if (tid == 0) {
+         p.status[mol] = bad;
+         p.lamg[mol] = nan;
+      }
+      return;
+   }
+   if (warp == 0) {
+      double sy = 0.0, sz = 0.0;
+      for (int i = lane; i < n; i += 32) { sy += b0[i]; sz += b1[i]; }
+      sy = warp_sum(sy);
+      sz = warp_sum(sz);
+      if (lane == 0) scal[0] = (sy - charge) / sz;
+   }
+   cons_sync();
+   const double lam = scal[0];
+   for (int i = tid; i < n; i += 32 * NCONS) p.qvec[off + i] = b0[i] - lam * b1[i];
+   if (tid == 0) {
+      p.status[mol] = 0;
+      p.lamg[mol] = lam;
+   }
+}
+
+static void launch_factor_tma(mchrg_b200_context* ctx, const Args& a, int count, int npa_max) {
+   const size_t smem = tma::smem_doubles(npa_max) * sizeof(double);
+   ctx->ensure_smem(eeq_factor_tma_kernel, tma::smem_doubles(NPA_MAX) * sizeof(double), /*max_carveout=*/true);
+   Args b = a;
+   b.np = npa_max;
+   MCHRG_LAUNCH(ctx, eeq_factor_tma_kernel, (unsigned)count, tma::NTHREADS, smem, b);
+}
+
 template <int NT>
 static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count, int npa_max) {
    const size_t smem = smem_doubles_ll(npa_max) * sizeof(double);
@@ -918,7 +1424,9 @@ constexpr int LL_NT = LL_NT_DEF;  // threads per molecule in the factorisation k
 static void launch_factor_groups(mchrg_b200_context* ctx, const Args& a, const int32_t* dperm,
                                  const std::vector<size_t>& cls_start, const std::vector<int>& cls_count) {
    constexpr int NCLASS = NP_MAX / KB;
-   const int group = (int)std::max<long long>(1, env_ll("MCHRG_B200_FACTOR_GROUP", 13));
+   // (the TMA-fed kernel's shared memory grows with the class: three groups keep small molecules at high residency)
+   const char* fkind = std::getenv("MCHRG_B200_FACTOR");
+   const int group = (int)std::max<long long>(1, env_ll("MCHRG_B200_FACTOR_GROUP", (fkind && fkind[0] == 'l') ? 13 : 4));
    for (int chi = NCLASS; chi >= 1; chi -= group) {  // perm holds the classes in descending order
       const int clo = std::max(1, chi - group + 1);
       int count = 0;
@@ -927,7 +1435,10 @@ static void launch_factor_groups(mchrg_b200_context* ctx, const Args& a, const i
       Args b = a;
       b.np = NPA_MAX;
       b.perm = dperm + cls_start[chi];
-      launch_factor_ll<LL_NT>(ctx, b, count, std::min(NPA_MAX, KB * (chi + 1)));
+      // MCHRG_B200_FACTOR = ll: the L2-latency-bound version above (A/B timing)
+      const char* fk = std::getenv("MCHRG_B200_FACTOR");
+      if (fk && fk[0] == 'l') launch_factor_ll<LL_NT>(ctx, b, count, std::min(NPA_MAX, KB * (chi + 1)));
+      else launch_factor_tma(ctx, b, count, std::min(NPA_MAX, KB * (chi + 1)));
    }
 }
 

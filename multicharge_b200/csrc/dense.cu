@@ -253,6 +253,71 @@ static void dsyrk_cyclic(mchrg_b200_context* ctx, int64_t n, int64_t k, const do
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small-tile DMMA product for the critical path of the distributed factorisation:
+//    C (m x 128) = alpha * A (m x k) * B^T (B: 128 x k) + beta * C ,   m multiple of 16, k multiple of 8
+// One CTA of 8 warps per 16 rows, one 16 x 16 tile per warp, fragments straight from global memory (L2): a
+// 128 x 128 x 128 product runs on 8 SMs in ~2 us, where the 128 x 128 CTA tile of dgemm_dmma_kernel takes one SM
+// ~20 us -- the two 128-wide products between consecutive leaf factorisations (row solve of the next diagonal
+// block's rows, update of the next diagonal block) are latency, not throughput.
+// C may alias A (the whole 16-row strip of A is read before anything is written).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dgemm_small128_kernel(int k, double alpha, const double* A, int64_t lda,
+                                                             const double* __restrict__ B, int64_t ldb, double beta,
+                                                             double* C, int64_t ldc) {
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   const int g = lane >> 2, t = lane & 3;
+   const int64_t m0 = (int64_t)blockIdx.x * 16;
+   const int n0 = warp * 16;
+   const double* a0p = A + m0 + g + (int64_t)t * lda;   // A(m0 + g [+ 8], kk + t)
+   const double* b0p = B + n0 + g + (int64_t)t * ldb;   // B(n0 + g [+ 8], kk + t)
+   double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll 1
+   for (int kk = 0; kk < k; kk += 32) {  // 8 k-steps of 4 per batch: 32 loads in flight per lane
+      double a[8][2], b[8][2];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+         const bool on = kk + 4 * u < k;
+         const int64_t ka = (int64_t)(kk + 4 * u) * lda, kb = (int64_t)(kk + 4 * u) * ldb;
+         a[u][0] = on ? a0p[ka] : 0.0;
+         a[u][1] = on ? a0p[ka + 8] : 0.0;
+         b[u][0] = on ? b0p[kb] : 0.0;
+         b[u][1] = on ? b0p[kb + 8] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+         dmma884(acc[0][0][0], acc[0][0][1], a[u][0], b[u][0]);
+         dmma884(acc[0][1][0], acc[0][1][1], a[u][0], b[u][1]);
+         dmma884(acc[1][0][0], acc[1][0][1], a[u][1], b[u][0]);
+         dmma884(acc[1][1][0], acc[1][1][1], a[u][1], b[u][1]);
+      }
+   }
+   double cold[2][2][2];
+#pragma unroll
+   for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+         const double* c = C + m0 + 8 * mt + g + (int64_t)(n0 + 8 * nt + 2 * t) * ldc;
+         cold[mt][nt][0] = (beta != 0.0) ? c[0] : 0.0;
+         cold[mt][nt][1] = (beta != 0.0) ? c[ldc] : 0.0;
+      }
+   __syncthreads();  // in-place products: every warp has read its strip of A
+#pragma unroll
+   for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+         double* c = C + m0 + 8 * mt + g + (int64_t)(n0 + 8 * nt + 2 * t) * ldc;
+         c[0] = alpha * acc[mt][nt][0] + beta * cold[mt][nt][0];
+         c[ldc] = alpha * acc[mt][nt][1] + beta * cold[mt][nt][1];
+      }
+}
+
+static void dgemm_small128(mchrg_b200_context* ctx, int64_t m, int64_t k, double alpha, const double* A, int64_t lda,
+                           const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
+   if (m % 16 || k % 8) fail(MCHRG_B200_ERR_ARG, "dgemm_small128: m=%lld k=%lld", (long long)m, (long long)k);
+   MCHRG_LAUNCH(ctx, dgemm_small128_kernel, (unsigned)(m / 16), 256, 0, (int)k, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Cholesky leaf: factor one 128 x 128 diagonal block and invert its factor in ONE CTA (8 warps), everything in
 // shared memory as 16 x 16 tiles (row stride 20: conflict-free FP64 mma fragment loads in both orientations).
 //   Cholesky, right-looking over 8 tile columns:
@@ -336,16 +401,39 @@ potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int g = lane >> 2, t = lane & 3;
    if (tid == 0) sfail = 0;
-   for (int e = tid; e < N * N; e += THREADS) {  // consecutive threads walk down a column: coalesced
-      const int r = e & (N - 1), c = e >> 7, R = r >> 4, C = c >> 4;
-      if (R >= C) Lt[tix(R, C) * TSZ + (r & 15) * TLD + (c & 15)] = (r >= c) ? W[r + (int64_t)c * ldw] : 0.0;
+#ifdef LEAF_PROF
+   long long tk[8];
+   tk[0] = clock64();
+#define LEAF_TICK(i) tk[i] = clock64()
+#else
+#define LEAF_TICK(i)
+#endif
+   {  // thread = (row r, column parity h): consecutive threads walk down a column (coalesced); the loads of a batch
+      // are issued back to back (32 in flight per thread) before the first one is consumed
+      const int r = tid & (N - 1), h = tid >> 7, R = r >> 4;
+#pragma unroll 1
+      for (int cb = 0; cb < N; cb += 64) {
+         double v[32];
+#pragma unroll
+         for (int u = 0; u < 32; ++u) {
+            const int c = cb + h + 2 * u;
+            v[u] = (r >= c) ? W[r + (int64_t)c * ldw] : 0.0;
+         }
+#pragma unroll
+         for (int u = 0; u < 32; ++u) {
+            const int c = cb + h + 2 * u, C = c >> 4;
+            if (R >= C) Lt[tix(R, C) * TSZ + (r & 15) * TLD + (c & 15)] = v[u];
+         }
+      }
    }
    __syncthreads();
+   LEAF_TICK(1);
    if (warp == 0) {
       const int bad = d16::diag_factor_inv<TLD, false, TLD>(Lt, Xd, cbuf, rbuf, dvec, lane, T16, true);
       if (bad && lane == 0) sfail = bad;
    }
    __syncthreads();
+   LEAF_TICK(2);
    for (int k = 0; k + 1 < NTL && !sfail; ++k) {
       const int nrem = NTL - 1 - k;
       if (warp < nrem) {  // S: one tile below the diagonal per warp, in place
@@ -385,11 +473,13 @@ potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv
       for (int e = tid; e < N * N; e += THREADS) dinv[e] = 0.0;
       return;
    }
+   LEAF_TICK(3);
    // publish L (lower triangle only)
    for (int e = tid; e < N * N; e += THREADS) {
       const int r = e & (N - 1), c = e >> 7;
       if (r >= c) W[r + (int64_t)c * ldw] = Lt[tix(r >> 4, c >> 4) * TSZ + (r & 15) * TLD + (c & 15)];
    }
+   LEAF_TICK(4);
    // inverse: blocks of h tiles are merged pairwise, X21 = -X22 (L21 X11); tile (R, C) of X: Xd when R == C
    auto xt = [&](int R, int C) -> const double* { return (R == C) ? Xd + R * TSZ : Lt + tix(R, C) * TSZ; };
    for (int h = 1; h < NTL; h *= 2) {
@@ -409,10 +499,17 @@ potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv
       }
       __syncthreads();
    }
+   LEAF_TICK(5);
    for (int e = tid; e < N * N; e += THREADS) {
       const int r = e & (N - 1), c = e >> 7;
       dinv[e] = (r >= c) ? xt(r >> 4, c >> 4)[(r & 15) * TLD + (c & 15)] : 0.0;
    }
+#ifdef LEAF_PROF
+   LEAF_TICK(6);
+   if (tid == 0)
+      printf("[leaf] load %lld first D %lld cholesky loop %lld store L %lld inverse %lld store inv %lld cycles\n", tk[1] - tk[0],
+             tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -527,21 +624,15 @@ static int64_t dist_group_width(const mchrg_b200_context* ctx, int64_t n) {
    while (db > TILE && n / db < 2 * (int64_t)ctx->comm->nranks) db -= TILE;
    return std::max<int64_t>(db, TILE);
 }
-static int64_t dist_sub_width(int64_t db) {
-   int64_t pw = env_ll("MCHRG_B200_DIST_PANEL", 128) / TILE * TILE;
-   pw = std::min(std::max<int64_t>(pw, TILE), db);
-   while (db % pw) pw -= TILE;
-   return pw;
-}
-
 int64_t dpotrf_dist_panel(const mchrg_b200_context* ctx, int64_t n) { return dist_applies(ctx, n) ? dist_group_width(ctx, n) : 0; }
 
 static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info, int64_t aug_end) {
    Comm* cm = ctx->comm;
    const int R = cm->nranks, me = cm->rank;
-   const int64_t DB = dist_group_width(ctx, n), PW = dist_sub_width(DB);
+   const int64_t DB = dist_group_width(ctx, n), PW = TILE;  // sub-panels are one 128 x 128 leaf wide
    const int ngrp = (int)((n + DB - 1) / DB);
-   cudaStream_t U = ctx->active, P = ctx->stream_hi, C = ctx->stream_comm;
+   const int nsub = (int)(n / PW), spg = (int)(DB / PW);  // sub-panels in all / per group
+   cudaStream_t U = ctx->active, P = ctx->stream_hi, Q = ctx->stream_hi2, C = ctx->stream_comm;
    auto g0_of = [&](int g) { return (int64_t)g * DB; };
    auto gw_of = [&](int g) { return std::min<int64_t>(DB, n - g0_of(g)); };
    auto owner = [&](int g) { return g % R; };
@@ -553,75 +644,163 @@ static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t l
    auto wait = [&](cudaStream_t s, cudaEvent_t e) {
       if (e) MCHRG_CUDA(cudaStreamWaitEvent(s, e, 0));
    };
-   // everything queued on U so far (the assembly) precedes the factorisation on P and the broadcasts on C
-   cudaEvent_t e_begin = rec(U);
-   wait(P, e_begin);
+   // MCHRG_B200_DIST_TRACE=1: timed events around the operations, summed per category and printed by every rank after
+   // the factorisation (synchronises: measurement runs only)
+   const bool trace = env_ll("MCHRG_B200_DIST_TRACE", 0) > 0;
+   struct Span { int cat; cudaEvent_t a, b; };
+   std::vector<Span> spans;
+   auto tic = [&](cudaStream_t s, int cat) {
+      if (!trace) return;
+      Span sp{cat, nullptr, nullptr};
+      MCHRG_CUDA(cudaEventCreate(&sp.a));
+      MCHRG_CUDA(cudaEventCreate(&sp.b));
+      MCHRG_CUDA(cudaEventRecord(sp.a, s));
+      spans.push_back(sp);
+   };
+   auto toc = [&](cudaStream_t s) {
+      if (trace) MCHRG_CUDA(cudaEventRecord(spans.back().b, s));
+   };
+   // ---- write tracker.  Per sub-panel column j three parts change hands between the streams:
+   //        PD  the diagonal tile (j, j)      PE  the tile below it (j+1, j)      PB  the rows from (j+2) * 128 on
+   //      Every operation that WRITES parts goes through `write`, which orders its stream after the last writer of
+   //      each part and records itself as the new one; READS of factored panel data wait for the events in
+   //      headE / tailB / arrived explicitly.
+   enum { PD = 1, PE = 2, PB = 4, PALL = 7 };
+   struct Touch { cudaEvent_t ev; cudaStream_t st; };
+   cudaEvent_t e_begin = rec(U);  // everything queued on U so far (the assembly)
+   std::vector<Touch> last((size_t)3 * nsub, Touch{e_begin, U});
    wait(C, e_begin);
-   // first_upd[g]: event after which this rank's copy of group g carries every bulk update issued so far
-   std::vector<cudaEvent_t> bulk_done(ngrp, nullptr);
-   cudaEvent_t last_bulk = nullptr;
+   auto write = [&](cudaStream_t X, int j0, int j1, int parts, int cat, auto&& launch) {
+      cudaEvent_t seen = nullptr;
+      for (int j = j0; j < j1; ++j)
+         for (int pt = 0; pt < 3; ++pt)
+            if ((parts >> pt) & 1) {
+               const Touch& tc = last[(size_t)3 * j + pt];
+               if (tc.st != X && tc.ev != seen) {
+                  wait(X, tc.ev);
+                  seen = tc.ev;
+               }
+            }
+      StreamScope on(ctx, X);
+      tic(X, cat);
+      launch();
+      toc(X);
+      cudaEvent_t e = rec(X);
+      for (int j = j0; j < j1; ++j)
+         for (int pt = 0; pt < 3; ++pt)
+            if ((parts >> pt) & 1) last[(size_t)3 * j + pt] = Touch{e, X};
+      return e;
+   };
+   // events after which the factored sub-panel s may be read on this rank: its tile (s+1, s) / its rows below / all of it
+   std::vector<cudaEvent_t> headE((size_t)nsub, nullptr), tailB((size_t)nsub, nullptr);
+   auto need_panel = [&](cudaStream_t X, int s, bool head, bool tail) {
+      if (head) wait(X, headE[s]);
+      if (tail) wait(X, tailB[s]);
+   };
+   // Eager (non-bulk) updates of the columns [t0, t1) with the factored sub-panel s.  The diagonal tile of column t0
+   // -- the next leaf -- is updated by the small-tile product on P; everything else goes to Q.
+   auto eager = [&](int s, int t0, int t1, int cat) {
+      const int64_t c0 = (int64_t)s * PW;
+      const int64_t r0 = (int64_t)t0 * PW;               // first row / column of the target range
+      const double* Lt0 = W + r0 + c0 * ldw;             // L(rows of tile t0, panel s)
+      const bool head_is_E = (t0 == s + 1);              // that tile is the panel's tile (s+1, s), else part of its tail
+      need_panel(P, s, head_is_E, !head_is_E);
+      write(P, t0, t0 + 1, PD, cat, [&]() { dgemm_small128(ctx, PW, PW, -1.0, Lt0, ldw, Lt0, ldw, 1.0, W + r0 + r0 * ldw, ldw); });
+      const int64_t rows2 = n - r0 - PW;                 // rows below the diagonal tile of column t0
+      if (rows2 > 0) {
+         need_panel(Q, s, head_is_E, true);
+         write(Q, t0, t0 + 1, PE | PB, cat, [&]() {
+            dgemm_padded(ctx, true, rows2, PW, PW, -1.0, Lt0 + PW, ldw, Lt0, ldw, 1.0, W + r0 + PW + r0 * ldw, ldw, false);
+         });
+         if (t0 + 1 < t1) {
+            const int64_t cb = (int64_t)(t0 + 1) * PW, ce = std::min<int64_t>(n, (int64_t)t1 * PW);
+            const double* A = W + cb + c0 * ldw;
+            write(Q, t0 + 1, t1, PALL, cat, [&]() {
+               dgemm_padded(ctx, true, n - cb, ce - cb, PW, -1.0, A, ldw, A, ldw, 1.0, W + cb + cb * ldw, ldw, false);
+            });
+         }
+      }
+   };
    for (int g = 0; g < ngrp; ++g) {
-      const int64_t g0 = g0_of(g), gw = gw_of(g), gend = g0 + gw;
+      const int64_t g0 = g0_of(g), gw = gw_of(g);
       const bool mine = owner(g) == me;
       const bool next_mine = g + 1 < ngrp && owner(g + 1) == me;
-      const int64_t h0 = gend, hw = (g + 1 < ngrp) ? gw_of(g + 1) : 0;  // the next group
-      // P works on this rank's copy of group g (owner) / g + 1 (next owner): the bulk updates of U come first
-      if (mine) wait(P, bulk_done[g]);
-      if (next_mine) wait(P, bulk_done[g + 1]);
-      cudaEvent_t e_last = nullptr;  // arrival of the group's last sub-panel
-      for (int64_t c0 = g0; c0 < gend; c0 += PW) {
-         const int64_t pw = std::min<int64_t>(PW, gend - c0), rem = n - c0 - pw;
+      const int s0 = g * spg, s1 = std::min(nsub, s0 + spg);  // sub-panels of this group
+      const int h0 = s1, h1 = std::min(nsub, s1 + spg);       // sub-panels of the next group
+      for (int s = s0; s < s1; ++s) {
+         const int64_t c0 = (int64_t)s * PW, rem = n - c0 - PW;
          double* D = W + c0 + c0 * ldw;
          double* dinv_k = dinv + (c0 / TILE) * TILE * TILE;
          if (mine) {
-            StreamScope on_p(ctx, P);
-            potrf_rec(ctx, pw, D, ldw, dinv_k, info, c0, aug_end);
-            if (rem > 0) dtrsm_right_lt(ctx, rem, pw, D, ldw, dinv_k, D + pw, ldw);
-            wait(C, rec(P));
+            // critical path on P: leaf, then only the 128 rows the next leaf depends on; the rows below on Q
+            cudaEvent_t e_leaf = write(P, s, s + 1, PD, 0, [&]() { potrf_rec(ctx, PW, D, ldw, dinv_k, info, c0, aug_end); });
+            headE[s] = tailB[s] = e_leaf;
+            if (rem > 0)
+               headE[s] = write(P, s, s + 1, PE, 1, [&]() { dgemm_small128(ctx, PW, PW, 1.0, D + PW, ldw, dinv_k, TILE, 0.0, D + PW, ldw); });
+            if (rem > PW) {
+               wait(Q, e_leaf);
+               tailB[s] = write(Q, s, s + 1, PB, 1, [&]() { dtrsm_right_lt(ctx, rem - PW, PW, D, ldw, dinv_k, D + 2 * PW, ldw); });
+            }
+            wait(C, headE[s]);
+            wait(C, tailB[s]);
          }
-         // sub-panel from its diagonal element to the end of its last column (one contiguous range) + inverted blocks
+         // sub-panel from its diagonal element to the end of its last column (one contiguous range) + inverted block
+         tic(C, 2);
          cm->group_begin();
-         cm->bcast(D, (size_t)(((pw - 1) * ldw + (n - c0)) * sizeof(double)), owner(g), C);
-         cm->bcast(dinv_k, (size_t)((pw / TILE) * TILE * TILE * sizeof(double)), owner(g), C);
+         cm->bcast(D, (size_t)(((PW - 1) * ldw + (n - c0)) * sizeof(double)), owner(g), C);
+         cm->bcast(dinv_k, (size_t)(TILE * TILE * sizeof(double)), owner(g), C);
          cm->group_end();
+         toc(C);
          cudaEvent_t e_arr = rec(C);
-         e_last = e_arr;
+         if (!mine) headE[s] = tailB[s] = e_arr;
          if (rem == 0) break;
-         const double* A21 = D + pw;  // rows below the sub-panel's diagonal block
-         if (mine && c0 + pw < gend) {  // rest of the own group
-            StreamScope on_p(ctx, P);
-            dgemm_padded(ctx, true, rem, gend - c0 - pw, pw, -1.0, A21, ldw, A21, ldw, 1.0, W + (c0 + pw) + (c0 + pw) * ldw, ldw,
-                         false);
-         }
-         if (next_mine) {  // the group this rank factors next, sub-panel by sub-panel as they arrive
-            StreamScope on_p(ctx, P);
-            wait(P, e_arr);
-            const double* Ah = W + h0 + c0 * ldw;
-            dgemm_padded(ctx, true, n - h0, hw, pw, -1.0, Ah, ldw, Ah, ldw, 1.0, W + h0 + h0 * ldw, ldw, false);
-         }
+         if (mine && s + 1 < s1) eager(s, s + 1, s1, 3);   // the rest of this group
+         if (next_mine) eager(s, h0, h1, 4);               // the group this rank factors next
       }
-      // bulk: all owned groups behind the next one, with the whole group g at once (rank-gw update)
+      // bulk: all owned groups behind the next one, with the whole group g at once (rank-gw update); the first of
+      // them -- the next one this rank will have to factor -- as its own launch
       int j1 = g + 2;
       while (j1 < ngrp && owner(j1) != me) ++j1;
       if (j1 < ngrp) {
-         StreamScope on_u(ctx, U);
-         wait(U, e_last);
+         for (int s = s0; s < s1; ++s) need_panel(U, s, false, true);  // rows far below: the tails
          const double* Pg = W + g0 * ldw;  // panel of the group, global rows
          const int64_t j0 = g0_of(j1);
-         const double* Aj = Pg + j0;
-         dgemm_padded(ctx, true, n - j0, gw_of(j1), gw, -1.0, Aj, ldw, Aj, ldw, 1.0, W + j0 + j0 * ldw, ldw, false);
-         bulk_done[j1] = rec(U);
+         write(U, j1 * spg, std::min(nsub, (j1 + 1) * spg), PALL, 5, [&]() {
+            const double* Aj = Pg + j0;
+            dgemm_padded(ctx, true, n - j0, gw_of(j1), gw, -1.0, Aj, ldw, Aj, ldw, 1.0, W + j0 + j0 * ldw, ldw, false);
+         });
          if (j1 + R < ngrp) {
-            dsyrk_cyclic(ctx, n, gw, Pg, W, ldw, (int)(g0_of(j1 + R) / TILE), (int)(R * DB / TILE), (int)(DB / TILE));
-            last_bulk = rec(U);
-            for (int j = j1 + R; j < ngrp; j += R) bulk_done[j] = last_bulk;
+            // (the tracker marks every sub-panel column from the first of them on; columns of foreign groups in between
+            //  are never written here, the extra ordering is harmless)
+            write(U, (j1 + R) * spg, nsub, PALL, 5, [&]() {
+               dsyrk_cyclic(ctx, n, gw, Pg, W, ldw, (int)(g0_of(j1 + R) / TILE), (int)(R * DB / TILE), (int)(DB / TILE));
+            });
          }
       }
    }
-   (void)last_bulk;
-   // the factor is complete on this rank when the last broadcast has arrived and P has drained
+   // the factor is complete on this rank when the last broadcast has arrived and P / Q have drained
    wait(U, rec(P));
+   wait(U, rec(Q));
    wait(U, rec(C));
+   if (trace) {
+      MCHRG_CUDA(cudaStreamSynchronize(U));
+      static const char* names[6] = {"leaf", "row solve (head+tail)", "broadcast", "own-group update", "next-group update", "bulk update"};
+      double sum[6] = {0, 0, 0, 0, 0, 0};
+      int cnt[6] = {0, 0, 0, 0, 0, 0};
+      for (auto& sp : spans) {
+         float ms = 0.f;
+         MCHRG_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+         sum[sp.cat] += ms;
+         cnt[sp.cat]++;
+      }
+      fprintf(stderr, "[mchrg_b200 dist trace] rank %d of %d n=%lld DB=%lld:", me, R, (long long)n, (long long)DB);
+      for (int c = 0; c < 6; ++c) fprintf(stderr, " %s %.2f ms/%d", names[c], sum[c], cnt[c]);
+      fprintf(stderr, "\n");
+      for (auto& sp : spans) {
+         cudaEventDestroy(sp.a);
+         cudaEventDestroy(sp.b);
+      }
+   }
    // every rank reports the same pivot failure
    double* slots = ctx->alloc<double>((size_t)R);
    MCHRG_LAUNCH(ctx, info_to_slot_kernel, 1, 1, 0, info, me, R, slots);

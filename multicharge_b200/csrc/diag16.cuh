@@ -10,6 +10,26 @@ namespace d16 {
 constexpr int KB = 16;   // tile order
 constexpr int CBW = 20;  // column buffer: 16 entries (parity-split) + [16] pivot + [17] next diagonal entry
 
+// 1 / x for the pivots (normal, positive x; anything else ends in the failed-pivot report anyway).
+// D16_RCP = 1 (default): hardware seed (MUFU.RCP64H, > 20 good bits) and two Newton steps, 5 dependent instructions;
+// the IEEE division (D16_RCP = 0) is a ~20-instruction sequence with a slow-path call and sits on the serial pivot
+// chain of every column step (measured: tools/micro/diag_variants.cu).  Relative error < 2^-52 x a few.
+#ifndef D16_RCP
+#define D16_RCP 1
+#endif
+__device__ __forceinline__ double pivot_rcp(double x) {
+#if D16_RCP
+   double y;
+   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+   double e = fma(-x, y, 1.0);
+   y = fma(y, e, y);
+   e = fma(-x, y, 1.0);
+   return fma(y, e, y);
+#else
+   return 1.0 / x;
+#endif
+}
+
 // conflict-free 16 x 16 layout for the FP64 mma fragment loads of batch.cu
 __device__ __forceinline__ int swz(int row, int col) { return row * KB + (col ^ ((row & 3) << 2)); }
 
@@ -56,7 +76,7 @@ __device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cb
    publish(0);
    __syncwarp();
    double piv = cbuf[16];
-   double d = 1.0 / piv;
+   double d = pivot_rcp(piv);
    int bad = !(piv > 0.0) ? 1 : 0;
 #pragma unroll
    for (int c = 0; c < KB; ++c) {
@@ -69,7 +89,7 @@ __device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cb
          const double u = cb[((c + 1) & 1) * 8 + ((c + 1) >> 1)];
          piv = forced ? 1.0 : fma(-u * u, d, cb[17]);
          bad = (!(piv > 0.0) && bad == 0) ? (c + 2) : bad;
-         dn = 1.0 / piv;
+         dn = pivot_rcp(piv);
       }
       const double f = cb[myslot] * d;  // 0 for r <= c: the updates below leave those rows alone
 #pragma unroll

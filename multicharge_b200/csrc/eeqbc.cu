@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(256) bc_cmat_kernel(int nat, int64_t npad, con
 // get_amat_0d (eeqbc.f90:475-530) into the padded work matrix (identity padding)
 __global__ void __launch_bounds__(128) bc_amat_kernel(int nat, int64_t npad, const double* __restrict__ xyz,
                                                       const double* __restrict__ atoms, const double* __restrict__ Cm,
-                                                      double* __restrict__ W, const double2* __restrict__ etab) {
+                                                      double* __restrict__ W, const double2* __restrict__ etab,
+                                                      int own_panel, int nranks, int rank) {
+   // multi-GPU factorisation: only the column groups this rank owns (block-cyclic, own_panel columns wide)
+   if (own_panel > 0 && (int)(((int64_t)blockIdx.y * 8) / own_panel) % nranks != rank) return;
    __shared__ double2 setab[eg::NTAB];
    eg::load_table(setab, etab, (int)threadIdx.x, (int)blockDim.x);
    __syncthreads();
@@ -191,13 +194,13 @@ __global__ void __launch_bounds__(256) bc_rows_kernel(int nat, int64_t npad, con
                                                       const double* __restrict__ Cm, const double* __restrict__ q,
                                                       const double* __restrict__ dcndr,
                                                       const double* __restrict__ dcndL, double* __restrict__ rows,
-                                                      const double2* __restrict__ etab) {
+                                                      const double2* __restrict__ etab, int row0, int row1) {
    __shared__ double2 setab[eg::NTAB];
    eg::load_table(setab, etab, (int)threadIdx.x, (int)blockDim.x);
    __syncthreads();
-   const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   const int a = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    const int lane = threadIdx.x & 31;
-   if (a >= nat) return;
+   if (a >= row1) return;
    const double xa = xyz[3 * a], ya = xyz[3 * a + 1], za = xyz[3 * a + 2];
    const double rada = atoms[5 * a], drada = atoms[5 * a + 1], capa = atoms[5 * a + 4];
    double La[9];
@@ -255,10 +258,10 @@ __global__ void __launch_bounds__(256) bc_strain_kernel(int nat, int64_t npad, B
                                                         const double* __restrict__ dcdL,
                                                         const double* __restrict__ dcndL,
                                                         const double* __restrict__ dqlocdL, double* __restrict__ dadL,
-                                                        double* __restrict__ dxdL) {
-   const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                                                        double* __restrict__ dxdL, int row0, int row1) {
+   const int a = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    const int lane = threadIdx.x & 31;
-   if (a >= nat) return;
+   if (a >= row1) return;
    double g[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
    for (int i = lane; i < nat; i += 32) {
       const double cia = Cm[i + (int64_t)a * npad], k1 = at.kcnchi[i] * cia, k2 = at.kqchi[i] * cia;
@@ -282,14 +285,17 @@ __global__ void __launch_bounds__(256) bc_strain_kernel(int nat, int64_t npad, B
 }
 
 // dtmpdr (eeqbc.f90:344-348) into the padded GEMM operand T(3a+c, i) = kcnchi_i dcndr(c,a,i) + kqchi_i dqlocdr(c,a,i)
+// rows of the atom block [jb, je): r = 3 (a - jb) + c
 __global__ void bc_dtmpdr_kernel(int nat, int64_t mp, int64_t npad, BcAtoms at, const double* __restrict__ dcndr,
-                                 const double* __restrict__ dqlocdr, double* __restrict__ T) {
+                                 const double* __restrict__ dqlocdr, double* __restrict__ T, int jb, int je) {
    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    const int64_t i = blockIdx.y;
    if (r >= mp || i >= npad) return;
    double v = 0.0;
-   if (r < 3 * (int64_t)nat && i < nat)
-      v = at.kcnchi[i] * dcndr[r + (size_t)3 * nat * i] + at.kqchi[i] * dqlocdr[r + (size_t)3 * nat * i];
+   if (r < 3 * (int64_t)(je - jb) && i < nat) {
+      const size_t src = (size_t)3 * jb + r + (size_t)3 * nat * i;
+      v = at.kcnchi[i] * dcndr[src] + at.kqchi[i] * dqlocdr[src];
+   }
    T[r + i * mp] = v;
 }
 
@@ -311,11 +317,13 @@ __global__ void __launch_bounds__(128) bc_build_b_kernel(int nat, int64_t npad, 
                                                          int add_atrace, double* __restrict__ Bout, int64_t ldb,
                                                          double* __restrict__ ga, double* __restrict__ gx,
                                                          const double* __restrict__ zvec, double* __restrict__ bz,
-                                                         const double2* __restrict__ etab) {
+                                                         const double2* __restrict__ etab, int jb, int je) {
    __shared__ double2 setab[eg::NTAB];
    eg::load_table(setab, etab, (int)threadIdx.x, (int)blockDim.x);
    __shared__ double sk[BCK][12];  // x y z rad drad h xtmp cap | q C_bb-weights(2) z
-   const int a = blockIdx.x * blockDim.x + threadIdx.x;
+   // atom a of the row block [jb, je); rows of Bout / ga / gx / bz are numbered within the block
+   const int al = blockIdx.x * blockDim.x + threadIdx.x;
+   const int a = jb + al;
    const int b0 = blockIdx.y * BCK;
    const int bn = min(BCK, nat - b0);
    for (int idx = threadIdx.x; idx < bn; idx += blockDim.x) {
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(128) bc_build_b_kernel(int nat, int64_t npad, 
       sk[idx][11] = zvec ? zvec[b] : 0.0;
    }
    __syncthreads();
-   if (a >= nat) return;
+   if (a >= je) return;
    const double xa = xyz[3 * a], ya = xyz[3 * a + 1], za = xyz[3 * a + 2];
    const double rada = atoms[5 * a], drada = atoms[5 * a + 1], xtmpa = atoms[5 * a + 3], capa = atoms[5 * a + 4];
    const double qa = q[a];
@@ -380,7 +388,7 @@ __global__ void __launch_bounds__(128) bc_build_b_kernel(int nat, int64_t npad, 
       sgx[1] += dx1 * qb + tk * c1 + tl * l1;
       sgx[2] += dx2 * qb + tk * c2 + tl * l2;
       if (Bout) {
-         double* o = Bout + (size_t)b * ldb + 3 * a;
+         double* o = Bout + (size_t)b * ldb + 3 * al;
          double b0v = sa * da0 - sx * dx0, b1v = sa * da1 - sx * dx1, b2v = sa * da2 - sx * dx2;
          if (sx != 0.0) { b0v += o[0]; b1v += o[1]; b2v += o[2]; }
          o[0] = b0v; o[1] = b1v; o[2] = b2v;
@@ -388,9 +396,9 @@ __global__ void __launch_bounds__(128) bc_build_b_kernel(int nat, int64_t npad, 
          sbz[0] = fma(b0v, zk, sbz[0]); sbz[1] = fma(b1v, zk, sbz[1]); sbz[2] = fma(b2v, zk, sbz[2]);
       }
    }
-   if (ga) { atomicAdd(ga + 3 * a, sga[0]); atomicAdd(ga + 3 * a + 1, sga[1]); atomicAdd(ga + 3 * a + 2, sga[2]); }
-   if (gx) { atomicAdd(gx + 3 * a, sgx[0]); atomicAdd(gx + 3 * a + 1, sgx[1]); atomicAdd(gx + 3 * a + 2, sgx[2]); }
-   if (bz && Bout) { atomicAdd(bz + 3 * a, sbz[0]); atomicAdd(bz + 3 * a + 1, sbz[1]); atomicAdd(bz + 3 * a + 2, sbz[2]); }
+   if (ga) { atomicAdd(ga + 3 * al, sga[0]); atomicAdd(ga + 3 * al + 1, sga[1]); atomicAdd(ga + 3 * al + 2, sga[2]); }
+   if (gx) { atomicAdd(gx + 3 * al, sgx[0]); atomicAdd(gx + 3 * al + 1, sgx[1]); atomicAdd(gx + 3 * al + 2, sgx[2]); }
+   if (bz && Bout) { atomicAdd(bz + 3 * al, sbz[0]); atomicAdd(bz + 3 * al + 1, sbz[1]); atomicAdd(bz + 3 * al + 2, sbz[2]); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -411,28 +419,69 @@ void bc_prepare(mchrg_b200_context* ctx, const DevMol& mol, const mchrg_b200_mod
                 model->dev_rvdw(), model->nid, model->kbc, w.Cm, w.dcdr_diag, w.dcdL, ctx->erf_tab);
 }
 
-void bc_amat(mchrg_b200_context* ctx, const DevMol& mol, const BcWork& w, double* W) {
+void bc_amat(mchrg_b200_context* ctx, const DevMol& mol, const BcWork& w, double* W, int64_t own_panel) {
    dim3 grid((unsigned)((w.npad + 127) / 128), (unsigned)((w.npad + 7) / 8));
-   MCHRG_LAUNCH(ctx, bc_amat_kernel, grid, 128, 0, mol.nat, w.npad, mol.xyz, w.atoms, w.Cm, W, ctx->erf_tab);
+   MCHRG_LAUNCH(ctx, bc_amat_kernel, grid, 128, 0, mol.nat, w.npad, mol.xyz, w.atoms, w.Cm, W, ctx->erf_tab, (int)own_panel,
+                ctx->nranks(), ctx->rank());
+}
+
+// (A q)_a = sum_b A_ab q_b re-evaluated from the pair formula (no copy of the matrix is kept for the energy,
+// type.F90:257-259); warp per row a in [row0, row1)
+__global__ void __launch_bounds__(256) bc_jq_rows_kernel(int nat, int64_t npad, const double* __restrict__ xyz,
+                                                         const double* __restrict__ atoms, const double* __restrict__ Cm,
+                                                         const double* __restrict__ q, double* __restrict__ jq,
+                                                         const double2* __restrict__ etab, int row0, int row1) {
+   __shared__ double2 setab[eg::NTAB];
+   eg::load_table(setab, etab, (int)threadIdx.x, (int)blockDim.x);
+   __syncthreads();
+   const int a = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   const int lane = threadIdx.x & 31;
+   if (a >= row1) return;
+   const double xa = xyz[3 * a], ya = xyz[3 * a + 1], za = xyz[3 * a + 2], ra = atoms[5 * a];
+   const double* col = Cm + (int64_t)a * npad;  // symmetric
+   double acc = 0.0;
+   for (int b = lane; b < nat; b += 32) {
+      if (b == a) continue;
+      const double dx = xyz[3 * b] - xa, dy = xyz[3 * b + 1] - ya, dz = xyz[3 * b + 2] - za;
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      const double rb = atoms[5 * b];
+      const double rinv = eg::fast_rsqrt(r2), gam = eg::fast_rsqrt(ra * ra + rb * rb);
+      double g;
+      acc = fma(eg::erf_gauss<5, false>(setab, r2 * rinv * gam, g) * rinv * col[b], q[b], acc);
+   }
+   acc = wsum(acc);
+   if (lane == 0) jq[a] = acc + (atoms[5 * a + 2] * col[a] + 1.0) * q[a];
+}
+void bc_jq_rows(mchrg_b200_context* ctx, const DevMol& mol, const BcWork& w, const double* q, double* jq, int row0, int row1) {
+   if (row1 < 0) { row0 = 0; row1 = mol.nat; }
+   if (row1 <= row0) return;
+   MCHRG_LAUNCH(ctx, bc_jq_rows_kernel, (unsigned)((row1 - row0 + 7) / 8), 256, 0, mol.nat, w.npad, mol.xyz, w.atoms, w.Cm, q, jq,
+                ctx->erf_tab, row0, row1);
 }
 
 void bc_rows(mchrg_b200_context* ctx, const DevMol& mol, const mchrg_b200_model* model, const BcWork& w,
-             const double* q, const double* dcndr, const double* dcndL, double* rows) {
-   MCHRG_LAUNCH(ctx, bc_rows_kernel, (unsigned)((mol.nat + 7) / 8), 256, 0, mol.nat, w.npad, mol.xyz, mol.id, w.atoms,
-                model->dev_rvdw(), model->nid, model->kbc, w.Cm, q, dcndr, dcndL, rows, ctx->erf_tab);
+             const double* q, const double* dcndr, const double* dcndL, double* rows, int row0, int row1) {
+   if (row1 < 0) { row0 = 0; row1 = mol.nat; }
+   if (row1 <= row0) return;
+   MCHRG_LAUNCH(ctx, bc_rows_kernel, (unsigned)((row1 - row0 + 7) / 8), 256, 0, mol.nat, w.npad, mol.xyz, mol.id, w.atoms,
+                model->dev_rvdw(), model->nid, model->kbc, w.Cm, q, dcndr, dcndL, rows, ctx->erf_tab, row0, row1);
 }
 
 void bc_strain(mchrg_b200_context* ctx, const DevMol& mol, const BcAtoms& at, const BcWork& w, const double* q,
-               const double* rows, const double* dcndL, const double* dqlocdL, double* dadL, double* dxdL) {
-   MCHRG_LAUNCH(ctx, bc_strain_kernel, (unsigned)((mol.nat + 7) / 8), 256, 0, mol.nat, w.npad, at, w.atoms, w.Cm, q, rows,
-                w.dcdL, dcndL, dqlocdL, dadL, dxdL);
+               const double* rows, const double* dcndL, const double* dqlocdL, double* dadL, double* dxdL, int row0,
+               int row1) {
+   if (row1 < 0) { row0 = 0; row1 = mol.nat; }
+   if (row1 <= row0) return;
+   MCHRG_LAUNCH(ctx, bc_strain_kernel, (unsigned)((row1 - row0 + 7) / 8), 256, 0, mol.nat, w.npad, at, w.atoms, w.Cm, q, rows,
+                w.dcdL, dcndL, dqlocdL, dadL, dxdL, row0, row1);
 }
 
 void bc_dxdr_gemm(mchrg_b200_context* ctx, const DevMol& mol, const BcAtoms& at, const BcWork& w, const double* dcndr,
-                  const double* dqlocdr, double alpha, double* Bm, int64_t mp) {
+                  const double* dqlocdr, double alpha, double* Bm, int64_t mp, int jb, int je) {
+   if (je < 0) { jb = 0; je = mol.nat; }
    double* T = ctx->alloc<double>((size_t)mp * w.npad);
    dim3 grid((unsigned)((mp + 255) / 256), (unsigned)w.npad);
-   MCHRG_LAUNCH(ctx, bc_dtmpdr_kernel, grid, 256, 0, mol.nat, mp, w.npad, at, dcndr, dqlocdr, T);
+   MCHRG_LAUNCH(ctx, bc_dtmpdr_kernel, grid, 256, 0, mol.nat, mp, w.npad, at, dcndr, dqlocdr, T, jb, je);
    // C is symmetric: op(B) = C^T = C
    dgemm_padded(ctx, true, mp, w.npad, w.npad, alpha, T, mp, w.Cm, w.npad, 0.0, Bm, mp, false);
 }
@@ -440,11 +489,12 @@ void bc_dxdr_gemm(mchrg_b200_context* ctx, const DevMol& mol, const BcAtoms& at,
 void bc_build_b(mchrg_b200_context* ctx, const DevMol& mol, const mchrg_b200_model* model, const BcAtoms& at,
                 const BcWork& w, const double* q, const double* cq, const double* rows, const double* dcndr,
                 const double* dqlocdr, double sa, double sx, bool add_atrace, double* Bout, int64_t ldb, double* ga,
-                double* gx, const double* zvec, double* bz) {
-   dim3 grid((unsigned)((mol.nat + 127) / 128), (unsigned)((mol.nat + BCK - 1) / BCK));
+                double* gx, const double* zvec, double* bz, int jb, int je) {
+   if (je < 0) { jb = 0; je = mol.nat; }
+   dim3 grid((unsigned)((je - jb + 127) / 128), (unsigned)((mol.nat + BCK - 1) / BCK));
    MCHRG_LAUNCH(ctx, bc_build_b_kernel, grid, 128, 0, mol.nat, w.npad, mol.xyz, mol.id, w.atoms, at, model->dev_rvdw(),
                 model->nid, model->kbc, w.Cm, q, cq, rows, w.dcdr_diag, dcndr, dqlocdr, sa, sx, add_atrace ? 1 : 0, Bout,
-                ldb, ga, gx, zvec, bz, ctx->erf_tab);
+                ldb, ga, gx, zvec, bz, ctx->erf_tab, jb, je);
 }
 
 }  // namespace mchrg

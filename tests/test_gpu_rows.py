@@ -76,3 +76,25 @@ def test_cluster_full_size_properties(mc):
     assert float(blk["dqdL"].sum(dim=0).abs().max()) < 1e-9 * max(1.0, float(blk["dqdL"].abs().max()))
     assert np.abs(blk["gradient"].cpu().numpy() - g[jb:je]).max() < 1e-11 * max(1.0, np.abs(g).max())
     assert np.abs(blk["qvec"].cpu().numpy() - q).max() < 1e-12
+
+
+def test_eeqbc_row_blocks_concatenate_to_full(mc, oracle):
+    """EEQ-BC through singlepoint_rows on one context: disjoint atom blocks reproduce the full dq/dr and gradient."""
+    from synth import cluster
+    from test_gpu_eeqbc import models
+    nat = 260
+    num, xyz = cluster(nat, 12)
+    mol, model, omol, omodel = models(mc, oracle, num, xyz, 0.0)
+    full = model.singlepoint(mol, want=("qvec", "energy", "gradient", "dqdr"))
+    o = oracle.eeqbc_singlepoint(omodel, omol, want=("qvec", "energy", "gradient", "dqdr"))
+    grad = np.zeros((nat, 3))
+    dqdr = np.zeros((nat, nat, 3))
+    for jb, je in ((0, 100), (100, 131), (131, nat)):
+        r = mc.singlepoint_rows(model, mol, jb, je)
+        grad[jb:je] = r["gradient"]
+        dqdr[:, jb:je, :] = r["dqdr"]
+        for key in ("qvec", "energy", "sigma", "dqdL"):
+            assert np.abs(r[key] - full[key]).max() < 1e-12 * max(1.0, np.abs(full[key]).max()), key
+    for got, key in ((grad, "gradient"), (dqdr, "dqdr")):
+        assert np.abs(got - full[key]).max() < 1e-12 * max(1.0, np.abs(full[key]).max())
+        assert np.abs(got - o[key]).max() < 1e-10 * max(1.0, np.abs(o[key]).max())
