@@ -144,6 +144,30 @@ def dist_setup(ngpu):
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank's host threads to the CPUs next to its GPU (the PCI device's local_cpulist) BEFORE any pinned
+    buffer is allocated, so that first-touch places the staging memory on the GPU's NUMA node -- what `numactl
+    --cpunodebind/--membind` does for a one-process-per-GPU launch.  Returns a short description for the bench line."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return f"cpus {spec} (GPU {bus})"
+        return f"unchanged ({len(allowed)} cpus allowed, GPU-local {spec or 'unknown'})"
+    except Exception as exc:  # noqa: BLE001 -- affinity is an optimisation, never a failure
+        return f"unavailable ({type(exc).__name__})"
+
+
 def barrier(world):
     if world > 1:
         import torch.distributed as dist
@@ -510,6 +534,7 @@ def run_ours(args):
         return 2
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa_node(torch, local) if world > 1 else "not applied (one rank)"
     ctx = mc.Context(local)
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
     model = mc.new_eeq2019_batch_model(ctx)
@@ -644,7 +669,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": batch_config(world, nmol, ntot),
         "e2e": {"value": world * nmol * e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e_steps, "host_equals_device_result": same},
+                "steps": e_steps, "host_equals_device_result": same, "host_affinity": affinity},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "eeq_factor_ll_kernel (per-molecule Cholesky + substitutions, DMMA)",

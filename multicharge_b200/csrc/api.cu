@@ -268,6 +268,41 @@ __global__ void shift_apply_kernel(int nat, double* __restrict__ W, int64_t ld, 
    if (r < nat && c < nat) W[r + (int64_t)c * ld] += sh[0];
 }
 
+// ---- indefinite fallback (see factor_solve): bordered matrix K of order nk (padded to npk with the identity) ----
+__global__ void bordered_kernel(int nat, int64_t npad, const double* __restrict__ W, int64_t npk, double* __restrict__ K) {
+   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t c = blockIdx.y;
+   if (r >= npk || c >= npk) return;
+   double v;
+   if (r < nat && c < nat) v = W[r + c * npad];
+   else if (r <= nat && c <= nat) v = (r == nat && c == nat) ? 0.0 : 1.0;  // constraint row / column
+   else v = (r == c) ? 1.0 : 0.0;
+   K[r + c * npk] = v;
+}
+// b = [x; Q; 0 ...] in column 0 of R (leading dimension npk), column 1 zero
+__global__ void bordered_rhs_kernel(int nat, int64_t npk, const double* __restrict__ xvec, double charge, double* __restrict__ R) {
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= npk) return;
+   R[i] = (i < nat) ? xvec[i] : (i == nat ? charge : 0.0);
+   R[i + npk] = 0.0;
+}
+// r = b - t   /   y += d   /   copy
+__global__ void axpby_kernel(int64_t n, double a, const double* __restrict__ x, double b, const double* __restrict__ y,
+                             double* __restrict__ out) {
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) out[i] = a * x[i] + b * y[i];
+}
+__global__ void fallback_charges_kernel(int nat, const double* __restrict__ y, double* __restrict__ vrhs, double* __restrict__ qvec,
+                                        double* __restrict__ scal) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i <= nat) vrhs[i] = y[i];
+   if (i < nat && qvec) qvec[i] = y[i];
+   if (i == 0) {
+      scal[0] = 1.0;
+      scal[1] = y[nat];
+   }
+}
+
 __global__ void fill_kernel(int64_t n, double v, double* __restrict__ p) {
    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (i < n) p[i] = v;
@@ -322,6 +357,7 @@ static DevMol stage_mol(mchrg_b200_context* ctx, const mchrg_b200_structure* mol
 struct Factor {
    double *W = nullptr, *dinv = nullptr, *R = nullptr, *vrhs = nullptr, *scal = nullptr, *shift = nullptr;
    int info = 0;
+   bool indefinite = false;  // solved through the normal equations of the bordered matrix: no factor of J (no dq/dr)
    const double* z(int64_t npad) const { return R + npad; }
 };
 
@@ -360,7 +396,64 @@ static Factor factor_solve(mchrg_b200_context* ctx, int nat, int64_t npad, Assem
       MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
       f.info = *h_info;
       if (f.info == 0) break;
-      if (attempt == 3) return f;  // not positive definite on the charge-conserving subspace either
+      if (attempt == 3) {
+         // J is indefinite on the charge-conserving subspace as well (e.g. two atoms far inside each other's charge
+         // width).  The reference's Bunch-Kaufman LDL^T (lapack.F90:165-201) factors any nonsingular bordered matrix
+         // K = [J 1; 1^T 0]; here K^2 = K K^T is positive definite, so  K^-1 = (K K^T)^-1 K : DMMA product, the same
+         // blocked Cholesky, and two steps of iterative refinement against K itself (the squared condition number
+         // costs digits only in the first solve).  Charges, energy and gradient; dq/dr is not offered on this route.
+         if (std::getenv("MCHRG_B200_NO_INDEFINITE")) return f;
+         const int pivot = f.info;
+         const int64_t npk = round_up(nat + 1, TILE);
+         assemble(f.W, /*first=*/false);
+         double* K = ctx->alloc<double>((size_t)npk * npk);
+         double* M = ctx->alloc<double>((size_t)npk * npk);
+         dim3 gk((unsigned)((npk + 255) / 256), (unsigned)npk);
+         MCHRG_LAUNCH(ctx, bordered_kernel, gk, 256, 0, nat, npad, f.W, npk, K);
+         dgemm_padded(ctx, true, npk, npk, npk, 1.0, K, npk, K, npk, 0.0, M, npk, /*lower_only=*/true);
+         double* dinvM = ctx->alloc<double>((size_t)npk * TILE);
+         MCHRG_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
+         {  // (never shared between ranks: every rank solves the small bordered problem itself)
+            Comm* keep = ctx->comm;
+            ctx->comm = nullptr;
+            try {
+               dpotrf_padded(ctx, npk, M, npk, dinvM, info);
+            } catch (...) {
+               ctx->comm = keep;
+               throw;
+            }
+            ctx->comm = keep;
+         }
+         MCHRG_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+         MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
+         if (*h_info != 0) {  // singular to working precision: report the pivot of the Coulomb block like before
+            f.info = pivot;
+            return f;
+         }
+         const unsigned gb = (unsigned)((npk + 255) / 256);
+         double* b = ctx->alloc<double>((size_t)npk * 2);
+         double* y = ctx->alloc_zero<double>((size_t)npk);
+         double* r = ctx->alloc<double>((size_t)npk * 2);
+         double* t = ctx->alloc<double>((size_t)npk);
+         MCHRG_LAUNCH(ctx, bordered_rhs_kernel, gb, 256, 0, nat, npk, xvec, charge, b);
+         MCHRG_CUDA(cudaMemcpyAsync(r, b, (size_t)npk * 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+         for (int it = 0; it < 3; ++it) {  // y += (K K^T)^-1 K r ;  r = b - K y
+            MCHRG_CUDA(cudaMemsetAsync(r + npk, 0, (size_t)npk * sizeof(double), ctx->stream));
+            pbc_symv(ctx, (int)npk, K, npk, r, t);
+            MCHRG_CUDA(cudaMemcpyAsync(r, t, (size_t)npk * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            dpotrs_vec(ctx, npk, M, npk, dinvM, r, npk, 2);
+            MCHRG_LAUNCH(ctx, axpby_kernel, gb, 256, 0, npk, 1.0, y, 1.0, r, y);
+            pbc_symv(ctx, (int)npk, K, npk, y, t);
+            MCHRG_LAUNCH(ctx, axpby_kernel, gb, 256, 0, npk, 1.0, b, -1.0, t, r);
+         }
+         f.vrhs = ctx->alloc<double>(nat + 1);
+         f.scal = ctx->alloc<double>(2);
+         f.R = ctx->alloc_zero<double>((size_t)npad * 2);
+         MCHRG_LAUNCH(ctx, fallback_charges_kernel, (unsigned)((nat + 256) / 256), 256, 0, nat, y, f.vrhs, qvec_out, f.scal);
+         f.info = 0;
+         f.indefinite = true;
+         return f;
+      }
       MCHRG_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
       assemble(f.W, /*first=*/false);
       apply_shift();
@@ -446,6 +539,8 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
       ctx->copybacks.clear();
       return f.info;
    }
+   if (f.indefinite && cpq)
+      fail(MCHRG_B200_ERR_MODEL, "dq/dr is not available for an indefinite Coulomb block (solved through the bordered system)");
    const double* vrhs = f.vrhs;
    const double* zvec = f.z(npad);
 
@@ -612,6 +707,8 @@ static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, 
       ctx->copybacks.clear();
       return f.info;
    }
+   if (f.indefinite && cpq)
+      fail(MCHRG_B200_ERR_MODEL, "dq/dr is not available for an indefinite Coulomb block (solved through the bordered system)");
    const double* q = f.vrhs;
    // molecular: [jq | rows (24 N) | dadL (9 N) | dxdL (9 N)] in one buffer, so that row shards are joined by ONE all-reduce
    const size_t n1 = (size_t)nat;
@@ -1174,12 +1271,17 @@ int mchrg_b200_solve(const mchrg_b200_model* model, const mchrg_b200_structure* 
       io.dcndL = ctx->in(dcndL, 9 * n);
       io.dqlocdr = ctx->in(dqlocdr, 3 * n * n);
       io.dqlocdL = ctx->in(dqlocdL, 9 * n);
+      // presence rules of type.F90:199-201 (EEQ-BC: eeqbc.f90:195 needs the local-charge derivatives as well): an
+      // output that will not be produced is not staged, so a host array stays untouched like the reference's
+      // intent(inout) arguments
+      const bool dcn = dcndr && dcndL && (model->kind == 1 || (dqlocdr && dqlocdL));
+      const bool grad = gradient && sigma && dcn, cpq = dqdr && dqdL && dcn;
       io.energy = ctx->out(energy, n, /*preload=*/true);
-      io.gradient = ctx->out(gradient, 3 * n);
-      io.sigma = ctx->out(sigma, 9, /*preload=*/true);
+      io.gradient = grad ? ctx->out(gradient, 3 * n) : nullptr;
+      io.sigma = grad ? ctx->out(sigma, 9, /*preload=*/true) : nullptr;
       io.qvec = ctx->out(qvec, n);
-      io.dqdr = ctx->out(dqdr, 3 * n * n);
-      io.dqdL = ctx->out(dqdL, 9 * n);
+      io.dqdr = cpq ? ctx->out(dqdr, 3 * n * n) : nullptr;
+      io.dqdL = cpq ? ctx->out(dqdL, 9 * n) : nullptr;
       return solve_dispatch(model, d, io);
    });
 }
@@ -1209,7 +1311,8 @@ static int singlepoint_impl(const mchrg_b200_model* model, const mchrg_b200_stru
       const double charge = mol->charge;
       int32_t status = 0;
       const int rc = mchrg_b200_singlepoint_batch(model, 1, offsets, mol->id, mol->xyz, &charge, qvec, nullptr, nullptr, &status);
-      return rc != 0 ? rc : status;
+      if (rc != 0 || status <= 0) return rc != 0 ? rc : status;
+      // failed pivot: the general path below retries with the rank-one shift, so that both routes agree
    }
    return guarded(ctx, [&]() {
       DevMol d = stage_mol(ctx, mol);
@@ -1256,8 +1359,8 @@ static int singlepoint_impl(const mchrg_b200_model* model, const mchrg_b200_stru
       io.je = je;
       io.lazy = lazy ? &lz : nullptr;
       io.energy = ctx->out(energy, n, accumulate);
-      io.gradient = ctx->out(gradient, 3 * nj);
-      io.sigma = ctx->out(sigma, 9, accumulate);
+      io.gradient = (gradient && sigma) ? ctx->out(gradient, 3 * nj) : nullptr;  // gradient and sigma only together
+      io.sigma = (gradient && sigma) ? ctx->out(sigma, 9, accumulate) : nullptr;
       io.qvec = ctx->out(qvec, n);
       io.dqdr = ctx->out(dqdr, 3 * nj * n);
       io.dqdL = ctx->out(dqdL, 9 * n);

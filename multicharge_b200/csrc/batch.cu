@@ -223,9 +223,14 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
 
    // ---- load atoms and per-element parameters (chi, rad, eta, kcnchi, rcov = slots 0..4) ----
    if (tid == 0) sfail = 0;
+   int badz = 0;
    for (int i = tid; i < np; i += NT) {
       if (i < n) {
-         const int z = p.num[off + i] - 1;
+         int z = p.num[off + i] - 1;
+         if ((unsigned)z >= (unsigned)p.nid) {  // not a species of the model: the molecule is rejected below
+            badz = 1;
+            z = 0;
+         }
          X[i] = p.xyz[3 * (off + i)];
          Y[i] = p.xyz[3 * (off + i) + 1];
          Z[i] = p.xyz[3 * (off + i) + 2];
@@ -242,7 +247,16 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       if (PH == 0 || PH == 1) cnfix[i] = cnfix[npv + i] = cnfix[2 * npv + i] = 0u;
    }
    eg::load_table(etab, p.etab, tid, NT);
-   __syncthreads();
+   if (__syncthreads_or(badz) && PH != 3) {  // atomic number outside the model's species: status MCHRG_B200_ERR_ARG, outputs poisoned
+      const double nan = __longlong_as_double(0x7ff8000000000000LL);
+      for (int i = tid; i < n; i += NT) {
+         p.qvec[off + i] = nan;
+         if (p.energy) p.energy[off + i] = nan;
+         if (p.gradient) p.gradient[3 * (off + i)] = p.gradient[3 * (off + i) + 1] = p.gradient[3 * (off + i) + 2] = nan;
+      }
+      if (tid == 0) p.status[mol] = MCHRG_B200_ERR_ARG;
+      return;
+   }
 
    const int ntri_n = tri(n);
    constexpr unsigned FULL = 0xffffffffu;
@@ -340,6 +354,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          A[lay(np - 2, i)] = xv[i];
          A[lay(np - 1, i)] = 1.0;
       }
+      if (tid == 0) p.status[mol] = 0;  // (a negative status tells the factorisation kernel to leave the molecule alone)
       return;
    }
    if (PH == 3) {
@@ -646,6 +661,10 @@ constexpr int TS = KB + 1;            // row stride of the diagonal tile
 #ifndef LL_MINB
 #define LL_MINB 6
 #endif
+#ifndef LL_UNROLL
+#define LL_UNROLL 2  // block pairs of the left-looking update in flight per warp (each: four 16-byte loads from L2)
+#endif
+constexpr int LLU = LL_UNROLL;
 using d16::CBW;              // column buffer of the diagonal-tile routine (diag16.cuh)
 using d16::swz;
 
@@ -687,6 +706,7 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
    double* b1 = b0 + npa;
    __shared__ int sfail, next_job;
    __shared__ double T2[KB * TS];  // next diagonal tile, updated one block column ahead
+   if (p.status[mol] < 0) return;   // rejected by pair phase A (atomic number outside the model)
    if (tid == 0) { sfail = 0; next_job = 0; }
    const int g = lane >> 2, t = lane & 3;
    if (warp == 0) {  // first diagonal tile: nothing to its left
@@ -724,7 +744,7 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
          const double2* pa1 = reinterpret_cast<const double2*>(S + 64 * tri((i0 >> 3) + 1)) + lane;
          const double2* pb0 = reinterpret_cast<const double2*>(S + 64 * tri(j0 >> 3)) + lane;
          const double2* pb1 = reinterpret_cast<const double2*>(S + 64 * tri((j0 >> 3) + 1)) + lane;
-#pragma unroll 2
+#pragma unroll LLU
          for (int cb = 0; cb < (k0 >> 3); ++cb) {
             const double2 a0 = pa0[32 * cb], a1 = pa1[32 * cb], c0 = pb0[32 * cb], c1 = pb1[32 * cb];
             dmma884(acc[0][0][0], acc[0][0][1], a0.x, c0.x);
@@ -860,6 +880,8 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
       }
    }
    __syncthreads();
+   // (tried: fetching the next step's strip column and inverted diagonal tile one step ahead into registers --
+   //  32 more live doubles push the kernel over its register budget: 11.2 vs 10.1 ms per 100k molecules)
    for (int k0 = npa - KB; k0 >= 0; k0 -= KB) {
       if (warp == ((blockIdx.x + (k0 >> 4)) % NW)) {  // y_blk = inv(L_kk)^T w_blk ; lane = (r, rhs h)
          const int r = lane & 15, h = lane >> 4;
@@ -911,23 +933,33 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
 // consumers, so the DMMA warps read their operands from shared memory and never wait for L2:
 //   * left-looking update of block column k0 = [old part: columns < k0 - 16, streamed] + [newest block column
 //     k0 - 16, still in shared memory: the row solves write L back into the block column buffer Cb];
-//   * chunk-major order: per chunk of 64 columns one B chunk (rows of the current block column) is shared by all
-//     row tiles, whose A chunks follow; every consumer warp keeps the accumulators of its (<= 4) row tiles in
+//   * chunk-major order: per chunk of CHB * 8 columns one B chunk (rows of the current block column) is shared by
+//     all row tiles, whose A chunks follow; every updating warp keeps the accumulators of its (<= 4) row tiles in
 //     registers across the chunks;
 //   * per step ONE consumer warp (rotating) factors the diagonal tile (D) and takes no update work; the other
-//     three consume the ring (the empty barriers count three arrivals); row solves (S) use all four;
-//   * backward substitution: the strip L(blk, :k0) and the inverted diagonal tile of every step arrive through the
-//     same ring, the solving warp rotates as D does.
-// Rings: A (NA slots) and B (NB slots) of 8 KB = two block rows x 8 blocks, a 1.5 KB diagonal-tile ring.
+//     three are the updating ROLES 0..2, role r owns the row tiles 1 + r + 3 m and a PRIVATE ring of A chunks (so a
+//     warp only ever waits for its own operands, and the producer runs ahead by the ring depth for each of them);
+//     the B ring is shared (its empty barriers count three arrivals); row solves (S) use all four warps;
+//   * backward substitution: the strip L(blk, :k0) of every step arrives through the private rings (chunk c to
+//     role c mod 3), the inverted diagonal tile through a small ring of its own; the solving warp rotates as D does.
+// Rings: 3 x NAW A slots and NB B slots of CHB KB (two block rows x CHB blocks), a 1.5 KB diagonal-tile ring.
 // A failed pivot does not stop the pipeline (the copies in flight must land); the molecule is finished with NaNs
 // and reports the pivot.
 // ------------------------------------------------------------------------------------------------
 namespace tma {
 constexpr int NCONS = 4;                        // consumer warps
 constexpr int NTHREADS = 32 * (NCONS + 1);      // + producer warp
-constexpr int CHB = 8;                          // 8 x 8 blocks per chunk and block row (64 columns)
+#ifndef TMA_CHB
+#define TMA_CHB 4
+#endif
+#ifndef TMA_NAW
+#define TMA_NAW 3
+#endif
+constexpr int CHB = TMA_CHB;                    // 8 x 8 blocks per chunk and block row (CHB * 8 columns)
 constexpr int SLOT = 2 * CHB * 64;              // doubles per ring slot
-constexpr int NA = 3, NB = 2, ND = 2;           // ring depths
+constexpr int NROLE = NCONS - 1;                // updating warps per step (one of the four factors the diagonal tile)
+constexpr int NAW = TMA_NAW;                    // slots of the private A ring of each updating role
+constexpr int NA = NROLE * NAW, NB = 2, ND = 2; // ring depths
 constexpr int DSLOT = 3 * 64;                   // diagonal tile: blocks (R,R), (R+1,R), (R+1,R+1)
 constexpr int NBAR = 2 * (NA + NB + ND);
 __host__ __device__ inline size_t smem_doubles(int npa) {
@@ -959,9 +991,21 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 }  // namespace tma
 
-__global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p) {
+#ifndef TMA_MINB
+#define TMA_MINB 3
+#endif
+__global__ void __launch_bounds__(tma::NTHREADS, TMA_MINB) eeq_factor_tma_kernel(Args p) {
    using namespace tma;
-   extern __shared__ __align__(128) double sm[];
+   extern __shared__ __align__(16) double sm[];  // (ring slots: multiples of 4 KB from the base)
+#ifdef TMA_PROF
+   long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // wait full | U total | D | S | fence | syncs | backward | total
+   const long long pf_t0 = clock64();
+#define PF_BEGIN(v) const long long v = clock64()
+#define PF_ADD(i, v) pf[i] += clock64() - v
+#else
+#define PF_BEGIN(v)
+#define PF_ADD(i, v)
+#endif
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int mol = p.perm[blockIdx.x];
    const int64_t off = p.offsets[mol];
@@ -970,7 +1014,7 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
    const int nblk = npa / KB;
    const double charge = p.charge[mol];
    double* S = p.scratch + p.soff[mol];  // fragment-order blocks, S[lay(i, j)]
-   double* ringA = sm;
+   double* ringA = sm;                   // [role][NAW] slots
    double* ringB = ringA + NA * SLOT;
    double* ringD = ringB + NB * SLOT;
    double* Cb = ringD + ND * DSLOT;      // block column buffer, ABSOLUTE rows: Cb[swz(row, c)]; later b0 | b1
@@ -987,11 +1031,12 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
             *emptyD = fullD + ND;
    __shared__ int sfail;
    __shared__ int steps_done;  // factor steps whose row solves are complete and visible to the bulk copies
+   if (p.status[mol] < 0) return;  // rejected by pair phase A (atomic number outside the model)
    if (tid == 0) {
       sfail = 0;
       steps_done = 0;
-      for (int i = 0; i < NA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, NCONS - 1); }
-      for (int i = 0; i < NB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, NCONS - 1); }
+      for (int i = 0; i < NA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 1); }
+      for (int i = 0; i < NB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, NROLE); }
       for (int i = 0; i < ND; ++i) { mbar_init(fullD + i, 1); mbar_init(emptyD + i, 1); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async;" ::: "memory");
@@ -1005,11 +1050,13 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
       }
    }
    __syncthreads();
+   // row tiles of role r among the tiles 1 .. nrt-1
+   auto tiles_of = [](int nrt, int r) { return (nrt - 1 > r) ? (nrt - 1 - r + NROLE - 1) / NROLE : 0; };
 
    // =================================== producer ===================================
    if (warp == NCONS) {
       if (lane != 0) return;
-      unsigned ia = 0, ib = 0, id = 0;
+      unsigned ia[NROLE] = {0, 0, 0}, ib = 0, id = 0;
       auto wait_steps = [&](int want) {
          for (unsigned spin = 0;; ++spin) {
             int v;
@@ -1018,14 +1065,18 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
             if (spin > (1u << 26)) __trap();
          }
       };
-      // one 64-column chunk of the two block rows R, R + 1 (blocks cb0 .. of each row, as far as the row has them up
-      // to block `lim`, exclusive) into a ring slot
-      auto load_chunk = [&](double* slot, uint64_t* full, int R, int cb0, int lim0, int lim1) {
-         const int nb0 = min(CHB, lim0 - cb0), nb1 = min(CHB, lim1 - cb0);
-         const unsigned bytes = (unsigned)((max(nb0, 0) + max(nb1, 0)) * 512);
-         mbar_expect_tx(full, bytes);
-         if (nb0 > 0) bulk_load(slot, S + 64 * (tri(R) + cb0), (unsigned)(nb0 * 512), full);
-         if (nb1 > 0) bulk_load(slot + CHB * 64, S + 64 * (tri(R + 1) + cb0), (unsigned)(nb1 * 512), full);
+      // one chunk of the two block rows R, R + 1 (blocks cb0 .. cb0 + CHB of each row, below block `lim`) into a slot
+      auto load_chunk = [&](double* slot, uint64_t* full, int R, int cb0, int lim) {
+         const int nb = min(CHB, lim - cb0);
+         mbar_expect_tx(full, (unsigned)(2 * nb * 512));
+         bulk_load(slot, S + 64 * (tri(R) + cb0), (unsigned)(nb * 512), full);
+         bulk_load(slot + CHB * 64, S + 64 * (tri(R + 1) + cb0), (unsigned)(nb * 512), full);
+      };
+      auto load_a = [&](int role, int R, int cb0, int lim) {
+         const unsigned slot = role * NAW + ia[role] % NAW, use = ia[role] / NAW;
+         if (use > 0) mbar_wait(emptyA + slot, (use - 1) & 1);
+         load_chunk(ringA + slot * SLOT, fullA + slot, R, cb0, lim);
+         ++ia[role];
       };
       for (int k0 = 2 * KB; k0 < npa; k0 += KB) {  // factor steps with an old part: columns [0, k0 - 16)
          const int nrt = (npa - k0) / KB;
@@ -1037,15 +1088,10 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
             {
                const unsigned slot = ib % NB, use = ib / NB;
                if (use > 0) mbar_wait(emptyB + slot, (use - 1) & 1);
-               load_chunk(ringB + slot * SLOT, fullB + slot, k0 >> 3, cb0, kob, kob);
+               load_chunk(ringB + slot * SLOT, fullB + slot, k0 >> 3, cb0, kob);
                ++ib;
             }
-            for (int ti = 1; ti < nrt; ++ti) {
-               const unsigned slot = ia % NA, use = ia / NA;
-               if (use > 0) mbar_wait(emptyA + slot, (use - 1) & 1);
-               load_chunk(ringA + slot * SLOT, fullA + slot, (k0 + KB * ti) >> 3, cb0, kob, kob);
-               ++ia;
-            }
+            for (int ti = 1; ti < nrt; ++ti) load_a((ti - 1) % NROLE, (k0 + KB * ti) >> 3, cb0, kob);
          }
       }
       // backward substitution: per step the diagonal tile (inverse) and the strip L(blk, :k0), highest columns first
@@ -1062,19 +1108,15 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
             bulk_load(d + 64, S + 64 * (tri(R + 1) + R), 1024, fullD + slot);
             ++id;
          }
-         for (int cb0 = ((R - 1) / CHB) * CHB; cb0 >= 0 && R > 0; cb0 -= CHB) {
-            const unsigned slot = ia % NA, use = ia / NA;
-            if (use > 0) mbar_wait(emptyA + slot, (use - 1) & 1);
-            load_chunk(ringA + slot * SLOT, fullA + slot, R, cb0, R, R);
-            ++ia;
-         }
+         const int nchb = (R + CHB - 1) / CHB;
+         for (int c = 0; c < nchb; ++c) load_a(c % NROLE, R, (nchb - 1 - c) * CHB, R);
       }
       return;
    }
 
    // =================================== consumers ===================================
    const int g = lane >> 2, t = lane & 3;
-   unsigned ia = 0, ib = 0, id = 0;  // ring positions, in lockstep with the producer
+   unsigned ia0 = 0, ia1 = 0, ia2 = 0, ib = 0, id = 0;  // ring positions, in lockstep with the producer
    for (int k0 = 0; k0 < npa; k0 += KB) {
       const int nrt = (npa - k0) / KB;
       const int kob = (nrt > 1 && k0 >= 2 * KB) ? (k0 - KB) >> 3 : 0;
@@ -1083,7 +1125,9 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
       if (warp == dwarp) {
          // ---- D: diagonal tile, Cholesky + inverse; the inverse goes to global in place of the block ----
          const bool last = (k0 + KB == npa);
+         PF_BEGIN(td);
          const int bad = diag_factor_inv(T, Li, cbuf, rbuf, dvec, lane, last ? KB - 2 : KB, last);
+         PF_ADD(2, td);
          if (bad && lane == 0 && sfail == 0) sfail = k0 + bad;
          __syncwarp();
          const int r = lane & 15, h = lane >> 4;
@@ -1096,17 +1140,41 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
             wl[lane] = (lane < KB - 2) ? T[(KB - 2) * TS + lane] : 0.0;
             wl[KB + lane] = (lane < KB - 2) ? T[(KB - 1) * TS + lane] : 0.0;
          }
-         ia += (unsigned)(nch * (nrt - 1));
-         ib += (unsigned)nch;
+      } else if (k0 == 0) {
+         // ---- first block column: nothing to its left, the row tiles are the original entries ----
+         const int idx = (warp - dwarp - 1) & 3;
+         for (int ti = 1 + idx; ti < nrt; ti += NROLE) {
+            const int i0 = KB * ti;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+               for (int ntl = 0; ntl < 2; ++ntl) {
+                  const double* src = S + lay(i0 + 8 * mt + g, 8 * ntl + 2 * t);
+                  *reinterpret_cast<double2*>(Cb + swz(i0 + 8 * mt + g, 8 * ntl + 2 * t)) = make_double2(src[0], src[2]);
+               }
+         }
+         if (idx == 0 && nrt > 1) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+               for (int ntl = 0; ntl < 2; ++ntl) {
+                  const int lr = 8 * mt + g, lc = 8 * ntl + 2 * t;
+                  const double* src = S + lay(KB + lr, KB + ((lc <= lr) ? lc : 0));
+                  T2[lr * TS + lc] = (lc <= lr) ? src[0] : 0.0;
+                  T2[lr * TS + lc + 1] = (lc + 1 <= lr) ? src[2] : 0.0;
+               }
+         }
       } else if (nrt > 1) {
          // ---- U: left-looking update of the row tiles ti = 1 + idx + 3 m of this block column (and, with tile 1, of
-         //      the next diagonal tile -> T2); idx = position among the three updating warps ----
+         //      the next diagonal tile -> T2); idx = role of this warp among the three updating warps ----
          const int idx = (warp - dwarp - 1) & 3;
+         unsigned mya = (idx == 0) ? ia0 : ((idx == 1) ? ia1 : ia2);
+         PF_BEGIN(tu);
          double acc[4][2][2][2], acc0[2][2][2];
          // original entries first: their loads overlap the wait for the first chunk
 #pragma unroll
          for (int m = 0; m < 4; ++m) {
-            const int ti = 1 + idx + 3 * m;
+            const int ti = 1 + idx + NROLE * m;
             const int i0 = k0 + KB * ti;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
@@ -1122,60 +1190,57 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
                   }
                }
          }
-         if (idx == 0) {  // next diagonal tile, rows and columns k0 + 16 ..
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-               for (int ntl = 0; ntl < 2; ++ntl) {
-                  const int row = k0 + KB + 8 * mt + g, col = k0 + KB + 8 * ntl + 2 * t;
-                  const double* src = S + lay(row, (col <= row) ? col : k0 + KB);
-                  acc0[mt][ntl][0] = (col <= row) ? -src[0] : 0.0;
-                  acc0[mt][ntl][1] = (col + 1 <= row) ? -src[2] : 0.0;
-               }
-         }
+            for (int ntl = 0; ntl < 2; ++ntl) {  // next diagonal tile, rows and columns k0 + 16 .. (role 0 only)
+               const int row = k0 + KB + 8 * mt + g, col = k0 + KB + 8 * ntl + 2 * t;
+               const double* src = S + lay(row, (col <= row) ? col : k0 + KB);
+               acc0[mt][ntl][0] = (idx == 0 && col <= row) ? -src[0] : 0.0;
+               acc0[mt][ntl][1] = (idx == 0 && col + 1 <= row) ? -src[2] : 0.0;
+            }
          // old part: columns [0, k0 - 16) through the rings
          for (int c = 0; c < nch; ++c) {
             const int nb = min(CHB, kob - c * CHB);
             const unsigned sb = ib % NB;
+            PF_BEGIN(tw);
             mbar_wait(fullB + sb, (ib / NB) & 1);
+            PF_ADD(0, tw);
             const double2* Bs = reinterpret_cast<const double2*>(ringB + sb * SLOT) + lane;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-#pragma unroll
-               for (int sub = 0; sub < 3; ++sub) {
-                  const int ti = 1 + 3 * m + sub;
-                  if (ti < nrt) {
-                     const unsigned sl = ia % NA;
-                     mbar_wait(fullA + sl, (ia / NA) & 1);
-                     if (sub == idx) {
-                        const double2* As = reinterpret_cast<const double2*>(ringA + sl * SLOT) + lane;
-                        for (int b = 0; b < nb; ++b) {
-                           const double2 a0 = As[32 * b], a1 = As[32 * (CHB + b)];
-                           const double2 c0 = Bs[32 * b], c1 = Bs[32 * (CHB + b)];
-                           dmma884(acc[m][0][0][0], acc[m][0][0][1], a0.x, c0.x);
-                           dmma884(acc[m][0][1][0], acc[m][0][1][1], a0.x, c1.x);
-                           dmma884(acc[m][1][0][0], acc[m][1][0][1], a1.x, c0.x);
-                           dmma884(acc[m][1][1][0], acc[m][1][1][1], a1.x, c1.x);
-                           dmma884(acc[m][0][0][0], acc[m][0][0][1], a0.y, c0.y);
-                           dmma884(acc[m][0][1][0], acc[m][0][1][1], a0.y, c1.y);
-                           dmma884(acc[m][1][0][0], acc[m][1][0][1], a1.y, c0.y);
-                           dmma884(acc[m][1][1][0], acc[m][1][1][1], a1.y, c1.y);
-                           if (m == 0 && sub == 0) {  // tile 1 with itself: the next diagonal tile
-                              dmma884(acc0[0][0][0], acc0[0][0][1], a0.x, a0.x);
-                              dmma884(acc0[0][1][0], acc0[0][1][1], a0.x, a1.x);
-                              dmma884(acc0[1][0][0], acc0[1][0][1], a1.x, a0.x);
-                              dmma884(acc0[1][1][0], acc0[1][1][1], a1.x, a1.x);
-                              dmma884(acc0[0][0][0], acc0[0][0][1], a0.y, a0.y);
-                              dmma884(acc0[0][1][0], acc0[0][1][1], a0.y, a1.y);
-                              dmma884(acc0[1][0][0], acc0[1][0][1], a1.y, a0.y);
-                              dmma884(acc0[1][1][0], acc0[1][1][1], a1.y, a1.y);
-                           }
-                        }
+               const int ti = 1 + idx + NROLE * m;
+               if (ti < nrt) {
+                  const unsigned sl = idx * NAW + mya % NAW;
+                  PF_BEGIN(tw2);
+                  mbar_wait(fullA + sl, (mya / NAW) & 1);
+                  PF_ADD(0, tw2);
+                  const double2* As = reinterpret_cast<const double2*>(ringA + sl * SLOT) + lane;
+                  for (int b = 0; b < nb; ++b) {
+                     const double2 a0 = As[32 * b], a1 = As[32 * (CHB + b)];
+                     const double2 c0 = Bs[32 * b], c1 = Bs[32 * (CHB + b)];
+                     dmma884(acc[m][0][0][0], acc[m][0][0][1], a0.x, c0.x);
+                     dmma884(acc[m][0][1][0], acc[m][0][1][1], a0.x, c1.x);
+                     dmma884(acc[m][1][0][0], acc[m][1][0][1], a1.x, c0.x);
+                     dmma884(acc[m][1][1][0], acc[m][1][1][1], a1.x, c1.x);
+                     dmma884(acc[m][0][0][0], acc[m][0][0][1], a0.y, c0.y);
+                     dmma884(acc[m][0][1][0], acc[m][0][1][1], a0.y, c1.y);
+                     dmma884(acc[m][1][0][0], acc[m][1][0][1], a1.y, c0.y);
+                     dmma884(acc[m][1][1][0], acc[m][1][1][1], a1.y, c1.y);
+                     if (m == 0 && idx == 0) {  // tile 1 with itself: the next diagonal tile
+                        dmma884(acc0[0][0][0], acc0[0][0][1], a0.x, a0.x);
+                        dmma884(acc0[0][1][0], acc0[0][1][1], a0.x, a1.x);
+                        dmma884(acc0[1][0][0], acc0[1][0][1], a1.x, a0.x);
+                        dmma884(acc0[1][1][0], acc0[1][1][1], a1.x, a1.x);
+                        dmma884(acc0[0][0][0], acc0[0][0][1], a0.y, a0.y);
+                        dmma884(acc0[0][1][0], acc0[0][1][1], a0.y, a1.y);
+                        dmma884(acc0[1][0][0], acc0[1][0][1], a1.y, a0.y);
+                        dmma884(acc0[1][1][0], acc0[1][1][1], a1.y, a1.y);
                      }
-                     __syncwarp();
-                     if (lane == 0) mbar_arrive(emptyA + sl);
-                     ++ia;
                   }
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(emptyA + sl);
+                  ++mya;
                }
             }
             __syncwarp();
@@ -1183,7 +1248,7 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
             ++ib;
          }
          // newest part: block column k0 - 16, whose rows (L after the row solves) are still in Cb
-         if (k0 >= KB) {
+         {
             double bn[4][2];  // rows k0 .. k0 + 15 of it: the B operand of every tile
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -1193,7 +1258,7 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
             }
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-               const int ti = 1 + idx + 3 * m;
+               const int ti = 1 + idx + NROLE * m;
                if (ti < nrt) {
                   const int i0 = k0 + KB * ti;
 #pragma unroll
@@ -1218,7 +1283,7 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
          // acc = L L^T - A: store the negative into Cb (own rows) / T2
 #pragma unroll
          for (int m = 0; m < 4; ++m) {
-            const int ti = 1 + idx + 3 * m;
+            const int ti = 1 + idx + NROLE * m;
             if (ti < nrt) {
                const int i0 = k0 + KB * ti;
 #pragma unroll
@@ -1239,8 +1304,16 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
                   T2[lr * TS + lc + 1] = (lc + 1 <= lr) ? -acc0[mt][ntl][1] : 0.0;
                }
          }
+         PF_ADD(1, tu);
       }
+      ia0 += (unsigned)(nch * tiles_of(nrt, 0));
+      ia1 += (unsigned)(nch * tiles_of(nrt, 1));
+      ia2 += (unsigned)(nch * tiles_of(nrt, 2));
+      if (warp == dwarp || k0 == 0 || nrt <= 1) ib += (unsigned)nch;  // (updating warps counted their B chunks above)
+      PF_BEGIN(ts1);
       cons_sync();
+      PF_ADD(5, ts1);
+      PF_BEGIN(tsp);
       // ---- S: rows below the diagonal tile, L(i, blk) = Cb(i, :) inv(L_kk)^T, to the scratch AND back into Cb (the
       //      newest part of the next step); the warp of the first tile also completes the next diagonal tile ----
       for (int ti = 1 + warp; ti < nrt; ti += NCONS) {
@@ -1291,13 +1364,19 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
                }
          }
       }
+      PF_ADD(3, tsp);
       // what this step wrote to the scratch must be visible to the bulk copies (async proxy) the producer issues next
+      PF_BEGIN(tf);
       asm volatile("fence.proxy.async;" ::: "memory");
+      PF_ADD(4, tf);
+      PF_BEGIN(ts2);
       cons_sync();
+      PF_ADD(5, ts2);
       if (tid == 0) asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(sa(&steps_done)), "r"((k0 >> 4) + 1) : "memory");
    }
 
    // ---- backward substitution L^T [y z] = [w_x w_1], right-looking by blocks; Cb is free now: b0 | b1 ----
+   PF_BEGIN(tbw);
    double* b0 = Cb;
    double* b1 = Cb + npa;
    {
@@ -1311,7 +1390,7 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
    for (int k0 = npa - KB; k0 >= 0; k0 -= KB) {
       const int R = k0 >> 3;
       const int solver = (blockIdx.x + (k0 >> 4)) & 3;
-      const int nchb = (R > 0) ? (R - 1) / CHB + 1 : 0;
+      const int nchb = (R + CHB - 1) / CHB;
       if (warp == solver) {  // y_blk = inv(L_kk)^T w_blk ; lane = (r, rhs h); inverse tile from the diagonal ring
          const unsigned sd = id % ND;
          mbar_wait(fullD + sd, (id / ND) & 1);
@@ -1332,16 +1411,17 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
       }
       ++id;
       cons_sync();
-      if (warp != solver) {  // w(:k0) -= L(blk, :k0)^T y_blk ; blocks of 8 columns dealt to the three warps
+      if (warp != solver) {  // w(:k0) -= L(blk, :k0)^T y_blk ; chunk c (highest columns first) goes to role c mod 3
          const int idx = (warp - solver - 1) & 3;
+         unsigned mya = (idx == 0) ? ia0 : ((idx == 1) ? ia1 : ia2);
          const int cc = lane & 7, rg = lane >> 3;  // column within the block, group of 4 rows
-         for (int c = 0; c < nchb; ++c) {
-            const int cb0 = ((R - 1) / CHB) * CHB - c * CHB;  // highest columns first
+         for (int c = idx; c < nchb; c += NROLE) {
+            const int cb0 = (nchb - 1 - c) * CHB;
             const int nb = min(CHB, R - cb0);
-            const unsigned sl = ia % NA;
-            mbar_wait(fullA + sl, (ia / NA) & 1);
+            const unsigned sl = idx * NAW + mya % NAW;
+            mbar_wait(fullA + sl, (mya / NAW) & 1);
             const double* As = ringA + sl * SLOT;
-            for (int b = idx; b < nb; b += 3) {
+            for (int b = 0; b < nb; ++b) {
                double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                for (int q = 0; q < 4; ++q) {
@@ -1362,13 +1442,21 @@ __global__ void __launch_bounds__(tma::NTHREADS, 3) eeq_factor_tma_kernel(Args p
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(emptyA + sl);
-            ++ia;
+            ++mya;
          }
-      } else {
-         ia += (unsigned)nchb;
       }
+      ia0 += (unsigned)((nchb + NROLE - 1) / NROLE);
+      ia1 += (unsigned)((nchb + NROLE - 2) / NROLE);
+      ia2 += (unsigned)((nchb + NROLE - 3) / NROLE);
       cons_sync();
    }
+   PF_ADD(6, tbw);
+#ifdef TMA_PROF
+   pf[7] = clock64() - pf_t0;
+   if (lane == 0 && blockIdx.x % 1000 == 7)
+      printf("[tma] blk %d n %d npa %d warp %d: wait_full %lld U %lld D %lld S %lld fence %lld syncs %lld backward %lld total %lld\n",
+             (int)blockIdx.x, n, npa, warp, pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], pf[7]);
+#endif
    const int bad = sfail;
    if (bad) {
       const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -1426,7 +1514,7 @@ static void launch_factor_groups(mchrg_b200_context* ctx, const Args& a, const i
    constexpr int NCLASS = NP_MAX / KB;
    // (the TMA-fed kernel's shared memory grows with the class: three groups keep small molecules at high residency)
    const char* fkind = std::getenv("MCHRG_B200_FACTOR");
-   const int group = (int)std::max<long long>(1, env_ll("MCHRG_B200_FACTOR_GROUP", (fkind && fkind[0] == 'l') ? 13 : 4));
+   const int group = (int)std::max<long long>(1, env_ll("MCHRG_B200_FACTOR_GROUP", (fkind && fkind[0] == 't') ? 4 : 13));
    for (int chi = NCLASS; chi >= 1; chi -= group) {  // perm holds the classes in descending order
       const int clo = std::max(1, chi - group + 1);
       int count = 0;
@@ -1435,10 +1523,10 @@ static void launch_factor_groups(mchrg_b200_context* ctx, const Args& a, const i
       Args b = a;
       b.np = NPA_MAX;
       b.perm = dperm + cls_start[chi];
-      // MCHRG_B200_FACTOR = ll: the L2-latency-bound version above (A/B timing)
+      // MCHRG_B200_FACTOR = tma: the TMA-fed variant (measured slower: 16.9 vs 10.1 ms per 100k molecules, see its header)
       const char* fk = std::getenv("MCHRG_B200_FACTOR");
-      if (fk && fk[0] == 'l') launch_factor_ll<LL_NT>(ctx, b, count, std::min(NPA_MAX, KB * (chi + 1)));
-      else launch_factor_tma(ctx, b, count, std::min(NPA_MAX, KB * (chi + 1)));
+      if (fk && fk[0] == 't') launch_factor_tma(ctx, b, count, std::min(NPA_MAX, KB * (chi + 1)));
+      else launch_factor_ll<LL_NT>(ctx, b, count, std::min(NPA_MAX, KB * (chi + 1)));
    }
 }
 

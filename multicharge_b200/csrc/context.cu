@@ -137,7 +137,9 @@ int mchrg_b200_context_create(int device, mchrg_b200_context** out) {
       MCHRG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo));
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, prio_hi));
-      MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_hi2, cudaStreamNonBlocking, prio_hi));
+      // second priority stream: between the critical-path stream and the bulk work when the device has a level for it
+      MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_hi2, cudaStreamNonBlocking,
+                                              (prio_lo - prio_hi >= 2) ? (prio_hi + prio_lo) / 2 : prio_hi));
       MCHRG_CUDA(cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, prio_lo));
       MCHRG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
       MCHRG_CUDA(cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));

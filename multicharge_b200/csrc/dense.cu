@@ -335,8 +335,9 @@ namespace leaf {
 constexpr int N = 128, T16 = 16, NTL = N / T16, TLD = 20, TSZ = T16 * TLD;
 constexpr int THREADS = 256, NW = THREADS / 32;
 constexpr int NTRI = NTL * (NTL + 1) / 2;
-// doubles: L tiles (lower block triangle) | diagonal tiles of the inverse | product scratch (16 tiles) | D scratch
-constexpr size_t SMEM_BYTES = ((size_t)(NTRI + NTL + 16) * TSZ + 2 * d16::CBW + 2 * T16 + T16) * sizeof(double);
+// doubles: L tiles (lower block triangle) | diagonal tiles of the inverse | D scratch.  113 KB, so that the leaf can
+// share an SM with one 128 x 64 GEMM CTA (108 KB) of the update streams instead of waiting for an empty SM.
+constexpr size_t SMEM_BYTES = ((size_t)(NTRI + NTL) * TSZ + 2 * d16::CBW + 2 * T16 + T16) * sizeof(double);
 __device__ __forceinline__ int tix(int R, int C) { return R * (R + 1) / 2 + C; }
 
 // acc += A B^T for 16 x 16 tiles (row stride TLD): D[m][n] = sum_c A[m][c] B[n][c]
@@ -393,8 +394,7 @@ potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv
    extern __shared__ __align__(16) double smem[];
    double* Lt = smem;               // tile (R, C), R >= C, at tix(R, C) * TSZ; later the off-diagonal tiles of inv(L)
    double* Xd = Lt + NTRI * TSZ;    // diagonal tiles of inv(L)
-   double* Ts = Xd + NTL * TSZ;     // products L21 X11 of the inversion
-   double* cbuf = Ts + 16 * TSZ;
+   double* cbuf = Xd + NTL * TSZ;
    double* rbuf = cbuf + 2 * d16::CBW;
    double* dvec = rbuf + 2 * T16;
    __shared__ int sfail;
@@ -480,24 +480,33 @@ potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv
       if (r >= c) W[r + (int64_t)c * ldw] = Lt[tix(r >> 4, c >> 4) * TSZ + (r & 15) * TLD + (c & 15)];
    }
    LEAF_TICK(4);
-   // inverse: blocks of h tiles are merged pairwise, X21 = -X22 (L21 X11); tile (R, C) of X: Xd when R == C
+   // inverse: blocks of h tiles are merged pairwise, X21 = -X22 (L21 X11); tile (R, C) of X: Xd when R == C.
+   // The products T = L21 X11 go to the eight DIAGONAL tiles of Lt (dead once L is published: the diagonal tiles of
+   // the inverse live in Xd); the last level (16 product tiles) runs as two passes over column halves -- the first
+   // pass reads all of L21 and overwrites only its first two tile columns, which the second pass no longer needs.
+   __syncthreads();  // the diagonal tiles of Lt are read by the publishing loop above
    auto xt = [&](int R, int C) -> const double* { return (R == C) ? Xd + R * TSZ : Lt + tix(R, C) * TSZ; };
+   auto ts = [&](int slot) -> double* { return Lt + tix(slot, slot) * TSZ; };
    for (int h = 1; h < NTL; h *= 2) {
-      const int nitems = (NTL / 2) * h, hh = h * h;  // (pair p, tile row i, tile column j) of the h x h tile block X21
-      for (int item = warp; item < nitems; item += NW) {
-         const int p = item / hh, i = (item % hh) / h, j = item % h, b0 = 2 * h * p;
-         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-         for (int k = j; k < h; ++k) mma_nn(acc, Lt + tix(b0 + h + i, b0 + k) * TSZ, xt(b0 + k, b0 + j), g, t);
-         put(Ts + item * TSZ, acc, 1.0, g, t);
+      const int jw = (h < 2) ? h : 2, npass = h / jw;  // tile columns of X21 per pass
+      const int per = h * jw, nitems = (NTL / (2 * h)) * per;  // (pair p, tile row i, tile column j) per pass
+      for (int pass = 0; pass < npass; ++pass) {
+         const int jb = pass * jw;
+         for (int item = warp; item < nitems; item += NW) {
+            const int p = item / per, i = (item % per) / jw, j = jb + item % jw, b0 = 2 * h * p;
+            double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+            for (int k = j; k < h; ++k) mma_nn(acc, Lt + tix(b0 + h + i, b0 + k) * TSZ, xt(b0 + k, b0 + j), g, t);
+            put(ts(item), acc, 1.0, g, t);
+         }
+         __syncthreads();
+         for (int item = warp; item < nitems; item += NW) {
+            const int p = item / per, i = (item % per) / jw, jl = item % jw, b0 = 2 * h * p;
+            double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+            for (int k = 0; k <= i; ++k) mma_nn(acc, xt(b0 + h + i, b0 + h + k), ts(p * per + k * jw + jl), g, t);
+            put(Lt + tix(b0 + h + i, b0 + jb + jl) * TSZ, acc, -1.0, g, t);
+         }
+         __syncthreads();
       }
-      __syncthreads();
-      for (int item = warp; item < nitems; item += NW) {
-         const int p = item / hh, i = (item % hh) / h, j = item % h, b0 = 2 * h * p;
-         double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-         for (int k = 0; k <= i; ++k) mma_nn(acc, xt(b0 + h + i, b0 + h + k), Ts + (p * hh + k * h + j) * TSZ, g, t);
-         put(Lt + tix(b0 + h + i, b0 + j) * TSZ, acc, -1.0, g, t);
-      }
-      __syncthreads();
    }
    LEAF_TICK(5);
    for (int e = tid; e < N * N; e += THREADS) {
@@ -621,14 +630,14 @@ static int64_t dist_group_width(const mchrg_b200_context* ctx, int64_t n) {
    // MCHRG_B200_DIST_GROUP: columns per ownership group (multiple of the sub-panel width)
    int64_t db = env_ll("MCHRG_B200_DIST_GROUP", 512) / TILE * TILE;
    // every rank should own at least two groups
-   while (db > TILE && n / db < 2 * (int64_t)ctx->comm->nranks) db -= TILE;
+   while (db > TILE && n / db < 2 * (int64_t)ctx->nranks()) db -= TILE;
    return std::max<int64_t>(db, TILE);
 }
 int64_t dpotrf_dist_panel(const mchrg_b200_context* ctx, int64_t n) { return dist_applies(ctx, n) ? dist_group_width(ctx, n) : 0; }
 
 static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, double* dinv, int* info, int64_t aug_end) {
-   Comm* cm = ctx->comm;
-   const int R = cm->nranks, me = cm->rank;
+   Comm* cm = ctx->comm;  // nullptr: one GPU, the same schedule without the broadcasts
+   const int R = cm ? cm->nranks : 1, me = cm ? cm->rank : 0;
    const int64_t DB = dist_group_width(ctx, n), PW = TILE;  // sub-panels are one 128 x 128 leaf wide
    const int ngrp = (int)((n + DB - 1) / DB);
    const int nsub = (int)(n / PW), spg = (int)(DB / PW);  // sub-panels in all / per group
@@ -745,17 +754,19 @@ static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t l
             wait(C, tailB[s]);
          }
          // sub-panel from its diagonal element to the end of its last column (one contiguous range) + inverted block
-         tic(C, 2);
-         cm->group_begin();
-         cm->bcast(D, (size_t)(((PW - 1) * ldw + (n - c0)) * sizeof(double)), owner(g), C);
-         cm->bcast(dinv_k, (size_t)(TILE * TILE * sizeof(double)), owner(g), C);
-         cm->group_end();
-         toc(C);
-         cudaEvent_t e_arr = rec(C);
-         if (!mine) headE[s] = tailB[s] = e_arr;
+         if (cm) {
+            tic(C, 2);
+            cm->group_begin();
+            cm->bcast(D, (size_t)(((PW - 1) * ldw + (n - c0)) * sizeof(double)), owner(g), C);
+            cm->bcast(dinv_k, (size_t)(TILE * TILE * sizeof(double)), owner(g), C);
+            cm->group_end();
+            toc(C);
+            cudaEvent_t e_arr = rec(C);
+            if (!mine) headE[s] = tailB[s] = e_arr;
+         }
          if (rem == 0) break;
          if (mine && s + 1 < s1) eager(s, s + 1, s1, 3);   // the rest of this group
-         if (next_mine) eager(s, h0, h1, 4);               // the group this rank factors next
+         if (next_mine && h0 < h1) eager(s, h0, h1, 4);    // the group this rank factors next
       }
       // bulk: all owned groups behind the next one, with the whole group g at once (rank-gw update); the first of
       // them -- the next one this rank will have to factor -- as its own launch
@@ -801,6 +812,7 @@ static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t l
          cudaEventDestroy(sp.b);
       }
    }
+   if (!cm) return;
    // every rank reports the same pivot failure
    double* slots = ctx->alloc<double>((size_t)R);
    MCHRG_LAUNCH(ctx, info_to_slot_kernel, 1, 1, 0, info, me, R, slots);
@@ -816,6 +828,12 @@ void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, d
    int64_t PANEL = env_ll("MCHRG_B200_PANEL", 256);  // tuning knob (multiple of 128); default chosen on B200 at n = 16384
    if (PANEL < TILE || PANEL % TILE) PANEL = 256;
    if (dist_applies(ctx, n)) {  // large system on several GPUs
+      dpotrf_dist(ctx, n, W, ldw, dinv, info, aug_end);
+      return;
+   }
+   // MCHRG_B200_POTRF=tracked: the schedule of the distributed factorisation on one GPU (critical path of leaf + two
+   // small-tile products on its own stream), for A/B timing against the two-stream look-ahead below
+   if (env_ll("MCHRG_B200_POTRF_TRACKED", 0) > 0 && n >= 8 * TILE && ctx->active == ctx->stream) {
       dpotrf_dist(ctx, n, W, ldw, dinv, info, aug_end);
       return;
    }

@@ -234,3 +234,43 @@ def test_batch_full_size_properties(mc):
     assert np.abs(r2["qvec"] - r["qvec"][idx]).max() < 1e-11
     assert np.abs(r2["energy"] - r["energy"][idx]).max() < 1e-11
     assert np.abs(r2["gradient"] - (r["gradient"] @ rot.T)[idx]).max() < 1e-10
+
+
+@pytest.mark.parametrize("mode", ["fused", "split"])
+def test_batch_rejects_atomic_numbers_outside_the_model(mc, monkeypatch, mode):
+    """An atomic number the model has no species for is reported per molecule (MCHRG_B200_ERR_ARG = -1, NaN outputs)
+    instead of reading a neighbouring parameter slot; the other molecules of the batch are unaffected."""
+    from synth import batch
+    monkeypatch.setenv("MCHRG_B200_BATCH_MODE", mode)
+    offsets, num, xyz, charge = batch(40, 3, 10, 60)
+    model = mc.new_eeq2019_batch_model()
+    good = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    bad_num = num.copy()
+    bad_num[offsets[7] + 2] = 0
+    bad_num[offsets[21]] = 104
+    out = mc.singlepoint_batch(model, offsets, bad_num, xyz, charge)
+    st = out["status"]
+    assert st[7] == -1 and st[21] == -1 and int((st != 0).sum()) == 2
+    assert np.all(np.isnan(out["qvec"][offsets[7]:offsets[8]]))
+    ok = np.ones(len(num), dtype=bool)
+    ok[offsets[7]:offsets[8]] = False
+    ok[offsets[21]:offsets[22]] = False
+    for key in ("qvec", "energy"):
+        assert np.array_equal(out[key][ok], good[key][ok])
+
+
+def test_get_charges_fast_path_agrees_with_general_path_on_failed_pivot(mc, monkeypatch):
+    """Two H atoms 0.5 Bohr apart: the Coulomb block is indefinite on the charge-conserving subspace.  The one-launch
+    get_charges route must not report anything the general route does not (it falls back to it)."""
+    mol = mc.Structure(np.array([1, 1]), np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 0.5]]), 0.0)
+    model = mc.new_eeq2019_model(mol)
+    res = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("MCHRG_B200_SMALL_FUSED", fused)
+        try:
+            res.append(("ok", mc.get_charges(model, mol)))
+        except mc.FactorizationError as exc:
+            res.append(("fail", exc.info))
+    assert res[0][0] == res[1][0]
+    if res[0][0] == "ok":
+        assert np.abs(res[0][1] - res[1][1]).max() < 1e-12

@@ -110,11 +110,30 @@ def test_medium_cluster_full_path(mc, oracle):
         assert np.abs(r[key] - o[key]).max() < TOL * max(1.0, np.abs(o[key]).max()), key
 
 
-def test_not_positive_definite_is_reported(mc):
-    """Two hydrogens 0.5 Bohr apart make the Coulomb block indefinite (SURVEY 7 'hard parts'):
-    the reference's LDL^T would go on; we report the failed pivot like fatal_error would."""
-    mol = mc.Structure([1, 1], [[0, 0, 0], [0.5, 0, 0]], 0.0)
-    model = mc.new_eeq2019_model(mol)
+@pytest.mark.parametrize("nat", [2, 40, 300])
+def test_indefinite_coulomb_block_is_solved_like_dsytrf(mc, oracle, monkeypatch, nat):
+    """Two hydrogens 0.5 Bohr apart make the Coulomb block indefinite on the charge-conserving subspace as well
+    (SURVEY 7 'hard parts').  The reference's Bunch-Kaufman LDL^T (lapack.F90:165-201) factors the bordered matrix
+    anyway; here the shifted Cholesky attempts fail and the solver falls back to the normal equations of the bordered
+    system (api.cu, factor_solve).  Charges, energy, gradient and sigma against the oracle (dsytrf / dsytrs); dq/dr is
+    refused on that route; with the fallback switched off the failed pivot is reported like fatal_error would."""
+    from synth import cluster
+    if nat == 2:
+        num, xyz = np.array([1, 1]), np.array([[0.0, 0.0, 0.0], [0.5, 0.0, 0.0]])
+    else:
+        num, xyz = cluster(nat, 50 + nat)
+        num[:2] = 1
+        xyz[1] = xyz[0] + np.array([0.5, 0.0, 0.0])
+    mol, model, omol, omodel = both(mc, oracle, num, xyz, 0.0)
+    o = oracle.eeq_singlepoint(omodel, omol, want=("qvec", "energy", "gradient"))
+    assert o.stat == 0
+    r = model.singlepoint(mol, want=("qvec", "energy", "gradient"))
+    for key in ("qvec", "energy", "gradient", "sigma"):
+        assert np.abs(r[key] - o[key]).max() < 1e-9 * max(1.0, np.abs(o[key]).max()), key
+    assert abs(r["qvec"].sum()) < 1e-10
+    with pytest.raises(mc.MchrgError):
+        model.singlepoint(mol, want=("qvec", "dqdr"))
+    monkeypatch.setenv("MCHRG_B200_NO_INDEFINITE", "1")
     with pytest.raises(mc.FactorizationError):
         model.singlepoint(mol)
 
