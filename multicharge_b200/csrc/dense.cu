@@ -5,6 +5,8 @@
 // Replaces, on the device: sytrf/sytri/sytrs (lapack.F90:165-363, called from model/type.F90:221-243)
 // and gemm/gemv/symv (blas.F90, called from model/type.F90:235-290).
 #include <cstdio>
+#include <cooperative_groups.h>
+
 #include "dense.cuh"
 #include "erfgauss.cuh"
 #include "diag16.cuh"
@@ -261,12 +263,11 @@ static void dsyrk_cyclic(mchrg_b200_context* ctx, int64_t n, int64_t k, const do
 // block's rows, update of the next diagonal block) are latency, not throughput.
 // C may alias A (the whole 16-row strip of A is read before anything is written).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dgemm_small128_kernel(int k, double alpha, const double* A, int64_t lda,
-                                                             const double* __restrict__ B, int64_t ldb, double beta,
-                                                             double* C, int64_t ldc) {
+// rows [m0, m0 + 16) of C by the 256 threads of one CTA
+__device__ __forceinline__ void small128_strip(int64_t m0, int k, double alpha, const double* A, int64_t lda, const double* B,
+                                               int64_t ldb, double beta, double* C, int64_t ldc) {
    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    const int g = lane >> 2, t = lane & 3;
-   const int64_t m0 = (int64_t)blockIdx.x * 16;
    const int n0 = warp * 16;
    const double* a0p = A + m0 + g + (int64_t)t * lda;   // A(m0 + g [+ 8], kk + t)
    const double* b0p = B + n0 + g + (int64_t)t * ldb;   // B(n0 + g [+ 8], kk + t)
@@ -309,6 +310,12 @@ __global__ void __launch_bounds__(256) dgemm_small128_kernel(int k, double alpha
          c[0] = alpha * acc[mt][nt][0] + beta * cold[mt][nt][0];
          c[ldc] = alpha * acc[mt][nt][1] + beta * cold[mt][nt][1];
       }
+}
+
+__global__ void __launch_bounds__(256) dgemm_small128_kernel(int k, double alpha, const double* A, int64_t lda,
+                                                             const double* B, int64_t ldb, double beta, double* C,
+                                                             int64_t ldc) {
+   small128_strip((int64_t)blockIdx.x * 16, k, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 
 static void dgemm_small128(mchrg_b200_context* ctx, int64_t m, int64_t k, double alpha, const double* A, int64_t lda,
@@ -387,11 +394,9 @@ __device__ __forceinline__ void sub(double* tile, const double (&acc)[2][2][2], 
 }
 }  // namespace leaf
 
-__global__ void __launch_bounds__(leaf::THREADS, 1)
-potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv, int* __restrict__ info,
-                  int pivot_base, int aug) {
+__device__ __forceinline__ void potrf_leaf_body(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv,
+                                                int* __restrict__ info, int pivot_base, int aug, double* smem) {
    using namespace leaf;
-   extern __shared__ __align__(16) double smem[];
    double* Lt = smem;               // tile (R, C), R >= C, at tix(R, C) * TSZ; later the off-diagonal tiles of inv(L)
    double* Xd = Lt + NTRI * TSZ;    // diagonal tiles of inv(L)
    double* cbuf = Xd + NTL * TSZ;
@@ -519,6 +524,41 @@ potrf_leaf_kernel(double* __restrict__ W, int64_t ldw, double* __restrict__ dinv
       printf("[leaf] load %lld first D %lld cholesky loop %lld store L %lld inverse %lld store inv %lld cycles\n", tk[1] - tk[0],
              tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5]);
 #endif
+}
+
+__global__ void __launch_bounds__(leaf::THREADS, 1)
+potrf_leaf_kernel(double* W, int64_t ldw, double* dinv, int* info, int pivot_base, int aug) {
+   extern __shared__ __align__(16) double smem[];
+   potrf_leaf_body(W, ldw, dinv, info, pivot_base, aug, smem);
+}
+
+// One step of the critical path of the tracked (multi-GPU) factorisation as ONE launch of a cluster of 8 CTAs,
+// D = W(c0.., c0..) the diagonal tile of the sub-panel:
+//   phase 0 (pre != nullptr)  D -= P P^T with P = L(rows of D, an arrived sub-panel): the last update the tile waits for
+//   leaf                      CTA 0 factors D and inverts the factor; the others wait at the cluster barrier
+//   phase 1 (do_head)         the tile below: X = W(c0 + 128 .., c0 ..) <- X inv(L)^T        (16 rows per CTA)
+//   phase 2 (do_next)         the next diagonal tile: W(c0 + 128 .., c0 + 128 ..) -= X X^T  (16 rows per CTA)
+// Three dependent launches with their stream-scheduling gaps (~10 us each next to 55 + 3 + 3 us of work) become one;
+// cluster barriers order the phases (release / acquire at cluster scope covers the global-memory hand-over).
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(leaf::THREADS, 1)
+potrf_step_kernel(double* W, int64_t ldw, double* dinv, int* info, int pivot_base, int aug, const double* pre, int do_head,
+                  int do_next) {
+   extern __shared__ __align__(16) double smem[];
+   namespace cg = cooperative_groups;
+   cg::cluster_group cluster = cg::this_cluster();
+   const int64_t r0 = 16 * (int64_t)cluster.block_rank();
+   if (pre != nullptr) {
+      small128_strip(r0, leaf::N, -1.0, pre, ldw, pre, ldw, 1.0, W, ldw);
+      cluster.sync();
+   }
+   if (cluster.block_rank() == 0) potrf_leaf_body(W, ldw, dinv, info, pivot_base, aug, smem);
+   if (!do_head) return;
+   cluster.sync();
+   double* X = W + leaf::N;
+   small128_strip(r0, leaf::N, 1.0, X, ldw, dinv, leaf::N, 0.0, X, ldw);
+   if (!do_next) return;
+   cluster.sync();
+   small128_strip(r0, leaf::N, -1.0, X, ldw, X, ldw, 1.0, W + leaf::N + leaf::N * ldw, ldw);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -679,26 +719,32 @@ static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t l
    cudaEvent_t e_begin = rec(U);  // everything queued on U so far (the assembly)
    std::vector<Touch> last((size_t)3 * nsub, Touch{e_begin, U});
    wait(C, e_begin);
-   auto write = [&](cudaStream_t X, int j0, int j1, int parts, int cat, auto&& launch) {
+   struct Range { int j0, j1, parts; };
+   auto write_multi = [&](cudaStream_t X, std::initializer_list<Range> ranges, int cat, auto&& launch) {
       cudaEvent_t seen = nullptr;
-      for (int j = j0; j < j1; ++j)
-         for (int pt = 0; pt < 3; ++pt)
-            if ((parts >> pt) & 1) {
-               const Touch& tc = last[(size_t)3 * j + pt];
-               if (tc.st != X && tc.ev != seen) {
-                  wait(X, tc.ev);
-                  seen = tc.ev;
+      for (const Range& rg : ranges)
+         for (int j = rg.j0; j < rg.j1; ++j)
+            for (int pt = 0; pt < 3; ++pt)
+               if ((rg.parts >> pt) & 1) {
+                  const Touch& tc = last[(size_t)3 * j + pt];
+                  if (tc.st != X && tc.ev != seen) {
+                     wait(X, tc.ev);
+                     seen = tc.ev;
+                  }
                }
-            }
       StreamScope on(ctx, X);
       tic(X, cat);
       launch();
       toc(X);
       cudaEvent_t e = rec(X);
-      for (int j = j0; j < j1; ++j)
-         for (int pt = 0; pt < 3; ++pt)
-            if ((parts >> pt) & 1) last[(size_t)3 * j + pt] = Touch{e, X};
+      for (const Range& rg : ranges)
+         for (int j = rg.j0; j < rg.j1; ++j)
+            for (int pt = 0; pt < 3; ++pt)
+               if ((rg.parts >> pt) & 1) last[(size_t)3 * j + pt] = Touch{e, X};
       return e;
+   };
+   auto write = [&](cudaStream_t X, int j0, int j1, int parts, int cat, auto&& launch) {
+      return write_multi(X, {Range{j0, j1, parts}}, cat, launch);
    };
    // events after which the factored sub-panel s may be read on this rank: its tile (s+1, s) / its rows below / all of it
    std::vector<cudaEvent_t> headE((size_t)nsub, nullptr), tailB((size_t)nsub, nullptr);
@@ -708,13 +754,22 @@ static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t l
    };
    // Eager (non-bulk) updates of the columns [t0, t1) with the factored sub-panel s.  The diagonal tile of column t0
    // -- the next leaf -- is updated by the small-tile product on P; everything else goes to Q.
-   auto eager = [&](int s, int t0, int t1, int cat) {
+   // The update of the diagonal tile of column t0 -- the next leaf -- is: diag_mode 0 a small-tile product on P now;
+   // 1 already done by the step kernel of sub-panel s (fused); 2 deferred into the step kernel of t0 (its phase 0).
+   std::vector<const double*> pre_ptr((size_t)nsub + 1, nullptr);
+   std::vector<int> pre_src((size_t)nsub + 1, -1);
+   auto eager = [&](int s, int t0, int t1, int cat, int diag_mode) {
       const int64_t c0 = (int64_t)s * PW;
       const int64_t r0 = (int64_t)t0 * PW;               // first row / column of the target range
       const double* Lt0 = W + r0 + c0 * ldw;             // L(rows of tile t0, panel s)
       const bool head_is_E = (t0 == s + 1);              // that tile is the panel's tile (s+1, s), else part of its tail
-      need_panel(P, s, head_is_E, !head_is_E);
-      write(P, t0, t0 + 1, PD, cat, [&]() { dgemm_small128(ctx, PW, PW, -1.0, Lt0, ldw, Lt0, ldw, 1.0, W + r0 + r0 * ldw, ldw); });
+      if (diag_mode == 0) {
+         need_panel(P, s, head_is_E, !head_is_E);
+         write(P, t0, t0 + 1, PD, cat, [&]() { dgemm_small128(ctx, PW, PW, -1.0, Lt0, ldw, Lt0, ldw, 1.0, W + r0 + r0 * ldw, ldw); });
+      } else if (diag_mode == 2) {
+         pre_ptr[t0] = Lt0;
+         pre_src[t0] = s;
+      }
       const int64_t rows2 = n - r0 - PW;                 // rows below the diagonal tile of column t0
       if (rows2 > 0) {
          need_panel(Q, s, head_is_E, true);
@@ -730,6 +785,9 @@ static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t l
          }
       }
    };
+   // (a cluster of 8 CTAs has to be placed at once: on ONE GPU, where the bulk updates keep every SM busy, that wait
+   //  costs more than the two launch gaps it saves -- n = 4096: 4.05 vs 3.34 ms -- so the fusion is for shared systems)
+   const bool fuse = env_ll("MCHRG_B200_DIST_FUSE", cm != nullptr ? 1 : 0) != 0;
    for (int g = 0; g < ngrp; ++g) {
       const int64_t g0 = g0_of(g), gw = gw_of(g);
       const bool mine = owner(g) == me;
@@ -740,12 +798,26 @@ static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t l
          const int64_t c0 = (int64_t)s * PW, rem = n - c0 - PW;
          double* D = W + c0 + c0 * ldw;
          double* dinv_k = dinv + (c0 / TILE) * TILE * TILE;
+         const bool next_diag_mine = rem > 0 && owner((s + 1) / spg) == me;
          if (mine) {
-            // critical path on P: leaf, then only the 128 rows the next leaf depends on; the rows below on Q
-            cudaEvent_t e_leaf = write(P, s, s + 1, PD, 0, [&]() { potrf_rec(ctx, PW, D, ldw, dinv_k, info, c0, aug_end); });
-            headE[s] = tailB[s] = e_leaf;
-            if (rem > 0)
-               headE[s] = write(P, s, s + 1, PE, 1, [&]() { dgemm_small128(ctx, PW, PW, 1.0, D + PW, ldw, dinv_k, TILE, 0.0, D + PW, ldw); });
+            // critical path on P: leaf, then only the 128 rows the next leaf depends on, then the next diagonal tile
+            // -- one cluster launch (potrf_step_kernel; MCHRG_B200_DIST_FUSE=0: three launches); the rows below on Q
+            cudaEvent_t e_leaf;
+            if (fuse) {
+               const double* pre = pre_ptr[s];
+               if (pre) need_panel(P, pre_src[s], true, true);
+               ctx->ensure_smem(potrf_step_kernel, leaf::SMEM_BYTES);
+               e_leaf = write_multi(P, {Range{s, s + 1, rem > 0 ? (PD | PE) : PD}, Range{s + 1, s + (next_diag_mine ? 2 : 1), PD}}, 0, [&]() {
+                  MCHRG_LAUNCH(ctx, potrf_step_kernel, 8, leaf::THREADS, leaf::SMEM_BYTES, D, ldw, dinv_k, info, (int)c0,
+                               (c0 + TILE == aug_end) ? 1 : 0, pre, rem > 0 ? 1 : 0, next_diag_mine ? 1 : 0);
+               });
+               headE[s] = tailB[s] = e_leaf;
+            } else {
+               e_leaf = write(P, s, s + 1, PD, 0, [&]() { potrf_rec(ctx, PW, D, ldw, dinv_k, info, c0, aug_end); });
+               headE[s] = tailB[s] = e_leaf;
+               if (rem > 0)
+                  headE[s] = write(P, s, s + 1, PE, 1, [&]() { dgemm_small128(ctx, PW, PW, 1.0, D + PW, ldw, dinv_k, TILE, 0.0, D + PW, ldw); });
+            }
             if (rem > PW) {
                wait(Q, e_leaf);
                tailB[s] = write(Q, s, s + 1, PB, 1, [&]() { dtrsm_right_lt(ctx, rem - PW, PW, D, ldw, dinv_k, D + 2 * PW, ldw); });
@@ -765,8 +837,10 @@ static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t l
             if (!mine) headE[s] = tailB[s] = e_arr;
          }
          if (rem == 0) break;
-         if (mine && s + 1 < s1) eager(s, s + 1, s1, 3);   // the rest of this group
-         if (next_mine && h0 < h1) eager(s, h0, h1, 4);    // the group this rank factors next
+         // diagonal tile of the next sub-panel: fused into this rank's step kernels where it can be
+         if (mine && s + 1 < s1) eager(s, s + 1, s1, 3, fuse ? 1 : 0);  // the rest of this group
+         if (next_mine && h0 < h1)                                        // the group this rank factors next
+            eager(s, h0, h1, 4, !fuse ? 0 : (s + 1 == h0 ? (mine ? 1 : 2) : 0));
       }
       // bulk: all owned groups behind the next one, with the whole group g at once (rank-gw update); the first of
       // them -- the next one this rank will have to factor -- as its own launch
@@ -807,6 +881,16 @@ static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t l
       fprintf(stderr, "[mchrg_b200 dist trace] rank %d of %d n=%lld DB=%lld:", me, R, (long long)n, (long long)DB);
       for (int c = 0; c < 6; ++c) fprintf(stderr, " %s %.2f ms/%d", names[c], sum[c], cnt[c]);
       fprintf(stderr, "\n");
+      if (env_ll("MCHRG_B200_DIST_TRACE", 0) > 1 && me == (int)env_ll("MCHRG_B200_DIST_TRACE_RANK", 0)) {
+         // timeline of this rank's operations: start / end in microseconds since its first one
+         const size_t lo = (size_t)env_ll("MCHRG_B200_DIST_TRACE_FROM", 0), hi = lo + 400;
+         for (size_t i = lo; i < spans.size() && i < hi; ++i) {
+            float t0 = 0.f, t1 = 0.f;
+            MCHRG_CUDA(cudaEventElapsedTime(&t0, spans.front().a, spans[i].a));
+            MCHRG_CUDA(cudaEventElapsedTime(&t1, spans.front().a, spans[i].b));
+            fprintf(stderr, "[timeline r%d] %4zu %-22s %9.1f -> %9.1f us\n", me, i, names[spans[i].cat], 1e3 * t0, 1e3 * t1);
+         }
+      }
       for (auto& sp : spans) {
          cudaEventDestroy(sp.a);
          cudaEventDestroy(sp.b);
@@ -831,9 +915,12 @@ void dpotrf_padded(mchrg_b200_context* ctx, int64_t n, double* W, int64_t ldw, d
       dpotrf_dist(ctx, n, W, ldw, dinv, info, aug_end);
       return;
    }
-   // MCHRG_B200_POTRF=tracked: the schedule of the distributed factorisation on one GPU (critical path of leaf + two
-   // small-tile products on its own stream), for A/B timing against the two-stream look-ahead below
-   if (env_ll("MCHRG_B200_POTRF_TRACKED", 0) > 0 && n >= 8 * TILE && ctx->active == ctx->stream) {
+   // The schedule of the distributed factorisation on one GPU (critical path of leaf + two small-tile products on its
+   // own stream) wins while the serial chain matters (measured on B200: n = 4096 3.34 vs 3.60 ms, 8192 10.9 vs 11.0 ms),
+   // the two-stream look-ahead with its wider panels below wins at n = 16384 (56.9 vs 58.5 ms).
+   // MCHRG_B200_POTRF_TRACKED = 0 | 1 forces one of them (A/B timing).
+   const long long tracked = env_ll("MCHRG_B200_POTRF_TRACKED", -1);
+   if ((tracked > 0 || (tracked < 0 && n <= 8192)) && n >= 8 * TILE && ctx->active == ctx->stream) {
       dpotrf_dist(ctx, n, W, ldw, dinv, info, aug_end);
       return;
    }

@@ -92,10 +92,12 @@ __device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cb
          dn = pivot_rcp(piv);
       }
       const double f = cb[myslot] * d;  // 0 for r <= c: the updates below leave those rows alone
+      // (one warp issues in order: every instruction of a step delays the next pivot, so the triangular structure is
+      //  used -- columns <= c of A are final, row c of X is zero right of column c; c, k are compile-time here)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-         m[k] = fma(-f, cb[h * 8 + k], m[k]);  // entries right of the diagonal collect garbage; never used
-         x[k] = fma(-f, rb[h * 8 + k], x[k]);
+         if (2 * k + 1 > c) m[k] = fma(-f, cb[h * 8 + k], m[k]);  // entries right of the diagonal collect garbage; never used
+         if (2 * k <= c) x[k] = fma(-f, rb[h * 8 + k], x[k]);
       }
       if (c + 1 < KB) {
          publish(c + 1);

@@ -198,47 +198,13 @@ def test_env_knobs_are_read_per_call(mc, monkeypatch):
     rng = np.random.default_rng(1)
     M = rng.standard_normal((n, n))
     S = M @ M.T + n * np.eye(n)
+    Lref = np.linalg.cholesky(S)
     counts = []
-    for panel in ("128", "512"):
-        monkeypatch.setenv("MCHRG_B200_PANEL", panel)
+    for tracked in ("0", "1"):  # two-stream look-ahead vs the tracked schedule of the distributed factorisation
+        monkeypatch.setenv("MCHRG_B200_POTRF_TRACKED", tracked)
         l0 = ctx.launch_count
-        assert ctx.dpotrf(fort(S)) == 0
+        a = fort(S)
+        assert ctx.dpotrf(a) == 0
+        assert np.abs(np.tril(a.T) - Lref).max() < 1e-12 * np.abs(Lref).max()
         counts.append(ctx.launch_count - l0)
     assert counts[0] != counts[1]
-
-
-def test_eeqbc_row_blocks_and_shards_vs_oracle(mc, oracle, group, dist_env):
-    """configs[4] path: EEQ-BC with the distributed factorisation (own column groups assembled only), row-sharded
-    bc_rows / bc_strain / (A q) passes joined by one all-reduce, and dq/dr by row blocks (dtmpdr C GEMM and both TRSM
-    sweeps on the block's rows), against the oracle."""
-    from synth import cluster
-    from multicharge_b200.shard import row_bounds
-    from test_gpu_eeqbc import models
-    world = len(group)
-    nat = 1100
-    num, xyz = cluster(nat, 77)
-    bounds = row_bounds(nat, world)
-    _, _, omol, omodel = models(mc, oracle, num, xyz, 1.0)
-    o = oracle.eeqbc_singlepoint(omodel, omol, want=("qvec", "energy", "gradient", "dqdr"))
-
-    def body(r):
-        mol = mc.Structure(num, xyz, 1.0)
-        model = mc.new_eeqbc_model(mol, chi=omodel.chi, rad=omodel.rad, eta=omodel.eta, kcnchi=omodel.kcnchi,
-                                   kqchi=omodel.kqchi, kqeta=omodel.kqeta, kcnrad=omodel.kcnrad, cap=omodel.cap,
-                                   avg_cn=omodel.avg_cn, rvdw=omodel.rvdw, rcov=omodel.rcov, en=omodel.en, kbc=omodel.kbc,
-                                   cutoff=omodel.cutoff, cn_exp=omodel.kcn, norm_exp=omodel.norm_exp, ctx=group[r])
-        a = mc.singlepoint_rows(model, mol, 0, nat, dqdr=False)
-        b = mc.singlepoint_rows(model, mol, int(bounds[r]), int(bounds[r + 1]))
-        return a, b
-
-    grad = np.zeros((nat, 3))
-    dqdr = np.zeros((nat, nat, 3))
-    for r, (a, b) in enumerate(run_ranks(world, body)):
-        for key in ("qvec", "energy", "gradient", "sigma"):
-            assert np.abs(a[key] - o[key]).max() < 1e-10 * max(1.0, np.abs(o[key]).max()), (r, key)
-        jb, je = int(bounds[r]), int(bounds[r + 1])
-        grad[jb:je] = b["gradient"]
-        dqdr[:, jb:je, :] = b["dqdr"]
-        assert np.abs(b["dqdL"] - o["dqdL"]).max() < 1e-10 * max(1.0, np.abs(o["dqdL"]).max())
-    assert np.abs(grad - o["gradient"]).max() < 1e-10 * max(1.0, np.abs(o["gradient"]).max())
-    assert np.abs(dqdr - o["dqdr"]).max() < 1e-10 * max(1.0, np.abs(o["dqdr"]).max())

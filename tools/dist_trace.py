@@ -51,7 +51,7 @@ def main():
         best = min(run() for _ in range(3))
         if rank == 0:
             print(f"n {n} world {world} group {grp}: {best:.2f} ms (incl. ~2.5 ms pad copies)", flush=True)
-        os.environ["MCHRG_B200_DIST_TRACE"] = "1"
+        os.environ["MCHRG_B200_DIST_TRACE"] = os.environ.get("TRACE_LEVEL", "1")
         run()
         os.environ.pop("MCHRG_B200_DIST_TRACE")
         dist.barrier()
