@@ -14,7 +14,8 @@ module mchrg_b200_shim
    implicit none
    private
 
-   public :: b200_model_type, new_b200_eeq2019_model, b200_get_charges
+   public :: b200_model_type, new_b200_eeq2019_model, new_b200_eeqbc2025_model, b200_get_charges
+   public :: b200_get_charges_batch, b200_comm_init_nccl, b200_comm_unique_id
 
    type, bind(C) :: c_structure
       integer(c_int32_t) :: nat
@@ -53,6 +54,31 @@ module mchrg_b200_shim
          integer(c_int32_t), value :: nid
          integer(c_int32_t), intent(in) :: num(*)
          type(c_ptr), intent(out) :: model
+         integer(c_int) :: stat
+      end function
+      function c_new_eeqbc2025_model(ctx, nid, num, rvdw, en, model) result(stat) &
+            & bind(C, name="mchrg_b200_new_eeqbc2025_model")
+         import :: c_int, c_int32_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int32_t), value :: nid
+         integer(c_int32_t), intent(in) :: num(*)
+         real(c_double), intent(in) :: rvdw(*), en(*)   ! get_vdw_rad(pair)*autoaa per species pair, get_pauling_en
+         type(c_ptr), intent(out) :: model
+         integer(c_int) :: stat
+      end function
+      function c_local_charge(model, mol, qloc, dqlocdr, dqlocdL) result(stat) bind(C, name="mchrg_b200_local_charge")
+         import :: c_int, c_ptr, c_structure
+         type(c_ptr), value :: model
+         type(c_structure), intent(in) :: mol
+         type(c_ptr), value :: qloc, dqlocdr, dqlocdL
+         integer(c_int) :: stat
+      end function
+      function c_singlepoint_batch(model, nmol, offsets, num, xyz, charge, qvec, energy, gradient, status) result(stat) &
+            & bind(C, name="mchrg_b200_singlepoint_batch")
+         import :: c_int, c_int32_t, c_ptr
+         type(c_ptr), value :: model
+         integer(c_int32_t), value :: nmol
+         type(c_ptr), value :: offsets, num, xyz, charge, qvec, energy, gradient, status
          integer(c_int) :: stat
       end function
       subroutine c_model_free(model) bind(C, name="mchrg_b200_model_free")
@@ -174,6 +200,79 @@ subroutine new_b200_eeq2019_model(mol, model, error, device)
    call move_alloc(self, model)
 end subroutine new_b200_eeq2019_model
 
+!> new_eeqbc2025_model (src/multicharge/param.f90:75-125); the pairwise D3 vdW radii and Pauling electronegativities come
+!> from mctc-lib on the Fortran side (get_vdw_rad, get_pauling_en: param.f90:105-115) and are passed per species (pair)
+subroutine new_b200_eeqbc2025_model(mol, model, error, device)
+   use mctc_data, only : get_vdw_rad, get_pauling_en
+   use mctc_io_convert, only : autoaa
+   type(structure_type), intent(in) :: mol
+   class(mchrg_model_type), allocatable, intent(out) :: model
+   type(error_type), allocatable, intent(out) :: error
+   integer, intent(in), optional :: device
+   type(b200_model_type), allocatable :: self
+   real(c_double), allocatable :: rvdw(:, :), en(:)
+   integer(c_int) :: stat, dev
+   integer :: isp, jsp
+
+   dev = 0
+   if (present(device)) dev = device
+   allocate(self, rvdw(mol%nid, mol%nid), en(mol%nid))
+   do isp = 1, mol%nid
+      en(isp) = get_pauling_en(mol%num(isp))
+      do jsp = 1, mol%nid
+         rvdw(jsp, isp) = get_vdw_rad(mol%num(jsp), mol%num(isp))*autoaa
+      end do
+   end do
+   stat = c_context_create(dev, self%ctx)
+   if (stat == 0) stat = c_new_eeqbc2025_model(self%ctx, int(mol%nid, c_int32_t), int(mol%num, c_int32_t), rvdw, en, &
+      & self%handle)
+   if (stat /= 0) then
+      call fatal_error(error, "mchrg_b200: "//c_message())
+      return
+   end if
+   call move_alloc(self, model)
+end subroutine new_b200_eeqbc2025_model
+
+!> get_charges over a batch of independent non-periodic molecules (charge.f90:37-77 per molecule): molecule m owns the atoms
+!> offsets(m)+1 .. offsets(m+1); num are atomic numbers; status(m) follows the return-value convention per molecule.
+!> The model must have been built for the species 1..103 (species index = atomic number).
+subroutine b200_get_charges_batch(model, offsets, num, xyz, charge, qvec, status, error, energy, gradient)
+   type(b200_model_type), intent(in) :: model
+   integer(c_int64_t), intent(in), contiguous, target :: offsets(:)
+   integer(c_int32_t), intent(in), contiguous, target :: num(:)
+   real(wp), intent(in), contiguous, target :: xyz(:, :), charge(:)
+   real(wp), intent(out), contiguous, target :: qvec(:)
+   integer(c_int32_t), intent(out), contiguous, target :: status(:)
+   type(error_type), allocatable, intent(out) :: error
+   real(wp), intent(out), contiguous, optional, target :: energy(:), gradient(:, :)
+   type(c_ptr) :: pe, pg
+   integer(c_int) :: stat
+   pe = c_null_ptr
+   pg = c_null_ptr
+   if (present(energy)) pe = c_loc(energy)
+   if (present(gradient)) pg = c_loc(gradient)
+   stat = c_singlepoint_batch(model%handle, int(size(charge), c_int32_t), c_loc(offsets), c_loc(num), c_loc(xyz), &
+      & c_loc(charge), c_loc(qvec), pe, pg, c_loc(status))
+   if (stat /= 0) call fatal_error(error, "mchrg_b200: "//c_message())
+end subroutine b200_get_charges_batch
+
+!> one large system on several GPUs, one MPI rank per GPU: rank 0 obtains the id, the caller broadcasts its 128 bytes
+!> (MPI_Bcast) and every rank joins; from then on solve / get_charges of structures with >= 8192 atoms share the work
+subroutine b200_comm_unique_id(id, error)
+   character(kind=c_char), intent(out), target :: id(128)
+   type(error_type), allocatable, intent(out) :: error
+   if (c_comm_unique_id(c_loc(id)) /= 0) call fatal_error(error, "mchrg_b200: "//c_message())
+end subroutine b200_comm_unique_id
+
+subroutine b200_comm_init_nccl(model, rank, nranks, id, error)
+   type(b200_model_type), intent(in) :: model
+   integer, intent(in) :: rank, nranks
+   character(kind=c_char), intent(in), target :: id(128)
+   type(error_type), allocatable, intent(out) :: error
+   if (c_comm_init_nccl(model%ctx, int(rank, c_int32_t), int(nranks, c_int32_t), c_loc(id)) /= 0) &
+      & call fatal_error(error, "mchrg_b200: "//c_message())
+end subroutine b200_comm_init_nccl
+
 subroutine b200_free(self)
    type(b200_model_type), intent(inout) :: self
    if (c_associated(self%handle)) call c_model_free(self%handle)
@@ -195,12 +294,16 @@ function c_message() result(msg)
    end do
 end function c_message
 
-function to_c(mol) result(cmol)
+!> C view of a structure.  The caller's `mol` must be a TARGET (or the call chain must keep it alive and contiguous for
+!> the duration of the C call: F2018 15.5.2.4 makes the addresses taken here valid only while `mol` is); `id32` is the
+!> caller-owned 32-bit copy of mol%id (mol%id is a default integer, which is not c_int32_t under -fdefault-integer-8).
+function to_c(mol, id32) result(cmol)
    type(structure_type), intent(in), target :: mol
+   integer(c_int32_t), intent(in), target :: id32(:)
    type(c_structure) :: cmol
    cmol%nat = int(mol%nat, c_int32_t)
    cmol%nid = int(mol%nid, c_int32_t)
-   cmol%id = c_loc(mol%id)
+   cmol%id = c_loc(id32)
    cmol%xyz = c_loc(mol%xyz)
    cmol%charge = mol%charge
    cmol%periodic = merge(1_c_int32_t, 0_c_int32_t, spread(any(mol%periodic), 1, 3) .and. mol%periodic)
@@ -232,23 +335,27 @@ end function opt1
 subroutine b200_solve(self, mol, error, cn, qloc, dcndr, dcndL, dqlocdr, dqlocdL, &
    & energy, gradient, sigma, qvec, dqdr, dqdL)
    class(b200_model_type), intent(in) :: self
-   type(structure_type), intent(in) :: mol
+   type(structure_type), intent(in), target :: mol
    type(error_type), allocatable, intent(out) :: error
    real(wp), intent(in), contiguous, target :: cn(:)
    real(wp), intent(in), contiguous, target :: qloc(:)
-   real(wp), intent(in), contiguous, optional :: dcndr(:, :, :)
-   real(wp), intent(in), contiguous, optional :: dcndL(:, :, :)
-   real(wp), intent(in), contiguous, optional :: dqlocdr(:, :, :)
-   real(wp), intent(in), contiguous, optional :: dqlocdL(:, :, :)
-   real(wp), intent(inout), contiguous, optional :: energy(:)
-   real(wp), intent(inout), contiguous, optional :: gradient(:, :)
-   real(wp), intent(inout), contiguous, optional :: sigma(:, :)
-   real(wp), intent(out), contiguous, optional :: qvec(:)
-   real(wp), intent(out), contiguous, optional :: dqdr(:, :, :)
-   real(wp), intent(out), contiguous, optional :: dqdL(:, :, :)
+   real(wp), intent(in), contiguous, optional, target :: dcndr(:, :, :)
+   real(wp), intent(in), contiguous, optional, target :: dcndL(:, :, :)
+   real(wp), intent(in), contiguous, optional, target :: dqlocdr(:, :, :)
+   real(wp), intent(in), contiguous, optional, target :: dqlocdL(:, :, :)
+   real(wp), intent(inout), contiguous, optional, target :: energy(:)
+   real(wp), intent(inout), contiguous, optional, target :: gradient(:, :)
+   real(wp), intent(inout), contiguous, optional, target :: sigma(:, :)
+   real(wp), intent(out), contiguous, optional, target :: qvec(:)
+   real(wp), intent(out), contiguous, optional, target :: dqdr(:, :, :)
+   real(wp), intent(out), contiguous, optional, target :: dqdL(:, :, :)
    integer(c_int) :: stat
+   integer(c_int32_t), allocatable, target :: id32(:)
+   type(c_structure) :: cmol
 
-   stat = c_solve(self%handle, to_c(mol), c_loc(cn), c_loc(qloc), opt3(dcndr), opt3(dcndL), &
+   id32 = int(mol%id, c_int32_t)   ! 32-bit species indices that outlive the C call
+   cmol = to_c(mol, id32)
+   stat = c_solve(self%handle, cmol, c_loc(cn), c_loc(qloc), opt3(dcndr), opt3(dcndL), &
       & opt3(dqlocdr), opt3(dqlocdL), opt1(energy), opt2(gradient), opt2(sigma), opt1(qvec), &
       & opt3(dqdr), opt3(dqdL))
    if (stat > 0) then
@@ -261,13 +368,17 @@ end subroutine b200_solve
 !> get_charges (src/multicharge/charge.f90:37-77) with the CN evaluated on the device
 subroutine b200_get_charges(model, mol, error, qvec, dqdr, dqdL)
    type(b200_model_type), intent(in) :: model
-   type(structure_type), intent(in) :: mol
+   type(structure_type), intent(in), target :: mol
    type(error_type), allocatable, intent(out) :: error
    real(wp), intent(out), contiguous, target :: qvec(:)
-   real(wp), intent(out), contiguous, optional :: dqdr(:, :, :)
-   real(wp), intent(out), contiguous, optional :: dqdL(:, :, :)
+   real(wp), intent(out), contiguous, optional, target :: dqdr(:, :, :)
+   real(wp), intent(out), contiguous, optional, target :: dqdL(:, :, :)
    integer(c_int) :: stat
-   stat = c_get_charges(model%handle, to_c(mol), c_loc(qvec), opt3(dqdr), opt3(dqdL))
+   integer(c_int32_t), allocatable, target :: id32(:)
+   type(c_structure) :: cmol
+   id32 = int(mol%id, c_int32_t)   ! 32-bit species indices that outlive the C call
+   cmol = to_c(mol, id32)
+   stat = c_get_charges(model%handle, cmol, c_loc(qvec), opt3(dqdr), opt3(dqdL))
    if (stat > 0) then
       call fatal_error(error, "Bunch-Kaufman factorization failed.")
    else if (stat < 0) then
@@ -322,52 +433,68 @@ end function p3
 
 subroutine b200_get_xvec(self, mol, cache, xvec)
    class(b200_model_type), intent(in) :: self
-   type(structure_type), intent(in) :: mol
+   type(structure_type), intent(in), target :: mol
    type(cache_container), intent(inout) :: cache
    real(wp), intent(out), target :: xvec(:)
    type(b200_cache), pointer :: c
    integer(c_int) :: stat
+   integer(c_int32_t), allocatable, target :: id32(:)
+   type(c_structure) :: cmol
    c => view(cache)
-   stat = c_get_xvec(self%handle, to_c(mol), p1(c%cn), p1(c%qloc), c_loc(xvec))
+   id32 = int(mol%id, c_int32_t)   ! 32-bit species indices that outlive the C call
+   cmol = to_c(mol, id32)
+   stat = c_get_xvec(self%handle, cmol, p1(c%cn), p1(c%qloc), c_loc(xvec))
    if (stat /= 0) error stop "mchrg_b200: get_xvec failed"
 end subroutine b200_get_xvec
 
 subroutine b200_get_xvec_derivs(self, mol, cache, dxdr, dxdL)
    class(b200_model_type), intent(in) :: self
-   type(structure_type), intent(in) :: mol
+   type(structure_type), intent(in), target :: mol
    type(cache_container), intent(inout) :: cache
    real(wp), intent(out), contiguous, target :: dxdr(:, :, :)
    real(wp), intent(out), contiguous, target :: dxdL(:, :, :)
    type(b200_cache), pointer :: c
    integer(c_int) :: stat
+   integer(c_int32_t), allocatable, target :: id32(:)
+   type(c_structure) :: cmol
    c => view(cache)
-   stat = c_get_xvec_derivs(self%handle, to_c(mol), p1(c%cn), p1(c%qloc), p3(c%dcndr), p3(c%dcndL), &
+   id32 = int(mol%id, c_int32_t)   ! 32-bit species indices that outlive the C call
+   cmol = to_c(mol, id32)
+   stat = c_get_xvec_derivs(self%handle, cmol, p1(c%cn), p1(c%qloc), p3(c%dcndr), p3(c%dcndL), &
       & p3(c%dqlocdr), p3(c%dqlocdL), c_loc(dxdr), c_loc(dxdL))
    if (stat /= 0) error stop "mchrg_b200: get_xvec_derivs failed"
 end subroutine b200_get_xvec_derivs
 
 subroutine b200_get_coulomb_matrix(self, mol, cache, amat)
    class(b200_model_type), intent(in) :: self
-   type(structure_type), intent(in) :: mol
+   type(structure_type), intent(in), target :: mol
    type(cache_container), intent(inout) :: cache
    real(wp), intent(out), target :: amat(:, :)
    type(b200_cache), pointer :: c
    integer(c_int) :: stat
+   integer(c_int32_t), allocatable, target :: id32(:)
+   type(c_structure) :: cmol
    c => view(cache)
-   stat = c_get_coulomb_matrix(self%handle, to_c(mol), p1(c%cn), p1(c%qloc), c_loc(amat))
+   id32 = int(mol%id, c_int32_t)   ! 32-bit species indices that outlive the C call
+   cmol = to_c(mol, id32)
+   stat = c_get_coulomb_matrix(self%handle, cmol, p1(c%cn), p1(c%qloc), c_loc(amat))
    if (stat /= 0) error stop "mchrg_b200: get_coulomb_matrix failed"
 end subroutine b200_get_coulomb_matrix
 
 subroutine b200_get_coulomb_derivs(self, mol, cache, qvec, dadr, dadL, atrace)
    class(b200_model_type), intent(in) :: self
-   type(structure_type), intent(in) :: mol
+   type(structure_type), intent(in), target :: mol
    type(cache_container), intent(inout) :: cache
    real(wp), intent(in), target :: qvec(:)
    real(wp), intent(out), target :: dadr(:, :, :), dadL(:, :, :), atrace(:, :)
    type(b200_cache), pointer :: c
    integer(c_int) :: stat
+   integer(c_int32_t), allocatable, target :: id32(:)
+   type(c_structure) :: cmol
    c => view(cache)
-   stat = c_get_coulomb_derivs(self%handle, to_c(mol), p1(c%cn), p1(c%qloc), p3(c%dcndr), p3(c%dcndL), &
+   id32 = int(mol%id, c_int32_t)   ! 32-bit species indices that outlive the C call
+   cmol = to_c(mol, id32)
+   stat = c_get_coulomb_derivs(self%handle, cmol, p1(c%cn), p1(c%qloc), p3(c%dcndr), p3(c%dcndL), &
       & p3(c%dqlocdr), p3(c%dqlocdL), c_loc(qvec), c_loc(dadr), c_loc(dadL), c_loc(atrace))
    if (stat /= 0) error stop "mchrg_b200: get_coulomb_derivs failed"
 end subroutine b200_get_coulomb_derivs

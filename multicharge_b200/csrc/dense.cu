@@ -785,9 +785,11 @@ static void dpotrf_dist(mchrg_b200_context* ctx, int64_t n, double* W, int64_t l
          }
       }
    };
-   // (a cluster of 8 CTAs has to be placed at once: on ONE GPU, where the bulk updates keep every SM busy, that wait
-   //  costs more than the two launch gaps it saves -- n = 4096: 4.05 vs 3.34 ms -- so the fusion is for shared systems)
-   const bool fuse = env_ll("MCHRG_B200_DIST_FUSE", cm != nullptr ? 1 : 0) != 0;
+   // MCHRG_B200_DIST_FUSE=1: the three launches of a step as one cluster launch (potrf_step_kernel).  Measured SLOWER and
+   // therefore off: a cluster of 8 CTAs has to be placed at once, and with the update streams keeping the SMs busy that
+   // wait costs more than the two launch gaps it saves (one GPU, n = 4096: 4.05 vs 3.34 ms; 8 GPUs, n = 16384: 25.8 vs
+   // 21.0 ms).  Kept for the parity tests of the cluster path and as the documented negative result.
+   const bool fuse = env_ll("MCHRG_B200_DIST_FUSE", 0) != 0;
    for (int g = 0; g < ngrp; ++g) {
       const int64_t g0 = g0_of(g), gw = gw_of(g);
       const bool mine = owner(g) == me;

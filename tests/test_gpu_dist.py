@@ -87,10 +87,14 @@ def test_local_collectives(mc, group):
         assert np.array_equal(g, base)
 
 
+@pytest.mark.parametrize("fuse", ["0", "1"])
 @pytest.mark.parametrize("n", [1024, 1500, 2176])
-def test_block_cyclic_cholesky_vs_lapack(mc, group, dist_env, n, monkeypatch):
+def test_block_cyclic_cholesky_vs_lapack(mc, group, dist_env, n, fuse, monkeypatch):
+    """fuse = 1: the cluster step kernel (leaf + head row solve + next diagonal tile in one launch, the arriving
+    sub-panel's last update as its phase 0) instead of the three launches."""
     world = len(group)
     monkeypatch.setenv("MCHRG_B200_DIST_GROUP", "256")
+    monkeypatch.setenv("MCHRG_B200_DIST_FUSE", fuse)
     rng = np.random.default_rng(n)
     M = rng.standard_normal((n, n))
     S = M @ M.T + n * np.eye(n)
