@@ -395,6 +395,8 @@ static Factor factor_solve(mchrg_b200_context* ctx, int nat, int64_t npad, Assem
       MCHRG_CUDA(cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       MCHRG_CUDA(cudaStreamSynchronize(ctx->stream));
       f.info = *h_info;
+      if (env_ll("MCHRG_B200_DIST_TRACE", 0) > 0)
+         fprintf(stderr, "[mchrg_b200 factor_solve] rank %d attempt %d npad %lld info %d\n", ctx->rank(), attempt, (long long)npad, f.info);
       if (f.info == 0) break;
       if (attempt == 3) {
          // J is indefinite on the charge-conserving subspace as well (e.g. two atoms far inside each other's charge

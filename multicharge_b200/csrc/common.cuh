@@ -197,6 +197,9 @@ int guarded(mchrg_b200_context* ctx, F&& body) {
       ctx->events_used = 0;
       int rc = body();
       ctx->finish();
+      // a call that outgrew the workspace leaves chained slabs: merge them NOW (this call pays for its own growth), not
+      // at the start of the next call, whose time a caller may be measuring
+      if (ctx->slabs.size() > 1) ctx->arena_reset();
       return rc;
    } catch (const Error& e) {
       set_last_error(e.msg);
