@@ -355,9 +355,11 @@ def cluster_block(torch, mc, ctx, ext, dev, rank, world, nat, fp64_peak, want_dq
         res["roofline_dqdr"] = {"bound": "tensor", "kernel": "dgemm_dmma_kernel (two right-side TRSM sweeps X = B L^-T L^-1)",
                                 "achieved": fl / t_dq / 1e12, "peak": fp64_peak, "unit": "TFLOP/s per GPU",
                                 "frac": fl / t_dq / 1e12 / fp64_peak,
-                                "traffic": 5.8e9 / 3.8e9 * 16.0 * nat * nat if world == 1 else None,
-                                "traffic_source": "ncu --set full of one trailing-update-shaped launch: DRAM bytes = 1.5x the "
-                                                  "algorithmic C read+write (profiles/r1_final_gemm_bn64_ncu_key_metrics.txt)",
+                                "traffic": 5.72e9 / 3.90e9 * (2.0 * 8.0 * (3.0 * nmax + 9.0) * nat) * (nat / 512.0 / 2.0 + 1.0),
+                                "traffic_source": "ncu --set full of one trailing-update-shaped launch (15360 x 15360 x 512, beta = 1): "
+                                                  "5.72 GB of DRAM traffic for 3.90 GB of algorithmic C read+write and operand reads "
+                                                  "(profiles/r2_gemm_ncu_key_metrics.txt), applied to the read-modify-write passes of the "
+                                                  "recursive right-side sweeps over this rank's rows",
                                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run"}
         del out, gsend, grecv
         torch.cuda.empty_cache()
@@ -728,9 +730,11 @@ def run_ours(args):
 
 # DRAM traffic of the factorisation kernel per molecule of the bench distribution, from the ncu --set full capture
 # under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum of one launch over 5000 molecules)
-NCU_FACTOR_DRAM_BYTES_PER_MOLECULE = 1.53e12 * 537.18e-6 / 5000
-NCU_TRAFFIC_SOURCE = ("DRAM throughput x duration of one eeq_factor_ll_kernel launch over 5000 molecules of this distribution "
-                      "(profiles/r1_final_batch_kernels_ncu_key_metrics.txt), scaled to the molecules of one step")
+NCU_FACTOR_DRAM_BYTES_PER_MOLECULE = (489.03e6 + 333.94e6) / 5000
+NCU_TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one eeq_factor_ll_kernel launch over 5000 molecules of this "
+                      "distribution (profiles/r2_batch_factor_ncu_key_metrics.txt), scaled to the molecules of one step; the "
+                      "per-molecule scratch matrices (~60 KB each, 300 MB per chunk) do not stay in the 126 MB L2 between the "
+                      "three kernels of a chunk")
 
 
 def main():
