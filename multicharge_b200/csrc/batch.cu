@@ -85,6 +85,26 @@ __device__ __forceinline__ double warp_sum(double v) {
    return v;
 }
 
+// Sums of six values over the warp with a butterfly that halves the number of values per lane at every step
+// (8 shuffles of a double instead of 30): value order (a0, a1, a2, 0, b0, b1, b2, 0); lane 4 v returns the total of
+// value v, the other lanes partial garbage.
+__device__ __forceinline__ double warp_sum_3x2(double a0, double a1, double a2, double b0, double b1, double b2, int lane) {
+   constexpr unsigned FULL = 0xffffffffu;
+   const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+   // step 1: (a_k, b_k) pairs; upper half-warp keeps b
+   const double w0 = (u16 ? b0 : a0) + __shfl_xor_sync(FULL, u16 ? a0 : b0, 16);
+   const double w1 = (u16 ? b1 : a1) + __shfl_xor_sync(FULL, u16 ? a1 : b1, 16);
+   const double w2 = (u16 ? b2 : a2) + __shfl_xor_sync(FULL, u16 ? a2 : b2, 16);
+   // step 2: (w0, w2), (w1, 0)
+   const double v0 = (u8 ? w2 : w0) + __shfl_xor_sync(FULL, u8 ? w0 : w2, 8);
+   const double v1 = (u8 ? 0.0 : w1) + __shfl_xor_sync(FULL, u8 ? w1 : 0.0, 8);
+   // step 3: (v0, v1)
+   double t = (u4 ? v1 : v0) + __shfl_xor_sync(FULL, u4 ? v0 : v1, 4);
+   t += __shfl_xor_sync(FULL, t, 2);
+   t += __shfl_xor_sync(FULL, t, 1);
+   return t;
+}
+
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                 : "+d"(d0), "+d"(d1)
@@ -286,6 +306,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
       //  most 224 values < 2^20, so nothing carries)
       const unsigned long long f = (unsigned long long)__double2ll_rn(c * FIX);
       const unsigned f0 = (unsigned)f & 0xfffffu, f1 = (unsigned)(f >> 20) & 0xfffffu, f2 = (unsigned)(f >> 40);
+      // (tried: summing the row atom's limbs in the warp first with match.any + redux, because 32 atomics on one
+      //  address serialise -- slower, 6.15 vs 5.72 ms per 100k molecules)
       atomicAdd(&cnfix[i], f0); atomicAdd(&cnfix[npv + i], f1); atomicAdd(&cnfix[2 * npv + i], f2);
       atomicAdd(&cnfix[j], f0); atomicAdd(&cnfix[npv + j], f1); atomicAdd(&cnfix[2 * npv + j], f2);
    };
@@ -564,9 +586,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
             if (i == ia) { ax = fma(f, vx, ax); ay = fma(f, vy, ay); az = fma(f, vz, az); }
             else { bx = fma(f, vx, bx); by = fma(f, vy, by); bz = fma(f, vz, bz); }
          };
-         for (int t0 = 0; t0 < len; t0 += 32) {
+         unsigned hmask = 0;  // near pairs of this lane, one bit per step (len <= 207: at most 7 steps); packed into the ring
+                              // once per pair of rows (a ballot per step as in phase A costs more here: 9.04 -> 8.65 ms
+                              // per 100k molecules together with the six-value warp sum below)
+         for (int t0 = 0, st = 0; t0 < len; t0 += 32, ++st) {
             const int tt = t0 + lane;
-            bool hit = false;
             const bool first = tt < ia;
             const int i = first ? ia : ib;
             const int j = first ? tt : tt - ia;
@@ -583,10 +607,20 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
                if (first) { ax = fma(f, vx, ax); ay = fma(f, vy, ay); az = fma(f, vz, az); }
                else { bx = fma(f, vx, bx); by = fma(f, vy, by); bz = fma(f, vz, bz); }
                const double rc = rcov[i] + rcov[j];
-               hit = r2 < near2 * rc * rc && r2 <= p.cutoff2 && r2 >= 1.0e-12;
+               if (r2 < near2 * rc * rc && r2 <= p.cutoff2 && r2 >= 1.0e-12) hmask |= 1u << st;
             }
-            const unsigned m = __ballot_sync(FULL, hit);
-            if (hit) ring[(wr + __popc(m & lt_mask)) & (AUX_RING - 1)] = (i << 16) | j;
+         }
+         for (;;) {
+            const bool h = hmask != 0u;
+            const unsigned m = __ballot_sync(FULL, h);
+            if (m == 0u) break;
+            if (h) {
+               const int tt = 32 * (__ffs(hmask) - 1) + lane;
+               hmask &= hmask - 1u;
+               const int i = (tt < ia) ? ia : ib;
+               const int j = (tt < ia) ? tt : tt - ia;
+               ring[(wr + __popc(m & lt_mask)) & (AUX_RING - 1)] = (i << 16) | j;
+            }
             wr += __popc(m);
             if (wr - rdp >= 32) {
                __syncwarp();
@@ -598,11 +632,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) eeq_batch_kernel(Args p) {
          __syncwarp();
          if (lane < wr - rdp) dcount_pairs(rdp + lane);  // the rest of this pair of rows
          __syncwarp();
-         ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
-         bx = warp_sum(bx); by = warp_sum(by); bz = warp_sum(bz);
-         if (lane == 0) {
-            G[ia] = ax; G[npv + ia] = ay; G[2 * npv + ia] = az;
-            if (ia != ib) { G[ib] = bx; G[npv + ib] = by; G[2 * npv + ib] = bz; }
+         // the six row shares at once: lane 4 v ends with the sum of value v (0-2: row ia, 4-6: row ib)
+         const double tot = warp_sum_3x2(ax, ay, az, bx, by, bz, lane);
+         if ((lane & 3) == 0 && (lane & 12) != 12) {
+            const int row = (lane & 16) ? ib : ia;
+            if (!(lane & 16) || ia != ib) G[((lane >> 2) & 3) * npv + row] = tot;
          }
       }
    }
@@ -661,6 +695,7 @@ constexpr int TS = KB + 1;            // row stride of the diagonal tile
 #ifndef LL_MINB
 #define LL_MINB 6
 #endif
+
 #ifndef LL_UNROLL
 #define LL_UNROLL 2  // block pairs of the left-looking update in flight per warp (each: four 16-byte loads from L2)
 #endif
@@ -686,6 +721,15 @@ __device__ __forceinline__ int diag_factor_inv(double* T, double* Li, double* cb
 template <int NT>
 __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
    extern __shared__ __align__(16) double sm[];
+#ifdef LL_PROF  // per-warp phase clocks of sampled molecules (tools/run_llprof.sh)
+   long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // D | U jobs | barrier 1 | S | barrier 2 | backward | - | total
+   const long long pf_t0 = clock64();
+#define LP_BEGIN(v) const long long v = clock64()
+#define LP_ADD(i, v) pf[i] += clock64() - v
+#else
+#define LP_BEGIN(v)
+#define LP_ADD(i, v)
+#endif
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    constexpr int NW = NT / 32;
    const int mol = p.perm[blockIdx.x];
@@ -775,7 +819,9 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
       if (warp == ((blockIdx.x + (k0 >> 4)) % NW)) {
          // ---- D: diagonal tile, Cholesky + inverse; the inverse goes to global in place of the block ----
          const bool last = (k0 + KB == npa);
+         LP_BEGIN(td);
          const int bad = diag_factor_inv(T, Li, cbuf, rbuf, dvec, lane, last ? KB - 2 : KB, last);
+         LP_ADD(0, td);
          if (bad && lane == 0) sfail = k0 + bad;
          __syncwarp();
          const int r = lane & 15, h = lane >> 4;
@@ -789,6 +835,7 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
             wl[KB + lane] = (lane < KB - 2) ? T[(KB - 1) * TS + lane] : 0.0;
          }
       }
+      LP_BEGIN(tu);
       if (nrt > 1) {
          for (;;) {
             int job = 0;
@@ -798,8 +845,12 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
             u_job(job);
          }
       }
+      LP_ADD(1, tu);
+      LP_BEGIN(tb1);
       __syncthreads();
+      LP_ADD(2, tb1);
       if (sfail) break;
+      LP_BEGIN(ts);
       // ---- S: rows below the diagonal tile, L(i, blk) = Cb(i, :) inv(L_kk)^T, straight to the scratch; the warp
       //      of the first tile also completes the next diagonal tile, T = T2 - L(tile, blk) L(tile, blk)^T ----
       for (int ti = 1 + warp; ti < nrt; ti += NW) {
@@ -855,7 +906,10 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
          }
       }
       if (tid == 0) next_job = 0;
+      LP_ADD(3, ts);
+      LP_BEGIN(tb2);
       __syncthreads();
+      LP_ADD(4, tb2);
    }
    if (sfail) {
       const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -872,6 +926,7 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
    }
 
    // ---- backward substitution L^T [y z] = [w_x w_1], right-looking by blocks ----
+   LP_BEGIN(tbw);
    {
       const int kl = npa - KB;
       for (int i = tid; i < npa; i += NT) {
@@ -907,6 +962,13 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
       }
       __syncthreads();
    }
+   LP_ADD(5, tbw);
+#ifdef LL_PROF
+   pf[7] = clock64() - pf_t0;
+   if (lane == 0 && blockIdx.x % 250 == 7)
+      printf("[ll] blk %d n %d npa %d warp %d: D %lld U %lld bar1 %lld S %lld bar2 %lld backward %lld total %lld\n", (int)blockIdx.x, n,
+             npa, warp, pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[7]);
+#endif
    if (warp == 0) {
       double sy = 0.0, sz = 0.0;
       for (int i = lane; i < n; i += 32) { sy += b0[i]; sz += b1[i]; }
@@ -1497,14 +1559,18 @@ static void launch_factor_tma(mchrg_b200_context* ctx, const Args& a, int count,
 
 template <int NT>
 static void launch_factor_ll(mchrg_b200_context* ctx, const Args& a, int count, int npa_max) {
-   const size_t smem = smem_doubles_ll(npa_max) * sizeof(double);
-   ctx->ensure_smem(eeq_factor_ll_kernel<NT>, smem_doubles_ll(NPA_MAX) * sizeof(double), /*max_carveout=*/true);
+   // MCHRG_B200_FACTOR_SMEM_KB: ask for at least this much shared memory per CTA (lowers the number of resident
+   // molecules per SM; residency experiments only)
+   const size_t floor_b = (size_t)std::max<long long>(0, env_ll("MCHRG_B200_FACTOR_SMEM_KB", 0)) * 1024;
+   const size_t smem = std::max(smem_doubles_ll(npa_max) * sizeof(double), floor_b);
+   ctx->ensure_smem(eeq_factor_ll_kernel<NT>, std::max(smem_doubles_ll(NPA_MAX) * sizeof(double), floor_b), /*max_carveout=*/true);
    MCHRG_LAUNCH(ctx, eeq_factor_ll_kernel<NT>, (unsigned)count, NT, smem, a);
 }
 
 #ifndef LL_NT_DEF
 #define LL_NT_DEF 128
 #endif
+
 constexpr int LL_NT = LL_NT_DEF;  // threads per molecule in the factorisation kernel
 
 // Factorisation launches of one chunk: the class-sorted permutation is cut into a few groups of size classes so
