@@ -1,10 +1,10 @@
 #!/bin/bash
-# Whole pipelined batch step (pair A | factorisation | pair C on three streams) under environment settings given as
-# arguments ("A=1+B=2" sets two variables), e.g. the factorisation kernel capped through MCHRG_B200_FACTOR_SMEM_KB.
+# Per-kernel trace times (pair A | factorisation | pair C over the whole 100k-molecule bench mix) under environment
+# settings given as arguments ("A=1+B=2" sets two variables; "" = defaults).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-cat > /tmp/mix.py <<'PY'
-import sys, os, time
+cat > /tmp/envtrace.py <<'PY'
+import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tools"))
 import numpy as np, torch
 import multicharge_b200 as mc
@@ -18,23 +18,19 @@ d_in = [torch.tensor(a, device=dev) for a in (offsets, num, xyz, charge)]
 ntot = int(offsets[-1])
 out = dict(qvec=torch.empty(ntot, dtype=torch.float64, device=dev), energy=torch.empty(ntot, dtype=torch.float64, device=dev),
            gradient=torch.empty(ntot, 3, dtype=torch.float64, device=dev), status=torch.empty(nmol, dtype=torch.int32, device=dev))
-def step_ms(reps=4):
-    mc.singlepoint_batch(model, *d_in, out=out)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        mc.singlepoint_batch(model, *d_in, out=out)
-    torch.cuda.synchronize()
-    return 1e3 * (time.perf_counter() - t0) / reps
+os.environ["MCHRG_B200_TRACE"] = "1"
 ref = None
 for env in sys.argv[1:]:
     kv = dict(x.split("=") for x in env.split("+") if x)
     for k, v in kv.items(): os.environ[k] = v
-    ms = step_ms()
+    best = None
+    for _ in range(4):
+        mc.singlepoint_batch(model, *d_in, out=out); torch.cuda.synchronize()
+        ms, nl = ctx.batch_trace()
+        best = ms if best is None else [min(a, b) for a, b in zip(best, ms)]
     q = out["qvec"].cpu().numpy().copy()
     if ref is None: ref = q
-    print(f"{env or 'default':60s} {ms:8.3f} ms/step  {nmol/ms/1e3:6.3f} M molecules/s  max|dq| {np.abs(q-ref).max():.1e}", flush=True)
+    print(f"{env or 'default':50s} pairA {best[0]:.3f}  factor {best[1]:.3f}  pairC {best[2]:.3f} ms  fails {int((out['status'] != 0).sum())}  max|dq| {np.abs(q - ref).max():.1e}", flush=True)
     for k in kv: os.environ.pop(k)
 PY
-timeout 900 python /tmp/mix.py "$@" > gpurun_out/mix.log 2>&1
-cat gpurun_out/mix.log
+timeout 900 python /tmp/envtrace.py "$@" 2>&1 | tee gpurun_out/env_trace.log | tail -30
