@@ -24,7 +24,8 @@ over that batch.  Molecules are independent, so ranks get disjoint batches and t
                                  seconds through singlepoint_rows (block-cyclic Cholesky with native NCCL panel
                                  broadcasts, row-sharded O(N^2) passes joined by all-reduce, row-sharded dq/dr),
                                  the factorisation alone, each with its own roofline
-                  periodic       configs[3] (N = 1 only): periodic N = 4096 cell, q+E+gradient and + dq/dr, dq/dL
+                  periodic       configs[3]: periodic N = 4096 cell, q+E+gradient (Ewald pair tiles shared between the ranks)
+                                 and, on one GPU, + dq/dr, dq/dL
                   eeqbc          configs[4] size: EEQ-BC cluster (N = 1: largest single-GPU size; N > 1: shared)
 
 `--impl reference` times the CPU oracle alone on the same workload (bounded sample per step) and prints the same
@@ -390,17 +391,21 @@ def _singlepoint_device(torch, mc, model, mol, dev, dq):
     return run
 
 
-def periodic_block(torch, mc, ctx, ext, dev, fp64_peak):
-    """configs[3]: periodic EEQ2019, 16^3 = 4096 jittered sites in a cubic cell, Ewald sums; q+E+gradient+sigma and
-    q+dq/dr+dq/dL (the cpq path)."""
+def periodic_block(torch, mc, ctx, ext, dev, rank, world, fp64_peak):
+    """configs[3]: periodic EEQ2019, 16^3 = 4096 jittered sites in a cubic cell, Ewald sums; q+E+gradient+sigma (on
+    several GPUs the Ewald pair tiles and the rows of Phi W Phi^T are shared between the ranks, one all-reduce of the
+    matrix; every rank ends with everything) and, on one GPU, q+dq/dr+dq/dL (the cpq path; replicated on several)."""
     from synth import periodic_cell
     num, xyz, lat = periodic_cell(16, 20250104)
     mol = mc.Structure(num, xyz, 0.0, lattice=lat)
     model = mc.new_eeq2019_model(mol, ctx)
-    res = {"nat": mol.nat}
-    for tag, dq in (("q_e_grad_seconds", False), ("q_e_grad_dqdr_dqdL_seconds", True)):
+    res = {"nat": mol.nat, "n_gpus": world}
+    cases = (("q_e_grad_seconds", False), ("q_e_grad_dqdr_dqdL_seconds", True)) if world == 1 else (("q_e_grad_seconds", False),)
+    for tag, dq in cases:
         run = _singlepoint_device(torch, mc, model, mol, dev, dq)
-        res[tag] = _timed(torch, ext, run, 2, 1, dev)
+        res[tag] = _timed(torch, ext, run, 2, world, dev)
+        if not dq:
+            res["charge_sum"] = float(run.keep[0]["qvec"].sum().item())
         del run
         torch.cuda.empty_cache()
     n = float(mol.nat)
@@ -659,13 +664,14 @@ def run_ours(args):
             mc.init_comm_from_torch(ctx)  # native NCCL communicator of the single-system path
         blocks = [("batch_strong", lambda: batch_strong_block(torch, mc, ctx, ext, dev, rank, world, nmol, 3)),
                   ("cluster", lambda: cluster_block(torch, mc, ctx, ext, dev, rank, world, args.nat, fp64_peak))]
-        if world == 1:
-            blocks.append(("periodic", lambda: periodic_block(torch, mc, ctx, ext, dev, fp64_peak)))
+        blocks.append(("periodic", lambda: periodic_block(torch, mc, ctx, ext, dev, rank, world, fp64_peak)))
         # configs[4]: N = 32768; the full dq/dr of that size needs the ranks' memory and flops together (25.8 GB per
         # (3, N, N) array, 4.6e14 flop): one GPU reports it at N = 8192
         nat_dq = args.nat_bc if world >= 2 else min(args.nat_bc, 8192)
         blocks.append(("eeqbc", lambda: eeqbc_block(torch, mc, ctx, ext, dev, rank, world, args.nat_bc, fp64_peak, False)))
         blocks.append(("eeqbc_dqdr", lambda: eeqbc_block(torch, mc, ctx, ext, dev, rank, world, nat_dq, fp64_peak, True)))
+        if args.extras:
+            blocks = [b for b in blocks if b[0] in args.extras.split(",")]
         for name, fn in blocks:
             # a failure on one rank would leave the others inside a collective: agree on the outcome per block
             try:
@@ -747,6 +753,7 @@ def main():
     ap.add_argument("--nmol", type=int, default=NMOL)
     ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--extras", default="", help="comma-separated subset of the extra blocks to run (default: all)")
     ap.add_argument("--workload", default="batch", choices=["batch", "cluster"])
     ap.add_argument("--nat", type=int, default=16384, help="atoms of the configs[2] cluster")
     ap.add_argument("--nat-bc", type=int, default=32768, help="atoms of the configs[4] EEQ-BC cluster")

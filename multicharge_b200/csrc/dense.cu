@@ -648,6 +648,10 @@ __global__ void info_combine_kernel(const double* __restrict__ slots, int nranks
 bool dist_rows_apply(const mchrg_b200_context* ctx, int64_t nat) {
    return ctx->comm != nullptr && ctx->comm->nranks > 1 && nat >= env_ll("MCHRG_B200_DIST_MIN", 8192);
 }
+bool dist_pbc_apply(const mchrg_b200_context* ctx, int64_t nat) {
+   return ctx->comm != nullptr && ctx->comm->nranks > 1 && nat >= env_ll("MCHRG_B200_DIST_MIN_PBC", 1024) &&
+          ctx->active == ctx->stream;
+}
 void row_share(const mchrg_b200_context* ctx, int nat, int* row0, int* row1) {
    const int64_t R = ctx->nranks(), r = ctx->rank();
    auto bound = [&](int64_t k) { return (int)std::min<int64_t>(nat, round_up((nat * k + R - 1) / R, 8)); };

@@ -35,6 +35,9 @@ int64_t dpotrf_dist_panel(const mchrg_b200_context* ctx, int64_t n);
 // (coordination number, (J q) / atrace / dadL, CN-gradient contraction) are row-sharded and joined by one
 // all-reduce each, and the factorisation is block-cyclic.  row_share: this rank's rows (multiples of 8).
 bool dist_rows_apply(const mchrg_b200_context* ctx, int64_t nat);
+// periodic structures: the Ewald pair tiles (125 direct translations per image and pair) are shared between the ranks from
+// MCHRG_B200_DIST_MIN_PBC atoms on (default 1024); the factorisation stays replicated below MCHRG_B200_DIST_MIN
+bool dist_pbc_apply(const mchrg_b200_context* ctx, int64_t nat);
 void row_share(const mchrg_b200_context* ctx, int nat, int* row0, int* row1);
 // in-place sum over ranks, ordered after / before the context's current stream
 void comm_allreduce_sum(mchrg_b200_context* ctx, double* buf, size_t count);

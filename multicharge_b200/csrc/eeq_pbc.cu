@@ -229,7 +229,7 @@ __device__ __forceinline__ void tile_coords(int b, int& ti, int& tj) {
 // W(i, j) += direct part (both triangles); W is pre-filled with the reciprocal matrix
 __global__ void __launch_bounds__(256) pbc_amat_tiles_kernel(int nat, const double* __restrict__ xyz,
                                                              const double* __restrict__ rad, PbcDev pb,
-                                                             double* __restrict__ W, int64_t ld) {
+                                                             double* __restrict__ W, int64_t ld, int tile0, int tstride) {
    __shared__ double sdt[3 * NDT];
    __shared__ double swt[3 * 27];
    __shared__ double2 setab[eg::NTAB];
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) pbc_amat_tiles_kernel(int nat, const doub
    for (int k = threadIdx.x; k < 3 * pb.nw; k += blockDim.x) swt[k] = pb.wtrans[k];
    __syncthreads();
    int ti, tj;
-   tile_coords(blockIdx.x, ti, tj);
+   tile_coords((int)blockIdx.x * tstride + tile0, ti, tj);  // several GPUs: tiles tile0, tile0 + tstride, ...
    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    const int j = tj * 32 + lane;
    for (int rr = 0; rr < 4; ++rr) {
@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(256) pbc_damat_tiles_kernel(int nat, const dou
                                                               const double* __restrict__ rad,
                                                               const double* __restrict__ q, PbcDev pb,
                                                               double* __restrict__ B, int64_t ldb,
-                                                              double* __restrict__ atrace, double* __restrict__ dadL) {
+                                                              double* __restrict__ atrace, double* __restrict__ dadL,
+                                                              int tile0, int tstride) {
    __shared__ double sdt[3 * NDT];
    __shared__ double swt[3 * 27];
    __shared__ double2 setab[eg::NTAB];
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(256) pbc_damat_tiles_kernel(int nat, const dou
    for (int k = threadIdx.x; k < 3 * pb.nw; k += blockDim.x) swt[k] = pb.wtrans[k];
    __syncthreads();
    int ti, tj;
-   tile_coords(blockIdx.x, ti, tj);
+   tile_coords((int)blockIdx.x * tstride + tile0, ti, tj);
    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    const int j = tj * 32 + lane;
    double aj[3] = {0.0, 0.0, 0.0}, lj[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -460,18 +461,28 @@ void pbc_end(PbcWork& work) {
 }
 
 void pbc_amat(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a, PbcWork& work,
-              double* W) {
+              double* W, bool shard) {
    auto* st = static_cast<PbcState*>(work.state);
    const int64_t npad = work.npad;
    const int nat = mol.nat;
+   const int R = shard ? ctx->nranks() : 1, r = shard ? ctx->rank() : 0;
    double* PhiW = ctx->alloc<double>((size_t)npad * KREC);
    dim3 gp((unsigned)((npad + 255) / 256), KREC);
    MCHRG_LAUNCH(ctx, pbc_phase_kernel, gp, 256, 0, nat, npad, mol.xyz, st->pb, st->Phi, PhiW);
-   dgemm_padded(ctx, true, npad, npad, KREC, 1.0, PhiW, npad, st->Phi, npad, 0.0, W, npad, false);
-   const int nt = (nat + 31) / 32;
-   MCHRG_LAUNCH(ctx, pbc_amat_tiles_kernel, (unsigned)(nt * (nt + 1) / 2), 256, 0, nat, mol.xyz, rad_a, st->pb, W, npad);
-   MCHRG_LAUNCH(ctx, pbc_amat_diag_kernel, (unsigned)((npad + 127) / 128), 128, 0, nat, npad, rad_a, eta_a, st->pb, W,
-                npad);
+   // reciprocal space Phi W Phi^T: row blocks of 128 shared between the ranks
+   const int64_t nrt = npad / TILE, t0 = nrt * r / R, t1 = nrt * (r + 1) / R;
+   if (shard) MCHRG_CUDA(cudaMemsetAsync(W, 0, (size_t)npad * npad * sizeof(double), ctx->active));
+   if (t1 > t0)
+      dgemm_padded(ctx, true, (t1 - t0) * TILE, npad, KREC, 1.0, PhiW + t0 * TILE, npad, st->Phi, npad, 0.0, W + t0 * TILE, npad,
+                   false);
+   const int nt = (nat + 31) / 32, ntiles = nt * (nt + 1) / 2;
+   if (ntiles > r)
+      MCHRG_LAUNCH(ctx, pbc_amat_tiles_kernel, (unsigned)((ntiles - r + R - 1) / R), 256, 0, nat, mol.xyz, rad_a, st->pb, W, npad,
+                   r, R);
+   if (r == 0)
+      MCHRG_LAUNCH(ctx, pbc_amat_diag_kernel, (unsigned)((npad + 127) / 128), 128, 0, nat, npad, rad_a, eta_a, st->pb, W,
+                   npad);
+   if (shard) comm_allreduce_sum(ctx, W, (size_t)npad * npad);
    work.phase_ready = true;
 }
 
@@ -903,22 +914,27 @@ void pbc_symv(mchrg_b200_context* ctx, int nat, const double* A, int64_t ld, con
 }
 
 void pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q, PbcWork& work,
-                double* B, int64_t ldb, int64_t mp, double* atrace, double* dadL) {
+                double* B, int64_t ldb, int64_t mp, double* atrace, double* dadL, bool shard) {
    auto* st = static_cast<PbcState*>(work.state);
    const int64_t npad = work.npad;
    const int nat = mol.nat;
+   if (shard && B) fail(MCHRG_B200_ERR_ARG, "pbc_derivs: the dq/dr right-hand side is not sharded");
+   const int R = shard ? ctx->nranks() : 1, r = shard ? ctx->rank() : 0;
    if (!work.phase_ready) {
       dim3 gp((unsigned)((npad + 255) / 256), KREC);
       MCHRG_LAUNCH(ctx, pbc_phase_kernel, gp, 256, 0, nat, npad, mol.xyz, st->pb, st->Phi, (double*)nullptr);
    }
-   double* sf = ctx->alloc<double>(KREC);
-   MCHRG_LAUNCH(ctx, pbc_sfac_kernel, KREC / 8, 256, 0, nat, npad, st->Phi, q, sf);
-   MCHRG_LAUNCH(ctx, pbc_rec_rows_kernel, (unsigned)((nat + 127) / 128), 128, 0, nat, npad, st->Phi, sf, st->pb, atrace,
-                dadL);
-   MCHRG_LAUNCH(ctx, pbc_damat_diag_kernel, (unsigned)((nat + 127) / 128), 128, 0, nat, rad_a, q, st->pb, dadL);
-   const int nt = (nat + 31) / 32;
-   MCHRG_LAUNCH(ctx, pbc_damat_tiles_kernel, (unsigned)(nt * (nt + 1) / 2), 256, 0, nat, mol.xyz, rad_a, q, st->pb, B, ldb,
-                atrace, dadL);
+   if (r == 0) {  // reciprocal-space rows (these OVERWRITE atrace / dadL) and the self images
+      double* sf = ctx->alloc<double>(KREC);
+      MCHRG_LAUNCH(ctx, pbc_sfac_kernel, KREC / 8, 256, 0, nat, npad, st->Phi, q, sf);
+      MCHRG_LAUNCH(ctx, pbc_rec_rows_kernel, (unsigned)((nat + 127) / 128), 128, 0, nat, npad, st->Phi, sf, st->pb, atrace,
+                   dadL);
+      MCHRG_LAUNCH(ctx, pbc_damat_diag_kernel, (unsigned)((nat + 127) / 128), 128, 0, nat, rad_a, q, st->pb, dadL);
+   }
+   const int nt = (nat + 31) / 32, ntiles = nt * (nt + 1) / 2;
+   if (ntiles > r)
+      MCHRG_LAUNCH(ctx, pbc_damat_tiles_kernel, (unsigned)((ntiles - r + R - 1) / R), 256, 0, nat, mol.xyz, rad_a, q, st->pb, B,
+                   ldb, atrace, dadL, r, R);
    if (B) {
       double* Psi = ctx->alloc<double>((size_t)mp * KREC);
       dim3 gs((unsigned)((mp + 255) / 256), KREC);

@@ -24,16 +24,21 @@ void pbc_begin(mchrg_b200_context* ctx, const DevMol& mol, PbcHost& host, PbcWor
 void pbc_end(PbcWork& work);
 
 // get_amat_3d (eeq.f90:244-307): Coulomb block into W (order work.npad, ld = npad, identity padding)
+// shard (several GPUs, dist_pbc_apply): every rank evaluates its share of the pair tiles and of the rows of the
+// reciprocal-space product, rank 0 the diagonal; ONE all-reduce of W joins them (every entry has at most two
+// non-zero contributions, so the sum equals the one-GPU result)
 void pbc_amat(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* eta_a, PbcWork& work,
-              double* W);
+              double* W, bool shard = false);
 
 // y = A x for a full symmetric column-major matrix
 void pbc_symv(mchrg_b200_context* ctx, int nat, const double* A, int64_t ld, const double* x, double* y);
 
 // get_damat_3d (eeq.f90:429-508): atrace[3 nat], dadL[9 nat] (overwritten) and, when B != nullptr, the
 // off-diagonal blocks dadr(:, j, k) into B (ld = ldb, mp padded rows; B must be zero-initialised)
+// shard (B == nullptr only): this rank's share of the pair tiles; rank 0 adds the reciprocal-space rows and the self
+// images; atrace / dadL must be zero on entry and are PARTIAL sums on return (the caller all-reduces them)
 void pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q, PbcWork& work,
-                double* B, int64_t ldb, int64_t mp, double* atrace, double* dadL);
+                double* B, int64_t ldb, int64_t mp, double* atrace, double* dadL, bool shard = false);
 
 // Periodic EEQ-BC, charge / energy path (get_cmat_3d eeqbc.f90:1065-1128, get_amat_3d :532-598): fills the
 // capacitance matrix Cm and the Coulomb block W (both order work.npad, ld = npad; padding: Cm zero, W identity)

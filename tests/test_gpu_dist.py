@@ -164,6 +164,41 @@ def test_sharded_singlepoint_vs_oracle(mc, oracle, group, dist_env, nat):
     assert np.abs(dqdr - o["dqdr"]).max() < 1e-10 * max(1.0, np.abs(o["dqdr"]).max())
 
 
+def test_sharded_periodic_singlepoint_vs_oracle(mc, oracle, group, monkeypatch):
+    """Periodic EEQ2019 (configs[3] path) shared by several ranks: Ewald pair tiles and rows of Phi W Phi^T per rank, ONE
+    all-reduce of the matrix, pair tiles of the derivatives per rank joined with the CN-gradient rows; q, E, gradient,
+    sigma against the one-context result and the oracle.  With dq/dr the periodic path stays replicated: same answer."""
+    from synth import periodic_cell
+    monkeypatch.setenv("MCHRG_B200_DIST_MIN_PBC", "128")
+    world = len(group)
+    num, xyz, lat = periodic_cell(7, 343, shear=0.1)
+    mol = mc.Structure(num, xyz, 0.0, lattice=lat)
+    single = mc.new_eeq2019_model(mol).singlepoint(mol, want=("qvec", "energy", "gradient"))
+
+    def body(r):
+        model = mc.new_eeq2019_model(mol, group[r])
+        l0 = group[r].launch_count
+        a = model.singlepoint(mol, want=("qvec", "energy", "gradient"))
+        launches[r] = group[r].launch_count - l0
+        b = model.singlepoint(mol, want=("qvec", "energy", "gradient", "dqdr"))
+        return a, b
+
+    launches = [0] * world
+    res = run_ranks(world, body)
+    # the shared path really ran: only rank 0 launches the diagonal / reciprocal-row kernels
+    assert all(launches[r] < launches[0] for r in range(1, world)), launches
+    omol = oracle.Mol(num, xyz, 0.0, lattice=lat)
+    o = oracle.eeq_singlepoint(oracle.new_eeq2019_model(omol), omol, want=("qvec", "energy", "gradient", "dqdr"))
+    for r, (a, b) in enumerate(res):
+        for key in ("cn", "qvec", "energy", "gradient", "sigma"):
+            scale = max(1.0, np.abs(o[key]).max())
+            assert np.abs(a[key] - o[key]).max() < 1e-10 * scale, (r, key)
+            assert np.abs(a[key] - single[key]).max() < 1e-11 * scale, (r, key)
+            assert np.abs(b[key] - o[key]).max() < 1e-10 * scale, (r, key, "dqdr call")
+        for key in ("dqdr", "dqdL"):
+            assert np.abs(b[key] - o[key]).max() < 1e-10 * max(1.0, np.abs(o[key]).max()), (r, key)
+
+
 def test_two_contexts_two_threads(mc, oracle):
     """A second context in the same process (what a Fortran caller driving several GPUs with OpenMP threads does):
     shared-memory attributes and launch state are per context, the calls are re-entrant."""
