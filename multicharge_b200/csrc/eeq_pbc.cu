@@ -260,13 +260,15 @@ __global__ void __launch_bounds__(256) pbc_amat_tiles_kernel(int nat, const doub
 
 // diagonal: self images (eeq.f90:284-294); padding rows become the identity
 __global__ void pbc_amat_diag_kernel(int nat, int64_t npad, const double* __restrict__ rad,
-                                     const double* __restrict__ eta, PbcDev pb, double* __restrict__ W, int64_t ld) {
+                                     const double* __restrict__ eta, PbcDev pb, double* __restrict__ W, int64_t ld,
+                                     int row0, int row1) {
    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= npad) return;
    if (i >= nat) {
-      W[i + i * ld] = 1.0;
+      if (row0 == 0) W[i + i * ld] = 1.0;  // (several GPUs: the rank that owns the first rows)
       return;
    }
+   if (i < row0 || i >= row1) return;
    const double gam = 1.0 / sqrt(2.0 * rad[i] * rad[i]);
    const unsigned mask = wsc_select(pb.wtrans, pb.nw, 0.0, 0.0, 0.0);
    const double wsw = 1.0 / (double)__popc(mask);
@@ -364,9 +366,9 @@ __global__ void __launch_bounds__(256) pbc_damat_tiles_kernel(int nat, const dou
 
 // self-image stress term (eeq.f90:488-497), real-space part: dadL_i += dS_self q_i
 __global__ void pbc_damat_diag_kernel(int nat, const double* __restrict__ rad, const double* __restrict__ q,
-                                      PbcDev pb, double* __restrict__ dadL) {
+                                      PbcDev pb, double* __restrict__ dadL, int row0, int row1) {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= nat) return;
+   if (i >= nat || i < row0 || i >= row1) return;
    const double gam = 1.0 / sqrt(2.0 * rad[i] * rad[i]);
    const unsigned mask = wsc_select(pb.wtrans, pb.nw, 0.0, 0.0, 0.0);
    const double wsw = 1.0 / (double)__popc(mask);
@@ -479,9 +481,10 @@ void pbc_amat(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, c
    if (ntiles > r)
       MCHRG_LAUNCH(ctx, pbc_amat_tiles_kernel, (unsigned)((ntiles - r + R - 1) / R), 256, 0, nat, mol.xyz, rad_a, st->pb, W, npad,
                    r, R);
-   if (r == 0)
-      MCHRG_LAUNCH(ctx, pbc_amat_diag_kernel, (unsigned)((npad + 127) / 128), 128, 0, nat, npad, rad_a, eta_a, st->pb, W,
-                   npad);
+   int row0 = 0, row1 = nat;  // self images of the diagonal: rows shared like the other row passes
+   if (shard) row_share(ctx, nat, &row0, &row1);
+   MCHRG_LAUNCH(ctx, pbc_amat_diag_kernel, (unsigned)((npad + 127) / 128), 128, 0, nat, npad, rad_a, eta_a, st->pb, W, npad,
+                row0, row1);
    if (shard) comm_allreduce_sum(ctx, W, (size_t)npad * npad);
    work.phase_ready = true;
 }
@@ -924,13 +927,15 @@ void pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a,
       dim3 gp((unsigned)((npad + 255) / 256), KREC);
       MCHRG_LAUNCH(ctx, pbc_phase_kernel, gp, 256, 0, nat, npad, mol.xyz, st->pb, st->Phi, (double*)nullptr);
    }
-   if (r == 0) {  // reciprocal-space rows (these OVERWRITE atrace / dadL) and the self images
+   if (r == 0) {  // reciprocal-space rows (these OVERWRITE atrace / dadL)
       double* sf = ctx->alloc<double>(KREC);
       MCHRG_LAUNCH(ctx, pbc_sfac_kernel, KREC / 8, 256, 0, nat, npad, st->Phi, q, sf);
       MCHRG_LAUNCH(ctx, pbc_rec_rows_kernel, (unsigned)((nat + 127) / 128), 128, 0, nat, npad, st->Phi, sf, st->pb, atrace,
                    dadL);
-      MCHRG_LAUNCH(ctx, pbc_damat_diag_kernel, (unsigned)((nat + 127) / 128), 128, 0, nat, rad_a, q, st->pb, dadL);
    }
+   int row0 = 0, row1 = nat;  // self images: rows shared between the ranks
+   if (shard) row_share(ctx, nat, &row0, &row1);
+   MCHRG_LAUNCH(ctx, pbc_damat_diag_kernel, (unsigned)((nat + 127) / 128), 128, 0, nat, rad_a, q, st->pb, dadL, row0, row1);
    const int nt = (nat + 31) / 32, ntiles = nt * (nt + 1) / 2;
    if (ntiles > r)
       MCHRG_LAUNCH(ctx, pbc_damat_tiles_kernel, (unsigned)((ntiles - r + R - 1) / R), 256, 0, nat, mol.xyz, rad_a, q, st->pb, B,
