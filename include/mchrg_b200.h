@@ -79,7 +79,11 @@ void* mchrg_b200_side_stream(mchrg_b200_context* ctx);
  *     broadcast, every rank updates only the groups it owns (csrc/dense.cu);
  *   - the O(N^2) row passes (coordination number, (J q) / atrace / dadL, CN-gradient contraction) are
  *     row-sharded and joined by one all-reduce each;
- *   - dq/dr is row-sharded by the caller through mchrg_b200_singlepoint_rows (no collective).
+ *   - dq/dr is row-sharded by the caller through mchrg_b200_singlepoint_rows (no collective);
+ *   - periodic EEQ2019 structures (eeq.f90 get_amat_3d / get_damat_3d) of at least MCHRG_B200_DIST_MIN_PBC
+ *     (default 1024) atoms: the Ewald real-space pair tiles, the rows of the reciprocal-space product and the
+ *     self-image rows are shared, one all-reduce of the matrix and one of the derivative rows join them
+ *     (q, E, gradient, sigma; with dq/dr requested the periodic path runs replicated).
  * All ranks must make the same sequence of library calls with the same inputs.
  * Two backends:
  *   NCCL  -- one process per GPU: rank 0 calls comm_unique_id, distributes the 128 bytes by its own means
