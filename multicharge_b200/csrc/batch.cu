@@ -113,6 +113,15 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 
 __device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
 // register-only broadcast of a double (the library overload goes through memory and forces arrays that are
 // shuffled element-wise into local memory)
 __device__ __forceinline__ double shfl_d(double v, int src) {
@@ -696,6 +705,9 @@ constexpr int TS = KB + 1;            // row stride of the diagonal tile
 #define LL_MINB 6
 #endif
 
+#ifndef LL_ASYNC_BACKWARD
+#define LL_ASYNC_BACKWARD 1  // backward substitution fed by cp.async-staged strips (0: direct loads)
+#endif
 #ifndef LL_UNROLL
 #define LL_UNROLL 2  // block pairs of the left-looking update in flight per warp (each: four 16-byte loads from L2)
 #endif
@@ -935,8 +947,112 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
       }
    }
    __syncthreads();
-   // (tried: fetching the next step's strip column and inverted diagonal tile one step ahead into registers --
-   //  32 more live doubles push the kernel over its register budget: 11.2 vs 10.1 ms per 100k molecules)
+   // Every operand of the sweep is known in advance -- only the FMAs wait for y -- so the strips of L and the inverted
+   // diagonal tiles are staged through shared memory with cp.async (no registers: fetching them one step ahead into
+   // registers pushed the kernel over its budget, 11.2 vs 10.1 ms per 100k molecules), two 64-column chunks and one tile
+   // ahead of their use; a step then costs shared-memory latencies and a few barriers instead of two dependent L2 /
+   // HBM round trips.  The chunks live in whatever the molecule leaves free of the launch's shared memory: behind
+   // b0 | b1 in the block-column buffer and / or behind its own arrays (two 8 KB stages fit for every order when the
+   // launch is sized for the largest class; otherwise the direct loads below).
+   constexpr int STG = 2 * 8 * 64;  // doubles per stage: 16 rows x 64 columns as 2 x 8 fragment-order blocks
+   unsigned dyn_bytes;
+   asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+   const int own = (int)smem_doubles_ll(npa);
+   const int n_cb = (npa > 2 * KB) ? ((npa - KB) * KB - 2 * npa) / STG : 0;
+   const int n_af = ((int)(dyn_bytes / sizeof(double)) - own) / STG;
+   if (LL_ASYNC_BACKWARD && NT == 128 && n_cb + n_af >= 2) {  // (the update below maps 128 threads to 64 columns x 2 right-hand sides)
+      double* stage[2];
+      stage[0] = (n_cb >= 1) ? Cb + 2 * npa : sm + own;
+      stage[1] = (n_cb >= 2) ? Cb + 2 * npa + STG : sm + own + (n_cb >= 1 ? 0 : STG);
+      int ik0 = npa - KB, ic0 = 0;  // next chunk to fetch: columns [ic0, ic0 + 64) of the strip of block row ik0
+      auto issue_tile = [&](int k0, double* dst) {  // blocks (R,R) | (R+1,R) (R+1,R+1) of the inverted diagonal tile
+         if (k0 >= 0 && tid < 96) {
+            const int R0 = k0 >> 3;
+            cp_async16(dst + 2 * tid, tid < 32 ? S + 64 * (tri(R0) + R0) + 2 * tid : S + 64 * (tri(R0 + 1) + R0) + 2 * (tid - 32));
+         }
+         cp_async_commit();
+      };
+      auto issue_chunk = [&](double* dst) {
+         if (ik0 >= KB) {
+            const int R0 = ik0 >> 3, C0 = ic0 >> 3, nbc = min(8, R0 - C0);
+            for (int i = tid; i < 64 * nbc; i += NT) {  // 2 block rows x nbc blocks x 32 chunks of 16 bytes
+               const int blk = i >> 5, w = i & 31, rb = (blk >= nbc) ? 1 : 0, cbk = blk - rb * nbc;
+               // odd blocks swap the halves of their rows: neighbouring blocks read conflict-free (see the reads)
+               cp_async16(dst + (rb * 8 + cbk) * 64 + 2 * (w ^ ((cbk & 1) << 2)), S + 64 * (tri(R0 + rb) + C0 + cbk) + 2 * w);
+            }
+            ic0 += 64;
+            if (ic0 >= ik0) { ik0 -= KB; ic0 = 0; }
+         }
+         cp_async_commit();  // (an empty group keeps the group count in step)
+      };
+      // groups are numbered in commit order; a wait names how many NEWER groups may stay in flight
+      int ncommit = 0;
+      auto wait_for = [&](int group) {
+         const int newer = ncommit - 1 - group;
+         if (newer <= 0) cp_async_wait<0>();
+         else if (newer == 1) cp_async_wait<1>();
+         else if (newer == 2) cp_async_wait<2>();
+         else cp_async_wait<3>();
+      };
+      issue_tile(npa - KB, T);
+      int g_t0 = ncommit++, g_t1 = -1;  // groups of the tiles in T / Li
+      issue_chunk(stage[0]);
+      int g_s0 = ncommit++;
+      issue_chunk(stage[1]);
+      int g_s1 = ncommit++;
+      int use = 0;
+      for (int k0 = npa - KB, tb = 0; k0 >= 0; k0 -= KB, tb ^= 1) {
+         wait_for(tb ? g_t1 : g_t0);
+         __syncthreads();  // tile visible; the updates of the previous step are complete, its last stage is free
+         if (k0 < npa - KB) {
+            issue_chunk(stage[use ^ 1]);
+            (use ? g_s0 : g_s1) = ncommit++;
+         }
+         issue_tile(k0 - KB, tb ? T : Li);
+         (tb ? g_t0 : g_t1) = ncommit++;
+         const double* Tk = tb ? Li : T;
+         if (warp == ((blockIdx.x + (k0 >> 4)) % NW)) {  // y_blk = inv(L_kk)^T w_blk ; lane = (r, rhs h)
+            const int r = lane & 15, h = lane >> 4;
+            const double* wv = (h ? b1 : b0) + k0;
+            double v0 = 0.0, v1 = 0.0;  // two chains: the step waits for this sum
+#pragma unroll
+            for (int c = 0; c < KB; c += 2) {
+               if (c >= r)
+                  v0 = fma(Tk[(c < 8 ? 0 : 64 + 64 * (r >> 3)) + ((((c & 7) << 2) + (r & 3)) << 1) + ((r >> 2) & 1)], wv[c], v0);
+               if (c + 1 >= r)
+                  v1 = fma(Tk[(c + 1 < 8 ? 0 : 64 + 64 * (r >> 3)) + (((((c + 1) & 7) << 2) + (r & 3)) << 1) + ((r >> 2) & 1)], wv[c + 1], v1);
+            }
+            __syncwarp();
+            (h ? b1 : b0)[k0 + r] = v0 + v1;
+         }
+         __syncthreads();
+         for (int c0 = 0; c0 < k0; c0 += 64) {  // w(:k0) -= L(blk, :k0)^T y_blk ; thread = (column, rhs)
+            wait_for(use ? g_s1 : g_s0);
+            __syncthreads();  // chunk visible; (for c0 > 0) everybody is done with the stage refilled below
+            if (c0 > 0) {
+               issue_chunk(stage[use ^ 1]);
+               (use ? g_s0 : g_s1) = ncommit++;
+            }
+            const int jl = tid & 63, h = tid >> 6, j = c0 + jl;
+            if (j < k0) {
+               double* bh = h ? b1 : b0;
+               const double* st = stage[use];
+               const int cbk = jl >> 3, cc = jl & 7, sw = (cbk & 1) << 3;
+               double acc = bh[j], acc1 = 0.0;
+#pragma unroll
+               for (int r = 0; r < 8; ++r) {
+                  const int e = ((((r << 2) + (cc & 3)) << 1) ^ sw) + (cc >> 2);
+                  acc = fma(-st[cbk * 64 + e], bh[k0 + r], acc);
+                  acc1 = fma(-st[(8 + cbk) * 64 + e], bh[k0 + 8 + r], acc1);
+               }
+               bh[j] = acc + acc1;
+            }
+            use ^= 1;
+         }
+         // (the stage of this step's last chunk is refilled behind the first barrier of the next step)
+      }
+      cp_async_wait<0>();
+   } else {
    for (int k0 = npa - KB; k0 >= 0; k0 -= KB) {
       if (warp == ((blockIdx.x + (k0 >> 4)) % NW)) {  // y_blk = inv(L_kk)^T w_blk ; lane = (r, rhs h)
          const int r = lane & 15, h = lane >> 4;
@@ -961,6 +1077,7 @@ __global__ void __launch_bounds__(NT, LL_MINB) eeq_factor_ll_kernel(Args p) {
          b1[j] = s1;
       }
       __syncthreads();
+   }
    }
    LP_ADD(5, tbw);
 #ifdef LL_PROF
