@@ -25,7 +25,7 @@ over that batch.  Molecules are independent, so ranks get disjoint batches and t
                                  broadcasts, row-sharded O(N^2) passes joined by all-reduce, row-sharded dq/dr),
                                  the factorisation alone, each with its own roofline
                   periodic       configs[3]: periodic N = 4096 cell, q+E+gradient (Ewald pair tiles shared between the ranks)
-                                 and, on one GPU, + dq/dr, dq/dL
+                                 and + dq/dr, dq/dL (dq/dr rows sharded over the ranks)
                   eeqbc          configs[4] size: EEQ-BC cluster (N = 1: largest single-GPU size; N > 1: shared)
 
 `--impl reference` times the CPU oracle alone on the same workload (bounded sample per step) and prints the same
@@ -394,21 +394,38 @@ def _singlepoint_device(torch, mc, model, mol, dev, dq):
 def periodic_block(torch, mc, ctx, ext, dev, rank, world, fp64_peak):
     """configs[3]: periodic EEQ2019, 16^3 = 4096 jittered sites in a cubic cell, Ewald sums; q+E+gradient+sigma (on
     several GPUs the Ewald pair tiles and the rows of Phi W Phi^T are shared between the ranks, one all-reduce of the
-    matrix; every rank ends with everything) and, on one GPU, q+dq/dr+dq/dL (the cpq path; replicated on several)."""
+    matrix; every rank ends with everything) and q+dq/dr+dq/dL (the cpq path; on several GPUs the dq/dr rows are
+    sharded over the ranks through singlepoint_rows, dq/dL on every rank)."""
     from synth import periodic_cell
+    from multicharge_b200.shard import row_bounds
     num, xyz, lat = periodic_cell(16, 20250104)
     mol = mc.Structure(num, xyz, 0.0, lattice=lat)
     model = mc.new_eeq2019_model(mol, ctx)
-    res = {"nat": mol.nat, "n_gpus": world}
-    cases = (("q_e_grad_seconds", False), ("q_e_grad_dqdr_dqdL_seconds", True)) if world == 1 else (("q_e_grad_seconds", False),)
-    for tag, dq in cases:
-        run = _singlepoint_device(torch, mc, model, mol, dev, dq)
-        res[tag] = _timed(torch, ext, run, 2, world, dev)
-        if not dq:
-            res["charge_sum"] = float(run.keep[0]["qvec"].sum().item())
+    nat = mol.nat
+    res = {"nat": nat, "n_gpus": world}
+    run = _singlepoint_device(torch, mc, model, mol, dev, False)
+    res["q_e_grad_seconds"] = _timed(torch, ext, run, 2, world, dev)
+    res["charge_sum"] = float(run.keep[0]["qvec"].sum().item())
+    del run
+    torch.cuda.empty_cache()
+    if world == 1:
+        run = _singlepoint_device(torch, mc, model, mol, dev, True)
+        res["q_e_grad_dqdr_dqdL_seconds"] = _timed(torch, ext, run, 2, world, dev)
         del run
-        torch.cuda.empty_cache()
-    n = float(mol.nat)
+    else:
+        bounds = row_bounds(nat, world)
+        jb, je = int(bounds[rank]), int(bounds[rank + 1])
+        f64 = dict(dtype=torch.float64, device=dev)
+        txyz, tid = torch.tensor(mol.xyz, device=dev), torch.tensor(mol.id, device=dev)
+        out = mc.api.SolveResult(cn=torch.empty(nat, **f64), qvec=torch.empty(nat, **f64), energy=torch.zeros(nat, **f64),
+                                 gradient=torch.empty(je - jb, 3, **f64), sigma=torch.zeros(3, 3, **f64),
+                                 dqdr=torch.empty(nat, je - jb, 3, **f64), dqdL=torch.empty(nat, 3, 3, **f64))
+        res["q_e_grad_dqdr_dqdL_seconds"] = _timed(
+            torch, ext, lambda: mc.singlepoint_rows(model, mol, jb, je, out=out, xyz=txyz, id=tid), 2, world, dev)
+        res["rows_per_rank"] = [int(x) for x in np.diff(bounds)]
+        del out
+    torch.cuda.empty_cache()
+    n = float(nat)
     fl = n ** 3 / 3.0 + 2.0 * n * n * 256.0
     res["roofline"] = {"bound": "fp64-alu", "kernel": "pbc_amat_tiles_kernel / pbc_damat_tiles_kernel (Ewald real-space pair tiles)",
                        "note": "pair kernels are FP64-ALU / issue bound; dense part (Cholesky + Phi W Phi^T) for scale",

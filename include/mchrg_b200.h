@@ -83,7 +83,8 @@ void* mchrg_b200_side_stream(mchrg_b200_context* ctx);
  *   - periodic EEQ2019 structures (eeq.f90 get_amat_3d / get_damat_3d) of at least MCHRG_B200_DIST_MIN_PBC
  *     (default 1024) atoms: the Ewald real-space pair tiles, the rows of the reciprocal-space product and the
  *     self-image rows are shared, one all-reduce of the matrix and one of the derivative rows join them
- *     (q, E, gradient, sigma; with dq/dr requested the periodic path runs replicated).
+ *     (q, E, gradient, sigma); dq/dr rows of a periodic structure are sharded through mchrg_b200_singlepoint_rows
+ *     like the molecular ones.
  * All ranks must make the same sequence of library calls with the same inputs.
  * Two backends:
  *   NCCL  -- one process per GPU: rank 0 calls comm_unique_id, distributes the 128 bytes by its own means
@@ -190,7 +191,7 @@ int mchrg_b200_singlepoint(const mchrg_b200_model* model, const mchrg_b200_struc
  * while cn, energy, sigma, qvec and dqdL are complete on every caller.  The right-side solves that
  * produce dq/dr act on its rows independently, so ranks that own disjoint blocks need NO data-path
  * collective; with a communicator on the context the factorisation and the O(N^2) row passes are shared as
- * described above (see DESIGN.md "Multi-GPU").  Non-periodic structures only. */
+ * described above (see DESIGN.md "Multi-GPU").  EEQ2019: molecular and periodic structures; EEQ-BC: molecular. */
 int mchrg_b200_singlepoint_rows(const mchrg_b200_model* model, const mchrg_b200_structure* mol, int32_t row_begin,
                                 int32_t row_end, double* cn, double* energy, double* gradient_rows, double* sigma,
                                 double* qvec, double* dqdr_rows, double* dqdL);

@@ -507,10 +507,9 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
    const bool grad = io.gradient && io.sigma && (dcn || lazy);
    const int jb = io.jb, je = io.je < 0 ? nat : io.je, nj = je - jb;
    if (jb < 0 || je > nat || nj <= 0) fail(MCHRG_B200_ERR_ARG, "invalid row block [%d, %d)", jb, je);
-   if (pbc && nj != nat) fail(MCHRG_B200_ERR_MODEL, "row blocks are not available for periodic structures");
    // one large system on several GPUs: the O(N^2) row passes are row-sharded and joined by one all-reduce; periodic
-   // structures share the Ewald pair tiles instead (dq/dr of a periodic structure stays replicated)
-   const bool shard = pbc ? (!cpq && dist_pbc_apply(ctx, nat)) : dist_rows_apply(ctx, nat);
+   // structures share the Ewald pair tiles instead
+   const bool shard = pbc ? dist_pbc_apply(ctx, nat) : dist_rows_apply(ctx, nat);
    int row0 = 0, row1 = nat;
    if (shard) row_share(ctx, nat, &row0, &row1);
 
@@ -565,7 +564,7 @@ static int solve_eeq_device(const mchrg_b200_model* model, const DevMol& mol, co
       if (pbc) {
          // sharded: (J q) by rank 0 alone, pair tiles of the derivatives by all ranks -- partial sums in `pack`
          if (io.energy && (!shard || ctx->rank() == 0)) pbc_symv(ctx, nat, Jc, npad, vrhs, jq);
-         if (grad || cpq) pbc_derivs(ctx, mol, ap.rad, vrhs, ps.work, Bm, mp, mp, atrace, dadL, shard);
+         if (grad || cpq) pbc_derivs(ctx, mol, ap.rad, vrhs, ps.work, Bm, mp, mp, atrace, dadL, shard, jb, je);
       } else {
          eeq_pair_rows_0d(ctx, mol, ap.rad, ap.eta, vrhs, jq, atrace, dadL, row0, row1);
       }

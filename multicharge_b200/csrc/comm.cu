@@ -121,11 +121,13 @@ struct LocalGroup {
          return;
       }
       const auto t0 = std::chrono::steady_clock::now();
+      // MCHRG_B200_COMM_TIMEOUT_S: how long a rank waits for its peers before it declares the group broken (default 120)
+      const double limit = (double)std::max<long long>(1, env_ll("MCHRG_B200_COMM_TIMEOUT_S", 120));
       for (uint64_t spin = 0; gen.load(std::memory_order_acquire) == g; ++spin) {
          if (broken.load(std::memory_order_relaxed)) fail(MCHRG_B200_ERR_CUDA, "local collective: a peer rank failed");
          if (spin > 2000) std::this_thread::yield();
          if ((spin & 0xffff) == 0xffff &&
-             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0) {
+             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit) {
             broken.store(1);
             fail(MCHRG_B200_ERR_CUDA, "local collective timed out: the ranks did not issue the same collectives");
          }

@@ -201,14 +201,15 @@ __global__ void pbc_rec_rows_kernel(int nat, int64_t npad, const double* __restr
 }
 
 // Psi((3j+c), G) = -q_j coef_G G_c s_Gj ; Psi((3j+c), 124+G) = +q_j coef_G G_c c_Gj ; rest zero
-__global__ void pbc_psi_kernel(int nat, int64_t npad, int64_t mp, const double* __restrict__ Phi,
+// (rows of the atom block [jb, jb + nj), numbered within the block)
+__global__ void pbc_psi_kernel(int jb, int nj, int64_t npad, int64_t mp, const double* __restrict__ Phi,
                                const double* __restrict__ q, PbcDev pb, double* __restrict__ Psi) {
    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    const int col = blockIdx.y;
    if (r >= mp) return;
    double v = 0.0;
-   if (r < 3 * (int64_t)nat && col < 2 * NRT) {
-      const int j = (int)(r / 3), c = (int)(r % 3), gi = col % NRT;
+   if (r < 3 * (int64_t)nj && col < 2 * NRT) {
+      const int j = jb + (int)(r / 3), c = (int)(r % 3), gi = col % NRT;
       const double f = q[j] * pb.rcoef[gi] * pb.rtrans[3 * gi + c];
       v = (col < NRT) ? -f * Phi[j + (int64_t)(NRT + gi) * npad] : f * Phi[j + (int64_t)gi * npad];
    }
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(256) pbc_damat_tiles_kernel(int nat, const dou
                                                               const double* __restrict__ q, PbcDev pb,
                                                               double* __restrict__ B, int64_t ldb,
                                                               double* __restrict__ atrace, double* __restrict__ dadL,
-                                                              int tile0, int tstride) {
+                                                              int tile0, int tstride, int jb, int je) {
    __shared__ double sdt[3 * NDT];
    __shared__ double swt[3 * 27];
    __shared__ double2 setab[eg::NTAB];
@@ -299,6 +300,10 @@ __global__ void __launch_bounds__(256) pbc_damat_tiles_kernel(int nat, const dou
    __syncthreads();
    int ti, tj;
    tile_coords((int)blockIdx.x * tstride + tile0, ti, tj);
+   // B is written for the rows of the atom block [jb, je) only (rows numbered within the block); a pass without the
+   // row sums (atrace == nullptr) skips the tiles that hold no atom of the block
+   const bool sums = atrace != nullptr;
+   if (!sums && (ti * 32 >= je || ti * 32 + 32 <= jb) && (tj * 32 >= je || tj * 32 + 32 <= jb)) return;
    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    const int j = tj * 32 + lane;
    double aj[3] = {0.0, 0.0, 0.0}, lj[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -323,12 +328,13 @@ __global__ void __launch_bounds__(256) pbc_damat_tiles_kernel(int nat, const dou
 #pragma unroll
          for (int c = 0; c < 6; ++c) s[c] *= wsw;
          if (B) {
-            double* bji = B + (int64_t)i * ldb + 3 * j;  // dadr(:, j, i)
-            double* bij = B + (int64_t)j * ldb + 3 * i;  // dadr(:, i, j)
+            double* bji = B + (int64_t)i * ldb + 3 * (j - jb);  // dadr(:, j, i)
+            double* bij = B + (int64_t)j * ldb + 3 * (i - jb);  // dadr(:, i, j)
+            const bool jin = j >= jb && j < je, iin = i >= jb && i < je;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-               bji[c] = g[c] * qj;
-               bij[c] = -g[c] * qi;
+               if (jin) bji[c] = g[c] * qj;
+               if (iin) bij[c] = -g[c] * qi;
             }
          }
 #pragma unroll
@@ -336,6 +342,7 @@ __global__ void __launch_bounds__(256) pbc_damat_tiles_kernel(int nat, const dou
 #pragma unroll
          for (int c = 0; c < 6; ++c) lj[c] += s[c] * qi;
       }
+      if (!sums) continue;  // (warp-uniform)
       // row-i reductions over the lanes
       double ri[9];
 #pragma unroll
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(256) pbc_damat_tiles_kernel(int nat, const dou
          atomicAdd(d + 6, ri[5]); atomicAdd(d + 7, ri[7]); atomicAdd(d + 8, ri[8]);
       }
    }
-   if (j < nat) {
+   if (sums && j < nat) {
 #pragma unroll
       for (int c = 0; c < 3; ++c)
          if (aj[c] != 0.0) atomicAdd(atrace + 3 * j + c, aj[c]);
@@ -917,11 +924,12 @@ void pbc_symv(mchrg_b200_context* ctx, int nat, const double* A, int64_t ld, con
 }
 
 void pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q, PbcWork& work,
-                double* B, int64_t ldb, int64_t mp, double* atrace, double* dadL, bool shard) {
+                double* B, int64_t ldb, int64_t mp, double* atrace, double* dadL, bool shard, int jb, int je) {
    auto* st = static_cast<PbcState*>(work.state);
    const int64_t npad = work.npad;
    const int nat = mol.nat;
-   if (shard && B) fail(MCHRG_B200_ERR_ARG, "pbc_derivs: the dq/dr right-hand side is not sharded");
+   if (je < 0) je = nat;
+   const int nj = je - jb;
    const int R = shard ? ctx->nranks() : 1, r = shard ? ctx->rank() : 0;
    if (!work.phase_ready) {
       dim3 gp((unsigned)((npad + 255) / 256), KREC);
@@ -937,13 +945,20 @@ void pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a,
    if (shard) row_share(ctx, nat, &row0, &row1);
    MCHRG_LAUNCH(ctx, pbc_damat_diag_kernel, (unsigned)((nat + 127) / 128), 128, 0, nat, rad_a, q, st->pb, dadL, row0, row1);
    const int nt = (nat + 31) / 32, ntiles = nt * (nt + 1) / 2;
+   // One pass over the pair tiles feeds the row sums AND B when this context evaluates every pair and wants every row
+   // of B anyway.  Otherwise two passes: the row sums of ALL atoms (tiles shared round robin between the ranks when
+   // `shard`; the caller all-reduces them), then B for the atom block [jb, je) from the tiles that hold one of its atoms.
+   const bool fused = B && R == 1 && nj == nat;
    if (ntiles > r)
-      MCHRG_LAUNCH(ctx, pbc_damat_tiles_kernel, (unsigned)((ntiles - r + R - 1) / R), 256, 0, nat, mol.xyz, rad_a, q, st->pb, B,
-                   ldb, atrace, dadL, r, R);
+      MCHRG_LAUNCH(ctx, pbc_damat_tiles_kernel, (unsigned)((ntiles - r + R - 1) / R), 256, 0, nat, mol.xyz, rad_a, q, st->pb,
+                   fused ? B : (double*)nullptr, ldb, atrace, dadL, r, R, jb, je);
+   if (B && !fused)
+      MCHRG_LAUNCH(ctx, pbc_damat_tiles_kernel, (unsigned)ntiles, 256, 0, nat, mol.xyz, rad_a, q, st->pb, B, ldb,
+                   (double*)nullptr, (double*)nullptr, 0, 1, jb, je);
    if (B) {
       double* Psi = ctx->alloc<double>((size_t)mp * KREC);
       dim3 gs((unsigned)((mp + 255) / 256), KREC);
-      MCHRG_LAUNCH(ctx, pbc_psi_kernel, gs, 256, 0, nat, npad, mp, st->Phi, q, st->pb, Psi);
+      MCHRG_LAUNCH(ctx, pbc_psi_kernel, gs, 256, 0, jb, nj, npad, mp, st->Phi, q, st->pb, Psi);
       dgemm_padded(ctx, true, mp, npad, KREC, 1.0, Psi, mp, st->Phi, npad, 1.0, B, ldb, false);
    }
 }

@@ -35,10 +35,12 @@ void pbc_symv(mchrg_b200_context* ctx, int nat, const double* A, int64_t ld, con
 
 // get_damat_3d (eeq.f90:429-508): atrace[3 nat], dadL[9 nat] (overwritten) and, when B != nullptr, the
 // off-diagonal blocks dadr(:, j, k) into B (ld = ldb, mp padded rows; B must be zero-initialised)
-// shard (B == nullptr only): this rank's share of the pair tiles; rank 0 adds the reciprocal-space rows and the self
-// images; atrace / dadL must be zero on entry and are PARTIAL sums on return (the caller all-reduces them)
+// shard: this rank's share of the pair tiles feeds the row sums; rank 0 adds the reciprocal-space rows, the self images
+// are row-shared; atrace / dadL must be zero on entry and are PARTIAL sums on return (the caller all-reduces them).
+// [jb, je): atom block whose rows of B are built (rows numbered within the block, mp >= 3 (je - jb) + 9).
 void pbc_derivs(mchrg_b200_context* ctx, const DevMol& mol, const double* rad_a, const double* q, PbcWork& work,
-                double* B, int64_t ldb, int64_t mp, double* atrace, double* dadL, bool shard = false);
+                double* B, int64_t ldb, int64_t mp, double* atrace, double* dadL, bool shard = false, int jb = 0,
+                int je = -1);
 
 // Periodic EEQ-BC, charge / energy path (get_cmat_3d eeqbc.f90:1065-1128, get_amat_3d :532-598): fills the
 // capacitance matrix Cm and the Coulomb block W (both order work.npad, ld = npad; padding: Cm zero, W identity)

@@ -15,6 +15,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # in-process communicator of the multi-rank GPU tests: a rank whose peer failed gives up after 30 s, not 120
+    os.environ.setdefault("MCHRG_B200_COMM_TIMEOUT_S", "30")
 
 
 def load_golden(name):

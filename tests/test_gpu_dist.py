@@ -167,7 +167,7 @@ def test_sharded_singlepoint_vs_oracle(mc, oracle, group, dist_env, nat):
 def test_sharded_periodic_singlepoint_vs_oracle(mc, oracle, group, monkeypatch):
     """Periodic EEQ2019 (configs[3] path) shared by several ranks: Ewald pair tiles and rows of Phi W Phi^T per rank, ONE
     all-reduce of the matrix, pair tiles of the derivatives per rank joined with the CN-gradient rows; q, E, gradient,
-    sigma against the one-context result and the oracle.  With dq/dr the periodic path stays replicated: same answer."""
+    sigma against the one-context result and the oracle; dq/dr in full on every rank and by row blocks (one per rank)."""
     from synth import periodic_cell
     monkeypatch.setenv("MCHRG_B200_DIST_MIN_PBC", "128")
     world = len(group)
@@ -175,13 +175,20 @@ def test_sharded_periodic_singlepoint_vs_oracle(mc, oracle, group, monkeypatch):
     mol = mc.Structure(num, xyz, 0.0, lattice=lat)
     single = mc.new_eeq2019_model(mol).singlepoint(mol, want=("qvec", "energy", "gradient"))
 
+    from multicharge_b200.shard import row_bounds
+    bounds = row_bounds(mol.nat, world, multiple=8)
+    assert np.all(np.diff(bounds) > 0)
+
     def body(r):
         model = mc.new_eeq2019_model(mol, group[r])
         l0 = group[r].launch_count
         a = model.singlepoint(mol, want=("qvec", "energy", "gradient"))
         launches[r] = group[r].launch_count - l0
         b = model.singlepoint(mol, want=("qvec", "energy", "gradient", "dqdr"))
+        rows[r] = mc.singlepoint_rows(model, mol, int(bounds[r]), int(bounds[r + 1]))  # dq/dr rows of this rank
         return a, b
+
+    rows = [None] * world
 
     launches = [0] * world
     res = run_ranks(world, body)
@@ -197,6 +204,16 @@ def test_sharded_periodic_singlepoint_vs_oracle(mc, oracle, group, monkeypatch):
             assert np.abs(b[key] - o[key]).max() < 1e-10 * scale, (r, key, "dqdr call")
         for key in ("dqdr", "dqdL"):
             assert np.abs(b[key] - o[key]).max() < 1e-10 * max(1.0, np.abs(o[key]).max()), (r, key)
+    dqdr = np.zeros_like(o["dqdr"])
+    grad = np.zeros_like(o["gradient"])
+    for r in range(world):
+        jb, je = int(bounds[r]), int(bounds[r + 1])
+        dqdr[:, jb:je, :] = rows[r]["dqdr"]
+        grad[jb:je] = rows[r]["gradient"]
+        for key in ("qvec", "energy", "sigma", "dqdL"):
+            assert np.abs(rows[r][key] - o[key]).max() < 1e-10 * max(1.0, np.abs(o[key]).max()), (r, key, "rows")
+    assert np.abs(dqdr - o["dqdr"]).max() < 1e-10 * max(1.0, np.abs(o["dqdr"]).max())
+    assert np.abs(grad - o["gradient"]).max() < 1e-10 * max(1.0, np.abs(o["gradient"]).max())
 
 
 def test_two_contexts_two_threads(mc, oracle):

@@ -98,3 +98,32 @@ def test_eeqbc_row_blocks_concatenate_to_full(mc, oracle):
     for got, key in ((grad, "gradient"), (dqdr, "dqdr")):
         assert np.abs(got - full[key]).max() < 1e-12 * max(1.0, np.abs(full[key]).max())
         assert np.abs(got - o[key]).max() < 1e-10 * max(1.0, np.abs(o[key]).max())
+
+
+@pytest.mark.parametrize("ncell,blocks,shear", [(6, 3, 0.0), (7, 2, 0.1)])
+def test_periodic_row_blocks_concatenate_to_full(mc, oracle, ncell, blocks, shear):
+    """Periodic EEQ2019 (configs[3] path): dq/dr rows of disjoint atom blocks -- the pair tiles of a block in a second
+    pass, Psi rows of the block for the reciprocal-space part -- concatenate to the one-call result and match the oracle."""
+    from synth import periodic_cell
+    num, xyz, lat = periodic_cell(ncell, 77 + ncell, shear=shear)
+    nat = len(num)
+    mol = mc.Structure(num, xyz, 0.0, lattice=lat)
+    model = mc.new_eeq2019_model(mol)
+    full = model.singlepoint(mol, want=("qvec", "energy", "gradient", "dqdr"))
+    bounds = np.linspace(0, nat, blocks + 1).astype(int)
+    bounds[1] = bounds[1] // 2 + 7  # unequal blocks, boundaries off the 32-atom tile grid
+    grad = np.zeros((nat, 3))
+    dqdr = np.zeros((nat, nat, 3))
+    for b in range(blocks):
+        jb, je = int(bounds[b]), int(bounds[b + 1])
+        r = mc.singlepoint_rows(model, mol, jb, je)
+        grad[jb:je] = r["gradient"]
+        dqdr[:, jb:je, :] = r["dqdr"]
+        for key in ("cn", "qvec", "energy", "sigma", "dqdL"):
+            assert np.abs(r[key] - full[key]).max() < 1e-11 * max(1.0, np.abs(full[key]).max()), key
+    assert np.abs(grad - full["gradient"]).max() < 1e-11 * max(1.0, np.abs(full["gradient"]).max())
+    assert np.abs(dqdr - full["dqdr"]).max() < 1e-11 * max(1.0, np.abs(full["dqdr"]).max())
+    omol = oracle.Mol(num, xyz, 0.0, lattice=lat)
+    o = oracle.eeq_singlepoint(oracle.new_eeq2019_model(omol), omol, want=("qvec", "energy", "gradient", "dqdr"))
+    assert np.abs(dqdr - o.dqdr).max() < 1e-10 * max(1.0, np.abs(o.dqdr).max())
+    assert np.abs(grad - o.gradient).max() < 1e-10 * max(1.0, np.abs(o.gradient).max())
