@@ -1732,6 +1732,22 @@ static void launch_class(mchrg_b200_context* ctx, const Args& a, int count) {
 namespace mchrg {
 namespace batch {
 
+// what the split path derives from the molecule offsets alone (kept on the context between calls)
+struct SplitPlan {
+   std::vector<int64_t> hoff;
+   int maxchunk = 0, nchunk = 0;
+   std::vector<std::vector<size_t>> starts;  // per chunk: start of every size class in the permutation
+   std::vector<std::vector<int>> counts;     // per chunk: molecules per size class
+   std::vector<size_t> chunk_off;            // chunk boundaries in the permutation
+   int64_t nscr = 0;                         // doubles of scratch for the matrices
+   int32_t* dperm = nullptr;                 // device: class-sorted molecule ids
+   int64_t* d_soff = nullptr;                // device: start of every molecule's matrix in the scratch
+   ~SplitPlan() {
+      if (dperm) cudaFree(dperm);
+      if (d_soff) cudaFree(d_soff);
+   }
+};
+
 // bucket the molecules [m0, m1) by padded order; returns the class-sorted permutation (chunk-local ids)
 // and the start of every class in it.  Molecules above NP_MAX atoms are left out (the entry point sends
 // them through the single-system path afterwards).
@@ -1894,33 +1910,49 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
          a.energy = ctx->out(energy, ntot);
          a.gradient = ctx->out(gradient, 3 * ntot);
          a.status = ctx->out(status, (size_t)nmol);
-         std::vector<int64_t> soff;
-         const int64_t nscr = batch::plan_scratch(hoff, 0, nmol, soff);
-         a.scratch = ctx->alloc<double>((size_t)nscr);
-         int64_t* d_soff = ctx->alloc<int64_t>(nmol);
-         MCHRG_CUDA(cudaMemcpyAsync(d_soff, soff.data(), (size_t)nmol * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-         a.soff = d_soff;
-         a.vecg = ctx->alloc<double>(3 * ntot);
-         a.lamg = ctx->alloc<double>(nmol);
-         a.ntot = (int64_t)ntot;
          // (measured on the 100k-molecule mix: 1 / 2 / 4 / 8 / 16 chunks -> 24.16 / 24.12 / 24.10 / 24.20 / 24.37 ms per step:
          //  every launch has a tail, and kernels of neighbouring chunks overlap only in those tails)
          const int maxchunk = (int)std::max<long long>(1, env_ll("MCHRG_B200_CHUNKS", 4));
-         const int nchunk = (int)std::min<int64_t>(maxchunk, std::max<int64_t>(1, nmol / 4096));
-         std::vector<int32_t> all_perm;
-         std::vector<std::vector<size_t>> starts(nchunk);
-         std::vector<std::vector<int>> counts(nchunk);
-         std::vector<size_t> chunk_off(nchunk + 1, 0);
-         for (int c = 0; c < nchunk; ++c) {
-            const int32_t m0 = (int32_t)((int64_t)nmol * c / nchunk), m1 = (int32_t)((int64_t)nmol * (c + 1) / nchunk);
-            batch::bucket(hoff, m0, m1, perm, starts[c], counts[c]);
-            for (auto& v : perm) v += m0;  // global molecule ids
-            chunk_off[c] = all_perm.size();
-            all_perm.insert(all_perm.end(), perm.begin(), perm.end());
+         // The size classes, the class-sorted permutation and the scratch layout depend on `offsets` alone: a caller that
+         // steps the same batch again (geometry updates of a fixed set of molecules) reuses them -- the plan is kept on
+         // the context and rebuilt when the offsets differ.
+         auto* plan = static_cast<batch::SplitPlan*>(ctx->batch_plan.get());
+         if (!plan || plan->maxchunk != maxchunk || plan->hoff != hoff) {
+            auto fresh = std::make_shared<batch::SplitPlan>();
+            plan = fresh.get();
+            plan->hoff = hoff;
+            plan->maxchunk = maxchunk;
+            std::vector<int64_t> soff;
+            plan->nscr = batch::plan_scratch(hoff, 0, nmol, soff);
+            plan->nchunk = (int)std::min<int64_t>(maxchunk, std::max<int64_t>(1, nmol / 4096));
+            std::vector<int32_t> all_perm;
+            plan->starts.resize(plan->nchunk);
+            plan->counts.resize(plan->nchunk);
+            plan->chunk_off.assign(plan->nchunk + 1, 0);
+            for (int c = 0; c < plan->nchunk; ++c) {
+               const int32_t m0 = (int32_t)((int64_t)nmol * c / plan->nchunk), m1 = (int32_t)((int64_t)nmol * (c + 1) / plan->nchunk);
+               batch::bucket(hoff, m0, m1, perm, plan->starts[c], plan->counts[c]);
+               for (auto& v : perm) v += m0;  // global molecule ids
+               plan->chunk_off[c] = all_perm.size();
+               all_perm.insert(all_perm.end(), perm.begin(), perm.end());
+            }
+            plan->chunk_off[plan->nchunk] = all_perm.size();
+            MCHRG_CUDA(cudaMalloc(&plan->d_soff, (size_t)nmol * sizeof(int64_t)));
+            MCHRG_CUDA(cudaMalloc(&plan->dperm, std::max<size_t>(1, all_perm.size()) * sizeof(int32_t)));
+            MCHRG_CUDA(cudaMemcpy(plan->d_soff, soff.data(), (size_t)nmol * sizeof(int64_t), cudaMemcpyHostToDevice));
+            MCHRG_CUDA(cudaMemcpy(plan->dperm, all_perm.data(), all_perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            ctx->batch_plan = fresh;
          }
-         chunk_off[nchunk] = all_perm.size();
-         int32_t* dperm = ctx->alloc<int32_t>(nmol);
-         MCHRG_CUDA(cudaMemcpyAsync(dperm, all_perm.data(), all_perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+         const int nchunk = plan->nchunk;
+         const auto& starts = plan->starts;
+         const auto& counts = plan->counts;
+         const auto& chunk_off = plan->chunk_off;
+         const int32_t* dperm = plan->dperm;
+         a.scratch = ctx->alloc<double>((size_t)plan->nscr);
+         a.soff = plan->d_soff;
+         a.vecg = ctx->alloc<double>(3 * ntot);
+         a.lamg = ctx->alloc<double>(nmol);
+         a.ntot = (int64_t)ntot;
          cudaEvent_t staged = ctx->next_event();
          MCHRG_CUDA(cudaEventRecord(staged, ctx->stream));
          if (env_ll("MCHRG_B200_TRACE", 0) > 0) {  // phases of the whole batch one after the other, each timed on its own

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <cstdlib>
 #include <string>
@@ -93,6 +94,8 @@ struct mchrg_b200_context {
    }
    std::mutex mu;
    uint64_t launches = 0;
+   // size classes / permutation / scratch layout of the last large device-resident batch (batch.cu, SplitPlan)
+   std::shared_ptr<void> batch_plan;
    // MCHRG_B200_TRACE=1: serial per-phase times of the last split-path batch (pair A, factorisation, pair C)
    double trace_ms[3] = {0.0, 0.0, 0.0};
    int trace_launches[3] = {0, 0, 0};

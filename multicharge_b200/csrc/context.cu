@@ -181,6 +181,7 @@ void mchrg_b200_context_destroy(mchrg_b200_context* ctx) {
          cudaStreamDestroy(st);
       }
    }
+   ctx->batch_plan.reset();
    for (auto e : ctx->events) cudaEventDestroy(e);
    if (ctx->erf_tab) cudaFree(ctx->erf_tab);
    for (auto& s : ctx->slabs) cudaFree(s.base);

@@ -204,6 +204,33 @@ def test_batch_split_path_equals_fused(mc, oracle, monkeypatch):
     assert np.abs(split["gradient"][sl] - r.gradient).max() < 1e-10
 
 
+def test_batch_plan_is_reused_and_rebuilt(mc, monkeypatch):
+    """The split path keeps what it derives from the offsets (size classes, permutation, scratch layout) on the context:
+    the same offsets with new coordinates reuse it, other offsets -- same number of molecules and atoms included --
+    rebuild it."""
+    from synth import batch
+    model = mc.new_eeq2019_batch_model()
+    offs_a, num_a, xyz_a, chg_a = batch(300, 5, nmin=3, nmax=120)
+    sizes = np.diff(offs_a)[::-1].copy()  # the same sizes in reverse order: same nmol, same ntot, other offsets
+    offs_b = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    rng = np.random.default_rng(9)
+    num_b = num_a[rng.permutation(len(num_a))].copy()
+    xyz_b = np.concatenate([xyz_a[offs_a[m]:offs_a[m + 1]] for m in range(299, -1, -1)]) + 0.01
+    chg_b = chg_a[::-1].copy()
+    xyz_a2 = xyz_a * 1.01
+    monkeypatch.setenv("MCHRG_B200_BATCH_MODE", "fused")
+    ref = [mc.singlepoint_batch(model, o, n, x, c) for o, n, x, c in
+           ((offs_a, num_a, xyz_a, chg_a), (offs_a, num_a, xyz_a2, chg_a), (offs_b, num_b, xyz_b, chg_b), (offs_a, num_a, xyz_a, chg_a))]
+    monkeypatch.setenv("MCHRG_B200_BATCH_MODE", "split")
+    got = [mc.singlepoint_batch(model, o, n, x, c) for o, n, x, c in
+           ((offs_a, num_a, xyz_a, chg_a), (offs_a, num_a, xyz_a2, chg_a), (offs_b, num_b, xyz_b, chg_b), (offs_a, num_a, xyz_a, chg_a))]
+    for r, g in zip(ref, got):
+        assert np.array_equal(r["status"], g["status"])
+        ok = np.repeat(r["status"] == 0, np.diff(offs_a) if g is not got[2] else np.diff(offs_b))
+        for key in ("qvec", "energy", "gradient"):
+            assert np.abs(r[key][ok] - g[key][ok]).max() < 1e-11, key
+
+
 def test_batch_full_size_properties(mc):
     """BASELINE.json configs[1] at its full size (100 000 molecules of 30-200 atoms, the bench workload), checked
     through size-independent properties: charge conservation per molecule, vanishing net force (translational
