@@ -231,6 +231,22 @@ def test_batch_plan_is_reused_and_rebuilt(mc, monkeypatch):
             assert np.abs(r[key][ok] - g[key][ok]).max() < 1e-11, key
 
 
+def test_batch_tma_fed_factorisation_variant(mc, monkeypatch):
+    """MCHRG_B200_FACTOR=tma: the factorisation kernel whose operands are streamed into shared-memory rings with
+    cp.async.bulk + mbarriers (measured slower than the default, kept as the documented alternative) gives the same
+    results as the default kernel, every size class included."""
+    from synth import batch
+    model = mc.new_eeq2019_batch_model()
+    offsets, num, xyz, charge = batch(400, 77, nmin=1, nmax=208)
+    monkeypatch.setenv("MCHRG_B200_BATCH_MODE", "split")
+    ref = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    monkeypatch.setenv("MCHRG_B200_FACTOR", "tma")
+    got = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    assert np.array_equal(ref["status"], got["status"]) and int((ref["status"] != 0).sum()) == 0
+    for key in ("qvec", "energy", "gradient"):
+        assert np.abs(ref[key] - got[key]).max() < 1e-11, key
+
+
 def test_batch_full_size_properties(mc):
     """BASELINE.json configs[1] at its full size (100 000 molecules of 30-200 atoms, the bench workload), checked
     through size-independent properties: charge conservation per molecule, vanishing net force (translational
