@@ -231,6 +231,24 @@ def test_batch_plan_is_reused_and_rebuilt(mc, monkeypatch):
             assert np.abs(r[key][ok] - g[key][ok]).max() < 1e-11, key
 
 
+@pytest.mark.parametrize("group", ["13", "4", "1"])
+def test_batch_factor_launch_groups(mc, monkeypatch, group):
+    """MCHRG_B200_FACTOR_GROUP: size classes per factorisation launch.  The shared memory of a launch is sized for its
+    largest class, and the backward substitution stages its operands in whatever the molecule leaves free of it (or
+    falls back to direct loads when two stages do not fit): every grouping gives the same results."""
+    from synth import batch
+    model = mc.new_eeq2019_batch_model()
+    offsets, num, xyz, charge = batch(500, 78, nmin=1, nmax=208)
+    monkeypatch.setenv("MCHRG_B200_BATCH_MODE", "fused")
+    ref = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    monkeypatch.setenv("MCHRG_B200_BATCH_MODE", "split")
+    monkeypatch.setenv("MCHRG_B200_FACTOR_GROUP", group)
+    got = mc.singlepoint_batch(model, offsets, num, xyz, charge)
+    assert np.array_equal(ref["status"], got["status"]) and int((ref["status"] != 0).sum()) == 0
+    for key in ("qvec", "energy", "gradient"):
+        assert np.abs(ref[key] - got[key]).max() < 1e-11, key
+
+
 def test_batch_tma_fed_factorisation_variant(mc, monkeypatch):
     """MCHRG_B200_FACTOR=tma: the factorisation kernel whose operands are streamed into shared-memory rings with
     cp.async.bulk + mbarriers (measured slower than the default, kept as the documented alternative) gives the same
