@@ -57,92 +57,140 @@ __device__ __forceinline__ double count_range2(const NcDev& p, double rc, double
    eg::load_table(setab, etab_global, (int)threadIdx.x, (int)blockDim.x);            \
    __syncthreads()
 
+constexpr int CN_TJ = 256;  // atoms j per shared-memory tile of the row kernels
 __global__ void __launch_bounds__(256) cn_rows_kernel(int nat, const double* __restrict__ xyz,
                                                       const double* __restrict__ rcov, const double* __restrict__ en,
                                                       NcDev p, int ntr, const double* __restrict__ trans,
                                                       double* __restrict__ cn_raw, const double2* __restrict__ etab,
                                                       int row0, int row1) {
    MCHRG_LOAD_ERF_TABLE(etab);
+   __shared__ double sj[5][CN_TJ];  // x, y, z, rcov, en of the tile's atoms: the CTA's eight rows share the loads
    const int i = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    const int lane = threadIdx.x & 31;
-   if (i >= row1) return;
-   const double xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2];
-   const double rci = rcov[i];
-   const double eni = p.use_en ? en[i] : 0.0;
+   const bool on = i < row1;
+   const int ic = on ? i : row1 - 1;
+   const double xi = xyz[3 * ic], yi = xyz[3 * ic + 1], zi = xyz[3 * ic + 2];
+   const double rci = rcov[ic];
+   const double eni = p.use_en ? en[ic] : 0.0;
    double acc = 0.0;
-   for (int j = lane; j < nat; j += 32) {
-      const double rc = rci + rcov[j];
-      const double rcn = (p.norm_exp == 1.0) ? rc : pow(rc, p.norm_exp);
-      const double den = p.use_en ? (en[j] - eni) : 1.0;
-      const double dx = xi - xyz[3 * j], dy = yi - xyz[3 * j + 1], dz = zi - xyz[3 * j + 2];
-      const double cut2 = count_range2(p, rc, rcn);
-      for (int itr = 0; itr < ntr; ++itr) {
-         const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
-         const double r2 = rx * rx + ry * ry + rz * rz;
-         if (r2 > cut2 || r2 < 1.0e-12) continue;
-         const double r1 = r2 * eg::fast_rsqrt(r2);
-         const double a = p.kcn * (r1 - rc) / rcn;
-         double g;
-         acc += den * (0.5 - copysign(0.5, a) * eg::erf_gauss<6, false>(setab, fabs(a), g));  // 1/2 (1 + erf(-a))
+   for (int j0 = 0; j0 < nat; j0 += CN_TJ) {
+      __syncthreads();
+      {
+         const int t = threadIdx.x, j = min(j0 + t, nat - 1);
+         sj[0][t] = xyz[3 * j]; sj[1][t] = xyz[3 * j + 1]; sj[2][t] = xyz[3 * j + 2];
+         sj[3][t] = rcov[j];
+         sj[4][t] = p.use_en ? en[j] : 0.0;
+      }
+      __syncthreads();
+      if (!on) continue;
+      const int tn = min(CN_TJ, nat - j0);
+      for (int t = lane; t < tn; t += 32) {
+         const double rc = rci + sj[3][t];
+         const double rcn = (p.norm_exp == 1.0) ? rc : pow(rc, p.norm_exp);
+         const double den = p.use_en ? (sj[4][t] - eni) : 1.0;
+         const double dx = xi - sj[0][t], dy = yi - sj[1][t], dz = zi - sj[2][t];
+         const double cut2 = count_range2(p, rc, rcn);
+         for (int itr = 0; itr < ntr; ++itr) {
+            const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
+            const double r2 = rx * rx + ry * ry + rz * rz;
+            if (r2 > cut2 || r2 < 1.0e-12) continue;
+            const double r1 = r2 * eg::fast_rsqrt(r2);
+            const double a = p.kcn * (r1 - rc) / rcn;
+            double g;
+            acc += den * (0.5 - copysign(0.5, a) * eg::erf_gauss<6, false>(setab, fabs(a), g));  // 1/2 (1 + erf(-a))
+         }
       }
    }
+   if (!on) return;
    acc = warp_sum(acc);
    if (lane == 0) cn_raw[i] = acc;
 }
 
+// dcndr(:, j, i) for all j and dcndL(:, :, i): one warp per atom i, the CTA's eight rows walk the atoms j together in
+// tiles of 128 staged in shared memory (coalesced loads instead of eight strided passes over xyz), and every warp hands
+// its 32 x 3 results through a shared-memory slab so that the (3, N, N) array -- 6.4 GB at N = 16384, the reason this
+// kernel exists -- is written with fully coalesced 256-byte stores (three strided 8-byte stores per lane before:
+// 0.9 TB/s).
+constexpr int CND_TJ = 128;
 __global__ void __launch_bounds__(256) cn_derivs_kernel(int nat, const double* __restrict__ xyz,
                                                         const double* __restrict__ rcov, const double* __restrict__ en,
                                                         NcDev p, int ntr, const double* __restrict__ trans,
                                                         const double* __restrict__ cn_raw, double* __restrict__ dcndr,
                                                         double* __restrict__ dcndL, const double2* __restrict__ etab) {
    MCHRG_LOAD_ERF_TABLE(etab);
-   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-   const int lane = threadIdx.x & 31;
-   if (i >= nat) return;
-   const double xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2];
-   const double rci = rcov[i];
-   const double eni = p.use_en ? en[i] : 0.0;
+   __shared__ double sj[5][CND_TJ];  // x, y, z, rcov, en of the tile's atoms
+   __shared__ double wbuf[8][96];   // per warp: 32 atoms x 3 components on their way out
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const int i = blockIdx.x * 8 + warp;
+   const bool on = i < nat;
+   const int ic = on ? i : nat - 1;
+   const double xi = xyz[3 * ic], yi = xyz[3 * ic + 1], zi = xyz[3 * ic + 2];
+   const double rci = rcov[ic];
+   const double eni = p.use_en ? en[ic] : 0.0;
    double fcut = 1.0;
    if (p.cut > 0.0) {
       const double ecut = exp(p.cut);
-      fcut = ecut / (ecut + exp(cn_raw[i]));
+      fcut = ecut / (ecut + exp(cn_raw[ic]));
    }
    double dg[3] = {0.0, 0.0, 0.0};
    double dl[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-   double* row = dcndr + (size_t)3 * nat * i;  // dcndr(:, :, i)
-   for (int j = lane; j < nat; j += 32) {
-      const double rc = rci + rcov[j];
-      const double rcn = (p.norm_exp == 1.0) ? rc : pow(rc, p.norm_exp);
-      const double den = p.use_en ? (en[j] - eni) : 1.0;
-      const double dx = xi - xyz[3 * j], dy = yi - xyz[3 * j + 1], dz = zi - xyz[3 * j + 2];
-      double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-      const double cut2 = count_range2(p, rc, rcn);
-      for (int itr = 0; itr < ntr; ++itr) {
-         const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
-         const double r2 = rx * rx + ry * ry + rz * rz;
-         if (r2 > cut2 || r2 < 1.0e-12) continue;
-         const double rinv = eg::fast_rsqrt(r2);
-         const double arg = p.kcn * (r2 * rinv - rc) / rcn;
-         double g;
-         eg::erf_gauss<6, true>(setab, fabs(arg), g);  // g = exp(-arg^2)
-         const double dc = den * (-p.kcn / SQRTPI / rcn * g) * rinv;
-         const double c0 = dc * rx, c1 = dc * ry, c2 = dc * rz;  // countd
-         g0 += c0; g1 += c1; g2 += c2;
-         dl[0] += c0 * rx; dl[1] += c0 * ry; dl[2] += c0 * rz;
-         dl[3] += c1 * rx; dl[4] += c1 * ry; dl[5] += c1 * rz;
-         dl[6] += c2 * rx; dl[7] += c2 * ry; dl[8] += c2 * rz;
+   double* row = dcndr + (size_t)3 * nat * ic;  // dcndr(:, :, i)
+   for (int j0 = 0; j0 < nat; j0 += CND_TJ) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < CND_TJ; t += blockDim.x) {
+         const int j = min(j0 + t, nat - 1);
+         sj[0][t] = xyz[3 * j]; sj[1][t] = xyz[3 * j + 1]; sj[2][t] = xyz[3 * j + 2];
+         sj[3][t] = rcov[j];
+         sj[4][t] = p.use_en ? en[j] : 0.0;
       }
-      if (j != i) {  // d cn_i / d r_j = -countd ; self images cancel in dcndr
-         row[3 * j] = -g0 * fcut;
-         row[3 * j + 1] = -g1 * fcut;
-         row[3 * j + 2] = -g2 * fcut;
-         dg[0] += g0; dg[1] += g1; dg[2] += g2;
+      __syncthreads();
+      if (!on) continue;
+      for (int t0 = 0; t0 < CND_TJ && j0 + t0 < nat; t0 += 32) {
+         const int t = t0 + lane, j = j0 + t;
+         double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+         if (j < nat) {
+            const double rc = rci + sj[3][t];
+            const double rcn = (p.norm_exp == 1.0) ? rc : pow(rc, p.norm_exp);
+            const double den = p.use_en ? (sj[4][t] - eni) : 1.0;
+            const double dx = xi - sj[0][t], dy = yi - sj[1][t], dz = zi - sj[2][t];
+            const double cut2 = count_range2(p, rc, rcn);
+            for (int itr = 0; itr < ntr; ++itr) {
+               const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
+               const double r2 = rx * rx + ry * ry + rz * rz;
+               if (r2 > cut2 || r2 < 1.0e-12) continue;
+               const double rinv = eg::fast_rsqrt(r2);
+               const double arg = p.kcn * (r2 * rinv - rc) / rcn;
+               double g;
+               eg::erf_gauss<6, true>(setab, fabs(arg), g);  // g = exp(-arg^2)
+               const double dc = den * (-p.kcn / SQRTPI / rcn * g) * rinv;
+               const double c0 = dc * rx, c1 = dc * ry, c2 = dc * rz;  // countd
+               g0 += c0; g1 += c1; g2 += c2;
+               dl[0] += c0 * rx; dl[1] += c0 * ry; dl[2] += c0 * rz;
+               dl[3] += c1 * rx; dl[4] += c1 * ry; dl[5] += c1 * rz;
+               dl[6] += c2 * rx; dl[7] += c2 * ry; dl[8] += c2 * rz;
+            }
+            if (j == i) g0 = g1 = g2 = 0.0;  // self images cancel in dcndr; the diagonal entry is written at the end
+            dg[0] += g0; dg[1] += g1; dg[2] += g2;
+         }
+         // d cn_i / d r_j = -countd
+         __syncwarp();
+         wbuf[warp][3 * lane] = -g0 * fcut;
+         wbuf[warp][3 * lane + 1] = -g1 * fcut;
+         wbuf[warp][3 * lane + 2] = -g2 * fcut;
+         __syncwarp();
+         const size_t base = (size_t)3 * (j0 + t0);
+         const int nval = 3 * min(32, nat - (j0 + t0));
+#pragma unroll
+         for (int c = 0; c < 3; ++c)
+            if (lane + 32 * c < nval) row[base + lane + 32 * c] = wbuf[warp][lane + 32 * c];
       }
    }
+   if (!on) return;
 #pragma unroll
    for (int c = 0; c < 3; ++c) dg[c] = warp_sum(dg[c]);
 #pragma unroll
    for (int c = 0; c < 9; ++c) dl[c] = warp_sum(dl[c]);
+   __syncwarp();
    if (lane == 0) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) row[3 * i + c] = dg[c] * fcut;
@@ -214,19 +262,32 @@ __global__ void __launch_bounds__(256) cn_grad_rows_kernel(int nat, const double
                                                            const double2* __restrict__ etab, int row0, int row1) {
    MCHRG_LOAD_ERF_TABLE(etab);
    __shared__ double sred[8][9];
+   __shared__ double sk[5][CN_TJ];  // x, y, z, rcov, wf of the tile's atoms k (shared by the CTA's eight rows)
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const int j = row0 + blockIdx.x * 8 + warp;
+   const bool on = j < row1;
+   const int jc = on ? j : row1 - 1;
    double gs[3] = {0.0, 0.0, 0.0};
    double dl[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-   if (j < row1) {
-      const double xj = xyz[3 * j], yj = xyz[3 * j + 1], zj = xyz[3 * j + 2];
-      const double rcj = rcov[j], wj = wf[j];
-      for (int k = lane; k < nat; k += 32) {
-         const double rc = rcj + rcov[k];
+   const double xj = xyz[3 * jc], yj = xyz[3 * jc + 1], zj = xyz[3 * jc + 2];
+   const double rcj = rcov[jc], wj = wf[jc];
+   for (int k0 = 0; k0 < nat; k0 += CN_TJ) {
+      __syncthreads();
+      {
+         const int t = threadIdx.x, k = min(k0 + t, nat - 1);
+         sk[0][t] = xyz[3 * k]; sk[1][t] = xyz[3 * k + 1]; sk[2][t] = xyz[3 * k + 2];
+         sk[3][t] = rcov[k];
+         sk[4][t] = wf[k];
+      }
+      __syncthreads();
+      if (!on) continue;
+      const int tn = min(CN_TJ, nat - k0);
+      for (int t = lane; t < tn; t += 32) {
+         const int k = k0 + t;
+         const double rc = rcj + sk[3][t];
          const double rcn = (p.norm_exp == 1.0) ? rc : pow(rc, p.norm_exp);
-         const double dx = xj - xyz[3 * k], dy = yj - xyz[3 * k + 1], dz = zj - xyz[3 * k + 2];
-         const double wjk = (k != j) ? wj + wf[k] : 0.0;  // self images cancel in dcndr
-         const double pre = -p.kcn / SQRTPI / rcn;
+         const double dx = xj - sk[0][t], dy = yj - sk[1][t], dz = zj - sk[2][t];
+         const double wjk = (k != j) ? wj + sk[4][t] : 0.0;  // self images cancel in dcndr
          const double cut2 = count_range2(p, rc, rcn);
          for (int itr = 0; itr < ntr; ++itr) {
             const double rx = dx - trans[3 * itr], ry = dy - trans[3 * itr + 1], rz = dz - trans[3 * itr + 2];
@@ -236,7 +297,7 @@ __global__ void __launch_bounds__(256) cn_grad_rows_kernel(int nat, const double
             const double arg = p.kcn * (r2 * rinv - rc) / rcn;
             double g;
             eg::erf_gauss<6, true>(setab, fabs(arg), g);  // g = exp(-arg^2)
-            const double dc = pre * g * rinv;
+            const double dc = -p.kcn / SQRTPI / rcn * g * rinv;  // (the division only for pairs in range)
             const double c0 = dc * rx, c1 = dc * ry, c2 = dc * rz;  // countd
             gs[0] = fma(wjk, c0, gs[0]); gs[1] = fma(wjk, c1, gs[1]); gs[2] = fma(wjk, c2, gs[2]);
             dl[0] += c0 * rx; dl[1] += c0 * ry; dl[2] += c0 * rz;
@@ -244,6 +305,8 @@ __global__ void __launch_bounds__(256) cn_grad_rows_kernel(int nat, const double
             dl[6] += c2 * rx; dl[7] += c2 * ry; dl[8] += c2 * rz;
          }
       }
+   }
+   if (on) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) gs[c] = warp_sum(gs[c]);
 #pragma unroll

@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(256) bc_rows_kernel(int nat, int64_t npad, con
                                                       const double* __restrict__ rvdw, int nid, double kbc,
                                                       const double* __restrict__ Cm, const double* __restrict__ q,
                                                       const double* __restrict__ dcndr,
+                                                      const double* __restrict__ ddiag,
                                                       const double* __restrict__ dcndL, double* __restrict__ rows,
                                                       const double2* __restrict__ etab, int row0, int row1) {
    __shared__ double2 setab[eg::NTAB];
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) bc_rows_kernel(int nat, int64_t npad, con
                                rvdw_pair(rvdw, nid, id, a, b), kbc);
       const double cab = Cm[b + (int64_t)a * npad], qb = q[b], xb = atoms[5 * b + 3];
       // dgam_ab(:, b) = -(rad_a drad_a dcndr(:, b, a) + rad_b drad_b dcndr(:, b, b)) gamma^3
-      const double* dbb = dcndr + ((size_t)nat * b + b) * 3;
+      const double* dbb = ddiag + 3 * b;  // dcndr(:, b, b), gathered once (in place it is one 32-byte sector per lane, N^2 times)
       const double wa = rada * drada, wb = radb * dradb;
       const double g0 = -(wa * dcn_a[3 * b] + wb * dbb[0]) * p.gam3;
       const double g1 = -(wa * dcn_a[3 * b + 1] + wb * dbb[1]) * p.gam3;
@@ -459,12 +460,21 @@ void bc_jq_rows(mchrg_b200_context* ctx, const DevMol& mol, const BcWork& w, con
                 ctx->erf_tab, row0, row1);
 }
 
+__global__ void bc_diag3_kernel(int nat, const double* __restrict__ d, double* __restrict__ out) {
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= 3 * nat) return;
+   const int b = t / 3, c = t - 3 * b;
+   out[t] = d[((size_t)nat * b + b) * 3 + c];
+}
+
 void bc_rows(mchrg_b200_context* ctx, const DevMol& mol, const mchrg_b200_model* model, const BcWork& w,
              const double* q, const double* dcndr, const double* dcndL, double* rows, int row0, int row1) {
    if (row1 < 0) { row0 = 0; row1 = mol.nat; }
    if (row1 <= row0) return;
+   double* ddiag = ctx->alloc<double>((size_t)3 * mol.nat);
+   MCHRG_LAUNCH(ctx, bc_diag3_kernel, (unsigned)((3 * mol.nat + 255) / 256), 256, 0, mol.nat, dcndr, ddiag);
    MCHRG_LAUNCH(ctx, bc_rows_kernel, (unsigned)((row1 - row0 + 7) / 8), 256, 0, mol.nat, w.npad, mol.xyz, mol.id, w.atoms,
-                model->dev_rvdw(), model->nid, model->kbc, w.Cm, q, dcndr, dcndL, rows, ctx->erf_tab, row0, row1);
+                model->dev_rvdw(), model->nid, model->kbc, w.Cm, q, dcndr, ddiag, dcndL, rows, ctx->erf_tab, row0, row1);
 }
 
 void bc_strain(mchrg_b200_context* ctx, const DevMol& mol, const BcAtoms& at, const BcWork& w, const double* q,
