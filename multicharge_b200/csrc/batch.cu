@@ -2021,9 +2021,9 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
       // Host buffers: pipeline chunks of molecules so that the H2D copy of chunk c+1 and the D2H copy of
       // chunk c-1 overlap the kernels of chunk c (asynchronous when the caller's buffers are pinned).
       const int host_chunks = (int)std::max<long long>(0, env_ll("MCHRG_B200_HOST_CHUNKS", 0));
-      // ~256k atoms per chunk (measured on the 100k-molecule bench: 5 / 12 / 24 / 48 chunks give 3.57 / 3.80 /
-      // 3.92 / 3.94 M molecules/s end to end: only the first H2D and the last D2H chunk stay exposed)
-      const int nchunk = host_chunks ? host_chunks : (int)std::min<size_t>(32, std::max<size_t>(2, ntot >> 18));
+      // ~256k atoms per chunk (measured on the 100k-molecule bench: 8 / 16 / 24 / 32 / 48 chunks give 3.94 / 4.08 / 4.14 /
+      // 4.16 / 4.18 M molecules/s end to end: only the first H2D and the last D2H chunk stay exposed)
+      const int nchunk = host_chunks ? host_chunks : (int)std::min<size_t>(48, std::max<size_t>(2, ntot >> 18));
       std::vector<int32_t> bounds(nchunk + 1, 0);
       for (int c = 1; c < nchunk; ++c) {  // split by atoms
          const int64_t target = (int64_t)(ntot * (size_t)c / nchunk);
