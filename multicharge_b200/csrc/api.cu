@@ -763,11 +763,23 @@ static int solve_eeqbc_device(const mchrg_b200_model* model, const DevMol& mol, 
             bz = ctx->alloc_zero<double>((size_t)mp);
             bc_dxdr_gemm(ctx, mol, at, w, io.dcndr, io.dqlocdr, -1.0, Bm, mp, jb, je);  // Bm = -dtmpdr C, rows of the block
          }
-         double* ga = grad ? ctx->alloc_zero<double>((size_t)3 * nj) : nullptr;
-         double* gx = grad ? ctx->alloc_zero<double>((size_t)3 * nj) : nullptr;
-         bc_build_b(ctx, mol, model, at, w, q, cq, rows, io.dcndr, io.dqlocdr, 1.0, 1.0, true, Bm, mp, ga, gx, f.z(npad), bz, jb,
-                    je);
-         if (grad) MCHRG_LAUNCH(ctx, bc_gradient_kernel, (3 * nj + 255) / 256, 256, 0, 3 * nj, ga, gx, io.gradient);
+         // several GPUs, gradient of ALL atoms wanted on every rank (no dq/dr): the pair pass behind the gradient rows
+         // is shared like the other row passes, one all-reduce of the 3 N values joins it
+         const bool gshard = shard && grad && !cpq && nj == nat;
+         const int gb = gshard ? row0 : jb, ge = gshard ? row1 : je, ng = ge - gb;
+         double* ga = (grad && ng > 0) ? ctx->alloc_zero<double>((size_t)3 * ng) : nullptr;
+         double* gx = (grad && ng > 0) ? ctx->alloc_zero<double>((size_t)3 * ng) : nullptr;
+         if (ng > 0)
+            bc_build_b(ctx, mol, model, at, w, q, cq, rows, io.dcndr, io.dqlocdr, 1.0, 1.0, true, Bm, mp, ga, gx, f.z(npad), bz,
+                       gb, ge);
+         if (gshard) {
+            double* gall = ctx->alloc_zero<double>((size_t)3 * nat);
+            if (ng > 0) MCHRG_LAUNCH(ctx, bc_gradient_kernel, (3 * ng + 255) / 256, 256, 0, 3 * ng, ga, gx, gall + 3 * (size_t)gb);
+            comm_allreduce_sum(ctx, gall, (size_t)3 * nat);
+            MCHRG_CUDA(cudaMemcpyAsync(io.gradient, gall, (size_t)3 * nat * sizeof(double), cudaMemcpyDeviceToDevice, ctx->active));
+         } else if (grad) {
+            MCHRG_LAUNCH(ctx, bc_gradient_kernel, (3 * nj + 255) / 256, 256, 0, 3 * nj, ga, gx, io.gradient);
+         }
          MCHRG_LAUNCH(ctx, bc_sigma_kernel, 1, 288, 0, nat, q, dadL, dxdL, grad ? io.sigma : nullptr, f.z(npad), Bm, mp, bz,
                       3 * (int64_t)nj);
          if (cpq) dq_tail(ctx, nat, nj, npad, mp, f, Bm, bz, io.dqdr, io.dqdL);

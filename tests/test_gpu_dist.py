@@ -164,6 +164,51 @@ def test_sharded_singlepoint_vs_oracle(mc, oracle, group, dist_env, nat):
     assert np.abs(dqdr - o["dqdr"]).max() < 1e-10 * max(1.0, np.abs(o["dqdr"]).max())
 
 
+def test_sharded_eeqbc_singlepoint_vs_oracle(mc, oracle, group, dist_env):
+    """EEQ-BC (configs[4] path) shared by several ranks: distributed factorisation, row-sharded pair passes joined by one
+    all-reduce, the gradient's pair pass shared as well (every rank ends with the whole gradient), dq/dr by row blocks;
+    against the one-context result and the oracle."""
+    from synth import cluster
+    from multicharge_b200.shard import row_bounds
+    world = len(group)
+    nat = 700
+    num, xyz = cluster(nat, 790)
+    mol = mc.Structure(num, xyz, 1.0)
+    omol = oracle.Mol(num, xyz, 1.0)
+    om = oracle.new_eeqbc2025_model(omol)
+
+    def make(ctx):
+        return mc.new_eeqbc_model(mol, chi=om.chi, rad=om.rad, eta=om.eta, kcnchi=om.kcnchi, kqchi=om.kqchi, kqeta=om.kqeta,
+                                  kcnrad=om.kcnrad, cap=om.cap, avg_cn=om.avg_cn, rvdw=om.rvdw, rcov=om.rcov, en=om.en,
+                                  kbc=om.kbc, cutoff=om.cutoff, cn_exp=om.kcn, norm_exp=om.norm_exp, ctx=ctx)
+
+    single = make(None).singlepoint(mol, want=("qvec", "energy", "gradient"))
+    bounds = row_bounds(nat, world, multiple=8)
+    assert np.all(np.diff(bounds) > 0)
+
+    def body(r):
+        model = make(group[r])
+        a = mc.singlepoint_rows(model, mol, 0, nat, dqdr=False)
+        b = mc.singlepoint_rows(model, mol, int(bounds[r]), int(bounds[r + 1]))
+        return a, b
+
+    res = run_ranks(world, body)
+    o = oracle.eeqbc_singlepoint(om, omol, want=("qvec", "energy", "gradient", "dqdr"))
+    grad = np.zeros((nat, 3))
+    dqdr = np.zeros((nat, nat, 3))
+    for r, (a, b) in enumerate(res):
+        for key in ("qvec", "energy", "gradient", "sigma"):
+            scale = max(1.0, np.abs(o[key]).max())
+            assert np.abs(a[key] - o[key]).max() < 1e-10 * scale, (r, key)
+            assert np.abs(a[key] - single[key]).max() < 1e-11 * scale, (r, key)
+        jb, je = int(bounds[r]), int(bounds[r + 1])
+        grad[jb:je] = b["gradient"]
+        dqdr[:, jb:je, :] = b["dqdr"]
+        assert np.abs(b["dqdL"] - o["dqdL"]).max() < 1e-10 * max(1.0, np.abs(o["dqdL"]).max())
+    assert np.abs(grad - o["gradient"]).max() < 1e-10 * max(1.0, np.abs(o["gradient"]).max())
+    assert np.abs(dqdr - o["dqdr"]).max() < 1e-10 * max(1.0, np.abs(o["dqdr"]).max())
+
+
 def test_sharded_periodic_singlepoint_vs_oracle(mc, oracle, group, monkeypatch):
     """Periodic EEQ2019 (configs[3] path) shared by several ranks: Ewald pair tiles and rows of Phi W Phi^T per rank, ONE
     all-reduce of the matrix, pair tiles of the derivatives per rank joined with the CN-gradient rows; q, E, gradient,
