@@ -105,3 +105,49 @@ def block_cyclic_cholesky_host(w, n, group, sub, rank, world, bcast):
                 j0, jend = j * group, min(n, (j + 1) * group)
                 a[j0:, j0:jend] -= a[j0:, g0:gend] @ a[j0:jend, g0:gend].T
     return nbcast
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Periodic structures on several ranks (pbc_amat / pbc_derivs in csrc/eeq_pbc.cu): what each rank evaluates
+# ---------------------------------------------------------------------------------------------------------------
+def pair_tiles(nat, tile=32):
+    """The 32 x 32 atom tiles of the lower block triangle in the order of the device kernels (tile_coords in
+    csrc/eeq_pbc.cu): index b = ti (ti + 1) / 2 + tj, tj <= ti."""
+    nt = (nat + tile - 1) // tile
+    return [(ti, tj) for ti in range(nt) for tj in range(ti + 1)]
+
+
+def tile_share(ntiles, rank, world):
+    """Tiles of one rank: round robin (tile0 = rank, stride = world), as launched by pbc_amat / pbc_derivs."""
+    return range(rank, ntiles, world)
+
+
+def rowblock_share(nblocks, rank, world):
+    """128-row blocks of the reciprocal-space product Phi W Phi^T computed by one rank."""
+    return range(nblocks * rank // world, nblocks * (rank + 1) // world)
+
+
+def periodic_matrix_shared_host(nat, pair, recip, diag, rank, world, allreduce, tile=32, rowblock=128):
+    """numpy mirror of the shared assembly of pbc_amat: this rank's pair tiles (both triangles), its row blocks of the
+    reciprocal-space matrix and its share of the diagonal into a zero matrix, joined by ONE all-reduce.
+    pair(i, j) -> direct part of A(i, j), i > j; recip -> full (nat, nat) reciprocal matrix (only this rank's row
+    blocks are read); diag(i) -> self term; allreduce(array) sums in place over the ranks."""
+    a = np.zeros((nat, nat))
+    tiles = pair_tiles(nat, tile)
+    for b in tile_share(len(tiles), rank, world):
+        ti, tj = tiles[b]
+        for i in range(ti * tile, min(nat, (ti + 1) * tile)):
+            for j in range(tj * tile, min(nat, (tj + 1) * tile)):
+                if j < i:
+                    v = pair(i, j)
+                    a[i, j] += v
+                    a[j, i] += v
+    nblk = (nat + rowblock - 1) // rowblock
+    for rb in rowblock_share(nblk, rank, world):
+        lo, hi = rb * rowblock, min(nat, (rb + 1) * rowblock)
+        a[lo:hi, :] += recip[lo:hi, :]
+    r = row_bounds(nat, world, multiple=8)
+    for i in range(int(r[rank]), int(r[rank + 1])):
+        a[i, i] += diag(i)
+    allreduce(a)
+    return a
