@@ -111,3 +111,48 @@ def test_eeqbc_2048_vs_oracle(mc, oracle):
     o = oracle.eeqbc_singlepoint(omodel, omol, want=("qvec", "energy", "gradient", "dqdr"))
     for key in ("qvec", "energy", "gradient", "sigma", "dqdr", "dqdL"):
         assert close(r[key], o[key]), (key, np.abs(r[key] - o[key]).max())
+
+
+def test_eeqbc_2048_two_ranks_vs_oracle(mc, oracle, monkeypatch):
+    """The same N = 2048 EEQ-BC system shared by two ranks (two contexts of one GPU, in-process communicator): distributed
+    factorisation, row-sharded pair passes, shared gradient pass, dq/dr rows of each rank -- against the oracle."""
+    from synth import cluster
+    from multicharge_b200.shard import row_bounds
+    monkeypatch.setenv("MCHRG_B200_DIST_MIN", "1024")
+    num, xyz = cluster(2048, 2048)
+    omol = oracle.Mol(num, xyz, 0.0)
+    om = oracle.new_eeqbc2025_model(omol)
+    mol = mc.Structure(num, xyz, 0.0)
+    ctxs = [mc.Context(0), mc.Context(0)]
+    mc.Context.comm_init_local(ctxs)
+    bounds = row_bounds(2048, 2)
+    out, err = [None, None], [None, None]
+
+    def body(r):
+        try:
+            model = mc.new_eeqbc_model(mol, chi=om.chi, rad=om.rad, eta=om.eta, kcnchi=om.kcnchi, kqchi=om.kqchi,
+                                       kqeta=om.kqeta, kcnrad=om.kcnrad, cap=om.cap, avg_cn=om.avg_cn, rvdw=om.rvdw,
+                                       rcov=om.rcov, en=om.en, kbc=om.kbc, cutoff=om.cutoff, cn_exp=om.kcn,
+                                       norm_exp=om.norm_exp, ctx=ctxs[r])
+            a = mc.singlepoint_rows(model, mol, 0, 2048, dqdr=False)
+            b = mc.singlepoint_rows(model, mol, int(bounds[r]), int(bounds[r + 1]))
+            out[r] = (a, b)
+        except BaseException as exc:  # noqa: BLE001
+            err[r] = exc
+
+    th = [threading.Thread(target=body, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=600) for t in th]
+    for c in ctxs:
+        c.comm_destroy()
+        c.close()
+    assert err == [None, None], err
+    o = oracle.eeqbc_singlepoint(om, omol, want=("qvec", "energy", "gradient", "dqdr"))
+    dqdr = np.zeros_like(o["dqdr"])
+    for r, (a, b) in enumerate(out):
+        for key in ("qvec", "energy", "gradient", "sigma"):
+            assert close(a[key], o[key]), (r, key, np.abs(a[key] - o[key]).max())
+        jb, je = int(bounds[r]), int(bounds[r + 1])
+        dqdr[:, jb:je, :] = b["dqdr"]
+        assert close(b["gradient"], o["gradient"][jb:je]) and close(b["dqdL"], o["dqdL"])
+    assert close(dqdr, o["dqdr"])
