@@ -1924,7 +1924,10 @@ extern "C" int mchrg_b200_singlepoint_batch(const mchrg_b200_model* model, int32
             plan->maxchunk = maxchunk;
             std::vector<int64_t> soff;
             plan->nscr = batch::plan_scratch(hoff, 0, nmol, soff);
-            plan->nchunk = (int)std::min<int64_t>(maxchunk, std::max<int64_t>(1, nmol / 4096));
+            // (at least 4096 molecules per chunk by default; an explicit MCHRG_B200_CHUNKS may go down to 256 per chunk --
+            //  the L2-residency experiment: ~500 molecules are 30 MB of scratch)
+            const int64_t per_chunk = std::getenv("MCHRG_B200_CHUNKS") ? 256 : 4096;
+            plan->nchunk = (int)std::min<int64_t>(maxchunk, std::max<int64_t>(1, nmol / per_chunk));
             std::vector<int32_t> all_perm;
             plan->starts.resize(plan->nchunk);
             plan->counts.resize(plan->nchunk);
