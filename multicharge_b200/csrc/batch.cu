@@ -13,6 +13,10 @@
 //                                            (L2 resident), forward/backward substitution, Schur complement
 //                  eeq_batch_kernel<256, 3>  pair phase C: energy, gradient
 //                  The scratch matrices are stored in FP64-mma fragment order (lay()).
+//                  What depends on the molecule offsets alone (size classes, launch order, scratch layout) is kept
+//                  on the context (SplitPlan) while a caller steps the same set of molecules.
+//                  eeq_factor_tma_kernel is the measured-slower alternative of the middle kernel
+//                  (MCHRG_B200_FACTOR=tma), kept under test.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
